@@ -1,0 +1,262 @@
+/*
+ * tpgx.h — C ABI of libtpgx.so, the B200-native evaluator for Tangled Program Graph policies.
+ *
+ * This is the drop-in boundary for GEGELATI's policy-evaluation hot path
+ * (Learn::LearningAgent::evaluateAllRoots / ParallelLearningAgent).  Every entry
+ * point names the reference interface it replaces.  "[UP]" = upstream GEGELATI library (not vendored
+ * in /root/reference; behaviour restated from its published v1.x/v2.0.0 sources), "[REF]" = a file in
+ * gegelati-apps.
+ *
+ * Conventions
+ *   - plain C types only; every function returns a tpgx_status (0 = OK, negative = error);
+ *     no C++ exception ever crosses this boundary (the reference throws std::runtime_error,
+ *     e.g. [REF] pendulum/src/Learn/pendulum.cpp:66-68; the C++ adapter re-throws).
+ *   - the caller owns every host buffer it passes in; inputs are copied before the call returns,
+ *     outputs are written into caller-allocated buffers whose sizes follow from the request.
+ *   - the library owns all device memory, streams and events; freed by tpgx_destroy.
+ *   - a tpgx_ctx is used by one caller thread at a time (like one Learn::LearningAgent).
+ *   - there is NO CPU fallback: without a CUDA device tpgx_create fails with TPGX_ERR_CUDA.
+ */
+#ifndef TPGX_H
+#define TPGX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TPGX_ABI_VERSION 1
+
+typedef int32_t tpgx_status;
+enum {
+    TPGX_OK = 0,
+    TPGX_ERR_BAD_ARG = -1,
+    TPGX_ERR_UNSUPPORTED = -2,   /* instruction / layout the device path does not implement (no fallback) */
+    TPGX_ERR_GRAPH_INVALID = -3, /* e.g. a team with no admissible out-edge ([UP] evaluateTeam throws)   */
+    TPGX_ERR_CUDA = -4,
+    TPGX_ERR_NCCL = -5,
+    TPGX_ERR_OOM = -6,
+    TPGX_ERR_STATE = -7          /* call order (graph / observations not set yet)                        */
+};
+
+/* ---- device opcode table ------------------------------------------------------------------------
+ * One entry per distinct behaviour of the 5 apps' Instructions::Set lambdas:
+ * [REF] mnist/src/main.cpp:47-88, pendulum/src/Learn/instructions.cpp:7-32,
+ * gridworld/src/instructions.cpp:7-27, stickgame/src/Learn/instructions.cpp:9-23,
+ * tic-tac-toe/src/Learn/main.cpp:15-34.  Operand types are implied by the opcode:
+ * D = double, I = int, C = Data::Constant, W = const double[3][3] window.                          */
+typedef enum {
+    TPGX_OP_SUB = 0,        /* (D,D)  a - b                                   */
+    TPGX_OP_ADD = 1,        /* (D,D)  a + b                                   */
+    TPGX_OP_MUL = 2,        /* (D,D)  a * b                                   */
+    TPGX_OP_DIV = 3,        /* (D,D)  a / b   (no zero guard)                 */
+    TPGX_OP_MAX = 4,        /* (D,D)  std::max(a,b) == (a < b) ? b : a        */
+    TPGX_OP_EXP = 5,        /* (D)    exp(a)                                  */
+    TPGX_OP_LOG = 6,        /* (D)    log(a)                                  */
+    TPGX_OP_COS = 7,        /* (D)    cos(a)                                  */
+    TPGX_OP_SIN = 8,        /* (D)    sin(a)                                  */
+    TPGX_OP_TAN = 9,        /* (D)    tan(a)                                  */
+    TPGX_OP_PI = 10,        /* (D)    M_PI  (operand fetched, ignored)        */
+    TPGX_OP_MULC = 11,      /* (D,C)  a * (double)c / 10.0                    */
+    TPGX_OP_FMODG = 12,     /* (D,D)  b != 0.0 ? fmod(a,b) : DBL_MIN          */
+    TPGX_OP_SUB_II = 13,    /* (I,I)  (double)a - (double)b                   */
+    TPGX_OP_CAST_I = 14,    /* (I)    (double)a                               */
+    TPGX_OP_EQ0 = 15,       /* (D)    a == 0.0  ? 10.0 : 0.0                  */
+    TPGX_OP_EQM1 = 16,      /* (D)    a == -1.0 ? 10.0 : 0.0                  */
+    TPGX_OP_EQ1 = 17,       /* (D)    a == 1.0  ? 10.0 : 0.0                  */
+    TPGX_OP_GE15 = 18,      /* (D)    a >= 15.0 ? 10.0 : 0.0                  */
+    TPGX_OP_COND = 19,      /* (D,D)  a < b ? -a : a                          */
+    TPGX_OP_SOBEL_MAGN = 20,/* (W)    sqrt(gx*gx + gy*gy)                     */
+    TPGX_OP_SOBEL_DIR = 21, /* (W)    atan(gy / gx)                           */
+    TPGX_OP_COUNT = 22
+} tpgx_opcode;
+
+/* Tie-break of [UP] TPG::TPGExecutionEngine::evaluateTeam.           */
+enum { TPGX_TIE_LAST_MAX = 0 /* `bid >= best` */, TPGX_TIE_FIRST_MAX = 1 /* `bid > best` */ };
+
+/* Element type of a data source as the *programs* see it ([UP] Data::PrimitiveTypeArray<T>,
+ * Data::Array2DWrapper<T>).                                                                        */
+enum { TPGX_ELEM_F64 = 0, TPGX_ELEM_I32 = 1 };
+/* Storage type of an uploaded observation batch. U8 is exact for MNIST (pixels are the integers
+ * 0..255 stored as double: [REF] mnist/src/mnist.h:16).                                            */
+enum { TPGX_STORE_U8 = 0, TPGX_STORE_F64 = 1, TPGX_STORE_I32 = 2 };
+
+typedef struct {
+    int32_t elem;   /* TPGX_ELEM_*                                                     */
+    int32_t height; /* 1 for a 1-D PrimitiveTypeArray, h for Array2DWrapper(h, w)      */
+    int32_t width;  /* number of elements (1-D) or w                                    */
+    int32_t is_2d;  /* 0: PrimitiveTypeArray<T>(width); 1: Array2DWrapper<T>(h, w)      */
+} tpgx_source_desc;
+
+typedef struct {
+    int32_t device;       /* CUDA device ordinal                                                    */
+    int32_t nb_registers; /* params.json nbRegisters (<= 8 on the device path)                      */
+    int32_t nb_constants; /* params.json nbProgramConstant (0 => no constant source in the index map) */
+    int32_t tie_break;    /* TPGX_TIE_*                                                             */
+    int32_t reserved[4];
+} tpgx_config;
+
+/* One program line in the reference's own encoding ([UP] Program::Line; dot format SURVEY.md C.1):
+ * instruction index into the Instructions::Set, destination register, two (source index, location)
+ * pairs.  Source 0 = registers, 1 = constants iff nb_constants > 0, then the environment's data
+ * sources in getDataSources() order.  Locations are un-reduced; the library takes them modulo the
+ * address space of (source, operand type), as [UP] ProgramExecutionEngine::fetchCurrentOperands. */
+typedef struct {
+    uint32_t instruction;
+    uint32_t destination;
+    uint32_t src[2];
+    uint32_t loc[2];
+} tpgx_line;
+
+/* The TPG, flattened by the caller in the reference's iteration order (edge order within a team =
+ * the library's std::list order — it decides ties).                                               */
+typedef struct {
+    int32_t nb_programs;
+    const int64_t* program_line_offset; /* [nb_programs + 1] into lines                              */
+    const tpgx_line* lines;
+    const uint8_t* intron;              /* optional, per line: 1 = intron ([UP] Program::identifyIntrons);
+                                           NULL => the library recomputes them                       */
+    const double* constants;            /* [nb_programs][nb_constants] (may be NULL if nb_constants==0) */
+    int32_t nb_teams;
+    const int32_t* team_edge_offset;    /* [nb_teams + 1] CSR                                        */
+    const int32_t* edge_program;        /* [nb_edges] program id                                     */
+    const int32_t* edge_destination;    /* [nb_edges] >= 0: team id;  < 0: action id = -1 - value    */
+    int32_t nb_roots;
+    const int32_t* root_team;           /* [nb_roots] team ids, in job-index order                   */
+} tpgx_graph;
+
+/* Work counters, in the reference's own units (what [UP] evaluateAllRoots would have executed).    */
+typedef struct {
+    uint64_t evaluations;        /* executeFromRoot + doAction pairs                                */
+    uint64_t team_visits;        /* evaluateTeam calls                                              */
+    uint64_t program_executions; /* evaluateEdge calls (admissible edges only)                      */
+    uint64_t lines_executed;     /* non-intron lines run by those executions                        */
+    uint64_t device_lines;       /* lines the GPU actually interpreted (dense program x sample)     */
+    uint64_t device_program_executions;
+} tpgx_counters;
+
+typedef struct tpgx_ctx tpgx_ctx;
+
+/* Replaces: construction of Learn::LearningAgent / Environment
+ * ([REF] mnist/src/main.cpp:106-107, pendulum/src/Learn/main.cpp:38-39).                           */
+tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out);
+tpgx_status tpgx_destroy(tpgx_ctx* ctx);
+/* Valid until the next call on ctx. ctx == NULL returns the last tpgx_create failure text.         */
+const char* tpgx_last_error(const tpgx_ctx* ctx);
+int32_t tpgx_abi_version(void);
+
+/* Replaces: Instructions::Set + LambdaInstruction<...> registration
+ * ([REF] mnist/src/main.cpp:79-88).  opcode[i] = device behaviour of instruction index i.           */
+tpgx_status tpgx_set_instruction_table(tpgx_ctx* ctx, int32_t n, const int32_t* opcode);
+
+/* Replaces: LearningEnvironment::getDataSources() ([REF] mnist/src/mnist.cpp:71-76,
+ * stickgame/src/Learn/stickGameAdversarial.cpp:118-125).                                           */
+tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_desc* src);
+
+/* Replaces: the TPG::TPGGraph held by the agent (la.getTPGGraph(), [REF] mnist/src/main.cpp:110)
+ * as seen by [UP] TPGExecutionEngine / ProgramExecutionEngine.  Flattens programs (introns
+ * stripped, locations reduced) to packed device bytecode and uploads it with the CSR graph.        */
+tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g);
+
+/* Replaces: the static dataset of [REF] mnist/src/mnist.cpp:6 / the Array2DWrapper pointer swap
+ * of MNIST::changeCurrentImage (:8-34).  `data` is sample-major [count][height*width] of `store`
+ * type, `labels` [count] class ids (may be NULL for bid-only use).  Copies host -> device and
+ * re-tiles on the device.                                                                          */
+tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data,
+                                  const uint8_t* labels, int64_t count);
+/* Same, but `data` / `labels` are DEVICE pointers already resident in HBM (no host copy).          */
+tpgx_status tpgx_set_observations_device(tpgx_ctx* ctx, int32_t source, int32_t store,
+                                         const void* d_data, const uint8_t* d_labels, int64_t count);
+
+/* Classification evaluation request: one generation of evaluateAllRoots for a
+ * ClassificationLearningEnvironment ([UP] ClassificationLearningAgent::evaluateJob; [REF]
+ * mnist/src/mnist.cpp:50-69).  Every root in [root_begin, root_end) classifies the same sample
+ * list (the reference seeds every root's episode identically: SURVEY.md §3.3).                     */
+typedef struct {
+    int64_t nb_samples;          /* number of doAction calls per root (MNIST: maxNbActionsPerEval)   */
+    const int32_t* sample_index; /* [nb_samples] indices into the uploaded observations; NULL = 0..n-1 */
+    int32_t nb_classes;          /* = nb actions for a classification LE (10)                        */
+    int32_t root_begin;          /* shard of the root list evaluated by this context                 */
+    int32_t root_end;
+    int32_t reserved;
+} tpgx_classif_request;
+
+typedef struct {                 /* every pointer optional (NULL = not wanted); sizes for nR = root_end-root_begin */
+    double* score;               /* [nR]            mean of per-class F1 (ClassificationEvaluationResult) */
+    double* class_f1;            /* [nR][C]                                                          */
+    uint64_t* confusion;         /* [nR][C][C]      table[true class][action]                        */
+    uint8_t* action;             /* [nR][nb_samples]                                                 */
+    double* bid;                 /* [nb_programs][nb_samples]  NaN already mapped to -inf            */
+    tpgx_counters* counters;
+    float* device_ms;            /* [3] K1 bid interpreter, K2 traversal, K3 score reduce (CUDA events) */
+} tpgx_classif_result;
+
+/* Replaces: Learn::LearningAgent::evaluateAllRoots(gen, mode) for classification environments
+ * ([REF] direct call tic-tac-toe/src/Learn/main.cpp:82-83; via trainOneGeneration
+ * mnist/src/main.cpp:145).                                                                         */
+tpgx_status tpgx_evaluate_classification(tpgx_ctx* ctx, const tpgx_classif_request* req,
+                                         tpgx_classif_result* out);
+/* Device-resident variant for callers that keep results on the GPU (multi-GPU allgather):
+ * d_records receives nR records of (1 + nb_classes) doubles {score, f1[0..C)} on `stream`
+ * (a cudaStream_t passed as void*); no host synchronisation is performed.                          */
+tpgx_status tpgx_evaluate_classification_device(tpgx_ctx* ctx, const tpgx_classif_request* req,
+                                                double* d_records, void* stream);
+
+/* ---- episodic environments ----------------------------------------------------------------------
+ * Batched lock-step restatements of the apps' LearningEnvironment::{reset,doAction,isTerminal,
+ * getScore(s)}.                                                             */
+typedef enum {
+    TPGX_ENV_GRIDWORLD = 0, /* [REF] gridworld/src/gridworld.cpp:3-83                               */
+    TPGX_ENV_STICKGAME = 1, /* [REF] stickgame/src/Learn/stickGameAdversarial.cpp:38-171            */
+    TPGX_ENV_TICTACTOE = 2, /* [REF] tic-tac-toe/src/Learn/TicTacToe.cpp:33-204                     */
+    TPGX_ENV_PENDULUM = 3   /* [REF] pendulum/src/Learn/pendulum.cpp:42-141                         */
+} tpgx_env_kind;
+
+typedef struct {
+    int32_t env;                 /* tpgx_env_kind                                                    */
+    int32_t mode;                /* Learn::LearningMode: 0 TRAINING, 1 VALIDATION, 2 TESTING         */
+    int32_t nb_iterations;       /* nbIterationsPerPolicyEvaluation (or nbIterationsPerJob)          */
+    int32_t max_actions;         /* maxNbActionsPerEval                                              */
+    const uint64_t* seeds;       /* [nb_iterations] value the agent passes to le.reset(seed, mode):
+                                    Hash(gen) ^ Hash(it) ([UP] LearningAgent::evaluateJob)           */
+    int32_t nb_jobs;
+    int32_t roots_per_job;       /* 1; 2 for AdversarialLearningAgent jobs (tic-tac-toe)             */
+    const int32_t* job_roots;    /* [nb_jobs][roots_per_job] indices into graph root list            */
+    int32_t second_player_random;/* stickgame / tic-tac-toe constructor flag                         */
+    int32_t nb_pendulum_actions; /* pendulum: size of availableActions (7)                           */
+    const double* pendulum_actions; /* [nb_pendulum_actions] ([REF] pendulum/src/Learn/main.cpp:33)  */
+    int32_t trace_steps;         /* >0: record the first trace_steps actions of every episode        */
+    int32_t reserved;
+} tpgx_episode_request;
+
+typedef struct {                 /* every pointer optional                                            */
+    double* score;               /* [nb_jobs][roots_per_job] mean over iterations (EvaluationResult)  */
+    double* episode_score;       /* [nb_jobs][nb_iterations][roots_per_job]                           */
+    int32_t* episode_actions;    /* [nb_jobs][nb_iterations] number of doAction calls                 */
+    int8_t* trace;               /* [nb_jobs][nb_iterations][trace_steps] action ids, -1 = not reached */
+    double* final_state;         /* [nb_jobs][nb_iterations][4] env-specific observable state         */
+    tpgx_counters* counters;
+    float* device_ms;            /* [1] episode kernel                                                */
+} tpgx_episode_result;
+
+/* Replaces: Learn::LearningAgent::evaluateAllRoots(gen, mode) for sequential environments
+ * ([UP] LearningAgent::evaluateJob / AdversarialLearningAgent::evaluateJob episode loop).          */
+tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req,
+                                   tpgx_episode_result* out);
+
+/* Direct access to single engine steps (used by parity tests; replaces
+ * [UP] ProgramExecutionEngine::executeProgram on an explicit observation batch):
+ * obs_f64 / obs_i32 are [count][address space] per source (NULL if absent); bid is [P][count].     */
+tpgx_status tpgx_execute_programs(tpgx_ctx* ctx, int64_t count, const double* const* obs_f64,
+                                  const int32_t* const* obs_i32, double* bid);
+
+/* FP64 issue-rate microbenchmark used as the roofline denominator (non-FMA DADD/DMUL and DFMA
+ * warp-instructions per second), measured on ctx's device.                                         */
+tpgx_status tpgx_measure_fp64_peak(tpgx_ctx* ctx, double* dadd_per_s, double* dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TPGX_H */
