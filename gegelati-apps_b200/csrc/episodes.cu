@@ -1,0 +1,331 @@
+/*
+ * episodes.cu — batched lock-step restatements of the apps' sequential LearningEnvironments and
+ * the episode loop of [UP] LearningAgent::evaluateJob / AdversarialLearningAgent::evaluateJob.
+ *
+ * thread = one episode (job, iteration).  Per step the thread walks the job's TPG from the acting
+ * root ([UP] executeFromRoot / evaluateTeam) running each admissible edge's program on the
+ * episode's own observation with the per-thread executor (dev_ops.cuh), then applies the
+ * environment's doAction.  Lanes of a warp are consecutive iterations of the same job, so they
+ * share programs until their paths diverge.  A second kernel averages the iteration scores in
+ * iteration order (the reference's sequential `result += getScore()`).
+ *
+ * Environment semantics, line by line: SURVEY.md Appendix B;
+ *   gridworld  [REF] gridworld/src/gridworld.cpp:3-83
+ *   stickgame  [REF] stickgame/src/Learn/stickGameAdversarial.cpp:38-171
+ *   tictactoe  [REF] tic-tac-toe/src/Learn/TicTacToe.cpp:33-204
+ *   pendulum   [REF] pendulum/src/Learn/pendulum.cpp:42-141
+ */
+#include <random>
+
+#include "dev_ops.cuh"
+#include "episodes.cuh"
+#include "kernels.cuh"
+
+void tpgx_rng_fill_raw(uint64_t seed, int n, uint64_t* out) {
+    std::mt19937_64 g(seed);
+    for (int i = 0; i < n; i++) out[i] = g();
+}
+
+namespace {
+
+struct ep_counters { unsigned int eval, team, prog, line; };
+
+/* [UP] executeFromRoot on one observation; returns the action id or -1 (error bits in err). */
+__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err) {
+    int visited[TPGX_MAX_PATH];
+    int depth = 0, cur = root;
+    for (;;) {
+        if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; return -1; }
+        visited[depth++] = cur;
+        c.team++;
+        const int eb = __ldg(p.team_edge_offset + cur), ee = __ldg(p.team_edge_offset + cur + 1);
+        bool have = false;
+        int best_dst = 0;
+        double best_bid = 0.0;
+        for (int e = eb; e < ee; e++) {
+            const int dst = __ldg(p.edge_destination + e);
+            if (dst >= 0) {
+                bool seen = false;
+                for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
+                if (seen) continue;
+            }
+            const int prog = __ldg(p.edge_program + e);
+            const int cb = __ldg(p.prog_offset + prog), n = __ldg(p.prog_offset + prog + 1) - cb;
+            double bid = tpgx_run_program(p.code + cb, n, p.constants + (size_t)prog * p.nb_constants, o);
+            if (bid != bid) bid = __longlong_as_double(0xfff0000000000000LL);
+            c.prog++;
+            c.line += (unsigned int)n;
+            const bool take = !have || (p.tie_break == TPGX_TIE_LAST_MAX ? (bid >= best_bid) : (bid > best_bid));
+            if (take) { have = true; best_dst = dst; best_bid = bid; }
+        }
+        if (!have) { err |= TPGX_DEV_NO_EDGE; return -1; }
+        if (best_dst < 0) return -1 - best_dst;
+        cur = best_dst;
+    }
+}
+
+/* ---------------------------------------------------------------- gridworld */
+struct GridWorld {
+    int x, y, terminated;
+    double total, st[2];
+    __device__ static int tile(int yy, int xx) {
+        const int g[3][4] = {{0, 0, 0, 2}, {0, 0, 3, 3}, {0, 0, 0, 1}};
+        return g[yy][xx];
+    }
+    __device__ static bool available(int px, int py) {
+        if (px == 4 || px == -1) return false;
+        if (py == 3 || py == -1) return false;
+        return tile(py, px) != 3;
+    }
+    __device__ void reset(const tpgx_episode_params&, tpgx_rng_cursor&) { x = 0; y = 0; terminated = 0; total = 0.0; st[0] = 0.0; st[1] = 0.0; }
+    __device__ void view(tpgx_obs_view& o) const { o.f64[0] = st; o.f64[1] = nullptr; o.i32[0] = nullptr; o.i32[1] = nullptr; o.width[0] = 2; o.width[1] = 0; }
+    __device__ bool do_action(const tpgx_episode_params&, int a, tpgx_rng_cursor&) {
+        switch (a) {
+        case 0: if (available(x - 1, y)) x--; break;
+        case 1: if (available(x, y + 1)) y++; break;
+        case 2: if (available(x + 1, y)) x++; break;
+        case 3: if (available(x, y - 1)) y--; break;
+        }
+        double reward = -1;
+        if (tile(y, x) == 1) { terminated = 1; reward = 100; }
+        else if (tile(y, x) == 2) { terminated = 1; reward = -100; }
+        total += reward;
+        st[0] = x; st[1] = y;
+        return true;
+    }
+    __device__ bool is_terminal() const { return terminated != 0; }
+    __device__ double score(int) const { return total; }
+    __device__ void summary(double* o) const { o[0] = st[0]; o[1] = st[1]; o[2] = total; o[3] = terminated ? 1.0 : 0.0; }
+};
+
+/* ---------------------------------------------------------------- stick game */
+struct StickGame {
+    int32_t sticks[1], hints[4];
+    int first_won, forb1, forb2, turn, second_random;
+    __device__ void reset(const tpgx_episode_params& p, tpgx_rng_cursor&) {
+        hints[0] = 1; hints[1] = 2; hints[2] = 3; hints[3] = 4;
+        sticks[0] = 21; first_won = 0; forb1 = 0; forb2 = 0; turn = 0; second_random = p.second_player_random;
+    }
+    __device__ void view(tpgx_obs_view& o) const { o.i32[0] = hints; o.i32[1] = sticks; o.f64[0] = nullptr; o.f64[1] = nullptr; o.width[0] = 4; o.width[1] = 1; }
+    __device__ bool is_terminal() const { return sticks[0] == 0; }
+    __device__ void random_play(tpgx_rng_cursor& rng) {
+        if (!is_terminal()) {
+            int s = sticks[0];
+            /* short-circuit order matters: the second draw only happens in the else branch */
+            if (tpgx_rng_u64(rng, 0, 3) != 0 && (s - 1) % 4 != 0) s -= (s - 1) % 4;
+            else s -= (int)tpgx_rng_u64(rng, 1, (uint64_t)min(s, 3));
+            sticks[0] = s;
+            if (s == 0) first_won = ((!turn) % 2 == 0);
+            turn++;
+        }
+    }
+    __device__ bool do_action(const tpgx_episode_params&, int a, tpgx_rng_cursor& rng) {
+        if (!is_terminal()) {
+            const bool first = turn % 2 == 0;
+            int s = sticks[0];
+            if (((double)a + 1) > s) {
+                if (first) forb1 = 1; else forb2 = 1;
+                sticks[0] = 0;
+                first_won = !first;
+                return true;
+            }
+            s -= (a + 1);
+            sticks[0] = s;
+            if (s == 0) first_won = !first;
+            turn++;
+            if (second_random) random_play(rng);
+        }
+        return true;
+    }
+    __device__ double score(int player) const {
+        double s1, s2;
+        if (first_won) { s1 = 1.0; s2 = forb2 ? -1.0 : 0.0; }
+        else { s2 = 1.0; s1 = forb1 ? -1.0 : 0.0; }
+        return player == 0 ? s1 : s2;
+    }
+    __device__ void summary(double* o) const { o[0] = sticks[0]; o[1] = turn; o[2] = first_won ? 1.0 : 0.0; o[3] = (forb1 ? 1.0 : 0.0) + (forb2 ? 2.0 : 0.0); }
+};
+
+/* ---------------------------------------------------------------- tic-tac-toe */
+struct TicTacToe {
+    double board[9];
+    int turn, win1, win2, forb1, forb2, null_game, end, second_random;
+    __device__ void reset(const tpgx_episode_params& p, tpgx_rng_cursor&) {
+        for (int i = 0; i < 9; i++) board[i] = -1.0;
+        turn = 0; win1 = win2 = forb1 = forb2 = null_game = end = 0; second_random = p.second_player_random;
+    }
+    __device__ void view(tpgx_obs_view& o) const { o.f64[0] = board; o.f64[1] = nullptr; o.i32[0] = nullptr; o.i32[1] = nullptr; o.width[0] = 9; o.width[1] = 0; }
+    __device__ bool is_terminal() const { return end != 0; }
+    __device__ void random_play(double sym, tpgx_rng_cursor& rng) {
+        const int remaining = 9 - turn;
+        int decision = (int)tpgx_rng_u64(rng, 0, (uint64_t)(remaining - 1));
+        int i = -1;
+        while (decision >= 0 && i < 8) { i++; if (board[i] == -1) decision--; }
+        board[i] = sym;
+    }
+    __device__ void update_game() {
+        const bool odd = turn % 2 != 0;
+        const double x00 = board[0], x10 = board[1], x20 = board[2], x01 = board[3], x11 = board[4], x21 = board[5],
+                     x02 = board[6], x12 = board[7], x22 = board[8];
+        bool won = false;
+        if (x11 != -1 && ((x01 == x11 && x11 == x21) || (x10 == x11 && x11 == x12) || (x00 == x11 && x11 == x22) || (x20 == x11 && x11 == x02))) won = true;
+        else if (x22 != -1.0 && ((x02 == x12 && x12 == x22) || (x20 == x21 && x21 == x22))) won = true;
+        else if (x00 != -1.0 && ((x00 == x10 && x10 == x20) || (x00 == x01 && x01 == x02))) won = true;
+        if (won) { end = 1; if (odd) win1 = 1; else win2 = 1; return; }
+        if (turn > 8) { null_game = 1; end = 1; }
+    }
+    __device__ bool do_action(const tpgx_episode_params&, int a, tpgx_rng_cursor& rng) {
+        const bool even = turn % 2 == 0;
+        if (!is_terminal()) {
+            const double cell = board[a];
+            if (cell != -1.0) { if (even) forb1 = 1; else forb2 = 1; random_play(0, rng); }
+            else board[a] = 0;
+            turn++;
+            update_game();
+            if (is_terminal()) return true;
+            if (second_random) { random_play(1, rng); turn++; update_game(); }
+            else for (int i = 0; i < 9; i++) { const double c = board[i]; board[i] = c == 0 ? 1 : c == 1 ? 0 : -1; }
+        }
+        return true;
+    }
+    __device__ double score(int player) const {
+        const double m1 = forb1 ? 1.0 : 0.0, m2 = forb2 ? 1.0 : 0.0;
+        if (null_game) return player == 0 ? 0.5 - m1 : 0.5 - m2;
+        if (win1) return player == 0 ? 1 - m1 : 0 - m2;
+        return player == 0 ? 0 - m1 : 1 - m2;
+    }
+    __device__ void summary(double* o) const {
+        double code = 0.0, w = 1.0;
+        for (int i = 0; i < 9; i++) { code += (board[i] + 1.0) * w; w *= 3.0; }
+        o[0] = code; o[1] = turn;
+        o[2] = (win1 ? 1 : 0) + (win2 ? 2 : 0) + (forb1 ? 4 : 0) + (forb2 ? 8 : 0) + (null_game ? 16 : 0) + (end ? 32 : 0);
+        o[3] = 0.0;
+    }
+};
+
+/* ---------------------------------------------------------------- pendulum */
+struct Pendulum {
+    double hist[300];
+    double total, st[2];
+    unsigned long long n_act;
+    __device__ void reset(const tpgx_episode_params&, tpgx_rng_cursor& rng) {
+        for (int i = 0; i < 300; i++) hist[i] = 0.0; /* a fresh clone's history ({0.0}); never observable before 300 writes */
+        st[0] = tpgx_rng_f64(rng, -TPGX_PI, TPGX_PI);
+        st[1] = tpgx_rng_f64(rng, -1.0, 1.0);
+        n_act = 0; total = 0.0;
+    }
+    __device__ void view(tpgx_obs_view& o) const { o.f64[0] = st; o.f64[1] = nullptr; o.i32[0] = nullptr; o.i32[1] = nullptr; o.width[0] = 2; o.width[1] = 0; }
+    __device__ bool do_action(const tpgx_episode_params& p, int a, tpgx_rng_cursor&) {
+        const int na = p.nb_pendulum_actions;
+        if (a < 0 || a >= na * 2 + 1) return false;
+        double cur = (a == 0) ? 0.0 : p.pendulum_actions[(a - 1) % na];
+        cur = (a <= na) ? cur : -cur;
+        cur *= 2.0; /* MAX_TORQUE */
+        double angle = st[0], velocity = st[1];
+        const double atu = fmod((angle + TPGX_PI), (2.f * TPGX_PI)) - TPGX_PI;
+        const double reward = -((atu * atu) + 0.2f * (velocity * velocity) + 0.01f * (cur * cur));
+        hist[n_act % 300] = reward;
+        n_act++;
+        total += reward;
+        velocity = velocity + ((-3.0) * 9.81 / (2.0 * 1.0) * (tpgx_math::sin(angle + TPGX_PI)) + (3.f / (1.0 * 1.0 * 1.0)) * cur) * 0.05;
+        velocity = fmin(fmax(velocity, -8.0), 8.0);
+        angle = angle + velocity * 0.05;
+        st[0] = angle; st[1] = velocity;
+        return true;
+    }
+    __device__ bool is_terminal() const {
+        bool r = false;
+        if (n_act >= 300) {
+            double acc = 0.0;
+            for (int i = 0; i < 300; i++) acc += hist[i];
+            acc /= 300.0;
+            r = fabs(acc) < 0.1;
+        }
+        return r;
+    }
+    __device__ double score(int) const {
+        if (is_terminal()) return 10.0 / tpgx_math::log(((double)n_act - 300.0 + 2.0));
+        return total / (double)n_act;
+    }
+    __device__ void summary(double* o) const { o[0] = st[0]; o[1] = st[1]; o[2] = total; o[3] = (double)n_act; }
+};
+
+template <class Env>
+__global__ void __launch_bounds__(64) tpgx_episode_kernel(const tpgx_episode_params p) {
+    const int NI = p.nb_iterations, K = p.roots_per_job;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = (long long)p.nb_jobs * NI;
+    ep_counters c = {0, 0, 0, 0};
+    int err = 0;
+    if (gid < total) {
+        const int j = (int)(gid / NI), it = (int)(gid % NI);
+        tpgx_rng_cursor rng;
+        rng.raw = p.rng_raw + (size_t)it * TPGX_RNG_TABLE;
+        rng.pos = 0;
+        rng.exhausted = 0;
+        Env env;
+        env.reset(p, rng);
+        tpgx_obs_view o;
+        int n = 0, turn = 0;
+        while (!env.is_terminal() && n < p.max_actions) {
+            env.view(o);
+            const int root = __ldg(p.job_teams + (size_t)j * K + turn);
+            const int action = ep_traverse(p, root, o, c, err);
+            c.eval++;
+            if (action < 0) break;
+            if (p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
+            if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; break; }
+            turn = (turn + 1 == K) ? 0 : turn + 1;
+            n++;
+        }
+        for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
+        for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
+        p.episode_actions[gid] = n;
+        env.summary(p.final_state + (size_t)gid * 4);
+        if (rng.exhausted) err |= TPGX_DEV_RNG_EXHAUSTED;
+    }
+    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+        c.eval += __shfl_xor_sync(0xffffffffu, c.eval, o2);
+        c.team += __shfl_xor_sync(0xffffffffu, c.team, o2);
+        c.prog += __shfl_xor_sync(0xffffffffu, c.prog, o2);
+        c.line += __shfl_xor_sync(0xffffffffu, c.line, o2);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(p.counters + 0, (unsigned long long)c.eval);
+        atomicAdd(p.counters + 1, (unsigned long long)c.team);
+        atomicAdd(p.counters + 2, (unsigned long long)c.prog);
+        atomicAdd(p.counters + 3, (unsigned long long)c.line);
+    }
+    if (err) atomicOr(p.status, err);
+}
+
+/* [UP] evaluateJob: result += getScore() over iterations in order, then result / nbIterations */
+__global__ void tpgx_job_score_kernel(const tpgx_episode_params p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int K = p.roots_per_job;
+    if (i >= p.nb_jobs * K) return;
+    const int j = i / K, k = i % K;
+    double result = 0.0;
+    for (int it = 0; it < p.nb_iterations; it++) result += p.episode_score[((size_t)j * p.nb_iterations + it) * K + k];
+    p.job_score[i] = result / (double)p.nb_iterations;
+}
+
+} // namespace
+
+cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) {
+    const long long total = (long long)p.nb_jobs * p.nb_iterations;
+    const int threads = 64;
+    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    switch (p.env) {
+    case TPGX_ENV_GRIDWORLD: tpgx_episode_kernel<GridWorld><<<blocks, threads, 0, st>>>(p); break;
+    case TPGX_ENV_STICKGAME: tpgx_episode_kernel<StickGame><<<blocks, threads, 0, st>>>(p); break;
+    case TPGX_ENV_TICTACTOE: tpgx_episode_kernel<TicTacToe><<<blocks, threads, 0, st>>>(p); break;
+    case TPGX_ENV_PENDULUM: tpgx_episode_kernel<Pendulum><<<blocks, threads, 0, st>>>(p); break;
+    default: return cudaErrorInvalidValue;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const int n = p.nb_jobs * p.roots_per_job;
+    tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}

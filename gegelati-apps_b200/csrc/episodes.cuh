@@ -1,0 +1,38 @@
+/*
+ * episodes.cuh — parameter block of the episodic-environment kernel (kernels for SURVEY.md §8 a8).
+ */
+#ifndef TPGX_EPISODES_CUH
+#define TPGX_EPISODES_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tpgx_internal.h"
+#include "tpgx_rng.h"
+
+struct tpgx_episode_params {
+    int env, mode, nb_iterations, max_actions, nb_jobs, roots_per_job, second_player_random, trace_steps;
+    int tie_break, nb_constants, nb_pendulum_actions;
+    double pendulum_actions[16];
+    const uint64_t* rng_raw;      /* [nb_iterations][TPGX_RNG_TABLE] raw mt19937_64 outputs          */
+    const int32_t* job_teams;     /* [nb_jobs][roots_per_job] root team ids                          */
+    const uint32_t* code;
+    const int32_t* prog_offset;
+    const double* constants;
+    const int32_t* team_edge_offset;
+    const int32_t* edge_program;
+    const int32_t* edge_destination;
+    double* episode_score;        /* [nb_jobs][nb_iterations][roots_per_job]                         */
+    int32_t* episode_actions;     /* [nb_jobs][nb_iterations]                                        */
+    double* final_state;          /* [nb_jobs][nb_iterations][4]                                     */
+    int8_t* trace;                /* [nb_jobs][nb_iterations][trace_steps]                           */
+    double* job_score;            /* [nb_jobs][roots_per_job]                                        */
+    unsigned long long* counters; /* [4]                                                             */
+    int* status;
+};
+
+cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st);
+/* host: raw outputs of std::mt19937_64 seeded with `seed` */
+void tpgx_rng_fill_raw(uint64_t seed, int n, uint64_t* out);
+
+#endif

@@ -1,0 +1,150 @@
+/*
+ * flatten.cpp — host flattener: reference-format programs + TPG -> packed device bytecode + CSR.
+ *
+ * Replaces the per-line work [UP] ProgramExecutionEngine::fetchCurrentOperands does at run time
+ * (type lookup, handler lookup, location % addressSpace) and the intron skipping of
+ * [UP] ProgramExecutionEngine::iterateThroughtProgram by a one-off pass per graph upload:
+ *   - [UP] Program::identifyIntrons (backward liveness from register 0),
+ *   - static reduction of every location,
+ *   - "never written => 0.0" register reads marked so the device needs no register clear.
+ */
+#include <cstdio>
+#include <cstring>
+
+#include "tpgx_internal.h"
+
+namespace {
+
+struct SourceMap {
+    const tpgx_config& cfg;
+    const std::vector<tpgx_source_desc>& src;
+    int first_env() const { return cfg.nb_constants > 0 ? 2 : 1; }
+    int total() const { return first_env() + (int)src.size(); }
+    /* address space of handler `s` for operand type `t`; 0 = the handler cannot provide it
+     * ([UP] DataHandler::getAddressSpace; PrimitiveTypeArray / Array2DWrapper rules) */
+    uint32_t space(int s, int t) const {
+        if (s == 0) return t == TPGX_T_D ? (uint32_t)cfg.nb_registers : 0u;
+        if (cfg.nb_constants > 0 && s == 1) return t == TPGX_T_C ? (uint32_t)cfg.nb_constants : 0u;
+        const int k = s - first_env();
+        if (k < 0 || k >= (int)src.size()) return 0u;
+        const tpgx_source_desc& d = src[k];
+        if (d.elem == TPGX_ELEM_I32) return (t == TPGX_T_I && !d.is_2d) ? (uint32_t)d.width : 0u;
+        if (t == TPGX_T_D) return (uint32_t)(d.height * d.width);
+        if (t == TPGX_T_W && d.is_2d && d.height >= 3 && d.width >= 3) return (uint32_t)((d.height - 2) * (d.width - 2));
+        return 0u;
+    }
+};
+
+std::string fmt(const char* f, long a = 0, long b = 0, long c = 0) {
+    char buf[256];
+    snprintf(buf, sizeof buf, f, a, b, c);
+    return buf;
+}
+
+} // namespace
+
+tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
+                               const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
+                               tpgx_flat_graph* out, std::string* err) {
+    auto fail = [&](tpgx_status st, const std::string& m) { if (err) *err = m; return st; };
+    if (!g || !g->program_line_offset || !g->team_edge_offset || !g->edge_program || !g->edge_destination || !g->root_team)
+        return fail(TPGX_ERR_BAD_ARG, "tpgx_set_graph: null array in graph");
+    if (g->nb_programs < 0 || g->nb_teams < 1 || g->nb_roots < 1) return fail(TPGX_ERR_BAD_ARG, "tpgx_set_graph: empty graph");
+    if (cfg.nb_constants > 0 && !g->constants) return fail(TPGX_ERR_BAD_ARG, "tpgx_set_graph: constants missing");
+    if (src.size() > 2) return fail(TPGX_ERR_UNSUPPORTED, "device bytecode addresses at most 2 data sources");
+    SourceMap sm{cfg, src};
+    const int R = cfg.nb_registers;
+
+    tpgx_flat_graph& f = *out;
+    f = tpgx_flat_graph();
+    f.nb_programs = g->nb_programs;
+    f.prog_offset.reserve(g->nb_programs + 1);
+    f.prog_offset.push_back(0);
+    f.prog_flops.resize(g->nb_programs);
+    if (cfg.nb_constants > 0) f.constants.assign(g->constants, g->constants + (size_t)g->nb_programs * cfg.nb_constants);
+
+    std::vector<uint8_t> keep;
+    for (int p = 0; p < g->nb_programs; p++) {
+        const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
+        if (e < b) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p));
+        const tpgx_line* L = g->lines + b;
+        const int n = (int)(e - b);
+        /* validate + backward liveness */
+        keep.assign(n, 0);
+        bool live[TPGX_MAX_REGS] = {false};
+        live[0] = true;
+        for (int i = n - 1; i >= 0; i--) {
+            const tpgx_line& l = L[i];
+            if (l.instruction >= opcode.size()) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", p, i, l.instruction));
+            if (l.destination >= (uint32_t)R) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: destination register out of range", p, i));
+            const tpgx_op_info oi = tpgx_get_op_info(opcode[l.instruction]);
+            for (int k = 0; k < oi.nb_operands; k++) {
+                if ((int)l.src[k] >= sm.total()) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", p, i, l.src[k]));
+                if (sm.space((int)l.src[k], oi.type[k]) == 0)
+                    return fail(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", p, i, l.src[k]));
+            }
+            if (!live[l.destination]) continue;
+            keep[i] = 1;
+            live[l.destination] = false;
+            for (int k = 0; k < oi.nb_operands; k++)
+                if (l.src[k] == 0) live[l.loc[k] % (uint32_t)R] = true;
+        }
+        if (g->intron) {
+            for (int i = 0; i < n; i++)
+                if ((g->intron[b + i] != 0) == (keep[i] != 0))
+                    return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i));
+        }
+        /* encode effective lines */
+        bool written[TPGX_MAX_REGS] = {false};
+        int flops = 0;
+        for (int i = 0; i < n; i++) {
+            if (!keep[i]) { f.total_introns++; continue; }
+            const tpgx_line& l = L[i];
+            const int op = opcode[l.instruction];
+            const tpgx_op_info oi = tpgx_get_op_info(op);
+            uint32_t kind[2] = {TPGX_KIND_REG, TPGX_KIND_REG}, loc[2] = {TPGX_LOC_ZERO, TPGX_LOC_ZERO};
+            for (int k = 0; k < oi.nb_operands; k++) {
+                const int s = (int)l.src[k];
+                uint32_t a = l.loc[k] % sm.space(s, oi.type[k]);
+                if (s == 0) { kind[k] = TPGX_KIND_REG; loc[k] = written[a] ? a : TPGX_LOC_ZERO; }
+                else if (cfg.nb_constants > 0 && s == 1) { kind[k] = TPGX_KIND_CONST; loc[k] = a; }
+                else {
+                    const int ks = s - sm.first_env();
+                    kind[k] = ks == 0 ? TPGX_KIND_SRC0 : TPGX_KIND_SRC1;
+                    if (oi.type[k] == TPGX_T_W) { /* [UP] Array2DWrapper window address -> top-left element */
+                        const uint32_t ww = (uint32_t)src[ks].width - 2u;
+                        a = (a / ww) * (uint32_t)src[ks].width + (a % ww);
+                    }
+                    if (a >= TPGX_MAX_LOC) return fail(TPGX_ERR_UNSUPPORTED, fmt("program %ld line %ld: location %ld exceeds the 10-bit device field", p, i, a));
+                    loc[k] = a;
+                }
+            }
+            f.code.push_back(tpgx_pack_line((uint32_t)op, l.destination, kind[0], loc[0], kind[1], loc[1]));
+            written[l.destination] = true;
+            flops += oi.flops;
+            f.total_lines++;
+        }
+        f.prog_flops[p] = flops;
+        f.prog_offset.push_back((int32_t)f.code.size());
+    }
+
+    f.nb_teams = g->nb_teams;
+    f.team_edge_offset.assign(g->team_edge_offset, g->team_edge_offset + g->nb_teams + 1);
+    if (f.team_edge_offset[0] != 0) return fail(TPGX_ERR_BAD_ARG, "team_edge_offset[0] != 0");
+    for (int t = 0; t < g->nb_teams; t++) {
+        if (f.team_edge_offset[t + 1] < f.team_edge_offset[t]) return fail(TPGX_ERR_BAD_ARG, "team_edge_offset not monotone");
+        if (f.team_edge_offset[t + 1] == f.team_edge_offset[t]) return fail(TPGX_ERR_GRAPH_INVALID, fmt("team %ld has no outgoing edge", t));
+    }
+    f.nb_edges = f.team_edge_offset[g->nb_teams];
+    f.edge_program.assign(g->edge_program, g->edge_program + f.nb_edges);
+    f.edge_destination.assign(g->edge_destination, g->edge_destination + f.nb_edges);
+    for (int e = 0; e < f.nb_edges; e++) {
+        if (f.edge_program[e] < 0 || f.edge_program[e] >= g->nb_programs) return fail(TPGX_ERR_BAD_ARG, fmt("edge %ld: program out of range", e));
+        if (f.edge_destination[e] >= g->nb_teams) return fail(TPGX_ERR_BAD_ARG, fmt("edge %ld: destination team out of range", e));
+        if (f.edge_destination[e] < -128) return fail(TPGX_ERR_UNSUPPORTED, fmt("edge %ld: action id above 127", e));
+    }
+    f.nb_roots = g->nb_roots;
+    f.root_team.assign(g->root_team, g->root_team + g->nb_roots);
+    for (int r : f.root_team) if (r < 0 || r >= g->nb_teams) return fail(TPGX_ERR_BAD_ARG, "root team out of range");
+    return TPGX_OK;
+}

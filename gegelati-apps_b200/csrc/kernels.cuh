@@ -1,0 +1,69 @@
+/*
+ * kernels.cuh — launch parameter blocks shared between kernels.cu and tpgx_api.cu.
+ */
+#ifndef TPGX_KERNELS_CUH
+#define TPGX_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tpgx_internal.h"
+
+/* K1: bid interpreter over a 2-D uint8 observation source (MNIST shape). */
+struct tpgx_bid_params {
+    const uint8_t* tiles;        /* [tiles][hw][TS] pixel-major sample tiles (first tile of the pass) */
+    int hw, width;               /* elements per observation, row length                              */
+    const uint32_t* code;
+    const int32_t* prog_offset;
+    const double* constants;
+    int nb_constants;
+    const int32_t* active_prog;  /* [nb_active] program id of each bid-matrix row                      */
+    int nb_active;
+    int progs_per_chunk;
+    double* bid;                 /* [nb_active][row_stride]                                            */
+    long long row_stride;        /* samples per row in this pass (multiple of TS)                      */
+};
+
+/* K2: graph traversal per (root, sample) on the bid matrix. */
+struct tpgx_trav_params {
+    const double* bid;
+    long long row_stride;
+    int nb_samples;              /* valid samples in this pass                                          */
+    const int32_t* team_edge_offset;
+    const int32_t* edge_row;     /* bid-matrix row of each edge's program                               */
+    const int32_t* edge_destination;
+    const int32_t* edge_lines;   /* effective line count of each edge's program                         */
+    const int32_t* roots;        /* [nb_roots] root team ids of this shard                              */
+    int nb_roots;
+    const uint8_t* labels;       /* [nb_samples] class of each sample of the pass (may be NULL)         */
+    int nb_classes;
+    uint8_t* action;             /* optional [nb_roots][action_stride], pass offset already applied     */
+    long long action_stride;
+    unsigned long long* confusion; /* [nb_roots][C*C]                                                   */
+    unsigned long long* counters;  /* [4] evaluations, team visits, program executions, lines           */
+    int tie_break;
+    int* status;                 /* OR of TPGX_DEV_* error bits                                         */
+};
+
+#define TPGX_DEV_NO_EDGE 1
+#define TPGX_DEV_PATH_TOO_LONG 2
+#define TPGX_DEV_BAD_ACTION 4
+#define TPGX_DEV_RNG_EXHAUSTED 8
+
+/* Launchers (defined in kernels.cu). variant: 0 = default tile shape. Returns cudaError_t. */
+int tpgx_bid_tile_samples(int variant);
+size_t tpgx_bid_smem_bytes(int variant, int hw);
+cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool trig, cudaStream_t st);
+cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p, cudaStream_t st);
+cudaError_t tpgx_launch_score(const unsigned long long* confusion, int nb_roots, int nb_classes,
+                              double* records, cudaStream_t st);
+cudaError_t tpgx_launch_pack(const uint8_t* obs, const int32_t* sample_index, long long nb_samples,
+                             long long nb_obs, int hw, int ts, uint8_t* tiles, const uint8_t* labels_in,
+                             uint8_t* labels_out, cudaStream_t st);
+cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_offset, const double* constants,
+                                     int nb_constants, int nb_programs, long long count,
+                                     const double* f0, const double* f1, const int32_t* i0, const int32_t* i1,
+                                     int space0, int space1, int width0, int width1, double* bid, cudaStream_t st);
+cudaError_t tpgx_launch_fp64_peak(int mode /*0 dadd+dmul, 1 dfma*/, int blocks, int iters, double* sink, cudaStream_t st);
+
+#endif

@@ -1,0 +1,637 @@
+/*
+ * tpgx_api.cu — the C ABI of libtpgx.so (include/tpgx.h): context, uploads, evaluation drivers.
+ * Host-side orchestration only; all arithmetic on observations happens in the kernels.
+ * There is no CPU fallback: every evaluation entry point launches CUDA kernels or fails.
+ */
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "episodes.cuh"
+#include "kernels.cuh"
+#include "tpgx_internal.h"
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct ShardPlan { /* programs reachable from a root range, cached between evaluations */
+    int root_begin = -1, root_end = -1;
+    uint64_t graph_version = 0;
+    int nb_active = 0;
+    int64_t active_lines = 0, active_flops = 0;
+};
+
+} // namespace
+
+struct tpgx_ctx {
+    tpgx_config cfg{};
+    std::string err;
+    std::vector<int32_t> opcode;
+    std::vector<tpgx_source_desc> src;
+    tpgx_flat_graph flat;
+    bool has_graph = false, uses_trig = false;
+    uint64_t graph_version = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    int variant = 0;
+    size_t bid_budget = (size_t)16 << 30;
+
+    DevBuf d_code, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
+    DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
+    DevBuf d_scratch[8];
+    const uint8_t* obs_dev = nullptr;    /* raw observations [nb_obs][hw] (ours or the caller's) */
+    const uint8_t* labels_dev = nullptr;
+    int64_t nb_obs = 0;
+    int obs_hw = 0, obs_width = 0;
+    bool tiles_identity_valid = false;   /* d_tiles holds the identity packing of all observations */
+    int tiles_ts = 0;
+    ShardPlan plan;
+    std::vector<int32_t> h_edge_row, h_active;
+
+    cudaEvent_t event(size_t i) {
+        while (events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); }
+        return events[i];
+    }
+};
+
+namespace {
+
+tpgx_status fail(tpgx_ctx* c, tpgx_status st, const std::string& m) {
+    if (c) c->err = m; else g_create_error = m;
+    return st;
+}
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess)                                                                          \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? TPGX_ERR_OOM : TPGX_ERR_CUDA,            \
+                        std::string(#call) + ": " + cudaGetErrorString(e__));                            \
+    } while (0)
+
+tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    CU(b.ensure(bytes ? bytes : 16));
+    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TPGX_OK;
+}
+
+/* Programs reachable from roots [rb, re): BFS over teams; rows in order of first appearance. */
+tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re) {
+    ShardPlan& pl = ctx->plan;
+    if (pl.root_begin == rb && pl.root_end == re && pl.graph_version == ctx->graph_version) return TPGX_OK;
+    const tpgx_flat_graph& f = ctx->flat;
+    std::vector<int32_t> row_of(f.nb_programs, -1);
+    std::vector<char> seen(f.nb_teams, 0);
+    std::vector<int32_t> queue;
+    ctx->h_active.clear();
+    ctx->h_edge_row.assign(f.nb_edges, -1);
+    for (int r = rb; r < re; r++) {
+        int t = f.root_team[r];
+        if (!seen[t]) { seen[t] = 1; queue.push_back(t); }
+    }
+    for (size_t q = 0; q < queue.size(); q++) {
+        const int t = queue[q];
+        for (int e = f.team_edge_offset[t]; e < f.team_edge_offset[t + 1]; e++) {
+            const int p = f.edge_program[e];
+            if (row_of[p] < 0) { row_of[p] = (int32_t)ctx->h_active.size(); ctx->h_active.push_back(p); }
+            ctx->h_edge_row[e] = row_of[p];
+            const int d = f.edge_destination[e];
+            if (d >= 0 && !seen[d]) { seen[d] = 1; queue.push_back(d); }
+        }
+    }
+    pl.nb_active = (int)ctx->h_active.size();
+    pl.active_lines = 0;
+    pl.active_flops = 0;
+    for (int p : ctx->h_active) { pl.active_lines += f.prog_offset[p + 1] - f.prog_offset[p]; pl.active_flops += f.prog_flops[p]; }
+    tpgx_status st;
+    if ((st = upload(ctx, ctx->d_active, ctx->h_active.data(), ctx->h_active.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_edge_row, ctx->h_edge_row.data(), ctx->h_edge_row.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_roots, f.root_team.data() + rb, (size_t)(re - rb) * 4)) != TPGX_OK) return st;
+    pl.root_begin = rb; pl.root_end = re; pl.graph_version = ctx->graph_version;
+    return TPGX_OK;
+}
+
+struct ClassifRun {
+    int nR = 0, C = 0, ts = 0;
+    int64_t nS = 0, nTiles = 0;
+    int passes = 0;
+};
+
+/* Enqueues one classification evaluateAllRoots on ctx->stream; no host synchronisation.
+ * records_out: device buffer of nR*(C+1) doubles. */
+tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* req, double* records_out,
+                                   bool want_action, bool keep_bid_single_pass, ClassifRun* run, bool timing) {
+    if (!ctx->has_graph) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_classification: no graph set");
+    if (!ctx->obs_dev) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_classification: no observations set");
+    if (!req || req->nb_samples <= 0) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples must be positive");
+    if (req->nb_classes < 1 || req->nb_classes > 16) return fail(ctx, TPGX_ERR_UNSUPPORTED, "nb_classes must be in [1,16]");
+    if (req->root_begin < 0 || req->root_end > ctx->flat.nb_roots || req->root_begin >= req->root_end)
+        return fail(ctx, TPGX_ERR_BAD_ARG, "root range out of bounds");
+    if (!req->sample_index && req->nb_samples > ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples exceeds uploaded observations");
+    if (!ctx->labels_dev) return fail(ctx, TPGX_ERR_STATE, "classification needs labels");
+    const int nR = req->root_end - req->root_begin, C = req->nb_classes;
+    const int64_t nS = req->nb_samples;
+    const int ts = tpgx_bid_tile_samples(ctx->variant);
+    const int64_t nTiles = (nS + ts - 1) / ts;
+    const int hw = ctx->obs_hw;
+    tpgx_status st = make_plan(ctx, req->root_begin, req->root_end);
+    if (st != TPGX_OK) return st;
+    const int nA = ctx->plan.nb_active;
+
+    /* observation tiles */
+    const bool identity = (req->sample_index == nullptr) && nS == ctx->nb_obs;
+    if (!(identity && ctx->tiles_identity_valid && ctx->tiles_ts == ts)) {
+        const int32_t* d_index = nullptr;
+        if (req->sample_index) {
+            for (int64_t i = 0; i < nS; i++)
+                if (req->sample_index[i] < 0 || req->sample_index[i] >= ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "sample_index out of range");
+            if ((st = upload(ctx, ctx->d_index, req->sample_index, (size_t)nS * 4)) != TPGX_OK) return st;
+            d_index = ctx->d_index.as<int32_t>();
+        }
+        CU(ctx->d_tiles.ensure((size_t)nTiles * hw * ts));
+        CU(ctx->d_labels.ensure((size_t)nTiles * ts));
+        CU(tpgx_launch_pack(ctx->obs_dev, d_index, nS, ctx->nb_obs, hw, ts, ctx->d_tiles.as<uint8_t>(), ctx->labels_dev,
+                            ctx->d_labels.as<uint8_t>(), ctx->stream));
+        ctx->tiles_identity_valid = identity;
+        ctx->tiles_ts = ts;
+    }
+
+    /* pass planning: keep the bid matrix of one pass within the budget */
+    int64_t tiles_per_pass = nTiles;
+    const size_t per_tile = (size_t)std::max(nA, 1) * ts * 8;
+    if (per_tile * (size_t)nTiles > ctx->bid_budget) tiles_per_pass = std::max<int64_t>(1, (int64_t)(ctx->bid_budget / per_tile));
+    if (keep_bid_single_pass && tiles_per_pass < nTiles) return fail(ctx, TPGX_ERR_OOM, "bid output requested but the bid matrix exceeds the budget");
+    const int passes = (int)((nTiles + tiles_per_pass - 1) / tiles_per_pass);
+    CU(ctx->d_bid.ensure(per_tile * (size_t)tiles_per_pass));
+    CU(ctx->d_conf.ensure((size_t)nR * C * C * 8));
+    CU(ctx->d_counters.ensure(8 * 8));
+    CU(ctx->d_status.ensure(16));
+    CU(cudaMemsetAsync(ctx->d_conf.p, 0, (size_t)nR * C * C * 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+    if (want_action) CU(ctx->d_action.ensure((size_t)nR * nS));
+
+    size_t ev = 0;
+    for (int ps = 0; ps < passes; ps++) {
+        const int64_t t0 = (int64_t)ps * tiles_per_pass;
+        const int nt = (int)std::min<int64_t>(tiles_per_pass, nTiles - t0);
+        const int64_t s0 = t0 * ts;
+        const int ns = (int)std::min<int64_t>((int64_t)nt * ts, nS - s0);
+        if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
+        if (nA > 0) {
+            tpgx_bid_params bp{};
+            bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * hw * ts;
+            bp.hw = hw; bp.width = ctx->obs_width;
+            bp.code = ctx->d_code.as<uint32_t>();
+            bp.prog_offset = ctx->d_prog_off.as<int32_t>();
+            bp.constants = ctx->d_consts.as<double>();
+            bp.nb_constants = ctx->cfg.nb_constants;
+            bp.active_prog = ctx->d_active.as<int32_t>();
+            bp.nb_active = nA;
+            /* enough CTAs for ~10 waves of 148 SMs x 2 resident CTAs, at least 4 programs per warp */
+            int chunks = (int)std::max<int64_t>(1, (148 * 2 * 10 + nt - 1) / nt);
+            chunks = std::min(chunks, std::max(1, nA / 64));
+            bp.progs_per_chunk = (nA + chunks - 1) / chunks;
+            bp.bid = ctx->d_bid.as<double>();
+            bp.row_stride = (long long)nt * ts;
+            CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->uses_trig, ctx->stream));
+        }
+        if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
+        tpgx_trav_params tp{};
+        tp.bid = ctx->d_bid.as<double>();
+        tp.row_stride = (long long)nt * ts;
+        tp.nb_samples = ns;
+        tp.team_edge_offset = ctx->d_team_off.as<int32_t>();
+        tp.edge_row = ctx->d_edge_row.as<int32_t>();
+        tp.edge_destination = ctx->d_edge_dst.as<int32_t>();
+        tp.edge_lines = ctx->d_edge_lines.as<int32_t>();
+        tp.roots = ctx->d_roots.as<int32_t>();
+        tp.nb_roots = nR;
+        tp.labels = ctx->d_labels.as<uint8_t>() + s0;
+        tp.nb_classes = C;
+        tp.action = want_action ? ctx->d_action.as<uint8_t>() + s0 : nullptr;
+        tp.action_stride = nS;
+        tp.confusion = ctx->d_conf.as<unsigned long long>();
+        tp.counters = ctx->d_counters.as<unsigned long long>();
+        tp.tie_break = ctx->cfg.tie_break;
+        tp.status = ctx->d_status.as<int>();
+        CU(tpgx_launch_traverse(tp, ctx->stream));
+        if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
+    }
+    CU(tpgx_launch_score(ctx->d_conf.as<unsigned long long>(), nR, C, records_out, ctx->stream));
+    if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
+    if (run) { run->nR = nR; run->C = C; run->ts = ts; run->nS = nS; run->nTiles = nTiles; run->passes = passes; }
+    return TPGX_OK;
+}
+
+tpgx_status check_device_status(tpgx_ctx* ctx, int status) {
+    if (status & TPGX_DEV_NO_EDGE) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "a team had no admissible outgoing edge (the reference throws \"No outgoing edge to evaluate\")");
+    if (status & TPGX_DEV_PATH_TOO_LONG) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "root->action path longer than TPGX_MAX_PATH teams");
+    if (status & TPGX_DEV_BAD_ACTION) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "action id outside [0, nb_classes)");
+    if (status & TPGX_DEV_RNG_EXHAUSTED) return fail(ctx, TPGX_ERR_STATE, "episode consumed more RNG draws than the table holds");
+    return TPGX_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t tpgx_abi_version(void) { return TPGX_ABI_VERSION; }
+
+const char* tpgx_last_error(const tpgx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out) {
+    tpgx_ctx* ctx = nullptr;
+    if (!cfg || !out) return fail(nullptr, TPGX_ERR_BAD_ARG, "tpgx_create: null argument");
+    *out = nullptr;
+    if (cfg->nb_registers < 1 || cfg->nb_registers > TPGX_MAX_REGS) return fail(nullptr, TPGX_ERR_UNSUPPORTED, "nb_registers must be in [1,8]");
+    if (cfg->nb_constants < 0 || cfg->nb_constants > TPGX_MAX_CONSTS) return fail(nullptr, TPGX_ERR_UNSUPPORTED, "nb_constants must be in [0,8]");
+    if (cfg->tie_break != TPGX_TIE_LAST_MAX && cfg->tie_break != TPGX_TIE_FIRST_MAX) return fail(nullptr, TPGX_ERR_BAD_ARG, "unknown tie_break");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TPGX_ERR_CUDA, std::string("tpgx_create: no CUDA device (") + cudaGetErrorString(e) + "); libtpgx has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, TPGX_ERR_BAD_ARG, "device ordinal out of range");
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, TPGX_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, cfg->device);
+    if (prop.major < 10) return fail(nullptr, TPGX_ERR_UNSUPPORTED, "libtpgx is built for sm_100a (Blackwell) only");
+    ctx = new tpgx_ctx();
+    ctx->cfg = *cfg;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(nullptr, TPGX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    if (const char* v = getenv("TPGX_K1_VARIANT")) ctx->variant = atoi(v);
+    if (const char* v = getenv("TPGX_BID_BUDGET_MB")) ctx->bid_budget = (size_t)atoll(v) << 20;
+    *out = ctx;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
+    if (!ctx) return TPGX_OK;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = {&ctx->d_code, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
+                     &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
+                     &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
+                     &ctx->d_counters, &ctx->d_status};
+    for (DevBuf* b : all) b->release();
+    for (DevBuf& b : ctx->d_scratch) b.release();
+    for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_set_instruction_table(tpgx_ctx* ctx, int32_t n, const int32_t* opcode) {
+    if (!ctx || !opcode || n < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_instruction_table: bad argument");
+    for (int i = 0; i < n; i++)
+        if (opcode[i] < 0 || opcode[i] >= TPGX_OP_COUNT)
+            return fail(ctx, TPGX_ERR_UNSUPPORTED, "instruction " + std::to_string(i) + " has no device opcode (no CPU fallback by design)");
+    ctx->opcode.assign(opcode, opcode + n);
+    ctx->has_graph = false;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_desc* src) {
+    if (!ctx || n < 1 || !src) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_data_sources: bad argument");
+    if (n > 2) return fail(ctx, TPGX_ERR_UNSUPPORTED, "at most 2 data sources");
+    for (int i = 0; i < n; i++) {
+        if (src[i].height < 1 || src[i].width < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "source dimensions must be positive");
+        if ((int64_t)src[i].height * src[i].width > TPGX_MAX_LOC) return fail(ctx, TPGX_ERR_UNSUPPORTED, "source address space above 1024 elements");
+        if (src[i].elem != TPGX_ELEM_F64 && src[i].elem != TPGX_ELEM_I32) return fail(ctx, TPGX_ERR_BAD_ARG, "unknown element type");
+    }
+    ctx->src.assign(src, src + n);
+    ctx->has_graph = false;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
+    if (!ctx) return TPGX_ERR_BAD_ARG;
+    if (ctx->opcode.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: instruction table not set");
+    if (ctx->src.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: data sources not set");
+    cudaSetDevice(ctx->cfg.device);
+    std::string msg;
+    tpgx_flat_graph f;
+    tpgx_status st = tpgx_flatten_graph(ctx->cfg, ctx->opcode, ctx->src, g, &f, &msg);
+    if (st != TPGX_OK) return fail(ctx, st, msg);
+    ctx->flat = std::move(f);
+    const tpgx_flat_graph& F = ctx->flat;
+    ctx->uses_trig = false;
+    for (uint32_t w : F.code) { uint32_t op = w & 31u; if (op == TPGX_OP_SIN || op == TPGX_OP_COS || op == TPGX_OP_TAN) ctx->uses_trig = true; }
+    std::vector<int32_t> edge_lines(F.nb_edges);
+    for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }
+    if ((st = upload(ctx, ctx->d_code, F.code.data(), F.code.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_prog_off, F.prog_offset.data(), F.prog_offset.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_consts, F.constants.data(), F.constants.size() * 8)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_team_off, F.team_edge_offset.data(), F.team_edge_offset.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_edge_dst, F.edge_destination.data(), F.edge_destination.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_edge_lines, edge_lines.data(), edge_lines.size() * 4)) != TPGX_OK) return st;
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->graph_version++;
+    ctx->has_graph = true;
+    return TPGX_OK;
+}
+
+static tpgx_status set_obs_common(tpgx_ctx* ctx, int32_t source, int32_t store, int64_t count) {
+    if (!ctx) return TPGX_ERR_BAD_ARG;
+    if (ctx->src.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_observations: data sources not set");
+    if (source != 0 || ctx->src.size() != 1) return fail(ctx, TPGX_ERR_UNSUPPORTED, "batched observations are supported for a single data source (index 0)");
+    if (store != TPGX_STORE_U8) return fail(ctx, TPGX_ERR_UNSUPPORTED, "batched observations must be stored as uint8 (exact for MNIST pixels)");
+    if (ctx->src[0].elem != TPGX_ELEM_F64) return fail(ctx, TPGX_ERR_BAD_ARG, "uint8 observations stand in for a double source");
+    if (count < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "count must be positive");
+    ctx->obs_hw = ctx->src[0].height * ctx->src[0].width;
+    ctx->obs_width = ctx->src[0].width;
+    if (tpgx_bid_smem_bytes(ctx->variant, ctx->obs_hw) > 227 * 1024)
+        return fail(ctx, TPGX_ERR_UNSUPPORTED, "observation tile does not fit in shared memory");
+    ctx->nb_obs = count;
+    ctx->tiles_identity_valid = false;
+    return TPGX_OK;
+}
+
+/* identity packing of all observations, done once at upload so evaluations over the full set start
+ * from the tiled layout that lives in HBM */
+static tpgx_status pack_identity(tpgx_ctx* ctx) {
+    const int ts = tpgx_bid_tile_samples(ctx->variant);
+    const int64_t nTiles = (ctx->nb_obs + ts - 1) / ts;
+    CU(ctx->d_tiles.ensure((size_t)nTiles * ctx->obs_hw * ts));
+    CU(ctx->d_labels.ensure((size_t)nTiles * ts));
+    CU(tpgx_launch_pack(ctx->obs_dev, nullptr, ctx->nb_obs, ctx->nb_obs, ctx->obs_hw, ts, ctx->d_tiles.as<uint8_t>(),
+                        ctx->labels_dev, ctx->d_labels.as<uint8_t>(), ctx->stream));
+    ctx->tiles_identity_valid = true;
+    ctx->tiles_ts = ts;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data, const uint8_t* labels, int64_t count) {
+    tpgx_status st = set_obs_common(ctx, source, store, count);
+    if (st != TPGX_OK) return st;
+    if (!data) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_observations: null data");
+    cudaSetDevice(ctx->cfg.device);
+    if ((st = upload(ctx, ctx->d_obs_raw, data, (size_t)count * ctx->obs_hw)) != TPGX_OK) return st;
+    ctx->obs_dev = ctx->d_obs_raw.as<uint8_t>();
+    ctx->labels_dev = nullptr;
+    if (labels) {
+        if ((st = upload(ctx, ctx->d_labels_raw, labels, (size_t)count)) != TPGX_OK) return st;
+        ctx->labels_dev = ctx->d_labels_raw.as<uint8_t>();
+    }
+    if ((st = pack_identity(ctx)) != TPGX_OK) return st;
+    CU(cudaStreamSynchronize(ctx->stream)); /* the caller may free its buffers on return */
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_set_observations_device(tpgx_ctx* ctx, int32_t source, int32_t store, const void* d_data, const uint8_t* d_labels, int64_t count) {
+    tpgx_status st = set_obs_common(ctx, source, store, count);
+    if (st != TPGX_OK) return st;
+    if (!d_data) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_observations_device: null data");
+    cudaSetDevice(ctx->cfg.device);
+    ctx->obs_dev = static_cast<const uint8_t*>(d_data);
+    ctx->labels_dev = d_labels;
+    if ((st = pack_identity(ctx)) != TPGX_OK) return st;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_evaluate_classification(tpgx_ctx* ctx, const tpgx_classif_request* req, tpgx_classif_result* out) {
+    if (!ctx || !req || !out) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_classification: null argument");
+    cudaSetDevice(ctx->cfg.device);
+    const int nRq = req->root_end - req->root_begin;
+    if (nRq > 0 && req->nb_classes > 0) CU(ctx->d_records.ensure((size_t)nRq * (req->nb_classes + 1) * 8));
+    ClassifRun run;
+    tpgx_status st = enqueue_classification(ctx, req, ctx->d_records.as<double>(), out->action != nullptr, out->bid != nullptr, &run, true);
+    if (st != TPGX_OK) return st;
+    CU(cudaStreamSynchronize(ctx->stream));
+    int status = 0;
+    CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
+    if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
+    const int nR = run.nR, C = run.C;
+    if (out->score || out->class_f1) {
+        std::vector<double> rec((size_t)nR * (C + 1));
+        CU(cudaMemcpy(rec.data(), ctx->d_records.p, rec.size() * 8, cudaMemcpyDeviceToHost));
+        for (int r = 0; r < nR; r++) {
+            if (out->score) out->score[r] = rec[(size_t)r * (C + 1)];
+            if (out->class_f1) memcpy(out->class_f1 + (size_t)r * C, &rec[(size_t)r * (C + 1) + 1], (size_t)C * 8);
+        }
+    }
+    if (out->confusion) CU(cudaMemcpy(out->confusion, ctx->d_conf.p, (size_t)nR * C * C * 8, cudaMemcpyDeviceToHost));
+    if (out->action) CU(cudaMemcpy(out->action, ctx->d_action.p, (size_t)nR * run.nS, cudaMemcpyDeviceToHost));
+    if (out->bid) {
+        /* rows are in shard order of first appearance; scatter to program ids. Unreached programs get NaN. */
+        const int64_t stride = run.nTiles * run.ts;
+        std::vector<double> tmp((size_t)ctx->plan.nb_active * stride);
+        CU(cudaMemcpy(tmp.data(), ctx->d_bid.p, tmp.size() * 8, cudaMemcpyDeviceToHost));
+        const double qnan = __builtin_nan("");
+        for (size_t i = 0; i < (size_t)ctx->flat.nb_programs * run.nS; i++) out->bid[i] = qnan;
+        for (int row = 0; row < ctx->plan.nb_active; row++)
+            memcpy(out->bid + (size_t)ctx->h_active[row] * run.nS, tmp.data() + (size_t)row * stride, (size_t)run.nS * 8);
+    }
+    if (out->counters) {
+        unsigned long long c[4];
+        CU(cudaMemcpy(c, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost));
+        memset(out->counters, 0, sizeof(*out->counters));
+        out->counters->evaluations = c[0];
+        out->counters->team_visits = c[1];
+        out->counters->program_executions = c[2];
+        out->counters->lines_executed = c[3];
+        out->counters->device_lines = (uint64_t)ctx->plan.active_lines * (uint64_t)run.nS;
+        out->counters->device_program_executions = (uint64_t)ctx->plan.nb_active * (uint64_t)run.nS;
+    }
+    if (out->device_ms) {
+        float k1 = 0, k2 = 0, k3 = 0, t;
+        for (int ps = 0; ps < run.passes; ps++) {
+            cudaEventElapsedTime(&t, ctx->event(3 * ps), ctx->event(3 * ps + 1)); k1 += t;
+            cudaEventElapsedTime(&t, ctx->event(3 * ps + 1), ctx->event(3 * ps + 2)); k2 += t;
+        }
+        cudaEventElapsedTime(&k3, ctx->event(3 * run.passes - 1), ctx->event(3 * run.passes));
+        out->device_ms[0] = k1; out->device_ms[1] = k2; out->device_ms[2] = k3;
+    }
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_evaluate_classification_device(tpgx_ctx* ctx, const tpgx_classif_request* req, double* d_records, void* stream) {
+    if (!ctx || !req || !d_records) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_classification_device: null argument");
+    cudaSetDevice(ctx->cfg.device);
+    /* order our stream after the caller's, run, then make the caller's stream wait for us */
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    cudaEvent_t ev_in = ctx->event(62), ev_out = ctx->event(63);
+    CU(cudaEventRecord(ev_in, user));
+    CU(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+    tpgx_status st = enqueue_classification(ctx, req, d_records, false, false, nullptr, false);
+    if (st != TPGX_OK) return st;
+    CU(cudaEventRecord(ev_out, ctx->stream));
+    CU(cudaStreamWaitEvent(user, ev_out, 0));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_execute_programs(tpgx_ctx* ctx, int64_t count, const double* const* obs_f64, const int32_t* const* obs_i32, double* bid) {
+    if (!ctx || count < 1 || !bid) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_execute_programs: bad argument");
+    if (!ctx->has_graph) return fail(ctx, TPGX_ERR_STATE, "tpgx_execute_programs: no graph set");
+    cudaSetDevice(ctx->cfg.device);
+    const double* f[2] = {nullptr, nullptr};
+    const int32_t* iv[2] = {nullptr, nullptr};
+    int space[2] = {0, 0}, width[2] = {0, 0};
+    tpgx_status st;
+    for (size_t k = 0; k < ctx->src.size(); k++) {
+        space[k] = ctx->src[k].height * ctx->src[k].width;
+        width[k] = ctx->src[k].width;
+        if (ctx->src[k].elem == TPGX_ELEM_F64) {
+            if (!obs_f64 || !obs_f64[k]) return fail(ctx, TPGX_ERR_BAD_ARG, "missing f64 observations");
+            if ((st = upload(ctx, ctx->d_scratch[k], obs_f64[k], (size_t)count * space[k] * 8)) != TPGX_OK) return st;
+            f[k] = ctx->d_scratch[k].as<double>();
+        } else {
+            if (!obs_i32 || !obs_i32[k]) return fail(ctx, TPGX_ERR_BAD_ARG, "missing i32 observations");
+            if ((st = upload(ctx, ctx->d_scratch[k], obs_i32[k], (size_t)count * space[k] * 4)) != TPGX_OK) return st;
+            iv[k] = ctx->d_scratch[k].as<int32_t>();
+        }
+    }
+    const int P = ctx->flat.nb_programs;
+    CU(ctx->d_scratch[2].ensure((size_t)P * count * 8));
+    CU(tpgx_launch_exec_generic(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(),
+                                ctx->cfg.nb_constants, P, count, f[0], f[1], iv[0], iv[1], space[0], space[1], width[0], width[1],
+                                ctx->d_scratch[2].as<double>(), ctx->stream));
+    CU(cudaMemcpyAsync(bid, ctx->d_scratch[2].p, (size_t)P * count * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_episode_result* out) {
+    if (!ctx || !req || !out) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_episodes: null argument");
+    if (!ctx->has_graph) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_episodes: no graph set");
+    cudaSetDevice(ctx->cfg.device);
+    const int K = req->roots_per_job, NI = req->nb_iterations, J = req->nb_jobs;
+    if (K < 1 || K > 2 || NI < 1 || J < 1 || req->max_actions < 1 || !req->seeds || !req->job_roots)
+        return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_episodes: bad request");
+    for (int i = 0; i < J * K; i++)
+        if (req->job_roots[i] < 0 || req->job_roots[i] >= ctx->flat.nb_roots) return fail(ctx, TPGX_ERR_BAD_ARG, "job root out of range");
+    /* expected data-source shapes per environment (getDataSources() of the app) */
+    const std::vector<tpgx_source_desc>& s = ctx->src;
+    bool ok = false;
+    switch (req->env) {
+    case TPGX_ENV_GRIDWORLD: case TPGX_ENV_PENDULUM:
+        ok = s.size() == 1 && s[0].elem == TPGX_ELEM_F64 && !s[0].is_2d && s[0].width == 2; break;
+    case TPGX_ENV_TICTACTOE:
+        ok = s.size() == 1 && s[0].elem == TPGX_ELEM_F64 && !s[0].is_2d && s[0].width == 9; break;
+    case TPGX_ENV_STICKGAME:
+        ok = s.size() == 2 && s[0].elem == TPGX_ELEM_I32 && s[0].width == 4 && s[1].elem == TPGX_ELEM_I32 && s[1].width == 1; break;
+    default: return fail(ctx, TPGX_ERR_BAD_ARG, "unknown environment kind");
+    }
+    if (!ok) return fail(ctx, TPGX_ERR_BAD_ARG, "data sources do not match the environment's getDataSources()");
+    if (req->env == TPGX_ENV_PENDULUM && (req->nb_pendulum_actions < 1 || req->nb_pendulum_actions > 16 || !req->pendulum_actions))
+        return fail(ctx, TPGX_ERR_BAD_ARG, "pendulum needs its availableActions list (<= 16 entries)");
+
+    tpgx_episode_params ep{};
+    ep.env = req->env; ep.mode = req->mode; ep.nb_iterations = NI; ep.max_actions = req->max_actions;
+    ep.nb_jobs = J; ep.roots_per_job = K; ep.second_player_random = req->second_player_random;
+    ep.trace_steps = out->trace ? req->trace_steps : 0;
+    ep.tie_break = ctx->cfg.tie_break;
+    ep.nb_constants = ctx->cfg.nb_constants;
+    ep.nb_pendulum_actions = req->nb_pendulum_actions;
+    for (int i = 0; i < req->nb_pendulum_actions && i < 16; i++) ep.pendulum_actions[i] = req->pendulum_actions[i];
+    /* RNG streams: every root sees the same seed per iteration ([UP] evaluateJob), so the raw
+       mt19937_64 outputs are generated once per iteration on the host and shared by all jobs */
+    std::vector<uint64_t> raw((size_t)NI * TPGX_RNG_TABLE);
+    for (int it = 0; it < NI; it++) tpgx_rng_fill_raw(tpgx_env_seed(req->seeds[it], req->mode), TPGX_RNG_TABLE, raw.data() + (size_t)it * TPGX_RNG_TABLE);
+    std::vector<int32_t> job_teams((size_t)J * K);
+    for (int i = 0; i < J * K; i++) job_teams[i] = ctx->flat.root_team[req->job_roots[i]];
+    tpgx_status st;
+    DevBuf* sc = ctx->d_scratch;
+    const size_t nE = (size_t)J * NI;
+    if ((st = upload(ctx, sc[0], raw.data(), raw.size() * 8)) != TPGX_OK) return st;
+    if ((st = upload(ctx, sc[1], job_teams.data(), job_teams.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, sc[7], ctx->flat.edge_program.data(), ctx->flat.edge_program.size() * 4)) != TPGX_OK) return st;
+    CU(sc[2].ensure(nE * K * 8));                  /* episode scores */
+    CU(sc[3].ensure(nE * 4));                      /* episode action counts */
+    CU(sc[4].ensure(nE * 4 * 8));                  /* final state */
+    CU(sc[5].ensure(std::max<size_t>(16, nE * (size_t)ep.trace_steps)));
+    CU(sc[6].ensure((size_t)J * K * 8));           /* job scores */
+    CU(ctx->d_counters.ensure(64));
+    CU(ctx->d_status.ensure(16));
+    CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+    ep.rng_raw = sc[0].as<uint64_t>();
+    ep.job_teams = sc[1].as<int32_t>();
+    ep.code = ctx->d_code.as<uint32_t>();
+    ep.prog_offset = ctx->d_prog_off.as<int32_t>();
+    ep.constants = ctx->d_consts.as<double>();
+    ep.team_edge_offset = ctx->d_team_off.as<int32_t>();
+    ep.edge_program = sc[7].as<int32_t>();
+    ep.edge_destination = ctx->d_edge_dst.as<int32_t>();
+    ep.episode_score = sc[2].as<double>();
+    ep.episode_actions = sc[3].as<int32_t>();
+    ep.final_state = sc[4].as<double>();
+    ep.trace = sc[5].as<int8_t>();
+    ep.job_score = sc[6].as<double>();
+    ep.counters = ctx->d_counters.as<unsigned long long>();
+    ep.status = ctx->d_status.as<int>();
+    CU(cudaEventRecord(ctx->event(0), ctx->stream));
+    CU(tpgx_launch_episodes(ep, ctx->stream));
+    CU(cudaEventRecord(ctx->event(1), ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int status = 0;
+    CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
+    if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
+    if (out->score) CU(cudaMemcpy(out->score, sc[6].p, (size_t)J * K * 8, cudaMemcpyDeviceToHost));
+    if (out->episode_score) CU(cudaMemcpy(out->episode_score, sc[2].p, nE * K * 8, cudaMemcpyDeviceToHost));
+    if (out->episode_actions) CU(cudaMemcpy(out->episode_actions, sc[3].p, nE * 4, cudaMemcpyDeviceToHost));
+    if (out->final_state) CU(cudaMemcpy(out->final_state, sc[4].p, nE * 4 * 8, cudaMemcpyDeviceToHost));
+    if (out->trace && ep.trace_steps > 0) CU(cudaMemcpy(out->trace, sc[5].p, nE * (size_t)ep.trace_steps, cudaMemcpyDeviceToHost));
+    if (out->counters) {
+        unsigned long long c[4];
+        CU(cudaMemcpy(c, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost));
+        memset(out->counters, 0, sizeof(*out->counters));
+        out->counters->evaluations = c[0]; out->counters->team_visits = c[1];
+        out->counters->program_executions = c[2]; out->counters->lines_executed = c[3];
+        out->counters->device_lines = c[3]; out->counters->device_program_executions = c[2];
+    }
+    if (out->device_ms) cudaEventElapsedTime(out->device_ms, ctx->event(0), ctx->event(1));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_measure_fp64_peak(tpgx_ctx* ctx, double* dadd_per_s, double* dfma_per_s) {
+    if (!ctx) return TPGX_ERR_BAD_ARG;
+    cudaSetDevice(ctx->cfg.device);
+    CU(ctx->d_scratch[0].ensure(64));
+    const int blocks = 148 * 8, iters = 20000;
+    double best[2] = {0, 0};
+    for (int mode = 0; mode < 2; mode++) {
+        for (int rep = 0; rep < 4; rep++) {
+            CU(cudaEventRecord(ctx->event(0), ctx->stream));
+            CU(tpgx_launch_fp64_peak(mode, blocks, iters, ctx->d_scratch[0].as<double>(), ctx->stream));
+            CU(cudaEventRecord(ctx->event(1), ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->event(0), ctx->event(1));
+            /* thread-level FP64 instructions per second */
+            const double ops = (double)blocks * 256.0 * iters * 16.0;
+            if (rep > 0) best[mode] = std::max(best[mode], ops / (ms * 1e-3));
+        }
+    }
+    if (dadd_per_s) *dadd_per_s = best[0];
+    if (dfma_per_s) *dfma_per_s = best[1];
+    return TPGX_OK;
+}
+
+} /* extern "C" */

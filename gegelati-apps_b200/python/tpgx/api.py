@@ -1,0 +1,176 @@
+"""ctypes binding of libtpgx.so — the C ABI declared in include/tpgx.h.  Mirrors the reference's
+agent-level calls: one Evaluator ~ one Learn::LearningAgent's evaluation engine.  There is no
+CPU fallback: if the CUDA library is missing or no GPU is present this raises."""
+import ctypes as C
+import os
+import numpy as np
+
+from . import _cabi as A
+from .graph import TPGraph
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "lib", "libtpgx.so"))
+
+EXPORTS = [
+    "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
+    "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_device",
+    "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_evaluate_episodes",
+    "tpgx_execute_programs", "tpgx_measure_fp64_peak",
+]
+
+_lib = None
+
+
+class TpgxError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("tpgx %s: %s" % (A.STATUS_NAME.get(status, status), message))
+        self.status = status
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libtpgx.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "or `make -C gegelati-apps_b200` — there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.tpgx_last_error.restype = C.c_char_p
+    lib.tpgx_last_error.argtypes = [C.c_void_p]
+    lib.tpgx_create.argtypes = [C.POINTER(A.Config), C.POINTER(C.c_void_p)]
+    lib.tpgx_destroy.argtypes = [C.c_void_p]
+    lib.tpgx_set_instruction_table.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.tpgx_set_data_sources.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.tpgx_set_graph.argtypes = [C.c_void_p, C.POINTER(A.Graph)]
+    lib.tpgx_set_observations.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.tpgx_set_observations_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.tpgx_evaluate_classification.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.POINTER(A.ClassifResult)]
+    lib.tpgx_evaluate_classification_device.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.c_void_p, C.c_void_p]
+    lib.tpgx_evaluate_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.POINTER(A.EpisodeResult)]
+    lib.tpgx_execute_programs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tpgx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None else None
+
+
+class Evaluator:
+    """Owns one tpgx_ctx (one GPU)."""
+
+    def __init__(self, opcodes, sources, nb_registers=8, nb_constants=0, tie_break=A.TIE_LAST_MAX, device=0):
+        self.lib = load_library()
+        cfg = A.Config(device=device, nb_registers=nb_registers, nb_constants=nb_constants, tie_break=tie_break)
+        h = C.c_void_p()
+        st = self.lib.tpgx_create(C.byref(cfg), C.byref(h))
+        if st != A.OK:
+            raise TpgxError(st, (self.lib.tpgx_last_error(None) or b"").decode())
+        self.h = h
+        self.nb_constants = nb_constants
+        self.sources = list(sources)
+        ops = np.ascontiguousarray(opcodes, dtype=np.int32)
+        self._check(self.lib.tpgx_set_instruction_table(self.h, len(ops), ops.ctypes.data))
+        sd = (A.SourceDesc * len(sources))(*[A.SourceDesc(*s) for s in sources])
+        self._check(self.lib.tpgx_set_data_sources(self.h, len(sources), C.cast(sd, C.c_void_p)))
+        self.graph = None
+        self.nb_obs = 0
+
+    def _check(self, st):
+        if st != A.OK:
+            raise TpgxError(st, (self.lib.tpgx_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.tpgx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_graph(self, g: TPGraph):
+        cs, keep = g.c_struct()
+        self._check(self.lib.tpgx_set_graph(self.h, C.byref(cs)))
+        self.graph = g
+
+    def set_observations(self, images_u8, labels=None):
+        img = np.ascontiguousarray(images_u8, dtype=np.uint8)
+        lab = np.ascontiguousarray(labels, dtype=np.uint8) if labels is not None else None
+        self._check(self.lib.tpgx_set_observations(self.h, 0, A.STORE_U8, img.ctypes.data, _ptr(lab), img.shape[0]))
+        self.nb_obs = img.shape[0]
+
+    def set_observations_device(self, data_ptr, labels_ptr, count):
+        self._check(self.lib.tpgx_set_observations_device(self.h, 0, A.STORE_U8, data_ptr, labels_ptr, count))
+        self.nb_obs = count
+
+    def evaluate_classification(self, nb_samples=None, sample_index=None, nb_classes=10, root_begin=0, root_end=None,
+                                want=("score", "class_f1", "confusion", "counters", "device_ms")):
+        g = self.graph
+        root_end = g.nb_roots if root_end is None else root_end
+        idx = np.ascontiguousarray(sample_index, dtype=np.int32) if sample_index is not None else None
+        nS = int(nb_samples if nb_samples is not None else (len(idx) if idx is not None else self.nb_obs))
+        nR = root_end - root_begin
+        req = A.ClassifRequest(nb_samples=nS, sample_index=_ptr(idx), nb_classes=nb_classes, root_begin=root_begin, root_end=root_end)
+        out = {}
+        res = A.ClassifResult()
+        cnt = A.Counters()
+        if "score" in want: out["score"] = np.zeros(nR); res.score = out["score"].ctypes.data
+        if "class_f1" in want: out["class_f1"] = np.zeros((nR, nb_classes)); res.class_f1 = out["class_f1"].ctypes.data
+        if "confusion" in want: out["confusion"] = np.zeros((nR, nb_classes, nb_classes), dtype=np.uint64); res.confusion = out["confusion"].ctypes.data
+        if "action" in want: out["action"] = np.zeros((nR, nS), dtype=np.uint8); res.action = out["action"].ctypes.data
+        if "bid" in want: out["bid"] = np.zeros((g.nb_programs, nS)); res.bid = out["bid"].ctypes.data
+        if "counters" in want: res.counters = C.pointer(cnt)
+        if "device_ms" in want: out["device_ms"] = np.zeros(3, dtype=np.float32); res.device_ms = out["device_ms"].ctypes.data
+        self._check(self.lib.tpgx_evaluate_classification(self.h, C.byref(req), C.byref(res)))
+        if "counters" in want: out["counters"] = cnt.as_dict()
+        return out
+
+    def evaluate_classification_device(self, records_ptr, stream_ptr, nb_samples, nb_classes=10, root_begin=0, root_end=None):
+        root_end = self.graph.nb_roots if root_end is None else root_end
+        req = A.ClassifRequest(nb_samples=int(nb_samples), sample_index=None, nb_classes=nb_classes, root_begin=root_begin, root_end=root_end)
+        self._check(self.lib.tpgx_evaluate_classification_device(self.h, C.byref(req), records_ptr, stream_ptr))
+
+    def execute_programs(self, count, obs):
+        """obs: list per data source of arrays [count, space] (float64 or int32). Returns bid [P, count]."""
+        n = len(self.sources)
+        f = (C.c_void_p * n)(); iv = (C.c_void_p * n)(); keep = []
+        for k, (elem, h, w, _) in enumerate(self.sources):
+            a = np.ascontiguousarray(obs[k], dtype=np.float64 if elem == A.ELEM_F64 else np.int32).reshape(count, h * w)
+            keep.append(a)
+            if elem == A.ELEM_F64: f[k] = a.ctypes.data
+            else: iv[k] = a.ctypes.data
+        bid = np.zeros((self.graph.nb_programs, count))
+        self._check(self.lib.tpgx_execute_programs(self.h, count, C.cast(f, C.c_void_p), C.cast(iv, C.c_void_p), bid.ctypes.data))
+        return bid
+
+    def evaluate_episodes(self, env, seeds, job_roots, max_actions, mode=A.MODE_TRAINING, roots_per_job=1,
+                          second_player_random=0, pendulum_actions=None, trace_steps=0):
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        jr = np.ascontiguousarray(job_roots, dtype=np.int32).reshape(-1, roots_per_job)
+        J, NI = jr.shape[0], len(seeds)
+        pa = np.ascontiguousarray(pendulum_actions, dtype=np.float64) if pendulum_actions is not None else None
+        req = A.EpisodeRequest(env=env, mode=mode, nb_iterations=NI, max_actions=max_actions, seeds=seeds.ctypes.data, nb_jobs=J,
+                               roots_per_job=roots_per_job, job_roots=jr.ctypes.data, second_player_random=second_player_random,
+                               nb_pendulum_actions=0 if pa is None else len(pa), pendulum_actions=_ptr(pa), trace_steps=trace_steps)
+        out = dict(score=np.zeros((J, roots_per_job)), episode_score=np.zeros((J, NI, roots_per_job)),
+                   episode_actions=np.zeros((J, NI), dtype=np.int32), final_state=np.zeros((J, NI, 4)),
+                   device_ms=np.zeros(1, dtype=np.float32))
+        cnt = A.Counters()
+        res = A.EpisodeResult(score=out["score"].ctypes.data, episode_score=out["episode_score"].ctypes.data,
+                              episode_actions=out["episode_actions"].ctypes.data, final_state=out["final_state"].ctypes.data,
+                              counters=C.pointer(cnt), device_ms=out["device_ms"].ctypes.data)
+        if trace_steps > 0:
+            out["trace"] = np.zeros((J, NI, trace_steps), dtype=np.int8)
+            res.trace = out["trace"].ctypes.data
+        self._check(self.lib.tpgx_evaluate_episodes(self.h, C.byref(req), C.byref(res)))
+        out["counters"] = cnt.as_dict()
+        return out
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.tpgx_measure_fp64_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

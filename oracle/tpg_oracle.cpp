@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "../gegelati-apps_b200/csrc/tpgx_math.h"
+#include "../gegelati-apps_b200/csrc/tpgx_rng.h"
 
 namespace {
 
@@ -300,6 +301,8 @@ struct Env {
     virtual SourceView view(int s) const = 0;
     virtual int state(double* out, int n) const = 0;
     virtual void set_state(const double* st, int n) = 0;
+    /* 4-value digest of the final state written to tpgx_episode_result.final_state */
+    virtual void summary(double* o) const { state(o, 4); }
 };
 
 /* [REF] gridworld/src/gridworld.{h,cpp} */
@@ -463,6 +466,13 @@ struct TicTacToeEnv : Env {
         return 11;
     }
     void set_state(const double* s, int n) override { for (int i = 0; i < 9 && i < n; i++) board[i] = s[i]; if (n >= 10) turn = (int)s[9]; }
+    void summary(double* o) const override { /* board as a base-3 number, turn, flag bits */
+        double code = 0.0, w = 1.0;
+        for (int i = 0; i < 9; i++) { code += (board[i] + 1.0) * w; w *= 3.0; }
+        o[0] = code; o[1] = turn;
+        o[2] = (win1 ? 1 : 0) + (win2 ? 2 : 0) + (forb1 ? 4 : 0) + (forb2 ? 8 : 0) + (null_game ? 16 : 0) + (end ? 32 : 0);
+        o[3] = 0.0;
+    }
 };
 
 /* [REF] pendulum/src/Learn/pendulum.{h,cpp} */
@@ -761,7 +771,7 @@ int32_t orc_evaluate_episodes(const orc_engine* e, const tpgx_episode_request* r
                 if (out->episode_score) out->episode_score[((size_t)j * NI + it) * K + k] = sc;
             }
             if (out->episode_actions) out->episode_actions[(size_t)j * NI + it] = n;
-            if (out->final_state) env->state(out->final_state + ((size_t)j * NI + it) * 4, 4);
+            if (out->final_state) env->summary(out->final_state + ((size_t)j * NI + it) * 4);
         }
         if (out->score) for (int k = 0; k < K; k++) out->score[(size_t)j * K + k] = result[k] / (double)NI;
     });
@@ -808,6 +818,23 @@ void orc_rng_f64(uint64_t seed, int64_t n, double lo, double hi, double* out) {
 void orc_rng_raw(uint64_t seed, int64_t n, uint64_t* out) {
     std::mt19937_64 g(seed);
     for (int64_t i = 0; i < n; i++) out[i] = g();
+}
+
+/* The product's restatement of libstdc++'s distributions (tpgx_rng.h) driven by the same engine:
+ * lets CPU tests pin it against the std:: distributions used above. */
+void orc_rng_restated_u64(uint64_t seed, int64_t n, uint64_t lo, uint64_t hi, uint64_t* out) {
+    std::vector<uint64_t> raw(TPGX_RNG_TABLE);
+    std::mt19937_64 g(seed);
+    for (auto& v : raw) v = g();
+    tpgx_rng_cursor c{raw.data(), 0, 0};
+    for (int64_t i = 0; i < n; i++) out[i] = tpgx_rng_u64(c, lo, hi);
+}
+void orc_rng_restated_f64(uint64_t seed, int64_t n, double lo, double hi, double* out) {
+    std::vector<uint64_t> raw(TPGX_RNG_TABLE);
+    std::mt19937_64 g(seed);
+    for (auto& v : raw) v = g();
+    tpgx_rng_cursor c{raw.data(), 0, 0};
+    for (int64_t i = 0; i < n; i++) out[i] = tpgx_rng_f64(c, lo, hi);
 }
 
 } /* extern "C" */

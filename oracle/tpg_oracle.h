@@ -80,6 +80,9 @@ int32_t orc_env_state(const orc_env* v, double* state, int32_t n);
 void orc_rng_u64(uint64_t seed, int64_t n, uint64_t lo, uint64_t hi, uint64_t* out);
 void orc_rng_f64(uint64_t seed, int64_t n, double lo, double hi, double* out);
 void orc_rng_raw(uint64_t seed, int64_t n, uint64_t* out);
+/* same draws through the product's restated distributions (tpgx_rng.h); n <= 256 raw draws */
+void orc_rng_restated_u64(uint64_t seed, int64_t n, uint64_t lo, uint64_t hi, uint64_t* out);
+void orc_rng_restated_f64(uint64_t seed, int64_t n, double lo, double hi, double* out);
 
 #ifdef __cplusplus
 }

