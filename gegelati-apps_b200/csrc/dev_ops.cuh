@@ -34,7 +34,7 @@ __device__ __forceinline__ double tpgx_apply_dd(uint32_t op, double a, double b)
     case TPGX_OP_SUB: return a - b;
     case TPGX_OP_ADD: return a + b;
     case TPGX_OP_MUL: return a * b;
-    case TPGX_OP_DIV: return a / b;
+    case TPGX_OP_DIV: return tpgx_math::xdiv(a, b);
     case TPGX_OP_MAX: return (a < b) ? b : a;
     case TPGX_OP_EXP: return tpgx_math::exp(a);
     case TPGX_OP_LOG: return tpgx_math::log(a);
@@ -42,7 +42,7 @@ __device__ __forceinline__ double tpgx_apply_dd(uint32_t op, double a, double b)
     case TPGX_OP_SIN: if (TRIG) return tpgx_math::sin(a); else return 0.0;
     case TPGX_OP_TAN: if (TRIG) return tpgx_math::tan(a); else return 0.0;
     case TPGX_OP_PI: return TPGX_PI;
-    case TPGX_OP_MULC: return a * b / 10.0;                 /* b carries the constant */
+    case TPGX_OP_MULC: return tpgx_math::xdiv(a * b, 10.0);  /* b carries the constant */
     case TPGX_OP_FMODG: return b != 0.0 ? fmod(a, b) : DBL_MIN;
     case TPGX_OP_EQ0: return (a == 0.0) ? 10.0 : 0.0;
     case TPGX_OP_EQM1: return (a == -1.0) ? 10.0 : 0.0;
@@ -58,7 +58,7 @@ __device__ __forceinline__ double tpgx_sobel_f64(uint32_t op, const double* w) {
     double gx = -w[0] + w[2] - 2.0 * w[3] + 2.0 * w[5] - w[6] + w[8];
     double gy = -w[0] - 2.0 * w[1] - w[2] + w[6] + 2.0 * w[7] + w[8];
     if (op == TPGX_OP_SOBEL_MAGN) return sqrt(gx * gx + gy * gy);
-    return tpgx_math::atan(gy / gx);
+    return tpgx_math::atan(tpgx_math::xdiv(gy, gx));
 }
 
 /* Observation of one episode / sample for the per-thread executor. */

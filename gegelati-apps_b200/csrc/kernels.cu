@@ -53,12 +53,12 @@ __device__ __forceinline__ double u8_to_f64(uint32_t v) { return __hiloint2doubl
  * CTA = one sample tile (TS = 32*K samples, staged once by a bulk TMA copy) x one chunk of
  * programs; each warp repeatedly claims a program of the chunk and interprets it for the 32*K
  * samples of the tile (lane = K consecutive samples), so opcode dispatch is warp-uniform.
- * TPG registers live in shared memory as [warp][reg][TS] doubles (conflict-free 8*K-byte lane
- * accesses); the line words of a program are held one per lane and broadcast by shuffle.           */
-template <int K> struct lane_vec;
-template <> struct lane_vec<1> { typedef double type; typedef uint8_t bytes; };
-template <> struct lane_vec<2> { typedef double2 type; typedef uchar2 bytes; };
-template <> struct lane_vec<4> { typedef double4 type; typedef uchar4 bytes; };
+ * TPG registers live in shared memory as [warp][9][TS] doubles (slot 8 is a constant 0.0 that
+ * stands for "never written" registers); lane accesses are conflict-free 8*K-byte vectors.  The
+ * line words of a program are held one per lane and broadcast by shuffle.  One dispatch per line;
+ * each case handles the lane's K samples.  Transcendentals and division are kept out of line so
+ * the interpreter loop stays small in the instruction cache.                                      */
+#define K1_SLOTS 9
 
 template <int K> __device__ __forceinline__ void ld_regs(const double* p, double (&v)[K]);
 template <> __device__ __forceinline__ void ld_regs<1>(const double* p, double (&v)[1]) { v[0] = *p; }
@@ -87,23 +87,28 @@ template <> __device__ __forceinline__ void ld_px<4>(const uint8_t* p, uint32_t 
     uchar4 t = *reinterpret_cast<const uchar4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
+/* a double operand: a TPG register (or the zero slot) or one pixel of each of the lane's K samples */
 template <int K>
 __device__ __forceinline__ void fetch_double(uint32_t f, double (&v)[K], const double* regs_lane, const uint8_t* tile_lane) {
     constexpr int TS = 32 * K;
-    const uint32_t kind = f >> 10, loc = f & 1023u;
-    if (kind == TPGX_KIND_REG) {
-        if (loc < TPGX_LOC_ZERO) ld_regs<K>(regs_lane + loc * TS, v);
-        else {
-#pragma unroll
-            for (int k = 0; k < K; k++) v[k] = 0.0;
-        }
-    } else { /* SRC0: one pixel of each of the lane's K samples */
+    if (f & (TPGX_KIND_SRC0 << 10)) {
         uint32_t px[K];
-        ld_px<K>(tile_lane + loc * TS, px);
+        ld_px<K>(tile_lane + (f & 1023u) * TS, px);
 #pragma unroll
         for (int k = 0; k < K; k++) v[k] = u8_to_f64(px[k]);
+    } else {
+        ld_regs<K>(regs_lane + (f & 15u) * TS, v);
     }
 }
+
+__device__ __forceinline__ double k1_exp(double x) { return tpgx_math::exp(x); }
+__device__ __forceinline__ double k1_log(double x) { return tpgx_math::log(x); }
+__device__ __forceinline__ double k1_atan(double x) { return tpgx_math::atan(x); }
+__device__ __noinline__ double k1_sin(double x) { return tpgx_math::sin(x); }
+__device__ __noinline__ double k1_cos(double x) { return tpgx_math::cos(x); }
+__device__ __noinline__ double k1_tan(double x) { return tpgx_math::tan(x); }
+__device__ __forceinline__ double k1_div(double a, double b) { return tpgx_math::xdiv(a, b); }
+__device__ __noinline__ double k1_fmodg(double a, double b) { return b != 0.0 ? fmod(a, b) : DBL_MIN; }
 
 template <int K, int NW, int MINB, bool TRIG>
 __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_params p) {
@@ -112,7 +117,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
     const int tile_bytes = p.hw * TS;
     uint8_t* tile = smem;
     double* regs = reinterpret_cast<double*>(smem + ((tile_bytes + 127) & ~127));
-    double* sconst = regs + NW * TPGX_MAX_REGS * TS;
+    double* sconst = regs + NW * K1_SLOTS * TS;
     uint64_t* bar = reinterpret_cast<uint64_t*>(sconst + NW * TPGX_MAX_CONSTS);
     int* s_next = reinterpret_cast<int*>(bar + 1);
 
@@ -127,9 +132,15 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
         mbar_expect_tx(bar, (uint32_t)tile_bytes);
         tma_load_1d(tile, p.tiles + (size_t)blockIdx.x * tile_bytes, (uint32_t)tile_bytes, bar);
     }
+    double* regs_lane = regs + warp * (K1_SLOTS * TS) + lane * K;
+    {
+        double z[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) z[k] = 0.0;
+        st_regs<K>(regs_lane + TPGX_LOC_ZERO * TS, z);
+    }
     mbar_wait(bar, 0);
 
-    double* regs_lane = regs + warp * (TPGX_MAX_REGS * TS) + lane * K;
     const uint8_t* tile_lane = tile + lane * K;
     double* my_const = sconst + warp * TPGX_MAX_CONSTS;
     const int chunk_begin = blockIdx.y * p.progs_per_chunk;
@@ -156,9 +167,10 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
         for (int base = 0; base < n; base += 32) {
             const uint32_t mine = (base + lane < n) ? __ldg(p.code + cb + base + lane) : 0u;
             const int m = min(32, n - base);
+#pragma unroll 1
             for (int j = 0; j < m; j++) {
                 const uint32_t w = __shfl_sync(0xffffffffu, mine, j);
-                const uint32_t op = w & 31u, dst = (w >> 5) & 7u;
+                const uint32_t op = w & 31u;
                 const uint32_t fa = (w >> 8) & 0xfffu, fb = w >> 20;
                 if (op >= TPGX_OP_SOBEL_MAGN) {
                     /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
@@ -172,22 +184,47 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
                     for (int k = 0; k < K; k++) {
                         const int gx = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
                         const int gy = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
-                        if (op == TPGX_OP_SOBEL_MAGN) res[k] = sqrt((double)(gx * gx + gy * gy));
-                        else res[k] = tpgx_math::atan((double)gy / (double)gx);
+                        if (op == TPGX_OP_SOBEL_MAGN) res[k] = tpgx_math::xsqrt_nonneg((double)(gx * gx + gy * gy));
+                        else res[k] = k1_atan(k1_div((double)gy, (double)gx));
                     }
                 } else {
                     double a[K], b[K];
                     fetch_double<K>(fa, a, regs_lane, tile_lane);
                     if ((TPGX_MASK_B_DOUBLE >> op) & 1u) fetch_double<K>(fb, b, regs_lane, tile_lane);
-                    else {
-                        const double c = (op == TPGX_OP_MULC) ? my_const[fb & 1023u] : 0.0;
+                    else if (op == TPGX_OP_MULC) {
+                        const double c = my_const[fb & 15u];
 #pragma unroll
                         for (int k = 0; k < K; k++) b[k] = c;
                     }
-#pragma unroll
-                    for (int k = 0; k < K; k++) res[k] = tpgx_apply_dd<TRIG>(op, a[k], b[k]);
+#define K1_EACH(expr)                              \
+    {                                              \
+        _Pragma("unroll") for (int k = 0; k < K; k++) { const double x = a[k], y = b[k]; (void)y; res[k] = (expr); } \
+    }                                              \
+    break;
+                    switch (op) {
+                    case TPGX_OP_SUB: K1_EACH(x - y)
+                    case TPGX_OP_ADD: K1_EACH(x + y)
+                    case TPGX_OP_MUL: K1_EACH(x * y)
+                    case TPGX_OP_DIV: K1_EACH(k1_div(x, y))
+                    case TPGX_OP_MAX: K1_EACH((x < y) ? y : x)
+                    case TPGX_OP_EXP: K1_EACH(k1_exp(x))
+                    case TPGX_OP_LOG: K1_EACH(k1_log(x))
+                    case TPGX_OP_COS: K1_EACH(TRIG ? k1_cos(x) : 0.0)
+                    case TPGX_OP_SIN: K1_EACH(TRIG ? k1_sin(x) : 0.0)
+                    case TPGX_OP_TAN: K1_EACH(TRIG ? k1_tan(x) : 0.0)
+                    case TPGX_OP_PI: K1_EACH(TPGX_PI)
+                    case TPGX_OP_MULC: K1_EACH(k1_div(x * y, 10.0))
+                    case TPGX_OP_FMODG: K1_EACH(k1_fmodg(x, y))
+                    case TPGX_OP_EQ0: K1_EACH((x == 0.0) ? 10.0 : 0.0)
+                    case TPGX_OP_EQM1: K1_EACH((x == -1.0) ? 10.0 : 0.0)
+                    case TPGX_OP_EQ1: K1_EACH((x == 1.0) ? 10.0 : 0.0)
+                    case TPGX_OP_GE15: K1_EACH((x >= 15.0) ? 10.0 : 0.0)
+                    case TPGX_OP_COND: K1_EACH(x < y ? -x : x)
+                    default: break;
+                    }
+#undef K1_EACH
                 }
-                st_regs<K>(regs_lane + dst * TS, res);
+                st_regs<K>(regs_lane + ((w >> 5) & 7u) * TS, res);
             }
         }
         /* [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
@@ -199,7 +236,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
 }
 
 struct bid_variant { int K, NW, MINB; };
-static const bid_variant g_variants[] = {{2, 14, 2}, {4, 12, 1}, {2, 8, 2}, {1, 16, 2}, {2, 24, 1}};
+static const bid_variant g_variants[] = {{2, 12, 2}, {4, 12, 1}, {2, 8, 2}, {1, 16, 2}, {2, 20, 1}, {4, 8, 1}};
 static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 int tpgx_bid_tile_samples(int variant) {
@@ -211,7 +248,7 @@ size_t tpgx_bid_smem_bytes(int variant, int hw) {
     const bid_variant& v = g_variants[variant];
     const int ts = 32 * v.K;
     size_t tile = ((size_t)hw * ts + 127) & ~(size_t)127;
-    return tile + (size_t)v.NW * TPGX_MAX_REGS * ts * 8 + (size_t)v.NW * TPGX_MAX_CONSTS * 8 + 16;
+    return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * TPGX_MAX_CONSTS * 8 + 16;
 }
 
 template <int K, int NW, int MINB>
@@ -238,8 +275,9 @@ cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant,
     case 1: return launch_bid_t<4, 12, 1>(p, nb_tiles, smem, trig, st);
     case 2: return launch_bid_t<2, 8, 2>(p, nb_tiles, smem, trig, st);
     case 3: return launch_bid_t<1, 16, 2>(p, nb_tiles, smem, trig, st);
-    case 4: return launch_bid_t<2, 24, 1>(p, nb_tiles, smem, trig, st);
-    default: return launch_bid_t<2, 14, 2>(p, nb_tiles, smem, trig, st);
+    case 4: return launch_bid_t<2, 20, 1>(p, nb_tiles, smem, trig, st);
+    case 5: return launch_bid_t<4, 8, 1>(p, nb_tiles, smem, trig, st);
+    default: return launch_bid_t<2, 12, 2>(p, nb_tiles, smem, trig, st);
     }
 }
 

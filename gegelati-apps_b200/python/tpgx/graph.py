@@ -266,6 +266,8 @@ def synthetic_graph(app="mnist", roots=500, edges=5, lines=20, depth=1, mix="uni
     allowed = None
     if mix == "scalar":
         allowed = [i for i, o in enumerate(opcodes) if o not in (A.OP_SOBEL_MAGN, A.OP_SOBEL_DIR)]
+    elif mix.startswith("ops:"):  # explicit instruction indices, e.g. "ops:0,1,2"
+        allowed = [int(v) for v in mix[4:].split(",")]
     elif mix == "arith":  # only exactly-rounded IEEE operations (no libm)
         allowed = [i for i, o in enumerate(opcodes) if o not in (A.OP_EXP, A.OP_LOG, A.OP_SOBEL_DIR, A.OP_COS, A.OP_SIN, A.OP_TAN)]
     widths = [roots] + [max(1, roots // 2)] * (depth - 1)
