@@ -53,11 +53,12 @@ __device__ __forceinline__ double u8_to_f64(uint32_t v) { return __hiloint2doubl
  * CTA = one sample tile (TS = 32*K samples, staged once by a bulk TMA copy) x one chunk of
  * programs; each warp repeatedly claims a program of the chunk and interprets it for the 32*K
  * samples of the tile (lane = K consecutive samples), so opcode dispatch is warp-uniform.
- * TPG registers live in shared memory as [warp][9][TS] doubles (slot 8 is a constant 0.0 that
- * stands for "never written" registers); lane accesses are conflict-free 8*K-byte vectors.  The
- * line words of a program are held one per lane and broadcast by shuffle.  One dispatch per line;
- * each case handles the lane's K samples.  Transcendentals and division are kept out of line so
- * the interpreter loop stays small in the instruction cache.                                      */
+ * TPG registers live in shared memory as [warp][9 slots][K/2][32 lanes][2] doubles (slot 8 is a
+ * constant 0.0 that stands for "never written" registers): every access is a conflict-free
+ * 16-byte-per-lane vector.  The line words of a program are held one per lane and broadcast by
+ * shuffle, one line ahead of execution.  Lines use the K1 "fused" opcodes (tpgx_internal.h): for
+ * the cheap instructions the operand kinds (register / pixel) are part of the opcode, so a line
+ * costs one indirect branch instead of a chain of kind tests.                                      */
 #define K1_SLOTS 9
 
 template <int K> __device__ __forceinline__ void ld_regs(const double* p, double (&v)[K]);
@@ -66,7 +67,7 @@ template <> __device__ __forceinline__ void ld_regs<2>(const double* p, double (
     double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y;
 }
 template <> __device__ __forceinline__ void ld_regs<4>(const double* p, double (&v)[4]) {
-    double2 t = *reinterpret_cast<const double2*>(p); double2 u = *reinterpret_cast<const double2*>(p + 2);
+    double2 t = *reinterpret_cast<const double2*>(p); double2 u = *reinterpret_cast<const double2*>(p + 64);
     v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
 }
 template <int K> __device__ __forceinline__ void st_regs(double* p, const double (&v)[K]);
@@ -76,7 +77,15 @@ template <> __device__ __forceinline__ void st_regs<2>(double* p, const double (
 }
 template <> __device__ __forceinline__ void st_regs<4>(double* p, const double (&v)[4]) {
     *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    *reinterpret_cast<double2*>(p + 64) = make_double2(v[2], v[3]);
+}
+/* global bid row: the lane's K samples are consecutive */
+template <int K> __device__ __forceinline__ void st_bid(double* p, const double (&v)[K]) {
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+        if (K == 1) p[0] = v[0];
+        else *reinterpret_cast<double2*>(p + k) = make_double2(v[k], v[k + 1 < K ? k + 1 : k]);
+    }
 }
 template <int K> __device__ __forceinline__ void ld_px(const uint8_t* p, uint32_t (&v)[K]);
 template <> __device__ __forceinline__ void ld_px<1>(const uint8_t* p, uint32_t (&v)[1]) { v[0] = *p; }
@@ -86,29 +95,12 @@ template <> __device__ __forceinline__ void ld_px<2>(const uint8_t* p, uint32_t 
 template <> __device__ __forceinline__ void ld_px<4>(const uint8_t* p, uint32_t (&v)[4]) {
     uchar4 t = *reinterpret_cast<const uchar4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
-
-/* a double operand: a TPG register (or the zero slot) or one pixel of each of the lane's K samples */
-template <int K>
-__device__ __forceinline__ void fetch_double(uint32_t f, double (&v)[K], const double* regs_lane, const uint8_t* tile_lane) {
-    constexpr int TS = 32 * K;
-    if (f & (TPGX_KIND_SRC0 << 10)) {
-        uint32_t px[K];
-        ld_px<K>(tile_lane + (f & 1023u) * TS, px);
+template <int K> __device__ __forceinline__ void ld_px_f64(const uint8_t* p, double (&v)[K]) {
+    uint32_t px[K];
+    ld_px<K>(p, px);
 #pragma unroll
-        for (int k = 0; k < K; k++) v[k] = u8_to_f64(px[k]);
-    } else {
-        ld_regs<K>(regs_lane + (f & 15u) * TS, v);
-    }
+    for (int k = 0; k < K; k++) v[k] = u8_to_f64(px[k]);
 }
-
-__device__ __forceinline__ double k1_exp(double x) { return tpgx_math::exp(x); }
-__device__ __forceinline__ double k1_log(double x) { return tpgx_math::log(x); }
-__device__ __forceinline__ double k1_atan(double x) { return tpgx_math::atan(x); }
-__device__ __noinline__ double k1_sin(double x) { return tpgx_math::sin(x); }
-__device__ __noinline__ double k1_cos(double x) { return tpgx_math::cos(x); }
-__device__ __noinline__ double k1_tan(double x) { return tpgx_math::tan(x); }
-__device__ __forceinline__ double k1_div(double a, double b) { return tpgx_math::xdiv(a, b); }
-__device__ __noinline__ double k1_fmodg(double a, double b) { return b != 0.0 ? fmod(a, b) : DBL_MIN; }
 
 template <int K, int NW, int MINB, bool TRIG>
 __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_params p) {
@@ -132,7 +124,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
         mbar_expect_tx(bar, (uint32_t)tile_bytes);
         tma_load_1d(tile, p.tiles + (size_t)blockIdx.x * tile_bytes, (uint32_t)tile_bytes, bar);
     }
-    double* regs_lane = regs + warp * (K1_SLOTS * TS) + lane * K;
+    double* regs_lane = regs + warp * (K1_SLOTS * TS) + lane * (K == 1 ? 1 : 2);
     {
         double z[K];
 #pragma unroll
@@ -167,76 +159,106 @@ __global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_
         for (int base = 0; base < n; base += 32) {
             const uint32_t mine = (base + lane < n) ? __ldg(p.code + cb + base + lane) : 0u;
             const int m = min(32, n - base);
+            uint32_t w = __shfl_sync(0xffffffffu, mine, 0);
 #pragma unroll 1
             for (int j = 0; j < m; j++) {
-                const uint32_t w = __shfl_sync(0xffffffffu, mine, j);
-                const uint32_t op = w & 31u;
-                const uint32_t fa = (w >> 8) & 0xfffu, fb = w >> 20;
-                if (op >= TPGX_OP_SOBEL_MAGN) {
-                    /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
-                       of the reference's double expression is an exactly representable integer */
-                    const uint8_t* t = tile_lane + (fa & 1023u) * TS;
-                    uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
-                    ld_px<K>(t, a00); ld_px<K>(t + TS, a01); ld_px<K>(t + 2 * TS, a02);
-                    ld_px<K>(t + wrow, a10); ld_px<K>(t + wrow + 2 * TS, a12);
-                    ld_px<K>(t + 2 * wrow, a20); ld_px<K>(t + 2 * wrow + TS, a21); ld_px<K>(t + 2 * wrow + 2 * TS, a22);
+                const uint32_t w_next = __shfl_sync(0xffffffffu, mine, j + 1); /* next line, one iteration ahead */
+                const uint32_t la = (w >> 10) & 1023u, lb = (w >> 20) & 1023u;
+                const double* ra = regs_lane + la * TS;   /* operand as a register slot */
+                const double* rb = regs_lane + lb * TS;
+                const uint8_t* pa = tile_lane + la * TS;  /* operand as a pixel */
+                const uint8_t* pb = tile_lane + lb * TS;
+                double a[K], b[K];
+#define K1_RR ld_regs<K>(ra, a); ld_regs<K>(rb, b);
+#define K1_PR ld_px_f64<K>(pa, a); ld_regs<K>(rb, b);
+#define K1_RP ld_regs<K>(ra, a); ld_px_f64<K>(pb, b);
+#define K1_PP ld_px_f64<K>(pa, a); ld_px_f64<K>(pb, b);
+#define K1_R ld_regs<K>(ra, a);
+#define K1_P ld_px_f64<K>(pa, a);
+#define K1_EACH(expr) { _Pragma("unroll") for (int k = 0; k < K; k++) { const double x = a[k], y = b[k]; (void)x; (void)y; res[k] = (expr); } } break;
+#define K1_BIN(id, expr)                                     \
+    case (id) * 4 + 0: K1_RR K1_EACH(expr)                    \
+    case (id) * 4 + 1: K1_PR K1_EACH(expr)                    \
+    case (id) * 4 + 2: K1_RP K1_EACH(expr)                    \
+    case (id) * 4 + 3: K1_PP K1_EACH(expr)
+#define K1_UN(id, expr)                                      \
+    case TPGX_K1_UNARY0 + (id) * 2 + 0: K1_R K1_EACH(expr)    \
+    case TPGX_K1_UNARY0 + (id) * 2 + 1: K1_P K1_EACH(expr)
+                switch (w & 127u) {
+                K1_BIN(0, x - y)
+                K1_BIN(1, x + y)
+                K1_BIN(2, x * y)
+                K1_BIN(3, (x < y) ? y : x)
+                K1_BIN(4, x < y ? -x : x)
+                K1_UN(0, (x == 0.0) ? 10.0 : 0.0)
+                K1_UN(1, (x == -1.0) ? 10.0 : 0.0)
+                K1_UN(2, (x == 1.0) ? 10.0 : 0.0)
+                K1_UN(3, (x >= 15.0) ? 10.0 : 0.0)
+                K1_UN(4, TPGX_PI)
+                default: {
+                    /* heavy instructions: operand kinds in bits 30/31, then one shared body */
+                    const uint32_t hop = w & 127u;
+                    if (hop >= TPGX_K1_SOBEL_MAGN) {
+                        /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
+                           of the reference's double expression is an exactly representable integer */
+                        uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
+                        ld_px<K>(pa, a00); ld_px<K>(pa + TS, a01); ld_px<K>(pa + 2 * TS, a02);
+                        ld_px<K>(pa + wrow, a10); ld_px<K>(pa + wrow + 2 * TS, a12);
+                        ld_px<K>(pa + 2 * wrow, a20); ld_px<K>(pa + 2 * wrow + TS, a21); ld_px<K>(pa + 2 * wrow + 2 * TS, a22);
 #pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        const int gx = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
-                        const int gy = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
-                        if (op == TPGX_OP_SOBEL_MAGN) res[k] = tpgx_math::xsqrt_nonneg((double)(gx * gx + gy * gy));
-                        else res[k] = k1_atan(k1_div((double)gy, (double)gx));
+                        for (int k = 0; k < K; k++) {
+                            const int gx = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
+                            const int gy = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
+                            if (hop == TPGX_K1_SOBEL_MAGN) res[k] = tpgx_math::xsqrt_nonneg((double)(gx * gx + gy * gy));
+                            else res[k] = tpgx_math::atan(tpgx_math::xdiv((double)gy, (double)gx));
+                        }
+                        break;
                     }
-                } else {
-                    double a[K], b[K];
-                    fetch_double<K>(fa, a, regs_lane, tile_lane);
-                    if ((TPGX_MASK_B_DOUBLE >> op) & 1u) fetch_double<K>(fb, b, regs_lane, tile_lane);
-                    else if (op == TPGX_OP_MULC) {
-                        const double c = my_const[fb & 15u];
+                    if (w & 0x40000000u) { K1_P } else { K1_R }
+                    if (hop == TPGX_K1_DIV || hop == TPGX_K1_FMODG) {
+                        if (w & 0x80000000u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
+                    } else if (hop == TPGX_K1_MULC) {
+                        const double c = my_const[lb & 7u];
 #pragma unroll
                         for (int k = 0; k < K; k++) b[k] = c;
                     }
-#define K1_EACH(expr)                              \
-    {                                              \
-        _Pragma("unroll") for (int k = 0; k < K; k++) { const double x = a[k], y = b[k]; (void)y; res[k] = (expr); } \
-    }                                              \
-    break;
-                    switch (op) {
-                    case TPGX_OP_SUB: K1_EACH(x - y)
-                    case TPGX_OP_ADD: K1_EACH(x + y)
-                    case TPGX_OP_MUL: K1_EACH(x * y)
-                    case TPGX_OP_DIV: K1_EACH(k1_div(x, y))
-                    case TPGX_OP_MAX: K1_EACH((x < y) ? y : x)
-                    case TPGX_OP_EXP: K1_EACH(k1_exp(x))
-                    case TPGX_OP_LOG: K1_EACH(k1_log(x))
-                    case TPGX_OP_COS: K1_EACH(TRIG ? k1_cos(x) : 0.0)
-                    case TPGX_OP_SIN: K1_EACH(TRIG ? k1_sin(x) : 0.0)
-                    case TPGX_OP_TAN: K1_EACH(TRIG ? k1_tan(x) : 0.0)
-                    case TPGX_OP_PI: K1_EACH(TPGX_PI)
-                    case TPGX_OP_MULC: K1_EACH(k1_div(x * y, 10.0))
-                    case TPGX_OP_FMODG: K1_EACH(k1_fmodg(x, y))
-                    case TPGX_OP_EQ0: K1_EACH((x == 0.0) ? 10.0 : 0.0)
-                    case TPGX_OP_EQM1: K1_EACH((x == -1.0) ? 10.0 : 0.0)
-                    case TPGX_OP_EQ1: K1_EACH((x == 1.0) ? 10.0 : 0.0)
-                    case TPGX_OP_GE15: K1_EACH((x >= 15.0) ? 10.0 : 0.0)
-                    case TPGX_OP_COND: K1_EACH(x < y ? -x : x)
+                    switch (hop) {
+                    case TPGX_K1_DIV: K1_EACH(tpgx_math::xdiv(x, y))
+                    case TPGX_K1_MULC: K1_EACH(tpgx_math::xdiv(x * y, 10.0))
+                    case TPGX_K1_FMODG: K1_EACH(y != 0.0 ? fmod(x, y) : DBL_MIN)
+                    case TPGX_K1_EXP: K1_EACH(tpgx_math::exp(x))
+                    case TPGX_K1_LOG: K1_EACH(tpgx_math::log(x))
+                    case TPGX_K1_COS: K1_EACH(TRIG ? tpgx_math::cos(x) : 0.0)
+                    case TPGX_K1_SIN: K1_EACH(TRIG ? tpgx_math::sin(x) : 0.0)
+                    case TPGX_K1_TAN: K1_EACH(TRIG ? tpgx_math::tan(x) : 0.0)
                     default: break;
                     }
-#undef K1_EACH
+                    break;
                 }
-                st_regs<K>(regs_lane + ((w >> 5) & 7u) * TS, res);
+                }
+#undef K1_RR
+#undef K1_PR
+#undef K1_RP
+#undef K1_PP
+#undef K1_R
+#undef K1_P
+#undef K1_EACH
+#undef K1_BIN
+#undef K1_UN
+                st_regs<K>(regs_lane + ((w >> 7) & 7u) * TS, res);
+                w = w_next;
             }
         }
         /* [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
 #pragma unroll
         for (int k = 0; k < K; k++)
             if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
-        st_regs<K>(p.bid + (size_t)row * p.row_stride + (size_t)blockIdx.x * TS + lane * K, res);
+        st_bid<K>(p.bid + (size_t)row * p.row_stride + (size_t)blockIdx.x * TS + lane * K, res);
     }
 }
 
 struct bid_variant { int K, NW, MINB; };
-static const bid_variant g_variants[] = {{2, 12, 2}, {4, 12, 1}, {2, 8, 2}, {1, 16, 2}, {2, 20, 1}, {4, 8, 1}};
+static const bid_variant g_variants[] = {{2, 32, 1}, {4, 12, 1}, {2, 16, 1}, {1, 16, 2}, {2, 12, 2}, {4, 8, 1}, {2, 24, 1}, {4, 10, 1}};
 static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 int tpgx_bid_tile_samples(int variant) {
@@ -273,11 +295,13 @@ cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant,
     const size_t smem = tpgx_bid_smem_bytes(variant, p.hw);
     switch (variant) {
     case 1: return launch_bid_t<4, 12, 1>(p, nb_tiles, smem, trig, st);
-    case 2: return launch_bid_t<2, 8, 2>(p, nb_tiles, smem, trig, st);
+    case 2: return launch_bid_t<2, 16, 1>(p, nb_tiles, smem, trig, st);
     case 3: return launch_bid_t<1, 16, 2>(p, nb_tiles, smem, trig, st);
-    case 4: return launch_bid_t<2, 20, 1>(p, nb_tiles, smem, trig, st);
+    case 4: return launch_bid_t<2, 12, 2>(p, nb_tiles, smem, trig, st);
     case 5: return launch_bid_t<4, 8, 1>(p, nb_tiles, smem, trig, st);
-    default: return launch_bid_t<2, 12, 2>(p, nb_tiles, smem, trig, st);
+    case 6: return launch_bid_t<2, 24, 1>(p, nb_tiles, smem, trig, st);
+    case 7: return launch_bid_t<4, 10, 1>(p, nb_tiles, smem, trig, st);
+    default: return launch_bid_t<2, 32, 1>(p, nb_tiles, smem, trig, st);
     }
 }
 

@@ -60,7 +60,7 @@ struct tpgx_ctx {
     int variant = 0;
     size_t bid_budget = (size_t)16 << 30;
 
-    DevBuf d_code, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
+    DevBuf d_code, d_code_k1, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[8];
     const uint8_t* obs_dev = nullptr;    /* raw observations [nb_obs][hw] (ours or the caller's) */
@@ -205,15 +205,15 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             tpgx_bid_params bp{};
             bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * hw * ts;
             bp.hw = hw; bp.width = ctx->obs_width;
-            bp.code = ctx->d_code.as<uint32_t>();
+            bp.code = ctx->d_code_k1.as<uint32_t>();
             bp.prog_offset = ctx->d_prog_off.as<int32_t>();
             bp.constants = ctx->d_consts.as<double>();
             bp.nb_constants = ctx->cfg.nb_constants;
             bp.active_prog = ctx->d_active.as<int32_t>();
             bp.nb_active = nA;
-            /* enough CTAs for ~10 waves of 148 SMs x 2 resident CTAs, at least 4 programs per warp */
-            int chunks = (int)std::max<int64_t>(1, (148 * 2 * 10 + nt - 1) / nt);
-            chunks = std::min(chunks, std::max(1, nA / 64));
+            /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 programs per warp */
+            int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
+            chunks = std::min(chunks, std::max(1, nA / 128));
             bp.progs_per_chunk = (nA + chunks - 1) / chunks;
             bp.bid = ctx->d_bid.as<double>();
             bp.row_stride = (long long)nt * ts;
@@ -294,7 +294,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* all[] = {&ctx->d_code, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
+    DevBuf* all[] = {&ctx->d_code, &ctx->d_code_k1, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
                      &ctx->d_counters, &ctx->d_status};
@@ -345,6 +345,12 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
     std::vector<int32_t> edge_lines(F.nb_edges);
     for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }
     if ((st = upload(ctx, ctx->d_code, F.code.data(), F.code.size() * 4)) != TPGX_OK) return st;
+    {
+        std::vector<uint32_t> k1(F.code.size());
+        for (size_t i = 0; i < k1.size(); i++) k1[i] = tpgx_k1_word(F.code[i]);
+        if ((st = upload(ctx, ctx->d_code_k1, k1.data(), k1.size() * 4)) != TPGX_OK) return st;
+        CU(cudaStreamSynchronize(ctx->stream)); /* k1 is a local */
+    }
     if ((st = upload(ctx, ctx->d_prog_off, F.prog_offset.data(), F.prog_offset.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_consts, F.constants.data(), F.constants.size() * 8)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_team_off, F.team_edge_offset.data(), F.team_edge_offset.size() * 4)) != TPGX_OK) return st;

@@ -43,6 +43,48 @@ static inline uint32_t tpgx_pack_line(uint32_t op, uint32_t dst, uint32_t ka, ui
     return (op & 31u) | ((dst & 7u) << 5) | (((ka << 10) | (la & 1023u)) << 8) | (((kb << 10) | (lb & 1023u)) << 20);
 }
 
+/* ---- K1 "fused" line word (built from the generic word by tpgx_k1_word) ---------------------------
+ *   [ 6: 0] K1 opcode   [ 9: 7] destination register   [19:10] operand A loc   [29:20] operand B loc
+ *   [30] A is a pixel (heavy opcodes)   [31] B is a pixel (heavy opcodes)
+ * Cheap instructions carry the operand kinds in the opcode: binary id*4 + (A pixel) + 2*(B pixel),
+ * unary TPGX_K1_UNARY0 + id*2 + (A pixel).  A register operand's loc is its slot (8 = zero slot). */
+#define TPGX_K1_UNARY0 20
+enum {
+    TPGX_K1_DIV = 32, TPGX_K1_MULC, TPGX_K1_FMODG, TPGX_K1_EXP, TPGX_K1_LOG, TPGX_K1_COS, TPGX_K1_SIN, TPGX_K1_TAN,
+    TPGX_K1_SOBEL_MAGN = 48, TPGX_K1_SOBEL_DIR = 49, TPGX_K1_INVALID = 127
+};
+
+static inline uint32_t tpgx_k1_word(uint32_t w) {
+    const uint32_t op = w & 31u, dst = (w >> 5) & 7u;
+    const uint32_t fa = (w >> 8) & 0xfffu, fb = w >> 20;
+    const uint32_t pa = (fa >> 10) == TPGX_KIND_SRC0, pb = (fb >> 10) == TPGX_KIND_SRC0;
+    uint32_t k1;
+    switch (op) {
+    case TPGX_OP_SUB: k1 = 0 * 4 + pa + 2 * pb; break;
+    case TPGX_OP_ADD: k1 = 1 * 4 + pa + 2 * pb; break;
+    case TPGX_OP_MUL: k1 = 2 * 4 + pa + 2 * pb; break;
+    case TPGX_OP_MAX: k1 = 3 * 4 + pa + 2 * pb; break;
+    case TPGX_OP_COND: k1 = 4 * 4 + pa + 2 * pb; break;
+    case TPGX_OP_EQ0: k1 = TPGX_K1_UNARY0 + 0 * 2 + pa; break;
+    case TPGX_OP_EQM1: k1 = TPGX_K1_UNARY0 + 1 * 2 + pa; break;
+    case TPGX_OP_EQ1: k1 = TPGX_K1_UNARY0 + 2 * 2 + pa; break;
+    case TPGX_OP_GE15: k1 = TPGX_K1_UNARY0 + 3 * 2 + pa; break;
+    case TPGX_OP_PI: k1 = TPGX_K1_UNARY0 + 4 * 2 + pa; break;
+    case TPGX_OP_DIV: k1 = TPGX_K1_DIV; break;
+    case TPGX_OP_MULC: k1 = TPGX_K1_MULC; break;
+    case TPGX_OP_FMODG: k1 = TPGX_K1_FMODG; break;
+    case TPGX_OP_EXP: k1 = TPGX_K1_EXP; break;
+    case TPGX_OP_LOG: k1 = TPGX_K1_LOG; break;
+    case TPGX_OP_COS: k1 = TPGX_K1_COS; break;
+    case TPGX_OP_SIN: k1 = TPGX_K1_SIN; break;
+    case TPGX_OP_TAN: k1 = TPGX_K1_TAN; break;
+    case TPGX_OP_SOBEL_MAGN: k1 = TPGX_K1_SOBEL_MAGN; break;
+    case TPGX_OP_SOBEL_DIR: k1 = TPGX_K1_SOBEL_DIR; break;
+    default: k1 = TPGX_K1_INVALID; break; /* int-typed instructions never reach K1 (no i32 source) */
+    }
+    return k1 | (dst << 7) | ((fa & 1023u) << 10) | ((fb & 1023u) << 20) | (pa << 30) | (pb << 31);
+}
+
 enum tpgx_operand_type { TPGX_T_NONE = 0, TPGX_T_D = 1, TPGX_T_I = 2, TPGX_T_C = 3, TPGX_T_W = 4 };
 
 struct tpgx_op_info {
