@@ -149,11 +149,15 @@ def run_reference(a):
         "data": "synthetic", "config": workload_config(a, 1), "instr_per_s": lines / dt,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), flush=True)
 
 
 def main():
     a = parse()
+    # keep stdout clean for the single JSON line: libraries (NCCL prints its version banner on fd 1) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if a.impl == "reference":
         return run_reference(a)
 
@@ -315,7 +319,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": 3 * a.steps,
             "clocks": sampler.result(), "wall_s_timed_region": wall, "score_checksum": score_check,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
