@@ -1,0 +1,343 @@
+/*
+ * k1_bid.cu — K1, the bid interpreter (sm_100a).
+ *
+ * Replaces [UP] Program::ProgramExecutionEngine::executeProgram + Data::*::getDataAt + the apps'
+ * instruction lambdas ([REF] mnist/src/main.cpp:47-88) for a whole generation at once:
+ * bid[row][s] = register 0 of program `row` on observation s, NaN mapped to -inf like
+ * [UP] TPGExecutionEngine::evaluateEdge.
+ *
+ * Mapping.  CTA = one sample tile (TS = 32*K samples, pixel-major uint8, staged ONCE by a bulk TMA
+ * copy) x one chunk of programs.  Each warp repeatedly claims a program of the chunk and interprets
+ * it for all TS samples of the tile: lane = K consecutive samples, so instruction dispatch is
+ * warp-uniform and never diverges.  Two builds of the kernel: the MNIST instruction set only
+ * (EXT = false: sub add mul div max exp ln multByConst sobelMagn sobelDir) and the extended one with
+ * every double-typed instruction of the five apps.
+ *
+ * Where the instructions went (ncu, round 1: the previous version issued 137 warp instructions per
+ * line of 64 samples, 26 of them FP64 arithmetic) and what this version does about it:
+ *   - decode: lines arrive pre-decoded as 16-byte quads (tpgx_k1_line): handler id, operand byte
+ *     offsets, destination byte offset.  No shifts, masks or multiplies per line.
+ *   - fetch: the quads of a program sit in a per-warp shared-memory buffer and are read with one
+ *     broadcast LDS.128 per line.  The NEXT program's quads are copied global -> shared with
+ *     cp.async into the warp's second buffer while the current program runs, so switching programs
+ *     costs a wait + __syncwarp and holds no registers.
+ *   - every handler loads its operands, computes and stores its result by itself, so no values
+ *     merge after the dispatch (the previous version spent ~8 register moves per line there); the
+ *     bid is read back from register slot 0 at the end of the program.
+ *   - TPG registers live in shared memory as [warp][9 slots][K/2][32 lanes][2] doubles (slot 8 is
+ *     a constant 0.0 = "never written", so no per-program clear): every access is a conflict-free
+ *     16-byte-per-lane vector.
+ *   - libm and division are straight-line per sample with one shared rare branch per K samples
+ *     (tpgx_math.h), so the K chains of a lane overlap; coefficients come from constant memory.
+ */
+#include <cuda_runtime.h>
+
+#include "dev_ops.cuh"
+#include "kernels.cuh"
+
+/* ------------------------------------------------------------------------------------------------
+ * small PTX helpers: mbarrier + 1-D bulk TMA copy (cp.async.bulk -> SASS UBLKCP)                  */
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+
+/* exact uint8 -> double without the conversion pipe: 2^52 + v has v in its low mantissa bits */
+__device__ __forceinline__ double u8_to_f64(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
+
+#define K1_SLOTS 9
+#define K1_CODE_QUADS 32 /* TPGX_K1_CQ constant quads + TPGX_K1_CAPL lines; two such buffers per warp */
+
+template <int K> __device__ __forceinline__ void ld_regs(const uint8_t* p, double (&v)[K]);
+template <> __device__ __forceinline__ void ld_regs<2>(const uint8_t* p, double (&v)[2]) {
+    const double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void ld_regs<4>(const uint8_t* p, double (&v)[4]) {
+    const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 512);
+    v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+}
+template <int K> __device__ __forceinline__ void st_regs(uint8_t* p, const double (&v)[K]);
+template <> __device__ __forceinline__ void st_regs<2>(uint8_t* p, const double (&v)[2]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void st_regs<4>(uint8_t* p, const double (&v)[4]) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 512) = make_double2(v[2], v[3]);
+}
+template <int K> __device__ __forceinline__ void ld_px(const uint8_t* p, uint32_t (&v)[K]);
+template <> __device__ __forceinline__ void ld_px<2>(const uint8_t* p, uint32_t (&v)[2]) {
+    const uchar2 t = *reinterpret_cast<const uchar2*>(p); v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void ld_px<4>(const uint8_t* p, uint32_t (&v)[4]) {
+    const uchar4 t = *reinterpret_cast<const uchar4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <int K> __device__ __forceinline__ void ld_px_f64(const uint8_t* p, double (&v)[K]) {
+    uint32_t px[K];
+    ld_px<K>(p, px);
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = u8_to_f64(px[k]);
+}
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int K, int NW, bool EXT>
+__global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_params p) {
+    constexpr int TS = 32 * K;
+    static_assert(K == 2 || K == 4, "lane owns 2 or 4 samples");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tile_bytes = p.hw * TS;
+    uint8_t* tile = smem;
+    uint8_t* regs = smem + ((tile_bytes + 127) & ~127);
+    uint4* codeb = reinterpret_cast<uint4*>(regs + NW * K1_SLOTS * TS * 8);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(codeb + NW * 2 * K1_CODE_QUADS);
+    int* s_next = reinterpret_cast<int*>(bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        *s_next = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, (uint32_t)tile_bytes);
+        tma_load_1d(tile, p.tiles + (size_t)blockIdx.x * tile_bytes, (uint32_t)tile_bytes, bar);
+    }
+    uint8_t* const regs_lane = regs + warp * (K1_SLOTS * TS * 8) + lane * 16;
+    const uint8_t* const tile_lane = tile + lane * K;
+    uint4* const mycode = codeb + warp * (2 * K1_CODE_QUADS);
+    {
+        double z[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) z[k] = 0.0;
+        st_regs<K>(regs_lane + TPGX_LOC_ZERO * TS * 8, z);
+    }
+
+    const int chunk_begin = blockIdx.y * p.progs_per_chunk;
+    const int chunk_n = min(p.progs_per_chunk, p.nb_active - chunk_begin);
+    const int wrow = p.width * TS;
+    const uint4* __restrict__ stream = p.stream;
+
+    auto claim = [&]() {
+        int i = 0;
+        if (lane == 0) i = atomicAdd(s_next, 1);
+        return __shfl_sync(0xffffffffu, i, 0);
+    };
+    auto load_desc = [&](int i) { return (i < chunk_n) ? __ldg(p.desc + chunk_begin + i) : make_int2(0, 0); };
+    /* asynchronous copy of a program's constants + first TPGX_K1_CAPL lines into a code buffer */
+    auto stage = [&](uint4* buf, const int2 d) {
+        if (lane < TPGX_K1_CQ + min(d.y, TPGX_K1_CAPL)) cp_async16(buf + lane, stream + d.x + lane);
+        cp_async_commit();
+    };
+    int i0 = claim();
+    int2 d0 = load_desc(i0);
+    int cur = 0;
+    stage(mycode, d0);
+    mbar_wait(bar, 0);
+
+    while (i0 < chunk_n) {
+        const int i1 = claim();
+        const int2 d1 = load_desc(i1);
+        cp_async_wait_all();
+        __syncwarp();
+        uint4* const code = mycode + cur * K1_CODE_QUADS;
+        stage(mycode + (cur ^ 1) * K1_CODE_QUADS, d1); /* next program's code: in flight while this one runs */
+
+        const int n = d0.y;
+        const uint8_t* const cbase = reinterpret_cast<const uint8_t*>(code); /* program constants at the head of the buffer */
+        for (int done = 0; done < n;) {
+            const int m = min(n - done, TPGX_K1_CAPL);
+            if (done > 0) { /* programs longer than one buffer: stage the next TPGX_K1_CAPL lines synchronously */
+                __syncwarp();
+                if (lane < m) code[TPGX_K1_CQ + lane] = __ldg(stream + d0.x + TPGX_K1_CQ + done + lane);
+                __syncwarp();
+            }
+            const uint4* lp = code + TPGX_K1_CQ;
+#pragma unroll 1
+            for (int j = 0; j < m; j++) {
+                const uint4 ln = lp[j];                 /* broadcast LDS.128: handler, operand offsets, destination offset */
+                const uint8_t* ra = regs_lane + ln.y;  /* operand as a register slot */
+                const uint8_t* rb = regs_lane + ln.z;
+                const uint8_t* pa = tile_lane + ln.y;  /* operand as a pixel */
+                const uint8_t* pb = tile_lane + ln.z;
+                uint8_t* const rd = regs_lane + ln.w;  /* destination register slot */
+                /* dispatch on single bits of the handler id; every handler loads, computes and stores by
+                   itself, so no values merge afterwards */
+                const uint32_t h = ln.x;
+                const uint32_t op = (h >> 2) & 15u;
+                double a[K], b[K], r[K];
+                if (!(h & TPGX_K1H_HEAVY)) {
+                    /* ---- cheap class: operands by kind, then one IEEE operation ---- */
+                    if (h & 1u) ld_px_f64<K>(pa, a); else ld_regs<K>(ra, a);
+                    if (EXT && op >= TPGX_K1C_EQ0) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) {
+                            const double x = a[k];
+                            r[k] = op == TPGX_K1C_EQ0 ? ((x == 0.0) ? 10.0 : 0.0) : op == TPGX_K1C_EQM1 ? ((x == -1.0) ? 10.0 : 0.0)
+                                 : op == TPGX_K1C_EQ1 ? ((x == 1.0) ? 10.0 : 0.0) : op == TPGX_K1C_GE15 ? ((x >= 15.0) ? 10.0 : 0.0) : TPGX_PI;
+                        }
+                    } else {
+                        if (h & 2u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
+                        if (op == TPGX_K1C_SUB) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) r[k] = a[k] - b[k];
+                        } else if (op == TPGX_K1C_ADD) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) r[k] = a[k] + b[k];
+                        } else if (op == TPGX_K1C_MUL) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) r[k] = a[k] * b[k];
+                        } else if (!EXT || op == TPGX_K1C_MAX) {
+#pragma unroll
+                            for (int k = 0; k < K; k++) r[k] = (a[k] < b[k]) ? b[k] : a[k];
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; k++) r[k] = (a[k] < b[k]) ? -a[k] : a[k];
+                        }
+                    }
+                    st_regs<K>(rd, r);
+                } else if (op == TPGX_K1X_SOBEL_MAGN || op == TPGX_K1X_SOBEL_DIR) {
+                    /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
+                       of the reference's double expression is an exactly representable integer */
+                    uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
+                    ld_px<K>(pa, a00); ld_px<K>(pa + TS, a01); ld_px<K>(pa + 2 * TS, a02);
+                    ld_px<K>(pa + wrow, a10); ld_px<K>(pa + wrow + 2 * TS, a12);
+                    ld_px<K>(pa + 2 * wrow, a20); ld_px<K>(pa + 2 * wrow + TS, a21); ld_px<K>(pa + 2 * wrow + 2 * TS, a22);
+                    int gx[K], gy[K];
+#pragma unroll
+                    for (int k = 0; k < K; k++) {
+                        gx[k] = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
+                        gy[k] = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
+                    }
+                    if (op == TPGX_K1X_SOBEL_MAGN) {
+#pragma unroll
+                        for (int k = 0; k < K; k++) r[k] = tpgx_math::xsqrt_nonneg((double)(gx[k] * gx[k] + gy[k] * gy[k]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; k++) r[k] = tpgx_math::atan(tpgx_math::xdiv_small_int(gy[k], gx[k]));
+                    }
+                    st_regs<K>(rd, r);
+                } else {
+                    /* ---- heavy class: division and libm ---- */
+                    if (h & 1u) ld_px_f64<K>(pa, a); else ld_regs<K>(ra, a);
+                    if (op == TPGX_K1X_EXP) {
+                        tpgx_math::exp_k<K>(a, r);
+                    } else if (op == TPGX_K1X_LOG) {
+                        tpgx_math::log_k<K>(a, r);
+                    } else if (op == TPGX_K1X_DIV || op == TPGX_K1X_MULC) {
+                        if (op == TPGX_K1X_MULC) {
+                            const double c = *reinterpret_cast<const double*>(cbase + ln.z);
+#pragma unroll
+                            for (int k = 0; k < K; k++) { a[k] = a[k] * c; b[k] = 10.0; }   /* (a * c) / 10.0 */
+                        } else {
+                            if (h & 2u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
+                        }
+                        tpgx_math::xdiv_k<K>(a, b, r);
+                    } else if (EXT) {
+                        if (op == TPGX_K1X_FMODG) {
+                            if (h & 2u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
+#pragma unroll
+                            for (int k = 0; k < K; k++) r[k] = (b[k] != 0.0) ? fmod(a[k], b[k]) : DBL_MIN;
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < K; k++)
+                                r[k] = op == TPGX_K1X_COS ? tpgx_math::cos(a[k]) : op == TPGX_K1X_SIN ? tpgx_math::sin(a[k]) : tpgx_math::tan(a[k]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < K; k++) r[k] = 0.0;
+                    }
+                    st_regs<K>(rd, r);
+                }
+            }
+            done += m;
+        }
+        /* the last effective line of a program writes register 0 (that is what makes it effective);
+           an empty program leaves the 0.0 of [UP] executeProgram's register reset */
+        double res[K];
+        ld_regs<K>(regs_lane + (n > 0 ? 0 : TPGX_LOC_ZERO * TS * 8), res);
+        /* [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
+#pragma unroll
+        for (int k = 0; k < K; k++)
+            if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
+        double* out = p.bid + (size_t)(chunk_begin + i0) * p.row_stride + (size_t)blockIdx.x * TS + lane * K;
+#pragma unroll
+        for (int k = 0; k < K; k += 2) *reinterpret_cast<double2*>(out + k) = make_double2(res[k], res[k + 1]);
+
+        i0 = i1; d0 = d1; cur ^= 1;
+    }
+    cp_async_wait_all();
+}
+
+struct bid_variant { int K, NW; };
+static const bid_variant g_variants[] = {{2, 32}, {4, 12}, {4, 10}, {2, 28}, {2, 24}, {2, 16}, {4, 8}};
+static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
+
+int tpgx_bid_tile_samples(int variant) {
+    if (variant < 0 || variant >= g_nb_variants) variant = 0;
+    return 32 * g_variants[variant].K;
+}
+size_t tpgx_bid_smem_bytes(int variant, int hw) {
+    if (variant < 0 || variant >= g_nb_variants) variant = 0;
+    const bid_variant& v = g_variants[variant];
+    const int ts = 32 * v.K;
+    const size_t tile = ((size_t)hw * ts + 127) & ~(size_t)127;
+    return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * 2 * K1_CODE_QUADS * 16 + 16;
+}
+
+template <int K, int NW>
+static cudaError_t launch_bid_t(const tpgx_bid_params& p, int nb_tiles, size_t smem, bool ext, cudaStream_t st) {
+    const int chunks = (p.nb_active + p.progs_per_chunk - 1) / p.progs_per_chunk;
+    dim3 grid(nb_tiles, chunks);
+    cudaError_t e;
+    if (ext) {
+        e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tpgx_bid_kernel<K, NW, true><<<grid, NW * 32, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tpgx_bid_kernel<K, NW, false><<<grid, NW * 32, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool ext, cudaStream_t st) {
+    if (variant < 0 || variant >= g_nb_variants) variant = 0;
+    const size_t smem = tpgx_bid_smem_bytes(variant, p.hw);
+    switch (variant) {
+    case 1: return launch_bid_t<4, 12>(p, nb_tiles, smem, ext, st);
+    case 2: return launch_bid_t<4, 10>(p, nb_tiles, smem, ext, st);
+    case 3: return launch_bid_t<2, 28>(p, nb_tiles, smem, ext, st);
+    case 4: return launch_bid_t<2, 24>(p, nb_tiles, smem, ext, st);
+    case 5: return launch_bid_t<2, 16>(p, nb_tiles, smem, ext, st);
+    case 6: return launch_bid_t<4, 8>(p, nb_tiles, smem, ext, st);
+    default: return launch_bid_t<2, 32>(p, nb_tiles, smem, ext, st);
+    }
+}

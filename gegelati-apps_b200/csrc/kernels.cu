@@ -2,8 +2,7 @@
  * kernels.cu — sm_100a kernels of the classification (MNIST-shape) path.
  *
  *   K0 pack      : gather + transpose sample-major uint8 observations into pixel-major tiles
- *   K1 bid       : warp = one program, lane = K samples; replaces
- *                  [UP] Program::ProgramExecutionEngine::executeProgram (+ Data::*::getDataAt)
+ *   (K1, the bid interpreter, lives in k1_bid.cu)
  *   K2 traverse  : thread = (root, sample); replaces [UP] TPG::TPGExecutionEngine::executeFromRoot /
  *                  evaluateTeam and [UP] ClassificationLearningEnvironment::doAction (confusion table)
  *   K3 score     : thread = root; replaces the F1 reduction of
@@ -15,295 +14,6 @@
 
 #include "dev_ops.cuh"
 #include "kernels.cuh"
-
-/* ------------------------------------------------------------------------------------------------
- * small PTX helpers: mbarrier + 1-D bulk TMA copy (cp.async.bulk -> SASS UBLKCP)                  */
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(phase)
-        : "memory");
-}
-
-/* exact uint8 -> double without the conversion pipe: 2^52 + v has v in its low mantissa bits */
-__device__ __forceinline__ double u8_to_f64(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
-
-/* ================================================================================================
- * K1 — bid interpreter.
- * CTA = one sample tile (TS = 32*K samples, staged once by a bulk TMA copy) x one chunk of
- * programs; each warp repeatedly claims a program of the chunk and interprets it for the 32*K
- * samples of the tile (lane = K consecutive samples), so opcode dispatch is warp-uniform.
- * TPG registers live in shared memory as [warp][9 slots][K/2][32 lanes][2] doubles (slot 8 is a
- * constant 0.0 that stands for "never written" registers): every access is a conflict-free
- * 16-byte-per-lane vector.  The line words of a program are held one per lane and broadcast by
- * shuffle, one line ahead of execution.  Lines use the K1 "fused" opcodes (tpgx_internal.h): for
- * the cheap instructions the operand kinds (register / pixel) are part of the opcode, so a line
- * costs one indirect branch instead of a chain of kind tests.                                      */
-#define K1_SLOTS 9
-
-template <int K> __device__ __forceinline__ void ld_regs(const double* p, double (&v)[K]);
-template <> __device__ __forceinline__ void ld_regs<1>(const double* p, double (&v)[1]) { v[0] = *p; }
-template <> __device__ __forceinline__ void ld_regs<2>(const double* p, double (&v)[2]) {
-    double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y;
-}
-template <> __device__ __forceinline__ void ld_regs<4>(const double* p, double (&v)[4]) {
-    double2 t = *reinterpret_cast<const double2*>(p); double2 u = *reinterpret_cast<const double2*>(p + 64);
-    v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
-}
-template <int K> __device__ __forceinline__ void st_regs(double* p, const double (&v)[K]);
-template <> __device__ __forceinline__ void st_regs<1>(double* p, const double (&v)[1]) { *p = v[0]; }
-template <> __device__ __forceinline__ void st_regs<2>(double* p, const double (&v)[2]) {
-    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-}
-template <> __device__ __forceinline__ void st_regs<4>(double* p, const double (&v)[4]) {
-    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-    *reinterpret_cast<double2*>(p + 64) = make_double2(v[2], v[3]);
-}
-/* global bid row: the lane's K samples are consecutive */
-template <int K> __device__ __forceinline__ void st_bid(double* p, const double (&v)[K]) {
-#pragma unroll
-    for (int k = 0; k < K; k += 2) {
-        if (K == 1) p[0] = v[0];
-        else *reinterpret_cast<double2*>(p + k) = make_double2(v[k], v[k + 1 < K ? k + 1 : k]);
-    }
-}
-template <int K> __device__ __forceinline__ void ld_px(const uint8_t* p, uint32_t (&v)[K]);
-template <> __device__ __forceinline__ void ld_px<1>(const uint8_t* p, uint32_t (&v)[1]) { v[0] = *p; }
-template <> __device__ __forceinline__ void ld_px<2>(const uint8_t* p, uint32_t (&v)[2]) {
-    uchar2 t = *reinterpret_cast<const uchar2*>(p); v[0] = t.x; v[1] = t.y;
-}
-template <> __device__ __forceinline__ void ld_px<4>(const uint8_t* p, uint32_t (&v)[4]) {
-    uchar4 t = *reinterpret_cast<const uchar4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-template <int K> __device__ __forceinline__ void ld_px_f64(const uint8_t* p, double (&v)[K]) {
-    uint32_t px[K];
-    ld_px<K>(p, px);
-#pragma unroll
-    for (int k = 0; k < K; k++) v[k] = u8_to_f64(px[k]);
-}
-
-template <int K, int NW, int MINB, bool TRIG>
-__global__ void __launch_bounds__(NW * 32, MINB) tpgx_bid_kernel(const tpgx_bid_params p) {
-    constexpr int TS = 32 * K;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tile_bytes = p.hw * TS;
-    uint8_t* tile = smem;
-    double* regs = reinterpret_cast<double*>(smem + ((tile_bytes + 127) & ~127));
-    double* sconst = regs + NW * K1_SLOTS * TS;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(sconst + NW * TPGX_MAX_CONSTS);
-    int* s_next = reinterpret_cast<int*>(bar + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_mbar_init();
-        *s_next = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, (uint32_t)tile_bytes);
-        tma_load_1d(tile, p.tiles + (size_t)blockIdx.x * tile_bytes, (uint32_t)tile_bytes, bar);
-    }
-    double* regs_lane = regs + warp * (K1_SLOTS * TS) + lane * (K == 1 ? 1 : 2);
-    {
-        double z[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) z[k] = 0.0;
-        st_regs<K>(regs_lane + TPGX_LOC_ZERO * TS, z);
-    }
-    mbar_wait(bar, 0);
-
-    const uint8_t* tile_lane = tile + lane * K;
-    double* my_const = sconst + warp * TPGX_MAX_CONSTS;
-    const int chunk_begin = blockIdx.y * p.progs_per_chunk;
-    const int chunk_n = min(p.progs_per_chunk, p.nb_active - chunk_begin);
-    const int wrow = p.width * TS;
-
-    for (;;) {
-        int i = 0;
-        if (lane == 0) i = atomicAdd(s_next, 1);
-        i = __shfl_sync(0xffffffffu, i, 0);
-        if (i >= chunk_n) break;
-        const int row = chunk_begin + i;
-        const int prog = __ldg(p.active_prog + row);
-        const int cb = __ldg(p.prog_offset + prog);
-        const int n = __ldg(p.prog_offset + prog + 1) - cb;
-        __syncwarp();
-        if (lane < p.nb_constants) my_const[lane] = __ldg(p.constants + (size_t)prog * p.nb_constants + lane);
-        __syncwarp();
-
-        double res[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) res[k] = 0.0;
-
-        for (int base = 0; base < n; base += 32) {
-            const uint32_t mine = (base + lane < n) ? __ldg(p.code + cb + base + lane) : 0u;
-            const int m = min(32, n - base);
-            uint32_t w = __shfl_sync(0xffffffffu, mine, 0);
-#pragma unroll 1
-            for (int j = 0; j < m; j++) {
-                const uint32_t w_next = __shfl_sync(0xffffffffu, mine, j + 1); /* next line, one iteration ahead */
-                const uint32_t la = (w >> 10) & 1023u, lb = (w >> 20) & 1023u;
-                const double* ra = regs_lane + la * TS;   /* operand as a register slot */
-                const double* rb = regs_lane + lb * TS;
-                const uint8_t* pa = tile_lane + la * TS;  /* operand as a pixel */
-                const uint8_t* pb = tile_lane + lb * TS;
-                double a[K], b[K];
-#define K1_RR ld_regs<K>(ra, a); ld_regs<K>(rb, b);
-#define K1_PR ld_px_f64<K>(pa, a); ld_regs<K>(rb, b);
-#define K1_RP ld_regs<K>(ra, a); ld_px_f64<K>(pb, b);
-#define K1_PP ld_px_f64<K>(pa, a); ld_px_f64<K>(pb, b);
-#define K1_R ld_regs<K>(ra, a);
-#define K1_P ld_px_f64<K>(pa, a);
-#define K1_EACH(expr) { _Pragma("unroll") for (int k = 0; k < K; k++) { const double x = a[k], y = b[k]; (void)x; (void)y; res[k] = (expr); } } break;
-#define K1_BIN(id, expr)                                     \
-    case (id) * 4 + 0: K1_RR K1_EACH(expr)                    \
-    case (id) * 4 + 1: K1_PR K1_EACH(expr)                    \
-    case (id) * 4 + 2: K1_RP K1_EACH(expr)                    \
-    case (id) * 4 + 3: K1_PP K1_EACH(expr)
-#define K1_UN(id, expr)                                      \
-    case TPGX_K1_UNARY0 + (id) * 2 + 0: K1_R K1_EACH(expr)    \
-    case TPGX_K1_UNARY0 + (id) * 2 + 1: K1_P K1_EACH(expr)
-                switch (w & 127u) {
-                K1_BIN(0, x - y)
-                K1_BIN(1, x + y)
-                K1_BIN(2, x * y)
-                K1_BIN(3, (x < y) ? y : x)
-                K1_BIN(4, x < y ? -x : x)
-                K1_UN(0, (x == 0.0) ? 10.0 : 0.0)
-                K1_UN(1, (x == -1.0) ? 10.0 : 0.0)
-                K1_UN(2, (x == 1.0) ? 10.0 : 0.0)
-                K1_UN(3, (x >= 15.0) ? 10.0 : 0.0)
-                K1_UN(4, TPGX_PI)
-                default: {
-                    /* heavy instructions: operand kinds in bits 30/31, then one shared body */
-                    const uint32_t hop = w & 127u;
-                    if (hop >= TPGX_K1_SOBEL_MAGN) {
-                        /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
-                           of the reference's double expression is an exactly representable integer */
-                        uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
-                        ld_px<K>(pa, a00); ld_px<K>(pa + TS, a01); ld_px<K>(pa + 2 * TS, a02);
-                        ld_px<K>(pa + wrow, a10); ld_px<K>(pa + wrow + 2 * TS, a12);
-                        ld_px<K>(pa + 2 * wrow, a20); ld_px<K>(pa + 2 * wrow + TS, a21); ld_px<K>(pa + 2 * wrow + 2 * TS, a22);
-#pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            const int gx = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
-                            const int gy = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
-                            if (hop == TPGX_K1_SOBEL_MAGN) res[k] = tpgx_math::xsqrt_nonneg((double)(gx * gx + gy * gy));
-                            else res[k] = tpgx_math::atan(tpgx_math::xdiv((double)gy, (double)gx));
-                        }
-                        break;
-                    }
-                    if (w & 0x40000000u) { K1_P } else { K1_R }
-                    if (hop == TPGX_K1_DIV || hop == TPGX_K1_FMODG) {
-                        if (w & 0x80000000u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
-                    } else if (hop == TPGX_K1_MULC) {
-                        const double c = my_const[lb & 7u];
-#pragma unroll
-                        for (int k = 0; k < K; k++) b[k] = c;
-                    }
-                    switch (hop) {
-                    case TPGX_K1_DIV: K1_EACH(tpgx_math::xdiv(x, y))
-                    case TPGX_K1_MULC: K1_EACH(tpgx_math::xdiv(x * y, 10.0))
-                    case TPGX_K1_FMODG: K1_EACH(y != 0.0 ? fmod(x, y) : DBL_MIN)
-                    case TPGX_K1_EXP: K1_EACH(tpgx_math::exp(x))
-                    case TPGX_K1_LOG: K1_EACH(tpgx_math::log(x))
-                    case TPGX_K1_COS: K1_EACH(TRIG ? tpgx_math::cos(x) : 0.0)
-                    case TPGX_K1_SIN: K1_EACH(TRIG ? tpgx_math::sin(x) : 0.0)
-                    case TPGX_K1_TAN: K1_EACH(TRIG ? tpgx_math::tan(x) : 0.0)
-                    default: break;
-                    }
-                    break;
-                }
-                }
-#undef K1_RR
-#undef K1_PR
-#undef K1_RP
-#undef K1_PP
-#undef K1_R
-#undef K1_P
-#undef K1_EACH
-#undef K1_BIN
-#undef K1_UN
-                st_regs<K>(regs_lane + ((w >> 7) & 7u) * TS, res);
-                w = w_next;
-            }
-        }
-        /* [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
-#pragma unroll
-        for (int k = 0; k < K; k++)
-            if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
-        st_bid<K>(p.bid + (size_t)row * p.row_stride + (size_t)blockIdx.x * TS + lane * K, res);
-    }
-}
-
-struct bid_variant { int K, NW, MINB; };
-static const bid_variant g_variants[] = {{2, 32, 1}, {4, 12, 1}, {2, 16, 1}, {1, 16, 2}, {2, 12, 2}, {4, 8, 1}, {2, 24, 1}, {4, 10, 1}};
-static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
-
-int tpgx_bid_tile_samples(int variant) {
-    if (variant < 0 || variant >= g_nb_variants) variant = 0;
-    return 32 * g_variants[variant].K;
-}
-size_t tpgx_bid_smem_bytes(int variant, int hw) {
-    if (variant < 0 || variant >= g_nb_variants) variant = 0;
-    const bid_variant& v = g_variants[variant];
-    const int ts = 32 * v.K;
-    size_t tile = ((size_t)hw * ts + 127) & ~(size_t)127;
-    return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * TPGX_MAX_CONSTS * 8 + 16;
-}
-
-template <int K, int NW, int MINB>
-static cudaError_t launch_bid_t(const tpgx_bid_params& p, int nb_tiles, size_t smem, bool trig, cudaStream_t st) {
-    const int chunks = (p.nb_active + p.progs_per_chunk - 1) / p.progs_per_chunk;
-    dim3 grid(nb_tiles, chunks);
-    cudaError_t e;
-    if (trig) {
-        e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, MINB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        tpgx_bid_kernel<K, NW, MINB, true><<<grid, NW * 32, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        tpgx_bid_kernel<K, NW, MINB, false><<<grid, NW * 32, smem, st>>>(p);
-    }
-    return cudaGetLastError();
-}
-
-cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool trig, cudaStream_t st) {
-    if (variant < 0 || variant >= g_nb_variants) variant = 0;
-    const size_t smem = tpgx_bid_smem_bytes(variant, p.hw);
-    switch (variant) {
-    case 1: return launch_bid_t<4, 12, 1>(p, nb_tiles, smem, trig, st);
-    case 2: return launch_bid_t<2, 16, 1>(p, nb_tiles, smem, trig, st);
-    case 3: return launch_bid_t<1, 16, 2>(p, nb_tiles, smem, trig, st);
-    case 4: return launch_bid_t<2, 12, 2>(p, nb_tiles, smem, trig, st);
-    case 5: return launch_bid_t<4, 8, 1>(p, nb_tiles, smem, trig, st);
-    case 6: return launch_bid_t<2, 24, 1>(p, nb_tiles, smem, trig, st);
-    case 7: return launch_bid_t<4, 10, 1>(p, nb_tiles, smem, trig, st);
-    default: return launch_bid_t<2, 32, 1>(p, nb_tiles, smem, trig, st);
-    }
-}
 
 /* ================================================================================================
  * K2 — traversal.  block = (span of samples, one root); thread = one (root, sample) walk.
@@ -492,6 +202,46 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
     dim3 grid((unsigned)((count + 127) / 128), nb_programs);
     tpgx_exec_generic_kernel<<<grid, 128, 0, st>>>(code, prog_offset, constants, nb_constants, nb_programs, count, f0, f1, i0,
                                                    i1, space0, space1, width0, width1, bid);
+    return cudaGetLastError();
+}
+
+/* ================================================================================================
+ * Arithmetic probe (tpgx_math_probe): thread = 4 consecutive elements, so the *_K codes exercise the
+ * 4-wide primitives exactly as K1 instantiates them.                                               */
+__global__ void tpgx_math_probe_kernel(int fn, long long n, const double* __restrict__ a, const double* __restrict__ b,
+                                       double* __restrict__ out) {
+    const long long i0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4; /* no early exit: the 4-wide primitives vote warp-wide */
+    double x[4], y[4], r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const long long i = (i0 + k < n) ? i0 + k : n - 1;
+        x[k] = a[i];
+        y[k] = b ? b[i] : 0.0;
+        r[k] = 0.0;
+    }
+    switch (fn) {
+    case TPGX_PROBE_DIV: for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv(x[k], y[k]); break;
+    case TPGX_PROBE_DIV_K: tpgx_math::xdiv_k<4>(x, y, r); break;
+    case TPGX_PROBE_EXP: for (int k = 0; k < 4; k++) r[k] = tpgx_math::exp(x[k]); break;
+    case TPGX_PROBE_EXP_K: tpgx_math::exp_k<4>(x, r); break;
+    case TPGX_PROBE_LOG: for (int k = 0; k < 4; k++) r[k] = tpgx_math::log(x[k]); break;
+    case TPGX_PROBE_LOG_K: tpgx_math::log_k<4>(x, r); break;
+    case TPGX_PROBE_ATAN: for (int k = 0; k < 4; k++) r[k] = tpgx_math::atan(x[k]); break;
+    case TPGX_PROBE_SQRT_NONNEG: for (int k = 0; k < 4; k++) r[k] = tpgx_math::xsqrt_nonneg(x[k]); break;
+    case TPGX_PROBE_DIV_SMALL_INT: for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv_small_int((int)x[k], (int)y[k]); break;
+    case TPGX_PROBE_SIN: for (int k = 0; k < 4; k++) r[k] = tpgx_math::sin(x[k]); break;
+    case TPGX_PROBE_COS: for (int k = 0; k < 4; k++) r[k] = tpgx_math::cos(x[k]); break;
+    case TPGX_PROBE_TAN: for (int k = 0; k < 4; k++) r[k] = tpgx_math::tan(x[k]); break;
+    default: break;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (i0 + k < n) out[i0 + k] = r[k];
+}
+
+cudaError_t tpgx_launch_math_probe(int fn, long long n, const double* a, const double* b, double* out, cudaStream_t st) {
+    const long long threads = (n + 3) / 4;
+    tpgx_math_probe_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(fn, n, a, b, out);
     return cudaGetLastError();
 }
 

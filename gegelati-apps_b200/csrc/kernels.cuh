@@ -13,11 +13,8 @@
 struct tpgx_bid_params {
     const uint8_t* tiles;        /* [tiles][hw][TS] pixel-major sample tiles (first tile of the pass) */
     int hw, width;               /* elements per observation, row length                              */
-    const uint32_t* code;
-    const int32_t* prog_offset;
-    const double* constants;
-    int nb_constants;
-    const int32_t* active_prog;  /* [nb_active] program id of each bid-matrix row                      */
+    const uint4* stream;         /* per bid-matrix row: TPGX_K1_CQ constant quads, then its wide lines */
+    const int2* desc;            /* [nb_active] {first quad of the row in stream, number of lines}      */
     int nb_active;
     int progs_per_chunk;
     double* bid;                 /* [nb_active][row_stride]                                            */
@@ -53,7 +50,7 @@ struct tpgx_trav_params {
 /* Launchers (defined in kernels.cu). variant: 0 = default tile shape. Returns cudaError_t. */
 int tpgx_bid_tile_samples(int variant);
 size_t tpgx_bid_smem_bytes(int variant, int hw);
-cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool trig, cudaStream_t st);
+cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool extended_ops, cudaStream_t st);
 cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p, cudaStream_t st);
 cudaError_t tpgx_launch_score(const unsigned long long* confusion, int nb_roots, int nb_classes,
                               double* records, cudaStream_t st);
@@ -64,6 +61,7 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
                                      int nb_constants, int nb_programs, long long count,
                                      const double* f0, const double* f1, const int32_t* i0, const int32_t* i1,
                                      int space0, int space1, int width0, int width1, double* bid, cudaStream_t st);
+cudaError_t tpgx_launch_math_probe(int fn, long long n, const double* a, const double* b, double* out, cudaStream_t st);
 cudaError_t tpgx_launch_fp64_peak(int mode /*0 dadd+dmul, 1 dfma*/, int blocks, int iters, double* sink, cudaStream_t st);
 
 #endif

@@ -42,6 +42,8 @@ struct ShardPlan { /* programs reachable from a root range, cached between evalu
     int root_begin = -1, root_end = -1;
     uint64_t graph_version = 0;
     int nb_active = 0;
+    int k1_ts = 0;        /* tile shape the K1 stream was encoded for */
+    bool k1_ext = false;  /* the shard uses instructions outside the MNIST set */
     int64_t active_lines = 0, active_flops = 0;
 };
 
@@ -60,7 +62,7 @@ struct tpgx_ctx {
     int variant = 0;
     size_t bid_budget = (size_t)16 << 30;
 
-    DevBuf d_code, d_code_k1, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
+    DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[8];
     const uint8_t* obs_dev = nullptr;    /* raw observations [nb_obs][hw] (ours or the caller's) */
@@ -99,9 +101,9 @@ tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
 }
 
 /* Programs reachable from roots [rb, re): BFS over teams; rows in order of first appearance. */
-tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re) {
+tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
     ShardPlan& pl = ctx->plan;
-    if (pl.root_begin == rb && pl.root_end == re && pl.graph_version == ctx->graph_version) return TPGX_OK;
+    if (pl.root_begin == rb && pl.root_end == re && pl.graph_version == ctx->graph_version && pl.k1_ts == ts) return TPGX_OK;
     const tpgx_flat_graph& f = ctx->flat;
     std::vector<int32_t> row_of(f.nb_programs, -1);
     std::vector<char> seen(f.nb_teams, 0);
@@ -130,7 +132,35 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re) {
     if ((st = upload(ctx, ctx->d_active, ctx->h_active.data(), ctx->h_active.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_row, ctx->h_edge_row.data(), ctx->h_edge_row.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_roots, f.root_team.data() + rb, (size_t)(re - rb) * 4)) != TPGX_OK) return st;
-    pl.root_begin = rb; pl.root_end = re; pl.graph_version = ctx->graph_version;
+    /* K1 stream: per row its constants (TPGX_K1_CQ quads) followed by its pre-decoded wide lines */
+    {
+        std::vector<tpgx_k1_quad> stream;
+        bool ext = false;
+        std::vector<int32_t> desc(2 * ctx->h_active.size());
+        stream.reserve((size_t)pl.active_lines + (size_t)TPGX_K1_CQ * ctx->h_active.size() + 64);
+        const int nc = ctx->cfg.nb_constants;
+        for (size_t row = 0; row < ctx->h_active.size(); row++) {
+            const int p = ctx->h_active[row];
+            desc[2 * row] = (int32_t)stream.size();
+            desc[2 * row + 1] = f.prog_offset[p + 1] - f.prog_offset[p];
+            double cq[2 * TPGX_K1_CQ] = {0};
+            for (int c = 0; c < nc; c++) cq[c] = f.constants[(size_t)p * nc + c];
+            tpgx_k1_quad q[TPGX_K1_CQ];
+            memcpy(q, cq, sizeof q);
+            stream.insert(stream.end(), q, q + TPGX_K1_CQ);
+            for (int i = f.prog_offset[p]; i < f.prog_offset[p + 1]; i++) {
+                stream.push_back(tpgx_k1_line(f.code[i], (uint32_t)ts));
+                if (stream.back().x == 0xffffffffu) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
+                ext |= tpgx_k1_is_extended(stream.back().x);
+            }
+        }
+        stream.resize(stream.size() + 64, tpgx_k1_quad{0, 0, 0, 0}); /* slack: a lane may read up to 32 quads past a row's start */
+        if ((st = upload(ctx, ctx->d_k1_stream, stream.data(), stream.size() * sizeof(tpgx_k1_quad))) != TPGX_OK) return st;
+        if ((st = upload(ctx, ctx->d_k1_desc, desc.data(), desc.size() * 4)) != TPGX_OK) return st;
+        CU(cudaStreamSynchronize(ctx->stream)); /* stream / desc are locals */
+        pl.k1_ext = ext;
+    }
+    pl.root_begin = rb; pl.root_end = re; pl.graph_version = ctx->graph_version; pl.k1_ts = ts;
     return TPGX_OK;
 }
 
@@ -157,7 +187,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     const int ts = tpgx_bid_tile_samples(ctx->variant);
     const int64_t nTiles = (nS + ts - 1) / ts;
     const int hw = ctx->obs_hw;
-    tpgx_status st = make_plan(ctx, req->root_begin, req->root_end);
+    tpgx_status st = make_plan(ctx, req->root_begin, req->root_end, ts);
     if (st != TPGX_OK) return st;
     const int nA = ctx->plan.nb_active;
 
@@ -205,11 +235,8 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             tpgx_bid_params bp{};
             bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * hw * ts;
             bp.hw = hw; bp.width = ctx->obs_width;
-            bp.code = ctx->d_code_k1.as<uint32_t>();
-            bp.prog_offset = ctx->d_prog_off.as<int32_t>();
-            bp.constants = ctx->d_consts.as<double>();
-            bp.nb_constants = ctx->cfg.nb_constants;
-            bp.active_prog = ctx->d_active.as<int32_t>();
+            bp.stream = ctx->d_k1_stream.as<uint4>();
+            bp.desc = ctx->d_k1_desc.as<int2>();
             bp.nb_active = nA;
             /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 programs per warp */
             int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
@@ -217,7 +244,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.progs_per_chunk = (nA + chunks - 1) / chunks;
             bp.bid = ctx->d_bid.as<double>();
             bp.row_stride = (long long)nt * ts;
-            CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->uses_trig, ctx->stream));
+            CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->plan.k1_ext, ctx->stream));
         }
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
         tpgx_trav_params tp{};
@@ -294,7 +321,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* all[] = {&ctx->d_code, &ctx->d_code_k1, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
+    DevBuf* all[] = {&ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
                      &ctx->d_counters, &ctx->d_status};
@@ -345,12 +372,6 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
     std::vector<int32_t> edge_lines(F.nb_edges);
     for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }
     if ((st = upload(ctx, ctx->d_code, F.code.data(), F.code.size() * 4)) != TPGX_OK) return st;
-    {
-        std::vector<uint32_t> k1(F.code.size());
-        for (size_t i = 0; i < k1.size(); i++) k1[i] = tpgx_k1_word(F.code[i]);
-        if ((st = upload(ctx, ctx->d_code_k1, k1.data(), k1.size() * 4)) != TPGX_OK) return st;
-        CU(cudaStreamSynchronize(ctx->stream)); /* k1 is a local */
-    }
     if ((st = upload(ctx, ctx->d_prog_off, F.prog_offset.data(), F.prog_offset.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_consts, F.constants.data(), F.constants.size() * 8)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_team_off, F.team_edge_offset.data(), F.team_edge_offset.size() * 4)) != TPGX_OK) return st;
@@ -613,6 +634,20 @@ tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* re
         out->counters->device_lines = c[3]; out->counters->device_program_executions = c[2];
     }
     if (out->device_ms) cudaEventElapsedTime(out->device_ms, ctx->event(0), ctx->event(1));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_math_probe(tpgx_ctx* ctx, int32_t fn, int64_t n, const double* a, const double* b, double* out) {
+    if (!ctx || n < 1 || !a || !out || fn < 0 || fn > TPGX_PROBE_TAN) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_math_probe: bad argument");
+    cudaSetDevice(ctx->cfg.device);
+    tpgx_status st;
+    if ((st = upload(ctx, ctx->d_scratch[0], a, (size_t)n * 8)) != TPGX_OK) return st;
+    if (b && (st = upload(ctx, ctx->d_scratch[1], b, (size_t)n * 8)) != TPGX_OK) return st;
+    CU(ctx->d_scratch[2].ensure((size_t)n * 8));
+    CU(tpgx_launch_math_probe(fn, n, ctx->d_scratch[0].as<double>(), b ? ctx->d_scratch[1].as<double>() : nullptr,
+                              ctx->d_scratch[2].as<double>(), ctx->stream));
+    CU(cudaMemcpyAsync(out, ctx->d_scratch[2].p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     return TPGX_OK;
 }
 

@@ -43,46 +43,71 @@ static inline uint32_t tpgx_pack_line(uint32_t op, uint32_t dst, uint32_t ka, ui
     return (op & 31u) | ((dst & 7u) << 5) | (((ka << 10) | (la & 1023u)) << 8) | (((kb << 10) | (lb & 1023u)) << 20);
 }
 
-/* ---- K1 "fused" line word (built from the generic word by tpgx_k1_word) ---------------------------
- *   [ 6: 0] K1 opcode   [ 9: 7] destination register   [19:10] operand A loc   [29:20] operand B loc
- *   [30] A is a pixel (heavy opcodes)   [31] B is a pixel (heavy opcodes)
- * Cheap instructions carry the operand kinds in the opcode: binary id*4 + (A pixel) + 2*(B pixel),
- * unary TPGX_K1_UNARY0 + id*2 + (A pixel).  A register operand's loc is its slot (8 = zero slot). */
-#define TPGX_K1_UNARY0 20
-enum {
-    TPGX_K1_DIV = 32, TPGX_K1_MULC, TPGX_K1_FMODG, TPGX_K1_EXP, TPGX_K1_LOG, TPGX_K1_COS, TPGX_K1_SIN, TPGX_K1_TAN,
-    TPGX_K1_SOBEL_MAGN = 48, TPGX_K1_SOBEL_DIR = 49, TPGX_K1_INVALID = 127
+/* ---- K1 wide line (16 bytes), derived from the generic word by tpgx_k1_line for one tile shape -----
+ * Everything the interpreter would otherwise shift, mask and multiply per line is precomputed:
+ *   x  handler id (below): for the cheap instructions the operand kinds (register / pixel) are part
+ *      of the id, so a line costs one dispatch and no kind tests
+ *   y  operand A: byte offset from the lane's register base (slot * TS * 8) or from the lane's pixel
+ *      base (loc * TS; for a 3x3 window its top-left pixel)
+ *   z  operand B: same, or the byte offset of the program constant (index * 8) for MULC
+ *   w  destination register: byte offset from the lane's register base
+ * TS = samples per tile (32 * K).  A program's stream entry is TPGX_K1_CQ quads holding its constants
+ * followed by its lines; TPGX_K1_CAPL lines are staged in shared memory at a time.                  */
+#define TPGX_K1_CQ 4
+#define TPGX_K1_CAPL 28
+/* handler id bit layout: [0] operand A is a pixel, [1] operand B is a pixel, [5:2] operation, [6] heavy class
+ * (own operand handling / libm), so the interpreter dispatches with a few single-bit tests */
+#define TPGX_K1H_HEAVY 64u
+enum { /* cheap class: (op << 2) | kinds */
+    TPGX_K1C_SUB = 0, TPGX_K1C_ADD, TPGX_K1C_MUL, TPGX_K1C_MAX, TPGX_K1C_COND, TPGX_K1C_EQ0, TPGX_K1C_EQM1, TPGX_K1C_EQ1,
+    TPGX_K1C_GE15, TPGX_K1C_PI
 };
+enum { /* heavy class: 64 | (op << 2) | kinds */
+    TPGX_K1X_DIV = 0, TPGX_K1X_MULC, TPGX_K1X_EXP, TPGX_K1X_LOG, TPGX_K1X_SOBEL_MAGN, TPGX_K1X_SOBEL_DIR,
+    TPGX_K1X_FMODG, TPGX_K1X_COS, TPGX_K1X_SIN, TPGX_K1X_TAN
+};
+/* operations outside the MNIST set ([REF] mnist/src/main.cpp:79-88): compiled into the "extended" kernel only */
+static inline bool tpgx_k1_is_extended(uint32_t h) {
+    const uint32_t op = (h >> 2) & 15u;
+    return (h & TPGX_K1H_HEAVY) ? op >= TPGX_K1X_FMODG : op >= TPGX_K1C_COND;
+}
 
-static inline uint32_t tpgx_k1_word(uint32_t w) {
-    const uint32_t op = w & 31u, dst = (w >> 5) & 7u;
-    const uint32_t fa = (w >> 8) & 0xfffu, fb = w >> 20;
+struct tpgx_k1_quad { uint32_t x, y, z, w; };
+
+static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts) {
+    const uint32_t op = word & 31u, dst = (word >> 5) & 7u;
+    const uint32_t fa = (word >> 8) & 0xfffu, fb = word >> 20;
     const uint32_t pa = (fa >> 10) == TPGX_KIND_SRC0, pb = (fb >> 10) == TPGX_KIND_SRC0;
-    uint32_t k1;
+    const uint32_t la = fa & 1023u, lb = fb & 1023u;
+    tpgx_k1_quad q;
+    q.y = pa ? la * ts : la * ts * 8u;
+    q.z = pb ? lb * ts : lb * ts * 8u;
+    q.w = dst * ts * 8u;
+    const uint32_t kk = pa + 2 * pb;
     switch (op) {
-    case TPGX_OP_SUB: k1 = 0 * 4 + pa + 2 * pb; break;
-    case TPGX_OP_ADD: k1 = 1 * 4 + pa + 2 * pb; break;
-    case TPGX_OP_MUL: k1 = 2 * 4 + pa + 2 * pb; break;
-    case TPGX_OP_MAX: k1 = 3 * 4 + pa + 2 * pb; break;
-    case TPGX_OP_COND: k1 = 4 * 4 + pa + 2 * pb; break;
-    case TPGX_OP_EQ0: k1 = TPGX_K1_UNARY0 + 0 * 2 + pa; break;
-    case TPGX_OP_EQM1: k1 = TPGX_K1_UNARY0 + 1 * 2 + pa; break;
-    case TPGX_OP_EQ1: k1 = TPGX_K1_UNARY0 + 2 * 2 + pa; break;
-    case TPGX_OP_GE15: k1 = TPGX_K1_UNARY0 + 3 * 2 + pa; break;
-    case TPGX_OP_PI: k1 = TPGX_K1_UNARY0 + 4 * 2 + pa; break;
-    case TPGX_OP_DIV: k1 = TPGX_K1_DIV; break;
-    case TPGX_OP_MULC: k1 = TPGX_K1_MULC; break;
-    case TPGX_OP_FMODG: k1 = TPGX_K1_FMODG; break;
-    case TPGX_OP_EXP: k1 = TPGX_K1_EXP; break;
-    case TPGX_OP_LOG: k1 = TPGX_K1_LOG; break;
-    case TPGX_OP_COS: k1 = TPGX_K1_COS; break;
-    case TPGX_OP_SIN: k1 = TPGX_K1_SIN; break;
-    case TPGX_OP_TAN: k1 = TPGX_K1_TAN; break;
-    case TPGX_OP_SOBEL_MAGN: k1 = TPGX_K1_SOBEL_MAGN; break;
-    case TPGX_OP_SOBEL_DIR: k1 = TPGX_K1_SOBEL_DIR; break;
-    default: k1 = TPGX_K1_INVALID; break; /* int-typed instructions never reach K1 (no i32 source) */
+    case TPGX_OP_SUB: q.x = (TPGX_K1C_SUB << 2) | kk; break;
+    case TPGX_OP_ADD: q.x = (TPGX_K1C_ADD << 2) | kk; break;
+    case TPGX_OP_MUL: q.x = (TPGX_K1C_MUL << 2) | kk; break;
+    case TPGX_OP_MAX: q.x = (TPGX_K1C_MAX << 2) | kk; break;
+    case TPGX_OP_COND: q.x = (TPGX_K1C_COND << 2) | kk; break;
+    case TPGX_OP_EQ0: q.x = (TPGX_K1C_EQ0 << 2) | pa; break;
+    case TPGX_OP_EQM1: q.x = (TPGX_K1C_EQM1 << 2) | pa; break;
+    case TPGX_OP_EQ1: q.x = (TPGX_K1C_EQ1 << 2) | pa; break;
+    case TPGX_OP_GE15: q.x = (TPGX_K1C_GE15 << 2) | pa; break;
+    case TPGX_OP_PI: q.x = (TPGX_K1C_PI << 2) | pa; break;
+    case TPGX_OP_DIV: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_DIV << 2) | kk; break;
+    case TPGX_OP_FMODG: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_FMODG << 2) | kk; break;
+    case TPGX_OP_MULC: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_MULC << 2) | pa; q.z = lb * 8u; break;
+    case TPGX_OP_EXP: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_EXP << 2) | pa; break;
+    case TPGX_OP_LOG: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_LOG << 2) | pa; break;
+    case TPGX_OP_COS: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_COS << 2) | pa; break;
+    case TPGX_OP_SIN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SIN << 2) | pa; break;
+    case TPGX_OP_TAN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_TAN << 2) | pa; break;
+    case TPGX_OP_SOBEL_MAGN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_MAGN << 2) | 1u; break;
+    case TPGX_OP_SOBEL_DIR: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_DIR << 2) | 1u; break;
+    default: q.x = 0xffffffffu; break; /* int-typed instructions never reach K1 (no i32 source) */
     }
-    return k1 | (dst << 7) | ((fa & 1023u) << 10) | ((fb & 1023u) << 20) | (pa << 30) | (pb << 31);
+    return q;
 }
 
 enum tpgx_operand_type { TPGX_T_NONE = 0, TPGX_T_D = 1, TPGX_T_I = 2, TPGX_T_C = 3, TPGX_T_W = 4 };

@@ -15,7 +15,7 @@ EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_evaluate_episodes",
-    "tpgx_execute_programs", "tpgx_measure_fp64_peak",
+    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe",
 ]
 
 _lib = None
@@ -49,6 +49,7 @@ def load_library():
     lib.tpgx_evaluate_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.POINTER(A.EpisodeResult)]
     lib.tpgx_execute_programs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tpgx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.tpgx_math_probe.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 
@@ -168,6 +169,14 @@ class Evaluator:
             res.trace = out["trace"].ctypes.data
         self._check(self.lib.tpgx_evaluate_episodes(self.h, C.byref(req), C.byref(res)))
         out["counters"] = cnt.as_dict()
+        return out
+
+    def math_probe(self, fn, a, b=None):
+        """Device arithmetic primitive `fn` (PROBE_*) elementwise — diagnostic for parity tests."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64) if b is not None else None
+        out = np.empty_like(a)
+        self._check(self.lib.tpgx_math_probe(self.h, fn, a.size, a.ctypes.data, _ptr(b), out.ctypes.data))
         return out
 
     def measure_fp64_peak(self):

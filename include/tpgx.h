@@ -256,6 +256,19 @@ tpgx_status tpgx_execute_programs(tpgx_ctx* ctx, int64_t count, const double* co
  * warp-instructions per second), measured on ctx's device.                                         */
 tpgx_status tpgx_measure_fp64_peak(tpgx_ctx* ctx, double* dadd_per_s, double* dfma_per_s);
 
+/* Diagnostic entry point for parity tests: evaluates ONE primitive of the device arithmetic
+ * (the division / square-root sequences and the shared libm of csrc/tpgx_math.h that stand in for
+ * the reference's `/`, sqrt, std::exp, std::log, std::atan, ... — [REF] mnist/src/main.cpp:50-77)
+ * elementwise on the GPU, so tests can compare it bit for bit with the host build of the same header
+ * on millions of operands.  The *_K codes run the 4-wide variants the K1 interpreter uses.          */
+enum {
+    TPGX_PROBE_DIV = 0, TPGX_PROBE_DIV_K = 1, TPGX_PROBE_EXP = 2, TPGX_PROBE_EXP_K = 3, TPGX_PROBE_LOG = 4,
+    TPGX_PROBE_LOG_K = 5, TPGX_PROBE_ATAN = 6, TPGX_PROBE_SQRT_NONNEG = 7 /* integer-valued a in [0, 2^31) */,
+    TPGX_PROBE_DIV_SMALL_INT = 8 /* (int)a / (int)b, Sobel gradient range */, TPGX_PROBE_SIN = 9, TPGX_PROBE_COS = 10,
+    TPGX_PROBE_TAN = 11
+};
+tpgx_status tpgx_math_probe(tpgx_ctx* ctx, int32_t fn, int64_t n, const double* a, const double* b, double* out);
+
 #ifdef __cplusplus
 }
 #endif

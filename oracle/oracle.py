@@ -38,6 +38,7 @@ def load():
     lib.orc_apply_op.restype = C.c_double
     lib.orc_apply_op.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_void_p]
     lib.orc_math_array.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.orc_math_probe.argtypes = [C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.orc_env_create.restype = C.c_void_p
     lib.orc_env_create.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32]
     lib.orc_env_destroy.argtypes = [C.c_void_p]
@@ -158,6 +159,15 @@ def math_array(fn, x, math=MATH_SHARED):
     x = np.ascontiguousarray(x, dtype=np.float64)
     out = np.empty_like(x)
     load().orc_math_array(fn, math, x.size, x.ctypes.data, out.ctypes.data)
+    return out
+
+
+def math_probe(fn, a, b=None):
+    """Host build of the arithmetic primitive `fn` (tpgx.abi PROBE_*) — the checker for tpgx_math_probe."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64) if b is not None else None
+    out = np.empty_like(a)
+    load().orc_math_probe(fn, a.size, a.ctypes.data, _ptr(b), out.ctypes.data)
     return out
 
 

@@ -790,6 +790,25 @@ void orc_math_array(int32_t fn, int32_t math_flavour, int64_t n, const double* i
     for (int64_t i = 0; i < n; i++) out[i] = apply_op(fn, m, in[i], 0.0, 0, 0, 0.0, nullptr);
 }
 
+/* Host build of the primitives tpgx_math_probe runs on the device (same fn codes, include/tpgx.h). */
+void orc_math_probe(int32_t fn, int64_t n, const double* a, const double* b, double* out) {
+    for (int64_t i = 0; i < n; i++) {
+        const double x = a[i], y = b ? b[i] : 0.0;
+        switch (fn) {
+        case TPGX_PROBE_DIV: case TPGX_PROBE_DIV_K: out[i] = x / y; break;
+        case TPGX_PROBE_EXP: case TPGX_PROBE_EXP_K: out[i] = tpgx_math::exp(x); break;
+        case TPGX_PROBE_LOG: case TPGX_PROBE_LOG_K: out[i] = tpgx_math::log(x); break;
+        case TPGX_PROBE_ATAN: out[i] = tpgx_math::atan(x); break;
+        case TPGX_PROBE_SQRT_NONNEG: out[i] = std::sqrt(x); break;
+        case TPGX_PROBE_DIV_SMALL_INT: out[i] = (double)(int)x / (double)(int)y; break;
+        case TPGX_PROBE_SIN: out[i] = tpgx_math::sin(x); break;
+        case TPGX_PROBE_COS: out[i] = tpgx_math::cos(x); break;
+        case TPGX_PROBE_TAN: out[i] = tpgx_math::tan(x); break;
+        default: out[i] = 0.0; break;
+        }
+    }
+}
+
 struct orc_env { std::unique_ptr<Env> env; };
 
 orc_env* orc_env_create(int32_t kind, int32_t second_player_random, int32_t npa, const double* pa, int32_t math_flavour) {

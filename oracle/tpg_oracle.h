@@ -63,6 +63,8 @@ double orc_apply_op(int32_t opcode, int32_t math_flavour, double a, double b, in
 void orc_math_array(int32_t fn /* tpgx_opcode EXP..TAN */, int32_t math_flavour, int64_t n,
                     const double* in, double* out);
 
+void orc_math_probe(int32_t fn /* TPGX_PROBE_* */, int64_t n, const double* a, const double* b, double* out);
+
 /* Environment restatements, stepped one action at a time. */
 typedef struct orc_env orc_env;
 orc_env* orc_env_create(int32_t kind, int32_t second_player_random, int32_t nb_pendulum_actions,
