@@ -64,40 +64,48 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "memory");
 }
 
-/* exact uint8 -> double without the conversion pipe: 2^52 + v has v in its low mantissa bits */
-__device__ __forceinline__ double u8_to_f64(uint32_t v) { return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0; }
-
 #define K1_SLOTS 9
 #define K1_CODE_QUADS 32 /* TPGX_K1_CQ constant quads + TPGX_K1_CAPL lines; two such buffers per warp */
 
-template <int K> __device__ __forceinline__ void ld_regs(const uint8_t* p, double (&v)[K]);
-template <> __device__ __forceinline__ void ld_regs<2>(const uint8_t* p, double (&v)[2]) {
-    const double2 t = *reinterpret_cast<const double2*>(p); v[0] = t.x; v[1] = t.y;
+/* Shared-memory accesses of the interpreter use explicit 32-bit shared addresses: with generic
+ * pointers the compiler re-derived the shared window base (S2UR + ULEA + IADD3) on every line. */
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& x, double& y) {
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(addr));
 }
-template <> __device__ __forceinline__ void ld_regs<4>(const uint8_t* p, double (&v)[4]) {
-    const double2 t = *reinterpret_cast<const double2*>(p), u = *reinterpret_cast<const double2*>(p + 512);
-    v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double x, double y) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(x), "d"(y) : "memory");
 }
-template <int K> __device__ __forceinline__ void st_regs(uint8_t* p, const double (&v)[K]);
-template <> __device__ __forceinline__ void st_regs<2>(uint8_t* p, const double (&v)[2]) {
-    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
-template <> __device__ __forceinline__ void st_regs<4>(uint8_t* p, const double (&v)[4]) {
-    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-    *reinterpret_cast<double2*>(p + 512) = make_double2(v[2], v[3]);
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
-template <int K> __device__ __forceinline__ void ld_px(const uint8_t* p, uint32_t (&v)[K]);
-template <> __device__ __forceinline__ void ld_px<2>(const uint8_t* p, uint32_t (&v)[2]) {
-    const uchar2 t = *reinterpret_cast<const uchar2*>(p); v[0] = t.x; v[1] = t.y;
+
+template <int K> __device__ __forceinline__ void ld_regs(uint32_t p, double (&v)[K]) {
+    lds_f64x2(p, v[0], v[1]);
+    if (K == 4) lds_f64x2(p + 512, v[2], v[3]);
 }
-template <> __device__ __forceinline__ void ld_px<4>(const uint8_t* p, uint32_t (&v)[4]) {
-    const uchar4 t = *reinterpret_cast<const uchar4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+template <int K> __device__ __forceinline__ void st_regs(uint32_t p, const double (&v)[K]) {
+    sts_f64x2(p, v[0], v[1]);
+    if (K == 4) sts_f64x2(p + 512, v[2], v[3]);
 }
-template <int K> __device__ __forceinline__ void ld_px_f64(const uint8_t* p, double (&v)[K]) {
-    uint32_t px[K];
-    ld_px<K>(p, px);
+/* K consecutive uint8 pixels of the lane -> packed word */
+template <int K> __device__ __forceinline__ uint32_t ld_px_word(uint32_t p) { return K == 2 ? lds_u16(p) : lds_u32(p); }
+template <int K> __device__ __forceinline__ void ld_px(uint32_t p, uint32_t (&v)[K]) {
+    const uint32_t w = ld_px_word<K>(p);
 #pragma unroll
-    for (int k = 0; k < K; k++) v[k] = u8_to_f64(px[k]);
+    for (int k = 0; k < K; k++) v[k] = __byte_perm(w, 0, 0x4440 + k); /* byte k, zero-extended: one PRMT */
+}
+/* uint8 -> double is exact; one I2F.F64.U8 with a byte selector per sample */
+template <int K> __device__ __forceinline__ void ld_px_f64(uint32_t p, double (&v)[K]) {
+    const uint32_t w = ld_px_word<K>(p);
+#pragma unroll
+    for (int k = 0; k < K; k++) v[k] = (double)__byte_perm(w, 0, 0x4440 + k);
 }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
@@ -129,8 +137,8 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
         mbar_expect_tx(bar, (uint32_t)tile_bytes);
         tma_load_1d(tile, p.tiles + (size_t)blockIdx.x * tile_bytes, (uint32_t)tile_bytes, bar);
     }
-    uint8_t* const regs_lane = regs + warp * (K1_SLOTS * TS * 8) + lane * 16;
-    const uint8_t* const tile_lane = tile + lane * K;
+    const uint32_t regs_lane = smem_u32(regs) + warp * (K1_SLOTS * TS * 8) + lane * 16;
+    const uint32_t tile_lane = smem_u32(tile) + lane * K;
     uint4* const mycode = codeb + warp * (2 * K1_CODE_QUADS);
     {
         double z[K];
@@ -182,11 +190,11 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
 #pragma unroll 1
             for (int j = 0; j < m; j++) {
                 const uint4 ln = lp[j];                 /* broadcast LDS.128: handler, operand offsets, destination offset */
-                const uint8_t* ra = regs_lane + ln.y;  /* operand as a register slot */
-                const uint8_t* rb = regs_lane + ln.z;
-                const uint8_t* pa = tile_lane + ln.y;  /* operand as a pixel */
-                const uint8_t* pb = tile_lane + ln.z;
-                uint8_t* const rd = regs_lane + ln.w;  /* destination register slot */
+                const uint32_t ra = regs_lane + ln.y;  /* operand as a register slot */
+                const uint32_t rb = regs_lane + ln.z;
+                const uint32_t pa = tile_lane + ln.y;  /* operand as a pixel */
+                const uint32_t pb = tile_lane + ln.z;
+                const uint32_t rd = regs_lane + ln.w;  /* destination register slot */
                 /* dispatch on single bits of the handler id; every handler loads, computes and stores by
                    itself, so no values merge afterwards */
                 const uint32_t h = ln.x;
@@ -225,15 +233,30 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                 } else if (op == TPGX_K1X_SOBEL_MAGN || op == TPGX_K1X_SOBEL_DIR) {
                     /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
                        of the reference's double expression is an exactly representable integer */
-                    uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
-                    ld_px<K>(pa, a00); ld_px<K>(pa + TS, a01); ld_px<K>(pa + 2 * TS, a02);
-                    ld_px<K>(pa + wrow, a10); ld_px<K>(pa + wrow + 2 * TS, a12);
-                    ld_px<K>(pa + 2 * wrow, a20); ld_px<K>(pa + 2 * wrow + TS, a21); ld_px<K>(pa + 2 * wrow + 2 * TS, a22);
                     int gx[K], gy[K];
+                    if (K == 2) {
+                        /* both samples of the lane at once: each 16-bit load becomes two 16-bit fields of one
+                           register (PRMT), the gradients are summed per field with 32-bit adds — a +1024 bias
+                           keeps every field positive so nothing borrows across the field boundary */
+                        auto px2 = [&](uint32_t addr) { return __byte_perm(lds_u16(addr), 0, 0x4140); };
+                        const uint32_t q00 = px2(pa), q01 = px2(pa + TS), q02 = px2(pa + 2 * TS);
+                        const uint32_t q10 = px2(pa + wrow), q12 = px2(pa + wrow + 2 * TS);
+                        const uint32_t q20 = px2(pa + 2 * wrow), q21 = px2(pa + 2 * wrow + TS), q22 = px2(pa + 2 * wrow + 2 * TS);
+                        const uint32_t BIAS = 0x04000400u;
+                        const uint32_t gxp = (q02 + q22 + 2 * q12 + BIAS) - (q00 + q20 + 2 * q10);
+                        const uint32_t gyp = (q20 + q22 + 2 * q21 + BIAS) - (q00 + q02 + 2 * q01);
+                        gx[0] = (int)(gxp & 0xffffu) - 1024; gx[K - 1] = (int)(gxp >> 16) - 1024;
+                        gy[0] = (int)(gyp & 0xffffu) - 1024; gy[K - 1] = (int)(gyp >> 16) - 1024;
+                    } else {
+                        uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
+                        ld_px<K>(pa, a00); ld_px<K>(pa + TS, a01); ld_px<K>(pa + 2 * TS, a02);
+                        ld_px<K>(pa + wrow, a10); ld_px<K>(pa + wrow + 2 * TS, a12);
+                        ld_px<K>(pa + 2 * wrow, a20); ld_px<K>(pa + 2 * wrow + TS, a21); ld_px<K>(pa + 2 * wrow + 2 * TS, a22);
 #pragma unroll
-                    for (int k = 0; k < K; k++) {
-                        gx[k] = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
-                        gy[k] = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
+                        for (int k = 0; k < K; k++) {
+                            gx[k] = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
+                            gy[k] = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
+                        }
                     }
                     if (op == TPGX_K1X_SOBEL_MAGN) {
 #pragma unroll
@@ -245,6 +268,16 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                     st_regs<K>(rd, r);
                 } else {
                     /* ---- heavy class: division and libm ---- */
+                    if ((op == TPGX_K1X_EXP || op == TPGX_K1X_LOG) && (h & 1u)) {
+                        /* exp / ln of a PIXEL: a uint8 has 256 possible values, so the result is memoised in a
+                           table filled once per context by the same tpgx_math routines (bit-identical) */
+                        const uint32_t w = ld_px_word<K>(pa);
+                        const double* __restrict__ t = p.pixel_lut + (op == TPGX_K1X_LOG ? 256 : 0);
+#pragma unroll
+                        for (int k = 0; k < K; k++) r[k] = __ldg(t + __byte_perm(w, 0, 0x4440 + k));
+                        st_regs<K>(rd, r);
+                        continue;
+                    }
                     if (h & 1u) ld_px_f64<K>(pa, a); else ld_regs<K>(ra, a);
                     if (op == TPGX_K1X_EXP) {
                         tpgx_math::exp_k<K>(a, r);
@@ -296,7 +329,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
 }
 
 struct bid_variant { int K, NW; };
-static const bid_variant g_variants[] = {{2, 32}, {4, 12}, {4, 10}, {2, 28}, {2, 24}, {2, 16}, {4, 8}};
+static const bid_variant g_variants[] = {{2, 32}, {4, 12}, {4, 10}, {2, 28}, {2, 24}, {2, 16}, {4, 8}, {2, 20}, {2, 22}, {2, 26}};
 static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 int tpgx_bid_tile_samples(int variant) {
@@ -338,6 +371,9 @@ cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant,
     case 4: return launch_bid_t<2, 24>(p, nb_tiles, smem, ext, st);
     case 5: return launch_bid_t<2, 16>(p, nb_tiles, smem, ext, st);
     case 6: return launch_bid_t<4, 8>(p, nb_tiles, smem, ext, st);
+    case 7: return launch_bid_t<2, 20>(p, nb_tiles, smem, ext, st);
+    case 8: return launch_bid_t<2, 22>(p, nb_tiles, smem, ext, st);
+    case 9: return launch_bid_t<2, 26>(p, nb_tiles, smem, ext, st);
     default: return launch_bid_t<2, 32>(p, nb_tiles, smem, ext, st);
     }
 }

@@ -206,6 +206,18 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
 }
 
 /* ================================================================================================
+ * exp / ln of the 256 uint8 pixel values, by the same routines K1 runs on register operands.       */
+__global__ void tpgx_pixel_lut_kernel(double* __restrict__ lut) {
+    const int v = threadIdx.x;
+    lut[v] = tpgx_math::exp((double)v);
+    lut[256 + v] = tpgx_math::log((double)v);
+}
+cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st) {
+    tpgx_pixel_lut_kernel<<<1, 256, 0, st>>>(lut);
+    return cudaGetLastError();
+}
+
+/* ================================================================================================
  * Arithmetic probe (tpgx_math_probe): thread = 4 consecutive elements, so the *_K codes exercise the
  * 4-wide primitives exactly as K1 instantiates them.                                               */
 __global__ void tpgx_math_probe_kernel(int fn, long long n, const double* __restrict__ a, const double* __restrict__ b,

@@ -15,6 +15,7 @@ struct tpgx_bid_params {
     int hw, width;               /* elements per observation, row length                              */
     const uint4* stream;         /* per bid-matrix row: TPGX_K1_CQ constant quads, then its wide lines */
     const int2* desc;            /* [nb_active] {first quad of the row in stream, number of lines}      */
+    const double* pixel_lut;     /* [2][256] exp / ln of every uint8 pixel value (tpgx_math, filled on the device) */
     int nb_active;
     int progs_per_chunk;
     double* bid;                 /* [nb_active][row_stride]                                            */
@@ -61,6 +62,7 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
                                      int nb_constants, int nb_programs, long long count,
                                      const double* f0, const double* f1, const int32_t* i0, const int32_t* i1,
                                      int space0, int space1, int width0, int width1, double* bid, cudaStream_t st);
+cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st);
 cudaError_t tpgx_launch_math_probe(int fn, long long n, const double* a, const double* b, double* out, cudaStream_t st);
 cudaError_t tpgx_launch_fp64_peak(int mode /*0 dadd+dmul, 1 dfma*/, int blocks, int iters, double* sink, cudaStream_t st);
 

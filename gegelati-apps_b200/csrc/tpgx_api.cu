@@ -62,6 +62,7 @@ struct tpgx_ctx {
     int variant = 0;
     size_t bid_budget = (size_t)16 << 30;
 
+    DevBuf d_pixel_lut;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[8];
@@ -237,6 +238,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.hw = hw; bp.width = ctx->obs_width;
             bp.stream = ctx->d_k1_stream.as<uint4>();
             bp.desc = ctx->d_k1_desc.as<int2>();
+            bp.pixel_lut = ctx->d_pixel_lut.as<double>();
             bp.nb_active = nA;
             /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 programs per warp */
             int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
@@ -311,6 +313,12 @@ tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out) {
     ctx->cfg = *cfg;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, TPGX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
+    if (ctx->d_pixel_lut.ensure(2 * 256 * 8) != cudaSuccess || tpgx_launch_pixel_lut(ctx->d_pixel_lut.as<double>(), ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, TPGX_ERR_CUDA, "tpgx_create: pixel table initialisation failed");
+    }
     if (const char* v = getenv("TPGX_K1_VARIANT")) ctx->variant = atoi(v);
     if (const char* v = getenv("TPGX_BID_BUDGET_MB")) ctx->bid_budget = (size_t)atoll(v) << 20;
     *out = ctx;
@@ -321,7 +329,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* all[] = {&ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
+    DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
                      &ctx->d_counters, &ctx->d_status};
