@@ -20,8 +20,12 @@
  * [UP] executeFromRoot: from the root team follow the best admissible edge until an action;
  * [UP] evaluateTeam: skip edges to already visited teams, first admissible edge is the initial
  * best, later edges replace it if bid >= best (last-max) / bid > best (first-max).                 */
+#ifndef TRAV_THREADS
 #define TRAV_THREADS 256
+#endif
+#ifndef TRAV_SPT
 #define TRAV_SPT 8
+#endif
 
 __global__ void __launch_bounds__(TRAV_THREADS) tpgx_traverse_kernel(const tpgx_trav_params p) {
     __shared__ unsigned int s_table[256];

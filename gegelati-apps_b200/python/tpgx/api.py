@@ -9,7 +9,7 @@ from . import _cabi as A
 from .graph import TPGraph
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_PKG, "..", "..", "lib", "libtpgx.so"))
+LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..", "..", "lib", "libtpgx.so"))
 
 EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
