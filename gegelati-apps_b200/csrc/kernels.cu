@@ -26,6 +26,7 @@
 #ifndef TRAV_SPT
 #define TRAV_SPT 8
 #endif
+#define TRAV_BATCH 8
 
 __global__ void __launch_bounds__(TRAV_THREADS) tpgx_traverse_kernel(const tpgx_trav_params p) {
     __shared__ unsigned int s_table[256];
@@ -55,18 +56,37 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_traverse_kernel(const tpgx_
             bool have = false;
             int best_dst = 0;
             double best_bid = 0.0;
-            for (int e = eb; e < ee; e++) {
-                const int dst = __ldg(p.edge_destination + e);
-                if (dst >= 0) {
-                    bool seen = false;
-                    for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
-                    if (seen) continue;
+            /* bids of up to TRAV_BATCH edges are requested together before any is compared: the walk is
+               bound by DRAM latency, so the loads of a team must be in flight at the same time */
+            for (int e0 = eb; e0 < ee; e0 += TRAV_BATCH) {
+                double bids[TRAV_BATCH];
+                int dsts[TRAV_BATCH];
+#pragma unroll
+                for (int i = 0; i < TRAV_BATCH; i++) {
+                    const int e = e0 + i;
+                    dsts[i] = 0;
+                    bids[i] = 0.0;
+                    if (e < ee) {
+                        dsts[i] = __ldg(p.edge_destination + e);
+                        bids[i] = __ldg(p.bid + (size_t)__ldg(p.edge_row + e) * p.row_stride + s);
+                    }
                 }
-                const double bid = __ldg(p.bid + (size_t)__ldg(p.edge_row + e) * p.row_stride + s);
-                c_prog++;
-                c_line += (unsigned int)__ldg(p.edge_lines + e);
-                const bool take = !have || (p.tie_break == TPGX_TIE_LAST_MAX ? (bid >= best_bid) : (bid > best_bid));
-                if (take) { have = true; best_dst = dst; best_bid = bid; }
+#pragma unroll
+                for (int i = 0; i < TRAV_BATCH; i++) {
+                    const int e = e0 + i;
+                    if (e >= ee) break;
+                    const int dst = dsts[i];
+                    if (dst >= 0) {
+                        bool seen = false;
+                        for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
+                        if (seen) continue;
+                    }
+                    const double bid = bids[i];
+                    c_prog++;
+                    c_line += (unsigned int)__ldg(p.edge_lines + e);
+                    const bool take = !have || (p.tie_break == TPGX_TIE_LAST_MAX ? (bid >= best_bid) : (bid > best_bid));
+                    if (take) { have = true; best_dst = dst; best_bid = bid; }
+                }
             }
             if (!have) { err |= TPGX_DEV_NO_EDGE; break; }
             if (best_dst < 0) { action = -1 - best_dst; break; } /* destination is an action */
