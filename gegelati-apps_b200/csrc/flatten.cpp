@@ -58,75 +58,108 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     tpgx_flat_graph& f = *out;
     f = tpgx_flat_graph();
     f.nb_programs = g->nb_programs;
-    f.prog_offset.reserve(g->nb_programs + 1);
-    f.prog_offset.push_back(0);
     f.prog_flops.resize(g->nb_programs);
     if (cfg.nb_constants > 0) f.constants.assign(g->constants, g->constants + (size_t)g->nb_programs * cfg.nb_constants);
 
-    std::vector<uint8_t> keep;
-    for (int p = 0; p < g->nb_programs; p++) {
-        const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
-        if (e < b) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p));
-        const tpgx_line* L = g->lines + b;
-        const int n = (int)(e - b);
-        /* validate + backward liveness */
-        keep.assign(n, 0);
-        bool live[TPGX_MAX_REGS] = {false};
-        live[0] = true;
-        for (int i = n - 1; i >= 0; i--) {
-            const tpgx_line& l = L[i];
-            if (l.instruction >= opcode.size()) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", p, i, l.instruction));
-            if (l.destination >= (uint32_t)R) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: destination register out of range", p, i));
-            const tpgx_op_info oi = tpgx_get_op_info(opcode[l.instruction]);
-            for (int k = 0; k < oi.nb_operands; k++) {
-                if ((int)l.src[k] >= sm.total()) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", p, i, l.src[k]));
-                if (sm.space((int)l.src[k], oi.type[k]) == 0)
-                    return fail(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", p, i, l.src[k]));
-            }
-            if (!live[l.destination]) continue;
-            keep[i] = 1;
-            live[l.destination] = false;
-            for (int k = 0; k < oi.nb_operands; k++)
-                if (l.src[k] == 0) live[l.loc[k] % (uint32_t)R] = true;
-        }
-        if (g->intron) {
-            for (int i = 0; i < n; i++)
-                if ((g->intron[b + i] != 0) == (keep[i] != 0))
-                    return fail(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i));
-        }
-        /* encode effective lines */
-        bool written[TPGX_MAX_REGS] = {false};
-        int flops = 0;
-        for (int i = 0; i < n; i++) {
-            if (!keep[i]) { f.total_introns++; continue; }
-            const tpgx_line& l = L[i];
-            const int op = opcode[l.instruction];
-            const tpgx_op_info oi = tpgx_get_op_info(op);
-            uint32_t kind[2] = {TPGX_KIND_REG, TPGX_KIND_REG}, loc[2] = {TPGX_LOC_ZERO, TPGX_LOC_ZERO};
-            for (int k = 0; k < oi.nb_operands; k++) {
-                const int s = (int)l.src[k];
-                uint32_t a = l.loc[k] % sm.space(s, oi.type[k]);
-                if (s == 0) { kind[k] = TPGX_KIND_REG; loc[k] = written[a] ? a : TPGX_LOC_ZERO; }
-                else if (cfg.nb_constants > 0 && s == 1) { kind[k] = TPGX_KIND_CONST; loc[k] = a; }
-                else {
-                    const int ks = s - sm.first_env();
-                    kind[k] = ks == 0 ? TPGX_KIND_SRC0 : TPGX_KIND_SRC1;
-                    if (oi.type[k] == TPGX_T_W) { /* [UP] Array2DWrapper window address -> top-left element */
-                        const uint32_t ww = (uint32_t)src[ks].width - 2u;
-                        a = (a / ww) * (uint32_t)src[ks].width + (a % ww);
+    /* pass 1 (parallel over programs): validate, mark introns by backward liveness, count effective lines */
+    const int P = g->nb_programs;
+    const int64_t total_in = P > 0 ? g->program_line_offset[P] : 0;
+    if (total_in < 0) return fail(TPGX_ERR_BAD_ARG, "negative line count");
+    std::vector<uint8_t> keep((size_t)total_in, 0);
+    std::vector<int32_t> n_eff((size_t)P, 0);
+    struct Err { tpgx_status st = TPGX_OK; std::string msg; };
+    std::vector<Err> errs(tpgx_parallel_workers());
+    for (int p = 0; p < P; p++)
+        if (g->program_line_offset[p + 1] < g->program_line_offset[p] || g->program_line_offset[p] < 0)
+            return fail(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p));
+    tpgx_parallel_blocks(P, 256, [&](int pb, int pe, int w) {
+        Err& er = errs[w];
+        auto bad = [&](tpgx_status st, const std::string& m) { if (er.st == TPGX_OK) { er.st = st; er.msg = m; } };
+        for (int p = pb; p < pe && er.st == TPGX_OK; p++) {
+            const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
+            const tpgx_line* L = g->lines + b;
+            const int n = (int)(e - b);
+            bool live[TPGX_MAX_REGS] = {false};
+            live[0] = true;
+            int cnt = 0;
+            for (int i = n - 1; i >= 0; i--) {
+                const tpgx_line& l = L[i];
+                if (l.instruction >= opcode.size()) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", p, i, l.instruction)); break; }
+                if (l.destination >= (uint32_t)R) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: destination register out of range", p, i)); break; }
+                const tpgx_op_info oi = tpgx_get_op_info(opcode[l.instruction]);
+                bool ok = true;
+                for (int k = 0; k < oi.nb_operands && ok; k++) {
+                    if ((int)l.src[k] >= sm.total()) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", p, i, l.src[k])); ok = false; }
+                    else if (sm.space((int)l.src[k], oi.type[k]) == 0) {
+                        bad(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", p, i, l.src[k]));
+                        ok = false;
                     }
-                    if (a >= TPGX_MAX_LOC) return fail(TPGX_ERR_UNSUPPORTED, fmt("program %ld line %ld: location %ld exceeds the 10-bit device field", p, i, a));
-                    loc[k] = a;
                 }
+                if (!ok) break;
+                if (!live[l.destination]) continue;
+                keep[b + i] = 1;
+                cnt++;
+                live[l.destination] = false;
+                for (int k = 0; k < oi.nb_operands; k++)
+                    if (l.src[k] == 0) live[l.loc[k] % (uint32_t)R] = true;
             }
-            f.code.push_back(tpgx_pack_line((uint32_t)op, l.destination, kind[0], loc[0], kind[1], loc[1]));
-            written[l.destination] = true;
-            flops += oi.flops;
-            f.total_lines++;
+            n_eff[p] = cnt;
+            if (g->intron && er.st == TPGX_OK) {
+                for (int i = 0; i < n; i++)
+                    if ((g->intron[b + i] != 0) == (keep[b + i] != 0)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i)); break; }
+            }
         }
-        f.prog_flops[p] = flops;
-        f.prog_offset.push_back((int32_t)f.code.size());
-    }
+    });
+    for (const Err& er : errs) if (er.st != TPGX_OK) return fail(er.st, er.msg);
+    f.prog_offset.assign((size_t)P + 1, 0);
+    for (int p = 0; p < P; p++) f.prog_offset[p + 1] = f.prog_offset[p] + n_eff[p];
+    f.code.assign((size_t)f.prog_offset[P], 0u);
+    f.total_lines = f.prog_offset[P];
+    f.total_introns = total_in - f.total_lines;
+
+    /* pass 2 (parallel): encode the effective lines */
+    tpgx_parallel_blocks(P, 256, [&](int pb, int pe, int w) {
+        Err& er = errs[w];
+        for (int p = pb; p < pe && er.st == TPGX_OK; p++) {
+            const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
+            const tpgx_line* L = g->lines + b;
+            const int n = (int)(e - b);
+            bool written[TPGX_MAX_REGS] = {false};
+            int flops = 0;
+            uint32_t* out_code = f.code.data() + f.prog_offset[p];
+            for (int i = 0; i < n; i++) {
+                if (!keep[b + i]) continue;
+                const tpgx_line& l = L[i];
+                const int op = opcode[l.instruction];
+                const tpgx_op_info oi = tpgx_get_op_info(op);
+                uint32_t kind[2] = {TPGX_KIND_REG, TPGX_KIND_REG}, loc[2] = {TPGX_LOC_ZERO, TPGX_LOC_ZERO};
+                for (int k = 0; k < oi.nb_operands; k++) {
+                    const int s = (int)l.src[k];
+                    uint32_t a = l.loc[k] % sm.space(s, oi.type[k]);
+                    if (s == 0) { kind[k] = TPGX_KIND_REG; loc[k] = written[a] ? a : TPGX_LOC_ZERO; }
+                    else if (cfg.nb_constants > 0 && s == 1) { kind[k] = TPGX_KIND_CONST; loc[k] = a; }
+                    else {
+                        const int ks = s - sm.first_env();
+                        kind[k] = ks == 0 ? TPGX_KIND_SRC0 : TPGX_KIND_SRC1;
+                        if (oi.type[k] == TPGX_T_W) { /* [UP] Array2DWrapper window address -> top-left element */
+                            const uint32_t ww = (uint32_t)src[ks].width - 2u;
+                            a = (a / ww) * (uint32_t)src[ks].width + (a % ww);
+                        }
+                        if (a >= TPGX_MAX_LOC) {
+                            if (er.st == TPGX_OK) { er.st = TPGX_ERR_UNSUPPORTED; er.msg = fmt("program %ld line %ld: location %ld exceeds the 10-bit device field", p, i, a); }
+                            a = 0;
+                        }
+                        loc[k] = a;
+                    }
+                }
+                *out_code++ = tpgx_pack_line((uint32_t)op, l.destination, kind[0], loc[0], kind[1], loc[1]);
+                written[l.destination] = true;
+                flops += oi.flops;
+            }
+            f.prog_flops[p] = flops;
+        }
+    });
+    for (const Err& er : errs) if (er.st != TPGX_OK) return fail(er.st, er.msg);
 
     f.nb_teams = g->nb_teams;
     f.team_edge_offset.assign(g->team_edge_offset, g->team_edge_offset + g->nb_teams + 1);

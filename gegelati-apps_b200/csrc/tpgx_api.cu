@@ -135,27 +135,40 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
     if ((st = upload(ctx, ctx->d_roots, f.root_team.data() + rb, (size_t)(re - rb) * 4)) != TPGX_OK) return st;
     /* K1 stream: per row its constants (TPGX_K1_CQ quads) followed by its pre-decoded wide lines */
     {
-        std::vector<tpgx_k1_quad> stream;
-        bool ext = false;
-        std::vector<int32_t> desc(2 * ctx->h_active.size());
-        stream.reserve((size_t)pl.active_lines + (size_t)TPGX_K1_CQ * ctx->h_active.size() + 64);
-        const int nc = ctx->cfg.nb_constants;
-        for (size_t row = 0; row < ctx->h_active.size(); row++) {
+        const int nrows = (int)ctx->h_active.size();
+        std::vector<int32_t> desc(2 * (size_t)nrows);
+        int64_t nq = 0;
+        for (int row = 0; row < nrows; row++) {
             const int p = ctx->h_active[row];
-            desc[2 * row] = (int32_t)stream.size();
+            desc[2 * row] = (int32_t)nq;
             desc[2 * row + 1] = f.prog_offset[p + 1] - f.prog_offset[p];
-            double cq[2 * TPGX_K1_CQ] = {0};
-            for (int c = 0; c < nc; c++) cq[c] = f.constants[(size_t)p * nc + c];
-            tpgx_k1_quad q[TPGX_K1_CQ];
-            memcpy(q, cq, sizeof q);
-            stream.insert(stream.end(), q, q + TPGX_K1_CQ);
-            for (int i = f.prog_offset[p]; i < f.prog_offset[p + 1]; i++) {
-                stream.push_back(tpgx_k1_line(f.code[i], (uint32_t)ts));
-                if (stream.back().x == 0xffffffffu) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
-                ext |= tpgx_k1_is_extended(stream.back().x);
-            }
+            nq += TPGX_K1_CQ + desc[2 * row + 1];
         }
-        stream.resize(stream.size() + 64, tpgx_k1_quad{0, 0, 0, 0}); /* slack: a lane may read up to 32 quads past a row's start */
+        std::vector<tpgx_k1_quad> stream((size_t)nq + 64, tpgx_k1_quad{0, 0, 0, 0}); /* slack: a lane may address up to 32 quads past a row's start */
+        const int nc = ctx->cfg.nb_constants;
+        std::vector<int> flags(tpgx_parallel_workers(), 0); /* bit 0: extended instruction, bit 1: int-typed instruction */
+        tpgx_parallel_blocks(nrows, 256, [&](int rb2, int re2, int w) {
+            int fl = 0;
+            for (int row = rb2; row < re2; row++) {
+                const int p = ctx->h_active[row];
+                tpgx_k1_quad* q = stream.data() + desc[2 * row];
+                double cq[2 * TPGX_K1_CQ] = {0};
+                for (int c = 0; c < nc; c++) cq[c] = f.constants[(size_t)p * nc + c];
+                memcpy(q, cq, sizeof cq);
+                q += TPGX_K1_CQ;
+                for (int i = f.prog_offset[p]; i < f.prog_offset[p + 1]; i++, q++) {
+                    *q = tpgx_k1_line(f.code[i], (uint32_t)ts);
+                    if (q->x == 0xffffffffu) fl |= 2;
+                    else if (tpgx_k1_is_extended(q->x)) fl |= 1;
+                }
+            }
+            flags[w] |= fl;
+        });
+        bool ext = false;
+        for (int fl : flags) {
+            if (fl & 2) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
+            ext |= (fl & 1) != 0;
+        }
         if ((st = upload(ctx, ctx->d_k1_stream, stream.data(), stream.size() * sizeof(tpgx_k1_quad))) != TPGX_OK) return st;
         if ((st = upload(ctx, ctx->d_k1_desc, desc.data(), desc.size() * 4)) != TPGX_OK) return st;
         CU(cudaStreamSynchronize(ctx->stream)); /* stream / desc are locals */

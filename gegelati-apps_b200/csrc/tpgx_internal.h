@@ -24,7 +24,9 @@
 
 #include <stdint.h>
 
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/tpgx.h"
@@ -155,6 +157,22 @@ struct tpgx_flat_graph {
     std::vector<int32_t> team_edge_offset, edge_program, edge_destination, root_team;
     int64_t total_lines = 0, total_introns = 0;
 };
+
+/* Splits [0, n) into contiguous blocks over up to 16 host threads (the host side of a generation is
+ * pure per-program work: intron marking, encoding); fn(begin, end, worker) runs once per block. */
+template <class F> static inline void tpgx_parallel_blocks(int n, int min_per_thread, F fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+    nt = std::max(1, std::min(nt, n / std::max(1, min_per_thread)));
+    if (nt <= 1) { fn(0, n, 0); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    const int per = (n + nt - 1) / nt;
+    for (int t = 1; t < nt; t++) th.emplace_back([=, &fn] { fn(std::min(n, t * per), std::min(n, (t + 1) * per), t); });
+    fn(0, std::min(n, per), 0);
+    for (auto& x : th) x.join();
+}
+static inline int tpgx_parallel_workers() { return 16; }
 
 /* Validates and flattens; returns TPGX_OK or an error code with a message in err. */
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
