@@ -171,7 +171,32 @@ def import_dot(path_or_text, nb_constants):
 
 
 def random_programs(rng, nb_programs, nb_lines, opcodes, sources, nb_registers, nb_constants, allowed=None,
-                    intron_lines=0, const_range=(-10, 10), integer_constants=True):
+                    intron_lines=0, const_range=(-10, 10), integer_constants=True, balance=True):
+    """Programs whose EFFECTIVE lines follow a uniform instruction mix over `allowed`.
+
+    A line that reads no register (a 3x3 window instruction) cannot be placed where it would leave no live
+    register for the earlier lines, so drawing instructions uniformly under-represents those instructions
+    (3.7 % instead of 10 % for the MNIST set).  With balance=True the draw weights are calibrated by a few
+    deterministic fixed-point passes so that the realised mix is uniform (4.7 flop per
+    line for the MNIST set)."""
+    allowed_arr = np.arange(len(opcodes)) if allowed is None else np.asarray(allowed)
+    base_seed = int(rng.integers(0, 2 ** 62))
+    weights = np.ones(len(allowed_arr)) / len(allowed_arr)
+    passes = 8 if (balance and nb_programs * nb_lines >= 2000 and len(allowed_arr) > 1) else 1
+    out = None
+    for t in range(passes):
+        out = _random_programs(np.random.default_rng([base_seed, 0 if passes == 1 else t]), nb_programs, nb_lines, opcodes, sources,
+                               nb_registers, nb_constants, allowed_arr, intron_lines, const_range, integer_constants, weights)
+        if t + 1 < passes:
+            ins = out[0]["instruction"].reshape(nb_programs, -1)[:, :nb_lines].ravel()
+            got = np.array([(ins == a).mean() for a in allowed_arr])
+            weights = weights * (1.0 / len(allowed_arr)) / np.maximum(got, 1e-4)
+            weights /= weights.sum()
+    return out
+
+
+def _random_programs(rng, nb_programs, nb_lines, opcodes, sources, nb_registers, nb_constants, allowed,
+                     intron_lines, const_range, integer_constants, weights):
     """nb_programs programs with exactly nb_lines EFFECTIVE lines each (built backward from r0 so that
     every destination is read later), plus `intron_lines` random extra lines spliced in that the
     intron pass must remove.  Instruction indices uniform over `allowed` (default: the whole set);
@@ -179,7 +204,6 @@ def random_programs(rng, nb_programs, nb_lines, opcodes, sources, nb_registers, 
     over [0, largest address space) and left un-reduced, like [UP] Mutator::LineMutator."""
     P, L = nb_programs, nb_lines
     n_ops = len(opcodes)
-    allowed = np.arange(n_ops) if allowed is None else np.asarray(allowed)
     sigs = [A.OP_SIGNATURE[o] for o in opcodes]
     first_env = 2 if nb_constants > 0 else 1
     n_src = first_env + len(sources)
@@ -195,7 +219,7 @@ def random_programs(rng, nb_programs, nb_lines, opcodes, sources, nb_registers, 
         score = rng.random((P, nb_registers)) * live
         dst = score.argmax(axis=1)
         live[np.arange(P), dst] = False
-        ins = allowed[rng.integers(0, len(allowed), P)]
+        ins = allowed[rng.choice(len(allowed), P, p=weights)]
         need_reg = (~live.any(axis=1)) & (i > 0)
         if need_reg.any():
             if len(allowed_reg) == 0:
