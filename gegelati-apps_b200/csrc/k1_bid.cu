@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
     __syncthreads();
     if (threadIdx.x == 0) {
         mbar_expect_tx(bar, (uint32_t)tile_bytes);
-        tma_load_1d(tile, p.tiles + (size_t)blockIdx.x * tile_bytes, (uint32_t)tile_bytes, bar);
+        tma_load_1d(tile, p.tiles + (size_t)blockIdx.y * tile_bytes, (uint32_t)tile_bytes, bar);
     }
     const uint32_t regs_lane = smem_u32(regs) + warp * (K1_SLOTS * TS * 8) + lane * 16;
     const uint32_t tile_lane = smem_u32(tile) + lane * K;
@@ -147,9 +147,11 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
         st_regs<K>(regs_lane + TPGX_LOC_ZERO * TS * 8, z);
     }
 
-    const int chunk_begin = blockIdx.y * p.progs_per_chunk;
+    const int chunk_begin = blockIdx.x * p.progs_per_chunk; /* chunks vary fastest: CTAs resident together share tiles (L2) */
     const int chunk_n = min(p.progs_per_chunk, p.nb_active - chunk_begin);
-    const int wrow = p.width * TS;
+    /* this tile's Sobel planes: [which][window][TS samples] doubles; the lane's K samples are consecutive */
+    const long long plane_stride = (long long)p.nwin * TS;
+    const double* const sobel_lane = p.sobel + (size_t)blockIdx.y * 2 * plane_stride + lane * K;
     const uint4* __restrict__ stream = p.stream;
 
     auto claim = [&]() {
@@ -231,39 +233,13 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                     }
                     st_regs<K>(rd, r);
                 } else if (op == TPGX_K1X_SOBEL_MAGN || op == TPGX_K1X_SOBEL_DIR) {
-                    /* window ops in exact integer arithmetic: pixels are integers, so every partial sum
-                       of the reference's double expression is an exactly representable integer */
-                    int gx[K], gy[K];
-                    if (K == 2) {
-                        /* both samples of the lane at once: each 16-bit load becomes two 16-bit fields of one
-                           register (PRMT), the gradients are summed per field with 32-bit adds — a +1024 bias
-                           keeps every field positive so nothing borrows across the field boundary */
-                        auto px2 = [&](uint32_t addr) { return __byte_perm(lds_u16(addr), 0, 0x4140); };
-                        const uint32_t q00 = px2(pa), q01 = px2(pa + TS), q02 = px2(pa + 2 * TS);
-                        const uint32_t q10 = px2(pa + wrow), q12 = px2(pa + wrow + 2 * TS);
-                        const uint32_t q20 = px2(pa + 2 * wrow), q21 = px2(pa + 2 * wrow + TS), q22 = px2(pa + 2 * wrow + 2 * TS);
-                        const uint32_t BIAS = 0x04000400u;
-                        const uint32_t gxp = (q02 + q22 + 2 * q12 + BIAS) - (q00 + q20 + 2 * q10);
-                        const uint32_t gyp = (q20 + q22 + 2 * q21 + BIAS) - (q00 + q02 + 2 * q01);
-                        gx[0] = (int)(gxp & 0xffffu) - 1024; gx[K - 1] = (int)(gxp >> 16) - 1024;
-                        gy[0] = (int)(gyp & 0xffffu) - 1024; gy[K - 1] = (int)(gyp >> 16) - 1024;
-                    } else {
-                        uint32_t a00[K], a01[K], a02[K], a10[K], a12[K], a20[K], a21[K], a22[K];
-                        ld_px<K>(pa, a00); ld_px<K>(pa + TS, a01); ld_px<K>(pa + 2 * TS, a02);
-                        ld_px<K>(pa + wrow, a10); ld_px<K>(pa + wrow + 2 * TS, a12);
-                        ld_px<K>(pa + 2 * wrow, a20); ld_px<K>(pa + 2 * wrow + TS, a21); ld_px<K>(pa + 2 * wrow + 2 * TS, a22);
+                    /* window instructions read only the image: their values were computed once per upload
+                       (K0b, tpgx_sobel_planes_kernel) and are fetched as one coalesced 16-byte load per lane */
+                    const double* src = sobel_lane + (op == TPGX_K1X_SOBEL_DIR ? plane_stride : 0) + (ln.y >> 3);
 #pragma unroll
-                        for (int k = 0; k < K; k++) {
-                            gx[k] = -(int)a00[k] + (int)a02[k] - 2 * (int)a10[k] + 2 * (int)a12[k] - (int)a20[k] + (int)a22[k];
-                            gy[k] = -(int)a00[k] - 2 * (int)a01[k] - (int)a02[k] + (int)a20[k] + 2 * (int)a21[k] + (int)a22[k];
-                        }
-                    }
-                    if (op == TPGX_K1X_SOBEL_MAGN) {
-#pragma unroll
-                        for (int k = 0; k < K; k++) r[k] = tpgx_math::xsqrt_nonneg((double)(gx[k] * gx[k] + gy[k] * gy[k]));
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < K; k++) r[k] = tpgx_math::atan(tpgx_math::xdiv_small_int(gy[k], gx[k]));
+                    for (int k = 0; k < K; k += 2) {
+                        const double2 v = __ldg(reinterpret_cast<const double2*>(src + k));
+                        r[k] = v.x; r[k + 1] = v.y;
                     }
                     st_regs<K>(rd, r);
                 } else {
@@ -319,7 +295,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
 #pragma unroll
         for (int k = 0; k < K; k++)
             if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
-        double* out = p.bid + (size_t)(chunk_begin + i0) * p.row_stride + (size_t)blockIdx.x * TS + lane * K;
+        double* out = p.bid + (size_t)(chunk_begin + i0) * p.row_stride + (size_t)blockIdx.y * TS + lane * K;
 #pragma unroll
         for (int k = 0; k < K; k += 2) *reinterpret_cast<double2*>(out + k) = make_double2(res[k], res[k + 1]);
 
@@ -347,7 +323,7 @@ size_t tpgx_bid_smem_bytes(int variant, int hw) {
 template <int K, int NW>
 static cudaError_t launch_bid_t(const tpgx_bid_params& p, int nb_tiles, size_t smem, bool ext, cudaStream_t st) {
     const int chunks = (p.nb_active + p.progs_per_chunk - 1) / p.progs_per_chunk;
-    dim3 grid(nb_tiles, chunks);
+    dim3 grid(chunks, nb_tiles);
     cudaError_t e;
     if (ext) {
         e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

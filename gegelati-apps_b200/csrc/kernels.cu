@@ -195,6 +195,39 @@ cudaError_t tpgx_launch_pack(const uint8_t* obs, const int32_t* sample_index, lo
 }
 
 /* ================================================================================================
+ * K0b — Sobel planes.  sobelMagn / sobelDir read nothing but the image, so their value at each of the
+ * (h-2)(w-2) window positions of each sample is a property of the OBSERVATIONS, not of a program:
+ * it is computed once per upload (by the tpgx_math routines, through the memoised gradient tables)
+ * and K1's Sobel handlers become one coalesced 16-byte load per lane.
+ * planes[tile][which][wp][TS] doubles, which = 0 magnitude, 1 direction.  thread = (window, sample).  */
+__global__ void __launch_bounds__(256) tpgx_sobel_planes_kernel(const uint8_t* __restrict__ tiles, int hw, int width, int nwin_w,
+                                                                int nwin, int ts, const double* __restrict__ lut,
+                                                                double* __restrict__ planes) {
+    const long long tile = blockIdx.y;
+    const int q = blockIdx.x * 256 + threadIdx.x;     /* (window position, sample) flattened, sample fastest */
+    if (q >= nwin * ts) return;
+    const int wp = q / ts, j = q % ts;
+    const int top = (wp / nwin_w) * width + (wp % nwin_w);
+    const uint8_t* t = tiles + tile * (long long)hw * ts + j;
+    auto px = [&](int dr, int dc) { return (int)t[(long long)(top + dr * width + dc) * ts]; };
+    const int gx = -px(0, 0) + px(0, 2) - 2 * px(1, 0) + 2 * px(1, 2) - px(2, 0) + px(2, 2);
+    const int gy = -px(0, 0) - 2 * px(0, 1) - px(0, 2) + px(2, 0) + 2 * px(2, 1) + px(2, 2);
+    const int idx = abs(gy) * TPGX_SOBEL_LUT_N + abs(gx);
+    const double magn = lut[512 + idx];
+    const double d = lut[512 + TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N + idx];
+    double* out = planes + tile * 2ll * nwin * ts;
+    out[(long long)wp * ts + j] = magn;
+    out[((long long)nwin + wp) * ts + j] = ((gy ^ gx) < 0) ? -d : d; /* atan(gy/gx) is odd in each; also gives -0 for 0 / negative */
+}
+cudaError_t tpgx_launch_sobel_planes(const uint8_t* tiles, long long nb_tiles, int hw, int height, int width, int ts, const double* lut,
+                                     double* planes, cudaStream_t st) {
+    const int nwin_w = width - 2, nwin = (height - 2) * nwin_w;
+    dim3 grid((nwin * ts + 255) / 256, (unsigned)nb_tiles);
+    tpgx_sobel_planes_kernel<<<grid, 256, 0, st>>>(tiles, hw, width, nwin_w, nwin, ts, lut, planes);
+    return cudaGetLastError();
+}
+
+/* ================================================================================================
  * Generic executor: thread = (program, observation) on explicit f64 / i32 observations.
  * Replaces [UP] ProgramExecutionEngine::executeProgram for tpgx_execute_programs (parity tests of
  * every opcode on every source shape); NaN -> -inf applied like evaluateEdge.                      */
@@ -236,8 +269,22 @@ __global__ void tpgx_pixel_lut_kernel(double* __restrict__ lut) {
     lut[v] = tpgx_math::exp((double)v);
     lut[256 + v] = tpgx_math::log((double)v);
 }
+/* Sobel results memoised over the gradient domain: pixels are uint8, so |gx|, |gy| <= 1020 and
+ * sobelMagn / sobelDir are functions of 1021 x 1021 integer pairs (sign restored by the caller).
+ * Filled by the routines the interpreter would otherwise run per sample, so the bits are the same. */
+__global__ void tpgx_sobel_lut_kernel(double* __restrict__ magn, double* __restrict__ dir) {
+    const int ax = blockIdx.x * blockDim.x + threadIdx.x, ay = blockIdx.y;
+    if (ax >= TPGX_SOBEL_LUT_N) return;
+    magn[ay * TPGX_SOBEL_LUT_N + ax] = tpgx_math::xsqrt_nonneg((double)(ax * ax + ay * ay));
+    dir[ay * TPGX_SOBEL_LUT_N + ax] = tpgx_math::atan(tpgx_math::xdiv_small_int(ay, ax));
+}
 cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st) {
     tpgx_pixel_lut_kernel<<<1, 256, 0, st>>>(lut);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    double* magn = lut + 512;
+    dim3 grid((TPGX_SOBEL_LUT_N + 127) / 128, TPGX_SOBEL_LUT_N);
+    tpgx_sobel_lut_kernel<<<grid, 128, 0, st>>>(magn, magn + TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N);
     return cudaGetLastError();
 }
 

@@ -15,7 +15,10 @@ struct tpgx_bid_params {
     int hw, width;               /* elements per observation, row length                              */
     const uint4* stream;         /* per bid-matrix row: TPGX_K1_CQ constant quads, then its wide lines */
     const int2* desc;            /* [nb_active] {first quad of the row in stream, number of lines}      */
-    const double* pixel_lut;     /* [2][256] exp / ln of every uint8 pixel value (tpgx_math, filled on the device) */
+    const double* pixel_lut;     /* [2][256] exp / ln of every uint8 pixel value, then [2][1021][1021] sobelMagn / sobelDir
+                                    of every |gy|, |gx| (filled on the device by the tpgx_math routines)          */
+    const double* sobel;         /* [tiles][2][nwin][TS] sobelMagn / sobelDir of every window position (first tile of the pass) */
+    int nwin;                    /* window positions per observation, (h-2)(w-2)                        */
     int nb_active;
     int progs_per_chunk;
     double* bid;                 /* [nb_active][row_stride]                                            */
@@ -43,6 +46,9 @@ struct tpgx_trav_params {
     int* status;                 /* OR of TPGX_DEV_* error bits                                         */
 };
 
+#define TPGX_SOBEL_LUT_N 1021
+#define TPGX_LUT_DOUBLES (512 + 2 * TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N)
+
 #define TPGX_DEV_NO_EDGE 1
 #define TPGX_DEV_PATH_TOO_LONG 2
 #define TPGX_DEV_BAD_ACTION 4
@@ -63,6 +69,8 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
                                      const double* f0, const double* f1, const int32_t* i0, const int32_t* i1,
                                      int space0, int space1, int width0, int width1, double* bid, cudaStream_t st);
 cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st);
+cudaError_t tpgx_launch_sobel_planes(const uint8_t* tiles, long long nb_tiles, int hw, int height, int width, int ts, const double* lut,
+                                     double* planes, cudaStream_t st);
 cudaError_t tpgx_launch_math_probe(int fn, long long n, const double* a, const double* b, double* out, cudaStream_t st);
 cudaError_t tpgx_launch_fp64_peak(int mode /*0 dadd+dmul, 1 dfma*/, int blocks, int iters, double* sink, cudaStream_t st);
 

@@ -62,14 +62,14 @@ struct tpgx_ctx {
     int variant = 0;
     size_t bid_budget = (size_t)16 << 30;
 
-    DevBuf d_pixel_lut;
+    DevBuf d_pixel_lut, d_sobel;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[8];
     const uint8_t* obs_dev = nullptr;    /* raw observations [nb_obs][hw] (ours or the caller's) */
     const uint8_t* labels_dev = nullptr;
     int64_t nb_obs = 0;
-    int obs_hw = 0, obs_width = 0;
+    int obs_hw = 0, obs_width = 0, nwin = 0;
     bool tiles_identity_valid = false;   /* d_tiles holds the identity packing of all observations */
     int tiles_ts = 0;
     ShardPlan plan;
@@ -157,7 +157,7 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
                 memcpy(q, cq, sizeof cq);
                 q += TPGX_K1_CQ;
                 for (int i = f.prog_offset[p]; i < f.prog_offset[p + 1]; i++, q++) {
-                    *q = tpgx_k1_line(f.code[i], (uint32_t)ts);
+                    *q = tpgx_k1_line(f.code[i], (uint32_t)ts, (uint32_t)ctx->obs_width);
                     if (q->x == 0xffffffffu) fl |= 2;
                     else if (tpgx_k1_is_extended(q->x)) fl |= 1;
                 }
@@ -175,6 +175,18 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
         pl.k1_ext = ext;
     }
     pl.root_begin = rb; pl.root_end = re; pl.graph_version = ctx->graph_version; pl.k1_ts = ts;
+    return TPGX_OK;
+}
+
+/* K0b after every re-tiling: sobelMagn / sobelDir planes of the tiles (2-D sources of at least 3x3 only) */
+tpgx_status sobel_planes(tpgx_ctx* ctx, int64_t nTiles, int ts) {
+    const tpgx_source_desc& d = ctx->src[0];
+    ctx->nwin = 0;
+    if (!d.is_2d || d.height < 3 || d.width < 3) return TPGX_OK;
+    ctx->nwin = (d.height - 2) * (d.width - 2);
+    CU(ctx->d_sobel.ensure((size_t)nTiles * 2 * ctx->nwin * ts * 8));
+    CU(tpgx_launch_sobel_planes(ctx->d_tiles.as<uint8_t>(), nTiles, ctx->obs_hw, d.height, d.width, ts, ctx->d_pixel_lut.as<double>(),
+                                ctx->d_sobel.as<double>(), ctx->stream));
     return TPGX_OK;
 }
 
@@ -219,6 +231,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         CU(ctx->d_labels.ensure((size_t)nTiles * ts));
         CU(tpgx_launch_pack(ctx->obs_dev, d_index, nS, ctx->nb_obs, hw, ts, ctx->d_tiles.as<uint8_t>(), ctx->labels_dev,
                             ctx->d_labels.as<uint8_t>(), ctx->stream));
+        if ((st = sobel_planes(ctx, nTiles, ts)) != TPGX_OK) return st;
         ctx->tiles_identity_valid = identity;
         ctx->tiles_ts = ts;
     }
@@ -252,6 +265,8 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.stream = ctx->d_k1_stream.as<uint4>();
             bp.desc = ctx->d_k1_desc.as<int2>();
             bp.pixel_lut = ctx->d_pixel_lut.as<double>();
+            bp.sobel = ctx->nwin ? ctx->d_sobel.as<double>() + (size_t)t0 * 2 * ctx->nwin * ts : nullptr;
+            bp.nwin = ctx->nwin;
             bp.nb_active = nA;
             /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 programs per warp */
             int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
@@ -326,7 +341,7 @@ tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out) {
     ctx->cfg = *cfg;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, TPGX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
-    if (ctx->d_pixel_lut.ensure(2 * 256 * 8) != cudaSuccess || tpgx_launch_pixel_lut(ctx->d_pixel_lut.as<double>(), ctx->stream) != cudaSuccess ||
+    if (ctx->d_pixel_lut.ensure((size_t)TPGX_LUT_DOUBLES * 8) != cudaSuccess || tpgx_launch_pixel_lut(ctx->d_pixel_lut.as<double>(), ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
         cudaStreamDestroy(ctx->stream);
         delete ctx;
@@ -342,7 +357,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
+    DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
                      &ctx->d_counters, &ctx->d_status};
@@ -429,6 +444,8 @@ static tpgx_status pack_identity(tpgx_ctx* ctx) {
     CU(ctx->d_labels.ensure((size_t)nTiles * ts));
     CU(tpgx_launch_pack(ctx->obs_dev, nullptr, ctx->nb_obs, ctx->nb_obs, ctx->obs_hw, ts, ctx->d_tiles.as<uint8_t>(),
                         ctx->labels_dev, ctx->d_labels.as<uint8_t>(), ctx->stream));
+    tpgx_status st = sobel_planes(ctx, nTiles, ts);
+    if (st != TPGX_OK) return st;
     ctx->tiles_identity_valid = true;
     ctx->tiles_ts = ts;
     return TPGX_OK;

@@ -50,7 +50,7 @@ static inline uint32_t tpgx_pack_line(uint32_t op, uint32_t dst, uint32_t ka, ui
  *   x  handler id (below): for the cheap instructions the operand kinds (register / pixel) are part
  *      of the id, so a line costs one dispatch and no kind tests
  *   y  operand A: byte offset from the lane's register base (slot * TS * 8) or from the lane's pixel
- *      base (loc * TS; for a 3x3 window its top-left pixel)
+ *      base (loc * TS); for a 3x3 window: byte offset of its window index in a Sobel plane (wp * TS * 8)
  *   z  operand B: same, or the byte offset of the program constant (index * 8) for MULC
  *   w  destination register: byte offset from the lane's register base
  * TS = samples per tile (32 * K).  A program's stream entry is TPGX_K1_CQ quads holding its constants
@@ -76,7 +76,7 @@ static inline bool tpgx_k1_is_extended(uint32_t h) {
 
 struct tpgx_k1_quad { uint32_t x, y, z, w; };
 
-static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts) {
+static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts, uint32_t width) {
     const uint32_t op = word & 31u, dst = (word >> 5) & 7u;
     const uint32_t fa = (word >> 8) & 0xfffu, fb = word >> 20;
     const uint32_t pa = (fa >> 10) == TPGX_KIND_SRC0, pb = (fb >> 10) == TPGX_KIND_SRC0;
@@ -105,8 +105,9 @@ static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts) {
     case TPGX_OP_COS: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_COS << 2) | pa; break;
     case TPGX_OP_SIN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SIN << 2) | pa; break;
     case TPGX_OP_TAN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_TAN << 2) | pa; break;
-    case TPGX_OP_SOBEL_MAGN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_MAGN << 2) | 1u; break;
-    case TPGX_OP_SOBEL_DIR: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_DIR << 2) | 1u; break;
+    /* window operand: la is the top-left pixel; the handlers read the precomputed plane at window index wp */
+    case TPGX_OP_SOBEL_MAGN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_MAGN << 2) | 1u; q.y = ((la / width) * (width - 2u) + la % width) * ts * 8u; break;
+    case TPGX_OP_SOBEL_DIR: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_DIR << 2) | 1u; q.y = ((la / width) * (width - 2u) + la % width) * ts * 8u; break;
     default: q.x = 0xffffffffu; break; /* int-typed instructions never reach K1 (no i32 source) */
     }
     return q;
