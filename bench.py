@@ -184,7 +184,7 @@ def main():
     img, lab = tpgx.synthetic_images(S)
     ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5, device=local)
     ev.set_graph(g)
-    rb, re = rank * R, (rank + 1) * R
+    rb, re = tpgx.shard_range(rank, world, R * world)   # contiguous slice of the job-index order: R roots per rank
 
     # ---- device-resident arm: observations already in HBM when the timed region starts
     d_img = torch.from_numpy(img).to(dev)
@@ -198,7 +198,7 @@ def main():
     def step():
         ev.evaluate_classification_device(records.data_ptr(), stream.cuda_stream, S, C, rb, re)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, records)
+            dist.all_gather_into_tensor(gathered, records)   # equal shards: the fixed-size record gather of tpgx.gather_records
 
     def barrier():
         torch.cuda.synchronize()
@@ -264,6 +264,7 @@ def main():
         pass
     roofline = {
         "kernel": "tpgx_bid_kernel (K1 bid interpreter)", "bound": "fp64", "unit": "TFLOP/s",
+        "note": "FP64-issue roofline (north_star): algorithmic flops / CUDA-event time / measured non-FMA FP64 issue rate; the nested hbm object is the same kernel against the HBM roofline",
         "achieved": k1_flops / (k1_ms * 1e-3) / 1e12, "peak": dadd / 1e12,
         "frac": (k1_flops / (k1_ms * 1e-3)) / dadd, "traffic": traffic,
         "peak_source": "measured live: non-FMA DADD/DMUL issue rate (tpgx_measure_fp64_peak); DFMA rate %.2f T instr/s" % (dfma / 1e12),

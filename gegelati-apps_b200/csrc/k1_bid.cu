@@ -154,9 +154,12 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
     const double* const sobel_lane = p.sobel + (size_t)blockIdx.y * 2 * plane_stride + lane * K;
     const uint4* __restrict__ stream = p.stream;
 
+    /* next unclaimed program of the chunk: one shared-memory atomic by lane 0 (plain atom.shared — the
+       compiler's warp-aggregation wrapper around atomicAdd costs ~35 instructions here), broadcast by shuffle */
+    const uint32_t s_next_addr = smem_u32(s_next);
     auto claim = [&]() {
         int i = 0;
-        if (lane == 0) i = atomicAdd(s_next, 1);
+        if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(i) : "r"(s_next_addr) : "memory");
         return __shfl_sync(0xffffffffu, i, 0);
     };
     auto load_desc = [&](int i) { return (i < chunk_n) ? __ldg(p.desc + chunk_begin + i) : make_int2(0, 0); };

@@ -148,3 +148,67 @@ def test_variants_agree(oracle_mod, monkeypatch):
         ev.set_graph(g)
         ev.set_observations(img, lab)
         compare(ev.evaluate_classification(want=("score", "bid", "action", "confusion", "counters")), ref)
+
+
+@pytest.mark.parametrize("lines", [28, 29, 57, 90])
+def test_long_programs_cross_the_staging_buffer(oracle_mod, lines):
+    """K1 stages 28 lines of a program at a time in shared memory (TPGX_K1_CAPL); programs at, just past and
+    several times past that size (tic-tac-toe allows 40 lines: [REF] tic-tac-toe/params.json:30) must give the
+    same bits, registers carried across the reloads."""
+    g, ev = make(roots=6, edges=3, lines=lines, depth=1, seed=100 + lines, intron_lines=1)
+    img, lab = tpgx.synthetic_images(130, seed=2)
+    ev.set_observations(img, lab)
+    want = ("score", "confusion", "action", "bid", "counters")
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+def test_uniform_mix_medium(oracle_mod):
+    """A few thousand lines of the calibrated uniform mix (every instruction ~10 %, both operand kinds, the
+    memoised exp / ln-of-pixel table and the Sobel planes) over several tiles."""
+    g, ev = make(roots=60, edges=5, lines=20, depth=2, share_prob=0.1, seed=77)
+    ins = np.bincount(g.lines["instruction"], minlength=10) / len(g.lines)
+    assert ins.min() > 0.06 and ins.max() < 0.14
+    img, lab = tpgx.synthetic_images(500, seed=21)
+    ev.set_observations(img, lab)
+    want = ("score", "class_f1", "confusion", "action", "bid", "counters")
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+def test_image_borders_and_extreme_pixels(oracle_mod):
+    """All-0 and all-255 images and single bright pixels in every corner: window positions on the image border,
+    gx = gy = 0 (sobelDir = atan(0/0) = NaN -> bid -inf), the largest gradients (+-1020) and log(0)."""
+    g, ev = make(roots=12, edges=5, lines=12, depth=1, seed=31)
+    img = np.zeros((64, 784), dtype=np.uint8)
+    img[1] = 255
+    for i, px in enumerate((0, 27, 756, 783, 28, 55, 392)):
+        img[2 + i, px] = 255
+    img[10:20] = np.random.default_rng(1).integers(0, 2, (10, 784)).astype(np.uint8) * 255   # hard 0 / 255 edges
+    img[20:] = tpgx.synthetic_images(44, seed=4)[0]
+    lab = (np.arange(64) % 10).astype(np.uint8)
+    ev.set_observations(img, lab)
+    want = ("score", "confusion", "action", "bid", "counters")
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+def test_full_size_properties():
+    """BASELINE C2 size (2000 roots x 60 000 samples): too large for the oracle, checked through size-independent
+    properties — every confusion table sums to the sample count, label marginals are the same for all roots,
+    scores lie in [0, 1], counters equal the closed form for a depth-1 graph, and the evaluation is
+    deterministic and shard-invariant (root halves concatenate to the full result)."""
+    R, E, L, S = 2000, 5, 20, 60000
+    g, ev = make(roots=R, edges=E, lines=L, depth=1, seed=42)
+    img, lab = tpgx.synthetic_images(S)
+    ev.set_observations(img, lab)
+    out = ev.evaluate_classification(want=("score", "class_f1", "confusion", "counters"))
+    conf = out["confusion"]
+    assert conf.shape == (R, 10, 10) and (conf.sum(axis=(1, 2)) == S).all()
+    assert (conf.sum(axis=2) == np.bincount(lab, minlength=10)[None, :]).all()
+    assert ((out["score"] >= 0) & (out["score"] <= 1)).all() and np.isfinite(out["class_f1"]).all()
+    assert np.array_equal(bits(out["score"]), bits(out["class_f1"].sum(axis=1) / 10.0)) or np.allclose(out["score"], out["class_f1"].mean(axis=1), rtol=0, atol=1e-15)
+    c = out["counters"]
+    assert (c["evaluations"], c["team_visits"], c["program_executions"], c["lines_executed"]) == (R * S, R * S, R * E * S, R * E * L * S)
+    again = ev.evaluate_classification(want=("score", "confusion"))
+    assert np.array_equal(bits(again["score"]), bits(out["score"])) and np.array_equal(again["confusion"], conf)
+    lo = ev.evaluate_classification(root_begin=0, root_end=R // 2, want=("score",))["score"]
+    hi = ev.evaluate_classification(root_begin=R // 2, root_end=R, want=("score",))["score"]
+    assert np.array_equal(bits(np.concatenate([lo, hi])), bits(out["score"]))
