@@ -2,12 +2,14 @@
  * episodes.cu — batched lock-step restatements of the apps' sequential LearningEnvironments and
  * the episode loop of [UP] LearningAgent::evaluateJob / AdversarialLearningAgent::evaluateJob.
  *
- * thread = one episode (job, iteration).  Per step the thread walks the job's TPG from the acting
- * root ([UP] executeFromRoot / evaluateTeam) running each admissible edge's program on the
- * episode's own observation with the per-thread executor (dev_ops.cuh), then applies the
- * environment's doAction.  Lanes of a warp are consecutive iterations of the same job, so they
- * share programs until their paths diverge.  A second kernel averages the iteration scores in
- * iteration order (the reference's sequential `result += getScore()`).
+ * warp = one episode (job, iteration).  Episodes are sequential (<= 1000 dependent steps) and every
+ * episode follows its own path through the graph, so the first version (thread = episode) ran 32
+ * different instruction streams per warp, serialised.  Now every lane of the warp carries a copy of
+ * the (tiny) environment state and steps it redundantly — uniform control flow — while the team
+ * evaluation of [UP] evaluateTeam is spread over the lanes: lane l interprets the program of the
+ * team's l-th outgoing edge with the per-thread executor (dev_ops.cuh) and a warp reduction picks
+ * the winner with the reference's order-dependent tie-break.  A second kernel averages the
+ * iteration scores in iteration order (the reference's sequential `result += getScore()`).
  *
  * Environment semantics, line by line: SURVEY.md Appendix B;
  *   gridworld  [REF] gridworld/src/gridworld.cpp:3-83
@@ -30,37 +32,59 @@ namespace {
 
 struct ep_counters { unsigned int eval, team, prog, line; };
 
-/* [UP] executeFromRoot on one observation; returns the action id or -1 (error bits in err). */
-__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err) {
+/* candidate edge of a team evaluation: the reference scans edges in list order and replaces the best when
+ * bid >= best (last-max) or bid > best (first-max), i.e. it ends on the maximal bid, ties going to the
+ * LAST / FIRST such edge — an order-free rule, so a warp reduction reproduces it exactly. */
+struct ep_cand { double bid; int e, dst; };
+__device__ __forceinline__ bool ep_better(const ep_cand& a, const ep_cand& b, int tie_break) { /* a beats b; e < 0 = no candidate */
+    if (a.e < 0) return false;
+    if (b.e < 0) return true;
+    if (a.bid != b.bid) return a.bid > b.bid;
+    return tie_break == TPGX_TIE_LAST_MAX ? a.e > b.e : a.e < b.e;
+}
+
+/* [UP] executeFromRoot on one observation by one warp; every lane returns the action id or -1 (error bits in err). */
+__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err, int lane) {
     int visited[TPGX_MAX_PATH];
     int depth = 0, cur = root;
     for (;;) {
         if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; return -1; }
         visited[depth++] = cur;
-        c.team++;
+        if (lane == 0) c.team++;
         const int eb = __ldg(p.team_edge_offset + cur), ee = __ldg(p.team_edge_offset + cur + 1);
-        bool have = false;
-        int best_dst = 0;
-        double best_bid = 0.0;
-        for (int e = eb; e < ee; e++) {
-            const int dst = __ldg(p.edge_destination + e);
-            if (dst >= 0) {
+        ep_cand best = {0.0, -1, 0};
+        for (int e0 = eb; e0 < ee; e0 += 32) {
+            ep_cand mine = {0.0, -1, 0};
+            const int e = e0 + lane;
+            if (e < ee) {
+                const int dst = __ldg(p.edge_destination + e);
                 bool seen = false;
-                for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
-                if (seen) continue;
+                if (dst >= 0)
+                    for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
+                if (!seen) { /* admissible edge: run its program on this lane */
+                    const int prog = __ldg(p.edge_program + e);
+                    const int cb = __ldg(p.prog_offset + prog), n = __ldg(p.prog_offset + prog + 1) - cb;
+                    double bid = tpgx_run_program(p.code + cb, n, p.constants + (size_t)prog * p.nb_constants, o);
+                    if (bid != bid) bid = __longlong_as_double(0xfff0000000000000LL);
+                    c.prog++;
+                    c.line += (unsigned int)n;
+                    mine.bid = bid; mine.e = e; mine.dst = dst;
+                }
             }
-            const int prog = __ldg(p.edge_program + e);
-            const int cb = __ldg(p.prog_offset + prog), n = __ldg(p.prog_offset + prog + 1) - cb;
-            double bid = tpgx_run_program(p.code + cb, n, p.constants + (size_t)prog * p.nb_constants, o);
-            if (bid != bid) bid = __longlong_as_double(0xfff0000000000000LL);
-            c.prog++;
-            c.line += (unsigned int)n;
-            const bool take = !have || (p.tie_break == TPGX_TIE_LAST_MAX ? (bid >= best_bid) : (bid > best_bid));
-            if (take) { have = true; best_dst = dst; best_bid = bid; }
+            __syncwarp();
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ep_cand other;
+                other.bid = __shfl_xor_sync(0xffffffffu, mine.bid, off);
+                other.e = __shfl_xor_sync(0xffffffffu, mine.e, off);
+                other.dst = __shfl_xor_sync(0xffffffffu, mine.dst, off);
+                if (ep_better(other, mine, p.tie_break)) mine = other;
+            }
+            if (ep_better(mine, best, p.tie_break)) best = mine;
         }
-        if (!have) { err |= TPGX_DEV_NO_EDGE; return -1; }
-        if (best_dst < 0) return -1 - best_dst;
-        cur = best_dst;
+        if (best.e < 0) { err |= TPGX_DEV_NO_EDGE; return -1; }
+        if (best.dst < 0) return -1 - best.dst;
+        cur = best.dst;
     }
 }
 
@@ -205,7 +229,7 @@ struct TicTacToe {
 
 /* ---------------------------------------------------------------- pendulum */
 struct Pendulum {
-    double hist[300];
+    double* hist; /* [300] reward history of the episode: ONE copy per warp in shared memory (every lane writes the same value) */
     double total, st[2];
     unsigned long long n_act;
     __device__ void reset(const tpgx_episode_params&, tpgx_rng_cursor& rng) {
@@ -250,10 +274,16 @@ struct Pendulum {
     __device__ void summary(double* o) const { o[0] = st[0]; o[1] = st[1]; o[2] = total; o[3] = (double)n_act; }
 };
 
+template <class Env> struct ep_scratch { __device__ static void attach(Env&, double*) {} };
+template <> struct ep_scratch<Pendulum> { __device__ static void attach(Pendulum& e, double* s) { e.hist = s; } };
+
+#define EP_WARPS 4
 template <class Env>
-__global__ void __launch_bounds__(64) tpgx_episode_kernel(const tpgx_episode_params p) {
+__global__ void __launch_bounds__(EP_WARPS * 32) tpgx_episode_kernel(const tpgx_episode_params p) {
+    __shared__ double s_scratch[EP_WARPS][304];
     const int NI = p.nb_iterations, K = p.roots_per_job;
-    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gid = blockIdx.x * (long long)EP_WARPS + warp;     /* episode = (job, iteration) */
     const long long total = (long long)p.nb_jobs * NI;
     ep_counters c = {0, 0, 0, 0};
     int err = 0;
@@ -263,25 +293,31 @@ __global__ void __launch_bounds__(64) tpgx_episode_kernel(const tpgx_episode_par
         rng.raw = p.rng_raw + (size_t)it * TPGX_RNG_TABLE;
         rng.pos = 0;
         rng.exhausted = 0;
-        Env env;
+        Env env;                                       /* replicated on every lane, stepped identically */
+        ep_scratch<Env>::attach(env, s_scratch[warp]);
         env.reset(p, rng);
+        __syncwarp();
         tpgx_obs_view o;
         int n = 0, turn = 0;
         while (!env.is_terminal() && n < p.max_actions) {
             env.view(o);
             const int root = __ldg(p.job_teams + (size_t)j * K + turn);
-            const int action = ep_traverse(p, root, o, c, err);
-            c.eval++;
+            const int action = ep_traverse(p, root, o, c, err, lane);
+            if (lane == 0) c.eval++;
             if (action < 0) break;
-            if (p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
+            if (lane == 0 && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
+            __syncwarp();
             if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; break; }
+            __syncwarp();
             turn = (turn + 1 == K) ? 0 : turn + 1;
             n++;
         }
-        for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
-        for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
-        p.episode_actions[gid] = n;
-        env.summary(p.final_state + (size_t)gid * 4);
+        if (lane == 0) {
+            for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
+            for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
+            p.episode_actions[gid] = n;
+            env.summary(p.final_state + (size_t)gid * 4);
+        }
         if (rng.exhausted) err |= TPGX_DEV_RNG_EXHAUSTED;
     }
     for (int o2 = 16; o2 > 0; o2 >>= 1) {
@@ -290,7 +326,7 @@ __global__ void __launch_bounds__(64) tpgx_episode_kernel(const tpgx_episode_par
         c.prog += __shfl_xor_sync(0xffffffffu, c.prog, o2);
         c.line += __shfl_xor_sync(0xffffffffu, c.line, o2);
     }
-    if ((threadIdx.x & 31) == 0) {
+    if (lane == 0) {
         atomicAdd(p.counters + 0, (unsigned long long)c.eval);
         atomicAdd(p.counters + 1, (unsigned long long)c.team);
         atomicAdd(p.counters + 2, (unsigned long long)c.prog);
@@ -314,8 +350,8 @@ __global__ void tpgx_job_score_kernel(const tpgx_episode_params p) {
 
 cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) {
     const long long total = (long long)p.nb_jobs * p.nb_iterations;
-    const int threads = 64;
-    const unsigned blocks = (unsigned)((total + threads - 1) / threads);
+    const int threads = EP_WARPS * 32;
+    const unsigned blocks = (unsigned)((total + EP_WARPS - 1) / EP_WARPS);
     switch (p.env) {
     case TPGX_ENV_GRIDWORLD: tpgx_episode_kernel<GridWorld><<<blocks, threads, 0, st>>>(p); break;
     case TPGX_ENV_STICKGAME: tpgx_episode_kernel<StickGame><<<blocks, threads, 0, st>>>(p); break;
