@@ -42,7 +42,7 @@ __device__ __forceinline__ double tpgx_apply_dd(uint32_t op, double a, double b)
     case TPGX_OP_SIN: if (TRIG) return tpgx_math::sin(a); else return 0.0;
     case TPGX_OP_TAN: if (TRIG) return tpgx_math::tan(a); else return 0.0;
     case TPGX_OP_PI: return TPGX_PI;
-    case TPGX_OP_MULC: return tpgx_math::xdiv(a * b, 10.0);  /* b carries the constant */
+    case TPGX_OP_MULC: return tpgx_math::xdiv10(a * b);  /* b carries the constant */
     case TPGX_OP_FMODG: return b != 0.0 ? fmod(a, b) : DBL_MIN;
     case TPGX_OP_EQ0: return (a == 0.0) ? 10.0 : 0.0;
     case TPGX_OP_EQM1: return (a == -1.0) ? 10.0 : 0.0;

@@ -262,14 +262,13 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                         tpgx_math::exp_k<K>(a, r);
                     } else if (op == TPGX_K1X_LOG) {
                         tpgx_math::log_k<K>(a, r);
-                    } else if (op == TPGX_K1X_DIV || op == TPGX_K1X_MULC) {
-                        if (op == TPGX_K1X_MULC) {
-                            const double c = *reinterpret_cast<const double*>(cbase + ln.z);
+                    } else if (op == TPGX_K1X_MULC) {
+                        const double c = *reinterpret_cast<const double*>(cbase + ln.z);
 #pragma unroll
-                            for (int k = 0; k < K; k++) { a[k] = a[k] * c; b[k] = 10.0; }   /* (a * c) / 10.0 */
-                        } else {
-                            if (h & 2u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
-                        }
+                        for (int k = 0; k < K; k++) a[k] = a[k] * c;
+                        tpgx_math::xdiv10_k<K>(a, r);                               /* (a * c) / 10.0 */
+                    } else if (op == TPGX_K1X_DIV) {
+                        if (h & 2u) ld_px_f64<K>(pb, b); else ld_regs<K>(rb, b);
                         tpgx_math::xdiv_k<K>(a, b, r);
                     } else if (EXT) {
                         if (op == TPGX_K1X_FMODG) {

@@ -315,6 +315,8 @@ __global__ void tpgx_math_probe_kernel(int fn, long long n, const double* __rest
     case TPGX_PROBE_SIN: for (int k = 0; k < 4; k++) r[k] = tpgx_math::sin(x[k]); break;
     case TPGX_PROBE_COS: for (int k = 0; k < 4; k++) r[k] = tpgx_math::cos(x[k]); break;
     case TPGX_PROBE_TAN: for (int k = 0; k < 4; k++) r[k] = tpgx_math::tan(x[k]); break;
+    case TPGX_PROBE_DIV10: for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv10(x[k]); break;
+    case TPGX_PROBE_DIV10_K: tpgx_math::xdiv10_k<4>(x, r); break;
     default: break;
     }
 #pragma unroll

@@ -676,7 +676,7 @@ tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* re
 }
 
 tpgx_status tpgx_math_probe(tpgx_ctx* ctx, int32_t fn, int64_t n, const double* a, const double* b, double* out) {
-    if (!ctx || n < 1 || !a || !out || fn < 0 || fn > TPGX_PROBE_TAN) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_math_probe: bad argument");
+    if (!ctx || n < 1 || !a || !out || fn < 0 || fn > TPGX_PROBE_DIV10_K) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_math_probe: bad argument");
     cudaSetDevice(ctx->cfg.device);
     tpgx_status st;
     if ((st = upload(ctx, ctx->d_scratch[0], a, (size_t)n * 8)) != TPGX_OK) return st;

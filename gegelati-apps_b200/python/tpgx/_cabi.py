@@ -13,7 +13,7 @@ ELEM_F64, ELEM_I32 = 0, 1
 STORE_U8, STORE_F64, STORE_I32 = 0, 1, 2
 ENV_GRIDWORLD, ENV_STICKGAME, ENV_TICTACTOE, ENV_PENDULUM = 0, 1, 2, 3
 (PROBE_DIV, PROBE_DIV_K, PROBE_EXP, PROBE_EXP_K, PROBE_LOG, PROBE_LOG_K, PROBE_ATAN, PROBE_SQRT_NONNEG, PROBE_DIV_SMALL_INT,
- PROBE_SIN, PROBE_COS, PROBE_TAN) = range(12)
+ PROBE_SIN, PROBE_COS, PROBE_TAN, PROBE_DIV10, PROBE_DIV10_K) = range(14)
 MODE_TRAINING, MODE_VALIDATION, MODE_TESTING = 0, 1, 2
 
 # operand signature per opcode: D double, I int, C constant, W 3x3 window

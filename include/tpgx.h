@@ -265,7 +265,7 @@ enum {
     TPGX_PROBE_DIV = 0, TPGX_PROBE_DIV_K = 1, TPGX_PROBE_EXP = 2, TPGX_PROBE_EXP_K = 3, TPGX_PROBE_LOG = 4,
     TPGX_PROBE_LOG_K = 5, TPGX_PROBE_ATAN = 6, TPGX_PROBE_SQRT_NONNEG = 7 /* integer-valued a in [0, 2^31) */,
     TPGX_PROBE_DIV_SMALL_INT = 8 /* (int)a / (int)b, Sobel gradient range */, TPGX_PROBE_SIN = 9, TPGX_PROBE_COS = 10,
-    TPGX_PROBE_TAN = 11
+    TPGX_PROBE_TAN = 11, TPGX_PROBE_DIV10 = 12, TPGX_PROBE_DIV10_K = 13 /* a / 10.0 (multByConst) */
 };
 tpgx_status tpgx_math_probe(tpgx_ctx* ctx, int32_t fn, int64_t n, const double* a, const double* b, double* out);
 

@@ -804,6 +804,7 @@ void orc_math_probe(int32_t fn, int64_t n, const double* a, const double* b, dou
         case TPGX_PROBE_SIN: out[i] = tpgx_math::sin(x); break;
         case TPGX_PROBE_COS: out[i] = tpgx_math::cos(x); break;
         case TPGX_PROBE_TAN: out[i] = tpgx_math::tan(x); break;
+        case TPGX_PROBE_DIV10: case TPGX_PROBE_DIV10_K: out[i] = x / 10.0; break;
         default: out[i] = 0.0; break;
         }
     }

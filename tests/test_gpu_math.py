@@ -77,3 +77,27 @@ def test_shared_libm_device_equals_host(ev, oracle_mod, fn, lo, hi):
     x = np.concatenate([rng.uniform(lo, hi, n), edge_values(), rng.standard_normal(n) * np.exp(rng.uniform(-740, 709, n)),
                         rng.integers(0, 256, n).astype(float) * (rng.random(n) < 0.5)])
     assert_same_bits(ev.math_probe(fn, x), oracle_mod.math_probe(fn, x), "libm fn %d" % fn)
+
+
+def test_division_by_ten_all_operand_classes(ev, oracle_mod):
+    """a / 10.0 through the 3-operation constant-divisor sequence: dense random mantissas over the whole exponent
+    range, quotients straddling every power of two (the one place a rounding tie can occur), multiples of 5 and 10,
+    subnormal quotients, and the specials."""
+    rng = np.random.default_rng(5)
+    n = 1 << 21
+    mant = rng.integers(0, 1 << 52, n, dtype=np.uint64)
+    expo = rng.integers(1, 2047, n, dtype=np.uint64)
+    sign = rng.integers(0, 2, n, dtype=np.uint64)
+    dense = ((sign << np.uint64(63)) | (expo << np.uint64(52)) | mant).view(np.float64)
+    k = np.arange(-1070, 1020)
+    near = []
+    for d in range(-40, 41):     # x = 10 * (2^k + d ulp): quotient next to a binade boundary, incl. 54-bit midpoints
+        q = np.ldexp(1.0, k) * (1.0 + d * 2.0 ** -53)
+        near.append(q * 10.0); near.append(np.nextafter(q * 10.0, np.inf)); near.append(np.nextafter(q * 10.0, -np.inf))
+    ints = np.arange(-200000, 200000, dtype=np.float64)
+    x = np.concatenate([dense, np.concatenate(near), ints, ints * 5.0, ints * 0.1, edge_values(), rng.integers(0, 256, n).astype(float) * rng.integers(-10, 11, n)])
+    with np.errstate(all="ignore"):
+        ref = x / 10.0
+    assert_same_bits(oracle_mod.math_probe(A.PROBE_DIV10, x), ref, "oracle / 10")
+    for fn in (A.PROBE_DIV10, A.PROBE_DIV10_K):
+        assert_same_bits(ev.math_probe(fn, x), ref, "division by ten fn %d" % fn)
