@@ -228,6 +228,40 @@ cudaError_t tpgx_launch_sobel_planes(const uint8_t* tiles, long long nb_tiles, i
 }
 
 /* ================================================================================================
+ * K1 stream encoder: expands the generic 32-bit line words of the shard's programs into K1's
+ * pre-decoded 16-byte quads (tpgx_k1_line) on the device — the host only ships the per-row
+ * descriptors.  block = one bid-matrix row; flags: bit 0 extended instruction, bit 1 int-typed.    */
+__global__ void tpgx_k1_encode_kernel(const uint32_t* __restrict__ code, const int32_t* __restrict__ prog_offset,
+                                      const double* __restrict__ constants, int nb_constants, const int32_t* __restrict__ active_prog,
+                                      const int2* __restrict__ desc, int ts, int width, uint4* __restrict__ stream,
+                                      int* __restrict__ flags) {
+    const int row = blockIdx.x;
+    const int p = active_prog[row];
+    const int2 d = desc[row];
+    uint4* out = stream + d.x;
+    if (threadIdx.x < 2 * TPGX_K1_CQ) {
+        double* cq = reinterpret_cast<double*>(out);
+        cq[threadIdx.x] = (int)threadIdx.x < nb_constants ? constants[(size_t)p * nb_constants + threadIdx.x] : 0.0;
+    }
+    const uint32_t* src = code + prog_offset[p];
+    int fl = 0;
+    for (int i = threadIdx.x; i < d.y; i += blockDim.x) {
+        const tpgx_k1_quad q = tpgx_k1_line(src[i], (uint32_t)ts, (uint32_t)width);
+        out[TPGX_K1_CQ + i] = make_uint4(q.x, q.y, q.z, q.w);
+        if (q.x == 0xffffffffu) fl |= 2;
+        else if (tpgx_k1_is_extended(q.x)) fl |= 1;
+    }
+    if (fl) atomicOr(flags, fl);
+}
+cudaError_t tpgx_launch_k1_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
+                                  const int32_t* active_prog, const int2* desc, int nb_rows, int ts, int width, uint4* stream,
+                                  int* flags, cudaStream_t st) {
+    if (nb_rows <= 0) return cudaSuccess;
+    tpgx_k1_encode_kernel<<<nb_rows, 32, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, ts, width, stream, flags);
+    return cudaGetLastError();
+}
+
+/* ================================================================================================
  * Generic executor: thread = (program, observation) on explicit f64 / i32 observations.
  * Replaces [UP] ProgramExecutionEngine::executeProgram for tpgx_execute_programs (parity tests of
  * every opcode on every source shape); NaN -> -inf applied like evaluateEdge.                      */

@@ -16,9 +16,15 @@
 #include "kernels.cuh"
 #include "tpgx_internal.h"
 
+#include <chrono>
 namespace {
 
 std::string g_create_error;
+struct Trace {
+    const char* what; std::chrono::steady_clock::time_point t0; bool on;
+    explicit Trace(const char* w) : what(w), t0(std::chrono::steady_clock::now()), on(getenv("TPGX_TRACE") != nullptr) {}
+    void lap(const char* step) { if (!on) return; auto t = std::chrono::steady_clock::now(); fprintf(stderr, "[tpgx] %s: %s %.3f ms\n", what, step, std::chrono::duration<double, std::milli>(t - t0).count()); t0 = t; }
+};
 
 struct DevBuf {
     void* p = nullptr;
@@ -55,7 +61,7 @@ struct tpgx_ctx {
     std::vector<int32_t> opcode;
     std::vector<tpgx_source_desc> src;
     tpgx_flat_graph flat;
-    bool has_graph = false, uses_trig = false;
+    bool has_graph = false, uses_trig = false, uses_ext = false, uses_int = false;
     uint64_t graph_version = 0;
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;
@@ -106,6 +112,7 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
     ShardPlan& pl = ctx->plan;
     if (pl.root_begin == rb && pl.root_end == re && pl.graph_version == ctx->graph_version && pl.k1_ts == ts) return TPGX_OK;
     const tpgx_flat_graph& f = ctx->flat;
+    Trace tr("make_plan");
     std::vector<int32_t> row_of(f.nb_programs, -1);
     std::vector<char> seen(f.nb_teams, 0);
     std::vector<int32_t> queue;
@@ -133,7 +140,9 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
     if ((st = upload(ctx, ctx->d_active, ctx->h_active.data(), ctx->h_active.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_row, ctx->h_edge_row.data(), ctx->h_edge_row.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_roots, f.root_team.data() + rb, (size_t)(re - rb) * 4)) != TPGX_OK) return st;
-    /* K1 stream: per row its constants (TPGX_K1_CQ quads) followed by its pre-decoded wide lines */
+    tr.lap("reachability + uploads");
+    /* K1 stream: per row its constants (TPGX_K1_CQ quads) followed by its pre-decoded wide lines.  The host
+       ships only the row descriptors; the quads are expanded on the device from the generic code. */
     {
         const int nrows = (int)ctx->h_active.size();
         std::vector<int32_t> desc(2 * (size_t)nrows);
@@ -144,36 +153,20 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
             desc[2 * row + 1] = f.prog_offset[p + 1] - f.prog_offset[p];
             nq += TPGX_K1_CQ + desc[2 * row + 1];
         }
-        std::vector<tpgx_k1_quad> stream((size_t)nq + 64, tpgx_k1_quad{0, 0, 0, 0}); /* slack: a lane may address up to 32 quads past a row's start */
-        const int nc = ctx->cfg.nb_constants;
-        std::vector<int> flags(tpgx_parallel_workers(), 0); /* bit 0: extended instruction, bit 1: int-typed instruction */
-        tpgx_parallel_blocks(nrows, 256, [&](int rb2, int re2, int w) {
-            int fl = 0;
-            for (int row = rb2; row < re2; row++) {
-                const int p = ctx->h_active[row];
-                tpgx_k1_quad* q = stream.data() + desc[2 * row];
-                double cq[2 * TPGX_K1_CQ] = {0};
-                for (int c = 0; c < nc; c++) cq[c] = f.constants[(size_t)p * nc + c];
-                memcpy(q, cq, sizeof cq);
-                q += TPGX_K1_CQ;
-                for (int i = f.prog_offset[p]; i < f.prog_offset[p + 1]; i++, q++) {
-                    *q = tpgx_k1_line(f.code[i], (uint32_t)ts, (uint32_t)ctx->obs_width);
-                    if (q->x == 0xffffffffu) fl |= 2;
-                    else if (tpgx_k1_is_extended(q->x)) fl |= 1;
-                }
-            }
-            flags[w] |= fl;
-        });
-        bool ext = false;
-        for (int fl : flags) {
-            if (fl & 2) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
-            ext |= (fl & 1) != 0;
-        }
-        if ((st = upload(ctx, ctx->d_k1_stream, stream.data(), stream.size() * sizeof(tpgx_k1_quad))) != TPGX_OK) return st;
         if ((st = upload(ctx, ctx->d_k1_desc, desc.data(), desc.size() * 4)) != TPGX_OK) return st;
-        CU(cudaStreamSynchronize(ctx->stream)); /* stream / desc are locals */
-        pl.k1_ext = ext;
+        CU(ctx->d_k1_stream.ensure(((size_t)nq + 64) * sizeof(tpgx_k1_quad))); /* slack: a lane may address up to 32 quads past a row's start */
+        CU(ctx->d_status.ensure(16));
+        int* d_flags = ctx->d_status.as<int>() + 2;
+        CU(cudaMemsetAsync(d_flags, 0, 4, ctx->stream));
+        CU(tpgx_launch_k1_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
+                                 ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->d_k1_stream.as<uint4>(),
+                                 d_flags, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream)); /* desc is a local */
+        /* which build of K1 (MNIST set only / extended) is known on the host from the opcode table */
+        if (ctx->uses_int) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
+        pl.k1_ext = ctx->uses_ext;
     }
+    tr.lap("K1 stream encode + upload");
     pl.root_begin = rb; pl.root_end = re; pl.graph_version = ctx->graph_version; pl.k1_ts = ts;
     return TPGX_OK;
 }
@@ -399,12 +392,25 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
     cudaSetDevice(ctx->cfg.device);
     std::string msg;
     tpgx_flat_graph f;
+    Trace tr("set_graph");
     tpgx_status st = tpgx_flatten_graph(ctx->cfg, ctx->opcode, ctx->src, g, &f, &msg);
     if (st != TPGX_OK) return fail(ctx, st, msg);
+    tr.lap("flatten");
     ctx->flat = std::move(f);
     const tpgx_flat_graph& F = ctx->flat;
-    ctx->uses_trig = false;
-    for (uint32_t w : F.code) { uint32_t op = w & 31u; if (op == TPGX_OP_SIN || op == TPGX_OP_COS || op == TPGX_OP_TAN) ctx->uses_trig = true; }
+    ctx->uses_trig = ctx->uses_ext = ctx->uses_int = false;
+    { /* instruction classes present among the effective lines (selects the K1 build, rejects int ops on image sources) */
+        bool present[32] = {false};
+        std::vector<uint32_t> seen(tpgx_parallel_workers(), 0u);
+        tpgx_parallel_blocks((int)F.code.size(), 1 << 15, [&](int b, int e, int w) { uint32_t m = 0; for (int i = b; i < e; i++) m |= 1u << (F.code[i] & 31u); seen[w] |= m; });
+        uint32_t mask = 0;
+        for (uint32_t m : seen) mask |= m;
+        for (int op = 0; op < 32; op++) present[op] = (mask >> op) & 1u;
+        ctx->uses_trig = present[TPGX_OP_SIN] || present[TPGX_OP_COS] || present[TPGX_OP_TAN];
+        ctx->uses_int = present[TPGX_OP_SUB_II] || present[TPGX_OP_CAST_I];
+        ctx->uses_ext = ctx->uses_trig || present[TPGX_OP_FMODG] || present[TPGX_OP_COND] || present[TPGX_OP_EQ0] || present[TPGX_OP_EQM1] ||
+                        present[TPGX_OP_EQ1] || present[TPGX_OP_GE15] || present[TPGX_OP_PI];
+    }
     std::vector<int32_t> edge_lines(F.nb_edges);
     for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }
     if ((st = upload(ctx, ctx->d_code, F.code.data(), F.code.size() * 4)) != TPGX_OK) return st;
@@ -414,6 +420,7 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
     if ((st = upload(ctx, ctx->d_edge_dst, F.edge_destination.data(), F.edge_destination.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_lines, edge_lines.data(), edge_lines.size() * 4)) != TPGX_OK) return st;
     CU(cudaStreamSynchronize(ctx->stream));
+    tr.lap("uploads");
     ctx->graph_version++;
     ctx->has_graph = true;
     return TPGX_OK;
@@ -463,8 +470,12 @@ tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, 
         if ((st = upload(ctx, ctx->d_labels_raw, labels, (size_t)count)) != TPGX_OK) return st;
         ctx->labels_dev = ctx->d_labels_raw.as<uint8_t>();
     }
+    /* the caller may free its buffers on return: wait for the host -> device copies only; the re-tiling and
+       Sobel-plane kernels keep running behind the host (later work is ordered on the same stream) */
+    cudaEvent_t copied = ctx->event(61);
+    CU(cudaEventRecord(copied, ctx->stream));
     if ((st = pack_identity(ctx)) != TPGX_OK) return st;
-    CU(cudaStreamSynchronize(ctx->stream)); /* the caller may free its buffers on return */
+    CU(cudaEventSynchronize(copied));
     return TPGX_OK;
 }
 
@@ -486,9 +497,12 @@ tpgx_status tpgx_evaluate_classification(tpgx_ctx* ctx, const tpgx_classif_reque
     const int nRq = req->root_end - req->root_begin;
     if (nRq > 0 && req->nb_classes > 0) CU(ctx->d_records.ensure((size_t)nRq * (req->nb_classes + 1) * 8));
     ClassifRun run;
+    Trace tr("evaluate_classification");
     tpgx_status st = enqueue_classification(ctx, req, ctx->d_records.as<double>(), out->action != nullptr, out->bid != nullptr, &run, true);
     if (st != TPGX_OK) return st;
+    tr.lap("enqueue (plan + launches)");
     CU(cudaStreamSynchronize(ctx->stream));
+    tr.lap("device");
     int status = 0;
     CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
     if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
@@ -524,6 +538,7 @@ tpgx_status tpgx_evaluate_classification(tpgx_ctx* ctx, const tpgx_classif_reque
         out->counters->device_lines = (uint64_t)ctx->plan.active_lines * (uint64_t)run.nS;
         out->counters->device_program_executions = (uint64_t)ctx->plan.nb_active * (uint64_t)run.nS;
     }
+    tr.lap("read-back");
     if (out->device_ms) {
         float k1 = 0, k2 = 0, k3 = 0, t;
         for (int ps = 0; ps < run.passes; ps++) {

@@ -69,14 +69,19 @@ enum { /* heavy class: 64 | (op << 2) | kinds */
     TPGX_K1X_FMODG, TPGX_K1X_COS, TPGX_K1X_SIN, TPGX_K1X_TAN
 };
 /* operations outside the MNIST set ([REF] mnist/src/main.cpp:79-88): compiled into the "extended" kernel only */
-static inline bool tpgx_k1_is_extended(uint32_t h) {
+#if defined(__CUDACC__)
+#define TPGX_HOSTDEV __host__ __device__
+#else
+#define TPGX_HOSTDEV
+#endif
+TPGX_HOSTDEV static inline bool tpgx_k1_is_extended(uint32_t h) {
     const uint32_t op = (h >> 2) & 15u;
     return (h & TPGX_K1H_HEAVY) ? op >= TPGX_K1X_FMODG : op >= TPGX_K1C_COND;
 }
 
 struct tpgx_k1_quad { uint32_t x, y, z, w; };
 
-static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts, uint32_t width) {
+TPGX_HOSTDEV static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts, uint32_t width) {
     const uint32_t op = word & 31u, dst = (word >> 5) & 7u;
     const uint32_t fa = (word >> 8) & 0xfffu, fb = word >> 20;
     const uint32_t pa = (fa >> 10) == TPGX_KIND_SRC0, pb = (fb >> 10) == TPGX_KIND_SRC0;

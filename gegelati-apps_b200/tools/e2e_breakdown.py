@@ -17,9 +17,9 @@ pin_img = torch.from_numpy(img).pin_memory().numpy()
 pin_lab = torch.from_numpy(lab).pin_memory().numpy()
 ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
 for rep in range(4):
-    t0 = time.perf_counter(); ev.set_graph(g)
-    t1 = time.perf_counter(); ev.set_observations(pin_img, pin_lab)
+    t0 = time.perf_counter(); ev.set_observations(pin_img, pin_lab)
+    t1 = time.perf_counter(); ev.set_graph(g)
     t2 = time.perf_counter(); out = ev.evaluate_classification(want=("score", "class_f1", "device_ms"))
     t3 = time.perf_counter()
-    print("rep %d: set_graph %.2f ms, set_observations %.2f ms, evaluate %.2f ms (device K1/K2/K3 %s), total %.2f ms" %
+    print("rep %d: set_observations %.2f ms, set_graph %.2f ms, evaluate %.2f ms (device K1/K2/K3 %s), total %.2f ms" %
           (rep, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, np.round(out["device_ms"], 2), (t3 - t0) * 1e3))
