@@ -114,7 +114,7 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int K, int NW, bool EXT>
+template <int K, int NW, bool EXT, bool TEAM>
 __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_params p) {
     constexpr int TS = 32 * K;
     static_assert(K == 2 || K == 4, "lane owns 2 or 4 samples");
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
         st_regs<K>(regs_lane + TPGX_LOC_ZERO * TS * 8, z);
     }
 
-    const int chunk_begin = blockIdx.x * p.progs_per_chunk; /* chunks vary fastest: CTAs resident together share tiles (L2) */
-    const int chunk_n = min(p.progs_per_chunk, p.nb_active - chunk_begin);
+    const int chunk_begin = blockIdx.x * p.units_per_chunk; /* chunks vary fastest: CTAs resident together share tiles (L2) */
+    const int chunk_n = min(p.units_per_chunk, p.nb_units - chunk_begin);
     /* this tile's Sobel planes: [which][window][TS samples] doubles; the lane's K samples are consecutive */
     const long long plane_stride = (long long)p.nwin * TS;
     const double* const sobel_lane = p.sobel + (size_t)blockIdx.y * 2 * plane_stride + lane * K;
@@ -162,21 +162,42 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
         if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(i) : "r"(s_next_addr) : "memory");
         return __shfl_sync(0xffffffffu, i, 0);
     };
-    auto load_desc = [&](int i) { return (i < chunk_n) ? __ldg(p.desc + chunk_begin + i) : make_int2(0, 0); };
+    /* A work unit is a program (TEAM = false: its bid row is written out) or a whole team (TEAM = true: the
+       programs of its outgoing edges run back to back, the winning edge per sample is kept in registers with
+       the reference's order-dependent tie-break and only its destination is written: [UP] evaluateTeam fused
+       into the interpreter, 4 bytes per (team, sample) instead of 8 bytes per (edge, sample)).
+       unit -> {first row, number of rows}; rows index p.desc.                                              */
+    auto load_unit = [&](int u) {
+        if (u >= chunk_n) return make_int2(0, 0);
+        return TEAM ? __ldg(p.team + chunk_begin + u) : make_int2(chunk_begin + u, 1);
+    };
+    auto load_desc = [&](int row, bool valid) { return valid ? __ldg(p.desc + row) : make_int2(0, 0); };
     /* asynchronous copy of a program's constants + first TPGX_K1_CAPL lines into a code buffer */
     auto stage = [&](uint4* buf, const int2 d) {
         if (lane < TPGX_K1_CQ + min(d.y, TPGX_K1_CAPL)) cp_async16(buf + lane, stream + d.x + lane);
         cp_async_commit();
     };
-    int i0 = claim();
-    int2 d0 = load_desc(i0);
+    int u0 = claim();
+    int2 un0 = load_unit(u0);
+    int row = un0.x, row_end = un0.x + un0.y;
+    int2 d0 = load_desc(row, u0 < chunk_n);
     int cur = 0;
     stage(mycode, d0);
     mbar_wait(bar, 0);
+    double best[K];
+    int best_dst[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) { best[k] = 0.0; best_dst[k] = 0; }
 
-    while (i0 < chunk_n) {
-        const int i1 = claim();
-        const int2 d1 = load_desc(i1);
+    while (u0 < chunk_n) {
+        /* the row after this one: next edge of the team, or the first row of the next claimed unit */
+        int u1 = u0, nrow = row + 1, nrow_end = row_end;
+        if (nrow >= row_end) {
+            u1 = claim();
+            const int2 un1 = load_unit(u1);
+            nrow = un1.x; nrow_end = un1.x + un1.y;
+        }
+        const int2 d1 = load_desc(nrow, u1 < chunk_n);
         cp_async_wait_all();
         __syncwarp();
         uint4* const code = mycode + cur * K1_CODE_QUADS;
@@ -297,17 +318,36 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
 #pragma unroll
         for (int k = 0; k < K; k++)
             if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
-        double* out = p.bid + (size_t)(chunk_begin + i0) * p.row_stride + (size_t)blockIdx.y * TS + lane * K;
+        if (!TEAM) {
+            double* out = p.bid + (size_t)row * p.row_stride + (size_t)blockIdx.y * TS + lane * K;
 #pragma unroll
-        for (int k = 0; k < K; k += 2) *reinterpret_cast<double2*>(out + k) = make_double2(res[k], res[k + 1]);
+            for (int k = 0; k < K; k += 2) *reinterpret_cast<double2*>(out + k) = make_double2(res[k], res[k + 1]);
+        } else {
+            /* [UP] evaluateTeam: the first edge is the initial best; a later edge replaces it if
+               bid >= best (last-max) / bid > best (first-max) */
+            const int dst = __ldg(p.row_dst + row);
+            const bool first = (row == row_end - (TEAM ? un0.y : 1));
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                const bool take = first | (p.tie_break == TPGX_TIE_LAST_MAX ? (res[k] >= best[k]) : (res[k] > best[k]));
+                best[k] = take ? res[k] : best[k];
+                best_dst[k] = take ? dst : best_dst[k];
+            }
+            if (row + 1 == row_end) {
+                int* out = p.decision + (size_t)(chunk_begin + u0) * p.row_stride + (size_t)blockIdx.y * TS + lane * K;
+#pragma unroll
+                for (int k = 0; k < K; k += 2) *reinterpret_cast<int2*>(out + k) = make_int2(best_dst[k], best_dst[k + 1]);
+            }
+        }
 
-        i0 = i1; d0 = d1; cur ^= 1;
+        if (u1 != u0) un0 = make_int2(nrow, nrow_end - nrow);
+        u0 = u1; row = nrow; row_end = nrow_end; d0 = d1; cur ^= 1;
     }
     cp_async_wait_all();
 }
 
 struct bid_variant { int K, NW; };
-static const bid_variant g_variants[] = {{2, 32}, {4, 12}, {4, 10}, {2, 28}, {2, 24}, {2, 16}, {4, 8}, {2, 20}, {2, 22}, {2, 26}};
+static const bid_variant g_variants[] = {{2, 32}, {4, 12}, {2, 28}, {2, 24}, {2, 16}};
 static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 
 int tpgx_bid_tile_samples(int variant) {
@@ -322,36 +362,29 @@ size_t tpgx_bid_smem_bytes(int variant, int hw) {
     return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * 2 * K1_CODE_QUADS * 16 + 16;
 }
 
-template <int K, int NW>
-static cudaError_t launch_bid_t(const tpgx_bid_params& p, int nb_tiles, size_t smem, bool ext, cudaStream_t st) {
-    const int chunks = (p.nb_active + p.progs_per_chunk - 1) / p.progs_per_chunk;
-    dim3 grid(chunks, nb_tiles);
-    cudaError_t e;
-    if (ext) {
-        e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        tpgx_bid_kernel<K, NW, true><<<grid, NW * 32, smem, st>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        tpgx_bid_kernel<K, NW, false><<<grid, NW * 32, smem, st>>>(p);
-    }
+template <int K, int NW, bool EXT, bool TEAM>
+static cudaError_t launch_bid_k(const tpgx_bid_params& p, dim3 grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, EXT, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tpgx_bid_kernel<K, NW, EXT, TEAM><<<grid, NW * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
+template <int K, int NW>
+static cudaError_t launch_bid_t(const tpgx_bid_params& p, int nb_tiles, size_t smem, bool ext, bool team, cudaStream_t st) {
+    const int chunks = (p.nb_units + p.units_per_chunk - 1) / p.units_per_chunk;
+    dim3 grid(chunks, nb_tiles);
+    if (ext) return team ? launch_bid_k<K, NW, true, true>(p, grid, smem, st) : launch_bid_k<K, NW, true, false>(p, grid, smem, st);
+    return team ? launch_bid_k<K, NW, false, true>(p, grid, smem, st) : launch_bid_k<K, NW, false, false>(p, grid, smem, st);
+}
 
-cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool ext, cudaStream_t st) {
+cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool ext, bool team, cudaStream_t st) {
     if (variant < 0 || variant >= g_nb_variants) variant = 0;
     const size_t smem = tpgx_bid_smem_bytes(variant, p.hw);
     switch (variant) {
-    case 1: return launch_bid_t<4, 12>(p, nb_tiles, smem, ext, st);
-    case 2: return launch_bid_t<4, 10>(p, nb_tiles, smem, ext, st);
-    case 3: return launch_bid_t<2, 28>(p, nb_tiles, smem, ext, st);
-    case 4: return launch_bid_t<2, 24>(p, nb_tiles, smem, ext, st);
-    case 5: return launch_bid_t<2, 16>(p, nb_tiles, smem, ext, st);
-    case 6: return launch_bid_t<4, 8>(p, nb_tiles, smem, ext, st);
-    case 7: return launch_bid_t<2, 20>(p, nb_tiles, smem, ext, st);
-    case 8: return launch_bid_t<2, 22>(p, nb_tiles, smem, ext, st);
-    case 9: return launch_bid_t<2, 26>(p, nb_tiles, smem, ext, st);
-    default: return launch_bid_t<2, 32>(p, nb_tiles, smem, ext, st);
+    case 1: return launch_bid_t<4, 12>(p, nb_tiles, smem, ext, team, st);
+    case 2: return launch_bid_t<2, 28>(p, nb_tiles, smem, ext, team, st);
+    case 3: return launch_bid_t<2, 24>(p, nb_tiles, smem, ext, team, st);
+    case 4: return launch_bid_t<2, 16>(p, nb_tiles, smem, ext, team, st);
+    default: return launch_bid_t<2, 32>(p, nb_tiles, smem, ext, team, st);
     }
 }

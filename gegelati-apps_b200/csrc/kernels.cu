@@ -129,6 +129,72 @@ cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p, cudaStream_t st) {
 }
 
 /* ================================================================================================
+ * K2 in team mode — walk.  K1 already ran [UP] evaluateTeam for every (team, sample): decision[u][s] is
+ * the destination of the winning edge.  [UP] executeFromRoot is then a pointer chase from the root's unit
+ * until an action; the reference-equivalent work counters come from per-team constants (in team mode the
+ * reachable graph is acyclic, so every edge of a visited team is admissible).                       */
+__global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk_params p) {
+    __shared__ unsigned int s_table[256];
+    __shared__ unsigned long long s_cnt[4];
+    const int C = p.nb_classes;
+    for (int i = threadIdx.x; i < C * C; i += TRAV_THREADS) s_table[i] = 0;
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int r = blockIdx.y;
+    const int root = __ldg(p.root_unit + r);
+    unsigned int c_eval = 0, c_team = 0, c_prog = 0, c_line = 0;
+    int err = 0;
+    const int s_begin = blockIdx.x * (TRAV_THREADS * TRAV_SPT);
+    for (int it = 0; it < TRAV_SPT; it++) {
+        const int s = s_begin + it * TRAV_THREADS + threadIdx.x;
+        if (s >= p.nb_samples) break;
+        int cur = root, action = -1;
+        for (int depth = 0;; depth++) {
+            if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; break; }
+            const int2 st = __ldg(p.team_stat + cur);
+            c_team++;
+            c_prog += (unsigned int)st.x;
+            c_line += (unsigned int)st.y;
+            const int d = __ldg(p.decision + (size_t)cur * p.row_stride + s);
+            if (d < 0) { action = -1 - d; break; }
+            cur = d;
+        }
+        c_eval++;
+        if (action >= 0) {
+            if (p.action) p.action[(size_t)r * p.action_stride + s] = (uint8_t)action;
+            if (p.labels) {
+                if (action < C) atomicAdd(&s_table[(int)__ldg(p.labels + s) * C + action], 1u);
+                else err |= TPGX_DEV_BAD_ACTION;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        c_eval += __shfl_xor_sync(0xffffffffu, c_eval, o);
+        c_team += __shfl_xor_sync(0xffffffffu, c_team, o);
+        c_prog += __shfl_xor_sync(0xffffffffu, c_prog, o);
+        c_line += __shfl_xor_sync(0xffffffffu, c_line, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&s_cnt[0], (unsigned long long)c_eval);
+        atomicAdd(&s_cnt[1], (unsigned long long)c_team);
+        atomicAdd(&s_cnt[2], (unsigned long long)c_prog);
+        atomicAdd(&s_cnt[3], (unsigned long long)c_line);
+    }
+    if (err) atomicOr(p.status, err);
+    __syncthreads();
+    if (p.labels)
+        for (int i = threadIdx.x; i < C * C; i += TRAV_THREADS)
+            if (s_table[i]) atomicAdd(p.confusion + (size_t)r * C * C + i, (unsigned long long)s_table[i]);
+    if (threadIdx.x < 4 && p.counters) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
+}
+
+cudaError_t tpgx_launch_walk(const tpgx_walk_params& p, cudaStream_t st) {
+    dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
+    tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+/* ================================================================================================
  * K3 — per-root score record {mean F1, F1[0..C)} from the confusion table, in the operation order
  * of [UP] ClassificationLearningAgent::evaluateJob: recall = TP/(TP+FN), precision = TP/(TP+FP),
  * F = TP != 0 ? 2*(P*R)/(P+R) : 0; score = (sum of F in class order starting from 0.0) / C.       */

@@ -14,15 +14,20 @@ struct tpgx_bid_params {
     const uint8_t* tiles;        /* [tiles][hw][TS] pixel-major sample tiles (first tile of the pass) */
     int hw, width;               /* elements per observation, row length                              */
     const uint4* stream;         /* per bid-matrix row: TPGX_K1_CQ constant quads, then its wide lines */
-    const int2* desc;            /* [nb_active] {first quad of the row in stream, number of lines}      */
+    const int2* desc;            /* [rows] {first quad of the row in stream, number of lines}           */
     const double* pixel_lut;     /* [2][256] exp / ln of every uint8 pixel value, then [2][1021][1021] sobelMagn / sobelDir
                                     of every |gy|, |gx| (filled on the device by the tpgx_math routines)          */
     const double* sobel;         /* [tiles][2][nwin][TS] sobelMagn / sobelDir of every window position (first tile of the pass) */
     int nwin;                    /* window positions per observation, (h-2)(w-2)                        */
-    int nb_active;
-    int progs_per_chunk;
-    double* bid;                 /* [nb_active][row_stride]                                            */
+    int nb_units;                /* work units: programs (bid mode) or teams (team mode)                */
+    int units_per_chunk;
+    double* bid;                 /* bid mode: [rows][row_stride]                                        */
     long long row_stride;        /* samples per row in this pass (multiple of TS)                      */
+    /* team mode ([UP] evaluateTeam fused into the interpreter) */
+    const int2* team;            /* [nb_units] {first row, number of edges}; rows index desc / row_dst  */
+    const int32_t* row_dst;      /* [rows] destination of the edge: >= 0 team unit index, < 0 action = -1 - value */
+    int32_t* decision;           /* [nb_units][row_stride] destination of the winning edge              */
+    int tie_break;
 };
 
 /* K2: graph traversal per (root, sample) on the bid matrix. */
@@ -46,6 +51,24 @@ struct tpgx_trav_params {
     int* status;                 /* OR of TPGX_DEV_* error bits                                         */
 };
 
+/* K2 in team mode: walk of the per-team decisions. */
+struct tpgx_walk_params {
+    const int32_t* decision;     /* [units][row_stride]                                                 */
+    long long row_stride;
+    int nb_samples;
+    const int2* team_stat;       /* [units] {number of edges, sum of their effective lines} (reference-equivalent counters) */
+    const int32_t* root_unit;    /* [nb_roots] unit index of each root team                             */
+    int nb_roots;
+    const uint8_t* labels;
+    int nb_classes;
+    uint8_t* action;
+    long long action_stride;
+    unsigned long long* confusion;
+    unsigned long long* counters;
+    int* status;
+};
+cudaError_t tpgx_launch_walk(const tpgx_walk_params& p, cudaStream_t st);
+
 #define TPGX_SOBEL_LUT_N 1021
 #define TPGX_LUT_DOUBLES (512 + 2 * TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N)
 
@@ -57,7 +80,7 @@ struct tpgx_trav_params {
 /* Launchers (defined in kernels.cu). variant: 0 = default tile shape. Returns cudaError_t. */
 int tpgx_bid_tile_samples(int variant);
 size_t tpgx_bid_smem_bytes(int variant, int hw);
-cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool extended_ops, cudaStream_t st);
+cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool extended_ops, bool team_mode, cudaStream_t st);
 cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p, cudaStream_t st);
 cudaError_t tpgx_launch_score(const unsigned long long* confusion, int nb_roots, int nb_classes,
                               double* records, cudaStream_t st);

@@ -50,6 +50,9 @@ struct ShardPlan { /* programs reachable from a root range, cached between evalu
     int nb_active = 0;
     int k1_ts = 0;        /* tile shape the K1 stream was encoded for */
     bool k1_ext = false;  /* the shard uses instructions outside the MNIST set */
+    bool team_mode = false; /* [UP] evaluateTeam fused into K1 (acyclic shard, no bid output, little program sharing) */
+    bool want_bid = false;
+    int nb_units = 0;     /* teams in team mode, programs otherwise */
     int64_t active_lines = 0, active_flops = 0;
 };
 
@@ -68,7 +71,7 @@ struct tpgx_ctx {
     int variant = 0;
     size_t bid_budget = (size_t)16 << 30;
 
-    DevBuf d_pixel_lut, d_sobel;
+    DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[8];
@@ -107,36 +110,91 @@ tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
     return TPGX_OK;
 }
 
-/* Programs reachable from roots [rb, re): BFS over teams; rows in order of first appearance. */
-tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts) {
+/* Plan of one evaluation shard.  Teams reachable from roots [rb, re) by BFS.
+ * Bid mode: one bid-matrix row per distinct program, in order of first appearance; K2 walks the graph on bids.
+ * Team mode (the default when it applies): one row per EDGE, grouped by team, and K1 itself keeps the winning
+ * edge per (team, sample).  It applies when no bid output is wanted, the reachable graph is acyclic (then the
+ * visited-team exclusion of [UP] evaluateTeam never removes an edge) and re-running shared programs once per
+ * referencing team costs at most 25 % more lines than running each distinct program once.              */
+tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
     ShardPlan& pl = ctx->plan;
-    if (pl.root_begin == rb && pl.root_end == re && pl.graph_version == ctx->graph_version && pl.k1_ts == ts) return TPGX_OK;
+    if (pl.root_begin == rb && pl.root_end == re && pl.graph_version == ctx->graph_version && pl.k1_ts == ts && pl.want_bid == want_bid) return TPGX_OK;
     const tpgx_flat_graph& f = ctx->flat;
     Trace tr("make_plan");
     std::vector<int32_t> row_of(f.nb_programs, -1);
-    std::vector<char> seen(f.nb_teams, 0);
+    std::vector<int32_t> unit_of(f.nb_teams, -1);
     std::vector<int32_t> queue;
-    ctx->h_active.clear();
+    std::vector<int32_t> uniq;
     ctx->h_edge_row.assign(f.nb_edges, -1);
     for (int r = rb; r < re; r++) {
         int t = f.root_team[r];
-        if (!seen[t]) { seen[t] = 1; queue.push_back(t); }
+        if (unit_of[t] < 0) { unit_of[t] = (int32_t)queue.size(); queue.push_back(t); }
     }
+    int64_t uniq_lines = 0, edge_lines_total = 0;
     for (size_t q = 0; q < queue.size(); q++) {
         const int t = queue[q];
         for (int e = f.team_edge_offset[t]; e < f.team_edge_offset[t + 1]; e++) {
             const int p = f.edge_program[e];
-            if (row_of[p] < 0) { row_of[p] = (int32_t)ctx->h_active.size(); ctx->h_active.push_back(p); }
+            const int n = f.prog_offset[p + 1] - f.prog_offset[p];
+            if (row_of[p] < 0) { row_of[p] = (int32_t)uniq.size(); uniq.push_back(p); uniq_lines += n; }
+            edge_lines_total += n;
             ctx->h_edge_row[e] = row_of[p];
             const int d = f.edge_destination[e];
-            if (d >= 0 && !seen[d]) { seen[d] = 1; queue.push_back(d); }
+            if (d >= 0 && unit_of[d] < 0) { unit_of[d] = (int32_t)queue.size(); queue.push_back(d); }
         }
+    }
+    /* acyclic?  Kahn's algorithm on the reachable team graph */
+    bool acyclic = true;
+    {
+        std::vector<int32_t> indeg(queue.size(), 0), stack;
+        for (int t : queue)
+            for (int e = f.team_edge_offset[t]; e < f.team_edge_offset[t + 1]; e++)
+                if (f.edge_destination[e] >= 0) indeg[unit_of[f.edge_destination[e]]]++;
+        for (size_t u = 0; u < queue.size(); u++) if (indeg[u] == 0) stack.push_back((int32_t)u);
+        size_t done = 0;
+        while (!stack.empty()) {
+            const int u = stack.back(); stack.pop_back(); done++;
+            const int t = queue[u];
+            for (int e = f.team_edge_offset[t]; e < f.team_edge_offset[t + 1]; e++)
+                if (f.edge_destination[e] >= 0 && --indeg[unit_of[f.edge_destination[e]]] == 0) stack.push_back(unit_of[f.edge_destination[e]]);
+        }
+        acyclic = done == queue.size();
+    }
+    const char* force = getenv("TPGX_TEAM_MODE");
+    pl.team_mode = !want_bid && acyclic && edge_lines_total * 4 <= uniq_lines * 5 && !(force && force[0] == '0');
+    pl.want_bid = want_bid;
+    tpgx_status st;
+    if (pl.team_mode) {
+        std::vector<int32_t> team(2 * queue.size()), stat(2 * queue.size()), rows, dsts, roots(re - rb);
+        for (size_t u = 0; u < queue.size(); u++) {
+            const int t = queue[u];
+            const int eb = f.team_edge_offset[t], ee = f.team_edge_offset[t + 1];
+            team[2 * u] = (int32_t)rows.size(); team[2 * u + 1] = ee - eb;
+            int lines = 0;
+            for (int e = eb; e < ee; e++) {
+                const int p = f.edge_program[e];
+                rows.push_back(p);
+                dsts.push_back(f.edge_destination[e] >= 0 ? unit_of[f.edge_destination[e]] : f.edge_destination[e]);
+                lines += f.prog_offset[p + 1] - f.prog_offset[p];
+            }
+            stat[2 * u] = ee - eb; stat[2 * u + 1] = lines;
+        }
+        for (int r = rb; r < re; r++) roots[r - rb] = unit_of[f.root_team[r]];
+        ctx->h_active = rows;
+        pl.nb_units = (int)queue.size();
+        if ((st = upload(ctx, ctx->d_tm_team, team.data(), team.size() * 4)) != TPGX_OK) return st;
+        if ((st = upload(ctx, ctx->d_tm_stat, stat.data(), stat.size() * 4)) != TPGX_OK) return st;
+        if ((st = upload(ctx, ctx->d_tm_dst, dsts.data(), dsts.size() * 4)) != TPGX_OK) return st;
+        if ((st = upload(ctx, ctx->d_tm_roots, roots.data(), roots.size() * 4)) != TPGX_OK) return st;
+        CU(cudaStreamSynchronize(ctx->stream)); /* locals */
+    } else {
+        ctx->h_active = uniq;
+        pl.nb_units = (int)uniq.size();
     }
     pl.nb_active = (int)ctx->h_active.size();
     pl.active_lines = 0;
     pl.active_flops = 0;
     for (int p : ctx->h_active) { pl.active_lines += f.prog_offset[p + 1] - f.prog_offset[p]; pl.active_flops += f.prog_flops[p]; }
-    tpgx_status st;
     if ((st = upload(ctx, ctx->d_active, ctx->h_active.data(), ctx->h_active.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_row, ctx->h_edge_row.data(), ctx->h_edge_row.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_roots, f.root_team.data() + rb, (size_t)(re - rb) * 4)) != TPGX_OK) return st;
@@ -206,7 +264,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     const int ts = tpgx_bid_tile_samples(ctx->variant);
     const int64_t nTiles = (nS + ts - 1) / ts;
     const int hw = ctx->obs_hw;
-    tpgx_status st = make_plan(ctx, req->root_begin, req->root_end, ts);
+    tpgx_status st = make_plan(ctx, req->root_begin, req->root_end, ts, keep_bid_single_pass);
     if (st != TPGX_OK) return st;
     const int nA = ctx->plan.nb_active;
 
@@ -229,13 +287,16 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         ctx->tiles_ts = ts;
     }
 
-    /* pass planning: keep the bid matrix of one pass within the budget */
+    /* pass planning: keep the bid matrix (or, in team mode, the decision matrix) of one pass within the budget */
+    const bool team_mode = ctx->plan.team_mode;
+    const int nU = ctx->plan.nb_units;
     int64_t tiles_per_pass = nTiles;
-    const size_t per_tile = (size_t)std::max(nA, 1) * ts * 8;
+    const size_t per_tile = team_mode ? (size_t)std::max(nU, 1) * ts * 4 : (size_t)std::max(nA, 1) * ts * 8;
     if (per_tile * (size_t)nTiles > ctx->bid_budget) tiles_per_pass = std::max<int64_t>(1, (int64_t)(ctx->bid_budget / per_tile));
     if (keep_bid_single_pass && tiles_per_pass < nTiles) return fail(ctx, TPGX_ERR_OOM, "bid output requested but the bid matrix exceeds the budget");
     const int passes = (int)((nTiles + tiles_per_pass - 1) / tiles_per_pass);
-    CU(ctx->d_bid.ensure(per_tile * (size_t)tiles_per_pass));
+    if (team_mode) CU(ctx->d_decision.ensure(per_tile * (size_t)tiles_per_pass));
+    else CU(ctx->d_bid.ensure(per_tile * (size_t)tiles_per_pass));
     CU(ctx->d_conf.ensure((size_t)nR * C * C * 8));
     CU(ctx->d_counters.ensure(8 * 8));
     CU(ctx->d_status.ensure(16));
@@ -260,35 +321,57 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.pixel_lut = ctx->d_pixel_lut.as<double>();
             bp.sobel = ctx->nwin ? ctx->d_sobel.as<double>() + (size_t)t0 * 2 * ctx->nwin * ts : nullptr;
             bp.nwin = ctx->nwin;
-            bp.nb_active = nA;
-            /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 programs per warp */
+            bp.nb_units = nU;
+            /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 units per warp */
             int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
-            chunks = std::min(chunks, std::max(1, nA / 128));
-            bp.progs_per_chunk = (nA + chunks - 1) / chunks;
+            chunks = std::min(chunks, std::max(1, nU / (team_mode ? 448 : 128))); /* >= ~14 teams (or 4 programs) per warp: load balance */
+            bp.units_per_chunk = (nU + chunks - 1) / chunks;
             bp.bid = ctx->d_bid.as<double>();
             bp.row_stride = (long long)nt * ts;
-            CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->plan.k1_ext, ctx->stream));
+            bp.team = ctx->d_tm_team.as<int2>();
+            bp.row_dst = ctx->d_tm_dst.as<int32_t>();
+            bp.decision = ctx->d_decision.as<int32_t>();
+            bp.tie_break = ctx->cfg.tie_break;
+            CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->plan.k1_ext, team_mode, ctx->stream));
         }
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
-        tpgx_trav_params tp{};
-        tp.bid = ctx->d_bid.as<double>();
-        tp.row_stride = (long long)nt * ts;
-        tp.nb_samples = ns;
-        tp.team_edge_offset = ctx->d_team_off.as<int32_t>();
-        tp.edge_row = ctx->d_edge_row.as<int32_t>();
-        tp.edge_destination = ctx->d_edge_dst.as<int32_t>();
-        tp.edge_lines = ctx->d_edge_lines.as<int32_t>();
-        tp.roots = ctx->d_roots.as<int32_t>();
-        tp.nb_roots = nR;
-        tp.labels = ctx->d_labels.as<uint8_t>() + s0;
-        tp.nb_classes = C;
-        tp.action = want_action ? ctx->d_action.as<uint8_t>() + s0 : nullptr;
-        tp.action_stride = nS;
-        tp.confusion = ctx->d_conf.as<unsigned long long>();
-        tp.counters = ctx->d_counters.as<unsigned long long>();
-        tp.tie_break = ctx->cfg.tie_break;
-        tp.status = ctx->d_status.as<int>();
-        CU(tpgx_launch_traverse(tp, ctx->stream));
+        if (team_mode) {
+            tpgx_walk_params wp{};
+            wp.decision = ctx->d_decision.as<int32_t>();
+            wp.row_stride = (long long)nt * ts;
+            wp.nb_samples = ns;
+            wp.team_stat = ctx->d_tm_stat.as<int2>();
+            wp.root_unit = ctx->d_tm_roots.as<int32_t>();
+            wp.nb_roots = nR;
+            wp.labels = ctx->d_labels.as<uint8_t>() + s0;
+            wp.nb_classes = C;
+            wp.action = want_action ? ctx->d_action.as<uint8_t>() + s0 : nullptr;
+            wp.action_stride = nS;
+            wp.confusion = ctx->d_conf.as<unsigned long long>();
+            wp.counters = ctx->d_counters.as<unsigned long long>();
+            wp.status = ctx->d_status.as<int>();
+            CU(tpgx_launch_walk(wp, ctx->stream));
+        } else {
+            tpgx_trav_params tp{};
+            tp.bid = ctx->d_bid.as<double>();
+            tp.row_stride = (long long)nt * ts;
+            tp.nb_samples = ns;
+            tp.team_edge_offset = ctx->d_team_off.as<int32_t>();
+            tp.edge_row = ctx->d_edge_row.as<int32_t>();
+            tp.edge_destination = ctx->d_edge_dst.as<int32_t>();
+            tp.edge_lines = ctx->d_edge_lines.as<int32_t>();
+            tp.roots = ctx->d_roots.as<int32_t>();
+            tp.nb_roots = nR;
+            tp.labels = ctx->d_labels.as<uint8_t>() + s0;
+            tp.nb_classes = C;
+            tp.action = want_action ? ctx->d_action.as<uint8_t>() + s0 : nullptr;
+            tp.action_stride = nS;
+            tp.confusion = ctx->d_conf.as<unsigned long long>();
+            tp.counters = ctx->d_counters.as<unsigned long long>();
+            tp.tie_break = ctx->cfg.tie_break;
+            tp.status = ctx->d_status.as<int>();
+            CU(tpgx_launch_traverse(tp, ctx->stream));
+        }
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
     }
     CU(tpgx_launch_score(ctx->d_conf.as<unsigned long long>(), nR, C, records_out, ctx->stream));
@@ -350,7 +433,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
+    DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_tm_team, &ctx->d_tm_dst, &ctx->d_tm_stat, &ctx->d_tm_roots, &ctx->d_decision, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
                      &ctx->d_counters, &ctx->d_status};

@@ -212,3 +212,42 @@ def test_full_size_properties():
     lo = ev.evaluate_classification(root_begin=0, root_end=R // 2, want=("score",))["score"]
     hi = ev.evaluate_classification(root_begin=R // 2, root_end=R, want=("score",))["score"]
     assert np.array_equal(bits(np.concatenate([lo, hi])), bits(out["score"]))
+
+
+@pytest.mark.parametrize("depth,share,tie", [(1, 0.0, A.TIE_LAST_MAX), (3, 0.05, A.TIE_LAST_MAX), (3, 0.05, A.TIE_FIRST_MAX), (4, 0.0, A.TIE_FIRST_MAX)])
+def test_team_mode_fused_evaluate_team(oracle_mod, depth, share, tie, monkeypatch):
+    """Without a bid output the library fuses [UP] evaluateTeam into the interpreter (team mode): actions, confusion
+    tables, scores and reference-equivalent counters must equal the oracle's AND the unfused bid-matrix path's."""
+    g, ev = make(roots=40, edges=5, lines=14, depth=depth, share_prob=share, seed=50 + depth, tie=tie, intron_lines=2)
+    img, lab = tpgx.synthetic_images(333, seed=6)
+    ev.set_observations(img, lab)
+    want = ("score", "class_f1", "confusion", "action", "counters")
+    dev = ev.evaluate_classification(want=want)
+    ref = oracle_for(oracle_mod, g, tie=tie).evaluate_classification(img, lab, want=want)
+    compare(dev, ref)
+    monkeypatch.setenv("TPGX_TEAM_MODE", "0")
+    g2, ev2 = make(roots=40, edges=5, lines=14, depth=depth, share_prob=share, seed=50 + depth, tie=tie, intron_lines=2)
+    ev2.set_observations(img, lab)
+    unfused = ev2.evaluate_classification(want=want)
+    compare(dev, unfused)
+    assert unfused["counters"]["device_lines"] <= dev["counters"]["device_lines"]   # shared programs run once per team when fused
+
+
+def test_cyclic_graph_uses_visited_team_rule(oracle_mod):
+    """Edges back to already visited teams are skipped BEFORE evaluation ([UP] evaluateTeam, Appendix F U3).  A graph
+    with cycles (every inner team also points back to its root and to itself) cannot be fused; results must still
+    match the oracle."""
+    g = tpgx.synthetic_graph("mnist", roots=12, edges=5, lines=10, depth=3, seed=91)
+    ed = g.edge_destination.copy()
+    teo = g.team_edge_offset
+    rng = np.random.default_rng(3)
+    for t in range(12, g.nb_teams):                       # inner teams: edge 1 -> a root, edge 2 -> itself (edge 0 stays an action)
+        ed[teo[t] + 1] = int(rng.integers(0, 12))
+        ed[teo[t] + 2] = t
+    g.edge_destination = ed
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+    ev.set_graph(g)
+    img, lab = tpgx.synthetic_images(200, seed=12)
+    ev.set_observations(img, lab)
+    want = ("score", "confusion", "action", "counters")
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
