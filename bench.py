@@ -6,7 +6,7 @@ evaluateAllRoots of a MNIST-shaped TPG over 60 000 synthetic 28x28 uint8 samples
     python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement on the host cores
 
 One "step" = one evaluateAllRoots of the whole graph shard over all samples:
-K1 bid interpreter -> K2 graph traversal (+ confusion tables) -> K3 per-root F1 records
+K1 bid interpreter (evaluateTeam fused in: per team x sample the winning edge) -> K2 walk (+ confusion tables) -> K3 per-root F1 records
 (-> NCCL allgather of the records when N > 1).  Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -48,8 +48,8 @@ def workload_config(a, n_gpus):
         "workload": "C2 mnist-shape evaluateAllRoots: G(R=%d per GPU, E=%d, L=%d effective lines, D=%d, mix=%s10, seed=42) x %d synthetic 28x28 uint8 samples, 10 actions"
                     % (a.roots, a.edges, a.lines, a.depth, a.mix, a.samples),
         "roots_per_gpu": a.roots, "total_roots": a.roots * n_gpus, "samples": a.samples, "edges_per_team": a.edges,
-        "lines_per_program": a.lines, "depth": a.depth, "mix": a.mix, "sharding": "roots split across GPUs, 1 NCCL allgather of score records",
-        "l2": "L2 flushed (256 MiB write) before every timed step; bid matrix (%.1f GB) exceeds L2 anyway" % (a.roots * a.edges * a.samples * 8 / 1e9),
+        "lines_per_program": a.lines, "depth": a.depth, "mix": a.mix, "sharding": "roots split across GPUs, 1 NCCL allgather of score records", "pipeline": "K1 bid interpreter with fused evaluateTeam (team mode) -> K2 decision walk + confusion tables -> K3 F1 records",
+        "l2": "L2 flushed (256 MiB write) before every timed step; decision matrix %.2f GB + Sobel planes 0.65 GB exceed L2 anyway" % (a.roots * a.samples * 4 / 1e9),
         "tie_break": "last-max (bid >= best)", "libm": "shared (tpgx_math.h)",
     }
 
@@ -256,7 +256,9 @@ def main():
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    k1_bytes = len(progs) * S * 8.0 + S * 784.0
+    # K1 in team mode (fused evaluateTeam): writes one int32 decision per (team, sample), reads each sample's tile and Sobel planes once
+    nb_teams_shard = (re - rb) if a.depth == 1 else g.nb_teams
+    k1_bytes = nb_teams_shard * S * 4.0 + S * (784.0 + 2 * 676 * 8.0)
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
@@ -273,7 +275,8 @@ def main():
         "hbm": {"achieved": k1_bytes / (k1_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": k1_bytes / (k1_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_launch": k1_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650 GB/s",
-                "k2_achieved": (len(progs) * S * 8.0) / (k2_ms * 1e-3) / 1e9},
+                "k2_achieved": (nb_teams_shard * S * 4.0) / (k2_ms * 1e-3) / 1e9,
+                "bytes_convention": "decision matrix write (4 B per team x sample) + uint8 tile + Sobel planes read once per sample"},
         "device_lines_per_s": cnt["device_lines"] / (k1_ms * 1e-3),
     }
 
