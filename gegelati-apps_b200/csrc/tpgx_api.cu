@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <random>
 #include <string>
 #include <vector>
 
@@ -770,6 +771,28 @@ tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* re
         out->counters->device_lines = c[3]; out->counters->device_program_executions = c[2];
     }
     if (out->device_ms) cudaEventElapsedTime(out->device_ms, ctx->event(0), ctx->event(1));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_mnist_episode_indices(uint64_t seed, int32_t mode, int64_t dataset_size, int64_t nb_actions, int32_t* out) {
+    if (!out || dataset_size < 1 || dataset_size > 0x7fffffff || nb_actions < 0 || mode < 0 || mode > 2) return TPGX_ERR_BAD_ARG;
+    if (mode == 2) { /* TESTING: currentIndex = (currentIndex + 1) % size, starting from -1 */
+        for (int64_t i = 0; i < nb_actions; i++) out[i] = (int32_t)(i % dataset_size);
+        return TPGX_OK;
+    }
+    /* libstdc++ uniform_int_distribution<uint64_t>(0, size-1) on a 64-bit engine: Lemire's nearly
+       divisionless method on the 64x64->128 product (the restatement of csrc/tpgx_rng.h, unbounded stream) */
+    std::mt19937_64 eng(seed);
+    const uint64_t range = (uint64_t)dataset_size;
+    for (int64_t i = 0; i < nb_actions; i++) {
+        unsigned __int128 prod = (unsigned __int128)eng() * range;
+        uint64_t low = (uint64_t)prod;
+        if (low < range) {
+            const uint64_t threshold = (0 - range) % range;
+            while (low < threshold) { prod = (unsigned __int128)eng() * range; low = (uint64_t)prod; }
+        }
+        out[i] = (int32_t)(uint64_t)(prod >> 64);
+    }
     return TPGX_OK;
 }
 

@@ -15,7 +15,7 @@ EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_evaluate_episodes",
-    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe",
+    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices",
 ]
 
 _lib = None
@@ -50,12 +50,41 @@ def load_library():
     lib.tpgx_execute_programs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tpgx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.tpgx_math_probe.argtypes = [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.tpgx_mnist_episode_indices.argtypes = [C.c_uint64, C.c_int32, C.c_int64, C.c_int64, C.c_void_p]
     _lib = lib
     return lib
 
 
 def _ptr(a):
     return a.ctypes.data if a is not None else None
+
+
+def mnist_episode_indices(seed, mode, dataset_size, nb_actions):
+    """sample_index list of one MNIST evaluation ([REF] mnist/src/mnist.cpp:8-34,58-69); host-only."""
+    out = np.zeros(int(nb_actions), dtype=np.int32)
+    st = load_library().tpgx_mnist_episode_indices(int(seed), int(mode), int(dataset_size), int(nb_actions), out.ctypes.data)
+    if st != A.OK:
+        raise TpgxError(st, "tpgx_mnist_episode_indices: bad argument")
+    return out
+
+
+def load_idx(path):
+    """IDX file (the MNIST distribution format read by [REF] mnist/src/mnist_reader/mnist_reader_common.hpp:24-78):
+    big-endian magic 0x0000 08 <ndim>, ndim big-endian uint32 extents, then uint8 data.  Returns a uint8 array;
+    images come back as [count, rows*cols] — the layout tpgx_set_observations takes."""
+    import gzip
+    import struct
+    opener = gzip.open if str(path).endswith(".gz") else open
+    with opener(path, "rb") as f:
+        raw = f.read()
+    if len(raw) < 4 or raw[0] != 0 or raw[1] != 0 or raw[2] != 0x08:
+        raise ValueError("%s: not an unsigned-byte IDX file" % path)
+    ndim = raw[3]
+    dims = struct.unpack(">%dI" % ndim, raw[4:4 + 4 * ndim])
+    data = np.frombuffer(raw, dtype=np.uint8, offset=4 + 4 * ndim)
+    if data.size != int(np.prod(dims)):
+        raise ValueError("%s: %d data bytes, header says %s" % (path, data.size, dims))
+    return data.reshape(dims[0], -1).copy() if ndim > 1 else data.copy()
 
 
 class Evaluator:

@@ -170,6 +170,51 @@ def import_dot(path_or_text, nb_constants):
                    names={"teams": team_ids, "programs": prog_order})
 
 
+def export_dot(g, path=None, version="2.0.0"):
+    """Writes a TPGraph in the TPGGraphDotExporter layout of GEGELATI v2.0.0 (the format of
+    [REF] pendulum/src/CodeGen/Pendulum_out_best.dot), the reference's checkpoint format
+    ([REF] mnist/src/main.cpp:140-143).  Lines are written as given (un-reduced locations, introns included);
+    constants with 6 decimals like the reference.  A program referenced by edges with different destinations is
+    written once per destination (the format ties a program to one destination).  Returns the text."""
+    out = ["// File exported with GEGELATI v%s" % version, "// With the class File::TPGGraphDotExporter (tpgx.export_dot)", "digraph{",
+           '\tgraph[pad = "0.212, 0.055" bgcolor = lightgray]', '\tnode[shape=circle style = filled label = ""]']
+    nc = g.constants.shape[1] if g.constants.ndim == 2 else 0
+    written = {}          # (program, destination) -> P id
+    next_p = 0
+    declared_actions = set()
+    for t in range(g.nb_teams):
+        out.append('\t\tT%d [fillcolor="#1199bb"]' % t)
+    for t in range(g.nb_teams):
+        for e in range(g.team_edge_offset[t], g.team_edge_offset[t + 1]):
+            p, d = int(g.edge_program[e]), int(g.edge_destination[e])
+            if (p, d) in written:
+                out.append("\t\tT%d -> P%d" % (t, written[(p, d)]))
+                continue
+            pid = next_p; next_p += 1
+            written[(p, d)] = pid
+            consts = "".join("%.6f|" % c for c in g.constants[p]) if nc else ""
+            out.append('\t\tP%d [fillcolor="#cccccc" shape=point label="0"] //%s' % (pid, consts))
+            body = "".join("%d|%d&%d|%d#%d|%d&#92;n" % (l["instruction"], l["destination"], l["src"][0], l["loc"][0], l["src"][1], l["loc"][1])
+                           for l in g.lines[g.program_line_offset[p]:g.program_line_offset[p + 1]])
+            out.append('\t\tI%d [shape=box style=invis label="%s"] ' % (pid, body))
+            out.append("\t\tP%d -> I%d[style=invis]" % (pid, pid))
+            if d < 0:
+                a = -1 - d
+                if a not in declared_actions:
+                    declared_actions.add(a)
+                out.append('\t\tA%d [fillcolor="#ff3366" shape=box margin=0.03 width=0 height=0 label="%d"]' % (1000 + a, a))
+                out.append("\t\tT%d -> P%d -> A%d" % (t, pid, 1000 + a))
+            else:
+                out.append("\t\tT%d -> P%d -> T%d" % (t, pid, d))
+    out.append("\t\t{ rank= same %s}" % "".join("T%d " % int(r) for r in g.root_team))
+    out.append("}")
+    text = "\n".join(out) + "\n"
+    if path is not None:
+        with open(path, "w") as f:
+            f.write(text)
+    return text
+
+
 def random_programs(rng, nb_programs, nb_lines, opcodes, sources, nb_registers, nb_constants, allowed=None,
                     intron_lines=0, const_range=(-10, 10), integer_constants=True, balance=True):
     """Programs whose EFFECTIVE lines follow a uniform instruction mix over `allowed`.

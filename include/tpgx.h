@@ -256,6 +256,15 @@ tpgx_status tpgx_execute_programs(tpgx_ctx* ctx, int64_t count, const double* co
  * warp-instructions per second), measured on ctx's device.                                         */
 tpgx_status tpgx_measure_fp64_peak(tpgx_ctx* ctx, double* dadd_per_s, double* dfma_per_s);
 
+/* The image indices one MNIST evaluation classifies, restating [REF] mnist/src/mnist.cpp:58-69 (reset:
+ * rng.setSeed(seed) with the RAW seed, currentIndex = -1, changeCurrentImage) and :8-34 / :50-56 (every
+ * doAction classifies the current image, then draws the next): in TRAINING (0) and VALIDATION (1) mode
+ * index i is the i-th draw of rng.getUnsignedInt64(0, dataset_size - 1) ([UP] Mutator::RNG = mt19937_64 +
+ * uniform_int_distribution); in TESTING (2) mode the images are taken in order, (i) % dataset_size.
+ * dataset_size is the size of the set the mode reads (training set in TRAINING, test set otherwise).
+ * The result is the sample_index list of tpgx_classif_request.  Pure host function, no GPU needed.          */
+tpgx_status tpgx_mnist_episode_indices(uint64_t seed, int32_t mode, int64_t dataset_size, int64_t nb_actions, int32_t* out);
+
 /* Diagnostic entry point for parity tests: evaluates ONE primitive of the device arithmetic
  * (the division / square-root sequences and the shared libm of csrc/tpgx_math.h that stand in for
  * the reference's `/`, sqrt, std::exp, std::log, std::atan, ... — [REF] mnist/src/main.cpp:50-77)

@@ -68,7 +68,8 @@ def test_sample_index_list_app_faithful_draw(oracle_mod):
     g, ev = make(roots=20, edges=5, lines=12, depth=2, seed=11)
     img, lab = tpgx.synthetic_images(2000, seed=2)
     ev.set_observations(img, lab)
-    idx = np.random.default_rng(0).integers(0, 2000, 500).astype(np.int32)
+    idx = tpgx.mnist_episode_indices(seed=7 ^ 0, mode=A.MODE_TRAINING, dataset_size=2000, nb_actions=500)   # Hash(gen) ^ Hash(it), gen 7
+    assert len(np.unique(idx)) < 500 <= len(idx)
     want = ("score", "class_f1", "confusion", "action", "counters")
     dev = ev.evaluate_classification(sample_index=idx, want=want)
     ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, sample_index=idx, want=want)
