@@ -1,0 +1,252 @@
+/*
+ * tpgx_gegelati.hpp — the reference-side binding: a header-only C++17 adapter between GEGELATI's own
+ * types (<gegelati.h>) and the C ABI of libtpgx.so (tpgx.h).
+ *
+ * tpgx::LearningAgent mirrors the part of Learn::LearningAgent / ParallelLearningAgent the apps use
+ * around evaluation ([REF] pendulum/src/Learn/main.cpp:38-39,83; tic-tac-toe/src/Learn/main.cpp:82-83):
+ * same constructor arguments, getTPGGraph(), and
+ *     evaluateAllRoots(generationNumber, mode) -> std::multimap<std::shared_ptr<Learn::EvaluationResult>,
+ *                                                                 const TPG::TPGVertex*>
+ * with the hot path running on the GPU.  It needs only public GEGELATI API: Instructions::Set /
+ * Instruction::{getNbOperands,getOperandTypes,execute}, TPG::TPGGraph::{getVertices,getRootVertices},
+ * TPGVertex::getOutgoingEdges, TPGEdge::{getProgram,getDestination}, TPGAction::getActionID,
+ * Program::{getNbLines,getLine,getConstantAt}, Line::{getInstructionIndex,getDestinationIndex,getOperand}.
+ * GEGELATI itself is not vendored in /root/reference; in this repository the header is compiled against
+ * the API-compatible stand-in oracle/shim/gegelati.h (tests/test_gpu_cpp_adapter.py).
+ *
+ * Errors: any non-zero tpgx_status is rethrown as std::runtime_error(tpgx_last_error()), matching the
+ * reference's error behaviour ([REF] pendulum/src/Learn/pendulum.cpp:66-68).  No CPU fallback: an
+ * instruction whose behaviour matches no device opcode, or an environment the device does not
+ * implement, is an error.
+ */
+#ifndef TPGX_GEGELATI_HPP
+#define TPGX_GEGELATI_HPP
+
+#include <gegelati.h>
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "tpgx.h"
+
+namespace tpgx {
+
+inline void check(tpgx_ctx* ctx, tpgx_status st, const char* where) {
+    if (st != TPGX_OK) throw std::runtime_error(std::string(where) + ": " + tpgx_last_error(ctx));
+}
+
+/* ---- Instructions::Set -> device opcodes by behavioural fingerprint ------------------------------
+ * LambdaInstruction wraps an opaque lambda, so each instruction is run on a fixed probe set and its
+ * results are compared, bit for bit, with the host evaluation of every device behaviour that has the
+ * same operand signature.  Transcendentals are compared through std:: (what the
+ * lambdas call); the device computes them with its own single-source libm (csrc/tpgx_math.h).      */
+namespace detail {
+inline double host_behaviour(int op, double a, double b, int ia, int ib, double c, const double* w) {
+    auto gx = [&] { return -w[0] + w[2] - 2.0 * w[3] + 2.0 * w[5] - w[6] + w[8]; };
+    auto gy = [&] { return -w[0] - 2.0 * w[1] - w[2] + w[6] + 2.0 * w[7] + w[8]; };
+    switch (op) {
+    case TPGX_OP_SUB: return a - b;
+    case TPGX_OP_ADD: return a + b;
+    case TPGX_OP_MUL: return a * b;
+    case TPGX_OP_DIV: return a / b;
+    case TPGX_OP_MAX: return (a < b) ? b : a;
+    case TPGX_OP_EXP: return std::exp(a);
+    case TPGX_OP_LOG: return std::log(a);
+    case TPGX_OP_COS: return std::cos(a);
+    case TPGX_OP_SIN: return std::sin(a);
+    case TPGX_OP_TAN: return std::tan(a);
+    case TPGX_OP_PI: return M_PI;
+    case TPGX_OP_MULC: return a * c / 10.0;
+    case TPGX_OP_FMODG: return b != 0.0 ? std::fmod(a, b) : DBL_MIN;
+    case TPGX_OP_SUB_II: return (double)ia - (double)ib;
+    case TPGX_OP_CAST_I: return (double)ia;
+    case TPGX_OP_EQ0: return a == 0.0 ? 10.0 : 0.0;
+    case TPGX_OP_EQM1: return a == -1.0 ? 10.0 : 0.0;
+    case TPGX_OP_EQ1: return a == 1.0 ? 10.0 : 0.0;
+    case TPGX_OP_GE15: return a >= 15.0 ? 10.0 : 0.0;
+    case TPGX_OP_COND: return a < b ? -a : a;
+    case TPGX_OP_SOBEL_MAGN: { const double x = gx(), y = gy(); return std::sqrt(x * x + y * y); }
+    case TPGX_OP_SOBEL_DIR: return std::atan(gy() / gx());
+    default: return 0.0;
+    }
+}
+inline const char* signature_of(int op) { /* D double, I int, C Data::Constant, W const double[3][3] */
+    switch (op) {
+    case TPGX_OP_SUB: case TPGX_OP_ADD: case TPGX_OP_MUL: case TPGX_OP_DIV: case TPGX_OP_MAX: case TPGX_OP_FMODG: case TPGX_OP_COND: return "DD";
+    case TPGX_OP_MULC: return "DC";
+    case TPGX_OP_SUB_II: return "II";
+    case TPGX_OP_CAST_I: return "I";
+    case TPGX_OP_SOBEL_MAGN: case TPGX_OP_SOBEL_DIR: return "W";
+    default: return "D";
+    }
+}
+inline bool same_bits(double x, double y) { return (x != x && y != y) || std::memcmp(&x, &y, 8) == 0; }
+} // namespace detail
+
+inline std::vector<int32_t> fingerprint(const Instructions::Set& set) {
+    static const double PD[][2] = {{0.0, 0.0}, {1.0, 2.0}, {-1.0, 1.0}, {0.5, -3.25}, {15.0, 7.0}, {16.5, -0.0}, {-7.75, 2.5}, {1e-3, 1e3},
+                                   {3.0, 0.0}, {0.0, 5.0}, {2.75, 2.75}, {-1.0, -1.0}, {100.25, -0.125}, {1.0, 1.0}, {0.3, 0.7}, {20.0, 3.0}};
+    static const int PI_[][2] = {{0, 0}, {3, 1}, {-4, 9}, {21, 4}, {7, 7}, {1, -1}, {100, 3}, {-8, -8}, {5, 2}, {0, 6}, {9, 0}, {2, 2}, {13, 5}, {1, 1}, {4, 8}, {6, 3}};
+    static const double PW[][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {1, 2, 3, 4, 5, 6, 7, 8, 9}, {255, 0, 0, 0, 255, 0, 0, 0, 255}, {10, 0, 200, 30, 7, 90, 0, 0, 1},
+                                   {0, 255, 0, 255, 0, 255, 0, 255, 0}, {9, 8, 7, 6, 5, 4, 3, 2, 1}, {0, 0, 255, 0, 0, 255, 0, 0, 255}, {3, 1, 4, 1, 5, 9, 2, 6, 5}};
+    std::vector<int32_t> ops;
+    for (uint64_t i = 0; i < set.getNbInstructions(); i++) {
+        const Instructions::Instruction& ins = set.getInstruction(i);
+        std::string sig;
+        for (const std::type_info& t : ins.getOperandTypes())
+            sig += t == typeid(double) ? 'D' : t == typeid(int) ? 'I' : t == typeid(Data::Constant) ? 'C' : t == typeid(const double[3][3]) ? 'W' : '?';
+        int found = -1;
+        for (int op = 0; op < TPGX_OP_COUNT && found < 0; op++) {
+            if (sig != detail::signature_of(op)) continue;
+            bool all = true;
+            const int n = sig == "W" ? 8 : 16;
+            for (int k = 0; k < n && all; k++) {
+                std::vector<Data::UntypedSharedPtr> args;
+                const double d0 = PD[k % 16][0], d1 = PD[k % 16][1];
+                for (size_t s = 0; s < sig.size(); s++) {
+                    if (sig[s] == 'D') args.emplace_back(std::make_shared<const double>(s == 0 ? d0 : d1));
+                    else if (sig[s] == 'I') args.emplace_back(std::make_shared<const int>(PI_[k][s]));
+                    else if (sig[s] == 'C') args.emplace_back(std::make_shared<const Data::Constant>(Data::Constant(d1)));
+                    else { /* 3x3 window: 9 contiguous doubles */
+                        std::shared_ptr<double> w(new double[9], std::default_delete<double[]>());
+                        std::memcpy(w.get(), PW[k % 8], sizeof(double) * 9);
+                        args.emplace_back(std::shared_ptr<const double>(w, w.get()));
+                    }
+                }
+                const double got = ins.execute(args);
+                const double want = detail::host_behaviour(op, d0, d1, PI_[k][0], PI_[k][1], d1, PW[k % 8]);
+                all = detail::same_bits(got, want);
+            }
+            if (all) found = op;
+        }
+        if (found < 0) throw std::runtime_error("tpgx::fingerprint: instruction " + std::to_string(i) + " matches no device opcode (no CPU fallback)");
+        ops.push_back(found);
+    }
+    return ops;
+}
+
+/* ---- TPG::TPGGraph -> tpgx_graph, in the library's own iteration order -------------------------- */
+struct FlatGraph {
+    std::vector<int64_t> lineOffset;
+    std::vector<tpgx_line> lines;
+    std::vector<double> constants;
+    std::vector<int32_t> teamEdgeOffset, edgeProgram, edgeDestination, rootTeam;
+    std::vector<const TPG::TPGVertex*> roots;
+    int32_t nbPrograms = 0, nbTeams = 0;
+    tpgx_graph view() const {
+        return tpgx_graph{nbPrograms, lineOffset.data(), lines.data(), nullptr, constants.empty() ? nullptr : constants.data(), nbTeams,
+                          teamEdgeOffset.data(), edgeProgram.data(), edgeDestination.data(), (int32_t)rootTeam.size(), rootTeam.data()};
+    }
+};
+
+inline FlatGraph flatten(const TPG::TPGGraph& graph) {
+    FlatGraph f;
+    const size_t nc = graph.getEnvironment().getNbConstant();
+    std::map<const TPG::TPGVertex*, int32_t> teamId;
+    std::map<const Program::Program*, int32_t> progId;
+    std::vector<const TPG::TPGTeam*> teams;
+    for (const TPG::TPGVertex* v : graph.getVertices())
+        if (auto* t = dynamic_cast<const TPG::TPGTeam*>(v)) { teamId[v] = (int32_t)teams.size(); teams.push_back(t); }
+    f.lineOffset.push_back(0);
+    f.teamEdgeOffset.push_back(0);
+    for (const TPG::TPGTeam* t : teams) {
+        for (const TPG::TPGEdge* e : t->getOutgoingEdges()) {          /* std::list order: it decides ties */
+            const Program::Program* p = &e->getProgram();
+            auto it = progId.find(p);
+            if (it == progId.end()) {
+                it = progId.emplace(p, (int32_t)progId.size()).first;
+                for (uint64_t l = 0; l < p->getNbLines(); l++) {
+                    const Program::Line& L = p->getLine(l);
+                    tpgx_line out{(uint32_t)L.getInstructionIndex(), (uint32_t)L.getDestinationIndex(),
+                                  {(uint32_t)L.getOperand(0).first, (uint32_t)L.getOperand(1).first},
+                                  {(uint32_t)L.getOperand(0).second, (uint32_t)L.getOperand(1).second}};
+                    f.lines.push_back(out);
+                }
+                f.lineOffset.push_back((int64_t)f.lines.size());
+                for (size_t c = 0; c < nc; c++) f.constants.push_back((double)p->getConstantAt(c));
+            }
+            f.edgeProgram.push_back(it->second);
+            const TPG::TPGVertex* d = e->getDestination();
+            if (auto* a = dynamic_cast<const TPG::TPGAction*>(d)) f.edgeDestination.push_back(-1 - (int32_t)a->getActionID());
+            else f.edgeDestination.push_back(teamId.at(d));
+        }
+        f.teamEdgeOffset.push_back((int32_t)f.edgeProgram.size());
+    }
+    for (const TPG::TPGVertex* r : graph.getRootVertices())
+        if (teamId.count(r)) { f.rootTeam.push_back(teamId.at(r)); f.roots.push_back(r); }
+    f.nbPrograms = (int32_t)progId.size();
+    f.nbTeams = (int32_t)teams.size();
+    return f;
+}
+
+/* ---- the agent ----------------------------------------------------------------------------------- */
+class LearningAgent {
+  protected:
+    Learn::LearningEnvironment& learningEnvironment;
+    Learn::LearningParameters params;
+    Environment env;
+    std::shared_ptr<TPG::TPGGraph> tpg;
+    tpgx_ctx* ctx = nullptr;
+    tpgx_env_kind kind;
+    int secondPlayerRandom = 0;
+    std::vector<double> pendulumActions;
+
+  public:
+    /* `kind` names the device restatement of `le` (the app's LearningEnvironment subclass) */
+    LearningAgent(Learn::LearningEnvironment& le, const Instructions::Set& set, const Learn::LearningParameters& p, tpgx_env_kind k,
+                  int tieBreak = TPGX_TIE_LAST_MAX)
+        : learningEnvironment(le), params(p), env(set, le.getDataSources(), p.nbRegisters, p.nbProgramConstant),
+          tpg(std::make_shared<TPG::TPGGraph>(env)), kind(k) {
+        tpgx_config cfg{};
+        cfg.device = 0; cfg.nb_registers = (int32_t)p.nbRegisters; cfg.nb_constants = (int32_t)p.nbProgramConstant; cfg.tie_break = tieBreak;
+        check(nullptr, tpgx_create(&cfg, &ctx), "tpgx_create");
+        const std::vector<int32_t> ops = fingerprint(set);
+        check(ctx, tpgx_set_instruction_table(ctx, (int32_t)ops.size(), ops.data()), "tpgx_set_instruction_table");
+        std::vector<tpgx_source_desc> src;
+        for (const Data::DataHandler& dh : le.getDataSources()) {   /* PrimitiveTypeArray<double|int>(n) */
+            const size_t nd = dh.getAddressSpace(typeid(double)), ni = dh.getAddressSpace(typeid(int));
+            src.push_back(tpgx_source_desc{nd ? TPGX_ELEM_F64 : TPGX_ELEM_I32, 1, (int32_t)(nd ? nd : ni), 0});
+        }
+        check(ctx, tpgx_set_data_sources(ctx, (int32_t)src.size(), src.data()), "tpgx_set_data_sources");
+    }
+    LearningAgent(const LearningAgent&) = delete;
+    ~LearningAgent() { tpgx_destroy(ctx); }
+
+    std::shared_ptr<TPG::TPGGraph> getTPGGraph() { return tpg; }
+    void setSecondPlayerRandom(bool r) { secondPlayerRandom = r ? 1 : 0; }
+    void setPendulumActions(const std::vector<double>& a) { pendulumActions = a; }   /* [REF] pendulum/src/Learn/main.cpp:33 */
+
+    /* [UP] LearningAgent::evaluateAllRoots: one job per root, nbIterationsPerPolicyEvaluation episodes of at most
+       maxNbActionsPerEval actions each, episode seed Hash(generationNumber) ^ Hash(iteration), score = mean. */
+    std::multimap<std::shared_ptr<Learn::EvaluationResult>, const TPG::TPGVertex*> evaluateAllRoots(uint64_t generationNumber, Learn::LearningMode mode) {
+        const FlatGraph f = flatten(*tpg);
+        const tpgx_graph g = f.view();
+        check(ctx, tpgx_set_graph(ctx, &g), "tpgx_set_graph");
+        const int NI = (int)params.nbIterationsPerPolicyEvaluation, R = (int)f.roots.size();
+        std::vector<uint64_t> seeds(NI);
+        for (int it = 0; it < NI; it++) seeds[it] = Data::Hash<uint64_t>()(generationNumber) ^ Data::Hash<uint64_t>()((uint64_t)it);
+        std::vector<int32_t> jobRoots(R);
+        for (int r = 0; r < R; r++) jobRoots[r] = r;
+        tpgx_episode_request rq{};
+        rq.env = kind; rq.mode = (int32_t)mode; rq.nb_iterations = NI; rq.max_actions = (int32_t)params.maxNbActionsPerEval;
+        rq.seeds = seeds.data(); rq.nb_jobs = R; rq.roots_per_job = 1; rq.job_roots = jobRoots.data();
+        rq.second_player_random = secondPlayerRandom;
+        rq.nb_pendulum_actions = (int32_t)pendulumActions.size(); rq.pendulum_actions = pendulumActions.data();
+        std::vector<double> score(R);
+        tpgx_episode_result out{};
+        out.score = score.data();
+        check(ctx, tpgx_evaluate_episodes(ctx, &rq, &out), "tpgx_evaluate_episodes");
+        std::multimap<std::shared_ptr<Learn::EvaluationResult>, const TPG::TPGVertex*> results;
+        for (int r = 0; r < R; r++) results.emplace(std::make_shared<Learn::EvaluationResult>(score[r], (size_t)NI), f.roots[r]);
+        return results;
+    }
+};
+
+} // namespace tpgx
+#endif

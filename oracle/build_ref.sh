@@ -42,5 +42,14 @@ obj stickgame_ins  "$REF/stickgame/src/Learn/instructions.cpp" -DfillInstruction
 obj tictactoe_env  "$REF/tic-tac-toe/src/Learn/TicTacToe.cpp"
 obj wrap           "$HERE/ref_wrap.cpp"
 "$CXX" -shared -o "$OUT/libtpgref.so" "$OUT"/*.o
+rm -f "$OUT/wrap.o"
+# The C++ adapter demo: the same reference objects + tests/cpp/adapter_driver.cpp + include/tpgx_gegelati.hpp, linked
+# against the product library (needs it built; skipped otherwise).
+LIBDIR="$HERE/../gegelati-apps_b200/lib"
+if [ -f "$LIBDIR/libtpgx.so" ]; then
+  "$CXX" $FLAGS -I"$HERE/../include" "$HERE/../tests/cpp/adapter_driver.cpp" "$OUT"/*.o -o "$OUT/adapter_driver" \
+      -L"$LIBDIR" -ltpgx -Wl,-rpath,'$ORIGIN/../../gegelati-apps_b200/lib'
+  echo "built $OUT/adapter_driver"
+fi
 rm -f "$OUT"/*.o
 echo "built $OUT/libtpgref.so"

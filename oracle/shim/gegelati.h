@@ -23,7 +23,9 @@
 #include <cstddef>
 #include <cstdint>
 #include <functional>
+#include <fstream>
 #include <iostream>
+#include <list>
 #include <map>
 #include <memory>
 #include <random>
@@ -118,6 +120,21 @@ class Instruction {
     virtual OperandKind getOperandKind(unsigned int i) const = 0;
     /* shim-only uniform call: every operand slot supplied in every representation */
     virtual double call(const double* d, const int* i, const double* c, const double (*w)[3]) const = 0;
+    /* upstream-style API used by adapters: operand types and execution on type-erased arguments */
+    virtual const std::vector<std::reference_wrapper<const std::type_info>>& getOperandTypes() const = 0;
+    double execute(const std::vector<Data::UntypedSharedPtr>& args) const {
+        double d[2] = {0, 0}, c[2] = {0, 0}, w[3][3] = {{0}};
+        int iv[2] = {0, 0};
+        for (unsigned k = 0; k < getNbOperands() && k < args.size(); k++) {
+            switch (getOperandKind(k)) {
+            case OperandKind::Double: d[k] = *args[k].getSharedPointer<const double>(); break;
+            case OperandKind::Int: iv[k] = *args[k].getSharedPointer<const int>(); break;
+            case OperandKind::Constant: c[k] = (double)*args[k].getSharedPointer<const Data::Constant>(); break;
+            case OperandKind::Window3x3: { const double* p = args[k].getSharedPointer<const double>().get(); for (int r = 0; r < 9; r++) w[r / 3][r % 3] = p[r]; break; }
+            }
+        }
+        return call(d, iv, c, w);
+    }
 };
 
 namespace detail {
@@ -154,6 +171,10 @@ template <class First, class... Rest> class LambdaInstruction : public Instructi
     double call(const double* d, const int* i, const double* c, const double (*w)[3]) const override {
         return invoke(std::index_sequence_for<Rest...>{}, d, i, c, w);
     }
+    const std::vector<std::reference_wrapper<const std::type_info>>& getOperandTypes() const override {
+        static const std::vector<std::reference_wrapper<const std::type_info>> types = {typeid(First), typeid(Rest)...};
+        return types;
+    }
     const std::string& getPrintTemplate() const { return printTemplate; }
 };
 
@@ -166,6 +187,171 @@ class Set {
 };
 
 } // namespace Instructions
+
+/* ---- minimal program / graph model (what an adapter flattens; names as the apps and upstream use them) ---- */
+class Environment {
+    const Instructions::Set& set;
+    std::vector<std::reference_wrapper<const Data::DataHandler>> sources;
+    size_t nbRegisters, nbConstants;
+  public:
+    Environment(const Instructions::Set& s, const std::vector<std::reference_wrapper<const Data::DataHandler>>& src, size_t nbRegs, size_t nbConst = 0)
+        : set(s), sources(src), nbRegisters(nbRegs), nbConstants(nbConst) {}
+    const Instructions::Set& getInstructionSet() const { return set; }
+    const std::vector<std::reference_wrapper<const Data::DataHandler>>& getDataSources() const { return sources; }
+    size_t getNbRegisters() const { return nbRegisters; }
+    size_t getNbConstant() const { return nbConstants; }
+};
+
+namespace Program {
+class Line {
+    uint64_t instructionIndex = 0, destinationIndex = 0;
+    std::pair<uint64_t, uint64_t> operands[2] = {{0, 0}, {0, 0}};
+  public:
+    uint64_t getInstructionIndex() const { return instructionIndex; }
+    uint64_t getDestinationIndex() const { return destinationIndex; }
+    const std::pair<uint64_t, uint64_t>& getOperand(unsigned k) const { return operands[k]; }
+    void setInstructionIndex(uint64_t v) { instructionIndex = v; }
+    void setDestinationIndex(uint64_t v) { destinationIndex = v; }
+    void setOperand(unsigned k, uint64_t source, uint64_t location) { operands[k] = {source, location}; }
+};
+class Program {
+    std::vector<Line> lines;
+    std::vector<double> constants;
+  public:
+    explicit Program(const Environment& env) : constants(env.getNbConstant(), 0.0) {}
+    size_t getNbLines() const { return lines.size(); }
+    const Line& getLine(uint64_t i) const { return lines.at(i); }
+    Line& addNewLine() { lines.emplace_back(); return lines.back(); }
+    Data::Constant getConstantAt(size_t i) const { return Data::Constant(constants.at(i)); }
+    void setConstantAt(size_t i, double v) { constants.at(i) = v; }
+};
+} // namespace Program
+
+namespace TPG {
+class TPGEdge;
+class TPGVertex {
+  protected:
+    std::list<TPGEdge*> outgoing;
+  public:
+    virtual ~TPGVertex() = default;
+    const std::list<TPGEdge*>& getOutgoingEdges() const { return outgoing; }
+    void addOutgoingEdge(TPGEdge* e) { outgoing.push_back(e); }
+};
+class TPGTeam : public TPGVertex {};
+class TPGAction : public TPGVertex {
+    uint64_t actionID;
+  public:
+    explicit TPGAction(uint64_t id) : actionID(id) {}
+    uint64_t getActionID() const { return actionID; }
+};
+class TPGEdge {
+    const TPGVertex* source;
+    const TPGVertex* destination;
+    std::shared_ptr<Program::Program> program;
+  public:
+    TPGEdge(const TPGVertex* s, const TPGVertex* d, std::shared_ptr<Program::Program> p) : source(s), destination(d), program(std::move(p)) {}
+    const TPGVertex* getSource() const { return source; }
+    const TPGVertex* getDestination() const { return destination; }
+    const Program::Program& getProgram() const { return *program; }
+    std::shared_ptr<Program::Program> getProgramSharedPointer() const { return program; }
+};
+class TPGGraph {
+    const Environment& env;
+    std::vector<std::unique_ptr<TPGVertex>> vertices;
+    std::list<std::unique_ptr<TPGEdge>> edges;
+    std::vector<const TPGVertex*> roots;
+  public:
+    explicit TPGGraph(const Environment& e) : env(e) {}
+    const Environment& getEnvironment() const { return env; }
+    TPGTeam& addNewTeam() { vertices.emplace_back(new TPGTeam()); return static_cast<TPGTeam&>(*vertices.back()); }
+    TPGAction& addNewAction(uint64_t id) { vertices.emplace_back(new TPGAction(id)); return static_cast<TPGAction&>(*vertices.back()); }
+    TPGEdge& addNewEdge(TPGVertex& src, const TPGVertex& dst, std::shared_ptr<Program::Program> prog) {
+        edges.emplace_back(new TPGEdge(&src, &dst, std::move(prog)));
+        src.addOutgoingEdge(edges.back().get());
+        return *edges.back();
+    }
+    std::vector<const TPGVertex*> getVertices() const { std::vector<const TPGVertex*> v; for (auto& x : vertices) v.push_back(x.get()); return v; }
+    /* upstream derives roots from incoming edges; the importer records them from the file */
+    void setRootVertices(const std::vector<const TPGVertex*>& r) { roots = r; }
+    const std::vector<const TPGVertex*>& getRootVertices() const { return roots; }
+    void clearProgramIntrons() {}
+};
+} // namespace TPG
+
+namespace File {
+/* Reader of the TPGGraphDotExporter layout, enough for the reference's golden graphs. */
+class TPGGraphDotImporter {
+    std::string path;
+    const Environment& env;
+    TPG::TPGGraph& graph;
+  public:
+    TPGGraphDotImporter(const char* filePath, const Environment& e, TPG::TPGGraph& g) : path(filePath), env(e), graph(g) {}
+    void importGraph() {
+        std::ifstream in(path);
+        if (!in) throw std::runtime_error("TPGGraphDotImporter: cannot open " + path);
+        std::map<long, TPG::TPGTeam*> teams;
+        std::map<long, std::shared_ptr<Program::Program>> programs;
+        std::map<long, const TPG::TPGVertex*> progDest;
+        std::map<long, long> actionLabel;
+        std::string ln;
+        auto num = [](const std::string& s, size_t& pos) { size_t used = 0; long v = std::stol(s.substr(pos), &used); pos += used; return v; };
+        while (std::getline(in, ln)) {
+            size_t p = ln.find_first_not_of(" \t");
+            if (p == std::string::npos) continue;
+            ln = ln.substr(p);
+            if (ln.rfind("{ rank= same", 0) == 0) {
+                std::vector<const TPG::TPGVertex*> roots;
+                for (size_t q = ln.find('T'); q != std::string::npos; q = ln.find('T', q)) { q++; roots.push_back(teams.at(num(ln, q))); }
+                graph.setRootVertices(roots);
+            } else if (ln[0] == 'T' && ln.find("[fillcolor") != std::string::npos) {
+                size_t q = 1; teams[num(ln, q)] = &graph.addNewTeam();
+            } else if (ln[0] == 'P' && ln.find("shape=point") != std::string::npos) {
+                size_t q = 1; const long id = num(ln, q);
+                auto prog = std::make_shared<Program::Program>(env);
+                q = ln.find("//");
+                if (q != std::string::npos) {
+                    q += 2; size_t i = 0;
+                    while (q < ln.size() && i < env.getNbConstant()) { size_t bar = ln.find('|', q); if (bar == std::string::npos) break; prog->setConstantAt(i++, std::stod(ln.substr(q, bar - q))); q = bar + 1; }
+                }
+                programs[id] = prog;
+            } else if (ln[0] == 'I' && ln.find("label=\"") != std::string::npos) {
+                size_t q = 1; const long id = num(ln, q);
+                q = ln.find("label=\"") + 7;
+                const size_t end = ln.find('"', q);
+                std::string body = ln.substr(q, end - q);
+                size_t b = 0;
+                while (b < body.size()) {
+                    size_t e2 = body.find("&#92;n", b);
+                    if (e2 == std::string::npos) e2 = body.size();
+                    std::string item = body.substr(b, e2 - b);
+                    if (!item.empty()) {   /* instr|dest&src0|loc0#src1|loc1 */
+                        long v[6]; size_t r = 0;
+                        for (int k = 0; k < 6; k++) { v[k] = num(item, r); r++; }
+                        Program::Line& L = programs.at(id)->addNewLine();
+                        L.setInstructionIndex((uint64_t)v[0]); L.setDestinationIndex((uint64_t)v[1]);
+                        L.setOperand(0, (uint64_t)v[2], (uint64_t)v[3]); L.setOperand(1, (uint64_t)v[4], (uint64_t)v[5]);
+                    }
+                    b = e2 + 6;
+                }
+            } else if (ln[0] == 'A' && ln.find("label=\"") != std::string::npos) {
+                size_t q = 1; const long id = num(ln, q);
+                q = ln.find("label=\"") + 7; actionLabel[id] = num(ln, q);
+            } else if (ln[0] == 'T' && ln.find("-> P") != std::string::npos) {
+                size_t q = 1; const long t = num(ln, q);
+                q = ln.find("-> P") + 4; const long pid = num(ln, q);
+                size_t arrow = ln.find("->", q);
+                if (arrow != std::string::npos) {
+                    q = ln.find_first_of("TA", arrow);
+                    const char kind = ln[q]; q++;
+                    const long d = num(ln, q);
+                    progDest[pid] = kind == 'T' ? static_cast<const TPG::TPGVertex*>(teams.at(d)) : &graph.addNewAction((uint64_t)actionLabel.at(d));
+                }
+                graph.addNewEdge(*teams.at(t), *progDest.at(pid), programs.at(pid));
+            }
+        }
+    }
+};
+} // namespace File
 
 namespace Learn {
 
@@ -201,6 +387,12 @@ class EvaluationResult {
     virtual ~EvaluationResult() = default;
     virtual double getResult() const { return result; }
     virtual size_t getNbEvaluation() const { return nbEvaluation; }
+};
+
+struct LearningParameters {   /* the fields evaluation reads (the apps' params.json files) */
+    size_t nbRegisters = 8, nbProgramConstant = 0;
+    uint64_t maxNbActionsPerEval = 1000, nbIterationsPerPolicyEvaluation = 5, nbIterationsPerJob = 1;
+    uint64_t nbGenerations = 1, nbThreads = 1;
 };
 
 class AdversarialEvaluationResult : public EvaluationResult {

@@ -1,0 +1,52 @@
+"""The C++ reference-side binding (include/tpgx_gegelati.hpp) end to end: a program that reads like the apps' own
+main.cpp — the REFERENCE's fillInstructionSet and LearningEnvironment classes, compiled unmodified, a golden graph
+imported with the dot importer, tpgx::LearningAgent::evaluateAllRoots — runs the hot path on the GPU; its per-root
+scores must equal the oracle's.  The binary is built by oracle/build_ref.sh in the build container (it contains
+reference code, so it lives in oracle/_ref/ and travels to the GPU box with the snapshot)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+import tpgx
+from tpgx import abi as A
+
+pytestmark = pytest.mark.gpu
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "adapter_driver")
+PEND_ACTIONS = [0.05, 0.1, 0.2, 0.4, 0.6, 0.8, 1.0]
+
+
+def run_driver(app, dot, generation, mode, iterations, max_actions, second_random=0):
+    out = subprocess.run([DRIVER, app, dot, str(generation), str(mode), str(iterations), str(max_actions), str(second_random)],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    rows = [ln.split() for ln in out.stdout.strip().splitlines()]
+    return np.array([float.fromhex(r[0]) for r in rows]), [int(r[1]) for r in rows]
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/adapter_driver not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("app,dot,iters,maxa,spr,exact", [
+    ("stickgame", "StickGame_out_best.dot", 100, 11, 1, True),       # [REF] stickgame/params.json:15,97; random second player
+    ("tictactoe", "TicTacToe_out_best.dot", 10, 5, 1, True),         # [REF] tic-tac-toe/params.json:15,97
+    ("pendulum", "Pendulum_out_best.dot", 5, 1000, 0, True),         # [REF] pendulum/params.json:18,142 (vs the shared-libm oracle)
+])
+def test_reference_sources_drive_the_gpu_evaluator(oracle_mod, app, dot, iters, maxa, spr, exact):
+    path = os.path.join(GOLDEN, dot)
+    generation, mode = 3, A.MODE_TRAINING
+    scores, nb_eval = run_driver(app, path, generation, mode, iters, maxa, spr)
+    g = tpgx.import_dot(path, tpgx.APP_CONSTANTS[app])
+    o = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], g, nb_constants=tpgx.APP_CONSTANTS[app])
+    ref = o.evaluate_episodes(tpgx.APP_ENV[app], seeds=[generation ^ it for it in range(iters)], job_roots=np.arange(g.nb_roots), max_actions=maxa,
+                              mode=mode, second_player_random=spr, pendulum_actions=PEND_ACTIONS if app == "pendulum" else None)
+    assert nb_eval == [iters] * g.nb_roots
+    assert scores.shape == (g.nb_roots,)
+    assert np.array_equal(scores.view(np.uint64), ref["score"][:, 0].view(np.uint64)), (scores, ref["score"][:, 0])
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/adapter_driver not built")
+def test_errors_surface_as_exceptions_like_the_reference():
+    """A missing graph file is reported through std::runtime_error -> exit code 1 and a message, not a crash."""
+    out = subprocess.run([DRIVER, "pendulum", "/nonexistent.dot", "0", "0", "1", "10"], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 1 and "cannot open" in out.stderr
