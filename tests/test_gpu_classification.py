@@ -252,3 +252,26 @@ def test_cyclic_graph_uses_visited_team_rule(oracle_mod):
     ev.set_observations(img, lab)
     want = ("score", "confusion", "action", "counters")
     compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+@pytest.mark.parametrize("ops_from", ["pendulum", "tictactoe"])
+def test_extended_instruction_build_of_k1(oracle_mod, ops_from):
+    """K1 has two builds: the MNIST instruction set only and the extended one (cos sin tan pi fmod-guard, the equality
+    tests, cond).  An image-classification agent is free to use any double-typed instruction, so the other apps'
+    sets are run over the MNIST data source too."""
+    opcodes = tpgx.INSTRUCTION_SETS[ops_from]
+    nc = tpgx.APP_CONSTANTS[ops_from]
+    rng = np.random.default_rng(17)
+    P, R, E = 60, 12, 5
+    lines, plo, consts = tpgx.random_programs(rng, P, 10, opcodes, tpgx.APP_SOURCES["mnist"], 8, nc)
+    g = tpgx.TPGraph(lines=lines, program_line_offset=plo, constants=consts, team_edge_offset=(np.arange(R + 1) * E).astype(np.int32),
+                     edge_program=np.arange(P, dtype=np.int32), edge_destination=(-1 - rng.integers(0, 10, P)).astype(np.int32),
+                     root_team=np.arange(R, dtype=np.int32))
+    img, lab = tpgx.synthetic_images(150, seed=33)
+    for want in (("score", "confusion", "action", "bid", "counters"), ("score", "confusion", "action", "counters")):   # bid mode, team mode
+        ev = tpgx.Evaluator(opcodes, tpgx.APP_SOURCES["mnist"], nb_constants=nc)
+        ev.set_graph(g)
+        ev.set_observations(img, lab)
+        dev = ev.evaluate_classification(want=want)
+        ref = oracle_mod.Oracle(opcodes, tpgx.APP_SOURCES["mnist"], g, nb_constants=nc).evaluate_classification(img, lab, want=want)
+        compare(dev, ref)
