@@ -285,11 +285,13 @@ def main():
     pin_lab = torch.from_numpy(lab).pin_memory()
     graph_bytes = g.lines.nbytes + g.program_line_offset.nbytes + g.constants.nbytes + g.team_edge_offset.nbytes + g.edge_program.nbytes + g.edge_destination.nbytes + g.root_team.nbytes
     ev2 = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5, device=local)
+    g_shard = g.subgraph(rb, re) if world > 1 else g   # a rank only ships the part of the graph its roots can reach
+    graph_bytes = g_shard.lines.nbytes + g_shard.program_line_offset.nbytes + g_shard.constants.nbytes + g_shard.team_edge_offset.nbytes + g_shard.edge_program.nbytes + g_shard.edge_destination.nbytes + g_shard.root_team.nbytes
 
     def e2e_step():
         ev2.set_observations(pin_img.numpy(), pin_lab.numpy())   # returns once the copies are done; re-tiling overlaps the next call
-        ev2.set_graph(g)
-        return ev2.evaluate_classification(root_begin=rb, root_end=re, want=("score", "class_f1"))
+        ev2.set_graph(g_shard)
+        return ev2.evaluate_classification(want=("score", "class_f1"))
 
     e2e_steps = max(2, min(a.steps, 5))
     e2e_step()

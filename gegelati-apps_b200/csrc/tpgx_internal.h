@@ -25,6 +25,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <vector>
@@ -167,8 +168,12 @@ struct tpgx_flat_graph {
 /* Splits [0, n) into contiguous blocks over up to 16 host threads (the host side of a generation is
  * pure per-program work: intron marking, encoding); fn(begin, end, worker) runs once per block. */
 template <class F> static inline void tpgx_parallel_blocks(int n, int min_per_thread, F fn) {
+    /* host threads of this process: TPGX_HOST_THREADS, else the cores divided by the ranks sharing the node
+       (torchrun exports LOCAL_WORLD_SIZE), at most 16 */
     unsigned hw = std::thread::hardware_concurrency();
+    if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) hw = std::max(1u, hw / (unsigned)w); }
     int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
+    if (const char* ht = getenv("TPGX_HOST_THREADS")) { const int v = atoi(ht); if (v >= 1) nt = std::min(v, 16); }
     nt = std::max(1, std::min(nt, n / std::max(1, min_per_thread)));
     if (nt <= 1) { fn(0, n, 0); return; }
     std::vector<std::thread> th;

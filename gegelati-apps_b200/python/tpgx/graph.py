@@ -56,6 +56,38 @@ class TPGraph:
     @property
     def nb_edges(self): return len(self.edge_program)
 
+    def subgraph(self, root_begin, root_end):
+        """The part of the graph reachable from roots [root_begin, root_end), renumbered (teams in BFS order, programs in
+        order of first use); its roots are exactly that slice.  What one rank of a multi-GPU job hands to tpgx_set_graph,
+        so that the host flattener only touches the rank's own shard."""
+        teo, ep, ed = self.team_edge_offset, self.edge_program, self.edge_destination
+        roots = np.asarray(self.root_team[root_begin:root_end])
+        order, seen = list(dict.fromkeys(int(t) for t in roots)), None
+        seen = set(order)
+        q = 0
+        while q < len(order):
+            t = order[q]; q += 1
+            for d in ed[teo[t]:teo[t + 1]]:
+                if d >= 0 and int(d) not in seen:
+                    seen.add(int(d)); order.append(int(d))
+        order = np.array(order, dtype=np.int64)
+        tmap = np.full(self.nb_teams, -1, dtype=np.int32); tmap[order] = np.arange(len(order), dtype=np.int32)
+        cnt = (teo[order + 1] - teo[order]).astype(np.int64)
+        new_teo = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+        eidx = np.concatenate([np.arange(teo[t], teo[t + 1]) for t in order]) if len(order) else np.zeros(0, dtype=np.int64)
+        old_p = ep[eidx]
+        uniq, first = np.unique(old_p, return_index=True)
+        uniq = uniq[np.argsort(first)]                      # order of first use
+        pmap = np.full(self.nb_programs, -1, dtype=np.int32); pmap[uniq] = np.arange(len(uniq), dtype=np.int32)
+        plo = self.program_line_offset
+        lens = (plo[uniq + 1] - plo[uniq]).astype(np.int64)
+        new_plo = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        lidx = np.concatenate([np.arange(plo[p], plo[p + 1]) for p in uniq]) if len(uniq) else np.zeros(0, dtype=np.int64)
+        d_old = ed[eidx]
+        new_ed = np.where(d_old >= 0, tmap[np.maximum(d_old, 0)], d_old).astype(np.int32)
+        return TPGraph(lines=self.lines[lidx], program_line_offset=new_plo, constants=self.constants[uniq], team_edge_offset=new_teo,
+                       edge_program=pmap[old_p], edge_destination=new_ed, root_team=tmap[roots].astype(np.int32))
+
     def c_struct(self):
         """Returns (Graph struct, keepalive list)."""
         arrs = dict(

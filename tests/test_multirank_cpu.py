@@ -60,3 +60,19 @@ def test_two_ranks_gloo_equal_single_process(tmp_path, oracle_mod):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % rank))
         assert got.shape == ref.shape
         assert np.array_equal(got.view(np.uint64), ref.view(np.uint64)), rank
+
+
+def test_subgraph_of_a_root_shard_evaluates_identically(oracle_mod):
+    """TPGraph.subgraph (what a rank uploads) keeps exactly the reachable part in reference order: scores of the
+    shard's roots are unchanged, shared inner teams and programs included."""
+    g = tpgx.synthetic_graph("mnist", roots=14, edges=4, lines=9, depth=3, share_prob=0.2, seed=23)
+    img, lab = tpgx.synthetic_images(80, seed=3)
+    full = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], g, nb_constants=5).evaluate_classification(
+        img, lab, want=("score", "confusion", "counters"))
+    for b, e in ((0, 5), (5, 14), (3, 4)):
+        sg = g.subgraph(b, e)
+        assert sg.nb_roots == e - b and sg.nb_teams <= g.nb_teams and sg.nb_programs <= g.nb_programs
+        part = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], sg, nb_constants=5).evaluate_classification(
+            img, lab, want=("score", "confusion"))
+        assert np.array_equal(part["score"].view(np.uint64), full["score"][b:e].view(np.uint64))
+        assert np.array_equal(part["confusion"], full["confusion"][b:e])
