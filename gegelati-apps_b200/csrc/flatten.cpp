@@ -45,7 +45,7 @@ std::string fmt(const char* f, long a = 0, long b = 0, long c = 0) {
 
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
                                const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
-                               tpgx_flat_graph* out, std::string* err) {
+                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out) {
     auto fail = [&](tpgx_status st, const std::string& m) { if (err) *err = m; return st; };
     if (!g || !g->program_line_offset || !g->team_edge_offset || !g->edge_program || !g->edge_destination || !g->root_team)
         return fail(TPGX_ERR_BAD_ARG, "tpgx_set_graph: null array in graph");
@@ -111,6 +111,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
         }
     });
     for (const Err& er : errs) if (er.st != TPGX_OK) return fail(er.st, er.msg);
+    if (keep_out) *keep_out = keep;
     f.prog_offset.assign((size_t)P + 1, 0);
     for (int p = 0; p < P; p++) f.prog_offset[p + 1] = f.prog_offset[p] + n_eff[p];
     f.code.assign((size_t)f.prog_offset[P], 0u);
@@ -179,5 +180,33 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     f.nb_roots = g->nb_roots;
     f.root_team.assign(g->root_team, g->root_team + g->nb_roots);
     for (int r : f.root_team) if (r < 0 || r >= g->nb_teams) return fail(TPGX_ERR_BAD_ARG, "root team out of range");
+    return TPGX_OK;
+}
+
+extern "C" tpgx_status tpgx_flatten_programs(const tpgx_config* cfg, int32_t nb_instructions, const int32_t* opcode, int32_t nb_sources,
+                                             const tpgx_source_desc* sources, const tpgx_graph* g, uint8_t* intron, int32_t* effective_lines,
+                                             uint32_t* code, int64_t code_capacity, int64_t* nb_code_words, char* err, size_t err_len) {
+    auto say = [&](const std::string& m) { if (err && err_len) snprintf(err, err_len, "%s", m.c_str()); };
+    if (!cfg || !opcode || nb_instructions < 1 || !sources || nb_sources < 1 || !g) { say("tpgx_flatten_programs: null argument"); return TPGX_ERR_BAD_ARG; }
+    if (cfg->nb_registers < 1 || cfg->nb_registers > TPGX_MAX_REGS || cfg->nb_constants < 0 || cfg->nb_constants > TPGX_MAX_CONSTS) {
+        say("nb_registers must be in [1,8], nb_constants in [0,8]");
+        return TPGX_ERR_UNSUPPORTED;
+    }
+    for (int i = 0; i < nb_instructions; i++)
+        if (opcode[i] < 0 || opcode[i] >= TPGX_OP_COUNT) { say("instruction without a device opcode"); return TPGX_ERR_UNSUPPORTED; }
+    std::vector<int32_t> ops(opcode, opcode + nb_instructions);
+    std::vector<tpgx_source_desc> src(sources, sources + nb_sources);
+    tpgx_flat_graph f;
+    std::vector<uint8_t> keep;
+    std::string msg;
+    const tpgx_status st = tpgx_flatten_graph(*cfg, ops, src, g, &f, &msg, &keep);
+    if (st != TPGX_OK) { say(msg); return st; }
+    if (intron) for (size_t i = 0; i < keep.size(); i++) intron[i] = keep[i] ? 0 : 1;
+    if (effective_lines) for (int p = 0; p < f.nb_programs; p++) effective_lines[p] = f.prog_offset[p + 1] - f.prog_offset[p];
+    if (nb_code_words) *nb_code_words = (int64_t)f.code.size();
+    if (code) {
+        if (code_capacity < (int64_t)f.code.size()) { say("code buffer too small"); return TPGX_ERR_BAD_ARG; }
+        memcpy(code, f.code.data(), f.code.size() * 4);
+    }
     return TPGX_OK;
 }

@@ -15,7 +15,7 @@ EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_evaluate_episodes",
-    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices",
+    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
 ]
 
 _lib = None
@@ -57,6 +57,28 @@ def load_library():
 
 def _ptr(a):
     return a.ctypes.data if a is not None else None
+
+
+def flatten_programs(opcodes, sources, graph, nb_registers=8, nb_constants=0):
+    """Host flattener alone (no GPU): returns dict(intron [lines] uint8, effective_lines [P] int32, code uint32[]).
+    Raises TpgxError with the status tpgx_set_graph would return."""
+    lib = load_library()
+    lib.tpgx_flatten_programs.argtypes = [C.POINTER(A.Config), C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.POINTER(A.Graph), C.c_void_p,
+                                          C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
+    cfg = A.Config(device=0, nb_registers=nb_registers, nb_constants=nb_constants, tie_break=A.TIE_LAST_MAX)
+    ops = np.ascontiguousarray(opcodes, dtype=np.int32)
+    sd = (A.SourceDesc * len(sources))(*[A.SourceDesc(*s) for s in sources])
+    gs, keep = graph.c_struct()
+    intron = np.zeros(len(graph.lines), dtype=np.uint8)
+    eff = np.zeros(graph.nb_programs, dtype=np.int32)
+    code = np.zeros(max(1, len(graph.lines)), dtype=np.uint32)
+    n = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    st = lib.tpgx_flatten_programs(C.byref(cfg), len(ops), ops.ctypes.data, len(sources), C.cast(sd, C.c_void_p), C.byref(gs), intron.ctypes.data,
+                                   eff.ctypes.data, code.ctypes.data, len(code), C.byref(n), err, 512)
+    if st != A.OK:
+        raise TpgxError(st, err.value.decode())
+    return dict(intron=intron, effective_lines=eff, code=code[:n.value])
 
 
 def mnist_episode_indices(seed, mode, dataset_size, nb_actions):

@@ -256,6 +256,17 @@ tpgx_status tpgx_execute_programs(tpgx_ctx* ctx, int64_t count, const double* co
  * warp-instructions per second), measured on ctx's device.                                         */
 tpgx_status tpgx_measure_fp64_peak(tpgx_ctx* ctx, double* dadd_per_s, double* dfma_per_s);
 
+/* Host flattener on its own (no GPU needed): the work [UP] Program::identifyIntrons and
+ * [UP] ProgramExecutionEngine::fetchCurrentOperands do — validates the graph against the instruction table and
+ * data sources, marks introns by backward liveness from register 0 and packs the effective lines.
+ * intron : optional [total lines], 1 = intron.   effective_lines : optional [nb_programs].
+ * code / code_capacity : optional buffer for the packed 32-bit device words of all effective lines in program
+ * order (csrc/tpgx_internal.h layout); *nb_code_words receives the count (also when code is NULL).
+ * err / err_len : optional message buffer.  Returns the status tpgx_set_graph would return.                  */
+tpgx_status tpgx_flatten_programs(const tpgx_config* cfg, int32_t nb_instructions, const int32_t* opcode, int32_t nb_sources,
+                                  const tpgx_source_desc* sources, const tpgx_graph* g, uint8_t* intron, int32_t* effective_lines,
+                                  uint32_t* code, int64_t code_capacity, int64_t* nb_code_words, char* err, size_t err_len);
+
 /* The image indices one MNIST evaluation classifies, restating [REF] mnist/src/mnist.cpp:58-69 (reset:
  * rng.setSeed(seed) with the RAW seed, currentIndex = -1, changeCurrentImage) and :8-34 / :50-56 (every
  * doAction classifies the current image, then draws the next): in TRAINING (0) and VALIDATION (1) mode
