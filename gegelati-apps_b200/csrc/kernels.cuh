@@ -79,6 +79,7 @@ cudaError_t tpgx_launch_walk(const tpgx_walk_params& p, cudaStream_t st);
 
 /* Launchers (defined in kernels.cu). variant: 0 = default tile shape. Returns cudaError_t. */
 int tpgx_bid_tile_samples(int variant);
+int tpgx_bid_warps(int variant);
 size_t tpgx_bid_smem_bytes(int variant, int hw);
 cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant, bool extended_ops, bool team_mode, cudaStream_t st);
 cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p, cudaStream_t st);

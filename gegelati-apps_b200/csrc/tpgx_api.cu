@@ -323,9 +323,13 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.sobel = ctx->nwin ? ctx->d_sobel.as<double>() + (size_t)t0 * 2 * ctx->nwin * ts : nullptr;
             bp.nwin = ctx->nwin;
             bp.nb_units = nU;
-            /* enough CTAs for ~12 waves of 148 SMs (one 32-warp CTA each), at least 4 units per warp */
+            /* chunks of work units per tile: ~12 waves of 148 CTAs when there is enough work, with >= ~14 teams (or 4
+               programs) per warp for load balance; small problems trade balance for occupancy (>= 2 CTAs per SM in
+               flight if every warp can still get a unit) */
+            const int nw = tpgx_bid_warps(ctx->variant);
             int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
-            chunks = std::min(chunks, std::max(1, nU / (team_mode ? 448 : 128))); /* >= ~14 teams (or 4 programs) per warp: load balance */
+            chunks = std::min(chunks, std::max(1, nU / (team_mode ? 14 * nw : 4 * nw)));
+            if ((int64_t)nt * chunks < 2 * 148) chunks = std::max(chunks, std::min((int)((2 * 148 + nt - 1) / nt), std::max(1, nU / nw)));
             bp.units_per_chunk = (nU + chunks - 1) / chunks;
             bp.bid = ctx->d_bid.as<double>();
             bp.row_stride = (long long)nt * ts;
