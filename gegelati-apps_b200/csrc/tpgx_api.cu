@@ -546,7 +546,7 @@ static tpgx_status pack_identity(tpgx_ctx* ctx) {
     return TPGX_OK;
 }
 
-tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data, const uint8_t* labels, int64_t count) {
+static tpgx_status set_observations_host(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data, const uint8_t* labels, int64_t count, bool wait_for_copies) {
     tpgx_status st = set_obs_common(ctx, source, store, count);
     if (st != TPGX_OK) return st;
     if (!data) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_observations: null data");
@@ -563,8 +563,23 @@ tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, 
     cudaEvent_t copied = ctx->event(61);
     CU(cudaEventRecord(copied, ctx->stream));
     if ((st = pack_identity(ctx)) != TPGX_OK) return st;
-    CU(cudaEventSynchronize(copied));
+    if (wait_for_copies) CU(cudaEventSynchronize(copied));
     return TPGX_OK;
+}
+
+tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data, const uint8_t* labels, int64_t count) {
+    return set_observations_host(ctx, source, store, data, labels, count, true);
+}
+
+tpgx_status tpgx_set_observations_pinned(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data, const uint8_t* labels, int64_t count) {
+    if (ctx && data) { /* must really be page-locked: an asynchronous copy from pageable memory is staged and may read it late */
+        cudaPointerAttributes at{};
+        if (cudaPointerGetAttributes(&at, data) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+            cudaGetLastError();
+            return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_observations_pinned: data is not page-locked host memory");
+        }
+    }
+    return set_observations_host(ctx, source, store, data, labels, count, false);
 }
 
 tpgx_status tpgx_set_observations_device(tpgx_ctx* ctx, int32_t source, int32_t store, const void* d_data, const uint8_t* d_labels, int64_t count) {

@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..
 
 EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
-    "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_device",
+    "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_evaluate_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
 ]
@@ -44,6 +44,7 @@ def load_library():
     lib.tpgx_set_graph.argtypes = [C.c_void_p, C.POINTER(A.Graph)]
     lib.tpgx_set_observations.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     lib.tpgx_set_observations_device.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.tpgx_set_observations_pinned.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     lib.tpgx_evaluate_classification.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.POINTER(A.ClassifResult)]
     lib.tpgx_evaluate_classification_device.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.c_void_p, C.c_void_p]
     lib.tpgx_evaluate_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.POINTER(A.EpisodeResult)]
@@ -154,6 +155,14 @@ class Evaluator:
         lab = np.ascontiguousarray(labels, dtype=np.uint8) if labels is not None else None
         self._check(self.lib.tpgx_set_observations(self.h, 0, A.STORE_U8, img.ctypes.data, _ptr(lab), img.shape[0]))
         self.nb_obs = img.shape[0]
+
+    def set_observations_pinned(self, images_u8, labels=None):
+        """Page-locked host arrays (e.g. torch pin_memory().numpy()): copies are only enqueued; the arrays must stay alive and
+        unchanged until the next evaluate_* returns."""
+        assert images_u8.dtype == np.uint8 and images_u8.flags.c_contiguous
+        self._pinned_keepalive = (images_u8, labels)
+        self._check(self.lib.tpgx_set_observations_pinned(self.h, 0, A.STORE_U8, images_u8.ctypes.data, _ptr(labels), images_u8.shape[0]))
+        self.nb_obs = images_u8.shape[0]
 
     def set_observations_device(self, data_ptr, labels_ptr, count):
         self._check(self.lib.tpgx_set_observations_device(self.h, 0, A.STORE_U8, data_ptr, labels_ptr, count))

@@ -17,7 +17,7 @@ pin_img = torch.from_numpy(img).pin_memory().numpy()
 pin_lab = torch.from_numpy(lab).pin_memory().numpy()
 ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
 for rep in range(4):
-    t0 = time.perf_counter(); ev.set_observations(pin_img, pin_lab)
+    t0 = time.perf_counter(); ev.set_observations_pinned(pin_img, pin_lab)
     t1 = time.perf_counter(); ev.set_graph(g)
     t2 = time.perf_counter(); out = ev.evaluate_classification(want=("score", "class_f1", "device_ms"))
     t3 = time.perf_counter()

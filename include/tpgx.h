@@ -166,6 +166,11 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g);
  * re-tiles on the device.                                                                          */
 tpgx_status tpgx_set_observations(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data,
                                   const uint8_t* labels, int64_t count);
+/* Same for PAGE-LOCKED host buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory): the copies are only
+ * enqueued and the call returns at once, so the host can flatten the next graph while the observations cross
+ * PCIe.  `data` / `labels` must stay valid and unmodified until the next tpgx_evaluate_* on ctx returns.       */
+tpgx_status tpgx_set_observations_pinned(tpgx_ctx* ctx, int32_t source, int32_t store, const void* data,
+                                         const uint8_t* labels, int64_t count);
 /* Same, but `data` / `labels` are DEVICE pointers already resident in HBM (no host copy).          */
 tpgx_status tpgx_set_observations_device(tpgx_ctx* ctx, int32_t source, int32_t store,
                                          const void* d_data, const uint8_t* d_labels, int64_t count);

@@ -275,3 +275,18 @@ def test_extended_instruction_build_of_k1(oracle_mod, ops_from):
         dev = ev.evaluate_classification(want=want)
         ref = oracle_mod.Oracle(opcodes, tpgx.APP_SOURCES["mnist"], g, nb_constants=nc).evaluate_classification(img, lab, want=want)
         compare(dev, ref)
+
+
+def test_pinned_observation_upload_equals_blocking_upload(oracle_mod):
+    """tpgx_set_observations_pinned only enqueues the copies (page-locked buffers); results are unchanged, and a
+    pageable buffer is refused."""
+    import torch
+    g, ev = make(roots=10, edges=4, lines=10, depth=2, seed=4)
+    img, lab = tpgx.synthetic_images(300, seed=8)
+    pin_img, pin_lab = torch.from_numpy(img).pin_memory().numpy(), torch.from_numpy(lab).pin_memory().numpy()
+    ev.set_observations_pinned(pin_img, pin_lab)
+    want = ("score", "confusion", "action", "counters")
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+    with pytest.raises(tpgx.TpgxError) as e:
+        ev.set_observations_pinned(img.copy(), lab.copy())
+    assert e.value.status == A.ERR_BAD_ARG
