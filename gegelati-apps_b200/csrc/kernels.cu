@@ -12,6 +12,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <cub/device/device_scan.cuh>
+
 #include "dev_ops.cuh"
 #include "kernels.cuh"
 
@@ -191,6 +193,91 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk
 cudaError_t tpgx_launch_walk(const tpgx_walk_params& p, cudaStream_t st) {
     dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
     tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+/* ================================================================================================
+ * Archive reproduction ([UP] Archive::addRecording, a side effect of evaluateEdge in TRAINING mode).
+ * The reference consumes one RNG draw per executed program, in execution order; which executions are
+ * recorded is decided on the host from that stream (tpgx_api.cu).  The device provides (1) how many
+ * programs each (root, sample) walk executes and (2), for the few recorded executions, which program
+ * ran on which sample and what it bid.  Both walk the bid matrix exactly like tpgx_traverse_kernel.   */
+template <class F>
+__device__ __forceinline__ int arch_walk(const tpgx_arch_params& p, int root, int s, F&& on_exec) {
+    int visited[TPGX_MAX_PATH];
+    int depth = 0, cur = root;
+    for (;;) {
+        if (depth >= TPGX_MAX_PATH) return TPGX_DEV_PATH_TOO_LONG;
+        visited[depth++] = cur;
+        const int eb = __ldg(p.team_edge_offset + cur), ee = __ldg(p.team_edge_offset + cur + 1);
+        bool have = false;
+        int best_dst = 0;
+        double best_bid = 0.0;
+        for (int e = eb; e < ee; e++) {
+            const int dst = __ldg(p.edge_destination + e);
+            if (dst >= 0) {
+                bool seen = false;
+                for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
+                if (seen) continue;
+            }
+            const double bid = __ldg(p.bid + (size_t)__ldg(p.edge_row + e) * p.row_stride + s);
+            if (on_exec(e, bid)) return 0;
+            const bool take = !have || (p.tie_break == TPGX_TIE_LAST_MAX ? (bid >= best_bid) : (bid > best_bid));
+            if (take) { have = true; best_dst = dst; best_bid = bid; }
+        }
+        if (!have) return TPGX_DEV_NO_EDGE;
+        if (best_dst < 0) return 0;
+        cur = best_dst;
+    }
+}
+
+__global__ void tpgx_arch_count_kernel(const tpgx_arch_params p) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (s >= p.nb_samples) return;
+    unsigned long long n = 0;
+    const int err = arch_walk(p, __ldg(p.roots + r), s, [&](int, double) { n++; return false; });
+    if (err) atomicOr(p.status, err);
+    p.counts[(size_t)r * p.nb_samples + s] = n;
+}
+cudaError_t tpgx_launch_arch_count(const tpgx_arch_params& p, cudaStream_t st) {
+    dim3 grid((p.nb_samples + 127) / 128, p.nb_roots);
+    tpgx_arch_count_kernel<<<grid, 128, 0, st>>>(p);
+    return cudaGetLastError();
+}
+/* inclusive prefix of every root's row, in place (temp == NULL: size query) */
+cudaError_t tpgx_arch_scan(const tpgx_arch_params& p, void* temp, size_t* temp_bytes, cudaStream_t st) {
+    if (!temp) return cub::DeviceScan::InclusiveSum(nullptr, *temp_bytes, p.counts, p.counts, p.nb_samples, st);
+    for (int r = 0; r < p.nb_roots; r++) {
+        unsigned long long* row = p.counts + (size_t)r * p.nb_samples;
+        cudaError_t e = cub::DeviceScan::InclusiveSum(temp, *temp_bytes, row, row, p.nb_samples, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+__global__ void tpgx_arch_resolve_kernel(const tpgx_arch_params p) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= p.nb_hits) return;
+    const int r = __ldg(p.hit_root + h);
+    const unsigned long long k = p.hit_k[h];
+    const unsigned long long* prefix = p.counts + (size_t)r * p.nb_samples;
+    int lo = 0, hi = p.nb_samples - 1;            /* smallest s with prefix[s] > k */
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (prefix[mid] > k) hi = mid; else lo = mid + 1; }
+    const int s = lo;
+    unsigned long long left = k - (s > 0 ? prefix[s - 1] : 0ull);
+    int prog = -1;
+    double bid = 0.0;
+    arch_walk(p, __ldg(p.roots + r), s, [&](int e, double b) {
+        if (left == 0) { prog = __ldg(p.edge_program + e); bid = b; return true; }
+        left--;
+        return false;
+    });
+    p.out_program[h] = prog;
+    p.out_sample[h] = p.sample_obs ? (long long)__ldg(p.sample_obs + s) : (long long)s;
+    p.out_bid[h] = bid;
+}
+cudaError_t tpgx_launch_arch_resolve(const tpgx_arch_params& p, cudaStream_t st) {
+    if (p.nb_hits <= 0) return cudaSuccess;
+    tpgx_arch_resolve_kernel<<<(p.nb_hits + 127) / 128, 128, 0, st>>>(p);
     return cudaGetLastError();
 }
 

@@ -69,6 +69,32 @@ struct tpgx_walk_params {
 };
 cudaError_t tpgx_launch_walk(const tpgx_walk_params& p, cudaStream_t st);
 
+/* Archive reproduction on the bid matrix (bid mode): the reference-order stream of program executions of each job. */
+struct tpgx_arch_params {
+    const double* bid;
+    long long row_stride;
+    int nb_samples;
+    const int32_t* team_edge_offset;
+    const int32_t* edge_row;
+    const int32_t* edge_destination;
+    const int32_t* edge_program;      /* global program id of each edge                                   */
+    const int32_t* roots;             /* [nb_roots] root team ids of the batch                             */
+    int nb_roots;
+    int tie_break;
+    unsigned long long* counts;       /* [nb_roots][nb_samples] executions of (root, sample); scanned in place to an inclusive prefix */
+    const unsigned long long* hit_k;  /* [nb_hits] execution index within its job                          */
+    const int32_t* hit_root;          /* [nb_hits] root index within the batch                             */
+    int nb_hits;
+    const int32_t* sample_obs;        /* [nb_samples] observation index of each sample, or NULL = identity */
+    int32_t* out_program;
+    long long* out_sample;
+    double* out_bid;
+    int* status;
+};
+cudaError_t tpgx_launch_arch_count(const tpgx_arch_params& p, cudaStream_t st);
+cudaError_t tpgx_arch_scan(const tpgx_arch_params& p, void* temp, size_t* temp_bytes, cudaStream_t st);
+cudaError_t tpgx_launch_arch_resolve(const tpgx_arch_params& p, cudaStream_t st);
+
 #define TPGX_SOBEL_LUT_N 1021
 #define TPGX_LUT_DOUBLES (512 + 2 * TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N)
 

@@ -251,7 +251,7 @@ struct ClassifRun {
 /* Enqueues one classification evaluateAllRoots on ctx->stream; no host synchronisation.
  * records_out: device buffer of nR*(C+1) doubles. */
 tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* req, double* records_out,
-                                   bool want_action, bool keep_bid_single_pass, ClassifRun* run, bool timing) {
+                                   bool want_action, bool keep_bid_single_pass, ClassifRun* run, bool timing, bool k1_only = false) {
     if (!ctx->has_graph) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_classification: no graph set");
     if (!ctx->obs_dev) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_classification: no observations set");
     if (!req || req->nb_samples <= 0) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples must be positive");
@@ -340,6 +340,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->plan.k1_ext, team_mode, ctx->stream));
         }
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
+        if (k1_only) break; /* bid matrix of the (single) pass is all the caller wants */
         if (team_mode) {
             tpgx_walk_params wp{};
             wp.decision = ctx->d_decision.as<int32_t>();
@@ -379,7 +380,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         }
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
     }
-    CU(tpgx_launch_score(ctx->d_conf.as<unsigned long long>(), nR, C, records_out, ctx->stream));
+    if (!k1_only) CU(tpgx_launch_score(ctx->d_conf.as<unsigned long long>(), nR, C, records_out, ctx->stream));
     if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
     if (run) { run->nR = nR; run->C = C; run->ts = ts; run->nS = nS; run->nTiles = nTiles; run->passes = passes; }
     return TPGX_OK;
@@ -811,6 +812,117 @@ tpgx_status tpgx_mnist_episode_indices(uint64_t seed, int32_t mode, int64_t data
             while (low < threshold) { prod = (unsigned __int128)eng() * range; low = (uint64_t)prod; }
         }
         out[i] = (int32_t)(uint64_t)(prod >> 64);
+    }
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_archive_classification(tpgx_ctx* ctx, const tpgx_classif_request* req, const tpgx_archive_request* arch,
+                                        tpgx_archive_result* out) {
+    if (!ctx || !req || !arch || !out || !arch->archive_seed || arch->archive_size < 0 || !(arch->probability >= 0.0))
+        return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_archive_classification: bad argument");
+    if (arch->archive_size > 0 && (!out->program || !out->sample || !out->bid)) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_archive_classification: null output");
+    if (!ctx->has_graph) return fail(ctx, TPGX_ERR_STATE, "tpgx_archive_classification: no graph set");
+    cudaSetDevice(ctx->cfg.device);
+    const int R0 = req->root_begin, R1 = req->root_end, cap = arch->archive_size;
+    if (R0 < 0 || R1 > ctx->flat.nb_roots || R0 >= R1) return fail(ctx, TPGX_ERR_BAD_ARG, "root range out of bounds");
+    out->nb_records = 0;
+    if (cap == 0 || arch->probability == 0.0) {
+        /* p == 0: `0 >= draw` only for a draw of exactly 0.0 (1 in 2^64) — still honoured below unless the archive is empty by size */
+        if (cap == 0) return TPGX_OK;
+    }
+    struct Rec { int32_t program; int64_t sample; double bid; };
+    std::vector<Rec> tail;                  /* collected from the LAST job backwards; reversed at the end */
+    int remaining = cap;
+    const int BATCH = 16;
+    tpgx_status st;
+    if ((st = upload(ctx, ctx->d_scratch[7], ctx->flat.edge_program.data(), ctx->flat.edge_program.size() * 4)) != TPGX_OK) return st;
+    for (int be = R1; be > R0 && remaining > 0; be -= BATCH) {
+        const int bb = std::max(R0, be - BATCH), nb = be - bb;
+        /* bid matrix of the programs these roots reach, all samples (bid mode, K1 only) */
+        tpgx_classif_request sub = *req;
+        sub.root_begin = bb; sub.root_end = be;
+        ClassifRun run;
+        if ((st = enqueue_classification(ctx, &sub, nullptr, false, true, &run, false, true)) != TPGX_OK) return st;
+        const int nS = (int)run.nS;
+        tpgx_arch_params ap{};
+        ap.bid = ctx->d_bid.as<double>();
+        ap.row_stride = (long long)run.nTiles * run.ts;
+        ap.nb_samples = nS;
+        ap.team_edge_offset = ctx->d_team_off.as<int32_t>();
+        ap.edge_row = ctx->d_edge_row.as<int32_t>();
+        ap.edge_destination = ctx->d_edge_dst.as<int32_t>();
+        ap.edge_program = ctx->d_scratch[7].as<int32_t>();
+        ap.roots = ctx->d_roots.as<int32_t>();
+        ap.nb_roots = nb;
+        ap.tie_break = ctx->cfg.tie_break;
+        ap.sample_obs = req->sample_index ? ctx->d_index.as<int32_t>() : nullptr;
+        ap.status = ctx->d_status.as<int>();
+        CU(ctx->d_scratch[3].ensure((size_t)nb * nS * 8));
+        ap.counts = ctx->d_scratch[3].as<unsigned long long>();
+        CU(tpgx_launch_arch_count(ap, ctx->stream));
+        size_t temp_bytes = 0;
+        CU(tpgx_arch_scan(ap, nullptr, &temp_bytes, ctx->stream));
+        CU(ctx->d_scratch[4].ensure(temp_bytes + 16));
+        CU(tpgx_arch_scan(ap, ctx->d_scratch[4].p, &temp_bytes, ctx->stream));
+        std::vector<unsigned long long> totals(nb);
+        for (int r = 0; r < nb; r++)
+            CU(cudaMemcpyAsync(&totals[r], ap.counts + (size_t)r * nS + (nS - 1), 8, cudaMemcpyDeviceToHost, ctx->stream));
+        int status = 0;
+        CU(cudaMemcpyAsync(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
+        /* the jobs of the batch, last first: replay the job's draw stream, keep its last recordings that still fit */
+        std::vector<unsigned long long> hit_k;
+        std::vector<int32_t> hit_root;
+        for (int r = nb - 1; r >= 0 && remaining > 0; r--) {
+            const unsigned long long N = totals[r];
+            std::vector<unsigned long long> hits;
+            if (arch->probability == 1.0) {
+                const unsigned long long take = std::min<unsigned long long>(N, (unsigned long long)remaining);
+                for (unsigned long long k = N - take; k < N; k++) hits.push_back(k);
+            } else {
+                std::mt19937_64 eng(arch->archive_seed[bb + r - R0]);
+                for (unsigned long long k = 0; k < N; k++) {
+                    double canon = (double)eng() / 18446744073709551616.0;     /* libstdc++ uniform_real_distribution<double>(0, 1) */
+                    if (canon >= 1.0) canon = 0.99999999999999988898;
+                    if (arch->probability >= canon) hits.push_back(k);
+                }
+                const size_t keep = std::min<size_t>(hits.size(), (size_t)std::min(remaining, cap));
+                hits.erase(hits.begin(), hits.end() - keep);
+            }
+            remaining -= (int)hits.size();
+            /* batch hit list is assembled job-descending; inside a job ascending */
+            hit_k.insert(hit_k.begin(), hits.begin(), hits.end());
+            hit_root.insert(hit_root.begin(), hits.size(), r);
+        }
+        const int nh = (int)hit_k.size();
+        if (nh > 0) {
+            if ((st = upload(ctx, ctx->d_scratch[5], hit_k.data(), (size_t)nh * 8)) != TPGX_OK) return st;
+            if ((st = upload(ctx, ctx->d_scratch[6], hit_root.data(), (size_t)nh * 4)) != TPGX_OK) return st;
+            CU(ctx->d_scratch[0].ensure((size_t)nh * 4));
+            CU(ctx->d_scratch[1].ensure((size_t)nh * 8));
+            CU(ctx->d_scratch[2].ensure((size_t)nh * 8));
+            ap.hit_k = ctx->d_scratch[5].as<unsigned long long>();
+            ap.hit_root = ctx->d_scratch[6].as<int32_t>();
+            ap.nb_hits = nh;
+            ap.out_program = ctx->d_scratch[0].as<int32_t>();
+            ap.out_sample = ctx->d_scratch[1].as<long long>();
+            ap.out_bid = ctx->d_scratch[2].as<double>();
+            CU(tpgx_launch_arch_resolve(ap, ctx->stream));
+            std::vector<int32_t> hp(nh);
+            std::vector<long long> hs(nh);
+            std::vector<double> hb(nh);
+            CU(cudaMemcpyAsync(hp.data(), ap.out_program, (size_t)nh * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(hs.data(), ap.out_sample, (size_t)nh * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(hb.data(), ap.out_bid, (size_t)nh * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            for (int i = nh - 1; i >= 0; i--) tail.push_back(Rec{hp[i], (int64_t)hs[i], hb[i]});   /* newest first */
+        }
+    }
+    out->nb_records = (int32_t)tail.size();
+    for (size_t i = 0; i < tail.size(); i++) {
+        const Rec& rc = tail[tail.size() - 1 - i];
+        out->program[i] = rc.program; out->sample[i] = rc.sample; out->bid[i] = rc.bid;
     }
     return TPGX_OK;
 }

@@ -68,6 +68,14 @@ class ClassifResult(C.Structure):
                 ("bid", C.c_void_p), ("counters", C.POINTER(Counters)), ("device_ms", C.c_void_p)]
 
 
+class ArchiveRequest(C.Structure):
+    _fields_ = [("archive_seed", C.c_void_p), ("probability", C.c_double), ("archive_size", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ArchiveResult(C.Structure):
+    _fields_ = [("program", C.c_void_p), ("sample", C.c_void_p), ("bid", C.c_void_p), ("nb_records", C.c_int32), ("reserved", C.c_int32)]
+
+
 class EpisodeRequest(C.Structure):
     _fields_ = [("env", C.c_int32), ("mode", C.c_int32), ("nb_iterations", C.c_int32), ("max_actions", C.c_int32),
                 ("seeds", C.c_void_p), ("nb_jobs", C.c_int32), ("roots_per_job", C.c_int32), ("job_roots", C.c_void_p),

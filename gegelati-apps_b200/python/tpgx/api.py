@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..
 EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
-    "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_evaluate_episodes",
+    "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
 ]
 
@@ -47,6 +47,7 @@ def load_library():
     lib.tpgx_set_observations_pinned.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64]
     lib.tpgx_evaluate_classification.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.POINTER(A.ClassifResult)]
     lib.tpgx_evaluate_classification_device.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.c_void_p, C.c_void_p]
+    lib.tpgx_archive_classification.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.POINTER(A.ArchiveRequest), C.POINTER(A.ArchiveResult)]
     lib.tpgx_evaluate_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.POINTER(A.EpisodeResult)]
     lib.tpgx_execute_programs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.tpgx_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
@@ -194,6 +195,21 @@ class Evaluator:
         root_end = self.graph.nb_roots if root_end is None else root_end
         req = A.ClassifRequest(nb_samples=int(nb_samples), sample_index=None, nb_classes=nb_classes, root_begin=root_begin, root_end=root_end)
         self._check(self.lib.tpgx_evaluate_classification_device(self.h, C.byref(req), records_ptr, stream_ptr))
+
+    def archive_classification(self, archive_seeds, probability, archive_size, nb_samples=None, sample_index=None, root_begin=0, root_end=None):
+        """Archive left by a TRAINING evaluateAllRoots ([UP] Archive::addRecording): dict(program, sample, bid) in archive order."""
+        root_end = self.graph.nb_roots if root_end is None else root_end
+        idx = np.ascontiguousarray(sample_index, dtype=np.int32) if sample_index is not None else None
+        nS = int(nb_samples if nb_samples is not None else (len(idx) if idx is not None else self.nb_obs))
+        req = A.ClassifRequest(nb_samples=nS, sample_index=_ptr(idx), nb_classes=10, root_begin=root_begin, root_end=root_end)
+        seeds = np.ascontiguousarray(archive_seeds, dtype=np.uint64)
+        assert len(seeds) == root_end - root_begin
+        prog = np.zeros(max(1, archive_size), dtype=np.int32); samp = np.zeros(max(1, archive_size), dtype=np.int64); bid = np.zeros(max(1, archive_size))
+        ar = A.ArchiveRequest(archive_seed=seeds.ctypes.data, probability=float(probability), archive_size=int(archive_size))
+        res = A.ArchiveResult(program=prog.ctypes.data, sample=samp.ctypes.data, bid=bid.ctypes.data)
+        self._check(self.lib.tpgx_archive_classification(self.h, C.byref(req), C.byref(ar), C.byref(res)))
+        n = res.nb_records
+        return dict(program=prog[:n], sample=samp[:n], bid=bid[:n])
 
     def execute_programs(self, count, obs):
         """obs: list per data source of arrays [count, space] (float64 or int32). Returns bid [P, count]."""

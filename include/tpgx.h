@@ -209,6 +209,30 @@ tpgx_status tpgx_evaluate_classification(tpgx_ctx* ctx, const tpgx_classif_reque
 tpgx_status tpgx_evaluate_classification_device(tpgx_ctx* ctx, const tpgx_classif_request* req,
                                                 double* d_records, void* stream);
 
+/* Archive side effect of a TRAINING evaluateAllRoots ([UP] Archive::addRecording, called by evaluateEdge for every executed
+ * program; archiveSize / archivingProbability: [REF] mnist/params.json:4,7).  Restated semantics:
+ * every job j evaluates its root with a private Archive seeded with archive_seed[j]; an execution is recorded iff
+ * `probability == 1.0 || probability >= rng.getDouble(0, 1)` (one draw per executed program, in execution order); a job keeps
+ * its last archive_size recordings; the per-job archives are concatenated in job order and the LAST archive_size kept.
+ * Output: records in final archive order as (program id, observation index — standing for the data-source hash —, bid).
+ * The device supplies the per-(root, sample) execution counts and resolves the recorded executions; the RNG stream is
+ * generated on the host (mt19937_64, as [UP] Mutator::RNG).  Only the jobs whose recordings survive the merge are evaluated. */
+typedef struct {
+    const uint64_t* archive_seed;  /* [root_end - root_begin] Job::archiveSeed of each root's job                     */
+    double probability;            /* archivingProbability                                                             */
+    int32_t archive_size;          /* archiveSize                                                                      */
+    int32_t reserved;
+} tpgx_archive_request;
+typedef struct {
+    int32_t* program;              /* [archive_size] */
+    int64_t* sample;               /* [archive_size] */
+    double* bid;                   /* [archive_size] */
+    int32_t nb_records;            /* out */
+    int32_t reserved;
+} tpgx_archive_result;
+tpgx_status tpgx_archive_classification(tpgx_ctx* ctx, const tpgx_classif_request* req, const tpgx_archive_request* arch,
+                                        tpgx_archive_result* out);
+
 /* ---- episodic environments ----------------------------------------------------------------------
  * Batched lock-step restatements of the apps' LearningEnvironment::{reset,doAction,isTerminal,
  * getScore(s)}.                                                             */

@@ -34,6 +34,8 @@ def load():
     lib.orc_effective_lines.argtypes = [C.c_void_p, C.c_void_p]
     lib.orc_execute_programs.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.orc_evaluate_classification.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(A.ClassifRequest), C.POINTER(A.ClassifResult), C.c_int32]
+    lib.orc_archive_classification.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(A.ClassifRequest), C.c_void_p, C.c_double, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     lib.orc_evaluate_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.POINTER(A.EpisodeResult), C.c_int32]
     lib.orc_apply_op.restype = C.c_double
     lib.orc_apply_op.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_void_p]
@@ -124,6 +126,22 @@ class Oracle:
             raise RuntimeError("oracle classification failed: %d" % st)
         out["counters"] = cnt.as_dict()
         return out
+
+    def archive_classification(self, images, archive_seeds, probability, archive_size, nb_samples=None, sample_index=None,
+                               root_begin=0, root_end=None):
+        img = np.ascontiguousarray(images, dtype=np.uint8)
+        root_end = self.graph.nb_roots if root_end is None else root_end
+        idx = np.ascontiguousarray(sample_index, dtype=np.int32) if sample_index is not None else None
+        nS = int(nb_samples if nb_samples is not None else (len(idx) if idx is not None else img.shape[0]))
+        req = A.ClassifRequest(nb_samples=nS, sample_index=_ptr(idx), nb_classes=10, root_begin=root_begin, root_end=root_end)
+        seeds = np.ascontiguousarray(archive_seeds, dtype=np.uint64)
+        prog = np.zeros(archive_size, dtype=np.int32); samp = np.zeros(archive_size, dtype=np.int64); bid = np.zeros(archive_size)
+        n = C.c_int32(0)
+        st = self.lib.orc_archive_classification(self.h, img.ctypes.data, img.shape[0], C.byref(req), seeds.ctypes.data, float(probability),
+                                                 int(archive_size), prog.ctypes.data, samp.ctypes.data, bid.ctypes.data, C.byref(n))
+        if st != 0:
+            raise RuntimeError("oracle status %d" % st)
+        return dict(program=prog[:n.value], sample=samp[:n.value], bid=bid[:n.value])
 
     def evaluate_episodes(self, env, seeds, job_roots, max_actions, mode=A.MODE_TRAINING, roots_per_job=1,
                           second_player_random=0, pendulum_actions=None, trace_steps=0, nb_threads=1):

@@ -22,6 +22,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <limits>
 #include <memory>
 #include <mutex>
@@ -135,7 +136,26 @@ struct SourceView {
     double get_d(size_t i) const { return f64 ? f64[i] : (double)u8[i]; }
 };
 
+/* [UP] Archive (App. F U12): one per job in TRAINING evaluation.  addRecording is called by evaluateEdge for every
+ * executed program; it records with probability p — `p == 1.0 || p >= rng.getDouble(0, 1)`, so no draw is consumed
+ * when p is 1 — and keeps at most max_size recordings (oldest dropped). */
+struct ArchiveRec { int32_t program; int64_t sample; double bid; };
+struct ArchiveRecorder {
+    std::mt19937_64 eng;
+    double p = 0.0;
+    size_t max_size = 0;
+    int64_t sample = -1;                 /* stands for the hash of the data sources: which observation is current */
+    std::deque<ArchiveRec> recs;
+    void add(int32_t program, double bid) {
+        if (p == 1.0 || p >= std::uniform_real_distribution<double>(0.0, 1.0)(eng)) {
+            recs.push_back({program, sample, bid});
+            while (recs.size() > max_size) recs.pop_front();
+        }
+    }
+};
+
 struct Counters {
+    ArchiveRecorder* archive = nullptr;
     uint64_t evaluations = 0, team_visits = 0, program_executions = 0, lines_executed = 0;
     void add(const Counters& o) {
         evaluations += o.evaluations; team_visits += o.team_visits;
@@ -238,6 +258,7 @@ struct orc_engine {
     double evaluate_edge(int edge, const SourceView* obs, Counters* cnt) const {
         double r = execute_program(programs[edge_program[edge]], obs, cnt);
         if (std::isnan(r)) r = -std::numeric_limits<double>::infinity();
+        if (cnt && cnt->archive) cnt->archive->add(edge_program[edge], r);   /* [UP] archive->addRecording(&prog, dataSources, r) */
         return r;
     }
 
@@ -788,6 +809,41 @@ double orc_apply_op(int32_t opcode, int32_t math_flavour, double a, double b, in
 void orc_math_array(int32_t fn, int32_t math_flavour, int64_t n, const double* in, double* out) {
     Math m{math_flavour};
     for (int64_t i = 0; i < n; i++) out[i] = apply_op(fn, m, in[i], 0.0, 0, 0, 0.0, nullptr);
+}
+
+/* [UP] ParallelLearningAgent::evaluateAllRoots in TRAINING mode, archive side effect only: every job evaluates its root
+ * with a private Archive(archive_size, probability) seeded with the job's archiveSeed; mergeArchiveMap then keeps the
+ * LAST archive_size recordings of the per-job archives concatenated in job-index order (App. F U12). */
+int32_t orc_archive_classification(const orc_engine* e, const uint8_t* images, int64_t n_images, const tpgx_classif_request* req,
+                                   const uint64_t* archive_seed, double probability, int32_t archive_size,
+                                   int32_t* out_program, int64_t* out_sample, double* out_bid, int32_t* nb_records) {
+    if (e->src.size() != 1 || archive_size < 0) return TPGX_ERR_BAD_ARG;
+    const size_t px = (size_t)e->src[0].height * e->src[0].width;
+    const int nR = req->root_end - req->root_begin;
+    std::deque<ArchiveRec> merged;
+    std::vector<int> visited;
+    for (int j = 0; j < nR; j++) {
+        ArchiveRecorder ar;
+        ar.eng.seed(archive_seed[j]);
+        ar.p = probability;
+        ar.max_size = (size_t)archive_size;
+        Counters cnt;
+        cnt.archive = &ar;
+        const int root = e->root_team[req->root_begin + j];
+        for (int64_t s = 0; s < req->nb_samples; s++) {
+            const int64_t idx = req->sample_index ? req->sample_index[s] : s;
+            if (idx < 0 || idx >= n_images) return TPGX_ERR_BAD_ARG;
+            SourceView v;
+            v.u8 = images + (size_t)idx * px;
+            ar.sample = idx;
+            if (e->execute_from_root(root, &v, &cnt, visited) < 0) return TPGX_ERR_GRAPH_INVALID;
+        }
+        for (const ArchiveRec& r : ar.recs) merged.push_back(r);
+        while (merged.size() > (size_t)archive_size) merged.pop_front();
+    }
+    *nb_records = (int32_t)merged.size();
+    for (size_t i = 0; i < merged.size(); i++) { out_program[i] = merged[i].program; out_sample[i] = merged[i].sample; out_bid[i] = merged[i].bid; }
+    return 0;
 }
 
 /* Host build of the primitives tpgx_math_probe runs on the device (same fn codes, include/tpgx.h). */

@@ -51,6 +51,12 @@ int32_t orc_evaluate_classification(const orc_engine* e, const uint8_t* images,
                                     const tpgx_classif_request* req, tpgx_classif_result* out,
                                     int32_t nb_threads);
 
+/* Archive side effect of a TRAINING evaluateAllRoots ([UP] Archive::addRecording via evaluateEdge, per-job archives merged
+ * in job order): the final <= archive_size recordings as (program id, observation index, bid). */
+int32_t orc_archive_classification(const orc_engine* e, const uint8_t* images, int64_t n_images, const tpgx_classif_request* req,
+                                   const uint64_t* archive_seed, double probability, int32_t archive_size,
+                                   int32_t* out_program, int64_t* out_sample, double* out_bid, int32_t* nb_records);
+
 /* Episodic evaluateAllRoots ([UP] LearningAgent::evaluateJob / AdversarialLearningAgent). */
 int32_t orc_evaluate_episodes(const orc_engine* e, const tpgx_episode_request* req,
                               tpgx_episode_result* out, int32_t nb_threads);
