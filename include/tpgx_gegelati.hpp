@@ -248,5 +248,85 @@ class LearningAgent {
     }
 };
 
+/* Classification (MNIST-shaped) agent: mirrors Learn::ClassificationLearningAgent<ParallelLearningAgent>
+ * ([REF] mnist/src/main.cpp:106).  The environment keeps its dataset private ([REF] mnist/src/mnist.h:16), so the two image
+ * sets are handed over once (converted to uint8: pixels are the integers 0..255 stored as double).  evaluateAllRoots restates
+ * [UP] ClassificationLearningAgent::evaluateJob with nbIterationsPerPolicyEvaluation = 1 ([REF] mnist/params.json:97): the
+ * images are those MNIST::reset / doAction would draw for seed Hash(generation) ^ Hash(0) (tpgx_mnist_episode_indices). */
+class ClassificationAgent {
+    Learn::LearningParameters params;
+    Environment env;
+    std::shared_ptr<TPG::TPGGraph> tpg;
+    tpgx_ctx* ctx = nullptr;
+    int64_t nbTrain = 0, nbTest = 0;
+    int nbClasses;
+
+  public:
+    ClassificationAgent(Learn::ClassificationLearningEnvironment& le, const Instructions::Set& set, const Learn::LearningParameters& p,
+                        const std::vector<std::vector<double>>& trainImages, const std::vector<uint8_t>& trainLabels,
+                        const std::vector<std::vector<double>>& testImages, const std::vector<uint8_t>& testLabels, int tieBreak = TPGX_TIE_LAST_MAX)
+        : params(p), env(set, le.getDataSources(), p.nbRegisters, p.nbProgramConstant), tpg(std::make_shared<TPG::TPGGraph>(env)),
+          nbTrain((int64_t)trainImages.size()), nbTest((int64_t)testImages.size()), nbClasses((int)le.getNbActions()) {
+        tpgx_config cfg{};
+        cfg.device = 0; cfg.nb_registers = (int32_t)p.nbRegisters; cfg.nb_constants = (int32_t)p.nbProgramConstant; cfg.tie_break = tieBreak;
+        check(nullptr, tpgx_create(&cfg, &ctx), "tpgx_create");
+        const std::vector<int32_t> ops = fingerprint(set);
+        check(ctx, tpgx_set_instruction_table(ctx, (int32_t)ops.size(), ops.data()), "tpgx_set_instruction_table");
+        /* the 2-D source's shape from its public address spaces: h*w scalars, (h-2)*(w-2) 3x3 windows (square image) */
+        const Data::DataHandler& dh = le.getDataSources().at(0).get();
+        const size_t A_ = dh.getAddressSpace(typeid(double)), B_ = dh.getAddressSpace(typeid(const double[3][3]));
+        const size_t sum = (A_ - B_ + 4) / 2;                       /* h + w */
+        const size_t side = sum / 2;
+        if (side * side != A_ || (side - 2) * (side - 2) != B_) throw std::runtime_error("tpgx::ClassificationAgent: a square 2-D double source is expected");
+        tpgx_source_desc src{TPGX_ELEM_F64, (int32_t)side, (int32_t)side, 1};
+        check(ctx, tpgx_set_data_sources(ctx, 1, &src), "tpgx_set_data_sources");
+        std::vector<uint8_t> img((size_t)(nbTrain + nbTest) * A_), lab((size_t)(nbTrain + nbTest));
+        auto put = [&](const std::vector<std::vector<double>>& images, const std::vector<uint8_t>& labels, size_t at) {
+            for (size_t i = 0; i < images.size(); i++) {
+                for (size_t k = 0; k < A_; k++) {
+                    const double v = images[i].at(k);
+                    if (!(v >= 0.0 && v <= 255.0) || v != std::floor(v)) throw std::runtime_error("tpgx::ClassificationAgent: pixel is not an integer in [0, 255]");
+                    img[(at + i) * A_ + k] = (uint8_t)v;
+                }
+                lab[at + i] = labels.at(i);
+            }
+        };
+        put(trainImages, trainLabels, 0);
+        put(testImages, testLabels, (size_t)nbTrain);
+        check(ctx, tpgx_set_observations(ctx, 0, TPGX_STORE_U8, img.data(), lab.data(), nbTrain + nbTest), "tpgx_set_observations");
+    }
+    ClassificationAgent(const ClassificationAgent&) = delete;
+    ~ClassificationAgent() { tpgx_destroy(ctx); }
+    std::shared_ptr<TPG::TPGGraph> getTPGGraph() { return tpg; }
+
+    std::multimap<std::shared_ptr<Learn::EvaluationResult>, const TPG::TPGVertex*> evaluateAllRoots(uint64_t generationNumber, Learn::LearningMode mode) {
+        const FlatGraph f = flatten(*tpg);
+        const tpgx_graph g = f.view();
+        check(ctx, tpgx_set_graph(ctx, &g), "tpgx_set_graph");
+        const bool training = mode == Learn::LearningMode::TRAINING;
+        const int64_t size = training ? nbTrain : nbTest, n = (int64_t)params.maxNbActionsPerEval;
+        std::vector<int32_t> idx((size_t)n);
+        const uint64_t seed = Data::Hash<uint64_t>()(generationNumber) ^ Data::Hash<uint64_t>()((uint64_t)0);
+        if (tpgx_mnist_episode_indices(seed, (int32_t)mode, size, n, idx.data()) != TPGX_OK) throw std::runtime_error("tpgx_mnist_episode_indices");
+        if (!training) for (int32_t& i : idx) i += (int32_t)nbTrain;       /* the test set follows the training set on the device */
+        const int R = (int)f.roots.size(), C = nbClasses;
+        tpgx_classif_request rq{n, idx.data(), C, 0, R, 0};
+        std::vector<double> f1((size_t)R * C);
+        std::vector<uint64_t> conf((size_t)R * C * C);
+        tpgx_classif_result out{};
+        out.class_f1 = f1.data();
+        out.confusion = conf.data();
+        check(ctx, tpgx_evaluate_classification(ctx, &rq, &out), "tpgx_evaluate_classification");
+        std::multimap<std::shared_ptr<Learn::EvaluationResult>, const TPG::TPGVertex*> results;
+        for (int r = 0; r < R; r++) {
+            std::vector<size_t> perClass(C, 0);
+            for (int c = 0; c < C; c++) for (int k = 0; k < C; k++) perClass[c] += (size_t)conf[((size_t)r * C + c) * C + k];
+            results.emplace(std::make_shared<Learn::ClassificationEvaluationResult>(std::vector<double>(f1.begin() + (size_t)r * C, f1.begin() + (size_t)(r + 1) * C), perClass),
+                            f.roots[r]);
+        }
+        return results;
+    }
+};
+
 } // namespace tpgx
 #endif

@@ -40,6 +40,22 @@ obj gridworld_ins  "$REF/gridworld/src/instructions.cpp" -DfillInstructionSet=gr
 obj stickgame_env  "$REF/stickgame/src/Learn/stickGameAdversarial.cpp"
 obj stickgame_ins  "$REF/stickgame/src/Learn/instructions.cpp" -DfillInstructionSet=stickgame_fillInstructionSet
 obj tictactoe_env  "$REF/tic-tac-toe/src/Learn/TicTacToe.cpp"
+# MNIST environment: its dataset is loaded at static-initialisation time from MNIST_DATA_LOCATION (IDX files, read by the
+# reference's own mnist_reader).  No dataset ships with the reference, so a small synthetic one (3000 + 1000 MNIST-shaped
+# images from tpgx.synthetic_images, fixed seeds) is generated next to the binary.
+DATA="$OUT/mnist_data"
+mkdir -p "$DATA"
+python3 - "$DATA" "$HERE/.." <<'PY'
+import os, struct, sys
+sys.path.insert(0, os.path.join(sys.argv[2], "gegelati-apps_b200", "python"))
+from tpgx.graph import synthetic_images
+d = sys.argv[1]
+for name, n, seed in (("train", 3000, 101), ("t10k", 1000, 202)):
+    img, lab = synthetic_images(n, seed=seed, label_seed=seed + 1)
+    open(os.path.join(d, "%s-images-idx3-ubyte" % name), "wb").write(struct.pack(">BBBBIII", 0, 0, 8, 3, n, 28, 28) + img.tobytes())
+    open(os.path.join(d, "%s-labels-idx1-ubyte" % name), "wb").write(struct.pack(">BBBBI", 0, 0, 8, 1, n) + lab.tobytes())
+PY
+obj mnist_env      "$REF/mnist/src/mnist.cpp" -DMNIST_DATA_LOCATION="\"/root/repo/oracle/_ref/mnist_data\""
 obj wrap           "$HERE/ref_wrap.cpp"
 "$CXX" -shared -o "$OUT/libtpgref.so" "$OUT"/*.o
 rm -f "$OUT/wrap.o"

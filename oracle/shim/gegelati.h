@@ -28,6 +28,7 @@
 #include <list>
 #include <map>
 #include <memory>
+#include <numeric>
 #include <random>
 #include <sstream>
 #include <stdexcept>
@@ -90,6 +91,31 @@ template <class T> class PrimitiveTypeArray : public DataHandler {
     }
     void resetData() { for (T& v : data) v = T(); }
     const T* raw() const { return data.data(); } /* shim-only accessor for the wrapper */
+};
+
+/* 2-D view on a caller-owned vector ([REF] mnist/src/mnist.h:25, mnist.cpp:27): provides T (h*w addresses) and
+ * T[3][3] windows ((h-2)*(w-2) addresses, address -> row a / (w-2), col a % (w-2)) */
+template <class T> class Array2DWrapper : public DataHandler {
+    size_t height, width;
+    const std::vector<T>* pointer = nullptr;
+  public:
+    Array2DWrapper(size_t h, size_t w) : height(h), width(w) {}
+    void setPointer(const std::vector<T>* p) { pointer = p; }
+    size_t getAddressSpace(const std::type_info& type) const override {
+        if (type == typeid(T)) return height * width;
+        if (type == typeid(const T[3][3]) || type == typeid(T[3][3])) return (height - 2) * (width - 2);
+        return 0;
+    }
+    size_t getLargestAddressSpace() const override { return height * width; }
+    UntypedSharedPtr getDataAt(const std::type_info& type, size_t address) const override {
+        if (!pointer) throw std::runtime_error("Array2DWrapper: null pointer");
+        if (type == typeid(T)) return UntypedSharedPtr(std::shared_ptr<const T>(std::shared_ptr<const T>(), &pointer->at(address)));
+        if (getAddressSpace(type) == 0 || address >= getAddressSpace(type)) throw std::invalid_argument("Array2DWrapper::getDataAt");
+        const size_t r0 = address / (width - 2), c0 = address % (width - 2);
+        std::shared_ptr<T> w(new T[9], std::default_delete<T[]>());
+        for (size_t r = 0; r < 3; r++) for (size_t c = 0; c < 3; c++) w.get()[r * 3 + c] = pointer->at((r0 + r) * width + c0 + c);
+        return UntypedSharedPtr(std::shared_ptr<const T>(w, w.get()));
+    }
 };
 
 } // namespace Data
@@ -277,6 +303,18 @@ class TPGGraph {
     void clearProgramIntrons() {}
 };
 } // namespace TPG
+class Archive;
+namespace TPG {
+/* Declared so that code holding a CPU engine compiles ([REF] mnist/src/mnist.cpp:104-124); the shim has no CPU engine —
+ * the repository's CPU restatement is oracle/tpg_oracle.cpp — so executing it is an error. */
+class TPGExecutionEngine {
+  public:
+    TPGExecutionEngine(const Environment&, Archive* = nullptr) {}
+    std::pair<std::vector<const TPGVertex*>, std::vector<size_t>> executeFromRoot(const TPGVertex&) {
+        throw std::runtime_error("shim TPGExecutionEngine: no CPU engine behind this stand-in");
+    }
+};
+} // namespace TPG
 
 namespace File {
 /* Reader of the TPGGraphDotExporter layout, enough for the reference's golden graphs. */
@@ -387,6 +425,45 @@ class EvaluationResult {
     virtual ~EvaluationResult() = default;
     virtual double getResult() const { return result; }
     virtual size_t getNbEvaluation() const { return nbEvaluation; }
+};
+
+class ClassificationLearningEnvironment : public LearningEnvironment {   /* [UP]; App. F U11 */
+  protected:
+    std::vector<std::vector<uint64_t>> classificationTable;
+    uint64_t currentClass = 0;
+  public:
+    ClassificationLearningEnvironment(uint64_t nbClass) : LearningEnvironment(nbClass), classificationTable(nbClass, std::vector<uint64_t>(nbClass, 0)) {}
+    void doAction(double actionID) override {
+        LearningEnvironment::doAction(actionID);
+        classificationTable.at(currentClass).at((uint64_t)actionID)++;
+    }
+    const std::vector<std::vector<uint64_t>>& getClassificationTable() const { return classificationTable; }
+    void reset(size_t = 0, LearningMode = LearningMode::TRAINING, uint16_t = 0, uint64_t = 0) override {
+        for (auto& row : classificationTable) std::fill(row.begin(), row.end(), 0);
+    }
+    double getScore() const override {
+        double sum = 0.0;
+        const size_t C = classificationTable.size();
+        for (size_t c = 0; c < C; c++) {
+            uint64_t tp = classificationTable[c][c], fn = 0, fp = 0;
+            for (size_t k = 0; k < C; k++) { if (k != c) { fn += classificationTable[c][k]; fp += classificationTable[k][c]; } }
+            const double recall = (double)tp / (double)(tp + fn), precision = (double)tp / (double)(tp + fp);
+            sum += (tp != 0) ? 2 * (precision * recall) / (precision + recall) : 0.0;
+        }
+        return sum / (double)C;
+    }
+};
+
+class ClassificationEvaluationResult : public EvaluationResult {
+    std::vector<double> scorePerClass;
+    std::vector<size_t> nbEvaluationPerClass;
+  public:
+    ClassificationEvaluationResult(const std::vector<double>& scores, const std::vector<size_t>& nbEval)
+        : EvaluationResult(scores.empty() ? 0.0 : std::accumulate(scores.begin(), scores.end(), 0.0) / (double)scores.size(),
+                           std::accumulate(nbEval.begin(), nbEval.end(), (size_t)0)),
+          scorePerClass(scores), nbEvaluationPerClass(nbEval) {}
+    const std::vector<double>& getScorePerClass() const { return scorePerClass; }
+    const std::vector<size_t>& getNbEvaluationPerClass() const { return nbEvaluationPerClass; }
 };
 
 struct LearningParameters {   /* the fields evaluation reads (the apps' params.json files) */

@@ -21,6 +21,7 @@
 #include "gridworld/src/gridworld.h"
 #include "stickgame/src/Learn/stickGameAdversarial.h"
 #include "tic-tac-toe/src/Learn/TicTacToe.h"
+#include "mnist/src/mnist.h"
 #include "tpgx_gegelati.hpp"
 
 void pendulum_fillInstructionSet(Instructions::Set& set);
@@ -28,6 +29,35 @@ void gridworld_fillInstructionSet(Instructions::Set& set);
 void stickgame_fillInstructionSet(Instructions::Set& set);
 static void tictactoe_fillInstructionSet(Instructions::Set& set) {
 #include "gen/tictactoe_set.inc"
+}
+static void mnist_fillInstructionSet(Instructions::Set& set) {   /* [REF] mnist/src/main.cpp:47-88, sliced at build time */
+#include "gen/mnist_set.inc"
+}
+/* the reference keeps its dataset protected: a subclass hands it to the adapter */
+struct MNISTOpen : MNIST {
+    static const mnist::MNIST_dataset<std::vector, std::vector<double>, uint8_t>& data() { return dataset; }
+};
+
+static int run_mnist(const char* dot, uint64_t generation, Learn::LearningMode mode, Learn::LearningParameters params) {
+    Instructions::Set set;
+    mnist_fillInstructionSet(set);
+    MNISTOpen le;                                      /* [REF] mnist/src/main.cpp:101 */
+    params.nbProgramConstant = 5;                      /* [REF] mnist/params.json:100 */
+    const auto& ds = MNISTOpen::data();
+    tpgx::ClassificationAgent la(le, set, params, ds.training_images, ds.training_labels, ds.test_images, ds.test_labels);
+    Environment env(set, le.getDataSources(), params.nbRegisters, params.nbProgramConstant);
+    File::TPGGraphDotImporter importer(dot, env, *la.getTPGGraph());
+    importer.importGraph();
+    auto results = la.evaluateAllRoots(generation, mode);
+    for (const TPG::TPGVertex* r : la.getTPGGraph()->getRootVertices())
+        for (const auto& kv : results)
+            if (kv.second == r) {
+                auto cr = std::dynamic_pointer_cast<Learn::ClassificationEvaluationResult>(kv.first);
+                printf("%a %zu", cr->getResult(), cr->getNbEvaluation());
+                for (double f : cr->getScorePerClass()) printf(" %a", f);
+                printf("\n");
+            }
+    return 0;
 }
 
 int main(int argc, char** argv) {
@@ -41,6 +71,7 @@ int main(int argc, char** argv) {
     params.maxNbActionsPerEval = strtoull(argv[6], nullptr, 10);
     const bool secondRandom = argc > 7 && atoi(argv[7]) != 0;
     try {
+        if (app == "mnist") return run_mnist(argv[2], generation, mode, params);
         Instructions::Set set;
         std::unique_ptr<Learn::LearningEnvironment> le;
         tpgx_env_kind kind;

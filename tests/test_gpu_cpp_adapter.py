@@ -50,3 +50,33 @@ def test_errors_surface_as_exceptions_like_the_reference():
     """A missing graph file is reported through std::runtime_error -> exit code 1 and a message, not a crash."""
     out = subprocess.run([DRIVER, "pendulum", "/nonexistent.dot", "0", "0", "1", "10"], capture_output=True, text=True, timeout=60)
     assert out.returncode == 1 and "cannot open" in out.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/adapter_driver not built")
+@pytest.mark.parametrize("mode", [A.MODE_TRAINING, A.MODE_VALIDATION, A.MODE_TESTING])
+def test_mnist_reference_environment_and_main_set_drive_the_gpu_classifier(oracle_mod, tmp_path, mode):
+    """The headline app: the instruction set sliced out of [REF] mnist/src/main.cpp:47-88, the reference's MNIST
+    environment (dataset read by its own mnist_reader from IDX files generated at build time), a graph in the
+    reference's dot format, tpgx::ClassificationAgent::evaluateAllRoots with params.json's 500 actions per evaluation —
+    per-root score, per-class F1 and evaluation counts equal the oracle's on the images MNIST::reset / doAction draw."""
+    g = tpgx.synthetic_graph("mnist", roots=25, edges=5, lines=12, depth=2, share_prob=0.1, seed=77)
+    dot = os.path.join(str(tmp_path), "mnist.dot")
+    tpgx.export_dot(g, dot)
+    generation, nb_actions = 5, 500
+    out = subprocess.run([DRIVER, "mnist", dot, str(generation), str(mode), "1", str(nb_actions)], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0, out.stderr
+    rows = [ln.split() for ln in out.stdout.strip().splitlines() if ln.startswith(("0x", "-0x"))]
+    assert len(rows) == g.nb_roots
+    score = np.array([float.fromhex(r[0]) for r in rows])
+    f1 = np.array([[float.fromhex(v) for v in r[2:]] for r in rows])
+    assert all(int(r[1]) == nb_actions for r in rows)
+    tr_img, tr_lab = tpgx.synthetic_images(3000, seed=101, label_seed=102)
+    te_img, te_lab = tpgx.synthetic_images(1000, seed=202, label_seed=203)
+    img, lab = np.concatenate([tr_img, te_img]), np.concatenate([tr_lab, te_lab])
+    size, offset = (3000, 0) if mode == A.MODE_TRAINING else (1000, 3000)
+    idx = tpgx.mnist_episode_indices(generation ^ 0, mode, size, nb_actions) + offset
+    g2 = tpgx.import_dot(dot, 5)
+    ref = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], g2, nb_constants=5).evaluate_classification(
+        img, lab, sample_index=idx.astype(np.int32), want=("score", "class_f1"))
+    assert np.array_equal(f1.view(np.uint64), ref["class_f1"].view(np.uint64))
+    assert np.allclose(score, ref["score"], rtol=0, atol=1e-15)   # the result object averages the 10 F1 values itself
