@@ -6,10 +6,11 @@
  * bid[row][s] = register 0 of program `row` on observation s, NaN mapped to -inf like
  * [UP] TPGExecutionEngine::evaluateEdge.
  *
- * Mapping.  CTA = one sample tile (TS = 32*K samples, pixel-major uint8, staged ONCE by a bulk TMA
- * copy) x one chunk of programs.  Each warp repeatedly claims a program of the chunk and interprets
- * it for all TS samples of the tile: lane = K consecutive samples, so instruction dispatch is
- * warp-uniform and never diverges.  Two builds of the kernel: the MNIST instruction set only
+ * Mapping.  CTA = one sample tile (TS = 32*K samples, pixel-major uint8; read in place through L1/L2
+ * by the default variant, staged by one bulk TMA copy by the TILE_SMEM variants) x one chunk of work
+ * units.  Each warp repeatedly claims a unit (program, or team in team mode) of the chunk and
+ * interprets it for all TS samples of the tile: lane = K consecutive samples, so instruction dispatch
+ * is warp-uniform and never diverges.  Two builds of the kernel: the MNIST instruction set only
  * (EXT = false: sub add mul div max exp ln multByConst sobelMagn sobelDir) and the extended one with
  * every double-typed instruction of the five apps.
  *
@@ -24,9 +25,11 @@
  *   - every handler loads its operands, computes and stores its result by itself, so no values
  *     merge after the dispatch (the previous version spent ~8 register moves per line there); the
  *     bid is read back from register slot 0 at the end of the program.
- *   - TPG registers live in shared memory as [warp][9 slots][K/2][32 lanes][2] doubles (slot 8 is
- *     a constant 0.0 = "never written", so no per-program clear): every access is a conflict-free
- *     16-byte-per-lane vector.
+ *   - TPG registers live in shared memory as [warp][8 slots][K/2][32 lanes][2] doubles: every access
+ *     is a conflict-free 16-byte-per-lane vector.  There is no per-program clear: a read of a register
+ *     no earlier line wrote is encoded as a read of the all-zero pixel row K0 appends to every tile.
+ *   - pixel and Sobel-plane operands are addressed as block-uniform base + 32-bit element index, which
+ *     is one IMAD.WIDE per global address.
  *   - libm and division are straight-line per sample with one shared rare branch per K samples
  *     (tpgx_math.h), so the K chains of a lane overlap; coefficients come from constant memory.
  */
@@ -66,7 +69,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
         : "memory");
 }
 
-#define K1_SLOTS 9
+#define K1_SLOTS 8
 #define K1_CODE_QUADS 32 /* TPGX_K1_CQ constant quads + TPGX_K1_CAPL lines; two such buffers per warp */
 
 /* Shared-memory accesses of the interpreter use explicit 32-bit shared addresses: with generic
@@ -96,13 +99,18 @@ template <int K> __device__ __forceinline__ void st_regs(uint32_t p, const doubl
     sts_f64x2(p, v[0], v[1]);
     if (K == 4) sts_f64x2(p + 512, v[2], v[3]);
 }
+/* pixel operand address: a shared-memory address (tile staged in shared memory) or a block-uniform global base plus a
+   32-bit per-thread offset (tile left in global memory) */
+template <bool TILE_SMEM> struct px_addr;
+template <> struct px_addr<true> { uint32_t a; };
+template <> struct px_addr<false> { const uint8_t* base; uint32_t idx; };
 /* K consecutive uint8 pixels of the lane -> packed word */
-template <int K> __device__ __forceinline__ uint32_t ld_px_word(uint32_t p) { return K == 2 ? lds_u16(p) : lds_u32(p); }
+template <int K> __device__ __forceinline__ uint32_t ld_px_word(px_addr<true> p) { return K == 2 ? lds_u16(p.a) : lds_u32(p.a); }
 /* same, tile left in global memory (read-only path, L1/L2) */
-template <int K> __device__ __forceinline__ uint32_t ld_px_word(const uint8_t* p) {
-    return K == 2 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p)) : __ldg(reinterpret_cast<const unsigned int*>(p));
+template <int K> __device__ __forceinline__ uint32_t ld_px_word(px_addr<false> p) {
+    return K == 2 ? (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(p.base) + p.idx) : __ldg(reinterpret_cast<const unsigned int*>(p.base) + p.idx);
 }
-template <int K> __device__ __forceinline__ void ld_px(uint32_t p, uint32_t (&v)[K]) {
+template <int K, class Addr> __device__ __forceinline__ void ld_px(Addr p, uint32_t (&v)[K]) {
     const uint32_t w = ld_px_word<K>(p);
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = __byte_perm(w, 0, 0x4440 + k); /* byte k, zero-extended: one PRMT */
@@ -127,7 +135,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
     extern __shared__ __align__(128) uint8_t smem[];
     /* TILE_SMEM: the sample tile is staged in shared memory by one bulk TMA copy.  Otherwise pixel operands are read
        from the tile in global memory (L1/L2) and all of shared memory goes to TPG registers, i.e. to more warps. */
-    const int tile_bytes = p.hw * TS;
+    const int tile_bytes = (p.hw + 1) * TS; /* + the all-zero row */
     uint8_t* tile = smem;
     uint8_t* regs = smem + (TILE_SMEM ? ((tile_bytes + 127) & ~127) : 0);
     uint4* codeb = reinterpret_cast<uint4*>(regs + NW * K1_SLOTS * TS * 8);
@@ -147,20 +155,16 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
     }
     const uint32_t regs_lane = smem_u32(regs) + warp * (K1_SLOTS * TS * 8) + lane * 16;
     const uint32_t tile_lane = smem_u32(tile) + lane * K;
-    const uint8_t* const gtile_lane = p.tiles + (size_t)blockIdx.y * tile_bytes + lane * K;
+    /* tile in global memory: block-uniform base + 32-bit index of the lane's packed word (K pixels) */
+    const uint8_t* __restrict__ const gtile = p.tiles + (size_t)blockIdx.y * tile_bytes;
     uint4* const mycode = codeb + warp * (2 * K1_CODE_QUADS);
-    {
-        double z[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) z[k] = 0.0;
-        st_regs<K>(regs_lane + TPGX_LOC_ZERO * TS * 8, z);
-    }
 
     const int chunk_begin = blockIdx.x * p.units_per_chunk; /* chunks vary fastest: CTAs resident together share tiles (L2) */
     const int chunk_n = min(p.units_per_chunk, p.nb_units - chunk_begin);
     /* this tile's Sobel planes: [which][window][TS samples] doubles; the lane's K samples are consecutive */
     const long long plane_stride = (long long)p.nwin * TS;
-    const double* const sobel_lane = p.sobel + (size_t)blockIdx.y * 2 * plane_stride + lane * K;
+    const double* __restrict__ const sobel_tile = p.sobel + (size_t)blockIdx.y * 2 * plane_stride;
+    const uint32_t sobel_lane = lane * (K / 2); /* double2 index */
     const uint4* __restrict__ stream = p.stream;
 
     /* next unclaimed program of the chunk: one shared-memory atomic by lane 0 (plain atom.shared — the
@@ -227,10 +231,9 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                 const uint4 ln = lp[j];                 /* broadcast LDS.128: handler, operand offsets, destination offset */
                 const uint32_t ra = regs_lane + ln.y;  /* operand as a register slot */
                 const uint32_t rb = regs_lane + ln.z;
-                using px_addr = typename std::conditional<TILE_SMEM, uint32_t, const uint8_t*>::type;
-                px_addr pa, pb;                         /* operand as a pixel */
-                if constexpr (TILE_SMEM) { pa = tile_lane + ln.y; pb = tile_lane + ln.z; }
-                else { pa = gtile_lane + ln.y; pb = gtile_lane + ln.z; }
+                px_addr<TILE_SMEM> pa, pb;              /* operand as a pixel */
+                if constexpr (TILE_SMEM) { pa.a = tile_lane + ln.y * K; pb.a = tile_lane + ln.z * K; }
+                else { pa.base = pb.base = gtile; pa.idx = lane + ln.y; pb.idx = lane + ln.z; }
                 const uint32_t rd = regs_lane + ln.w;  /* destination register slot */
                 /* dispatch on single bits of the handler id; every handler loads, computes and stores by
                    itself, so no values merge afterwards */
@@ -270,10 +273,11 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                 } else if (op == TPGX_K1X_SOBEL_MAGN || op == TPGX_K1X_SOBEL_DIR) {
                     /* window instructions read only the image: their values were computed once per upload
                        (K0b, tpgx_sobel_planes_kernel) and are fetched as one coalesced 16-byte load per lane */
-                    const double* src = sobel_lane + (op == TPGX_K1X_SOBEL_DIR ? plane_stride : 0) + (ln.y >> 3);
+                    const double2* src = reinterpret_cast<const double2*>(sobel_tile)
+                                       + (uint32_t)(sobel_lane + (op == TPGX_K1X_SOBEL_DIR ? (uint32_t)(plane_stride >> 1) : 0u) + ln.y);
 #pragma unroll
                     for (int k = 0; k < K; k += 2) {
-                        const double2 v = __ldg(reinterpret_cast<const double2*>(src + k));
+                        const double2 v = __ldg(src + (k >> 1));
                         r[k] = v.x; r[k + 1] = v.y;
                     }
                     st_regs<K>(rd, r);
@@ -324,7 +328,11 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
         /* the last effective line of a program writes register 0 (that is what makes it effective);
            an empty program leaves the 0.0 of [UP] executeProgram's register reset */
         double res[K];
-        ld_regs<K>(regs_lane + (n > 0 ? 0 : TPGX_LOC_ZERO * TS * 8), res);
+        if (n > 0) ld_regs<K>(regs_lane, res);
+        else {
+#pragma unroll
+            for (int k = 0; k < K; k++) res[k] = 0.0;
+        }
         /* [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
 #pragma unroll
         for (int k = 0; k < K; k++)
@@ -359,10 +367,10 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
 
 struct bid_variant { int K, NW; bool tile_smem; };
 /* variant 0 is the default: 4 samples per lane amortise the per-line work (fetch, dispatch, addressing) over 128 samples;
-   the tile stays in global memory (pixel operands through L1/L2) so that shared memory holds the TPG registers of 20 warps
-   and each thread gets 96 registers.  Measured on C2 (round 1): 16.4 ms vs 17.2 ms for {2, 32, tile in shared memory}. */
-static const bid_variant g_variants[] = {{4, 20, false}, {2, 32, true}, {2, 28, true}, {2, 24, true}, {4, 12, true},
-                                         {4, 16, false}, {2, 32, false}, {4, 22, false}};
+   the tile stays in global memory (pixel operands through L1/L2) so that shared memory holds the TPG registers of 24 warps
+   (9 KB each incl. code buffers; 25 would fit but leave 72 registers per thread) at 80 registers per thread. */
+static const bid_variant g_variants[] = {{4, 24, false}, {2, 32, true}, {2, 28, true}, {2, 24, true}, {4, 12, true},
+                                         {4, 16, false}, {2, 32, false}, {4, 20, false}, {4, 22, false}};
 static const int g_nb_variants = sizeof(g_variants) / sizeof(g_variants[0]);
 int tpgx_bid_warps(int variant) {
     if (variant < 0 || variant >= g_nb_variants) variant = 0;
@@ -377,7 +385,7 @@ size_t tpgx_bid_smem_bytes(int variant, int hw) {
     if (variant < 0 || variant >= g_nb_variants) variant = 0;
     const bid_variant& v = g_variants[variant];
     const int ts = 32 * v.K;
-    const size_t tile = v.tile_smem ? (((size_t)hw * ts + 127) & ~(size_t)127) : 0;
+    const size_t tile = v.tile_smem ? (((size_t)(hw + 1) * ts + 127) & ~(size_t)127) : 0;
     return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * 2 * K1_CODE_QUADS * 16 + 16;
 }
 
@@ -406,7 +414,8 @@ cudaError_t tpgx_launch_bid(const tpgx_bid_params& p, int nb_tiles, int variant,
     case 4: return launch_bid_t<4, 12, true>(p, nb_tiles, smem, ext, team, st);
     case 5: return launch_bid_t<4, 16, false>(p, nb_tiles, smem, ext, team, st);
     case 6: return launch_bid_t<2, 32, false>(p, nb_tiles, smem, ext, team, st);
-    case 7: return launch_bid_t<4, 22, false>(p, nb_tiles, smem, ext, team, st);
-    default: return launch_bid_t<4, 20, false>(p, nb_tiles, smem, ext, team, st);
+    case 7: return launch_bid_t<4, 20, false>(p, nb_tiles, smem, ext, team, st);
+    case 8: return launch_bid_t<4, 22, false>(p, nb_tiles, smem, ext, team, st);
+    default: return launch_bid_t<4, 24, false>(p, nb_tiles, smem, ext, team, st);
     }
 }

@@ -311,7 +311,7 @@ cudaError_t tpgx_launch_score(const unsigned long long* confusion, int nb_roots,
 }
 
 /* ================================================================================================
- * K0 — pack: tiles[t][px][j] = obs[index[t*TS + j]][px]; samples past the end replicate zeros.
+ * K0 — pack: tiles[t][px][j] = obs[index[t*TS + j]][px], px < hw; tiles[t][hw][j] = 0; samples past the end are zeros.
  * Block = (32 pixels x TS samples) sub-tile staged through shared memory so both the global read
  * (along pixels) and the global write (along samples) are coalesced.                               */
 __global__ void __launch_bounds__(256) tpgx_pack_kernel(const uint8_t* __restrict__ obs, const int32_t* __restrict__ index,
@@ -333,16 +333,17 @@ __global__ void __launch_bounds__(256) tpgx_pack_kernel(const uint8_t* __restric
         sm[j][lane] = v;
     }
     __syncthreads();
+    /* a tile has hw + 1 pixel rows: the last one is all zeros (K1 reads it for never-written TPG registers) */
     for (int q = threadIdx.x; q < 32 * ts; q += 256) {
         const int px = q / ts, j = q % ts;
-        if (p0 + px < hw) tiles[(tile * hw + p0 + px) * ts + j] = sm[j][px];
+        if (p0 + px <= hw) tiles[(tile * (hw + 1) + p0 + px) * ts + j] = (p0 + px < hw) ? sm[j][px] : (uint8_t)0;
     }
 }
 
 cudaError_t tpgx_launch_pack(const uint8_t* obs, const int32_t* sample_index, long long nb_samples, long long nb_obs, int hw,
                              int ts, uint8_t* tiles, const uint8_t* labels_in, uint8_t* labels_out, cudaStream_t st) {
     const long long nb_tiles = (nb_samples + ts - 1) / ts;
-    dim3 grid((unsigned)nb_tiles, (hw + 31) / 32);
+    dim3 grid((unsigned)nb_tiles, (hw + 1 + 31) / 32);
     tpgx_pack_kernel<<<grid, 256, 0, st>>>(obs, sample_index, nb_samples, nb_obs, hw, ts, tiles, labels_in, labels_out);
     return cudaGetLastError();
 }
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(256) tpgx_sobel_planes_kernel(const uint8_t* _
     if (q >= nwin * ts) return;
     const int wp = q / ts, j = q % ts;
     const int top = (wp / nwin_w) * width + (wp % nwin_w);
-    const uint8_t* t = tiles + tile * (long long)hw * ts + j;
+    const uint8_t* t = tiles + tile * (long long)(hw + 1) * ts + j;
     auto px = [&](int dr, int dc) { return (int)t[(long long)(top + dr * width + dc) * ts]; };
     const int gx = -px(0, 0) + px(0, 2) - 2 * px(1, 0) + 2 * px(1, 2) - px(2, 0) + px(2, 2);
     const int gy = -px(0, 0) - 2 * px(0, 1) - px(0, 2) + px(2, 0) + 2 * px(2, 1) + px(2, 2);
@@ -386,7 +387,7 @@ cudaError_t tpgx_launch_sobel_planes(const uint8_t* tiles, long long nb_tiles, i
  * descriptors.  block = one bid-matrix row; flags: bit 0 extended instruction, bit 1 int-typed.    */
 __global__ void tpgx_k1_encode_kernel(const uint32_t* __restrict__ code, const int32_t* __restrict__ prog_offset,
                                       const double* __restrict__ constants, int nb_constants, const int32_t* __restrict__ active_prog,
-                                      const int2* __restrict__ desc, int ts, int width, uint4* __restrict__ stream,
+                                      const int2* __restrict__ desc, int ts, int width, int hw, uint4* __restrict__ stream,
                                       int* __restrict__ flags) {
     const int row = blockIdx.x;
     const int p = active_prog[row];
@@ -399,7 +400,7 @@ __global__ void tpgx_k1_encode_kernel(const uint32_t* __restrict__ code, const i
     const uint32_t* src = code + prog_offset[p];
     int fl = 0;
     for (int i = threadIdx.x; i < d.y; i += blockDim.x) {
-        const tpgx_k1_quad q = tpgx_k1_line(src[i], (uint32_t)ts, (uint32_t)width);
+        const tpgx_k1_quad q = tpgx_k1_line(src[i], (uint32_t)ts, (uint32_t)width, (uint32_t)hw);
         out[TPGX_K1_CQ + i] = make_uint4(q.x, q.y, q.z, q.w);
         if (q.x == 0xffffffffu) fl |= 2;
         else if (tpgx_k1_is_extended(q.x)) fl |= 1;
@@ -407,10 +408,10 @@ __global__ void tpgx_k1_encode_kernel(const uint32_t* __restrict__ code, const i
     if (fl) atomicOr(flags, fl);
 }
 cudaError_t tpgx_launch_k1_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
-                                  const int32_t* active_prog, const int2* desc, int nb_rows, int ts, int width, uint4* stream,
+                                  const int32_t* active_prog, const int2* desc, int nb_rows, int ts, int width, int hw, uint4* stream,
                                   int* flags, cudaStream_t st) {
     if (nb_rows <= 0) return cudaSuccess;
-    tpgx_k1_encode_kernel<<<nb_rows, 32, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, ts, width, stream, flags);
+    tpgx_k1_encode_kernel<<<nb_rows, 32, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, ts, width, hw, stream, flags);
     return cudaGetLastError();
 }
 

@@ -119,7 +119,7 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
                                      const double* f0, const double* f1, const int32_t* i0, const int32_t* i1,
                                      int space0, int space1, int width0, int width1, double* bid, cudaStream_t st);
 cudaError_t tpgx_launch_k1_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
-                                  const int32_t* active_prog, const int2* desc, int nb_rows, int ts, int width, uint4* stream,
+                                  const int32_t* active_prog, const int2* desc, int nb_rows, int ts, int width, int hw, uint4* stream,
                                   int* flags, cudaStream_t st);
 cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st);
 cudaError_t tpgx_launch_sobel_planes(const uint8_t* tiles, long long nb_tiles, int hw, int height, int width, int ts, const double* lut,

@@ -218,7 +218,7 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         int* d_flags = ctx->d_status.as<int>() + 2;
         CU(cudaMemsetAsync(d_flags, 0, 4, ctx->stream));
         CU(tpgx_launch_k1_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
-                                 ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->d_k1_stream.as<uint4>(),
+                                 ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->obs_hw, ctx->d_k1_stream.as<uint4>(),
                                  d_flags, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream)); /* desc is a local */
         /* which build of K1 (MNIST set only / extended) is known on the host from the opcode table */
@@ -279,7 +279,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             if ((st = upload(ctx, ctx->d_index, req->sample_index, (size_t)nS * 4)) != TPGX_OK) return st;
             d_index = ctx->d_index.as<int32_t>();
         }
-        CU(ctx->d_tiles.ensure((size_t)nTiles * hw * ts));
+        CU(ctx->d_tiles.ensure((size_t)nTiles * (hw + 1) * ts));
         CU(ctx->d_labels.ensure((size_t)nTiles * ts));
         CU(tpgx_launch_pack(ctx->obs_dev, d_index, nS, ctx->nb_obs, hw, ts, ctx->d_tiles.as<uint8_t>(), ctx->labels_dev,
                             ctx->d_labels.as<uint8_t>(), ctx->stream));
@@ -315,7 +315,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
         if (nA > 0) {
             tpgx_bid_params bp{};
-            bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * hw * ts;
+            bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * (hw + 1) * ts;
             bp.hw = hw; bp.width = ctx->obs_width;
             bp.stream = ctx->d_k1_stream.as<uint4>();
             bp.desc = ctx->d_k1_desc.as<int2>();
@@ -330,6 +330,17 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             int chunks = (int)std::max<int64_t>(1, (148 * 12 + nt - 1) / nt);
             chunks = std::min(chunks, std::max(1, nU / (team_mode ? 14 * nw : 4 * nw)));
             if ((int64_t)nt * chunks < 2 * 148) chunks = std::max(chunks, std::min((int)((2 * 148 + nt - 1) / nt), std::max(1, nU / nw)));
+            else { /* one CTA per SM: prefer a nearby chunk count whose last wave of 148 CTAs is nearly full */
+                const int cmax = std::min(chunks + 2, std::max(1, nU / (team_mode ? 10 * nw : 3 * nw)));
+                double best_fill = 0.0;
+                int best_c = chunks;
+                for (int c = std::max(1, chunks - 1); c <= std::max(chunks, cmax); c++) {
+                    const double waves = (double)nt * c / 148.0, fill = waves / std::ceil(waves);
+                    if (fill > best_fill + 0.01) { best_fill = fill; best_c = c; }
+                }
+                chunks = best_c;
+            }
+            if (const char* v = getenv("TPGX_K1_CHUNKS")) chunks = std::max(1, std::min(atoi(v), nU)); /* experiments */
             bp.units_per_chunk = (nU + chunks - 1) / chunks;
             bp.bid = ctx->d_bid.as<double>();
             bp.row_stride = (long long)nt * ts;
@@ -536,7 +547,7 @@ static tpgx_status set_obs_common(tpgx_ctx* ctx, int32_t source, int32_t store, 
 static tpgx_status pack_identity(tpgx_ctx* ctx) {
     const int ts = tpgx_bid_tile_samples(ctx->variant);
     const int64_t nTiles = (ctx->nb_obs + ts - 1) / ts;
-    CU(ctx->d_tiles.ensure((size_t)nTiles * ctx->obs_hw * ts));
+    CU(ctx->d_tiles.ensure((size_t)nTiles * (ctx->obs_hw + 1) * ts));
     CU(ctx->d_labels.ensure((size_t)nTiles * ts));
     CU(tpgx_launch_pack(ctx->obs_dev, nullptr, ctx->nb_obs, ctx->nb_obs, ctx->obs_hw, ts, ctx->d_tiles.as<uint8_t>(),
                         ctx->labels_dev, ctx->d_labels.as<uint8_t>(), ctx->stream));

@@ -50,8 +50,10 @@ static inline uint32_t tpgx_pack_line(uint32_t op, uint32_t dst, uint32_t ka, ui
  * Everything the interpreter would otherwise shift, mask and multiply per line is precomputed:
  *   x  handler id (below): for the cheap instructions the operand kinds (register / pixel) are part
  *      of the id, so a line costs one dispatch and no kind tests
- *   y  operand A: byte offset from the lane's register base (slot * TS * 8) or from the lane's pixel
- *      base (loc * TS); for a 3x3 window: byte offset of its window index in a Sobel plane (wp * TS * 8)
+ *   y  operand A: byte offset from the lane's register base (slot * TS * 8), or — pixel — index of the
+ *      lane-0 packed word (K pixels) in the tile (loc * 32); for a 3x3 window: index of the lane-0 double2
+ *      of its window in a Sobel plane (wp * TS / 2).  Indices rather than byte offsets, so that a 64-bit
+ *      global address is one IMAD.WIDE (index * element size + base)
  *   z  operand B: same, or the byte offset of the program constant (index * 8) for MULC
  *   w  destination register: byte offset from the lane's register base
  * TS = samples per tile (32 * K).  A program's stream entry is TPGX_K1_CQ quads holding its constants
@@ -82,14 +84,17 @@ TPGX_HOSTDEV static inline bool tpgx_k1_is_extended(uint32_t h) {
 
 struct tpgx_k1_quad { uint32_t x, y, z, w; };
 
-TPGX_HOSTDEV static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts, uint32_t width) {
+TPGX_HOSTDEV static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts, uint32_t width, uint32_t hw) {
     const uint32_t op = word & 31u, dst = (word >> 5) & 7u;
     const uint32_t fa = (word >> 8) & 0xfffu, fb = word >> 20;
-    const uint32_t pa = (fa >> 10) == TPGX_KIND_SRC0, pb = (fb >> 10) == TPGX_KIND_SRC0;
-    const uint32_t la = fa & 1023u, lb = fb & 1023u;
+    /* a never-written TPG register (TPGX_LOC_ZERO) reads the all-zero pixel row hw that K0 appends to every tile */
+    const uint32_t za = (fa >> 10) == TPGX_KIND_REG && (fa & 1023u) >= TPGX_LOC_ZERO;
+    const uint32_t zb = (fb >> 10) == TPGX_KIND_REG && (fb & 1023u) >= TPGX_LOC_ZERO;
+    const uint32_t pa = (fa >> 10) == TPGX_KIND_SRC0 || za, pb = (fb >> 10) == TPGX_KIND_SRC0 || zb;
+    const uint32_t la = za ? hw : (fa & 1023u), lb = zb ? hw : (fb & 1023u);
     tpgx_k1_quad q;
-    q.y = pa ? la * ts : la * ts * 8u;
-    q.z = pb ? lb * ts : lb * ts * 8u;
+    q.y = pa ? la * 32u : la * ts * 8u;
+    q.z = pb ? lb * 32u : lb * ts * 8u;
     q.w = dst * ts * 8u;
     const uint32_t kk = pa + 2 * pb;
     switch (op) {
@@ -112,8 +117,8 @@ TPGX_HOSTDEV static inline tpgx_k1_quad tpgx_k1_line(uint32_t word, uint32_t ts,
     case TPGX_OP_SIN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SIN << 2) | pa; break;
     case TPGX_OP_TAN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_TAN << 2) | pa; break;
     /* window operand: la is the top-left pixel; the handlers read the precomputed plane at window index wp */
-    case TPGX_OP_SOBEL_MAGN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_MAGN << 2) | 1u; q.y = ((la / width) * (width - 2u) + la % width) * ts * 8u; break;
-    case TPGX_OP_SOBEL_DIR: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_DIR << 2) | 1u; q.y = ((la / width) * (width - 2u) + la % width) * ts * 8u; break;
+    case TPGX_OP_SOBEL_MAGN: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_MAGN << 2) | 1u; q.y = ((la / width) * (width - 2u) + la % width) * (ts / 2u); break;
+    case TPGX_OP_SOBEL_DIR: q.x = TPGX_K1H_HEAVY | (TPGX_K1X_SOBEL_DIR << 2) | 1u; q.y = ((la / width) * (width - 2u) + la % width) * (ts / 2u); break;
     default: q.x = 0xffffffffu; break; /* int-typed instructions never reach K1 (no i32 source) */
     }
     return q;
