@@ -8,12 +8,65 @@
  *   - static reduction of every location,
  *   - "never written => 0.0" register reads marked so the device needs no register clear.
  */
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 
 #include "tpgx_internal.h"
 
 namespace {
+
+/* Worker pool behind tpgx_pool_run: up to 15 sleeping threads, created on first use, joined at unload.
+   One job at a time (callers of the library hold one context per thread; concurrent callers serialise here). */
+class Pool {
+    std::mutex run_mutex, m;
+    std::condition_variable wake, idle;
+    std::vector<std::thread> workers;
+    void (*fn)(int, void*) = nullptr;
+    void* arg = nullptr;
+    int nt = 0, pending = 0;
+    uint64_t generation = 0;
+    bool stop = false;
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            void (*f)(int, void*);
+            void* a;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                wake.wait(lk, [&] { return stop || generation != seen; });
+                if (stop) return;
+                seen = generation;
+                if (id >= nt) continue; /* not part of this job */
+                f = fn; a = arg;
+            }
+            f(id, a);
+            std::lock_guard<std::mutex> lk(m);
+            if (--pending == 0) idle.notify_one();
+        }
+    }
+public:
+    ~Pool() {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        wake.notify_all();
+        for (auto& t : workers) t.join();
+    }
+    void run(int n, void (*f)(int, void*), void* a) {
+        if (n <= 1) { f(0, a); return; }
+        std::lock_guard<std::mutex> one(run_mutex);
+        {
+            std::lock_guard<std::mutex> lk(m);
+            while ((int)workers.size() < n - 1) { const int id = (int)workers.size() + 1; workers.emplace_back([this, id] { loop(id); }); }
+            fn = f; arg = a; nt = n; pending = n - 1;
+            generation++;
+        }
+        wake.notify_all();
+        f(0, a);
+        std::unique_lock<std::mutex> lk(m);
+        idle.wait(lk, [&] { return pending == 0; });
+    }
+};
 
 struct SourceMap {
     const tpgx_config& cfg;
@@ -42,6 +95,11 @@ std::string fmt(const char* f, long a = 0, long b = 0, long c = 0) {
 }
 
 } // namespace
+
+void tpgx_pool_run(int nt, void (*fn)(int, void*), void* arg) {
+    static Pool pool;
+    pool.run(std::min(nt, 16), fn, arg);
+}
 
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
                                const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
@@ -72,41 +130,58 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     for (int p = 0; p < P; p++)
         if (g->program_line_offset[p + 1] < g->program_line_offset[p] || g->program_line_offset[p] < 0)
             return fail(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p));
+    /* per-instruction operand signature and per-(source, type) address space, looked up per line below */
+    struct OpRow { int32_t op, nb, type[2], flops; };
+    std::vector<OpRow> optab(opcode.size());
+    for (size_t i = 0; i < opcode.size(); i++) {
+        const tpgx_op_info oi = tpgx_get_op_info(opcode[i]);
+        optab[i] = {opcode[i], oi.nb_operands, {oi.type[0], oi.type[1]}, oi.flops};
+    }
+    const int nsrc = sm.total();
+    std::vector<uint32_t> space_tab((size_t)nsrc * 8, 0u);
+    for (int sidx = 0; sidx < nsrc; sidx++)
+        for (int t = 0; t <= TPGX_T_W; t++) space_tab[(size_t)sidx * 8 + t] = sm.space(sidx, t);
+    const uint32_t nI = (uint32_t)opcode.size();
     tpgx_parallel_blocks(P, 256, [&](int pb, int pe, int w) {
         Err& er = errs[w];
         auto bad = [&](tpgx_status st, const std::string& m) { if (er.st == TPGX_OK) { er.st = st; er.msg = m; } };
         for (int p = pb; p < pe && er.st == TPGX_OK; p++) {
             const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
             const tpgx_line* L = g->lines + b;
+            uint8_t* kp = keep.data() + b;
             const int n = (int)(e - b);
-            bool live[TPGX_MAX_REGS] = {false};
-            live[0] = true;
+            /* [UP] Program::identifyIntrons: backward liveness from register 0, as a bit mask and without
+               data-dependent branches (whether a line is an intron is unpredictable) */
+            uint32_t live = 1u;
             int cnt = 0;
             for (int i = n - 1; i >= 0; i--) {
                 const tpgx_line& l = L[i];
-                if (l.instruction >= opcode.size()) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", p, i, l.instruction)); break; }
+                if (l.instruction >= nI) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", p, i, l.instruction)); break; }
                 if (l.destination >= (uint32_t)R) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: destination register out of range", p, i)); break; }
-                const tpgx_op_info oi = tpgx_get_op_info(opcode[l.instruction]);
+                const OpRow& o = optab[l.instruction];
+                uint32_t reads = 0;
                 bool ok = true;
-                for (int k = 0; k < oi.nb_operands && ok; k++) {
-                    if ((int)l.src[k] >= sm.total()) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", p, i, l.src[k])); ok = false; }
-                    else if (sm.space((int)l.src[k], oi.type[k]) == 0) {
-                        bad(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", p, i, l.src[k]));
+                for (int k = 0; k < o.nb; k++) {
+                    const uint32_t sidx = l.src[k];
+                    if (sidx >= (uint32_t)nsrc) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", p, i, sidx)); ok = false; break; }
+                    const uint32_t sp = space_tab[(size_t)sidx * 8 + o.type[k]];
+                    if (sp == 0) {
+                        bad(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", p, i, sidx));
                         ok = false;
+                        break;
                     }
+                    if (sidx == 0) reads |= 1u << (l.loc[k] < sp ? l.loc[k] : l.loc[k] % sp);
                 }
                 if (!ok) break;
-                if (!live[l.destination]) continue;
-                keep[b + i] = 1;
-                cnt++;
-                live[l.destination] = false;
-                for (int k = 0; k < oi.nb_operands; k++)
-                    if (l.src[k] == 0) live[l.loc[k] % (uint32_t)R] = true;
+                const uint32_t k1 = (live >> l.destination) & 1u;
+                kp[i] = (uint8_t)k1;
+                cnt += (int)k1;
+                live = (live & ~(k1 << l.destination)) | (reads & (0u - k1));
             }
             n_eff[p] = cnt;
             if (g->intron && er.st == TPGX_OK) {
                 for (int i = 0; i < n; i++)
-                    if ((g->intron[b + i] != 0) == (keep[b + i] != 0)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i)); break; }
+                    if ((g->intron[b + i] != 0) == (kp[i] != 0)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i)); break; }
             }
         }
     });
@@ -125,24 +200,24 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
             const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
             const tpgx_line* L = g->lines + b;
             const int n = (int)(e - b);
-            bool written[TPGX_MAX_REGS] = {false};
+            uint32_t written = 0;
             int flops = 0;
             uint32_t* out_code = f.code.data() + f.prog_offset[p];
             for (int i = 0; i < n; i++) {
                 if (!keep[b + i]) continue;
                 const tpgx_line& l = L[i];
-                const int op = opcode[l.instruction];
-                const tpgx_op_info oi = tpgx_get_op_info(op);
+                const OpRow& o = optab[l.instruction];
                 uint32_t kind[2] = {TPGX_KIND_REG, TPGX_KIND_REG}, loc[2] = {TPGX_LOC_ZERO, TPGX_LOC_ZERO};
-                for (int k = 0; k < oi.nb_operands; k++) {
+                for (int k = 0; k < o.nb; k++) {
                     const int s = (int)l.src[k];
-                    uint32_t a = l.loc[k] % sm.space(s, oi.type[k]);
-                    if (s == 0) { kind[k] = TPGX_KIND_REG; loc[k] = written[a] ? a : TPGX_LOC_ZERO; }
+                    const uint32_t sp = space_tab[(size_t)s * 8 + o.type[k]];
+                    uint32_t a = l.loc[k] < sp ? l.loc[k] : l.loc[k] % sp;
+                    if (s == 0) { kind[k] = TPGX_KIND_REG; loc[k] = ((written >> a) & 1u) ? a : TPGX_LOC_ZERO; }
                     else if (cfg.nb_constants > 0 && s == 1) { kind[k] = TPGX_KIND_CONST; loc[k] = a; }
                     else {
                         const int ks = s - sm.first_env();
                         kind[k] = ks == 0 ? TPGX_KIND_SRC0 : TPGX_KIND_SRC1;
-                        if (oi.type[k] == TPGX_T_W) { /* [UP] Array2DWrapper window address -> top-left element */
+                        if (o.type[k] == TPGX_T_W) { /* [UP] Array2DWrapper window address -> top-left element */
                             const uint32_t ww = (uint32_t)src[ks].width - 2u;
                             a = (a / ww) * (uint32_t)src[ks].width + (a % ww);
                         }
@@ -153,9 +228,9 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                         loc[k] = a;
                     }
                 }
-                *out_code++ = tpgx_pack_line((uint32_t)op, l.destination, kind[0], loc[0], kind[1], loc[1]);
-                written[l.destination] = true;
-                flops += oi.flops;
+                *out_code++ = tpgx_pack_line((uint32_t)o.op, l.destination, kind[0], loc[0], kind[1], loc[1]);
+                written |= 1u << l.destination;
+                flops += o.flops;
             }
             f.prog_flops[p] = flops;
         }

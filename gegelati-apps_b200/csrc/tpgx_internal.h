@@ -170,23 +170,30 @@ struct tpgx_flat_graph {
     int64_t total_lines = 0, total_introns = 0;
 };
 
+/* Persistent host worker pool (flatten.cpp): run(nt, fn) calls fn(t) for t in [0, nt), t = 0 on the caller, the rest on
+ * pool threads that sleep between calls — a generation's host work is a few hundred microseconds, less than spawning
+ * threads for it costs. */
+void tpgx_pool_run(int nt, void (*fn)(int, void*), void* arg);
+
 /* Splits [0, n) into contiguous blocks over up to 16 host threads (the host side of a generation is
  * pure per-program work: intron marking, encoding); fn(begin, end, worker) runs once per block. */
-template <class F> static inline void tpgx_parallel_blocks(int n, int min_per_thread, F fn) {
+static inline int tpgx_host_threads() {
     /* host threads of this process: TPGX_HOST_THREADS, else the cores divided by the ranks sharing the node
        (torchrun exports LOCAL_WORLD_SIZE), at most 16 */
     unsigned hw = std::thread::hardware_concurrency();
     if (const char* lw = getenv("LOCAL_WORLD_SIZE")) { const int w = atoi(lw); if (w > 1) hw = std::max(1u, hw / (unsigned)w); }
     int nt = (int)std::min<unsigned>(hw ? hw : 1u, 16u);
     if (const char* ht = getenv("TPGX_HOST_THREADS")) { const int v = atoi(ht); if (v >= 1) nt = std::min(v, 16); }
-    nt = std::max(1, std::min(nt, n / std::max(1, min_per_thread)));
+    return nt;
+}
+template <class F> static inline void tpgx_parallel_blocks(int n, int min_per_thread, F fn) {
+    const int nt = std::max(1, std::min(tpgx_host_threads(), n / std::max(1, min_per_thread)));
     if (nt <= 1) { fn(0, n, 0); return; }
-    std::vector<std::thread> th;
-    th.reserve(nt - 1);
-    const int per = (n + nt - 1) / nt;
-    for (int t = 1; t < nt; t++) th.emplace_back([=, &fn] { fn(std::min(n, t * per), std::min(n, (t + 1) * per), t); });
-    fn(0, std::min(n, per), 0);
-    for (auto& x : th) x.join();
+    struct Ctx { F* fn; int n, per; } c{&fn, n, (n + nt - 1) / nt};
+    tpgx_pool_run(nt, [](int t, void* a) {
+        Ctx& c = *static_cast<Ctx*>(a);
+        (*c.fn)(std::min(c.n, t * c.per), std::min(c.n, (t + 1) * c.per), t);
+    }, &c);
 }
 static inline int tpgx_parallel_workers() { return 16; }
 
