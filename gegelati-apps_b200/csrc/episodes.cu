@@ -43,8 +43,19 @@ __device__ __forceinline__ bool ep_better(const ep_cand& a, const ep_cand& b, in
     return tie_break == TPGX_TIE_LAST_MAX ? a.e > b.e : a.e < b.e;
 }
 
+/* recorded executions of the episode still to resolve (warp-uniform): next entry, end, executions so far */
+struct ep_hits { int pos, end, base, step; };
+
+__device__ void ep_record_obs(const tpgx_episode_params& p, int slot, const tpgx_obs_view& o) {
+    double* out = p.rec_obs + (size_t)slot * p.obs_len;
+    int q = 0;
+    for (int s = 0; s < 2; s++)
+        for (int i = 0; i < o.width[s] && q < p.obs_len; i++) out[q++] = o.f64[s] ? o.f64[s][i] : (double)o.i32[s][i];
+    for (; q < p.obs_len; q++) out[q] = 0.0;
+}
+
 /* [UP] executeFromRoot on one observation by one warp; every lane returns the action id or -1 (error bits in err). */
-__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err, int lane) {
+__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err, int lane, ep_hits& h) {
     int visited[TPGX_MAX_PATH];
     int depth = 0, cur = root;
     for (;;) {
@@ -56,13 +67,14 @@ __device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_ob
         for (int e0 = eb; e0 < ee; e0 += 32) {
             ep_cand mine = {0.0, -1, 0};
             const int e = e0 + lane;
+            int prog = -1;
             if (e < ee) {
                 const int dst = __ldg(p.edge_destination + e);
                 bool seen = false;
                 if (dst >= 0)
                     for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
                 if (!seen) { /* admissible edge: run its program on this lane */
-                    const int prog = __ldg(p.edge_program + e);
+                    prog = __ldg(p.edge_program + e);
                     const int cb = __ldg(p.prog_offset + prog), n = __ldg(p.prog_offset + prog + 1) - cb;
                     double bid = tpgx_run_program(p.code + cb, n, p.constants + (size_t)prog * p.nb_constants, o);
                     if (bid != bid) bid = __longlong_as_double(0xfff0000000000000LL);
@@ -72,6 +84,19 @@ __device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_ob
                 }
             }
             __syncwarp();
+            if (p.hit_offset) { /* archive pass: the reference executes the admissible edges in list order = lane order */
+                const unsigned adm = __ballot_sync(0xffffffffu, prog >= 0);
+                const int nadm = __popc(adm), rank = __popc(adm & ((1u << lane) - 1u));
+                while (h.pos < h.end) {
+                    const int x = __ldg(p.hit_exec + h.pos) - h.base;
+                    if (x >= nadm) break;
+                    const int slot = __ldg(p.hit_slot + h.pos);
+                    if (prog >= 0 && rank == x) { p.rec_program[slot] = prog; p.rec_bid[slot] = mine.bid; p.rec_step[slot] = h.step; }
+                    if (lane == 0 && p.rec_obs) ep_record_obs(p, slot, o);
+                    h.pos++;
+                }
+                h.base += nadm;
+            }
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 ep_cand other;
@@ -293,6 +318,9 @@ __global__ void __launch_bounds__(EP_WARPS * 32) tpgx_episode_kernel(const tpgx_
         rng.raw = p.rng_raw + (size_t)it * TPGX_RNG_TABLE;
         rng.pos = 0;
         rng.exhausted = 0;
+        ep_hits hits = {0, 0, 0, 0};
+        const bool archive_pass = p.hit_offset != nullptr;
+        if (archive_pass) { hits.pos = __ldg(p.hit_offset + gid); hits.end = __ldg(p.hit_offset + gid + 1); }
         Env env;                                       /* replicated on every lane, stepped identically */
         ep_scratch<Env>::attach(env, s_scratch[warp]);
         env.reset(p, rng);
@@ -300,19 +328,21 @@ __global__ void __launch_bounds__(EP_WARPS * 32) tpgx_episode_kernel(const tpgx_
         tpgx_obs_view o;
         int n = 0, turn = 0;
         while (!env.is_terminal() && n < p.max_actions) {
+            if (archive_pass && hits.pos >= hits.end) break; /* nothing (more) to resolve in this episode */
             env.view(o);
             const int root = __ldg(p.job_teams + (size_t)j * K + turn);
-            const int action = ep_traverse(p, root, o, c, err, lane);
+            hits.step = n;
+            const int action = ep_traverse(p, root, o, c, err, lane, hits);
             if (lane == 0) c.eval++;
             if (action < 0) break;
-            if (lane == 0 && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
+            if (lane == 0 && !archive_pass && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
             __syncwarp();
             if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; break; }
             __syncwarp();
             turn = (turn + 1 == K) ? 0 : turn + 1;
             n++;
         }
-        if (lane == 0) {
+        if (lane == 0 && !archive_pass) {
             for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
             for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
             p.episode_actions[gid] = n;
@@ -326,6 +356,7 @@ __global__ void __launch_bounds__(EP_WARPS * 32) tpgx_episode_kernel(const tpgx_
         c.prog += __shfl_xor_sync(0xffffffffu, c.prog, o2);
         c.line += __shfl_xor_sync(0xffffffffu, c.line, o2);
     }
+    if (lane == 0 && p.episode_progs && gid < total && p.hit_offset == nullptr) p.episode_progs[gid] = (int32_t)c.prog;
     if (lane == 0) {
         atomicAdd(p.counters + 0, (unsigned long long)c.eval);
         atomicAdd(p.counters + 1, (unsigned long long)c.team);
@@ -361,6 +392,7 @@ cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) 
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (p.hit_offset) return cudaSuccess; /* archive pass: scores were produced by the counting pass */
     const int n = p.nb_jobs * p.roots_per_job;
     tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
     return cudaGetLastError();

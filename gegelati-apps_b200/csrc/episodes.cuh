@@ -29,6 +29,19 @@ struct tpgx_episode_params {
     double* job_score;            /* [nb_jobs][roots_per_job]                                        */
     unsigned long long* counters; /* [4]                                                             */
     int* status;
+    /* archive reproduction ([UP] Archive::addRecording): pass 1 counts the program executions of
+       every episode; pass 2 (hit_offset != nullptr) re-runs the episodes that hold recorded executions and resolves
+       them — the h-th recorded execution of an episode is execution number hit_exec[h] (0-based, in the reference's
+       order: steps, then teams along the path, then admissible edges in list order) and goes to record hit_slot[h] */
+    int32_t* episode_progs;       /* [nb_jobs][nb_iterations] out, optional                          */
+    const int32_t* hit_offset;    /* [nb_jobs * nb_iterations + 1]                                   */
+    const int32_t* hit_exec;
+    const int32_t* hit_slot;
+    int32_t* rec_program;         /* [records]                                                       */
+    int32_t* rec_step;            /* [records] number of doAction calls before the observation       */
+    double* rec_bid;              /* [records]                                                       */
+    double* rec_obs;              /* [records][obs_len] data sources at that step, concatenated      */
+    int obs_len;
 };
 
 cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st);

@@ -75,7 +75,7 @@ struct tpgx_ctx {
     DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
-    DevBuf d_scratch[8];
+    DevBuf d_scratch[16];
     const uint8_t* obs_dev = nullptr;    /* raw observations [nb_obs][hw] (ours or the caller's) */
     const uint8_t* labels_dev = nullptr;
     int64_t nb_obs = 0;
@@ -712,7 +712,16 @@ tpgx_status tpgx_execute_programs(tpgx_ctx* ctx, int64_t count, const double* co
     return TPGX_OK;
 }
 
-tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_episode_result* out) {
+/* archive pass of the episode kernel: the recorded executions to resolve, per episode, and where the records go */
+struct EpHitPass {
+    std::vector<int32_t> hit_offset, hit_exec, hit_slot;
+    int nb_records = 0, obs_len = 0;
+    std::vector<int32_t> rec_program, rec_step;
+    std::vector<double> rec_bid, rec_obs;
+};
+
+static tpgx_status episodes_impl(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_episode_result* out,
+                                 std::vector<int32_t>* progs_out, EpHitPass* hp) {
     if (!ctx || !req || !out) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_episodes: null argument");
     if (!ctx->has_graph) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_episodes: no graph set");
     cudaSetDevice(ctx->cfg.device);
@@ -781,6 +790,28 @@ tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* re
     ep.job_score = sc[6].as<double>();
     ep.counters = ctx->d_counters.as<unsigned long long>();
     ep.status = ctx->d_status.as<int>();
+    if (progs_out) {
+        CU(sc[8].ensure(nE * 4));
+        ep.episode_progs = sc[8].as<int32_t>();
+    }
+    if (hp) {
+        if ((st = upload(ctx, sc[9], hp->hit_offset.data(), hp->hit_offset.size() * 4)) != TPGX_OK) return st;
+        if ((st = upload(ctx, sc[10], hp->hit_exec.data(), std::max<size_t>(1, hp->hit_exec.size()) * 4)) != TPGX_OK) return st;
+        if ((st = upload(ctx, sc[11], hp->hit_slot.data(), std::max<size_t>(1, hp->hit_slot.size()) * 4)) != TPGX_OK) return st;
+        const size_t nr = (size_t)std::max(1, hp->nb_records);
+        CU(sc[12].ensure(nr * 4));
+        CU(sc[13].ensure(nr * 4));
+        CU(sc[14].ensure(nr * 8));
+        CU(sc[15].ensure(nr * (size_t)std::max(1, hp->obs_len) * 8));
+        ep.hit_offset = sc[9].as<int32_t>();
+        ep.hit_exec = sc[10].as<int32_t>();
+        ep.hit_slot = sc[11].as<int32_t>();
+        ep.rec_program = sc[12].as<int32_t>();
+        ep.rec_step = sc[13].as<int32_t>();
+        ep.rec_bid = sc[14].as<double>();
+        ep.rec_obs = hp->obs_len > 0 ? sc[15].as<double>() : nullptr;
+        ep.obs_len = hp->obs_len;
+    }
     CU(cudaEventRecord(ctx->event(0), ctx->stream));
     CU(tpgx_launch_episodes(ep, ctx->stream));
     CU(cudaEventRecord(ctx->event(1), ctx->stream));
@@ -788,6 +819,21 @@ tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* re
     int status = 0;
     CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
     if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
+    if (progs_out) {
+        progs_out->resize(nE);
+        CU(cudaMemcpy(progs_out->data(), sc[8].p, nE * 4, cudaMemcpyDeviceToHost));
+    }
+    if (hp) {
+        const size_t nr = (size_t)hp->nb_records;
+        hp->rec_program.resize(nr); hp->rec_step.resize(nr); hp->rec_bid.resize(nr); hp->rec_obs.resize(nr * (size_t)hp->obs_len);
+        if (nr) {
+            CU(cudaMemcpy(hp->rec_program.data(), sc[12].p, nr * 4, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(hp->rec_step.data(), sc[13].p, nr * 4, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(hp->rec_bid.data(), sc[14].p, nr * 8, cudaMemcpyDeviceToHost));
+            if (hp->obs_len > 0) CU(cudaMemcpy(hp->rec_obs.data(), sc[15].p, nr * (size_t)hp->obs_len * 8, cudaMemcpyDeviceToHost));
+        }
+        return TPGX_OK; /* the archive pass writes records only */
+    }
     if (out->score) CU(cudaMemcpy(out->score, sc[6].p, (size_t)J * K * 8, cudaMemcpyDeviceToHost));
     if (out->episode_score) CU(cudaMemcpy(out->episode_score, sc[2].p, nE * K * 8, cudaMemcpyDeviceToHost));
     if (out->episode_actions) CU(cudaMemcpy(out->episode_actions, sc[3].p, nE * 4, cudaMemcpyDeviceToHost));
@@ -802,6 +848,85 @@ tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* re
         out->counters->device_lines = c[3]; out->counters->device_program_executions = c[2];
     }
     if (out->device_ms) cudaEventElapsedTime(out->device_ms, ctx->event(0), ctx->event(1));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_episode_result* out) {
+    return episodes_impl(ctx, req, out, nullptr, nullptr);
+}
+
+/* [UP] Archive::addRecording during a TRAINING evaluateAllRoots of a sequential environment.  Pass 1 is the evaluation
+   itself and yields the number of program executions of every episode; the host replays every job's draw stream over
+   the job's executions (iterations in order), keeps the recordings that survive the per-job and the merged ring, and
+   pass 2 re-runs only the episodes that hold such an execution to resolve (program, step, bid, observation). */
+tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, const tpgx_archive_request* arch,
+                                  tpgx_episode_result* eval_out, tpgx_episode_archive_result* out) {
+    if (!ctx || !req || !arch || !out || !arch->archive_seed || arch->archive_size < 0 || !(arch->probability >= 0.0 && arch->probability <= 1.0))
+        return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_archive_episodes: bad argument");
+    if (arch->archive_size > 0 && (!out->program || !out->job || !out->iteration || !out->step || !out->bid))
+        return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_archive_episodes: null output");
+    if (out->observation && out->obs_len < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_archive_episodes: obs_len missing");
+    tpgx_episode_result scratch_out{};
+    std::vector<int32_t> progs;
+    tpgx_status st = episodes_impl(ctx, req, eval_out ? eval_out : &scratch_out, &progs, nullptr);
+    if (st != TPGX_OK) return st;
+    out->nb_records = 0;
+    const int J = req->nb_jobs, NI = req->nb_iterations, cap = arch->archive_size;
+    if (cap == 0 || arch->probability == 0.0) return TPGX_OK;
+    /* per job: the job-local indices of its recorded executions (its own ring keeps the last `cap`) */
+    std::vector<std::vector<int64_t>> job_hits((size_t)J);
+    tpgx_parallel_blocks(J, 8, [&](int jb, int je, int) {
+        for (int j = jb; j < je; j++) {
+            int64_t N = 0;
+            for (int it = 0; it < NI; it++) N += progs[(size_t)j * NI + it];
+            std::vector<int64_t>& hits = job_hits[j];
+            if (arch->probability == 1.0) {
+                for (int64_t k = std::max<int64_t>(0, N - cap); k < N; k++) hits.push_back(k);
+            } else {
+                std::mt19937_64 eng(arch->archive_seed[j]);
+                for (int64_t k = 0; k < N; k++) {
+                    double canon = (double)eng() / 18446744073709551616.0;     /* libstdc++ uniform_real_distribution<double>(0, 1) */
+                    if (canon >= 1.0) canon = 0.99999999999999988898;
+                    if (arch->probability >= canon) hits.push_back(k);
+                }
+                if (hits.size() > (size_t)cap) hits.erase(hits.begin(), hits.end() - cap);
+            }
+        }
+    });
+    /* merged archive = the last `cap` recordings of the per-job archives concatenated in job order */
+    int64_t total = 0;
+    for (int j = 0; j < J; j++) total += (int64_t)job_hits[j].size();
+    int64_t drop = std::max<int64_t>(0, total - cap);
+    EpHitPass hp;
+    hp.obs_len = out->observation ? out->obs_len : 0;
+    hp.hit_offset.assign((size_t)J * NI + 1, 0);
+    std::vector<int32_t> rec_job, rec_it;
+    for (int j = 0; j < J; j++) {
+        std::vector<int64_t>& hits = job_hits[j];
+        size_t first = 0;
+        if (drop > 0) { first = (size_t)std::min<int64_t>(drop, (int64_t)hits.size()); drop -= (int64_t)first; }
+        int it = 0;
+        int64_t it_begin = 0;
+        for (size_t h = first; h < hits.size(); h++) {
+            while (it < NI && hits[h] >= it_begin + progs[(size_t)j * NI + it]) { it_begin += progs[(size_t)j * NI + it]; it++; }
+            if (it >= NI) return fail(ctx, TPGX_ERR_STATE, "tpgx_archive_episodes: internal execution-count mismatch");
+            hp.hit_offset[(size_t)j * NI + it + 1]++;
+            hp.hit_exec.push_back((int32_t)(hits[h] - it_begin));
+            hp.hit_slot.push_back((int32_t)rec_job.size());
+            rec_job.push_back(j);
+            rec_it.push_back(it);
+        }
+    }
+    for (size_t i = 1; i < hp.hit_offset.size(); i++) hp.hit_offset[i] += hp.hit_offset[i - 1];
+    hp.nb_records = (int)rec_job.size();
+    if (hp.nb_records == 0) return TPGX_OK;
+    if ((st = episodes_impl(ctx, req, &scratch_out, nullptr, &hp)) != TPGX_OK) return st;
+    out->nb_records = hp.nb_records;
+    for (int i = 0; i < hp.nb_records; i++) {
+        out->program[i] = hp.rec_program[i]; out->job[i] = rec_job[i]; out->iteration[i] = rec_it[i];
+        out->step[i] = hp.rec_step[i]; out->bid[i] = hp.rec_bid[i];
+    }
+    if (out->observation) memcpy(out->observation, hp.rec_obs.data(), hp.rec_obs.size() * 8);
     return TPGX_OK;
 }
 

@@ -76,6 +76,11 @@ class ArchiveResult(C.Structure):
     _fields_ = [("program", C.c_void_p), ("sample", C.c_void_p), ("bid", C.c_void_p), ("nb_records", C.c_int32), ("reserved", C.c_int32)]
 
 
+class EpisodeArchiveResult(C.Structure):
+    _fields_ = [("program", C.c_void_p), ("job", C.c_void_p), ("iteration", C.c_void_p), ("step", C.c_void_p), ("bid", C.c_void_p),
+                ("observation", C.c_void_p), ("obs_len", C.c_int32), ("nb_records", C.c_int32)]
+
+
 class EpisodeRequest(C.Structure):
     _fields_ = [("env", C.c_int32), ("mode", C.c_int32), ("nb_iterations", C.c_int32), ("max_actions", C.c_int32),
                 ("seeds", C.c_void_p), ("nb_jobs", C.c_int32), ("roots_per_job", C.c_int32), ("job_roots", C.c_void_p),

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..
 EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
-    "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes",
+    "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
 ]
 
@@ -245,6 +245,35 @@ class Evaluator:
             res.trace = out["trace"].ctypes.data
         self._check(self.lib.tpgx_evaluate_episodes(self.h, C.byref(req), C.byref(res)))
         out["counters"] = cnt.as_dict()
+        return out
+
+    def archive_episodes(self, env, seeds, job_roots, max_actions, archive_seeds, probability, archive_size, obs_len=0,
+                         mode=A.MODE_TRAINING, roots_per_job=1, second_player_random=0, pendulum_actions=None):
+        """Archive left by a TRAINING evaluateAllRoots of a sequential environment ([UP] Archive::addRecording):
+        dict(program, job, iteration, step, bid[, observation]) in archive order, plus the evaluation's scores."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        jr = np.ascontiguousarray(job_roots, dtype=np.int32).reshape(-1, roots_per_job)
+        J, NI = jr.shape[0], len(seeds)
+        pa = np.ascontiguousarray(pendulum_actions, dtype=np.float64) if pendulum_actions is not None else None
+        req = A.EpisodeRequest(env=env, mode=mode, nb_iterations=NI, max_actions=max_actions, seeds=seeds.ctypes.data, nb_jobs=J,
+                               roots_per_job=roots_per_job, job_roots=jr.ctypes.data, second_player_random=second_player_random,
+                               nb_pendulum_actions=0 if pa is None else len(pa), pendulum_actions=_ptr(pa), trace_steps=0)
+        aseeds = np.ascontiguousarray(archive_seeds, dtype=np.uint64)
+        assert len(aseeds) == J
+        n = max(1, int(archive_size))
+        o = dict(program=np.zeros(n, dtype=np.int32), job=np.zeros(n, dtype=np.int32), iteration=np.zeros(n, dtype=np.int32),
+                 step=np.zeros(n, dtype=np.int32), bid=np.zeros(n))
+        if obs_len > 0:
+            o["observation"] = np.zeros((n, obs_len))
+        score = np.zeros((J, roots_per_job))
+        ev = A.EpisodeResult(score=score.ctypes.data)
+        ar = A.ArchiveRequest(archive_seed=aseeds.ctypes.data, probability=float(probability), archive_size=int(archive_size))
+        res = A.EpisodeArchiveResult(program=o["program"].ctypes.data, job=o["job"].ctypes.data, iteration=o["iteration"].ctypes.data,
+                                     step=o["step"].ctypes.data, bid=o["bid"].ctypes.data,
+                                     observation=o["observation"].ctypes.data if obs_len > 0 else None, obs_len=int(obs_len))
+        self._check(self.lib.tpgx_archive_episodes(self.h, C.byref(req), C.byref(ar), C.byref(ev), C.byref(res)))
+        out = {k: v[:res.nb_records] for k, v in o.items()}
+        out["score"] = score
         return out
 
     def math_probe(self, fn, a, b=None):

@@ -275,6 +275,27 @@ typedef struct {                 /* every pointer optional                      
 tpgx_status tpgx_evaluate_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req,
                                    tpgx_episode_result* out);
 
+/* Archive side effect of a TRAINING evaluateAllRoots of a sequential environment ([UP] Archive::addRecording called by
+ * evaluateEdge; archiveSize / archivingProbability: [REF] pendulum/params.json:4,7, gridworld/params.json:2-3,
+ * stickgame/params.json:4,7, tic-tac-toe/params.json:4,7).  Same restated semantics as tpgx_archive_classification
+ * (one Archive per job seeded with archive_seed[job], one draw per executed program in execution order — iterations, steps,
+ * teams along the path, admissible edges in list order; both roots of an adversarial job share the job's archive), with
+ * the recorded observation identified by (job, iteration, step) and optionally copied out.  eval_out (optional) receives
+ * the evaluation results of the same call: the archive is a side effect of evaluateAllRoots, not a second evaluation.   */
+typedef struct {
+    int32_t* program;              /* [archive_size] */
+    int32_t* job;                  /* [archive_size] */
+    int32_t* iteration;            /* [archive_size] */
+    int32_t* step;                 /* [archive_size] doAction calls made before the recorded observation               */
+    double* bid;                   /* [archive_size] */
+    double* observation;           /* optional [archive_size][obs_len]: the data sources at that step, concatenated in
+                                      getDataSources() order (int sources converted to double), zero padded           */
+    int32_t obs_len;               /* in */
+    int32_t nb_records;            /* out */
+} tpgx_episode_archive_result;
+tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, const tpgx_archive_request* arch,
+                                  tpgx_episode_result* eval_out, tpgx_episode_archive_result* out);
+
 /* Direct access to single engine steps (used by parity tests; replaces
  * [UP] ProgramExecutionEngine::executeProgram on an explicit observation batch):
  * obs_f64 / obs_i32 are [count][address space] per source (NULL if absent); bid is [P][count].     */

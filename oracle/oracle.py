@@ -37,6 +37,8 @@ def load():
     lib.orc_archive_classification.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(A.ClassifRequest), C.c_void_p, C.c_double, C.c_int32,
                                                C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
     lib.orc_evaluate_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.POINTER(A.EpisodeResult), C.c_int32]
+    lib.orc_archive_episodes.argtypes = [C.c_void_p, C.POINTER(A.EpisodeRequest), C.c_void_p, C.c_double, C.c_int32] + [C.c_void_p] * 6 + [
+        C.c_int32, C.POINTER(C.c_int32)]
     lib.orc_apply_op.restype = C.c_double
     lib.orc_apply_op.argtypes = [C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_void_p]
     lib.orc_math_array.argtypes = [C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p]
@@ -166,6 +168,35 @@ class Oracle:
             raise RuntimeError("oracle episodes failed: %d" % st)
         out["counters"] = cnt.as_dict()
         return out
+
+
+def _archive_episodes(self, env, seeds, job_roots, max_actions, archive_seeds, probability, archive_size, obs_len=0,
+                      mode=A.MODE_TRAINING, roots_per_job=1, second_player_random=0, pendulum_actions=None):
+    seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+    jr = np.ascontiguousarray(job_roots, dtype=np.int32).reshape(-1, roots_per_job)
+    J, NI = jr.shape[0], len(seeds)
+    pa = np.ascontiguousarray(pendulum_actions, dtype=np.float64) if pendulum_actions is not None else None
+    req = A.EpisodeRequest(env=env, mode=mode, nb_iterations=NI, max_actions=max_actions, seeds=seeds.ctypes.data, nb_jobs=J,
+                           roots_per_job=roots_per_job, job_roots=jr.ctypes.data, second_player_random=second_player_random,
+                           nb_pendulum_actions=0 if pa is None else len(pa), pendulum_actions=_ptr(pa), trace_steps=0)
+    aseeds = np.ascontiguousarray(archive_seeds, dtype=np.uint64)
+    n = max(1, int(archive_size))
+    o = dict(program=np.zeros(n, dtype=np.int32), job=np.zeros(n, dtype=np.int32), iteration=np.zeros(n, dtype=np.int32),
+             step=np.zeros(n, dtype=np.int32), bid=np.zeros(n))
+    obs = np.zeros((n, max(1, obs_len)))
+    cnt = C.c_int32(0)
+    st = self.lib.orc_archive_episodes(self.h, C.byref(req), aseeds.ctypes.data, float(probability), int(archive_size), o["program"].ctypes.data,
+                                       o["job"].ctypes.data, o["iteration"].ctypes.data, o["step"].ctypes.data, o["bid"].ctypes.data,
+                                       obs.ctypes.data if obs_len > 0 else None, int(obs_len), C.byref(cnt))
+    if st != 0:
+        raise RuntimeError("oracle status %d" % st)
+    out = {k: v[:cnt.value] for k, v in o.items()}
+    if obs_len > 0:
+        out["observation"] = obs[:cnt.value]
+    return out
+
+
+Oracle.archive_episodes = _archive_episodes
 
 
 def apply_op(opcode, a=0.0, b=0.0, ia=0, ib=0, c=0.0, win=None, math=MATH_SHARED):

@@ -139,16 +139,20 @@ struct SourceView {
 /* [UP] Archive (App. F U12): one per job in TRAINING evaluation.  addRecording is called by evaluateEdge for every
  * executed program; it records with probability p — `p == 1.0 || p >= rng.getDouble(0, 1)`, so no draw is consumed
  * when p is 1 — and keeps at most max_size recordings (oldest dropped). */
-struct ArchiveRec { int32_t program; int64_t sample; double bid; };
+struct ArchiveRec { int32_t program; int64_t sample; double bid; int32_t job, iteration, step; double obs[16]; };
 struct ArchiveRecorder {
     std::mt19937_64 eng;
     double p = 0.0;
     size_t max_size = 0;
     int64_t sample = -1;                 /* stands for the hash of the data sources: which observation is current */
+    int32_t job = 0, iteration = 0, step = 0; /* episodic environments: where the current observation was seen */
+    double obs[16] = {0};                /* ... and a copy of it ([UP] the archive clones the data handlers) */
     std::deque<ArchiveRec> recs;
     void add(int32_t program, double bid) {
         if (p == 1.0 || p >= std::uniform_real_distribution<double>(0.0, 1.0)(eng)) {
-            recs.push_back({program, sample, bid});
+            ArchiveRec r{program, sample, bid, job, iteration, step, {0}};
+            std::memcpy(r.obs, obs, sizeof obs);
+            recs.push_back(r);
             while (recs.size() > max_size) recs.pop_front();
         }
     }
@@ -798,6 +802,58 @@ int32_t orc_evaluate_episodes(const orc_engine* e, const tpgx_episode_request* r
     });
     if (status) return status;
     export_counters(total, out->counters);
+    return 0;
+}
+
+/* [UP] evaluateAllRoots in TRAINING mode on a sequential environment, archive side effect: one Archive per job (shared by
+ * both roots of an adversarial job), a draw per executed program in execution order, per-job rings merged in job order. */
+int32_t orc_archive_episodes(const orc_engine* e, const tpgx_episode_request* req, const uint64_t* archive_seed, double probability,
+                             int32_t archive_size, int32_t* out_program, int32_t* out_job, int32_t* out_iteration, int32_t* out_step,
+                             double* out_bid, double* out_obs, int32_t obs_len, int32_t* nb_records) {
+    const int K = req->roots_per_job, NI = req->nb_iterations;
+    if (K < 1 || K > 2 || NI < 1 || archive_size < 0) return TPGX_ERR_BAD_ARG;
+    std::deque<ArchiveRec> merged;
+    std::vector<int> visited;
+    for (int j = 0; j < req->nb_jobs; j++) {
+        ArchiveRecorder ar;
+        ar.eng.seed(archive_seed[j]);
+        ar.p = probability;
+        ar.max_size = (size_t)archive_size;
+        ar.job = j;
+        Counters cnt;
+        cnt.archive = &ar;
+        auto env = make_env(req->env, req->second_player_random != 0, req->pendulum_actions, req->nb_pendulum_actions, e->math);
+        if (!env || env->nb_sources() != (int)e->src.size()) return TPGX_ERR_BAD_ARG;
+        std::vector<SourceView> v(env->nb_sources());
+        for (int it = 0; it < NI; it++) {
+            env->reset(req->seeds[it], req->mode);
+            int n = 0, turn = 0;
+            while (!env->is_terminal() && n < req->max_actions) {
+                int q = 0;
+                for (int s = 0; s < env->nb_sources(); s++) {
+                    v[s] = env->view(s);
+                    for (int i = 0; i < e->src[s].width * std::max(1, e->src[s].height) && q < 16; i++)
+                        ar.obs[q++] = v[s].f64 ? v[s].f64[i] : (double)v[s].i32[i];
+                }
+                for (; q < 16; q++) ar.obs[q] = 0.0;
+                ar.iteration = it; ar.step = n;
+                const int root = e->root_team[req->job_roots[(size_t)j * K + turn]];
+                const int action = e->execute_from_root(root, v.data(), &cnt, visited);
+                if (action < 0) return TPGX_ERR_GRAPH_INVALID;
+                if (!env->do_action((double)action)) return TPGX_ERR_BAD_ARG;
+                turn = (turn + 1) % K;
+                n++;
+            }
+        }
+        for (const ArchiveRec& r : ar.recs) merged.push_back(r);
+        while (merged.size() > (size_t)archive_size) merged.pop_front();
+    }
+    *nb_records = (int32_t)merged.size();
+    for (size_t i = 0; i < merged.size(); i++) {
+        const ArchiveRec& r = merged[i];
+        out_program[i] = r.program; out_job[i] = r.job; out_iteration[i] = r.iteration; out_step[i] = r.step; out_bid[i] = r.bid;
+        if (out_obs) for (int q = 0; q < obs_len; q++) out_obs[i * (size_t)obs_len + q] = q < 16 ? r.obs[q] : 0.0;
+    }
     return 0;
 }
 

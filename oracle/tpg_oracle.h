@@ -61,6 +61,12 @@ int32_t orc_archive_classification(const orc_engine* e, const uint8_t* images, i
 int32_t orc_evaluate_episodes(const orc_engine* e, const tpgx_episode_request* req,
                               tpgx_episode_result* out, int32_t nb_threads);
 
+/* Archive side effect of the same call in TRAINING mode: final <= archive_size recordings as (program, job, iteration,
+ * step, bid) plus the observation (data sources concatenated, ints as doubles, obs_len <= 16 values). */
+int32_t orc_archive_episodes(const orc_engine* e, const tpgx_episode_request* req, const uint64_t* archive_seed, double probability,
+                             int32_t archive_size, int32_t* out_program, int32_t* out_job, int32_t* out_iteration, int32_t* out_step,
+                             double* out_bid, double* out_obs, int32_t obs_len, int32_t* nb_records);
+
 /* ---- single pieces exposed for pinning tests ---- */
 /* Apply device-opcode semantics on scalar operands: a,b doubles / ia,ib ints / c constant /
  * win 3x3 row-major window. */
