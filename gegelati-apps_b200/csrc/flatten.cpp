@@ -75,17 +75,7 @@ struct SourceMap {
     int total() const { return first_env() + (int)src.size(); }
     /* address space of handler `s` for operand type `t`; 0 = the handler cannot provide it
      * ([UP] DataHandler::getAddressSpace; PrimitiveTypeArray / Array2DWrapper rules) */
-    uint32_t space(int s, int t) const {
-        if (s == 0) return t == TPGX_T_D ? (uint32_t)cfg.nb_registers : 0u;
-        if (cfg.nb_constants > 0 && s == 1) return t == TPGX_T_C ? (uint32_t)cfg.nb_constants : 0u;
-        const int k = s - first_env();
-        if (k < 0 || k >= (int)src.size()) return 0u;
-        const tpgx_source_desc& d = src[k];
-        if (d.elem == TPGX_ELEM_I32) return (t == TPGX_T_I && !d.is_2d) ? (uint32_t)d.width : 0u;
-        if (t == TPGX_T_D) return (uint32_t)(d.height * d.width);
-        if (t == TPGX_T_W && d.is_2d && d.height >= 3 && d.width >= 3) return (uint32_t)((d.height - 2) * (d.width - 2));
-        return 0u;
-    }
+    uint32_t space(int s, int t) const { return tpgx_source_space(cfg, src, s, t); }
 };
 
 std::string fmt(const char* f, long a = 0, long b = 0, long c = 0) {

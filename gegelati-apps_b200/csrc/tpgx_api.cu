@@ -930,6 +930,78 @@ tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req
     return TPGX_OK;
 }
 
+/* ---- GPU backend of the host generation loop (csrc/train.cpp) for the sequential environments ---- */
+namespace {
+struct EpBackend {
+    tpgx_ctx* ctx;
+    tpgx_episode_request req;
+};
+tpgx_status epbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, const uint64_t* archive_seed, double probability,
+                          int32_t archive_size, double* scores, int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len,
+                          int32_t* nb_records) {
+    EpBackend* b = static_cast<EpBackend*>(user);
+    tpgx_status st = tpgx_set_graph(b->ctx, g);
+    if (st != TPGX_OK) return st;
+    const int R = g->nb_roots, NI = b->req.nb_iterations;
+    std::vector<int32_t> job_roots((size_t)R);
+    for (int j = 0; j < R; j++) job_roots[j] = j;
+    std::vector<uint64_t> seeds((size_t)NI);
+    for (int it = 0; it < NI; it++) seeds[it] = 1000ull * generation + (uint64_t)it; /* stands for Hash(gen) ^ Hash(it) */
+    tpgx_episode_request req = b->req;
+    req.nb_jobs = R; req.roots_per_job = 1; req.job_roots = job_roots.data(); req.seeds = seeds.data(); req.trace_steps = 0;
+    const size_t cap = (size_t)std::max(1, archive_size);
+    std::vector<int32_t> job(cap), iteration(cap), step(cap);
+    tpgx_archive_request ar{archive_seed, probability, archive_size, 0};
+    tpgx_episode_result ev{};
+    ev.score = scores;
+    tpgx_episode_archive_result out{rec_program, job.data(), iteration.data(), step.data(), rec_bid, rec_obs, obs_len, 0};
+    st = tpgx_archive_episodes(b->ctx, &req, &ar, &ev, &out);
+    *nb_records = out.nb_records;
+    return st;
+}
+tpgx_status epbe_execute(void* user, const tpgx_graph* g, int64_t count, const double* obs, int32_t obs_len, double* bid) {
+    EpBackend* b = static_cast<EpBackend*>(user);
+    tpgx_status st = tpgx_set_graph(b->ctx, g);
+    if (st != TPGX_OK) return st;
+    const std::vector<tpgx_source_desc>& src = b->ctx->src;
+    std::vector<std::vector<double>> f(src.size());
+    std::vector<std::vector<int32_t>> iv(src.size());
+    const double* pf[2] = {nullptr, nullptr};
+    const int32_t* pi[2] = {nullptr, nullptr};
+    int col = 0;
+    for (size_t k = 0; k < src.size(); k++) {
+        const int sp = src[k].height * src[k].width;
+        if (col + sp > obs_len) return fail(b->ctx, TPGX_ERR_BAD_ARG, "observation rows shorter than the data sources");
+        if (src[k].elem == TPGX_ELEM_F64) {
+            f[k].resize((size_t)count * sp);
+            for (int64_t i = 0; i < count; i++) for (int q = 0; q < sp; q++) f[k][(size_t)i * sp + q] = obs[(size_t)i * obs_len + col + q];
+            pf[k] = f[k].data();
+        } else {
+            iv[k].resize((size_t)count * sp);
+            for (int64_t i = 0; i < count; i++) for (int q = 0; q < sp; q++) iv[k][(size_t)i * sp + q] = (int32_t)obs[(size_t)i * obs_len + col + q];
+            pi[k] = iv[k].data();
+        }
+        col += sp;
+    }
+    return tpgx_execute_programs(b->ctx, count, pf, pi, bid);
+}
+} // namespace
+
+tpgx_status tpgx_train_backend_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_train_backend* out) {
+    if (!ctx || !req || !out) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_train_backend_episodes: null argument");
+    if (req->nb_iterations < 1 || req->max_actions < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_train_backend_episodes: bad request template");
+    EpBackend* b = new EpBackend{ctx, *req};
+    out->user = b;
+    out->evaluate = epbe_evaluate;
+    out->execute = epbe_execute;
+    return TPGX_OK;
+}
+void tpgx_train_backend_release(tpgx_train_backend* backend) {
+    if (!backend || backend->evaluate != epbe_evaluate) return;
+    delete static_cast<EpBackend*>(backend->user);
+    backend->user = nullptr;
+}
+
 tpgx_status tpgx_mnist_episode_indices(uint64_t seed, int32_t mode, int64_t dataset_size, int64_t nb_actions, int32_t* out) {
     if (!out || dataset_size < 1 || dataset_size > 0x7fffffff || nb_actions < 0 || mode < 0 || mode > 2) return TPGX_ERR_BAD_ARG;
     if (mode == 2) { /* TESTING: currentIndex = (currentIndex + 1) % size, starting from -1 */

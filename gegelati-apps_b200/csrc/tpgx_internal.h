@@ -159,6 +159,22 @@ static inline tpgx_op_info tpgx_get_op_info(int op) {
     }
 }
 
+/* Address space of handler `s` of [registers, constants iff nb_constants > 0, data sources...] for operand type `t`;
+ * 0 = the handler cannot provide it ([UP] DataHandler::getAddressSpace; PrimitiveTypeArray / Array2DWrapper rules,
+ * SURVEY.md App. F U6/U7). */
+static inline uint32_t tpgx_source_space(const tpgx_config& cfg, const std::vector<tpgx_source_desc>& src, int s, int t) {
+    if (s == 0) return t == TPGX_T_D ? (uint32_t)cfg.nb_registers : 0u;
+    const int first_env = cfg.nb_constants > 0 ? 2 : 1;
+    if (cfg.nb_constants > 0 && s == 1) return t == TPGX_T_C ? (uint32_t)cfg.nb_constants : 0u;
+    const int k = s - first_env;
+    if (k < 0 || k >= (int)src.size()) return 0u;
+    const tpgx_source_desc& d = src[k];
+    if (d.elem == TPGX_ELEM_I32) return (t == TPGX_T_I && !d.is_2d) ? (uint32_t)d.width : 0u;
+    if (t == TPGX_T_D) return (uint32_t)(d.height * d.width);
+    if (t == TPGX_T_W && d.is_2d && d.height >= 3 && d.width >= 3) return (uint32_t)((d.height - 2) * (d.width - 2));
+    return 0u;
+}
+
 /* Result of flattening a tpgx_graph for the device. */
 struct tpgx_flat_graph {
     int nb_programs = 0, nb_teams = 0, nb_edges = 0, nb_roots = 0;

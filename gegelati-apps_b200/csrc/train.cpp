@@ -1,0 +1,501 @@
+/*
+ * train.cpp — host generation loop around the GPU evaluator.
+ *
+ * Restates [UP] Learn::LearningAgent::{init, trainOneGeneration} as the apps call them
+ * ([REF] gridworld/src/main.cpp:33-34,57-65): initRandomTPG; per generation populateTPG -> evaluateAllRoots(TRAINING)
+ * -> decimateWorstRoots, with [UP] Mutator::TPGMutator / ProgramMutator operators driven by the params.json keys
+ * ([REF] gridworld/params.json:7-38).  The upstream library is not in /root/reference: the operators follow the
+ * published TPG algorithm (Kelly & Heywood 2017; GEGELATI, Desnos et al. 2021), not upstream's draw order.
+ * All evaluation and all program execution happen behind tpgx_train_backend (the GPU); this file is pure host policy:
+ * graph bookkeeping, mutation, selection, archive ring.
+ */
+#include <cmath>
+#include <cstring>
+#include <deque>
+#include <map>
+#include <random>
+
+#include "tpgx_internal.h"
+
+namespace {
+
+struct TProg {
+    std::vector<tpgx_line> lines;
+    double consts[TPGX_MAX_CONSTS] = {0};
+    int refs = 0;
+    bool alive = false;
+};
+struct TEdge { int prog, dest; /* dest >= 0: team id; < 0: action = -1 - dest */ };
+struct TTeam {
+    std::vector<TEdge> edges;
+    int incoming = 0;
+    bool alive = false;
+};
+struct ARec { int prog; double bid; std::vector<double> obs; };
+/* a program created by this populate: still to be mutated / behaviour-checked against its origin */
+struct NewProg { int id; std::vector<tpgx_line> parent_lines; double parent_consts[TPGX_MAX_CONSTS]; };
+
+} // namespace
+
+struct tpgx_trainer {
+    tpgx_config cfg{};
+    std::vector<int32_t> opcode;
+    std::vector<tpgx_source_desc> src;
+    tpgx_train_params P{};
+    std::mt19937_64 rng;
+    std::vector<TProg> progs;
+    std::vector<int> free_progs;
+    std::vector<TTeam> teams;
+    std::vector<int> free_teams;
+    std::vector<int> order;          /* alive teams in creation order: the graph's vertex / root iteration order */
+    std::deque<ARec> archive;
+    int obs_len = 0;
+    uint32_t max_loc = 1;
+    int nb_src_total = 0;
+    std::vector<std::vector<int>> providers; /* per operand type: the source indices that can provide it */
+    std::string err;
+    /* flattened view */
+    std::vector<int64_t> v_off;
+    std::vector<tpgx_line> v_lines;
+    std::vector<double> v_consts;
+    std::vector<int32_t> v_teo, v_ep, v_ed, v_roots;
+    std::vector<int> v_prog_id, v_root_team;
+
+    uint64_t u64(uint64_t lo, uint64_t hi) { return std::uniform_int_distribution<uint64_t>(lo, hi)(rng); } /* [UP] RNG::getUnsignedInt64 */
+    double dbl() { return std::uniform_real_distribution<double>(0.0, 1.0)(rng); }                          /* [UP] RNG::getDouble(0, 1) */
+
+    /* ---- bookkeeping ---- */
+    int new_prog() {
+        int id;
+        if (!free_progs.empty()) { id = free_progs.back(); free_progs.pop_back(); }
+        else { id = (int)progs.size(); progs.emplace_back(); }
+        progs[id] = TProg();
+        progs[id].alive = true;
+        return id;
+    }
+    void unref_prog(int id) {
+        if (--progs[id].refs > 0) return;
+        progs[id].alive = false;
+        progs[id].lines.clear();
+        free_progs.push_back(id);
+        /* [UP] the archive forgets the recordings of deleted programs */
+        for (size_t i = 0; i < archive.size();)
+            if (archive[i].prog == id) archive.erase(archive.begin() + (long)i); else i++;
+    }
+    int new_team() {
+        int id;
+        if (!free_teams.empty()) { id = free_teams.back(); free_teams.pop_back(); }
+        else { id = (int)teams.size(); teams.emplace_back(); }
+        teams[id] = TTeam();
+        teams[id].alive = true;
+        order.push_back(id);
+        return id;
+    }
+    void add_edge(int team, int prog, int dest) {
+        teams[team].edges.push_back({prog, dest});
+        progs[prog].refs++;
+        if (dest >= 0) teams[dest].incoming++;
+    }
+    void remove_edge(int team, size_t idx) {
+        const TEdge e = teams[team].edges[idx];
+        teams[team].edges.erase(teams[team].edges.begin() + (long)idx);
+        if (e.dest >= 0) teams[e.dest].incoming--;
+        unref_prog(e.prog);
+    }
+    void remove_team(int team) {
+        while (!teams[team].edges.empty()) remove_edge(team, teams[team].edges.size() - 1);
+        teams[team].alive = false;
+        order.erase(std::find(order.begin(), order.end(), team));
+        free_teams.push_back(team);
+    }
+    int nb_action_edges(int team) const {
+        int n = 0;
+        for (const TEdge& e : teams[team].edges) n += e.dest < 0;
+        return n;
+    }
+    std::vector<int> roots() const {
+        std::vector<int> r;
+        for (int t : order) if (teams[t].incoming == 0) r.push_back(t);
+        return r;
+    }
+
+    /* ---- [UP] ProgramMutator ---- */
+    tpgx_line random_line() {
+        tpgx_line l{};
+        l.instruction = (uint32_t)u64(0, opcode.size() - 1);
+        l.destination = (uint32_t)u64(0, (uint64_t)cfg.nb_registers - 1);
+        const tpgx_op_info oi = tpgx_get_op_info(opcode[l.instruction]);
+        for (int k = 0; k < 2; k++) {
+            const int t = k < oi.nb_operands ? oi.type[k] : TPGX_T_D;
+            const std::vector<int>& pv = providers[t];
+            l.src[k] = (uint32_t)pv[u64(0, pv.size() - 1)];
+            l.loc[k] = (uint32_t)u64(0, max_loc - 1);
+        }
+        return l;
+    }
+    void alter_line(tpgx_line& l) {
+        /* re-draw one of: instruction, destination, operand 0, operand 1; the operands are re-validated against the
+           (possibly new) instruction's operand types */
+        const uint64_t what = u64(0, 3);
+        if (what == 0) l.instruction = (uint32_t)u64(0, opcode.size() - 1);
+        else if (what == 1) l.destination = (uint32_t)u64(0, (uint64_t)cfg.nb_registers - 1);
+        const tpgx_op_info oi = tpgx_get_op_info(opcode[l.instruction]);
+        for (int k = 0; k < 2; k++) {
+            const int t = k < oi.nb_operands ? oi.type[k] : TPGX_T_D;
+            const std::vector<int>& pv = providers[t];
+            const bool redraw = (what == (uint64_t)(2 + k)) || std::find(pv.begin(), pv.end(), (int)l.src[k]) == pv.end();
+            if (redraw) { l.src[k] = (uint32_t)pv[u64(0, pv.size() - 1)]; l.loc[k] = (uint32_t)u64(0, max_loc - 1); }
+        }
+    }
+    void mutate_program(TProg& p) {
+        bool any = false;
+        do {
+            if (p.lines.size() > 1 && dbl() < P.p_delete) { p.lines.erase(p.lines.begin() + (long)u64(0, p.lines.size() - 1)); any = true; }
+            if ((int)p.lines.size() < P.max_program_size && dbl() < P.p_add) { p.lines.insert(p.lines.begin() + (long)u64(0, p.lines.size()), random_line()); any = true; }
+            if (!p.lines.empty() && dbl() < P.p_mutate) { alter_line(p.lines[u64(0, p.lines.size() - 1)]); any = true; }
+            if (p.lines.size() > 1 && dbl() < P.p_swap) {
+                const size_t a = u64(0, p.lines.size() - 1);
+                size_t b = u64(0, p.lines.size() - 2);
+                if (b >= a) b++;
+                std::swap(p.lines[a], p.lines[b]);
+                any = true;
+            }
+            for (int c = 0; c < cfg.nb_constants; c++)
+                if (dbl() < P.p_constant_mutation) {
+                    p.consts[c] = (double)((int64_t)u64(0, (uint64_t)(P.max_const_value - P.min_const_value)) + P.min_const_value);
+                    any = true;
+                }
+        } while (!any);
+    }
+
+    /* ---- [UP] TPGMutator ---- */
+    void init_random_tpg() {
+        const int nA = P.nb_actions;
+        std::vector<int> made;
+        for (int i = 0; i < nA; i++) {
+            const int t = new_team();
+            for (int k = 0; k < 2; k++) { /* two edges to two different actions */
+                const int p = new_prog();
+                progs[p].lines.push_back(random_line());
+                for (int c = 0; c < cfg.nb_constants; c++)
+                    progs[p].consts[c] = (double)((int64_t)u64(0, (uint64_t)(P.max_const_value - P.min_const_value)) + P.min_const_value);
+                mutate_program(progs[p]);
+                add_edge(t, p, -1 - ((i + k) % nA));
+                made.push_back(p);
+            }
+        }
+        /* extra initial edges, sharing the programs made above, up to maxInitOutgoingEdges */
+        for (int t : std::vector<int>(order)) {
+            const int extra = P.max_init_outgoing_edges > 2 ? (int)u64(0, (uint64_t)P.max_init_outgoing_edges - 2) : 0;
+            for (int x = 0; x < extra; x++) {
+                const int p = made[u64(0, made.size() - 1)];
+                bool has = false;
+                for (const TEdge& e : teams[t].edges) has |= e.prog == p;
+                if (!has) add_edge(t, p, -1 - (int)u64(0, (uint64_t)nA - 1));
+            }
+        }
+    }
+    void mutate_team(int team, const std::vector<TEdge>& pre_edges, const std::vector<int>& pre_teams, std::vector<NewProg>& fresh) {
+        TTeam& T = teams[team];
+        while (T.edges.size() > 2 && dbl() < P.p_edge_deletion) {
+            size_t idx = u64(0, T.edges.size() - 1);
+            if (T.edges[idx].dest < 0 && nb_action_edges(team) == 1) { /* a team always keeps an action edge */
+                size_t other = u64(0, T.edges.size() - 2);
+                idx = other >= idx ? other + 1 : other;
+            }
+            remove_edge(team, idx);
+        }
+        while ((int)T.edges.size() < P.max_outgoing_edges && dbl() < P.p_edge_addition) {
+            std::vector<size_t> cand;
+            for (size_t i = 0; i < pre_edges.size(); i++) {
+                bool has = !progs[pre_edges[i].prog].alive || (pre_edges[i].dest >= 0 && !teams[pre_edges[i].dest].alive);
+                for (const TEdge& e : T.edges) has |= e.prog == pre_edges[i].prog;
+                if (!has) cand.push_back(i);
+            }
+            if (cand.empty()) break;
+            const TEdge& e = pre_edges[cand[u64(0, cand.size() - 1)]];
+            add_edge(team, e.prog, e.dest);
+        }
+        bool any = false;
+        do {
+            for (size_t i = 0; i < T.edges.size(); i++) {
+                if (!(dbl() < P.p_program_mutation)) continue;
+                any = true;
+                const int old = T.edges[i].prog;
+                const int np = new_prog();
+                progs[np].lines = progs[old].lines;
+                std::memcpy(progs[np].consts, progs[old].consts, sizeof progs[np].consts);
+                progs[np].refs = 1;
+                NewProg rec;
+                rec.id = np;
+                rec.parent_lines = progs[old].lines;
+                std::memcpy(rec.parent_consts, progs[old].consts, sizeof rec.parent_consts);
+                fresh.push_back(rec);
+                T.edges[i].prog = np;
+                unref_prog(old);
+                if (dbl() < P.p_edge_destination_change) {
+                    const bool only_action = T.edges[i].dest < 0 && nb_action_edges(team) == 1;
+                    int dest;
+                    if (only_action || pre_teams.empty() || dbl() < P.p_edge_destination_is_action) dest = -1 - (int)u64(0, (uint64_t)P.nb_actions - 1);
+                    else dest = pre_teams[u64(0, pre_teams.size() - 1)];
+                    if (T.edges[i].dest >= 0) teams[T.edges[i].dest].incoming--;
+                    T.edges[i].dest = dest;
+                    if (dest >= 0) teams[dest].incoming++;
+                }
+            }
+        } while (!any);
+    }
+
+    /* ---- view in the C ABI's layout ---- */
+    void build_view(tpgx_graph* g) {
+        std::vector<int> pidx(progs.size(), -1);
+        v_prog_id.clear();
+        for (size_t p = 0; p < progs.size(); p++)
+            if (progs[p].alive && progs[p].refs > 0) { pidx[p] = (int)v_prog_id.size(); v_prog_id.push_back((int)p); }
+        const int nP = (int)v_prog_id.size(), nC = cfg.nb_constants;
+        v_off.assign((size_t)nP + 1, 0);
+        v_lines.clear();
+        v_consts.assign((size_t)nP * (size_t)std::max(1, nC), 0.0);
+        for (int i = 0; i < nP; i++) {
+            const TProg& p = progs[v_prog_id[i]];
+            v_lines.insert(v_lines.end(), p.lines.begin(), p.lines.end());
+            v_off[i + 1] = (int64_t)v_lines.size();
+            for (int c = 0; c < nC; c++) v_consts[(size_t)i * nC + c] = p.consts[c];
+        }
+        std::vector<int> tidx(teams.size(), -1);
+        for (size_t i = 0; i < order.size(); i++) tidx[order[i]] = (int)i;
+        v_teo.assign(1, 0);
+        v_ep.clear(); v_ed.clear(); v_roots.clear(); v_root_team.clear();
+        for (int t : order) {
+            for (const TEdge& e : teams[t].edges) { v_ep.push_back(pidx[e.prog]); v_ed.push_back(e.dest >= 0 ? tidx[e.dest] : e.dest); }
+            v_teo.push_back((int32_t)v_ep.size());
+            if (teams[t].incoming == 0) { v_roots.push_back(tidx[t]); v_root_team.push_back(t); }
+        }
+        g->nb_programs = nP;
+        g->program_line_offset = v_off.data();
+        g->lines = v_lines.data();
+        g->intron = nullptr;
+        g->constants = nC > 0 ? v_consts.data() : nullptr;
+        g->nb_teams = (int32_t)order.size();
+        g->team_edge_offset = v_teo.data();
+        g->edge_program = v_ep.data();
+        g->edge_destination = v_ed.data();
+        g->nb_roots = (int32_t)v_roots.size();
+        g->root_team = v_roots.data();
+    }
+
+    /* ---- [UP] mutateNewProgramBehaviors: mutate every new program; with forceProgramBehaviorChangeOnMutation, again
+       until it behaves differently from its origin and from every archived program on the archived observations ---- */
+    tpgx_status settle_new_programs(std::vector<NewProg>& fresh, const tpgx_train_backend* be, int* retries) {
+        for (NewProg& n : fresh) mutate_program(progs[n.id]);
+        if (!P.force_program_behavior_change || archive.empty() || fresh.empty()) return TPGX_OK;
+        if (!be || !be->execute) { err = "forceProgramBehaviorChangeOnMutation needs a backend to run the new programs on the archive"; return TPGX_ERR_BAD_ARG; }
+        const int64_t count = (int64_t)archive.size();
+        std::vector<double> obs((size_t)count * obs_len);
+        std::map<int, std::vector<int>> by_prog;
+        for (int64_t i = 0; i < count; i++) {
+            std::memcpy(obs.data() + (size_t)i * obs_len, archive[(size_t)i].obs.data(), (size_t)obs_len * 8);
+            by_prog[archive[(size_t)i].prog].push_back((int)i);
+        }
+        const double tau = 1e-4; /* [UP] Archive::areProgramResultsUnique default tolerance */
+        auto close = [&](double a, double b) { return a == b || std::fabs(a - b) <= tau; };
+        std::vector<size_t> pending(fresh.size());
+        for (size_t i = 0; i < fresh.size(); i++) pending[i] = i;
+        for (int round = 0; round < 16 && !pending.empty(); round++) {
+            /* a scratch graph: [mutant, origin] per pending program, one team pointing at all of them */
+            const int M = (int)pending.size(), nC = cfg.nb_constants;
+            std::vector<int64_t> off(1, 0);
+            std::vector<tpgx_line> lines;
+            std::vector<double> consts((size_t)2 * M * (size_t)std::max(1, nC), 0.0);
+            std::vector<int32_t> teo = {0, 2 * M}, ep((size_t)2 * M), ed((size_t)2 * M, -1), root = {0};
+            for (int i = 0; i < M; i++) {
+                const NewProg& n = fresh[pending[i]];
+                const TProg& mp = progs[n.id];
+                lines.insert(lines.end(), mp.lines.begin(), mp.lines.end());
+                off.push_back((int64_t)lines.size());
+                lines.insert(lines.end(), n.parent_lines.begin(), n.parent_lines.end());
+                off.push_back((int64_t)lines.size());
+                for (int c = 0; c < nC; c++) { consts[(size_t)(2 * i) * nC + c] = mp.consts[c]; consts[(size_t)(2 * i + 1) * nC + c] = n.parent_consts[c]; }
+                ep[2 * i] = 2 * i; ep[2 * i + 1] = 2 * i + 1;
+            }
+            tpgx_graph g{2 * M, off.data(), lines.data(), nullptr, nC > 0 ? consts.data() : nullptr, 1, teo.data(), ep.data(), ed.data(), 1, root.data()};
+            std::vector<double> bid((size_t)2 * M * (size_t)count);
+            const tpgx_status st = be->execute(be->user, &g, count, obs.data(), obs_len, bid.data());
+            if (st != TPGX_OK) { err = "backend execute failed"; return st; }
+            std::vector<size_t> again;
+            for (int i = 0; i < M; i++) {
+                const double* bm = bid.data() + (size_t)(2 * i) * count;
+                const double* bp = bm + count;
+                bool differs = false;
+                for (int64_t k = 0; k < count && !differs; k++) differs = !close(bm[k], bp[k]);
+                bool unique = differs;
+                for (auto it = by_prog.begin(); unique && it != by_prog.end(); ++it) {
+                    bool same = true;
+                    for (int k : it->second) if (!close(bm[k], archive[(size_t)k].bid)) { same = false; break; }
+                    unique = !same;
+                }
+                if (!unique) { mutate_program(progs[fresh[pending[i]].id]); again.push_back(pending[i]); (*retries)++; }
+            }
+            pending.swap(again);
+        }
+        return TPGX_OK;
+    }
+};
+
+/* ================================================================================================ C ABI */
+extern "C" {
+
+tpgx_status tpgx_trainer_create(const tpgx_config* cfg, int32_t nb_instructions, const int32_t* opcode, int32_t nb_sources,
+                                const tpgx_source_desc* sources, const tpgx_train_params* params, uint64_t seed, tpgx_trainer** out) {
+    if (!cfg || !opcode || nb_instructions < 1 || !sources || nb_sources < 1 || nb_sources > 2 || !params || !out) return TPGX_ERR_BAD_ARG;
+    if (cfg->nb_registers < 1 || cfg->nb_registers > TPGX_MAX_REGS || cfg->nb_constants < 0 || cfg->nb_constants > TPGX_MAX_CONSTS) return TPGX_ERR_UNSUPPORTED;
+    const tpgx_train_params& P = *params;
+    if (P.nb_actions < 2 || P.nb_actions > 128 || P.nb_roots < P.nb_actions || P.max_outgoing_edges < 2 || P.max_init_outgoing_edges < 2 ||
+        P.max_init_outgoing_edges > P.max_outgoing_edges || P.max_program_size < 1 || P.max_const_value < P.min_const_value ||
+        !(P.ratio_deleted_roots >= 0.0 && P.ratio_deleted_roots < 1.0) || P.archive_size < 0)
+        return TPGX_ERR_BAD_ARG;
+    for (int i = 0; i < nb_instructions; i++)
+        if (opcode[i] < 0 || opcode[i] >= TPGX_OP_COUNT) return TPGX_ERR_UNSUPPORTED;
+    tpgx_trainer* t = new tpgx_trainer();
+    t->cfg = *cfg;
+    t->opcode.assign(opcode, opcode + nb_instructions);
+    t->src.assign(sources, sources + nb_sources);
+    t->P = P;
+    t->rng.seed(seed);
+    t->nb_src_total = (cfg->nb_constants > 0 ? 2 : 1) + nb_sources;
+    t->providers.assign(TPGX_T_W + 1, std::vector<int>());
+    for (int ty = 0; ty <= TPGX_T_W; ty++)
+        for (int s = 0; s < t->nb_src_total; s++) {
+            const uint32_t sp = tpgx_source_space(t->cfg, t->src, s, ty);
+            if (sp) { t->providers[ty].push_back(s); t->max_loc = std::max(t->max_loc, sp); }
+        }
+    for (int i = 0; i < nb_instructions; i++) { /* every instruction must be satisfiable, else random lines cannot be valid */
+        const tpgx_op_info oi = tpgx_get_op_info(opcode[i]);
+        for (int k = 0; k < oi.nb_operands; k++)
+            if (t->providers[oi.type[k]].empty()) { delete t; return TPGX_ERR_UNSUPPORTED; }
+    }
+    for (const tpgx_source_desc& d : t->src) t->obs_len += d.height * d.width;
+    t->init_random_tpg();
+    *out = t;
+    return TPGX_OK;
+}
+
+void tpgx_trainer_destroy(tpgx_trainer* t) { delete t; }
+const char* tpgx_trainer_last_error(const tpgx_trainer* t) { return t ? t->err.c_str() : "null trainer"; }
+
+tpgx_status tpgx_trainer_graph(tpgx_trainer* t, tpgx_graph* view) {
+    if (!t || !view) return TPGX_ERR_BAD_ARG;
+    t->build_view(view);
+    return TPGX_OK;
+}
+
+static void fill_graph_stats(tpgx_trainer* t, tpgx_train_stats* s) {
+    if (!s) return;
+    int np = 0;
+    for (const TProg& p : t->progs) np += p.alive && p.refs > 0;
+    s->nb_teams = (int32_t)t->order.size();
+    s->nb_programs = np;
+    s->nb_roots = (int32_t)t->roots().size();
+    s->archive_records = (int32_t)t->archive.size();
+}
+
+tpgx_status tpgx_trainer_populate(tpgx_trainer* t, const tpgx_train_backend* backend, tpgx_train_stats* stats) {
+    if (!t) return TPGX_ERR_BAD_ARG;
+    /* [UP] populateTPG: the roots present now are the parents; edges and teams present now are what mutations may reuse */
+    const std::vector<int> parents = t->roots();
+    if (parents.empty()) { t->err = "no root left to clone"; return TPGX_ERR_GRAPH_INVALID; }
+    std::vector<TEdge> pre_edges;
+    for (int tm : t->order) for (const TEdge& e : t->teams[tm].edges) pre_edges.push_back(e);
+    const std::vector<int> pre_teams = t->order;
+    std::vector<NewProg> fresh;
+    int nb_roots = (int)parents.size();
+    while (nb_roots < t->P.nb_roots) {
+        const int parent = parents[t->u64(0, parents.size() - 1)];
+        const int child = t->new_team();
+        for (const TEdge e : std::vector<TEdge>(t->teams[parent].edges)) t->add_edge(child, e.prog, e.dest);
+        t->mutate_team(child, pre_edges, pre_teams, fresh);
+        nb_roots = (int)t->roots().size(); /* a destination change may have turned a parent into an inner team */
+    }
+    /* programs created and dropped again within this populate are gone already */
+    std::vector<NewProg> live;
+    for (NewProg& n : fresh) if (t->progs[n.id].alive && t->progs[n.id].refs > 0) live.push_back(std::move(n));
+    int retries = 0;
+    const tpgx_status st = t->settle_new_programs(live, backend, &retries);
+    if (st != TPGX_OK) return st;
+    if (stats) { fill_graph_stats(t, stats); stats->nb_new_programs = (int32_t)live.size(); stats->behaviour_retries = retries; }
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_trainer_decimate(tpgx_trainer* t, const double* root_scores, tpgx_train_stats* stats) {
+    if (!t || !root_scores) return TPGX_ERR_BAD_ARG;
+    const std::vector<int> roots = t->roots();
+    /* [UP] decimateWorstRoots: the floor(ratioDeletedRoots * nbRoots) lowest-scored roots go; equal scores keep root order */
+    std::vector<int> idx(roots.size());
+    for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return root_scores[a] < root_scores[b]; });
+    int kill = (int)std::floor(t->P.ratio_deleted_roots * (double)t->P.nb_roots);
+    kill = std::min(kill, (int)roots.size() - 1);
+    for (int i = 0; i < kill; i++) t->remove_team(roots[idx[i]]);
+    if (stats) {
+        fill_graph_stats(t, stats);
+        stats->nb_removed_roots = kill;
+        double best = -INFINITY, worst = INFINITY, sum = 0.0;
+        for (size_t i = 0; i < roots.size(); i++) { best = std::max(best, root_scores[i]); worst = std::min(worst, root_scores[i]); sum += root_scores[i]; }
+        stats->best_score = best; stats->worst_score = worst; stats->mean_score = sum / (double)roots.size();
+    }
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_backend* be, uint64_t generation, tpgx_train_stats* stats) {
+    if (!t || !be || !be->evaluate) return TPGX_ERR_BAD_ARG;
+    tpgx_train_stats s{};
+    tpgx_status st = tpgx_trainer_populate(t, be, &s);
+    if (st != TPGX_OK) return st;
+    tpgx_graph g{};
+    t->build_view(&g);
+    const int R = g.nb_roots, cap = t->P.archive_size;
+    std::vector<uint64_t> aseed((size_t)R);
+    for (int j = 0; j < R; j++) aseed[j] = t->u64(0, UINT64_MAX); /* [UP] Job::archiveSeed drawn from the agent's RNG */
+    std::vector<double> scores((size_t)R, 0.0), rbid((size_t)std::max(1, cap)), robs((size_t)std::max(1, cap) * (size_t)std::max(1, t->obs_len));
+    std::vector<int32_t> rprog((size_t)std::max(1, cap));
+    int32_t nrec = 0;
+    st = be->evaluate(be->user, &g, generation, aseed.data(), t->P.archiving_probability, cap, scores.data(), rprog.data(), rbid.data(), robs.data(), t->obs_len, &nrec);
+    if (st != TPGX_OK) { t->err = "backend evaluate failed"; return st; }
+    for (int i = 0; i < nrec; i++) {
+        ARec r;
+        r.prog = t->v_prog_id[rprog[i]];
+        r.bid = rbid[i];
+        r.obs.assign(robs.begin() + (long)i * t->obs_len, robs.begin() + (long)(i + 1) * t->obs_len);
+        t->archive.push_back(std::move(r));
+    }
+    while ((int)t->archive.size() > cap) t->archive.pop_front();
+    tpgx_train_stats d{};
+    st = tpgx_trainer_decimate(t, scores.data(), &d);
+    if (st != TPGX_OK) return st;
+    if (stats) {
+        *stats = d;
+        stats->nb_new_programs = s.nb_new_programs;
+        stats->behaviour_retries = s.behaviour_retries;
+        stats->nb_roots = R; stats->nb_teams = s.nb_teams; stats->nb_programs = s.nb_programs; /* sizes as evaluated */
+    }
+    return TPGX_OK;
+}
+
+uint64_t tpgx_trainer_fingerprint(const tpgx_trainer* t) {
+    if (!t) return 0;
+    uint64_t h = 1469598103934665603ull;
+    auto mix = [&](uint64_t v) { for (int i = 0; i < 8; i++) { h ^= (v >> (8 * i)) & 0xff; h *= 1099511628211ull; } };
+    for (int tm : t->order) {
+        mix(0xfeedull + (uint64_t)tm);
+        for (const TEdge& e : t->teams[tm].edges) {
+            mix((uint64_t)(int64_t)e.dest);
+            const TProg& p = t->progs[e.prog];
+            mix(p.lines.size());
+            for (const tpgx_line& l : p.lines) { mix(l.instruction | ((uint64_t)l.destination << 32)); mix(l.src[0] | ((uint64_t)l.loc[0] << 32)); mix(l.src[1] | ((uint64_t)l.loc[1] << 32)); }
+            for (int c = 0; c < t->cfg.nb_constants; c++) { uint64_t b; std::memcpy(&b, &p.consts[c], 8); mix(b); }
+        }
+    }
+    return h;
+}
+
+} /* extern "C" */

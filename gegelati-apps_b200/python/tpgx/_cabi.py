@@ -92,3 +92,32 @@ class EpisodeResult(C.Structure):
     _fields_ = [("score", C.c_void_p), ("episode_score", C.c_void_p), ("episode_actions", C.c_void_p),
                 ("trace", C.c_void_p), ("final_state", C.c_void_p), ("counters", C.POINTER(Counters)),
                 ("device_ms", C.c_void_p)]
+
+
+class TrainParams(C.Structure):
+    _fields_ = [("nb_actions", C.c_int32), ("nb_roots", C.c_int32), ("max_init_outgoing_edges", C.c_int32), ("max_outgoing_edges", C.c_int32),
+                ("p_edge_deletion", C.c_double), ("p_edge_addition", C.c_double), ("p_program_mutation", C.c_double),
+                ("p_edge_destination_change", C.c_double), ("p_edge_destination_is_action", C.c_double),
+                ("force_program_behavior_change", C.c_int32), ("max_program_size", C.c_int32),
+                ("p_delete", C.c_double), ("p_add", C.c_double), ("p_mutate", C.c_double), ("p_swap", C.c_double), ("p_constant_mutation", C.c_double),
+                ("min_const_value", C.c_int32), ("max_const_value", C.c_int32), ("ratio_deleted_roots", C.c_double),
+                ("archive_size", C.c_int32), ("reserved", C.c_int32), ("archiving_probability", C.c_double)]
+
+
+EVALUATE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Graph), C.c_uint64, C.POINTER(C.c_uint64), C.c_double, C.c_int32,
+                          C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32,
+                          C.POINTER(C.c_int32))
+EXECUTE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Graph), C.c_int64, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double))
+
+
+class TrainBackend(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("evaluate", EVALUATE_FN), ("execute", EXECUTE_FN)]
+
+
+class TrainStats(C.Structure):
+    _fields_ = [("nb_teams", C.c_int32), ("nb_programs", C.c_int32), ("nb_roots", C.c_int32), ("nb_new_programs", C.c_int32),
+                ("nb_removed_roots", C.c_int32), ("archive_records", C.c_int32), ("behaviour_retries", C.c_int32), ("reserved", C.c_int32),
+                ("best_score", C.c_double), ("mean_score", C.c_double), ("worst_score", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -296,6 +296,80 @@ typedef struct {
 tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, const tpgx_archive_request* arch,
                                   tpgx_episode_result* eval_out, tpgx_episode_archive_result* out);
 
+/* ---- host generation loop ------------------------------------------------------
+ * Learn::LearningAgent::{init, trainOneGeneration} as the apps drive it ([REF] gridworld/src/main.cpp:33-34,57-65;
+ * pendulum/src/Learn/main.cpp:38-39,83): initRandomTPG, then per generation populateTPG (clone + mutate roots up to
+ * nbRoots, mutate the new programs until their behaviour changes against the archive) -> evaluateAllRoots in TRAINING
+ * mode (scores + archive side effect) -> decimateWorstRoots.  The mutation operators are [UP] Mutator::TPGMutator /
+ * ProgramMutator restated from the published algorithm with the params.json keys below; the library's exact draw order
+ * is not in /root/reference, so graphs evolve like the reference's but not draw for draw ("parity unpinned",
+ * DESIGN.md §5).  What IS exact: with the same trainer seed the loop is deterministic, and it depends on the evaluator
+ * only through scores and archive records, which the GPU backend reproduces bit for bit — so the elite / mutation
+ * sequence with the GPU evaluator equals the one with the CPU oracle (tests/test_gpu_trainer.py).
+ * Evaluation and program execution go through a backend of two callbacks; tpgx_train_backend_episodes fills it with the
+ * GPU implementation for the sequential environments.  There is no CPU backend in the library.                       */
+typedef struct {
+    int32_t nb_actions;                /* LearningEnvironment::getNbActions()                                       */
+    int32_t nb_roots;                  /* mutation.tpg.nbRoots                                                      */
+    int32_t max_init_outgoing_edges;   /* mutation.tpg.maxInitOutgoingEdges                                         */
+    int32_t max_outgoing_edges;        /* mutation.tpg.maxOutgoingEdges                                             */
+    double p_edge_deletion, p_edge_addition, p_program_mutation, p_edge_destination_change, p_edge_destination_is_action;
+    int32_t force_program_behavior_change; /* mutation.tpg.forceProgramBehaviorChangeOnMutation                     */
+    int32_t max_program_size;          /* mutation.prog.maxProgramSize                                              */
+    double p_delete, p_add, p_mutate, p_swap, p_constant_mutation;
+    int32_t min_const_value, max_const_value;
+    double ratio_deleted_roots;        /* ratioDeletedRoots                                                         */
+    int32_t archive_size;              /* archiveSize                                                               */
+    int32_t reserved;
+    double archiving_probability;      /* archivingProbability                                                      */
+} tpgx_train_params;
+
+typedef struct {
+    void* user;
+    /* evaluateAllRoots(generation, TRAINING) of graph g, job j = root j: scores[nb_roots]; archive side effect with one
+       Archive per job seeded archive_seed[j]: <= archive_size records (program id in g, bid, observation row of obs_len
+       doubles) in archive order.  Returns a tpgx_status.                                                            */
+    tpgx_status (*evaluate)(void* user, const tpgx_graph* g, uint64_t generation, const uint64_t* archive_seed, double probability,
+                            int32_t archive_size, double* scores, int32_t* rec_program, double* rec_bid, double* rec_obs,
+                            int32_t obs_len, int32_t* nb_records);
+    /* bid[nb_programs][count] of every program of g on `count` observation rows (obs_len doubles each)             */
+    tpgx_status (*execute)(void* user, const tpgx_graph* g, int64_t count, const double* obs, int32_t obs_len, double* bid);
+} tpgx_train_backend;
+
+typedef struct {
+    int32_t nb_teams, nb_programs, nb_roots, nb_new_programs; /* after populate                                      */
+    int32_t nb_removed_roots, archive_records, behaviour_retries, reserved;
+    double best_score, mean_score, worst_score;              /* over the evaluated roots                             */
+} tpgx_train_stats;
+
+typedef struct tpgx_trainer tpgx_trainer;
+/* [UP] LearningAgent::init(seed): RNG seeded, initRandomTPG.  obs_len = values per archived observation row (sum of
+ * the data sources' address spaces).  Instruction table and data sources as for a context.                         */
+tpgx_status tpgx_trainer_create(const tpgx_config* cfg, int32_t nb_instructions, const int32_t* opcode, int32_t nb_sources,
+                                const tpgx_source_desc* sources, const tpgx_train_params* params, uint64_t seed,
+                                tpgx_trainer** out);
+void tpgx_trainer_destroy(tpgx_trainer* t);
+const char* tpgx_trainer_last_error(const tpgx_trainer* t);
+/* The current graph in the C ABI's layout (roots in creation order); pointers stay valid until the next call that
+ * changes the trainer.                                                                                              */
+tpgx_status tpgx_trainer_graph(tpgx_trainer* t, tpgx_graph* view);
+/* [UP] LearningAgent::trainOneGeneration(generation) through the backend.                                          */
+tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_backend* backend, uint64_t generation,
+                                          tpgx_train_stats* stats);
+/* The three steps on their own (tests, custom loops): populate needs the backend only for the behaviour-change test
+ * (may be NULL when force_program_behavior_change is 0 or the archive is empty).                                    */
+tpgx_status tpgx_trainer_populate(tpgx_trainer* t, const tpgx_train_backend* backend, tpgx_train_stats* stats);
+tpgx_status tpgx_trainer_decimate(tpgx_trainer* t, const double* root_scores, tpgx_train_stats* stats);
+/* 64-bit fingerprint of the graph (teams, edges, programs, constants): equal fingerprints <=> same evolution so far */
+uint64_t tpgx_trainer_fingerprint(const tpgx_trainer* t);
+/* GPU backend for the sequential environments: evaluate = tpgx_set_graph + tpgx_archive_episodes with the request
+ * template `req` (nb_jobs / job_roots / seeds are filled per generation: job j = root j, iteration seeds
+ * 1000 * generation + it — SURVEY.md §8d, the real Data::Hash is upstream), execute = tpgx_set_graph +
+ * tpgx_execute_programs.  The backend borrows ctx and req (and req->pendulum_actions); free with
+ * tpgx_train_backend_release.                                                                                       */
+tpgx_status tpgx_train_backend_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_train_backend* out);
+void tpgx_train_backend_release(tpgx_train_backend* backend);
+
 /* Direct access to single engine steps (used by parity tests; replaces
  * [UP] ProgramExecutionEngine::executeProgram on an explicit observation batch):
  * obs_f64 / obs_i32 are [count][address space] per source (NULL if absent); bid is [P][count].     */

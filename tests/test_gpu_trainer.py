@@ -1,0 +1,50 @@
+"""Host generation loop with the GPU backend (tpgx_train_backend_episodes) vs the same loop with the CPU oracle behind the
+backend callbacks: scores and archive records are bit-identical, so the whole evolution — populate, behaviour test against
+the archive, selection — is identical generation by generation (north_star: "the resulting elite/mutation sequence")."""
+import numpy as np
+import pytest
+
+import tpgx
+from tpgx import abi as A
+from test_trainer_cpu import GRID
+from trainer_util import oracle_backend
+
+pytestmark = pytest.mark.gpu
+PEND_ACTIONS = [0.05, 0.1, 0.2, 0.4, 0.6, 0.8, 1.0]  # [REF] pendulum/src/Learn/main.cpp:33
+
+
+def run_pair(oracle_mod, app, generations, nb_iterations, max_actions, seed, second_player_random=0, pendulum_actions=None, **over):
+    p = dict(GRID, nb_actions=tpgx.APP_ACTIONS[app], **over)
+    nc = tpgx.APP_CONSTANTS[app]
+    mk = lambda: tpgx.Trainer(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], p, nb_constants=nc, seed=seed)
+    t_gpu, t_cpu = mk(), mk()
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], nb_constants=nc)
+    be_gpu = tpgx.episodes_backend(ev, tpgx.APP_ENV[app], nb_iterations, max_actions, second_player_random=second_player_random,
+                                   pendulum_actions=pendulum_actions)
+    be_cpu = oracle_backend(oracle_mod, app, nb_iterations, max_actions, second_player_random=second_player_random,
+                            pendulum_actions=pendulum_actions)
+    out = []
+    for gen in range(generations):
+        a, b = t_gpu.train_generation(be_gpu, gen), t_cpu.train_generation(be_cpu, gen)
+        assert a == b, (gen, a, b)
+        assert t_gpu.fingerprint() == t_cpu.fingerprint(), gen
+        out.append(a)
+    return out
+
+
+def test_gridworld_evolution_identical_and_learning(oracle_mod):
+    stats = run_pair(oracle_mod, "gridworld", generations=12, nb_iterations=1, max_actions=100, seed=2, nb_roots=60, archive_size=300)
+    assert max(s["best_score"] for s in stats) > 0.0
+    assert sum(s["behaviour_retries"] for s in stats) > 0, "the behaviour test against the archive ran on the GPU"
+
+
+def test_stickgame_evolution_identical(oracle_mod):
+    """int-typed data sources, random opponent, 20 iterations per job, no program constants."""
+    run_pair(oracle_mod, "stickgame", generations=5, nb_iterations=20, max_actions=11, seed=7, second_player_random=1, nb_roots=40,
+             archive_size=200, max_outgoing_edges=5, max_init_outgoing_edges=3, p_constant_mutation=0.0)
+
+
+def test_pendulum_evolution_identical(oracle_mod):
+    """libm-heavy environment: identical only because the GPU and the oracle share one libm sequence."""
+    run_pair(oracle_mod, "pendulum", generations=3, nb_iterations=2, max_actions=300, seed=9, pendulum_actions=PEND_ACTIONS, nb_roots=30,
+             archive_size=200, max_outgoing_edges=5, max_init_outgoing_edges=3)

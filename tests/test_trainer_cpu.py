@@ -1,0 +1,114 @@
+"""Host generation loop (include/tpgx.h tpgx_trainer_*) without a GPU: graph invariants of
+initRandomTPG / populateTPG / decimateWorstRoots, determinism, params.json loading, and — with the CPU oracle plugged into
+the backend callbacks (test infrastructure) — that training a gridworld policy actually learns."""
+import os
+
+import numpy as np
+import pytest
+
+import tpgx
+from tpgx import abi as A
+from trainer_util import SMALL, oracle_backend
+
+REF_PARAMS = "/root/reference/gridworld/params.json"
+# gridworld/params.json values (the file itself only exists in the build container)
+GRID = dict(nb_actions=4, nb_roots=500, max_init_outgoing_edges=4, max_outgoing_edges=10, p_edge_deletion=0.7, p_edge_addition=0.7,
+            p_program_mutation=0.2, p_edge_destination_change=0.1, p_edge_destination_is_action=0.5, force_program_behavior_change=1,
+            max_program_size=20, p_delete=0.5, p_add=0.5, p_mutate=1.0, p_swap=1.0, p_constant_mutation=0.5, min_const_value=-10,
+            max_const_value=10, ratio_deleted_roots=0.5, archive_size=2000, archiving_probability=0.01)
+
+
+def make(app="gridworld", seed=1, **over):
+    p = dict(GRID, nb_actions=tpgx.APP_ACTIONS[app], **over)
+    return tpgx.Trainer(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], p, nb_constants=tpgx.APP_CONSTANTS[app], seed=seed), p
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PARAMS), reason="reference tree not present")
+def test_params_json_of_the_app_loads_with_its_comments():
+    p = tpgx.load_params_json(REF_PARAMS, nb_actions=4)
+    for k, v in GRID.items():
+        assert p[k] == v, k
+    assert p["max_actions"] == 100 and p["nb_iterations"] == 1
+
+
+def check_invariants(g, p, app):
+    teo, ed, ep = g.team_edge_offset, g.edge_destination, g.edge_program
+    n_edges = np.diff(teo)
+    assert n_edges.min() >= 1 and n_edges.max() <= p["max_outgoing_edges"]
+    incoming = np.zeros(g.nb_teams, dtype=int)
+    for t in range(g.nb_teams):
+        dst = ed[teo[t]:teo[t + 1]]
+        assert (dst < 0).any(), "every team keeps an edge to an action"
+        assert dst.min() >= -p["nb_actions"]
+        assert (dst[dst >= 0] < t).all(), "edges only lead to older teams: the graph stays acyclic"
+        assert len(set(ep[teo[t]:teo[t + 1]].tolist())) == n_edges[t], "a team never holds the same program twice"
+        np.add.at(incoming, dst[dst >= 0], 1)
+    assert np.array_equal(np.flatnonzero(incoming == 0), g.root_team)
+    assert set(ep.tolist()) == set(range(g.nb_programs)), "no orphan program in the view"
+    assert np.diff(g.program_line_offset).min() >= 1 and np.diff(g.program_line_offset).max() <= p["max_program_size"]
+    # every line is executable: the flattener (what tpgx_set_graph runs) accepts the graph
+    tpgx.flatten_programs(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], g, nb_constants=tpgx.APP_CONSTANTS[app])
+
+
+@pytest.mark.parametrize("app", ["gridworld", "stickgame", "tictactoe", "pendulum"])
+def test_populate_and_decimate_keep_the_graph_valid(app):
+    tr, p = make(app, seed=3, nb_roots=120, force_program_behavior_change=0)
+    g = tr.graph()
+    assert g.nb_roots == g.nb_teams == p["nb_actions"]
+    rng = np.random.default_rng(0)
+    for gen in range(6):
+        s = tr.populate()
+        g = tr.graph()
+        assert g.nb_roots == 120 == s["nb_roots"]
+        check_invariants(g, p, app)
+        d = tr.decimate(rng.normal(size=g.nb_roots))
+        assert d["nb_removed_roots"] == 60
+        check_invariants(tr.graph(), p, app)
+
+
+def test_decimate_removes_the_lowest_scores_and_keeps_root_order_on_ties():
+    tr, p = make(seed=5, nb_roots=40, force_program_behavior_change=0)
+    tr.populate()
+    before = tr.graph()
+    scores = np.arange(40, dtype=np.float64)[::-1].copy()       # root 39 is the worst
+    scores[:10] = 100.0                                         # ten equal best
+    tr.decimate(scores)
+    after = tr.graph()
+    # survivors are the 20 best roots, in their original order; compare their first programs' lines
+    def first_lines(g, r):
+        t = g.root_team[r]; pr = g.edge_program[g.team_edge_offset[t]]
+        return g.lines[g.program_line_offset[pr]:g.program_line_offset[pr + 1]].tobytes()
+    assert after.nb_roots >= 20
+    kept = [first_lines(before, r) for r in range(20)]
+    got = [first_lines(after, r) for r in range(after.nb_roots)]
+    it = iter(got)
+    assert all(any(k == x for x in it) for k in kept), "the 20 best roots survive, order preserved"
+
+
+def test_same_seed_same_evolution():
+    a, _ = make(seed=11, nb_roots=80, force_program_behavior_change=0)
+    b, _ = make(seed=11, nb_roots=80, force_program_behavior_change=0)
+    c, _ = make(seed=12, nb_roots=80, force_program_behavior_change=0)
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        for t in (a, b, c):
+            t.populate()
+        sc = rng.normal(size=80)
+        assert a.fingerprint() == b.fingerprint() != c.fingerprint()
+        for t in (a, b, c):
+            t.decimate(sc)
+    assert a.fingerprint() == b.fingerprint()
+
+
+def test_gridworld_training_learns_with_the_oracle_backend(oracle_mod):
+    """[REF] gridworld/src/main.cpp:57-65 with params.json scaled to 60 roots: the best policy reaches the exit
+    (score > 0: +100 on the exit tile, -1 per step) within a few generations; archive and behaviour test active."""
+    tr, p = make(seed=2, **SMALL)
+    log = []
+    be = oracle_backend(oracle_mod, "gridworld", nb_iterations=1, max_actions=100, log=log)
+    stats = [tr.train_generation(be, gen) for gen in range(12)]
+    best = [s["best_score"] for s in stats]
+    assert best[0] <= best[-1] and max(best) > 0.0, best
+    assert all(np.array_equal(np.sort(sc)[::-1][0], s["best_score"]) for sc, s in zip(log, stats))
+    assert stats[-1]["archive_records"] > 0 and sum(s["behaviour_retries"] for s in stats) >= 0
+    assert all(s["nb_roots"] == 60 and s["nb_removed_roots"] == 30 for s in stats)
