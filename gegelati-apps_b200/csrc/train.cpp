@@ -290,13 +290,20 @@ struct tpgx_trainer {
         for (NewProg& n : fresh) mutate_program(progs[n.id]);
         if (!P.force_program_behavior_change || archive.empty() || fresh.empty()) return TPGX_OK;
         if (!be || !be->execute) { err = "forceProgramBehaviorChangeOnMutation needs a backend to run the new programs on the archive"; return TPGX_ERR_BAD_ARG; }
-        const int64_t count = (int64_t)archive.size();
-        std::vector<double> obs((size_t)count * obs_len);
-        std::map<int, std::vector<int>> by_prog;
-        for (int64_t i = 0; i < count; i++) {
-            std::memcpy(obs.data() + (size_t)i * obs_len, archive[(size_t)i].obs.data(), (size_t)obs_len * 8);
-            by_prog[archive[(size_t)i].prog].push_back((int)i);
+        /* the distinct archived observations ([UP] the archive keys its data-handler copies by hash) and, per archived
+           program, its recorded bid on each of them */
+        std::map<std::vector<double>, int> obs_index;
+        std::vector<double> obs;
+        std::map<int, std::map<int, double>> by_prog;
+        for (const ARec& r : archive) {
+            auto it = obs_index.find(r.obs);
+            if (it == obs_index.end()) {
+                it = obs_index.emplace(r.obs, (int)obs_index.size()).first;
+                obs.insert(obs.end(), r.obs.begin(), r.obs.end());
+            }
+            by_prog[r.prog][it->second] = r.bid;
         }
+        const int64_t count = (int64_t)obs_index.size();
         const double tau = 1e-4; /* [UP] Archive::areProgramResultsUnique default tolerance */
         auto close = [&](double a, double b) { return a == b || std::fabs(a - b) <= tau; };
         std::vector<size_t> pending(fresh.size());
@@ -328,10 +335,13 @@ struct tpgx_trainer {
                 const double* bp = bm + count;
                 bool differs = false;
                 for (int64_t k = 0; k < count && !differs; k++) differs = !close(bm[k], bp[k]);
+                /* [UP] areProgramResultsUnique: an archived program with a recording on every archived observation and
+                   all of them within tau of the candidate makes the candidate a duplicate */
                 bool unique = differs;
                 for (auto it = by_prog.begin(); unique && it != by_prog.end(); ++it) {
+                    if ((int64_t)it->second.size() != count) continue;
                     bool same = true;
-                    for (int k : it->second) if (!close(bm[k], archive[(size_t)k].bid)) { same = false; break; }
+                    for (const auto& kv : it->second) if (!close(bm[kv.first], kv.second)) { same = false; break; }
                     unique = !same;
                 }
                 if (!unique) { mutate_program(progs[fresh[pending[i]].id]); again.push_back(pending[i]); (*retries)++; }
