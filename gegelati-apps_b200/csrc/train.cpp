@@ -171,7 +171,7 @@ struct tpgx_trainer {
     /* ---- [UP] TPGMutator ---- */
     void init_random_tpg() {
         const int nA = P.nb_actions;
-        std::vector<int> made;
+        std::vector<TEdge> made;
         for (int i = 0; i < nA; i++) {
             const int t = new_team();
             for (int k = 0; k < 2; k++) { /* two edges to two different actions */
@@ -181,17 +181,18 @@ struct tpgx_trainer {
                     progs[p].consts[c] = (double)((int64_t)u64(0, (uint64_t)(P.max_const_value - P.min_const_value)) + P.min_const_value);
                 mutate_program(progs[p]);
                 add_edge(t, p, -1 - ((i + k) % nA));
-                made.push_back(p);
+                made.push_back({p, -1 - ((i + k) % nA)});
             }
         }
-        /* extra initial edges, sharing the programs made above, up to maxInitOutgoingEdges */
+        /* extra initial edges up to maxInitOutgoingEdges: duplicates of edges made above (same program, same action),
+           so that a program always bids for one destination — what the dot format can express */
         for (int t : std::vector<int>(order)) {
             const int extra = P.max_init_outgoing_edges > 2 ? (int)u64(0, (uint64_t)P.max_init_outgoing_edges - 2) : 0;
             for (int x = 0; x < extra; x++) {
-                const int p = made[u64(0, made.size() - 1)];
+                const TEdge m = made[u64(0, made.size() - 1)];
                 bool has = false;
-                for (const TEdge& e : teams[t].edges) has |= e.prog == p;
-                if (!has) add_edge(t, p, -1 - (int)u64(0, (uint64_t)nA - 1));
+                for (const TEdge& e : teams[t].edges) has |= e.prog == m.prog;
+                if (!has) add_edge(t, m.prog, m.dest);
             }
         }
     }

@@ -33,7 +33,7 @@ def run_pair(oracle_mod, app, generations, nb_iterations, max_actions, seed, sec
 
 
 def test_gridworld_evolution_identical_and_learning(oracle_mod):
-    stats = run_pair(oracle_mod, "gridworld", generations=12, nb_iterations=1, max_actions=100, seed=2, nb_roots=60, archive_size=300)
+    stats = run_pair(oracle_mod, "gridworld", generations=10, nb_iterations=1, max_actions=100, seed=5, nb_roots=60, archive_size=300)
     assert max(s["best_score"] for s in stats) > 0.0
     assert sum(s["behaviour_retries"] for s in stats) > 0, "the behaviour test against the archive ran on the GPU"
 

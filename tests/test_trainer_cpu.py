@@ -103,10 +103,10 @@ def test_same_seed_same_evolution():
 def test_gridworld_training_learns_with_the_oracle_backend(oracle_mod):
     """[REF] gridworld/src/main.cpp:57-65 with params.json scaled to 60 roots: the best policy reaches the exit
     (score > 0: +100 on the exit tile, -1 per step) within a few generations; archive and behaviour test active."""
-    tr, p = make(seed=2, **SMALL)
+    tr, p = make(seed=5, **SMALL)
     log = []
     be = oracle_backend(oracle_mod, "gridworld", nb_iterations=1, max_actions=100, log=log)
-    stats = [tr.train_generation(be, gen) for gen in range(12)]
+    stats = [tr.train_generation(be, gen) for gen in range(10)]
     best = [s["best_score"] for s in stats]
     assert best[0] <= best[-1] and max(best) > 0.0, best
     assert all(np.array_equal(np.sort(sc)[::-1][0], s["best_score"]) for sc, s in zip(log, stats))
