@@ -115,11 +115,12 @@ template <int K, class Addr> __device__ __forceinline__ void ld_px(Addr p, uint3
 #pragma unroll
     for (int k = 0; k < K; k++) v[k] = __byte_perm(w, 0, 0x4440 + k); /* byte k, zero-extended: one PRMT */
 }
-/* uint8 -> double is exact; one I2F.F64.U8 with a byte selector per sample */
+/* uint8 -> double is exact; cvt.rn.f64.u8 of (w >> 8k) compiles to ONE I2F.F64.U8 with a byte selector (R.Bk) per sample
+   (the C++ cast goes through PRMT + I2F.F64.U32) */
 template <int K, class Addr> __device__ __forceinline__ void ld_px_f64(Addr p, double (&v)[K]) {
     const uint32_t w = ld_px_word<K>(p);
 #pragma unroll
-    for (int k = 0; k < K; k++) v[k] = (double)__byte_perm(w, 0, 0x4440 + k);
+    for (int k = 0; k < K; k++) asm("cvt.rn.f64.u8 %0, %1;" : "=d"(v[k]) : "r"(w >> (8 * k)));
 }
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
