@@ -123,6 +123,18 @@ template <int K, class Addr> __device__ __forceinline__ void ld_px_f64(Addr p, d
     for (int k = 0; k < K; k++) asm("cvt.rn.f64.u8 %0, %1;" : "=d"(v[k]) : "r"(w >> (8 * k)));
 }
 
+/* exp / ln tables of tpgx_math.h read from the CTA's shared-memory copy (K1 leaves almost no L1, so the global
+   tables would be fetched from L2 on most lookups) */
+#define K1_TAB_BYTES (256 * 8 + 512 * 8)
+struct tab_shared {
+    uint32_t exp_addr, log_addr;
+    __device__ __forceinline__ void exp_entry(int i, double& tail, double& T) const { lds_f64x2(exp_addr + (uint32_t)i * 16u, tail, T); }
+    __device__ __forceinline__ void log_entry(int i, double& invc, double& logc_hi, double& logc_lo) const {
+        lds_f64x2(log_addr + (uint32_t)i * 32u, invc, logc_hi);
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(logc_lo) : "r"(log_addr + (uint32_t)i * 32u + 16u));
+    }
+};
+
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
@@ -142,6 +154,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
     uint4* codeb = reinterpret_cast<uint4*>(regs + NW * K1_SLOTS * TS * 8);
     uint64_t* bar = reinterpret_cast<uint64_t*>(codeb + NW * 2 * K1_CODE_QUADS);
     int* s_next = reinterpret_cast<int*>(bar + 1);
+    double* s_tab = reinterpret_cast<double*>(bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -149,6 +162,9 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
         fence_mbar_init();
         *s_next = 0;
     }
+    for (int i = threadIdx.x; i < 256 + 512; i += NW * 32)
+        s_tab[i] = i < 256 ? tpgx_math::tpgx_exp_tab_dev[i] : tpgx_math::tpgx_log_tab_dev[i - 256];
+    const tab_shared tabs = {smem_u32(s_tab), smem_u32(s_tab + 256)};
     __syncthreads();
     if (TILE_SMEM && threadIdx.x == 0) {
         mbar_expect_tx(bar, (uint32_t)tile_bytes);
@@ -296,9 +312,9 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                     }
                     if (h & 1u) ld_px_f64<K>(pa, a); else ld_regs<K>(ra, a);
                     if (op == TPGX_K1X_EXP) {
-                        tpgx_math::exp_k<K>(a, r);
+                        tpgx_math::exp_k<K>(a, r, tabs);
                     } else if (op == TPGX_K1X_LOG) {
-                        tpgx_math::log_k<K>(a, r);
+                        tpgx_math::log_k<K>(a, r, tabs);
                     } else if (op == TPGX_K1X_MULC) {
                         const double c = *reinterpret_cast<const double*>(cbase + ln.z);
 #pragma unroll
@@ -387,7 +403,7 @@ size_t tpgx_bid_smem_bytes(int variant, int hw) {
     const bid_variant& v = g_variants[variant];
     const int ts = 32 * v.K;
     const size_t tile = v.tile_smem ? (((size_t)(hw + 1) * ts + 127) & ~(size_t)127) : 0;
-    return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * 2 * K1_CODE_QUADS * 16 + 16;
+    return tile + (size_t)v.NW * K1_SLOTS * ts * 8 + (size_t)v.NW * 2 * K1_CODE_QUADS * 16 + 16 + K1_TAB_BYTES;
 }
 
 template <int K, int NW, bool EXT, bool TEAM, bool TS_>
