@@ -242,10 +242,16 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                 if (lane < m) code[TPGX_K1_CQ + lane] = __ldg(stream + d0.x + TPGX_K1_CQ + done + lane);
                 __syncwarp();
             }
-            const uint4* lp = code + TPGX_K1_CQ;
+            /* no trip counter: the encoder flags the last line of every staged block (TPGX_K1H_LAST), so the loop costs a
+               pointer increment, one bit test and a branch (m >= 1 here) */
+            uint32_t lp = smem_u32(code + TPGX_K1_CQ);
+            uint32_t last;
 #pragma unroll 1
-            for (int j = 0; j < m; j++) {
-                const uint4 ln = lp[j];                 /* broadcast LDS.128: handler, operand offsets, destination offset */
+            do {
+                uint4 ln;                               /* broadcast LDS.128: handler, operand offsets, destination offset */
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ln.x), "=r"(ln.y), "=r"(ln.z), "=r"(ln.w) : "r"(lp));
+                lp += 16u;
+                last = ln.x & TPGX_K1H_LAST;
                 const uint32_t ra = regs_lane + ln.y;  /* operand as a register slot */
                 const uint32_t rb = regs_lane + ln.z;
                 px_addr<TILE_SMEM> pa, pb;              /* operand as a pixel */
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(NW * 32, 1) tpgx_bid_kernel(const tpgx_bid_par
                     }
                     st_regs<K>(rd, r);
                 }
-            }
+            } while (!last);
             done += m;
         }
         /* the last effective line of a program writes register 0 (that is what makes it effective);

@@ -401,7 +401,8 @@ __global__ void tpgx_k1_encode_kernel(const uint32_t* __restrict__ code, const i
     int fl = 0;
     for (int i = threadIdx.x; i < d.y; i += blockDim.x) {
         const tpgx_k1_quad q = tpgx_k1_line(src[i], (uint32_t)ts, (uint32_t)width, (uint32_t)hw);
-        out[TPGX_K1_CQ + i] = make_uint4(q.x, q.y, q.z, q.w);
+        const bool last = q.x != 0xffffffffu && (i == d.y - 1 || (i % TPGX_K1_CAPL) == TPGX_K1_CAPL - 1);
+        out[TPGX_K1_CQ + i] = make_uint4(last ? (q.x | TPGX_K1H_LAST) : q.x, q.y, q.z, q.w);
         if (q.x == 0xffffffffu) fl |= 2;
         else if (tpgx_k1_is_extended(q.x)) fl |= 1;
     }

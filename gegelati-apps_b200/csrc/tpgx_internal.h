@@ -61,8 +61,10 @@ static inline uint32_t tpgx_pack_line(uint32_t op, uint32_t dst, uint32_t ka, ui
 #define TPGX_K1_CQ 4
 #define TPGX_K1_CAPL 28
 /* handler id bit layout: [0] operand A is a pixel, [1] operand B is a pixel, [5:2] operation, [6] heavy class
- * (own operand handling / libm), so the interpreter dispatches with a few single-bit tests */
+ * (own operand handling / libm), so the interpreter dispatches with a few single-bit tests; [7] set by the stream
+ * encoder on the last line of a block */
 #define TPGX_K1H_HEAVY 64u
+#define TPGX_K1H_LAST 128u /* last line of a staged block (TPGX_K1_CAPL lines) or of the program: ends K1's line loop */
 enum { /* cheap class: (op << 2) | kinds */
     TPGX_K1C_SUB = 0, TPGX_K1C_ADD, TPGX_K1C_MUL, TPGX_K1C_MAX, TPGX_K1C_COND, TPGX_K1C_EQ0, TPGX_K1C_EQM1, TPGX_K1C_EQ1,
     TPGX_K1C_GE15, TPGX_K1C_PI
