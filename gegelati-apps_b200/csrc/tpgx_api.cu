@@ -76,6 +76,12 @@ struct tpgx_ctx {
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[16];
+    /* tpgx_set_observations_pinned enqueues its copy / re-tiling / Sobel-plane work on a stream of its own, so that
+       the graph uploads that follow on the main stream are not queued behind 47 MB of observations; consumers of the
+       tiles wait for obs_ready */
+    cudaStream_t obs_stream = nullptr;
+    cudaEvent_t obs_ready = nullptr;
+    bool obs_pending = false;
     const uint8_t* obs_dev = nullptr;    /* raw observations [nb_obs][hw] (ours or the caller's) */
     const uint8_t* labels_dev = nullptr;
     int64_t nb_obs = 0;
@@ -104,6 +110,13 @@ tpgx_status fail(tpgx_ctx* c, tpgx_status st, const std::string& m) {
             return fail(ctx, e__ == cudaErrorMemoryAllocation ? TPGX_ERR_OOM : TPGX_ERR_CUDA,            \
                         std::string(#call) + ": " + cudaGetErrorString(e__));                            \
     } while (0)
+
+/* work on the main stream that reads the observation buffers is ordered after a pending pinned upload */
+static cudaError_t wait_for_observations(tpgx_ctx* ctx) {
+    if (!ctx->obs_pending) return cudaSuccess;
+    ctx->obs_pending = false;
+    return cudaStreamWaitEvent(ctx->stream, ctx->obs_ready, 0);
+}
 
 tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
     CU(b.ensure(bytes ? bytes : 16));
@@ -260,6 +273,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         return fail(ctx, TPGX_ERR_BAD_ARG, "root range out of bounds");
     if (!req->sample_index && req->nb_samples > ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples exceeds uploaded observations");
     if (!ctx->labels_dev) return fail(ctx, TPGX_ERR_STATE, "classification needs labels");
+    CU(wait_for_observations(ctx));
     const int nR = req->root_end - req->root_begin, C = req->nb_classes;
     const int64_t nS = req->nb_samples;
     const int ts = tpgx_bid_tile_samples(ctx->variant);
@@ -433,6 +447,8 @@ tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out) {
     ctx = new tpgx_ctx();
     ctx->cfg = *cfg;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->obs_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->obs_ready, cudaEventDisableTiming);
     if (e != cudaSuccess) { delete ctx; return fail(nullptr, TPGX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); }
     if (ctx->d_pixel_lut.ensure((size_t)TPGX_LUT_DOUBLES * 8) != cudaSuccess || tpgx_launch_pixel_lut(ctx->d_pixel_lut.as<double>(), ctx->stream) != cudaSuccess ||
         cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -450,6 +466,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->obs_stream) cudaStreamSynchronize(ctx->obs_stream);
     DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_tm_team, &ctx->d_tm_dst, &ctx->d_tm_stat, &ctx->d_tm_roots, &ctx->d_decision, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
@@ -457,6 +474,8 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : ctx->d_scratch) b.release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+    if (ctx->obs_stream) { cudaStreamSynchronize(ctx->obs_stream); cudaStreamDestroy(ctx->obs_stream); }
+    if (ctx->obs_ready) cudaEventDestroy(ctx->obs_ready);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TPGX_OK;
@@ -563,6 +582,17 @@ static tpgx_status set_observations_host(tpgx_ctx* ctx, int32_t source, int32_t 
     if (st != TPGX_OK) return st;
     if (!data) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_observations: null data");
     cudaSetDevice(ctx->cfg.device);
+    CU(wait_for_observations(ctx));
+    /* enqueue-only (pinned) uploads run on obs_stream, after whatever the main stream still does with the old tiles */
+    struct StreamSwap {
+        tpgx_ctx* c; cudaStream_t main; bool on;
+        ~StreamSwap() { if (on) c->stream = main; }
+    } swap{ctx, ctx->stream, !wait_for_copies};
+    if (swap.on) {
+        CU(cudaEventRecord(ctx->event(60), ctx->stream));
+        CU(cudaStreamWaitEvent(ctx->obs_stream, ctx->event(60), 0));
+        ctx->stream = ctx->obs_stream;
+    }
     if ((st = upload(ctx, ctx->d_obs_raw, data, (size_t)count * ctx->obs_hw)) != TPGX_OK) return st;
     ctx->obs_dev = ctx->d_obs_raw.as<uint8_t>();
     ctx->labels_dev = nullptr;
@@ -576,6 +606,10 @@ static tpgx_status set_observations_host(tpgx_ctx* ctx, int32_t source, int32_t 
     CU(cudaEventRecord(copied, ctx->stream));
     if ((st = pack_identity(ctx)) != TPGX_OK) return st;
     if (wait_for_copies) CU(cudaEventSynchronize(copied));
+    if (swap.on) {
+        CU(cudaEventRecord(ctx->obs_ready, ctx->obs_stream));
+        ctx->obs_pending = true;
+    }
     return TPGX_OK;
 }
 
@@ -599,6 +633,7 @@ tpgx_status tpgx_set_observations_device(tpgx_ctx* ctx, int32_t source, int32_t 
     if (st != TPGX_OK) return st;
     if (!d_data) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_observations_device: null data");
     cudaSetDevice(ctx->cfg.device);
+    CU(wait_for_observations(ctx));
     ctx->obs_dev = static_cast<const uint8_t*>(d_data);
     ctx->labels_dev = d_labels;
     if ((st = pack_identity(ctx)) != TPGX_OK) return st;
