@@ -290,3 +290,38 @@ def test_pinned_observation_upload_equals_blocking_upload(oracle_mod):
     with pytest.raises(tpgx.TpgxError) as e:
         ev.set_observations_pinned(img.copy(), lab.copy())
     assert e.value.status == A.ERR_BAD_ARG
+
+
+def test_pinned_uploads_interleave_with_graph_uploads_and_other_observations(oracle_mod):
+    """The pinned upload runs on its own stream: every consumer of the observation buffers (identity tiles, an index-list
+    re-tiling, a later blocking upload, the archive pass) is ordered after it, and a second pinned upload waits for the
+    evaluation still reading the first."""
+    import torch
+    g1, ev = make(roots=12, edges=4, lines=10, depth=2, seed=21)
+    g2 = tpgx.synthetic_graph("mnist", roots=9, edges=5, lines=12, depth=1, seed=22)
+    want = ("score", "confusion", "action", "counters")
+    sets = [tpgx.synthetic_images(n, seed=s) for n, s in ((700, 31), (333, 32), (512, 33))]
+    pins = [(torch.from_numpy(i).pin_memory().numpy(), torch.from_numpy(l).pin_memory().numpy()) for i, l in sets]
+    for rep in range(3):
+        for k, ((img, lab), (pi, pl)) in enumerate(zip(sets, pins)):
+            ev.set_observations_pinned(pi, pl)          # enqueue only
+            g = g1 if (rep + k) % 2 == 0 else g2
+            ev.set_graph(g)                             # graph uploads while the observations are still in flight
+            o = oracle_for(oracle_mod, g)
+            if k == 1:                                  # index list: re-tiling on the main stream reads the raw upload
+                idx = np.random.default_rng(rep).integers(0, len(img), 200).astype(np.int32)
+                compare(ev.evaluate_classification(sample_index=idx, want=want), o.evaluate_classification(img, lab, sample_index=idx, want=want))
+            else:
+                compare(ev.evaluate_classification(want=want), o.evaluate_classification(img, lab, want=want))
+    # pinned, then a blocking upload of other data, then evaluate: the blocking upload must win
+    ev.set_observations_pinned(*pins[0])
+    ev.set_observations(*sets[2])
+    ev.set_graph(g1)
+    compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g1).evaluate_classification(*sets[2], want=want))
+    # pinned, then the archive pass
+    ev.set_observations_pinned(*pins[1])
+    seeds = np.arange(g1.nb_roots, dtype=np.uint64) + 3
+    dev = ev.archive_classification(seeds, 0.05, 64)
+    ref = oracle_for(oracle_mod, g1).archive_classification(sets[1][0], seeds, 0.05, 64)
+    assert np.array_equal(dev["program"], ref["program"]) and np.array_equal(dev["sample"], ref["sample"])
+    assert np.array_equal(dev["bid"].view(np.uint64), ref["bid"].view(np.uint64))
