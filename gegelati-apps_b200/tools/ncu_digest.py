@@ -33,6 +33,8 @@ hdr = rows[1]
 ia, isrc, ismp = hdr.index("Instructions Executed"), hdr.index("Source"), hdr.index("# Samples")
 tot, by = 0, collections.Counter()
 for row in rows[2:]:
+    if len(row) <= max(ia, isrc) or not row[ia].isdigit():   # a second kernel's header / partial rows
+        continue
     m = re.match(r"(@!?U?P\d+\s+)?([A-Z0-9_.]+)", row[isrc].strip())
     op = m.group(2).split(".")[0] if m else row[isrc]
     by[op] += int(row[ia]); tot += int(row[ia])
@@ -46,8 +48,13 @@ for row in rows:
         cur = row[1].split("/")[-1]; continue
     if row and row[0] == "Line No":
         hdr = row; ia, ismp = row.index("Instructions Executed"), row.index("# Samples"); continue
-    if hdr and row and row[0] != "" and row[0].isdigit() and row[ia].isdigit():
+    if hdr and len(row) > max(ia, ismp) and row[0] != "" and row[0].isdigit() and row[ia].isdigit():
         agg.append((cur, int(row[0]), row[1].strip()[:100], int(row[ia]), int(row[ismp]) if row[ismp].isdigit() else 0))
+merged = collections.OrderedDict()   # the same line can appear once per captured launch / inlined copy
+for f, l, src, n, sm in agg:
+    k = (f, l, src)
+    merged[k] = (merged.get(k, (0, 0))[0] + n, merged.get(k, (0, 0))[1] + sm)
+agg = [(k[0], k[1], k[2], v[0], v[1]) for k, v in merged.items()]
 ti, ts = sum(a[3] for a in agg), sum(a[4] for a in agg)
 print("\n== hottest source lines (share of executed instructions | share of stall samples)")
 for f, l, s, n, sm in sorted(agg, key=lambda a: -a[3])[:top]:
