@@ -472,7 +472,9 @@ tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_back
     int32_t nrec = 0;
     st = be->evaluate(be->user, &g, generation, aseed.data(), t->P.archiving_probability, cap, scores.data(), rprog.data(), rbid.data(), robs.data(), t->obs_len, &nrec);
     if (st != TPGX_OK) { t->err = "backend evaluate failed"; return st; }
+    if (nrec < 0 || nrec > std::max(0, cap)) { t->err = "backend returned more archive records than archive_size"; return TPGX_ERR_STATE; }
     for (int i = 0; i < nrec; i++) {
+        if (rprog[i] < 0 || rprog[i] >= (int32_t)t->v_prog_id.size()) { t->err = "backend returned an archive record for an unknown program"; return TPGX_ERR_STATE; }
         ARec r;
         r.prog = t->v_prog_id[rprog[i]];
         r.bid = rbid[i];
