@@ -1022,6 +1022,69 @@ tpgx_status epbe_execute(void* user, const tpgx_graph* g, int64_t count, const d
 }
 } // namespace
 
+/* ---- GPU backend of the host generation loop for the classification environment (the mnist app) ---- */
+namespace {
+struct ClBackend {
+    tpgx_ctx* ctx;
+    const uint8_t* images; /* host copy of what was uploaded: [nb_images][height * width], borrowed */
+    int64_t nb_images;
+    int32_t nb_classes;
+    int64_t actions;
+};
+tpgx_status clbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, const uint64_t* archive_seed, double probability,
+                          int32_t archive_size, double* scores, int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len,
+                          int32_t* nb_records) {
+    ClBackend* b = static_cast<ClBackend*>(user);
+    tpgx_status st = tpgx_set_graph(b->ctx, g);
+    if (st != TPGX_OK) return st;
+    /* [REF] mnist/src/mnist.cpp:58-69 + :8-34: the evaluation classifies the images drawn from the episode seed */
+    std::vector<int32_t> idx((size_t)b->actions);
+    if ((st = tpgx_mnist_episode_indices(1000ull * generation, 0 /* TRAINING */, b->nb_images, b->actions, idx.data())) != TPGX_OK) return st;
+    tpgx_classif_request req{};
+    req.nb_samples = b->actions; req.sample_index = idx.data(); req.nb_classes = b->nb_classes; req.root_begin = 0; req.root_end = g->nb_roots;
+    tpgx_classif_result ev{};
+    ev.score = scores;
+    if ((st = tpgx_evaluate_classification(b->ctx, &req, &ev)) != TPGX_OK) return st;
+    *nb_records = 0;
+    if (archive_size <= 0 || probability == 0.0) return TPGX_OK;
+    const int px = b->ctx->obs_hw;
+    if (obs_len < px) return fail(b->ctx, TPGX_ERR_BAD_ARG, "observation rows shorter than an image");
+    std::vector<int64_t> sample((size_t)archive_size);
+    tpgx_archive_request ar{archive_seed, probability, archive_size, 0};
+    tpgx_archive_result res{rec_program, sample.data(), rec_bid, 0, 0};
+    if ((st = tpgx_archive_classification(b->ctx, &req, &ar, &res)) != TPGX_OK) return st;
+    for (int i = 0; i < res.nb_records; i++) { /* the recorded observation: the image itself, as the doubles the programs see */
+        const uint8_t* im = b->images + (size_t)sample[i] * px;
+        double* row = rec_obs + (size_t)i * obs_len;
+        for (int q = 0; q < px; q++) row[q] = (double)im[q];
+        for (int q = px; q < obs_len; q++) row[q] = 0.0;
+    }
+    *nb_records = res.nb_records;
+    return TPGX_OK;
+}
+tpgx_status clbe_execute(void* user, const tpgx_graph* g, int64_t count, const double* obs, int32_t obs_len, double* bid) {
+    ClBackend* b = static_cast<ClBackend*>(user);
+    tpgx_status st = tpgx_set_graph(b->ctx, g);
+    if (st != TPGX_OK) return st;
+    if (obs_len != b->ctx->obs_hw) return fail(b->ctx, TPGX_ERR_BAD_ARG, "observation rows must be one image long");
+    const double* pf[2] = {obs, nullptr};
+    const int32_t* pi[2] = {nullptr, nullptr};
+    return tpgx_execute_programs(b->ctx, count, pf, pi, bid);
+}
+} // namespace
+
+tpgx_status tpgx_train_backend_classification(tpgx_ctx* ctx, const uint8_t* images, int64_t nb_images, int32_t nb_classes,
+                                              int64_t actions_per_evaluation, tpgx_train_backend* out) {
+    if (!ctx || !images || !out || nb_images < 1 || nb_classes < 2 || actions_per_evaluation < 1)
+        return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_train_backend_classification: bad argument");
+    if (!ctx->obs_dev || ctx->nb_obs != nb_images) return fail(ctx, TPGX_ERR_STATE, "tpgx_train_backend_classification: upload the same images with tpgx_set_observations first");
+    ClBackend* b = new ClBackend{ctx, images, nb_images, nb_classes, actions_per_evaluation};
+    out->user = b;
+    out->evaluate = clbe_evaluate;
+    out->execute = clbe_execute;
+    return TPGX_OK;
+}
+
 tpgx_status tpgx_train_backend_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_train_backend* out) {
     if (!ctx || !req || !out) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_train_backend_episodes: null argument");
     if (req->nb_iterations < 1 || req->max_actions < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_train_backend_episodes: bad request template");
@@ -1032,8 +1095,10 @@ tpgx_status tpgx_train_backend_episodes(tpgx_ctx* ctx, const tpgx_episode_reques
     return TPGX_OK;
 }
 void tpgx_train_backend_release(tpgx_train_backend* backend) {
-    if (!backend || backend->evaluate != epbe_evaluate) return;
-    delete static_cast<EpBackend*>(backend->user);
+    if (!backend || !backend->user) return;
+    if (backend->evaluate == epbe_evaluate) delete static_cast<EpBackend*>(backend->user);
+    else if (backend->evaluate == clbe_evaluate) delete static_cast<ClBackend*>(backend->user);
+    else return;
     backend->user = nullptr;
 }
 

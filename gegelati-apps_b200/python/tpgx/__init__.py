@@ -3,5 +3,5 @@ from . import _cabi as abi
 from .api import Evaluator, TpgxError, load_library, LIB_PATH, EXPORTS, mnist_episode_indices, load_idx, flatten_programs
 from .graph import (TPGraph, INSTRUCTION_SETS, APP_SOURCES, APP_CONSTANTS, APP_ACTIONS, APP_ENV, import_dot, export_dot,
                     synthetic_graph, synthetic_images, random_programs, address_space, LINE_DTYPE)
-from .train import Trainer, load_params_json, python_backend, episodes_backend
+from .train import Trainer, load_params_json, python_backend, episodes_backend, classification_backend
 from .sharding import shard_range, gather_records, records_from

@@ -177,3 +177,16 @@ def episodes_backend(evaluator, env, nb_iterations, max_actions, mode=A.MODE_TRA
         raise TpgxError(st, (lib.tpgx_last_error(evaluator.h) or b"").decode())
     be._keep = (pa, req, evaluator)
     return be
+
+
+def classification_backend(evaluator, images, nb_classes=10, actions_per_evaluation=500):
+    """The GPU backend (tpgx_train_backend_classification) on an Evaluator whose observations are `images` (uint8 [S, H*W])."""
+    lib = evaluator.lib
+    img = np.ascontiguousarray(images, dtype=np.uint8)
+    be = A.TrainBackend()
+    lib.tpgx_train_backend_classification.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.POINTER(A.TrainBackend)]
+    st = lib.tpgx_train_backend_classification(evaluator.h, img.ctypes.data, img.shape[0], int(nb_classes), int(actions_per_evaluation), C.byref(be))
+    if st != A.OK:
+        raise TpgxError(st, (lib.tpgx_last_error(evaluator.h) or b"").decode())
+    be._keep = (img, evaluator)
+    return be

@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""BASELINE.json config 5: gridworld full training loop — host mutation + GPU evaluation, end-to-end generations/s with the
-app's params.json values ([REF] gridworld/params.json: 500 roots, 1 iteration x <= 100 actions, archive 2000 @ 0.01).
-usage: train_case.py [generations=200] [nb_roots=500]"""
+"""Full training loops — host mutation + GPU evaluation + archive — with the apps' params.json values, end-to-end generations/s.
+  gridworld (BASELINE.json config 5; [REF] gridworld/params.json: 500 roots, 1 iteration x <= 100 actions, archive 2000 @ 0.01)
+  mnist     ([REF] mnist/params.json: 500 roots, 500 images per generation drawn from 60 000 synthetic ones, archive 500 @ 0.01)
+usage: train_case.py [gridworld|mnist] [generations=200] [nb_roots=500]"""
 import os
 import sys
 import time
@@ -10,20 +11,30 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "python"))
 import tpgx  # noqa: E402
 
-gens = int(sys.argv[1]) if len(sys.argv) > 1 else 200
-P = dict(nb_actions=4, nb_roots=int(sys.argv[2]) if len(sys.argv) > 2 else 500, max_init_outgoing_edges=4, max_outgoing_edges=10,
-         p_edge_deletion=0.7, p_edge_addition=0.7, p_program_mutation=0.2, p_edge_destination_change=0.1, p_edge_destination_is_action=0.5,
-         force_program_behavior_change=1, max_program_size=20, p_delete=0.5, p_add=0.5, p_mutate=1.0, p_swap=1.0, p_constant_mutation=0.5,
-         min_const_value=-10, max_const_value=10, ratio_deleted_roots=0.5, archive_size=2000, archiving_probability=0.01)
-tr = tpgx.Trainer(tpgx.INSTRUCTION_SETS["gridworld"], tpgx.APP_SOURCES["gridworld"], P, nb_constants=5, seed=0)
-ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["gridworld"], tpgx.APP_SOURCES["gridworld"], nb_constants=5)
-be = tpgx.episodes_backend(ev, tpgx.abi.ENV_GRIDWORLD, nb_iterations=1, max_actions=100)
+app = sys.argv[1] if len(sys.argv) > 1 else "gridworld"
+gens = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+roots = int(sys.argv[3]) if len(sys.argv) > 3 else 500
+COMMON = dict(nb_roots=roots, p_edge_deletion=0.7, p_edge_addition=0.7, p_program_mutation=0.2, p_edge_destination_change=0.1,
+              p_edge_destination_is_action=0.5, force_program_behavior_change=1, max_program_size=20, p_delete=0.5, p_add=0.5, p_mutate=1.0,
+              p_swap=1.0, p_constant_mutation=0.5, min_const_value=-10, max_const_value=10, ratio_deleted_roots=0.5, archiving_probability=0.01)
+if app == "gridworld":
+    P = dict(COMMON, nb_actions=4, max_init_outgoing_edges=4, max_outgoing_edges=10, archive_size=2000)
+else:
+    P = dict(COMMON, nb_actions=10, max_init_outgoing_edges=3, max_outgoing_edges=5, archive_size=500)
+tr = tpgx.Trainer(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], P, nb_constants=5, seed=0)
+ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], nb_constants=5)
+if app == "gridworld":
+    be = tpgx.episodes_backend(ev, tpgx.abi.ENV_GRIDWORLD, nb_iterations=1, max_actions=100)
+else:
+    img, lab = tpgx.synthetic_images(60000)
+    ev.set_observations(img, lab)
+    be = tpgx.classification_backend(ev, img, nb_classes=10, actions_per_evaluation=500)
 tr.train_generation(be, 0)  # warm-up (context buffers, first-launch costs)
 t0 = time.perf_counter()
 for gen in range(1, gens + 1):
     s = tr.train_generation(be, gen)
     if gen % max(1, gens // 10) == 0:
-        print("gen %4d  best %7.2f  mean %8.2f  teams %4d  programs %5d  archive %4d  retries %5d" %
+        print("gen %4d  best %8.4f  mean %9.4f  teams %4d  programs %5d  archive %4d  retries %5d" %
               (gen, s["best_score"], s["mean_score"], s["nb_teams"], s["nb_programs"], s["archive_records"], s["behaviour_retries"]))
 dt = time.perf_counter() - t0
-print("%d generations in %.2f s = %.1f generations/s (%d roots, fingerprint %016x)" % (gens, dt, gens / dt, P["nb_roots"], tr.fingerprint()))
+print("%s: %d generations in %.2f s = %.1f generations/s (%d roots, fingerprint %016x)" % (app, gens, dt, gens / dt, roots, tr.fingerprint()))

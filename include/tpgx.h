@@ -368,6 +368,13 @@ uint64_t tpgx_trainer_fingerprint(const tpgx_trainer* t);
  * tpgx_execute_programs.  The backend borrows ctx and req (and req->pendulum_actions); free with
  * tpgx_train_backend_release.                                                                                       */
 tpgx_status tpgx_train_backend_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req, tpgx_train_backend* out);
+/* GPU backend for the classification environment ([REF] mnist/src/main.cpp:106-107,145: ClassificationLearningAgent +
+ * trainOneGeneration): every generation classifies the actions_per_evaluation (maxNbActionsPerEval) images that
+ * tpgx_mnist_episode_indices draws from seed 1000 * generation, evaluate = tpgx_set_graph + tpgx_evaluate_classification +
+ * tpgx_archive_classification (the archived observation is the image, 784 doubles), execute = tpgx_execute_programs.
+ * `images` is the caller's host copy of the observations already uploaded to ctx (borrowed until release).             */
+tpgx_status tpgx_train_backend_classification(tpgx_ctx* ctx, const uint8_t* images, int64_t nb_images, int32_t nb_classes,
+                                              int64_t actions_per_evaluation, tpgx_train_backend* out);
 void tpgx_train_backend_release(tpgx_train_backend* backend);
 
 /* Direct access to single engine steps (used by parity tests; replaces

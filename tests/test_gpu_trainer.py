@@ -48,3 +48,22 @@ def test_pendulum_evolution_identical(oracle_mod):
     """libm-heavy environment: identical only because the GPU and the oracle share one libm sequence."""
     run_pair(oracle_mod, "pendulum", generations=3, nb_iterations=2, max_actions=300, seed=9, pendulum_actions=PEND_ACTIONS, nb_roots=30,
              archive_size=200, max_outgoing_edges=5, max_init_outgoing_edges=3)
+
+
+def test_mnist_evolution_identical(oracle_mod):
+    """The mnist app's loop ([REF] mnist/src/main.cpp:106-107,145) at a reduced size: ClassificationLearningAgent semantics
+    (F1 scores), the per-generation image draw, the archive of images and the behaviour test on them."""
+    from trainer_util import oracle_classification_backend
+    img, lab = tpgx.synthetic_images(600, seed=41)
+    p = dict(GRID, nb_actions=10, nb_roots=40, archive_size=100, max_outgoing_edges=5, max_init_outgoing_edges=3)
+    mk = lambda: tpgx.Trainer(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], p, nb_constants=5, seed=3)
+    t_gpu, t_cpu = mk(), mk()
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+    ev.set_observations(img, lab)
+    be_gpu = tpgx.classification_backend(ev, img, nb_classes=10, actions_per_evaluation=120)
+    be_cpu = oracle_classification_backend(oracle_mod, img, lab, 120)
+    for gen in range(4):
+        a, b = t_gpu.train_generation(be_gpu, gen), t_cpu.train_generation(be_cpu, gen)
+        assert a == b, (gen, a, b)
+        assert t_gpu.fingerprint() == t_cpu.fingerprint(), gen
+    assert a["archive_records"] > 0 and 0.0 <= a["best_score"] <= 1.0

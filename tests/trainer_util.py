@@ -38,3 +38,23 @@ def oracle_backend(oracle_mod, app, nb_iterations, max_actions, second_player_ra
         return o.execute_programs(len(obs), split_obs(src, obs))
 
     return tpgx.python_backend(evaluate, execute, nb_constants=nc)
+
+
+def oracle_classification_backend(oracle_mod, images, labels, actions):
+    """Same conventions as tpgx_train_backend_classification: the images of generation `gen` are those
+    tpgx_mnist_episode_indices draws from seed 1000 * gen in TRAINING mode; the archived observation is the image."""
+    ops, src, nc = tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], tpgx.APP_CONSTANTS["mnist"]
+
+    def evaluate(g, generation, aseeds, prob, cap, obs_len):
+        o = oracle_mod.Oracle(ops, src, g, nb_constants=nc)
+        idx = tpgx.mnist_episode_indices(seed=1000 * generation, mode=A.MODE_TRAINING, dataset_size=len(images), nb_actions=actions)
+        score = o.evaluate_classification(images, labels, sample_index=idx, want=("score",))["score"]
+        if cap == 0 or prob == 0.0:
+            return score, [], [], np.zeros((0, obs_len))
+        ar = o.archive_classification(images, aseeds, prob, cap, sample_index=idx)
+        return score, ar["program"], ar["bid"], images[ar["sample"]].astype(np.float64)
+
+    def execute(g, obs):
+        return oracle_mod.Oracle(ops, src, g, nb_constants=nc).execute_programs(len(obs), [obs])
+
+    return tpgx.python_backend(evaluate, execute, nb_constants=nc)
