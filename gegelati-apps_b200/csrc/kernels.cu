@@ -367,8 +367,9 @@ __global__ void __launch_bounds__(256) tpgx_sobel_planes_kernel(const uint8_t* _
     const int gx = -px(0, 0) + px(0, 2) - 2 * px(1, 0) + 2 * px(1, 2) - px(2, 0) + px(2, 2);
     const int gy = -px(0, 0) - 2 * px(0, 1) - px(0, 2) + px(2, 0) + 2 * px(2, 1) + px(2, 2);
     const int idx = abs(gy) * TPGX_SOBEL_LUT_N + abs(gx);
-    const double magn = lut[512 + idx];
-    const double d = lut[512 + TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N + idx];
+    /* {magnitude, direction} interleaved: one 16-byte gather (one L2 sector) per window */
+    const double2 md = __ldg(reinterpret_cast<const double2*>(lut + 512) + idx);
+    const double magn = md.x, d = md.y;
     double* out = planes + tile * 2ll * nwin * ts;
     out[(long long)wp * ts + j] = magn;
     out[((long long)nwin + wp) * ts + j] = ((gy ^ gx) < 0) ? -d : d; /* atan(gy/gx) is odd in each; also gives -0 for 0 / negative */
@@ -461,19 +462,18 @@ __global__ void tpgx_pixel_lut_kernel(double* __restrict__ lut) {
 /* Sobel results memoised over the gradient domain: pixels are uint8, so |gx|, |gy| <= 1020 and
  * sobelMagn / sobelDir are functions of 1021 x 1021 integer pairs (sign restored by the caller).
  * Filled by the routines the interpreter would otherwise run per sample, so the bits are the same. */
-__global__ void tpgx_sobel_lut_kernel(double* __restrict__ magn, double* __restrict__ dir) {
+__global__ void tpgx_sobel_lut_kernel(double2* __restrict__ magn_dir) {
     const int ax = blockIdx.x * blockDim.x + threadIdx.x, ay = blockIdx.y;
     if (ax >= TPGX_SOBEL_LUT_N) return;
-    magn[ay * TPGX_SOBEL_LUT_N + ax] = tpgx_math::xsqrt_nonneg((double)(ax * ax + ay * ay));
-    dir[ay * TPGX_SOBEL_LUT_N + ax] = tpgx_math::atan(tpgx_math::xdiv_small_int(ay, ax));
+    magn_dir[ay * TPGX_SOBEL_LUT_N + ax] = make_double2(tpgx_math::xsqrt_nonneg((double)(ax * ax + ay * ay)),
+                                                        tpgx_math::atan(tpgx_math::xdiv_small_int(ay, ax)));
 }
 cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st) {
     tpgx_pixel_lut_kernel<<<1, 256, 0, st>>>(lut);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    double* magn = lut + 512;
     dim3 grid((TPGX_SOBEL_LUT_N + 127) / 128, TPGX_SOBEL_LUT_N);
-    tpgx_sobel_lut_kernel<<<grid, 128, 0, st>>>(magn, magn + TPGX_SOBEL_LUT_N * TPGX_SOBEL_LUT_N);
+    tpgx_sobel_lut_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<double2*>(lut + 512));
     return cudaGetLastError();
 }
 
