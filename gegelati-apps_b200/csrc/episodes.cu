@@ -2,14 +2,18 @@
  * episodes.cu — batched lock-step restatements of the apps' sequential LearningEnvironments and
  * the episode loop of [UP] LearningAgent::evaluateJob / AdversarialLearningAgent::evaluateJob.
  *
- * warp = one episode (job, iteration).  Episodes are sequential (<= 1000 dependent steps) and every
- * episode follows its own path through the graph, so the first version (thread = episode) ran 32
- * different instruction streams per warp, serialised.  Now every lane of the warp carries a copy of
- * the (tiny) environment state and steps it redundantly — uniform control flow — while the team
- * evaluation of [UP] evaluateTeam is spread over the lanes: lane l interprets the program of the
- * team's l-th outgoing edge with the per-thread executor (dev_ops.cuh) and a warp reduction picks
- * the winner with the reference's order-dependent tie-break.  A second kernel averages the
- * iteration scores in iteration order (the reference's sequential `result += getScore()`).
+ * warp = up to 4 episodes (job, iteration), each on a power-of-two group of lanes at least as wide as the largest
+ * team of the graph (5 edges -> 8 lanes -> 4 episodes per warp).  Episodes are sequential (<= 1000 dependent steps)
+ * and every episode follows its own path through the graph, so the first version (thread = episode) ran 32
+ * different instruction streams per warp, serialised.  Now every lane of a group carries a copy of the (tiny)
+ * environment state and steps it redundantly — uniform control flow — while the team evaluation of [UP]
+ * evaluateTeam is spread over the lanes: lane l of the group interprets the program of the team's l-th outgoing
+ * edge with the per-thread executor (dev_ops.cuh) and a reduction inside the group picks the winner with the
+ * reference's order-dependent tie-break.  Consecutive episodes share a warp; the iterations of one job are
+ * consecutive, start from the same root and therefore mostly run the SAME programs on different states — the
+ * divergent per-lane interpreter then costs little more for four episodes than for one (the second version ran
+ * one episode per warp with 5.8 of 32 lanes active).  A second kernel averages the iteration scores in
+ * iteration order (the reference's sequential `result += getScore()`).
  *
  * Environment semantics, line by line: SURVEY.md Appendix B;
  *   gridworld  [REF] gridworld/src/gridworld.cpp:3-83
@@ -54,21 +58,31 @@ __device__ void ep_record_obs(const tpgx_episode_params& p, int slot, const tpgx
     for (; q < p.obs_len; q++) out[q] = 0.0;
 }
 
-/* [UP] executeFromRoot on one observation by one warp; every lane returns the action id or -1 (error bits in err). */
-__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err, int lane, ep_hits& h) {
+/* lane layout of a warp: `width` lanes per episode group (power of two), `sl` = lane inside its group */
+struct ep_group { int width, sl; unsigned mask; };
+
+/* [UP] executeFromRoot on one observation per lane group; warp-synchronous: every lane of the warp calls it, groups
+   with walk == false only take part in the shuffles.  Every lane of a walking group returns the action id, or -1
+   (error bits in err). */
+__device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_obs_view& o, ep_counters& c, int& err, const ep_group g, bool walk, ep_hits& h) {
     int visited[TPGX_MAX_PATH];
-    int depth = 0, cur = root;
-    for (;;) {
-        if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; return -1; }
-        visited[depth++] = cur;
-        if (lane == 0) c.team++;
-        const int eb = __ldg(p.team_edge_offset + cur), ee = __ldg(p.team_edge_offset + cur + 1);
+    int depth = 0, cur = root, action = -1;
+    while (__any_sync(0xffffffffu, walk)) {
+        int eb = 0, ee = 0;
+        if (walk) {
+            if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; walk = false; }
+            else {
+                visited[depth++] = cur;
+                if (g.sl == 0) c.team++;
+                eb = __ldg(p.team_edge_offset + cur); ee = __ldg(p.team_edge_offset + cur + 1);
+            }
+        }
         ep_cand best = {0.0, -1, 0};
-        for (int e0 = eb; e0 < ee; e0 += 32) {
+        for (int e0 = eb; __any_sync(0xffffffffu, walk && e0 < ee); e0 += g.width) {
             ep_cand mine = {0.0, -1, 0};
-            const int e = e0 + lane;
+            const int e = e0 + g.sl;
             int prog = -1;
-            if (e < ee) {
+            if (walk && e < ee) {
                 const int dst = __ldg(p.edge_destination + e);
                 bool seen = false;
                 if (dst >= 0)
@@ -85,20 +99,19 @@ __device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_ob
             }
             __syncwarp();
             if (p.hit_offset) { /* archive pass: the reference executes the admissible edges in list order = lane order */
-                const unsigned adm = __ballot_sync(0xffffffffu, prog >= 0);
-                const int nadm = __popc(adm), rank = __popc(adm & ((1u << lane) - 1u));
+                const unsigned adm = __ballot_sync(0xffffffffu, prog >= 0) & g.mask;
+                const int nadm = __popc(adm), rank = __popc(adm & ((1u << (threadIdx.x & 31)) - 1u));
                 while (h.pos < h.end) {
                     const int x = __ldg(p.hit_exec + h.pos) - h.base;
                     if (x >= nadm) break;
                     const int slot = __ldg(p.hit_slot + h.pos);
                     if (prog >= 0 && rank == x) { p.rec_program[slot] = prog; p.rec_bid[slot] = mine.bid; p.rec_step[slot] = h.step; }
-                    if (lane == 0 && p.rec_obs) ep_record_obs(p, slot, o);
+                    if (g.sl == 0 && p.rec_obs) ep_record_obs(p, slot, o);
                     h.pos++;
                 }
                 h.base += nadm;
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
+            for (int off = g.width >> 1; off > 0; off >>= 1) { /* stays inside the group: off < width */
                 ep_cand other;
                 other.bid = __shfl_xor_sync(0xffffffffu, mine.bid, off);
                 other.e = __shfl_xor_sync(0xffffffffu, mine.e, off);
@@ -107,10 +120,13 @@ __device__ int ep_traverse(const tpgx_episode_params& p, int root, const tpgx_ob
             }
             if (ep_better(mine, best, p.tie_break)) best = mine;
         }
-        if (best.e < 0) { err |= TPGX_DEV_NO_EDGE; return -1; }
-        if (best.dst < 0) return -1 - best.dst;
-        cur = best.dst;
+        if (walk) {
+            if (best.e < 0) { err |= TPGX_DEV_NO_EDGE; walk = false; }
+            else if (best.dst < 0) { action = -1 - best.dst; walk = false; }
+            else cur = best.dst;
+        }
     }
+    return action;
 }
 
 /* ---------------------------------------------------------------- gridworld */
@@ -254,11 +270,13 @@ struct TicTacToe {
 
 /* ---------------------------------------------------------------- pendulum */
 struct Pendulum {
-    double* hist; /* [300] reward history of the episode: ONE copy per warp in shared memory (every lane writes the same value) */
+    double* hist; /* [300] reward history of the episode, element i at hist[i * hs]: ONE copy per episode in shared memory (every thread that
+                     steps the episode writes the same value) */
+    int hs;
     double total, st[2];
     unsigned long long n_act;
     __device__ void reset(const tpgx_episode_params&, tpgx_rng_cursor& rng) {
-        for (int i = 0; i < 300; i++) hist[i] = 0.0; /* a fresh clone's history ({0.0}); never observable before 300 writes */
+        for (int i = 0; i < 300; i++) hist[i * hs] = 0.0; /* a fresh clone's history ({0.0}); never observable before 300 writes */
         st[0] = tpgx_rng_f64(rng, -TPGX_PI, TPGX_PI);
         st[1] = tpgx_rng_f64(rng, -1.0, 1.0);
         n_act = 0; total = 0.0;
@@ -273,7 +291,7 @@ struct Pendulum {
         double angle = st[0], velocity = st[1];
         const double atu = fmod((angle + TPGX_PI), (2.f * TPGX_PI)) - TPGX_PI;
         const double reward = -((atu * atu) + 0.2f * (velocity * velocity) + 0.01f * (cur * cur));
-        hist[n_act % 300] = reward;
+        hist[(int)(n_act % 300) * hs] = reward;
         n_act++;
         total += reward;
         velocity = velocity + ((-3.0) * 9.81 / (2.0 * 1.0) * (tpgx_math::sin(angle + TPGX_PI)) + (3.f / (1.0 * 1.0 * 1.0)) * cur) * 0.05;
@@ -285,10 +303,13 @@ struct Pendulum {
     __device__ bool is_terminal() const {
         bool r = false;
         if (n_act >= 300) {
+            /* the reference sums all 300 rewards in index order and tests |sum / 300| < 0.1.  Every reward is <= 0
+               (minus a sum of squares), so the partial sums never increase: once one is below -31 the full sum is
+               too and the test is false whatever follows — same boolean, without the 300-long dependent chain */
             double acc = 0.0;
-            for (int i = 0; i < 300; i++) acc += hist[i];
-            acc /= 300.0;
-            r = fabs(acc) < 0.1;
+            int i = 0;
+            for (; i < 300 && acc >= -31.0; i++) acc += hist[i * hs];
+            r = i == 300 && fabs(acc / 300.0) < 0.1;
         }
         return r;
     }
@@ -299,71 +320,231 @@ struct Pendulum {
     __device__ void summary(double* o) const { o[0] = st[0]; o[1] = st[1]; o[2] = total; o[3] = (double)n_act; }
 };
 
-template <class Env> struct ep_scratch { __device__ static void attach(Env&, double*) {} };
-template <> struct ep_scratch<Pendulum> { __device__ static void attach(Pendulum& e, double* s) { e.hist = s; } };
+template <class Env> struct ep_scratch { __device__ static void attach(Env&, double*, int) {} };
+template <> struct ep_scratch<Pendulum> { __device__ static void attach(Pendulum& e, double* s, int stride) { e.hist = s; e.hs = stride; } };
 
 #define EP_WARPS 4
+#define EP_MAX_GROUPS 4 /* episodes per warp (shared memory for the pendulum histories: EP_WARPS * EP_MAX_GROUPS * 304 doubles) */
+
 template <class Env>
 __global__ void __launch_bounds__(EP_WARPS * 32) tpgx_episode_kernel(const tpgx_episode_params p) {
-    __shared__ double s_scratch[EP_WARPS][304];
+    __shared__ double s_scratch[EP_WARPS][EP_MAX_GROUPS][304];
     const int NI = p.nb_iterations, K = p.roots_per_job;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gid = blockIdx.x * (long long)EP_WARPS + warp;     /* episode = (job, iteration) */
+    const int W = p.group_width, G = p.groups_per_warp;
+    const int grp = lane / W;                                         /* lanes past the last group idle along */
+    ep_group g;
+    g.width = W; g.sl = lane % W;
+    g.mask = (W == 32 ? 0xffffffffu : ((1u << W) - 1u)) << ((grp * W) & 31);
+    const long long gid = (blockIdx.x * (long long)EP_WARPS + warp) * G + grp; /* episode = (job, iteration) */
     const long long total = (long long)p.nb_jobs * NI;
+    const bool valid = grp < G && gid < total;
+    const bool archive_pass = p.hit_offset != nullptr;
     ep_counters c = {0, 0, 0, 0};
     int err = 0;
-    if (gid < total) {
-        const int j = (int)(gid / NI), it = (int)(gid % NI);
-        tpgx_rng_cursor rng;
-        rng.raw = p.rng_raw + (size_t)it * TPGX_RNG_TABLE;
-        rng.pos = 0;
-        rng.exhausted = 0;
-        ep_hits hits = {0, 0, 0, 0};
-        const bool archive_pass = p.hit_offset != nullptr;
-        if (archive_pass) { hits.pos = __ldg(p.hit_offset + gid); hits.end = __ldg(p.hit_offset + gid + 1); }
-        Env env;                                       /* replicated on every lane, stepped identically */
-        ep_scratch<Env>::attach(env, s_scratch[warp]);
-        env.reset(p, rng);
-        __syncwarp();
-        tpgx_obs_view o;
-        int n = 0, turn = 0;
-        while (!env.is_terminal() && n < p.max_actions) {
-            if (archive_pass && hits.pos >= hits.end) break; /* nothing (more) to resolve in this episode */
+    const int j = valid ? (int)(gid / NI) : 0, it = valid ? (int)(gid % NI) : 0;
+    tpgx_rng_cursor rng;
+    rng.raw = p.rng_raw + (size_t)it * TPGX_RNG_TABLE;
+    rng.pos = 0;
+    rng.exhausted = 0;
+    ep_hits hits = {0, 0, 0, 0};
+    if (archive_pass && valid) { hits.pos = __ldg(p.hit_offset + gid); hits.end = __ldg(p.hit_offset + gid + 1); }
+    Env env;                                       /* replicated on every lane of the group, stepped identically */
+    ep_scratch<Env>::attach(env, s_scratch[warp][grp < G ? grp : 0], 1);
+    if (valid) env.reset(p, rng);
+    __syncwarp();
+    tpgx_obs_view o;
+    int n = 0, turn = 0;
+    bool running = valid;
+    for (;;) {
+        /* nothing (more) to resolve in this episode ends an archive pass early */
+        running = running && !env.is_terminal() && n < p.max_actions && !(archive_pass && hits.pos >= hits.end);
+        if (!__any_sync(0xffffffffu, running)) break;
+        int root = 0;
+        if (running) {
             env.view(o);
-            const int root = __ldg(p.job_teams + (size_t)j * K + turn);
+            root = __ldg(p.job_teams + (size_t)j * K + turn);
             hits.step = n;
-            const int action = ep_traverse(p, root, o, c, err, lane, hits);
-            if (lane == 0) c.eval++;
-            if (action < 0) break;
-            if (lane == 0 && !archive_pass && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
-            __syncwarp();
-            if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; break; }
-            __syncwarp();
-            turn = (turn + 1 == K) ? 0 : turn + 1;
-            n++;
         }
-        if (lane == 0 && !archive_pass) {
-            for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
-            for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
-            p.episode_actions[gid] = n;
-            env.summary(p.final_state + (size_t)gid * 4);
+        const int action = ep_traverse(p, root, o, c, err, g, running, hits);
+        if (running) {
+            if (g.sl == 0) c.eval++;
+            if (action < 0) running = false;
+            else if (g.sl == 0 && !archive_pass && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
         }
-        if (rng.exhausted) err |= TPGX_DEV_RNG_EXHAUSTED;
+        __syncwarp();
+        if (running) {
+            if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; running = false; }
+            else {
+                turn = (turn + 1 == K) ? 0 : turn + 1;
+                n++;
+            }
+        }
+        __syncwarp();
     }
-    for (int o2 = 16; o2 > 0; o2 >>= 1) {
+    if (valid && g.sl == 0 && !archive_pass) {
+        for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
+        for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
+        p.episode_actions[gid] = n;
+        env.summary(p.final_state + (size_t)gid * 4);
+    }
+    if (rng.exhausted) err |= TPGX_DEV_RNG_EXHAUSTED;
+    for (int o2 = W >> 1; o2 > 0; o2 >>= 1) { /* totals of the group */
         c.eval += __shfl_xor_sync(0xffffffffu, c.eval, o2);
         c.team += __shfl_xor_sync(0xffffffffu, c.team, o2);
         c.prog += __shfl_xor_sync(0xffffffffu, c.prog, o2);
         c.line += __shfl_xor_sync(0xffffffffu, c.line, o2);
     }
-    if (lane == 0 && p.episode_progs && gid < total && p.hit_offset == nullptr) p.episode_progs[gid] = (int32_t)c.prog;
-    if (lane == 0) {
+    if (valid && g.sl == 0) {
+        if (p.episode_progs && !archive_pass) p.episode_progs[gid] = (int32_t)c.prog;
         atomicAdd(p.counters + 0, (unsigned long long)c.eval);
         atomicAdd(p.counters + 1, (unsigned long long)c.team);
         atomicAdd(p.counters + 2, (unsigned long long)c.prog);
         atomicAdd(p.counters + 3, (unsigned long long)c.line);
     }
     if (err) atomicOr(p.status, err);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Plain evaluation pass, latency-oriented mapping: CTA = one job x up to 32 of its iterations, lane = iteration
+ * (episode), warp = outgoing edge of the episode's current team.  The episodes of a job start every step at the same
+ * root team, so the lanes of a warp mostly interpret the SAME program on different states (no divergence), and the
+ * edges of a team run in parallel on different warps instead of one after the other on the lanes of one warp: the
+ * dependent chain of a step is one program, not the sum of the team's programs.  Every warp carries a replica of the
+ * episode state of its lanes and steps it identically, so all control flow — including the number of barriers — is
+ * the same in every warp; the candidates (bid, edge, destination) meet in shared memory once per team evaluation.
+ * The archive resolution pass (hit_offset != nullptr) stays on tpgx_episode_kernel.                              */
+#define EP2_MAX_WARPS 16
+template <class Env>
+__global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(const tpgx_episode_params p) {
+    extern __shared__ double s_hist[];                     /* pendulum: [300][lanes] */
+    __shared__ ep_cand s_cand[2][EP2_MAX_WARPS][32];
+    __shared__ unsigned int s_prog[32], s_line[32];
+    const int NI = p.nb_iterations, K = p.roots_per_job;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int j = blockIdx.y, it = blockIdx.x * 32 + lane;
+    const int lanes = min(32, NI - (int)blockIdx.x * 32);
+    const bool valid = it < NI;
+    const long long gid = (long long)j * NI + it;
+    if (w == 0) { s_prog[lane] = 0; s_line[lane] = 0; }
+    ep_counters c = {0, 0, 0, 0};
+    int err = 0;
+    tpgx_rng_cursor rng;
+    rng.raw = p.rng_raw + (size_t)(valid ? it : 0) * TPGX_RNG_TABLE;
+    rng.pos = 0;
+    rng.exhausted = 0;
+    Env env;                                               /* replicated in every warp, stepped identically */
+    ep_scratch<Env>::attach(env, s_hist + lane, lanes);
+    if (valid) env.reset(p, rng);
+    __syncthreads();
+    tpgx_obs_view o;
+    int n = 0, turn = 0, buf = 0;
+    bool running = valid;
+    for (;;) {
+        running = running && !env.is_terminal() && n < p.max_actions;
+        if (!__any_sync(0xffffffffu, running)) break;
+        int cur = 0;
+        if (running) {
+            env.view(o);
+            cur = __ldg(p.job_teams + (size_t)j * K + turn);
+        }
+        /* [UP] executeFromRoot, one team per round: warp w takes edges w, w + nw, ... of every lane's current team */
+        int visited[TPGX_MAX_PATH];
+        int depth = 0, action = -1;
+        bool walk = running;
+        while (__any_sync(0xffffffffu, walk)) {
+            int eb = 0, ee = 0;
+            if (walk) {
+                if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; walk = false; }
+                else {
+                    visited[depth++] = cur;
+                    if (w == 0) c.team++;
+                    eb = __ldg(p.team_edge_offset + cur); ee = __ldg(p.team_edge_offset + cur + 1);
+                }
+            }
+            ep_cand best = {0.0, -1, 0};
+            for (int e0 = eb; __any_sync(0xffffffffu, walk && e0 < ee); e0 += nw) {
+                ep_cand mine = {0.0, -1, 0};
+                const int e = e0 + w;
+                if (walk && e < ee) {
+                    const int dst = __ldg(p.edge_destination + e);
+                    bool seen = false;
+                    if (dst >= 0)
+                        for (int v = 0; v < depth; v++) seen |= (visited[v] == dst);
+                    if (!seen) { /* admissible edge */
+                        const int prog = __ldg(p.edge_program + e);
+                        const int cb = __ldg(p.prog_offset + prog), nl = __ldg(p.prog_offset + prog + 1) - cb;
+                        double bid = tpgx_run_program(p.code + cb, nl, p.constants + (size_t)prog * p.nb_constants, o);
+                        if (bid != bid) bid = __longlong_as_double(0xfff0000000000000LL);
+                        c.prog++;
+                        c.line += (unsigned int)nl;
+                        mine.bid = bid; mine.e = e; mine.dst = dst;
+                    }
+                }
+                s_cand[buf][w][lane] = mine;
+                __syncthreads();                           /* one barrier per round: the buffers alternate */
+                for (int ww = 0; ww < nw; ww++) {
+                    const ep_cand other = s_cand[buf][ww][lane];
+                    if (ep_better(other, best, p.tie_break)) best = other;
+                }
+                buf ^= 1;
+            }
+            if (walk) {
+                if (best.e < 0) { err |= TPGX_DEV_NO_EDGE; walk = false; }
+                else if (best.dst < 0) { action = -1 - best.dst; walk = false; }
+                else cur = best.dst;
+            }
+        }
+        if (running) {
+            if (w == 0) c.eval++;
+            if (action < 0) running = false;
+            else {
+                if (w == 0 && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
+                if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; running = false; }
+                else {
+                    turn = (turn + 1 == K) ? 0 : turn + 1;
+                    n++;
+                }
+            }
+        }
+    }
+    if (valid && w == 0) {
+        for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
+        for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
+        p.episode_actions[gid] = n;
+        env.summary(p.final_state + (size_t)gid * 4);
+    }
+    if (rng.exhausted) err |= TPGX_DEV_RNG_EXHAUSTED;
+    if (valid && c.prog) { atomicAdd(&s_prog[lane], c.prog); atomicAdd(&s_line[lane], c.line); }
+    __syncthreads();
+    if (w == 0) {
+        if (valid && p.episode_progs) p.episode_progs[gid] = (int32_t)s_prog[lane];
+        c.prog = valid ? s_prog[lane] : 0u; c.line = valid ? s_line[lane] : 0u;
+        for (int o2 = 16; o2 > 0; o2 >>= 1) {
+            c.eval += __shfl_xor_sync(0xffffffffu, c.eval, o2);
+            c.team += __shfl_xor_sync(0xffffffffu, c.team, o2);
+            c.prog += __shfl_xor_sync(0xffffffffu, c.prog, o2);
+            c.line += __shfl_xor_sync(0xffffffffu, c.line, o2);
+        }
+        if (lane == 0) {
+            atomicAdd(p.counters + 0, (unsigned long long)c.eval);
+            atomicAdd(p.counters + 1, (unsigned long long)c.team);
+            atomicAdd(p.counters + 2, (unsigned long long)c.prog);
+            atomicAdd(p.counters + 3, (unsigned long long)c.line);
+        }
+    }
+    if (err) atomicOr(p.status, err);
+}
+
+template <class Env>
+static cudaError_t launch_cta(const tpgx_episode_params& p, size_t smem, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(tpgx_episode_cta_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    dim3 grid((p.nb_iterations + 31) / 32, p.nb_jobs);
+    tpgx_episode_cta_kernel<Env><<<grid, p.cta_warps * 32, smem, st>>>(p);
+    return cudaGetLastError();
 }
 
 /* [UP] evaluateJob: result += getScore() over iterations in order, then result / nbIterations */
@@ -382,7 +563,25 @@ __global__ void tpgx_job_score_kernel(const tpgx_episode_params p) {
 cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) {
     const long long total = (long long)p.nb_jobs * p.nb_iterations;
     const int threads = EP_WARPS * 32;
-    const unsigned blocks = (unsigned)((total + EP_WARPS - 1) / EP_WARPS);
+    const int W = p.group_width;
+    if (W < 1 || W > 32 || (W & (W - 1)) || p.groups_per_warp < 1 || p.groups_per_warp > EP_MAX_GROUPS || p.groups_per_warp * W > 32) return cudaErrorInvalidValue;
+    const long long per_block = (long long)EP_WARPS * p.groups_per_warp;
+    const unsigned blocks = (unsigned)((total + per_block - 1) / per_block);
+    if (p.cta_warps > 0 && !p.hit_offset) { /* one CTA per job, warp = edge, lane = iteration */
+        if (p.cta_warps > EP2_MAX_WARPS) return cudaErrorInvalidValue;
+        cudaError_t e;
+        switch (p.env) {
+        case TPGX_ENV_GRIDWORLD: e = launch_cta<GridWorld>(p, 0, st); break;
+        case TPGX_ENV_STICKGAME: e = launch_cta<StickGame>(p, 0, st); break;
+        case TPGX_ENV_TICTACTOE: e = launch_cta<TicTacToe>(p, 0, st); break;
+        case TPGX_ENV_PENDULUM: e = launch_cta<Pendulum>(p, (size_t)300 * 8 * (p.nb_iterations < 32 ? p.nb_iterations : 32), st); break;
+        default: return cudaErrorInvalidValue;
+        }
+        if (e != cudaSuccess) return e;
+        const int n = p.nb_jobs * p.roots_per_job;
+        tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+        return cudaGetLastError();
+    }
     switch (p.env) {
     case TPGX_ENV_GRIDWORLD: tpgx_episode_kernel<GridWorld><<<blocks, threads, 0, st>>>(p); break;
     case TPGX_ENV_STICKGAME: tpgx_episode_kernel<StickGame><<<blocks, threads, 0, st>>>(p); break;

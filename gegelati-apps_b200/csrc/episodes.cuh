@@ -13,6 +13,9 @@
 struct tpgx_episode_params {
     int env, mode, nb_iterations, max_actions, nb_jobs, roots_per_job, second_player_random, trace_steps;
     int tie_break, nb_constants, nb_pendulum_actions;
+    int group_width;              /* lanes per episode: power of two >= the largest team's edge count, <= 32 */
+    int groups_per_warp;          /* episodes per warp: 1..4, groups_per_warp * group_width <= 32          */
+    int cta_warps;                /* > 0: the plain pass runs tpgx_episode_cta_kernel with that many edge warps */
     double pendulum_actions[16];
     const uint64_t* rng_raw;      /* [nb_iterations][TPGX_RNG_TABLE] raw mt19937_64 outputs          */
     const int32_t* job_teams;     /* [nb_jobs][roots_per_job] root team ids                          */

@@ -789,6 +789,25 @@ static tpgx_status episodes_impl(tpgx_ctx* ctx, const tpgx_episode_request* req,
     ep.nb_constants = ctx->cfg.nb_constants;
     ep.nb_pendulum_actions = req->nb_pendulum_actions;
     for (int i = 0; i < req->nb_pendulum_actions && i < 16; i++) ep.pendulum_actions[i] = req->pendulum_actions[i];
+    {   /* lanes per episode: a team's edges are spread over a power-of-two lane group.  Several episodes share a warp
+           only when there are enough of them to keep ~4 warps on every scheduler anyway: the kernel is bound by the
+           latency of each episode's dependent steps, and a packed warp runs its groups' divergent programs one after
+           the other (measured: stick game 100 x 100 episodes 1.21 -> 0.80 ms packed by 4; pendulum 500 x 5 episodes
+           49 -> 57 ms, so that one stays at one episode per warp) */
+        int deg = 1;
+        for (size_t t = 0; t + 1 < ctx->flat.team_edge_offset.size(); t++) deg = std::max(deg, ctx->flat.team_edge_offset[t + 1] - ctx->flat.team_edge_offset[t]);
+        int w = 1;
+        while (w < deg && w < 32) w <<= 1;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->cfg.device);
+        int g = std::min(4, 32 / w);
+        while (g > 1 && (long long)J * NI / g < 16ll * sms) g >>= 1;
+        if (const char* v = getenv("TPGX_EP_GROUPS")) { const int f = atoi(v); if (f >= 1 && f <= 4 && f * w <= 32) g = f; }
+        ep.group_width = w;
+        ep.groups_per_warp = g;
+        ep.cta_warps = std::min(deg, 16);
+        if (const char* v = getenv("TPGX_EP_CTA_WARPS")) { const int f = atoi(v); if (f >= 0 && f <= 16) ep.cta_warps = f; }
+    }
     /* RNG streams: every root sees the same seed per iteration ([UP] evaluateJob), so the raw
        mt19937_64 outputs are generated once per iteration on the host and shared by all jobs */
     std::vector<uint64_t> raw((size_t)NI * TPGX_RNG_TABLE);

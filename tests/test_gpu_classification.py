@@ -143,7 +143,7 @@ def test_variants_agree(oracle_mod, monkeypatch):
     img, lab = tpgx.synthetic_images(333, seed=3)
     g = tpgx.synthetic_graph("mnist", roots=10, edges=5, lines=15, depth=2, seed=9)
     ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=("score", "bid", "action", "confusion", "counters"))
-    for v in range(5):
+    for v in range(9):
         monkeypatch.setenv("TPGX_K1_VARIANT", str(v))
         ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
         ev.set_graph(g)
