@@ -76,12 +76,23 @@ __device__ __forceinline__ double tpgx_run_program(const uint32_t* __restrict__ 
                                                    const tpgx_obs_view& o) {
     double reg[TPGX_MAX_REGS];
     double res = 0.0;
+    uint32_t next = n > 0 ? __ldg(code) : 0u;
     for (int i = 0; i < n; i++) {
-        const uint32_t w = __ldg(code + i);
+        const uint32_t w = next;
+        if (i + 1 < n) next = __ldg(code + i + 1); /* the next line's word is in flight while this line runs */
         const uint32_t op = w & 31u, dst = (w >> 5) & 7u;
         const uint32_t fa = (w >> 8) & 0xfffu, fb = w >> 20;
         const uint32_t ka = fa >> 10, la = fa & 1023u, kb = fb >> 10, lb = fb & 1023u;
-        if (op == TPGX_OP_SOBEL_MAGN || op == TPGX_OP_SOBEL_DIR) {
+        if ((TPGX_MASK_A_DOUBLE >> op) & 1u) { /* the common case first: double operands */
+            double a, b = 0.0;
+            if (ka == TPGX_KIND_REG) a = (la < TPGX_LOC_ZERO) ? reg[la] : 0.0;
+            else a = o.f64[ka - 2][la];
+            if ((TPGX_MASK_B_DOUBLE >> op) & 1u) {
+                if (kb == TPGX_KIND_REG) b = (lb < TPGX_LOC_ZERO) ? reg[lb] : 0.0;
+                else b = o.f64[kb - 2][lb];
+            } else if (op == TPGX_OP_MULC) b = consts[lb];
+            res = tpgx_apply_dd<true>(op, a, b);
+        } else if (op == TPGX_OP_SOBEL_MAGN || op == TPGX_OP_SOBEL_DIR) {
             const int s = (int)ka - 2;
             const double* base = o.f64[s] + la;
             const int wd = o.width[s];
@@ -97,14 +108,7 @@ __device__ __forceinline__ double tpgx_run_program(const uint32_t* __restrict__ 
         } else if (op == TPGX_OP_CAST_I) {
             res = (double)o.i32[ka - 2][la];
         } else {
-            double a = 0.0, b = 0.0;
-            if (ka == TPGX_KIND_REG) a = (la < TPGX_LOC_ZERO) ? reg[la] : 0.0;
-            else a = o.f64[ka - 2][la];
-            if ((TPGX_MASK_B_DOUBLE >> op) & 1u) {
-                if (kb == TPGX_KIND_REG) b = (lb < TPGX_LOC_ZERO) ? reg[lb] : 0.0;
-                else b = o.f64[kb - 2][lb];
-            } else if (op == TPGX_OP_MULC) b = consts[lb];
-            res = tpgx_apply_dd<true>(op, a, b);
+            res = tpgx_apply_dd<true>(op, 0.0, 0.0); /* no operand (pi) */
         }
         reg[dst] = res;
     }
