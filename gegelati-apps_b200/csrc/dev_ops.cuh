@@ -76,7 +76,7 @@ __device__ __forceinline__ double tpgx_run_program(const uint32_t* __restrict__ 
                                                    const tpgx_obs_view& o) {
     double reg[TPGX_MAX_REGS];
     double res = 0.0;
-    uint32_t next = n > 0 ? __ldg(code) : 0u;
+    uint32_t next = n > 0 ? __ldg(code) : 0u, prev = 0xffffffffu;
     for (int i = 0; i < n; i++) {
         const uint32_t w = next;
         if (i + 1 < n) next = __ldg(code + i + 1); /* the next line's word is in flight while this line runs */
@@ -84,11 +84,15 @@ __device__ __forceinline__ double tpgx_run_program(const uint32_t* __restrict__ 
         const uint32_t fa = (w >> 8) & 0xfffu, fb = w >> 20;
         const uint32_t ka = fa >> 10, la = fa & 1023u, kb = fb >> 10, lb = fb & 1023u;
         if ((TPGX_MASK_A_DOUBLE >> op) & 1u) { /* the common case first: double operands */
+            /* a register operand that names the previous line's destination is that line's result, still in `res`:
+               most operands of an effective program are, and it keeps the local-memory round trip off the chain */
             double a, b = 0.0;
-            if (ka == TPGX_KIND_REG) a = (la < TPGX_LOC_ZERO) ? reg[la] : 0.0;
+            if (fa == prev) a = res;
+            else if (ka == TPGX_KIND_REG) a = (la < TPGX_LOC_ZERO) ? reg[la] : 0.0;
             else a = o.f64[ka - 2][la];
             if ((TPGX_MASK_B_DOUBLE >> op) & 1u) {
-                if (kb == TPGX_KIND_REG) b = (lb < TPGX_LOC_ZERO) ? reg[lb] : 0.0;
+                if (fb == prev) b = res;
+                else if (kb == TPGX_KIND_REG) b = (lb < TPGX_LOC_ZERO) ? reg[lb] : 0.0;
                 else b = o.f64[kb - 2][lb];
             } else if (op == TPGX_OP_MULC) b = consts[lb];
             res = tpgx_apply_dd<true>(op, a, b);
@@ -111,6 +115,7 @@ __device__ __forceinline__ double tpgx_run_program(const uint32_t* __restrict__ 
             res = tpgx_apply_dd<true>(op, 0.0, 0.0); /* no operand (pi) */
         }
         reg[dst] = res;
+        prev = dst; /* as an operand field: kind REG (0) << 10 | dst */
     }
     return res;
 }
