@@ -10,6 +10,7 @@
  * graph bookkeeping, mutation, selection, archive ring.
  */
 #include <cmath>
+#include <chrono>
 #include <cstring>
 #include <deque>
 #include <map>
@@ -33,7 +34,12 @@ struct TTeam {
 };
 struct ARec { int prog; double bid; std::vector<double> obs; };
 /* a program created by this populate: still to be mutated / behaviour-checked against its origin */
-struct NewProg { int id; std::vector<tpgx_line> parent_lines; double parent_consts[TPGX_MAX_CONSTS]; };
+struct NewProg {
+    int id;
+    std::vector<tpgx_line> parent_lines;
+    double parent_consts[TPGX_MAX_CONSTS];
+    std::mt19937_64 rng; /* [UP] mutateNewProgramBehaviors gives every new program its own RNG, seeded from the agent's */
+};
 
 } // namespace
 
@@ -61,8 +67,12 @@ struct tpgx_trainer {
     std::vector<int32_t> v_teo, v_ep, v_ed, v_roots;
     std::vector<int> v_prog_id, v_root_team;
 
-    uint64_t u64(uint64_t lo, uint64_t hi) { return std::uniform_int_distribution<uint64_t>(lo, hi)(rng); } /* [UP] RNG::getUnsignedInt64 */
-    double dbl() { return std::uniform_real_distribution<double>(0.0, 1.0)(rng); }                          /* [UP] RNG::getDouble(0, 1) */
+    std::vector<uint32_t> prog_mark; /* mutate_team: programs already on the team carry the current stamp */
+    uint32_t stamp = 0;
+    std::vector<size_t> cand_scratch;
+    std::mt19937_64* cur = nullptr; /* the engine u64() / dbl() draw from: the agent's, or a new program's own while it is being mutated */
+    uint64_t u64(uint64_t lo, uint64_t hi) { return std::uniform_int_distribution<uint64_t>(lo, hi)(cur ? *cur : rng); } /* [UP] RNG::getUnsignedInt64 */
+    double dbl() { return std::uniform_real_distribution<double>(0.0, 1.0)(cur ? *cur : rng); }                          /* [UP] RNG::getDouble(0, 1) */
 
     /* ---- bookkeeping ---- */
     int new_prog() {
@@ -207,11 +217,16 @@ struct tpgx_trainer {
             remove_edge(team, idx);
         }
         while ((int)T.edges.size() < P.max_outgoing_edges && dbl() < P.p_edge_addition) {
-            std::vector<size_t> cand;
+            /* candidates: the pre-existing edges whose program is not on this team yet (programs of the team stamped, so
+               the scan is one test per edge: it used to be the bulk of a generation's host time) */
+            if (prog_mark.size() < progs.size()) prog_mark.resize(progs.size() * 2, 0u);
+            stamp++;
+            for (const TEdge& e : T.edges) prog_mark[(size_t)e.prog] = stamp;
+            std::vector<size_t>& cand = cand_scratch;
+            cand.clear();
             for (size_t i = 0; i < pre_edges.size(); i++) {
-                bool has = !progs[pre_edges[i].prog].alive || (pre_edges[i].dest >= 0 && !teams[pre_edges[i].dest].alive);
-                for (const TEdge& e : T.edges) has |= e.prog == pre_edges[i].prog;
-                if (!has) cand.push_back(i);
+                const TEdge& pe = pre_edges[i];
+                if (prog_mark[(size_t)pe.prog] != stamp && progs[pe.prog].alive && (pe.dest < 0 || teams[pe.dest].alive)) cand.push_back(i);
             }
             if (cand.empty()) break;
             const TEdge& e = pre_edges[cand[u64(0, cand.size() - 1)]];
@@ -288,7 +303,21 @@ struct tpgx_trainer {
     /* ---- [UP] mutateNewProgramBehaviors: mutate every new program; with forceProgramBehaviorChangeOnMutation, again
        until it behaves differently from its origin and from every archived program on the archived observations ---- */
     tpgx_status settle_new_programs(std::vector<NewProg>& fresh, const tpgx_train_backend* be, int* retries) {
-        for (NewProg& n : fresh) mutate_program(progs[n.id]);
+        /* every new program mutates with an engine of its own, so its chain of mutants does not depend on how the
+           other programs fare: the behaviour test below can try several mutants of a program in ONE backend call
+           and keep the first that passes — same result as trying them one call at a time */
+        static const bool trace = getenv("TPGX_TRACE") != nullptr;
+        auto tick = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) {
+            if (!trace) return;
+            const auto t = std::chrono::steady_clock::now();
+            fprintf(stderr, "[tpgx] settle: %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tick).count());
+            tick = t;
+        };
+        for (NewProg& n : fresh) n.rng.seed(u64(0, UINT64_MAX));
+        struct Scope { tpgx_trainer* t; Scope(tpgx_trainer* t_, std::mt19937_64* e) : t(t_) { t->cur = e; } ~Scope() { t->cur = nullptr; } };
+        for (NewProg& n : fresh) { Scope sc(this, &n.rng); mutate_program(progs[n.id]); }
+        lap("seed + first mutation");
         if (!P.force_program_behavior_change || archive.empty() || fresh.empty()) return TPGX_OK;
         if (!be || !be->execute) { err = "forceProgramBehaviorChangeOnMutation needs a backend to run the new programs on the archive"; return TPGX_ERR_BAD_ARG; }
         /* the distinct archived observations ([UP] the archive keys its data-handler copies by hash) and, per archived
@@ -305,49 +334,87 @@ struct tpgx_trainer {
             by_prog[r.prog][it->second] = r.bid;
         }
         const int64_t count = (int64_t)obs_index.size();
+        /* archived programs recorded on every archived observation: the only ones that can make a candidate a duplicate */
+        std::vector<std::vector<double>> full;
+        for (const auto& kv : by_prog)
+            if ((int64_t)kv.second.size() == count) {
+                full.emplace_back((size_t)count);
+                for (const auto& ob : kv.second) full.back()[(size_t)ob.first] = ob.second;
+            }
+        lap("archive index");
         const double tau = 1e-4; /* [UP] Archive::areProgramResultsUnique default tolerance */
         auto close = [&](double a, double b) { return a == b || std::fabs(a - b) <= tau; };
+        const int max_attempts = 16, nC = cfg.nb_constants;
         std::vector<size_t> pending(fresh.size());
         for (size_t i = 0; i < fresh.size(); i++) pending[i] = i;
-        for (int round = 0; round < 16 && !pending.empty(); round++) {
-            /* a scratch graph: [mutant, origin] per pending program, one team pointing at all of them */
-            const int M = (int)pending.size(), nC = cfg.nb_constants;
+        /* attempts tried per backend call: 4 first (most programs pass within a few), then all that are left */
+        for (int done = 0; done < max_attempts && !pending.empty();) {
+            const int S = done == 0 ? 4 : max_attempts - done;
+            const int M = (int)pending.size();
+            /* candidates of pending program i: c[0] = its current mutant, c[k] = one more mutation of c[k-1] */
+            std::vector<TProg> cand((size_t)M * S);
+            for (int i = 0; i < M; i++) {
+                NewProg& n = fresh[pending[i]];
+                Scope sc(this, &n.rng);
+                cand[(size_t)i * S] = progs[n.id];
+                for (int k = 1; k < S; k++) { cand[(size_t)i * S + k] = cand[(size_t)i * S + k - 1]; mutate_program(cand[(size_t)i * S + k]); }
+            }
+            lap("candidates");
+            /* a scratch graph: per pending program its S candidates then its origin, one team pointing at all of them */
+            const int per = S + 1, NP = M * per;
             std::vector<int64_t> off(1, 0);
             std::vector<tpgx_line> lines;
-            std::vector<double> consts((size_t)2 * M * (size_t)std::max(1, nC), 0.0);
-            std::vector<int32_t> teo = {0, 2 * M}, ep((size_t)2 * M), ed((size_t)2 * M, -1), root = {0};
+            std::vector<double> consts((size_t)NP * (size_t)std::max(1, nC), 0.0);
+            std::vector<int32_t> teo = {0, NP}, ep((size_t)NP), ed((size_t)NP, -1), root = {0};
             for (int i = 0; i < M; i++) {
                 const NewProg& n = fresh[pending[i]];
-                const TProg& mp = progs[n.id];
-                lines.insert(lines.end(), mp.lines.begin(), mp.lines.end());
-                off.push_back((int64_t)lines.size());
+                for (int k = 0; k < S; k++) {
+                    const TProg& c = cand[(size_t)i * S + k];
+                    lines.insert(lines.end(), c.lines.begin(), c.lines.end());
+                    off.push_back((int64_t)lines.size());
+                    for (int q = 0; q < nC; q++) consts[(size_t)(i * per + k) * nC + q] = c.consts[q];
+                }
                 lines.insert(lines.end(), n.parent_lines.begin(), n.parent_lines.end());
                 off.push_back((int64_t)lines.size());
-                for (int c = 0; c < nC; c++) { consts[(size_t)(2 * i) * nC + c] = mp.consts[c]; consts[(size_t)(2 * i + 1) * nC + c] = n.parent_consts[c]; }
-                ep[2 * i] = 2 * i; ep[2 * i + 1] = 2 * i + 1;
+                for (int q = 0; q < nC; q++) consts[(size_t)(i * per + S) * nC + q] = n.parent_consts[q];
             }
-            tpgx_graph g{2 * M, off.data(), lines.data(), nullptr, nC > 0 ? consts.data() : nullptr, 1, teo.data(), ep.data(), ed.data(), 1, root.data()};
-            std::vector<double> bid((size_t)2 * M * (size_t)count);
+            for (int q = 0; q < NP; q++) ep[q] = q;
+            tpgx_graph g{NP, off.data(), lines.data(), nullptr, nC > 0 ? consts.data() : nullptr, 1, teo.data(), ep.data(), ed.data(), 1, root.data()};
+            std::vector<double> bid((size_t)NP * (size_t)count);
+            lap("scratch graph");
             const tpgx_status st = be->execute(be->user, &g, count, obs.data(), obs_len, bid.data());
             if (st != TPGX_OK) { err = "backend execute failed"; return st; }
+            lap("backend execute");
             std::vector<size_t> again;
             for (int i = 0; i < M; i++) {
-                const double* bm = bid.data() + (size_t)(2 * i) * count;
-                const double* bp = bm + count;
-                bool differs = false;
-                for (int64_t k = 0; k < count && !differs; k++) differs = !close(bm[k], bp[k]);
-                /* [UP] areProgramResultsUnique: an archived program with a recording on every archived observation and
-                   all of them within tau of the candidate makes the candidate a duplicate */
-                bool unique = differs;
-                for (auto it = by_prog.begin(); unique && it != by_prog.end(); ++it) {
-                    if ((int64_t)it->second.size() != count) continue;
-                    bool same = true;
-                    for (const auto& kv : it->second) if (!close(bm[kv.first], kv.second)) { same = false; break; }
-                    unique = !same;
+                const double* bp = bid.data() + (size_t)(i * per + S) * count; /* the origin's bids */
+                int pick = -1;
+                for (int k = 0; k < S && pick < 0; k++) {
+                    const double* bm = bid.data() + (size_t)(i * per + k) * count;
+                    bool differs = false;
+                    for (int64_t q = 0; q < count && !differs; q++) differs = !close(bm[q], bp[q]);
+                    /* [UP] areProgramResultsUnique: an archived program with a recording on every archived observation and
+                       all of them within tau of the candidate makes the candidate a duplicate */
+                    bool unique = differs;
+                    for (size_t f = 0; unique && f < full.size(); f++) {
+                        bool same = true;
+                        for (int64_t q = 0; q < count && same; q++) same = close(bm[q], full[f][(size_t)q]);
+                        unique = !same;
+                    }
+                    if (unique) pick = k; else (*retries)++;
                 }
-                if (!unique) { mutate_program(progs[fresh[pending[i]].id]); again.push_back(pending[i]); (*retries)++; }
+                NewProg& n = fresh[pending[i]];
+                if (pick >= 0) progs[n.id] = cand[(size_t)i * S + pick];
+                else { /* all S failed: one more mutation of the last one opens the next call (a retry like the others) */
+                    progs[n.id] = cand[(size_t)i * S + S - 1];
+                    Scope sc(this, &n.rng);
+                    mutate_program(progs[n.id]);
+                    again.push_back(pending[i]);
+                }
             }
             pending.swap(again);
+            done += S;
+            lap("uniqueness checks");
         }
         return TPGX_OK;
     }
@@ -460,8 +527,13 @@ tpgx_status tpgx_trainer_decimate(tpgx_trainer* t, const double* root_scores, tp
 tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_backend* be, uint64_t generation, tpgx_train_stats* stats) {
     if (!t || !be || !be->evaluate) return TPGX_ERR_BAD_ARG;
     tpgx_train_stats s{};
+    static const bool trace = getenv("TPGX_TRACE") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const auto t0 = now();
     tpgx_status st = tpgx_trainer_populate(t, be, &s);
     if (st != TPGX_OK) return st;
+    const auto t1 = now();
     tpgx_graph g{};
     t->build_view(&g);
     const int R = g.nb_roots, cap = t->P.archive_size;
@@ -472,6 +544,7 @@ tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_back
     int32_t nrec = 0;
     st = be->evaluate(be->user, &g, generation, aseed.data(), t->P.archiving_probability, cap, scores.data(), rprog.data(), rbid.data(), robs.data(), t->obs_len, &nrec);
     if (st != TPGX_OK) { t->err = "backend evaluate failed"; return st; }
+    const auto t2 = now();
     if (nrec < 0 || nrec > std::max(0, cap)) { t->err = "backend returned more archive records than archive_size"; return TPGX_ERR_STATE; }
     for (int i = 0; i < nrec; i++) {
         if (rprog[i] < 0 || rprog[i] >= (int32_t)t->v_prog_id.size()) { t->err = "backend returned an archive record for an unknown program"; return TPGX_ERR_STATE; }
@@ -485,6 +558,8 @@ tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_back
     tpgx_train_stats d{};
     st = tpgx_trainer_decimate(t, scores.data(), &d);
     if (st != TPGX_OK) return st;
+    if (trace) fprintf(stderr, "[tpgx] generation %llu: populate %.3f ms (%d new programs, %d behaviour retries), evaluate + archive %.3f ms, archive merge + decimate %.3f ms\n",
+                       (unsigned long long)generation, ms(t0, t1), s.nb_new_programs, s.behaviour_retries, ms(t1, t2), ms(t2, now()));
     if (stats) {
         *stats = d;
         stats->nb_new_programs = s.nb_new_programs;
