@@ -67,6 +67,20 @@ struct tpgx_trainer {
     std::vector<int32_t> v_teo, v_ep, v_ed, v_roots;
     std::vector<int> v_prog_id, v_root_team;
 
+    bool defer_archive = false;      /* set while no program id can be reused (decimation): unref_prog only notes the deleted programs */
+    std::vector<int> dead_progs;
+    void purge_archive() {
+        if (!dead_progs.empty()) {
+            std::vector<char> dead(progs.size(), 0);
+            for (int id : dead_progs) dead[(size_t)id] = 1;
+            std::deque<ARec> kept;
+            for (ARec& r : archive)
+                if (!dead[(size_t)r.prog]) kept.push_back(std::move(r));
+            archive.swap(kept);
+            dead_progs.clear();
+        }
+        defer_archive = false;
+    }
     std::vector<uint32_t> prog_mark; /* mutate_team: programs already on the team carry the current stamp */
     uint32_t stamp = 0;
     std::vector<size_t> cand_scratch;
@@ -89,6 +103,7 @@ struct tpgx_trainer {
         progs[id].lines.clear();
         free_progs.push_back(id);
         /* [UP] the archive forgets the recordings of deleted programs */
+        if (defer_archive) { dead_progs.push_back(id); return; } /* decimation: one pass over the archive for all of them */
         for (size_t i = 0; i < archive.size();)
             if (archive[i].prog == id) archive.erase(archive.begin() + (long)i); else i++;
     }
@@ -513,7 +528,12 @@ tpgx_status tpgx_trainer_decimate(tpgx_trainer* t, const double* root_scores, tp
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return root_scores[a] < root_scores[b]; });
     int kill = (int)std::floor(t->P.ratio_deleted_roots * (double)t->P.nb_roots);
     kill = std::min(kill, (int)roots.size() - 1);
+    static const bool trace = getenv("TPGX_TRACE") != nullptr;
+    const auto c0 = std::chrono::steady_clock::now();
+    t->defer_archive = true;
     for (int i = 0; i < kill; i++) t->remove_team(roots[idx[i]]);
+    t->purge_archive();
+    if (trace) fprintf(stderr, "[tpgx] decimate: remove %d teams %.3f ms\n", kill, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count());
     if (stats) {
         fill_graph_stats(t, stats);
         stats->nb_removed_roots = kill;
