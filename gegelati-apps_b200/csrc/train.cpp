@@ -67,6 +67,12 @@ struct tpgx_trainer {
     std::vector<int32_t> v_teo, v_ep, v_ed, v_roots;
     std::vector<int> v_prog_id, v_root_team;
 
+    /* mutate_team's index of the valid pre-existing edges (see there) */
+    const void* pre_built = nullptr;
+    uint64_t deaths = 0, pre_deaths = 0;
+    std::vector<size_t> pre_valid;
+    std::vector<int> pre_pos;
+    std::map<int, std::vector<int>> pre_by_prog;
     bool defer_archive = false;      /* set while no program id can be reused (decimation): unref_prog only notes the deleted programs */
     std::vector<int> dead_progs;
     void purge_archive() {
@@ -100,6 +106,7 @@ struct tpgx_trainer {
     void unref_prog(int id) {
         if (--progs[id].refs > 0) return;
         progs[id].alive = false;
+        deaths++;
         progs[id].lines.clear();
         free_progs.push_back(id);
         /* [UP] the archive forgets the recordings of deleted programs */
@@ -232,19 +239,37 @@ struct tpgx_trainer {
             remove_edge(team, idx);
         }
         while ((int)T.edges.size() < P.max_outgoing_edges && dbl() < P.p_edge_addition) {
-            /* candidates: the pre-existing edges whose program is not on this team yet (programs of the team stamped, so
-               the scan is one test per edge: it used to be the bulk of a generation's host time) */
+            /* candidates, in pre_edges order: the still valid pre-existing edges (program alive, destination team alive)
+               whose program is not on this team yet.  The valid ones are indexed once (and again after a program died,
+               which is rare while populating); per addition only the few edges of the team's programs are taken out
+               — scanning all pre-existing edges here used to be the bulk of a generation's host time. */
+            if (pre_built != &pre_edges || pre_deaths != deaths) {
+                pre_built = &pre_edges; pre_deaths = deaths;
+                pre_valid.clear(); pre_pos.assign(pre_edges.size(), -1); pre_by_prog.clear();
+                for (size_t i = 0; i < pre_edges.size(); i++) {
+                    const TEdge& pe = pre_edges[i];
+                    if (progs[pe.prog].alive && (pe.dest < 0 || teams[pe.dest].alive)) {
+                        pre_pos[i] = (int)pre_valid.size();
+                        pre_valid.push_back(i);
+                        pre_by_prog[pe.prog].push_back((int)i);
+                    }
+                }
+            }
             if (prog_mark.size() < progs.size()) prog_mark.resize(progs.size() * 2, 0u);
             stamp++;
-            for (const TEdge& e : T.edges) prog_mark[(size_t)e.prog] = stamp;
-            std::vector<size_t>& cand = cand_scratch;
-            cand.clear();
-            for (size_t i = 0; i < pre_edges.size(); i++) {
-                const TEdge& pe = pre_edges[i];
-                if (prog_mark[(size_t)pe.prog] != stamp && progs[pe.prog].alive && (pe.dest < 0 || teams[pe.dest].alive)) cand.push_back(i);
+            std::vector<size_t>& out = cand_scratch; /* positions (in pre_valid) that are NOT candidates */
+            out.clear();
+            for (const TEdge& e : T.edges) {
+                if (prog_mark[(size_t)e.prog] == stamp) continue;
+                prog_mark[(size_t)e.prog] = stamp;
+                const auto it = pre_by_prog.find(e.prog);
+                if (it != pre_by_prog.end()) for (int i : it->second) out.push_back((size_t)pre_pos[(size_t)i]);
             }
-            if (cand.empty()) break;
-            const TEdge& e = pre_edges[cand[u64(0, cand.size() - 1)]];
+            if (pre_valid.size() == out.size()) break;
+            size_t r = u64(0, pre_valid.size() - out.size() - 1); /* r-th candidate = r-th valid position not taken out */
+            std::sort(out.begin(), out.end());
+            for (size_t x : out) { if (x <= r) r++; else break; }
+            const TEdge& e = pre_edges[pre_valid[r]];
             add_edge(team, e.prog, e.dest);
         }
         bool any = false;
@@ -500,6 +525,7 @@ tpgx_status tpgx_trainer_populate(tpgx_trainer* t, const tpgx_train_backend* bac
     std::vector<TEdge> pre_edges;
     for (int tm : t->order) for (const TEdge& e : t->teams[tm].edges) pre_edges.push_back(e);
     const std::vector<int> pre_teams = t->order;
+    t->pre_built = nullptr;
     std::vector<NewProg> fresh;
     int nb_roots = (int)parents.size();
     while (nb_roots < t->P.nb_roots) {
