@@ -389,7 +389,8 @@ struct tpgx_trainer {
         for (size_t i = 0; i < fresh.size(); i++) pending[i] = i;
         /* attempts tried per backend call: 4 first (most programs pass within a few), then all that are left */
         for (int done = 0; done < max_attempts && !pending.empty();) {
-            const int S = done == 0 ? 4 : max_attempts - done;
+            int S = done == 0 ? 4 : max_attempts - done;
+            if (const char* v = getenv("TPGX_TRAIN_ATTEMPTS_PER_CALL")) { const int f = atoi(v); if (f >= 1) S = std::min(f, max_attempts - done); } /* tests: 1 = one mutant per call */
             const int M = (int)pending.size();
             /* candidates of pending program i: c[0] = its current mutant, c[k] = one more mutation of c[k-1] */
             std::vector<TProg> cand((size_t)M * S);

@@ -93,3 +93,29 @@ def test_pendulum_golden_graph_vs_glibc_oracle(oracle_mod):
     dev, ref = ev.evaluate_episodes(A.ENV_PENDULUM, **kw), o_std.evaluate_episodes(A.ENV_PENDULUM, **kw)
     assert np.array_equal(dev["episode_actions"], ref["episode_actions"])
     assert np.allclose(dev["episode_score"], ref["episode_score"], rtol=1e-9, atol=0)
+
+
+@pytest.mark.parametrize("env_var,value", [("TPGX_EP_CTA_WARPS", "0"), ("TPGX_EP_CTA_WARPS", "2"), ("TPGX_EP_CTA_WARPS", "16"),
+                                           ("TPGX_EP_GROUPS", "4"), ("TPGX_EP_GROUPS", "2")])
+@pytest.mark.parametrize("app", ["pendulum", "stickgame", "tictactoe"])
+def test_episode_kernel_mappings_agree(oracle_mod, monkeypatch, app, env_var, value):
+    """The plain pass runs one CTA per job (warp = edge, lane = iteration) with as many edge warps as the largest team has
+    edges; fewer warps (teams evaluated in several rounds), more warps than edges, and the lane-group kernel
+    (TPGX_EP_CTA_WARPS=0: 1, 2 or 4 episodes per warp) must all give the oracle's bits."""
+    monkeypatch.setenv(env_var, value)
+    if env_var == "TPGX_EP_GROUPS":
+        monkeypatch.setenv("TPGX_EP_CTA_WARPS", "0")
+    edges = {"pendulum": 5, "stickgame": 5, "tictactoe": 7}[app]
+    g = tpgx.synthetic_graph(app, roots=24, edges=edges, lines=10, depth=3, share_prob=0.1, seed=21)
+    ev, o = pair(oracle_mod, app, g)
+    if app == "pendulum":
+        kw = dict(seeds=np.arange(5, dtype=np.uint64) + 40, job_roots=np.arange(24), max_actions=400, pendulum_actions=PEND_ACTIONS, trace_steps=64)
+        dev = ev.evaluate_episodes(A.ENV_PENDULUM, **kw)
+        check(dev, o.evaluate_episodes(A.ENV_PENDULUM, **kw))
+    elif app == "stickgame":
+        kw = dict(seeds=np.arange(37, dtype=np.uint64) + 3, job_roots=np.arange(24), max_actions=11, second_player_random=1, trace_steps=11)
+        check(ev.evaluate_episodes(A.ENV_STICKGAME, **kw), o.evaluate_episodes(A.ENV_STICKGAME, **kw))
+    else:
+        jobs = np.random.default_rng(2).integers(0, 24, (30, 2))
+        kw = dict(seeds=np.arange(3, dtype=np.uint64) + 100, job_roots=jobs, roots_per_job=2, max_actions=9, second_player_random=0, trace_steps=9)
+        check(ev.evaluate_episodes(A.ENV_TICTACTOE, **kw), o.evaluate_episodes(A.ENV_TICTACTOE, **kw))

@@ -112,3 +112,20 @@ def test_gridworld_training_learns_with_the_oracle_backend(oracle_mod):
     assert all(np.array_equal(np.sort(sc)[::-1][0], s["best_score"]) for sc, s in zip(log, stats))
     assert stats[-1]["archive_records"] > 0 and sum(s["behaviour_retries"] for s in stats) >= 0
     assert all(s["nb_roots"] == 60 and s["nb_removed_roots"] == 30 for s in stats)
+
+
+def test_batched_behaviour_test_equals_one_mutant_per_call(oracle_mod, monkeypatch):
+    """Every new program mutates with an engine of its own, so trying several successive mutants of a program in one
+    backend call (the default: 4, then the remaining 12) must give the evolution of one mutant per call."""
+    prints = []
+    for attempts in (None, "1", "3"):
+        if attempts is None:
+            monkeypatch.delenv("TPGX_TRAIN_ATTEMPTS_PER_CALL", raising=False)
+        else:
+            monkeypatch.setenv("TPGX_TRAIN_ATTEMPTS_PER_CALL", attempts)
+        tr, _ = make(seed=9, **SMALL)
+        be = oracle_backend(oracle_mod, "gridworld", nb_iterations=1, max_actions=100)
+        stats = [tr.train_generation(be, gen) for gen in range(6)]
+        prints.append((tr.fingerprint(), [s["behaviour_retries"] for s in stats], [s["best_score"] for s in stats]))
+    assert sum(prints[0][1]) > 0, "the behaviour test never had to retry: the case does not exercise it"
+    assert prints[0] == prints[1] == prints[2]
