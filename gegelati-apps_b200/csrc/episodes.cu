@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(EP_WARPS * 32) tpgx_episode_kernel(const tpgx_
  * dependent chain of a step is one program, not the sum of the team's programs.  Every warp carries a replica of the
  * episode state of its lanes and steps it identically, so all control flow — including the number of barriers — is
  * the same in every warp; the candidates (bid, edge, destination) meet in shared memory once per team evaluation.
- * The archive resolution pass (hit_offset != nullptr) stays on tpgx_episode_kernel.                              */
+ * Serves the plain pass and the archive resolution pass (hit_offset != nullptr); tpgx_episode_kernel above is the
+ * alternative mapping (cta_warps == 0).                                                                          */
 #define EP2_MAX_WARPS 16
 template <class Env>
 __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(const tpgx_episode_params p) {
@@ -433,6 +434,9 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
     rng.raw = p.rng_raw + (size_t)(valid ? it : 0) * TPGX_RNG_TABLE;
     rng.pos = 0;
     rng.exhausted = 0;
+    const bool archive_pass = p.hit_offset != nullptr;     /* resolution pass of the archive: see tpgx_episode_params */
+    ep_hits hits = {0, 0, 0, 0};                           /* replicated in every warp like the rest of the episode state */
+    if (archive_pass && valid) { hits.pos = __ldg(p.hit_offset + gid); hits.end = __ldg(p.hit_offset + gid + 1); }
     Env env;                                               /* replicated in every warp, stepped identically */
     ep_scratch<Env>::attach(env, s_hist + lane, lanes);
     if (valid) env.reset(p, rng);
@@ -441,12 +445,13 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
     int n = 0, turn = 0, buf = 0;
     bool running = valid;
     for (;;) {
-        running = running && !env.is_terminal() && n < p.max_actions;
+        running = running && !env.is_terminal() && n < p.max_actions && !(archive_pass && hits.pos >= hits.end);
         if (!__any_sync(0xffffffffu, running)) break;
         int cur = 0;
         if (running) {
             env.view(o);
             cur = __ldg(p.job_teams + (size_t)j * K + turn);
+            hits.step = n;
         }
         /* [UP] executeFromRoot, one team per round: warp w takes edges w, w + nw, ... of every lane's current team */
         int visited[TPGX_MAX_PATH];
@@ -483,9 +488,23 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
                 }
                 s_cand[buf][w][lane] = mine;
                 __syncthreads();                           /* one barrier per round: the buffers alternate */
+                int nadm = 0, rank = 0;                    /* admissible edges of this round / of them, before this warp's */
                 for (int ww = 0; ww < nw; ww++) {
                     const ep_cand other = s_cand[buf][ww][lane];
+                    nadm += other.e >= 0;
+                    rank += (other.e >= 0) & (ww < w);
                     if (ep_better(other, best, p.tie_break)) best = other;
+                }
+                if (archive_pass && walk) { /* the reference executes the admissible edges in list order = warp order */
+                    while (hits.pos < hits.end) {
+                        const int x = __ldg(p.hit_exec + hits.pos) - hits.base;
+                        if (x >= nadm) break;
+                        const int slot = __ldg(p.hit_slot + hits.pos);
+                        if (mine.e >= 0 && rank == x) { p.rec_program[slot] = __ldg(p.edge_program + mine.e); p.rec_bid[slot] = mine.bid; p.rec_step[slot] = hits.step; }
+                        if (w == 0 && p.rec_obs) ep_record_obs(p, slot, o);
+                        hits.pos++;
+                    }
+                    hits.base += nadm;
                 }
                 buf ^= 1;
             }
@@ -499,7 +518,7 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
             if (w == 0) c.eval++;
             if (action < 0) running = false;
             else {
-                if (w == 0 && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
+                if (w == 0 && !archive_pass && p.trace_steps > 0 && n < p.trace_steps) p.trace[(size_t)gid * p.trace_steps + n] = (int8_t)action;
                 if (!env.do_action(p, action, rng)) { err |= TPGX_DEV_BAD_ACTION; running = false; }
                 else {
                     turn = (turn + 1 == K) ? 0 : turn + 1;
@@ -508,7 +527,7 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
             }
         }
     }
-    if (valid && w == 0) {
+    if (valid && w == 0 && !archive_pass) {
         for (int q = n; q < p.trace_steps; q++) p.trace[(size_t)gid * p.trace_steps + q] = -1;
         for (int k = 0; k < K; k++) p.episode_score[(size_t)gid * K + k] = env.score(k);
         p.episode_actions[gid] = n;
@@ -518,7 +537,7 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
     if (valid && c.prog) { atomicAdd(&s_prog[lane], c.prog); atomicAdd(&s_line[lane], c.line); }
     __syncthreads();
     if (w == 0) {
-        if (valid && p.episode_progs) p.episode_progs[gid] = (int32_t)s_prog[lane];
+        if (valid && p.episode_progs && !archive_pass) p.episode_progs[gid] = (int32_t)s_prog[lane];
         c.prog = valid ? s_prog[lane] : 0u; c.line = valid ? s_line[lane] : 0u;
         for (int o2 = 16; o2 > 0; o2 >>= 1) {
             c.eval += __shfl_xor_sync(0xffffffffu, c.eval, o2);
@@ -567,7 +586,7 @@ cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) 
     if (W < 1 || W > 32 || (W & (W - 1)) || p.groups_per_warp < 1 || p.groups_per_warp > EP_MAX_GROUPS || p.groups_per_warp * W > 32) return cudaErrorInvalidValue;
     const long long per_block = (long long)EP_WARPS * p.groups_per_warp;
     const unsigned blocks = (unsigned)((total + per_block - 1) / per_block);
-    if (p.cta_warps > 0 && !p.hit_offset) { /* one CTA per job, warp = edge, lane = iteration */
+    if (p.cta_warps > 0) { /* one CTA per job, warp = edge, lane = iteration */
         if (p.cta_warps > EP2_MAX_WARPS) return cudaErrorInvalidValue;
         cudaError_t e;
         switch (p.env) {
@@ -578,6 +597,7 @@ cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) 
         default: return cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return e;
+        if (p.hit_offset) return cudaSuccess; /* archive pass: scores were produced by the counting pass */
         const int n = p.nb_jobs * p.roots_per_job;
         tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
         return cudaGetLastError();
