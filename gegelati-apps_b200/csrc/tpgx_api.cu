@@ -922,8 +922,10 @@ tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req
     if (out->observation && out->obs_len < 1) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_archive_episodes: obs_len missing");
     tpgx_episode_result scratch_out{};
     std::vector<int32_t> progs;
+    Trace tr("archive_episodes");
     tpgx_status st = episodes_impl(ctx, req, eval_out ? eval_out : &scratch_out, &progs, nullptr);
     if (st != TPGX_OK) return st;
+    tr.lap("evaluation pass");
     out->nb_records = 0;
     const int J = req->nb_jobs, NI = req->nb_iterations, cap = arch->archive_size;
     if (cap == 0 || arch->probability == 0.0) return TPGX_OK;
@@ -947,6 +949,7 @@ tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req
             }
         }
     });
+    tr.lap("host replay of the draw streams");
     /* merged archive = the last `cap` recordings of the per-job archives concatenated in job order */
     int64_t total = 0;
     for (int j = 0; j < J; j++) total += (int64_t)job_hits[j].size();
@@ -974,7 +977,9 @@ tpgx_status tpgx_archive_episodes(tpgx_ctx* ctx, const tpgx_episode_request* req
     for (size_t i = 1; i < hp.hit_offset.size(); i++) hp.hit_offset[i] += hp.hit_offset[i - 1];
     hp.nb_records = (int)rec_job.size();
     if (hp.nb_records == 0) return TPGX_OK;
+    tr.lap("hit lists");
     if ((st = episodes_impl(ctx, req, &scratch_out, nullptr, &hp)) != TPGX_OK) return st;
+    tr.lap("resolution pass");
     out->nb_records = hp.nb_records;
     for (int i = 0; i < hp.nb_records; i++) {
         out->program[i] = hp.rec_program[i]; out->job[i] = rec_job[i]; out->iteration[i] = rec_it[i];
