@@ -120,3 +120,27 @@ def test_episode_archive_pendulum(oracle_mod):
     dev = ev.archive_episodes(A.ENV_PENDULUM, **kw)
     same_episodes(dev, o.archive_episodes(A.ENV_PENDULUM, **kw))
     assert len(dev["program"]) == 500
+
+
+@pytest.mark.parametrize("env_var,value", [("TPGX_EP_CTA_WARPS", "0"), ("TPGX_EP_CTA_WARPS", "3"), ("TPGX_EP_GROUPS", "4")])
+def test_episode_archive_kernel_mappings_agree(oracle_mod, monkeypatch, env_var, value):
+    """The resolution pass finds a recorded execution by its rank among the team's admissible edges: across the edge
+    warps of a CTA (several rounds with 3 warps for 6 edges), or across the lanes of a lane group."""
+    monkeypatch.setenv(env_var, value)
+    if env_var == "TPGX_EP_GROUPS":
+        monkeypatch.setenv("TPGX_EP_CTA_WARPS", "0")
+    g = tpgx.synthetic_graph("gridworld", roots=40, edges=6, lines=10, depth=3, share_prob=0.1, seed=31)
+    ev, o = pair_app(oracle_mod, "gridworld", g)
+    aseeds = np.random.default_rng(5).integers(0, 2 ** 63, 40).astype(np.uint64)
+    kw = dict(seeds=[3, 4, 5], job_roots=np.arange(40), max_actions=100, archive_seeds=aseeds, probability=0.05, archive_size=300, obs_len=2)
+    same_episodes(ev.archive_episodes(A.ENV_GRIDWORLD, **kw), o.archive_episodes(A.ENV_GRIDWORLD, **kw))
+
+
+def test_episode_archive_wide_teams(oracle_mod):
+    """45 edges per team: three rounds of 16 edge warps per team evaluation; ranks continue across the rounds."""
+    g = tpgx.synthetic_graph("tictactoe", roots=12, edges=45, lines=6, depth=2, seed=23)
+    ev, o = pair_app(oracle_mod, "tictactoe", g)
+    jobs = np.random.default_rng(3).integers(0, 12, (20, 2))
+    kw = dict(seeds=np.arange(4, dtype=np.uint64) + 11, job_roots=jobs, roots_per_job=2, max_actions=9, second_player_random=0,
+              archive_seeds=np.arange(20, dtype=np.uint64) + 9, probability=0.05, archive_size=200, obs_len=9)
+    same_episodes(ev.archive_episodes(A.ENV_TICTACTOE, **kw), o.archive_episodes(A.ENV_TICTACTOE, **kw))

@@ -119,3 +119,22 @@ def test_episode_kernel_mappings_agree(oracle_mod, monkeypatch, app, env_var, va
         jobs = np.random.default_rng(2).integers(0, 24, (30, 2))
         kw = dict(seeds=np.arange(3, dtype=np.uint64) + 100, job_roots=jobs, roots_per_job=2, max_actions=9, second_player_random=0, trace_steps=9)
         check(ev.evaluate_episodes(A.ENV_TICTACTOE, **kw), o.evaluate_episodes(A.ENV_TICTACTOE, **kw))
+
+
+def test_pendulum_more_iterations_than_lanes(oracle_mod):
+    """40 iterations per job: two CTAs per job (32 + 8 lanes), 76.8 KB of reward histories in dynamic shared memory, and
+    enough steps for the 300-entry history to wrap and for isTerminal's early exit to be exercised."""
+    g = tpgx.synthetic_graph("pendulum", roots=6, edges=5, lines=10, depth=2, seed=17)
+    ev, o = pair(oracle_mod, "pendulum", g)
+    kw = dict(seeds=np.arange(40, dtype=np.uint64) + 7, job_roots=np.arange(6), max_actions=700, pendulum_actions=PEND_ACTIONS, trace_steps=32)
+    check(ev.evaluate_episodes(A.ENV_PENDULUM, **kw), o.evaluate_episodes(A.ENV_PENDULUM, **kw))
+
+
+def test_wide_teams_take_several_rounds(oracle_mod):
+    """tic-tac-toe/params.json allows 60 outgoing edges: teams wider than the 16 edge warps of a CTA are evaluated in
+    several rounds, the admissible-edge order (ties, archive ranks) must survive that."""
+    g = tpgx.synthetic_graph("tictactoe", roots=12, edges=45, lines=6, depth=2, seed=23)
+    ev, o = pair(oracle_mod, "tictactoe", g)
+    jobs = np.random.default_rng(3).integers(0, 12, (20, 2))
+    kw = dict(seeds=np.arange(4, dtype=np.uint64) + 11, job_roots=jobs, roots_per_job=2, max_actions=9, second_player_random=0, trace_steps=9)
+    check(ev.evaluate_episodes(A.ENV_TICTACTOE, **kw), o.evaluate_episodes(A.ENV_TICTACTOE, **kw))
