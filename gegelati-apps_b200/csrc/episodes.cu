@@ -423,8 +423,8 @@ __global__ void __launch_bounds__(EP2_MAX_WARPS * 32) tpgx_episode_cta_kernel(co
     __shared__ unsigned int s_prog[32], s_line[32];
     const int NI = p.nb_iterations, K = p.roots_per_job;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int j = blockIdx.y, it = blockIdx.x * 32 + lane;
-    const int lanes = min(32, NI - (int)blockIdx.x * 32);
+    const int j = blockIdx.x, it = blockIdx.y * 32 + lane;  /* jobs on grid.x (no 65 535 limit), chunks of 32 iterations on grid.y */
+    const int lanes = min(32, NI - (int)blockIdx.y * 32);
     const bool valid = it < NI;
     const long long gid = (long long)j * NI + it;
     if (w == 0) { s_prog[lane] = 0; s_line[lane] = 0; }
@@ -561,7 +561,8 @@ static cudaError_t launch_cta(const tpgx_episode_params& p, size_t smem, cudaStr
         cudaError_t e = cudaFuncSetAttribute(tpgx_episode_cta_kernel<Env>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }
-    dim3 grid((p.nb_iterations + 31) / 32, p.nb_jobs);
+    dim3 grid(p.nb_jobs, (p.nb_iterations + 31) / 32);
+    if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
     tpgx_episode_cta_kernel<Env><<<grid, p.cta_warps * 32, smem, st>>>(p);
     return cudaGetLastError();
 }
