@@ -426,27 +426,28 @@ __global__ void tpgx_exec_generic_kernel(const uint32_t* __restrict__ code, cons
                                          long long count, const double* f0, const double* f1, const int32_t* i0,
                                          const int32_t* i1, int space0, int space1, int width0, int width1,
                                          double* __restrict__ bid) {
-    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const int p = blockIdx.y;
-    if (s >= count) return;
-    tpgx_obs_view o;
-    o.f64[0] = f0 ? f0 + s * space0 : nullptr;
-    o.f64[1] = f1 ? f1 + s * space1 : nullptr;
-    o.i32[0] = i0 ? i0 + s * space0 : nullptr;
-    o.i32[1] = i1 ? i1 + s * space1 : nullptr;
-    o.width[0] = width0;
-    o.width[1] = width1;
-    const int cb = prog_offset[p];
-    double r = tpgx_run_program(code + cb, prog_offset[p + 1] - cb, constants + (size_t)p * nb_constants, o);
-    if (r != r) r = __longlong_as_double(0xfff0000000000000LL);
-    bid[(size_t)p * count + s] = r;
+    /* programs on grid.x (no 65 535 limit on their number), observations on grid.y with a grid stride */
+    const int p = blockIdx.x;
+    const int cb = prog_offset[p], n = prog_offset[p + 1] - cb;
+    for (long long s = blockIdx.y * (long long)blockDim.x + threadIdx.x; s < count; s += (long long)gridDim.y * blockDim.x) {
+        tpgx_obs_view o;
+        o.f64[0] = f0 ? f0 + s * space0 : nullptr;
+        o.f64[1] = f1 ? f1 + s * space1 : nullptr;
+        o.i32[0] = i0 ? i0 + s * space0 : nullptr;
+        o.i32[1] = i1 ? i1 + s * space1 : nullptr;
+        o.width[0] = width0;
+        o.width[1] = width1;
+        double r = tpgx_run_program(code + cb, n, constants + (size_t)p * nb_constants, o);
+        if (r != r) r = __longlong_as_double(0xfff0000000000000LL);
+        bid[(size_t)p * count + s] = r;
+    }
 }
 
 cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
                                      int nb_programs, long long count, const double* f0, const double* f1, const int32_t* i0,
                                      const int32_t* i1, int space0, int space1, int width0, int width1, double* bid,
                                      cudaStream_t st) {
-    dim3 grid((unsigned)((count + 127) / 128), nb_programs);
+    dim3 grid(nb_programs, (unsigned)std::min<long long>((count + 127) / 128, 65535));
     tpgx_exec_generic_kernel<<<grid, 128, 0, st>>>(code, prog_offset, constants, nb_constants, nb_programs, count, f0, f1, i0,
                                                    i1, space0, space1, width0, width1, bid);
     return cudaGetLastError();
