@@ -273,7 +273,9 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         return fail(ctx, TPGX_ERR_BAD_ARG, "root range out of bounds");
     if (!req->sample_index && req->nb_samples > ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples exceeds uploaded observations");
     if (!ctx->labels_dev) return fail(ctx, TPGX_ERR_STATE, "classification needs labels");
+    Trace etr("enqueue_classification");
     CU(wait_for_observations(ctx));
+    etr.lap("wait for observations");
     const int nR = req->root_end - req->root_begin, C = req->nb_classes;
     const int64_t nS = req->nb_samples;
     const int ts = tpgx_bid_tile_samples(ctx->variant);
@@ -281,6 +283,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     const int hw = ctx->obs_hw;
     tpgx_status st = make_plan(ctx, req->root_begin, req->root_end, ts, keep_bid_single_pass);
     if (st != TPGX_OK) return st;
+    etr.lap("plan");
     const int nA = ctx->plan.nb_active;
 
     /* observation tiles */
@@ -302,6 +305,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         ctx->tiles_ts = ts;
     }
 
+    etr.lap("tiles + Sobel planes");
     /* pass planning: keep the bid matrix (or, in team mode, the decision matrix) of one pass within the budget */
     const bool team_mode = ctx->plan.team_mode;
     const int nU = ctx->plan.nb_units;
@@ -319,6 +323,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
     if (want_action) CU(ctx->d_action.ensure((size_t)nR * nS));
+    etr.lap("buffers");
 
     size_t ev = 0;
     for (int ps = 0; ps < passes; ps++) {
@@ -363,6 +368,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.decision = ctx->d_decision.as<int32_t>();
             bp.tie_break = ctx->cfg.tie_break;
             CU(tpgx_launch_bid(bp, nt, ctx->variant, ctx->plan.k1_ext, team_mode, ctx->stream));
+            etr.lap(team_mode ? "K1 launch (team mode)" : "K1 launch (bid mode)");
         }
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
         if (k1_only) break; /* bid matrix of the (single) pass is all the caller wants */
