@@ -147,17 +147,30 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk
     unsigned int c_eval = 0, c_team = 0, c_prog = 0, c_line = 0;
     int err = 0;
     const int s_begin = blockIdx.x * (TRAV_THREADS * TRAV_SPT);
+    /* the first decision (the root's) and the label of all of the thread's samples are requested up front: the walk is
+       a chain of dependent L2 round trips per sample, so the samples' chains have to overlap */
+    int first[TRAV_SPT];
+    int lab[TRAV_SPT];
+    const int2 root_stat = __ldg(p.team_stat + root);
+#pragma unroll
+    for (int it = 0; it < TRAV_SPT; it++) {
+        const int s = s_begin + it * TRAV_THREADS + threadIdx.x;
+        const bool in = s < p.nb_samples;
+        first[it] = in ? __ldg(p.decision + (size_t)root * p.row_stride + s) : 0;
+        lab[it] = (in && p.labels) ? (int)__ldg(p.labels + s) : 0;
+    }
+#pragma unroll
     for (int it = 0; it < TRAV_SPT; it++) {
         const int s = s_begin + it * TRAV_THREADS + threadIdx.x;
         if (s >= p.nb_samples) break;
         int cur = root, action = -1;
         for (int depth = 0;; depth++) {
             if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; break; }
-            const int2 st = __ldg(p.team_stat + cur);
+            const int2 st = depth == 0 ? root_stat : __ldg(p.team_stat + cur);
             c_team++;
             c_prog += (unsigned int)st.x;
             c_line += (unsigned int)st.y;
-            const int d = __ldg(p.decision + (size_t)cur * p.row_stride + s);
+            const int d = depth == 0 ? first[it] : __ldg(p.decision + (size_t)cur * p.row_stride + s);
             if (d < 0) { action = -1 - d; break; }
             cur = d;
         }
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk
         if (action >= 0) {
             if (p.action) p.action[(size_t)r * p.action_stride + s] = (uint8_t)action;
             if (p.labels) {
-                if (action < C) atomicAdd(&s_table[(int)__ldg(p.labels + s) * C + action], 1u);
+                if (action < C) atomicAdd(&s_table[lab[it] * C + action], 1u);
                 else err |= TPGX_DEV_BAD_ACTION;
             }
         }
