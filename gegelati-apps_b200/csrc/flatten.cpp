@@ -13,6 +13,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "k1v2_encode.h"
 #include "tpgx_internal.h"
 
 namespace {
@@ -274,4 +275,29 @@ extern "C" tpgx_status tpgx_flatten_programs(const tpgx_config* cfg, int32_t nb_
         memcpy(code, f.code.data(), f.code.size() * 4);
     }
     return TPGX_OK;
+}
+
+/* K1 v2 encoder on its own (host only; the device runs the same function): entry stream, entry count and
+ * shared-memory slots of one program given its packed generic words. */
+extern "C" tpgx_status tpgx_k1v2_encode_program(const uint32_t* words, int32_t nb_words, int32_t width, int32_t hw, int32_t nwin,
+                                                uint32_t* quads, int32_t quad_capacity, int32_t* nb_entries, int32_t* nb_slots) {
+    if ((!words && nb_words > 0) || nb_words < 0 || width < 1 || hw < 1) return TPGX_ERR_BAD_ARG;
+    const tpgx_k1v2_info count = tpgx_k1v2_encode(words, nb_words, 128u, (uint32_t)width, (uint32_t)hw, (uint32_t)nwin, nullptr);
+    if (nb_entries) *nb_entries = count.entries;
+    if (nb_slots) *nb_slots = count.slots;
+    if (!count.ok) return TPGX_ERR_UNSUPPORTED;
+    if (quads) {
+        if (quad_capacity < count.entries) return TPGX_ERR_BAD_ARG;
+        const tpgx_k1v2_info w = tpgx_k1v2_encode(words, nb_words, 128u, (uint32_t)width, (uint32_t)hw, (uint32_t)nwin, reinterpret_cast<tpgx_k1_quad*>(quads));
+        if (w.entries != count.entries || w.slots != count.slots) return TPGX_ERR_STATE;
+    }
+    return TPGX_OK;
+}
+extern "C" const char* tpgx_k1v2_handler_name(int32_t h) {
+    static const char* const names[] = {
+#define K1V2_NAME(n) #n,
+        K1V2_HANDLERS(K1V2_NAME)
+#undef K1V2_NAME
+    };
+    return (h >= 0 && h < K2H_COUNT) ? names[h] : nullptr;
 }

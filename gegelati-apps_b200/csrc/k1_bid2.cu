@@ -1,0 +1,521 @@
+/*
+ * k1_bid2.cu — K1 v2, the threaded bid interpreter (sm_100a) for the MNIST instruction set.
+ *
+ * Replaces [UP] Program::ProgramExecutionEngine::executeProgram + Data::*::getDataAt + the mnist app's
+ * instruction lambdas ([REF] mnist/src/main.cpp:47-88) and, in team mode, [UP] TPGExecutionEngine::evaluateTeam,
+ * like K1 v1 (k1_bid.cu) — same results bit for bit, about half the instructions per line.  What changed:
+ *
+ *   dispatch     the line loop is ONE inline-PTX block: fetch the 16-byte entry (broadcast LDS.128), then a
+ *                single warp-uniform indirect branch (brx.idx.uni -> LDC + BRX) to a handler specialised for
+ *                (operation, kind of A, kind of B).  No compare chains, no BSSY / BSYNC, no predicated loads of
+ *                the operand kind that is not there.
+ *   accumulator  the result of a line stays in 8 machine registers (4 samples per lane).  The encoder
+ *                (k1v2_encode.h) forwards it to the next line — 77 % of the register operands of effective
+ *                programs — and emits a store only for results that are read later than that (26 %).
+ *                Handler entry points fall through: <op>_RR loads A from its slot and continues into <op>_AR.
+ *   slots        live-range allocation leaves at most K1V2_SLOTS (5) shared-memory slots per warp instead of 8
+ *                fixed registers: 6.25 KB per warp incl. code buffers -> 32 warps per SM (v1: 24) and ~20 KB of L1 left.  Programs that need more run on v1.
+ *   scheduling   a persistent grid, one CTA per SM; every WARP pulls (tile, group of units) items from a global
+ *                counter, tile-major, so no CTA waits for its slowest warp and a shard of any size fills the
+ *                machine to the last item (v1 launched (chunks x tiles) CTAs in waves of 148).
+ *   arithmetic   identical sequences to tpgx_math.h (division, exp, ln, a*c/10), hand-scheduled in PTX so that
+ *                operands arrive in, and results leave in, the accumulator's registers; the rare operands
+ *                (subnormals, the slivers next to exp's overflow / underflow) leave the block and run the
+ *                C++ routines.
+ */
+#include <cuda_runtime.h>
+
+#include "dev_ops.cuh"
+#include "k1v2_encode.h"
+#include "kernels.cuh"
+
+#define K2_NW 32
+#define K2_TS 128
+#define K2_BUF (K1V2_CQ + K1V2_CAP) /* quads per code buffer */
+#define K2_TAB_BYTES (256 * 8 + 512 * 8)
+
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void k2_cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void k2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+struct k2_tab_shared {
+    uint32_t exp_addr, log_addr;
+    __device__ __forceinline__ void exp_entry(int i, double& tail, double& T) const {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tail), "=d"(T) : "r"(exp_addr + (uint32_t)i * 16u));
+    }
+    __device__ __forceinline__ void log_entry(int i, double& invc, double& logc_hi, double& logc_lo) const {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc_hi) : "r"(log_addr + (uint32_t)i * 32u));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(logc_lo) : "r"(log_addr + (uint32_t)i * 32u + 16u));
+    }
+};
+
+/* ---- the interpreter block --------------------------------------------------------------------------------
+ * operands of the asm statement */
+#define A0 "%0"
+#define A1 "%1"
+#define A2 "%2"
+#define A3 "%3"
+#define B0 "%4"
+#define B1 "%5"
+#define B2 "%6"
+#define B3 "%7"
+#define LP "%8"
+#define CODE "%9"
+#define REGS "%10"
+#define LANE "%11"
+#define GTILE "%12"
+#define SOBEL "%13"
+#define LUT "%14"
+#define CBASE "%15"
+#define EXPT "%16"
+#define LOGT "%17"
+
+
+/* IEEE-754 double constants of tpgx_math.h, as PTX literals */
+#define KD_INV_LN2N "0d40671547652B82FE"    /* 128 / ln2 */
+#define KD_MAGIC "0d4338000000000000"       /* 1.5 * 2^52 */
+#define KD_NEG_LN2N_HI "0dBF762E42FF000000" /* -(ln2 / 128) high part */
+#define KD_NEG_LN2N_LO "0d3D5718432A1B0E26" /* -(ln2 / 128) low part */
+#define KD_C1_6 "0d3FC5555555555555"
+#define KD_C1_24 "0d3FA5555555555555"
+#define KD_C1_120 "0d3F81111111111111"
+#define KD_HALF "0d3FE0000000000000"
+#define KD_X710 "0d4086300000000000"
+#define KD_XM746 "0dC087500000000000"
+#define KD_LN2_HI "0d3FE62E42FEFA3800"
+#define KD_LN2_LO "0d3D2EF35793C76730"
+#define KD_C1_7 "0d3FC2492492492492"
+#define KD_CM1_6 "0dBFC5555555555555"
+#define KD_C0_2 "0d3FC999999999999A"
+#define KD_CM0_25 "0dBFD0000000000000"
+#define KD_C1_3 "0d3FD5555555555555"
+#define KD_CM0_5 "0dBFE0000000000000"
+#define KD_ONE "0d3FF0000000000000"
+#define KD_MONE "0dBFF0000000000000"
+#define KD_T01 "0d3FB999999999999A"         /* RN(0.1) */
+#define KD_M10 "0dC024000000000000"
+#define KD_ZERO "0d0000000000000000"
+#define KD_INF "0d7FF0000000000000"
+#define KD_NINF "0dFFF0000000000000"
+#define KD_NAN "0d7FF8000000000000"
+
+/* exit codes of the interpreter block beyond the handler ids: operands of a heavy operation that need the
+   generic routine (tpgx_math.h).  Operands are left in the accumulator (and b) registers. */
+#define K2X_SLOW_DIV 1000
+#define K2X_SLOW_EXP 1001
+#define K2X_SLOW_LN 1002
+#define K2X_SLOW_MULC 1003
+
+/* tpgx_math::xdiv_k, one sample: quotient of a / b into q; pall &= (special | fast path accepted) */
+#define DIV1(a, b, q)                                                                            \
+    "rcp.approx.ftz.f64 sd, " b ";\n"                                                            \
+    "mov.b64 {alo, ahi}, " a ";\n mov.b64 {blo, bhi}, " b ";\n"                                  \
+    "and.b32 ha, ahi, 0x7fffffff;\n and.b32 hb, bhi, 0x7fffffff;\n"                              \
+    "or.b32 t0, ha, alo;\n setp.eq.u32 p1, t0, 0;\n setp.ge.u32 p2, ha, 0x7ff00000;\n or.pred pas, p1, p2;\n" \
+    "or.b32 t0, hb, blo;\n setp.eq.u32 p1, t0, 0;\n setp.ge.u32 p2, hb, 0x7ff00000;\n or.pred pbs, p1, p2;\n" \
+    "sub.u32 t0, hb, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fb00000;\n and.pred pas, pas, p1;\n or.pred psp, pbs, pas;\n" \
+    "mov.b64 {slo, shi}, sd;\n mov.b32 slo, 1;\n mov.b64 rr, {slo, shi};\n"                      \
+    "neg.f64 nb, " b ";\n"                                                                       \
+    "fma.rn.f64 t1, nb, rr, " KD_ONE ";\n fma.rn.f64 t1, t1, t1, t1;\n fma.rn.f64 r1, rr, t1, rr;\n" \
+    "fma.rn.f64 t2, nb, r1, " KD_ONE ";\n fma.rn.f64 r2, r1, t2, r1;\n"                           \
+    "mul.rn.f64 q0, " a ", r2;\n fma.rn.f64 rem, nb, q0, " a ";\n fma.rn.f64 " q ", r2, rem, q0;\n" \
+    "mov.b64 {qlo, qhi}, " q ";\n"                                                               \
+    "mov.b32 fq, qhi;\n mov.b32 fb, bhi;\n mov.b32 fa, ahi;\n"                                   \
+    "fma.rn.f32 ft, 0f00000000, fb, fq;\n abs.f32 ft, ft;\n setp.gt.f32 p1, ft, 0f00100000;\n"   \
+    "abs.f32 fa, fa;\n setp.ge.f32 p2, fa, 0f03600000;\n and.pred p1, p1, p2;\n"                 \
+    "or.pred p1, p1, psp;\n and.pred pall, pall, p1;\n"                                          \
+    "mul.rn.f64 sp, " a ", sd;\n selp.f64 " q ", sp, " q ", psp;\n"
+
+/* tpgx_math::exp_k, one sample (x in place).  EXP_RARE accumulates the sliver test, EXP_MAIN computes. */
+#define EXP_RARE(x, k)                                                                            \
+    "mov.b64 {xlo, xhi}, " x ";\n and.b32 ax, xhi, 0x7fffffff;\n setp.lt.u32 pm" k ", ax, 0x4085e000;\n" \
+    "setp.lt.f64 p1, " x ", " KD_X710 ";\n setp.le.f64 pt" k ", " x ", " KD_XM746 ";\n"            \
+    "not.pred p2, pm" k ";\n and.pred p1, p1, p2;\n not.pred p2, pt" k ";\n and.pred p1, p1, p2;\n or.pred prare, prare, p1;\n"
+#define EXP_MAIN(x, k)                                                                            \
+    "mul.rn.f64 z, " x ", " KD_INV_LN2N ";\n add.rn.f64 tm, z, " KD_MAGIC ";\n sub.rn.f64 kd, tm, " KD_MAGIC ";\n" \
+    "mov.b64 {ki, t0}, tm;\n"                                                                    \
+    "fma.rn.f64 r, kd, " KD_NEG_LN2N_HI ", " x ";\n fma.rn.f64 r, kd, " KD_NEG_LN2N_LO ", r;\n"   \
+    "and.b32 ii, ki, 127;\n shr.s32 ee, ki, 7;\n shl.b32 ii, ii, 4;\n add.u32 ii, ii, " EXPT ";\n" \
+    "ld.shared.v2.f64 {tail, TT}, [ii];\n"                                                       \
+    "mul.rn.f64 r2, r, r;\n fma.rn.f64 pa, r, " KD_C1_6 ", " KD_HALF ";\n fma.rn.f64 pb, r, " KD_C1_120 ", " KD_C1_24 ";\n" \
+    "add.rn.f64 tmp, tail, r;\n fma.rn.f64 tmp, r2, pa, tmp;\n mul.rn.f64 r4, r2, r2;\n fma.rn.f64 tmp, r4, pb, tmp;\n" \
+    "fma.rn.f64 y, TT, tmp, TT;\n"                                                               \
+    "mov.b64 {ylo, yhi}, y;\n shl.b32 ee, ee, 20;\n add.u32 yhi, yhi, ee;\n mov.b64 y, {ylo, yhi};\n" \
+    "add.rn.f64 ev, " x ", " KD_INF ";\n selp.f64 ev, " KD_ZERO ", ev, pt" k ";\n selp.f64 " x ", y, ev, pm" k ";\n"
+
+/* tpgx_math::log_k, one sample (x in place) */
+#define LN_RARE(x, k)                                                                             \
+    "mov.b64 {xlo, xhi}, " x ";\n setp.eq.f64 pz" k ", " x ", " KD_ZERO ";\n setp.lt.u32 p1, xhi, 0x00100000;\n" \
+    "not.pred p2, pz" k ";\n and.pred p1, p1, p2;\n or.pred prare, prare, p1;\n"
+#define LN_MAIN(x, k)                                                                             \
+    "mov.b64 {xlo, xhi}, " x ";\n"                                                               \
+    "sub.u32 t0, xhi, 0x3FE6B000;\n shr.u32 ii, t0, 13;\n and.b32 ii, ii, 127;\n shr.s32 kk, t0, 20;\n" \
+    "and.b32 t0, t0, 0xfff00000;\n sub.u32 t0, xhi, t0;\n mov.b64 z, {xlo, t0};\n"               \
+    "shl.b32 ii, ii, 5;\n add.u32 ii, ii, " LOGT ";\n ld.shared.v2.f64 {invc, lchi}, [ii];\n ld.shared.f64 lclo, [ii+16];\n" \
+    "fma.rn.f64 r, z, invc, " KD_MONE ";\n cvt.rn.f64.s32 kd, kk;\n fma.rn.f64 w, kd, " KD_LN2_HI ", lchi;\n add.rn.f64 hi, w, r;\n" \
+    "sub.rn.f64 lo, w, hi;\n add.rn.f64 lo, lo, r;\n fma.rn.f64 tmp, kd, " KD_LN2_LO ", lclo;\n add.rn.f64 lo, lo, tmp;\n" \
+    "mul.rn.f64 r2, r, r;\n fma.rn.f64 pa, r, " KD_C1_7 ", " KD_CM1_6 ";\n fma.rn.f64 pa, r, pa, " KD_C0_2 ";\n" \
+    "fma.rn.f64 pa, r, pa, " KD_CM0_25 ";\n fma.rn.f64 pa, r, pa, " KD_C1_3 ";\n fma.rn.f64 pa, r, pa, " KD_CM0_5 ";\n" \
+    "fma.rn.f64 tmp, r2, pa, lo;\n add.rn.f64 y, hi, tmp;\n"                                     \
+    "sub.u32 t0, xhi, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fe00000;\n"                           \
+    "add.rn.f64 ev, " x ", " x ";\n setp.lt.f64 p2, " x ", " KD_ZERO ";\n selp.f64 ev, " KD_NAN ", ev, p2;\n" \
+    "selp.f64 ev, " KD_NINF ", ev, pz" k ";\n selp.f64 " x ", y, ev, p1;\n"
+
+/* tpgx_math::xdiv10_k, one sample: x / 10 into q; pall &= accepted */
+#define DIV10_1(x, q)                                                                             \
+    "mul.rn.f64 q0, " x ", " KD_T01 ";\n fma.rn.f64 rem, " KD_M10 ", q0, " x ";\n fma.rn.f64 " q ", rem, " KD_T01 ", q0;\n" \
+    "mov.b64 {xlo, xhi}, " x ";\n and.b32 ha, xhi, 0x7fffffff;\n"                                \
+    "or.b32 t0, ha, xlo;\n setp.eq.u32 p1, t0, 0;\n setp.ge.u32 p2, ha, 0x7ff00000;\n or.pred psp, p1, p2;\n" \
+    "sub.u32 t0, ha, 0x01700000;\n setp.lt.u32 p1, t0, 0x7d000000;\n"                            \
+    "mov.b64 {qlo, qhi}, " q ";\n mov.b64 {slo, shi}, q0;\n xor.b32 t0, qhi, shi;\n and.b32 t0, t0, 0x7ff00000;\n setp.eq.u32 p2, t0, 0;\n" \
+    "and.pred p1, p1, p2;\n or.pred p1, p1, psp;\n and.pred pall, pall, p1;\n"                   \
+    "selp.f64 " q ", q0, " q ", psp;\n"
+
+/* 4 doubles of the lane from a shared-memory slot (byte offset in `f`) */
+#define LOAD_R(d0, d1, d2, d3, f)                          \
+    "add.u32 ra, " f ", " REGS ";\n"                       \
+    "ld.shared.v2.f64 {" d0 ", " d1 "}, [ra];\n"           \
+    "ld.shared.v2.f64 {" d2 ", " d3 "}, [ra+512];\n"
+/* 4 pixels of the lane (word index of lane 0 in `f`), uint8 -> double (exact) */
+#define LOAD_P(d0, d1, d2, d3, f)                          \
+    "add.u32 pw, " f ", " LANE ";\n"                       \
+    "mad.wide.u32 ga, pw, 4, " GTILE ";\n"                 \
+    "ld.global.nc.u32 pw, [ga];\n"                         \
+    "cvt.rn.f64.u8 " d0 ", pw;\n"                          \
+    "shr.u32 t0, pw, 8;\n"                                 \
+    "cvt.rn.f64.u8 " d1 ", t0;\n"                          \
+    "shr.u32 t0, pw, 16;\n"                                \
+    "cvt.rn.f64.u8 " d2 ", t0;\n"                          \
+    "shr.u32 t0, pw, 24;\n"                                \
+    "cvt.rn.f64.u8 " d3 ", t0;\n"
+#define LOAD_AR LOAD_R(A0, A1, A2, A3, "ya")
+#define LOAD_AP LOAD_P(A0, A1, A2, A3, "ya")
+#define LOAD_BR(f) LOAD_R(B0, B1, B2, B3, f)
+#define LOAD_BP(f) LOAD_P(B0, B1, B2, B3, f)
+#define MOV_B_A "mov.f64 " B0 ", " A0 ";\n mov.f64 " B1 ", " A1 ";\n mov.f64 " B2 ", " A2 ";\n mov.f64 " B3 ", " A3 ";\n"
+#define NEXT_LINE "bra.uni FETCH;\n"
+/* acc = acc op b / acc = b op acc / acc = acc op acc */
+#define OP_AB(op) op " " A0 ", " A0 ", " B0 ";\n" op " " A1 ", " A1 ", " B1 ";\n" op " " A2 ", " A2 ", " B2 ";\n" op " " A3 ", " A3 ", " B3 ";\n"
+#define OP_BA(op) op " " A0 ", " B0 ", " A0 ";\n" op " " A1 ", " B1 ", " A1 ";\n" op " " A2 ", " B2 ", " A2 ";\n" op " " A3 ", " B3 ", " A3 ";\n"
+#define OP_AA(op) op " " A0 ", " A0 ", " A0 ";\n" op " " A1 ", " A1 ", " A1 ";\n" op " " A2 ", " A2 ", " A2 ";\n" op " " A3 ", " A3 ", " A3 ";\n"
+/* [REF] mnist/src/main.cpp: max = (a < b) ? b : a  (NaN in a stays, NaN in b is dropped) */
+#define MAX1(a, b) "setp.lt.f64 pq, " a ", " b ";\n selp.f64 " a ", " b ", " a ", pq;\n"
+#define RMAX1(a, b) "setp.lt.f64 pq, " b ", " a ";\n selp.f64 " a ", " a ", " b ", pq;\n" /* a = (b < a) ? a : b, operand A in b */
+#define MAX_AB MAX1(A0, B0) MAX1(A1, B1) MAX1(A2, B2) MAX1(A3, B3)
+#define MAX_BA RMAX1(A0, B0) RMAX1(A1, B1) RMAX1(A2, B2) RMAX1(A3, B3)
+
+/* commutative binary operation: AA AR RR AP RP PP */
+#define BIN_COMM(N, op)                                                   \
+    "H_" N "_PP:\n" LOAD_AP "bra.uni H_" N "_AP;\n"                       \
+    "H_" N "_RP:\n" LOAD_AR                                               \
+    "H_" N "_AP:\n" LOAD_BP("zb") OP_AB(op) NEXT_LINE                     \
+    "H_" N "_RR:\n" LOAD_AR                                               \
+    "H_" N "_AR:\n" LOAD_BR("zb") OP_AB(op) NEXT_LINE                     \
+    "H_" N "_AA:\n" OP_AA(op) NEXT_LINE
+/* ordered binary operation: AA AR RR PR AP RP PP RA PA, with the given bodies */
+#define BIN_ORD(N, body_ab, body_ba, body_aa)                             \
+    "H_" N "_PP:\n" LOAD_AP "bra.uni H_" N "_AP;\n"                       \
+    "H_" N "_RP:\n" LOAD_AR                                               \
+    "H_" N "_AP:\n" LOAD_BP("zb") body_ab NEXT_LINE                       \
+    "H_" N "_PR:\n" LOAD_AP "bra.uni H_" N "_AR;\n"                       \
+    "H_" N "_RR:\n" LOAD_AR                                               \
+    "H_" N "_AR:\n" LOAD_BR("zb") body_ab NEXT_LINE                       \
+    "H_" N "_RA:\n" LOAD_BR("ya") body_ba NEXT_LINE                       \
+    "H_" N "_PA:\n" LOAD_BP("ya") body_ba NEXT_LINE                       \
+    "H_" N "_AA:\n" body_aa NEXT_LINE
+
+#define K2_TARGET(n) "H_" #n ", "
+
+template <bool TEAM>
+__global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid2_params p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* regs = smem;
+    uint4* codeb = reinterpret_cast<uint4*>(regs + K2_NW * K1V2_SLOTS * K2_TS * 8);
+    double* s_tab = reinterpret_cast<double*>(codeb + K2_NW * 2 * K2_BUF);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < 256 + 512; i += K2_NW * 32)
+        s_tab[i] = i < 256 ? tpgx_math::tpgx_exp_tab_dev[i] : tpgx_math::tpgx_log_tab_dev[i - 256];
+    const k2_tab_shared tabs = {k2_smem_u32(s_tab), k2_smem_u32(s_tab + 256)};
+    __syncthreads();
+    /* from here on every warp is on its own */
+    const uint32_t regs_lane = k2_smem_u32(regs) + warp * (K1V2_SLOTS * K2_TS * 8) + lane * 16;
+    const uint32_t mycode = k2_smem_u32(codeb + warp * (2 * K2_BUF));
+    const uint4* __restrict__ stream = p.stream;
+    const int tile_bytes = (p.hw + 1) * K2_TS;
+    const long long plane_stride = (long long)p.nwin * K2_TS; /* doubles per plane of a tile */
+
+    /* cursor over the rows (programs) this warp runs: item = (tile, group of units); unit = team or program */
+    struct Cur { int tile, unit, unit_end, row, row_end, first; };
+    auto claim = [&]() {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(p.work_counter, 1u);
+        return (int)__shfl_sync(0xffffffffu, i, 0);
+    };
+    auto open_unit = [&](Cur& c) {
+        const int2 t = TEAM ? __ldg(p.team + c.unit) : make_int2(c.unit, 1);
+        c.row = t.x; c.row_end = t.x + t.y; c.first = t.x;
+    };
+    auto open_item = [&](Cur& c) {
+        const int item = claim();
+        if (item >= p.nb_items) { c.tile = -1; return; }
+        c.tile = item / p.items_per_tile;
+        const int g = item - c.tile * p.items_per_tile;
+        c.unit = g * p.units_per_item;
+        c.unit_end = min(c.unit + p.units_per_item, p.nb_units);
+        open_unit(c);
+    };
+    auto advance = [&](Cur& c) {
+        if (++c.row < c.row_end) return;
+        if (++c.unit < c.unit_end) { open_unit(c); return; }
+        open_item(c);
+    };
+    auto load_desc = [&](const Cur& c) { return c.tile >= 0 ? __ldg(p.desc + c.row) : make_int2(0, 0); };
+    /* asynchronous copy of a program's constants + first block of entries into a code buffer */
+    auto stage = [&](uint32_t buf, const int2 d) {
+        const int nq = K1V2_CQ + min(d.y, K1V2_CAP);
+        for (int i = lane; i < nq; i += 32) k2_cp_async16(buf + i * 16, stream + d.x + i);
+        k2_cp_async_commit();
+    };
+
+    Cur c;
+    open_item(c);
+    int2 d0 = load_desc(c);
+    int cur = 0;
+    stage(mycode, d0);
+    double best[4];
+    int best_dst[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { best[k] = 0.0; best_dst[k] = 0; }
+
+    while (c.tile >= 0) {
+        Cur nx = c;
+        advance(nx);
+        const int2 d1 = load_desc(nx);
+        k2_cp_async_wait_all();
+        __syncwarp();
+        const uint32_t code = mycode + cur * (K2_BUF * 16);
+        stage(mycode + (cur ^ 1) * (K2_BUF * 16), d1); /* next program's code: in flight while this one runs */
+
+        const uint8_t* __restrict__ const gtile = p.tiles + (size_t)c.tile * tile_bytes;
+        const double* __restrict__ const sobel_tile = p.sobel + (size_t)c.tile * 2 * plane_stride;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        uint32_t lp = code + K1V2_CQ * 16;
+        int staged = min(d0.y, K1V2_CAP); /* entries of the program staged so far */
+        for (;;) {
+            uint32_t xc;
+            asm volatile(
+                "{\n"
+                ".reg .b32 hx, ya, zb, wd, ra, pw, t0;\n"
+                ".reg .b64 ga;\n"
+                ".reg .pred pq, p1, p2, pas, pbs, psp, pall, prare, pm0, pm1, pm2, pm3, pt0, pt1, pt2, pt3, pz0, pz1, pz2, pz3;\n"
+                ".reg .b32 alo, ahi, blo, bhi, ha, hb, slo, shi, qlo, qhi, xlo, xhi, ax, ki, ii, ee, kk, ylo, yhi;\n"
+                ".reg .f32 fq, fb, fa, ft;\n"
+                ".reg .f64 sd, rr, nb, t1, t2, r1, r2, q0, rem, sp, qr0, qr1, qr2, qr3, cst;\n"
+                ".reg .f64 z, tm, kd, r, tail, TT, pa, pb, tmp, r4, y, ev, invc, lchi, lclo, w, hi, lo;\n"
+                "tlist: .branchtargets " K1V2_HANDLERS(K2_TARGET) "H_END;\n"
+                "FETCH:\n"
+                "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n"
+                "add.u32 " LP ", " LP ", 16;\n"
+                "brx.idx.uni hx, tlist;\n"
+                "H_ST:\n"
+                "add.u32 ra, wd, " REGS ";\n"
+                "st.shared.v2.f64 [ra], {" A0 ", " A1 "};\n"
+                "st.shared.v2.f64 [ra+512], {" A2 ", " A3 "};\n"
+                NEXT_LINE
+                BIN_COMM("ADD", "add.rn.f64")
+                BIN_COMM("MUL", "mul.rn.f64")
+                BIN_ORD("SUB", OP_AB("sub.rn.f64"), OP_BA("sub.rn.f64"), OP_AA("sub.rn.f64"))
+                BIN_ORD("MAX", MAX_AB, MAX_BA, "")
+                /* Sobel planes: one 32-byte group per lane */
+                "H_SOBM:\n"
+                "H_SOBD:\n"
+                "add.u32 pw, ya, " LANE ";\n"
+                "mad.wide.u32 ga, pw, 32, " SOBEL ";\n"
+                "ld.global.nc.v2.f64 {" A0 ", " A1 "}, [ga];\n"
+                "ld.global.nc.v2.f64 {" A2 ", " A3 "}, [ga+16];\n"
+                NEXT_LINE
+                /* exp / ln of a pixel: 256-entry tables */
+                "H_LUTL:\n"
+                "add.u32 pw, ya, " LANE ";\n"
+                "mad.wide.u32 ga, pw, 4, " GTILE ";\n"
+                "ld.global.nc.u32 pw, [ga];\n"
+                "and.b32 t0, pw, 255;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A0 ", [ga+2048];\n"
+                "bfe.u32 t0, pw, 8, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A1 ", [ga+2048];\n"
+                "bfe.u32 t0, pw, 16, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A2 ", [ga+2048];\n"
+                "shr.u32 t0, pw, 24;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A3 ", [ga+2048];\n"
+                NEXT_LINE
+                "H_LUTE:\n"
+                "add.u32 pw, ya, " LANE ";\n"
+                "mad.wide.u32 ga, pw, 4, " GTILE ";\n"
+                "ld.global.nc.u32 pw, [ga];\n"
+                "and.b32 t0, pw, 255;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A0 ", [ga];\n"
+                "bfe.u32 t0, pw, 8, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A1 ", [ga];\n"
+                "bfe.u32 t0, pw, 16, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A2 ", [ga];\n"
+                "shr.u32 t0, pw, 24;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A3 ", [ga];\n"
+                NEXT_LINE
+                /* division: operands into (acc, b) in order, then the body */
+                "H_DIV_PP:\n" LOAD_AP "bra.uni H_DIV_AP;\n"
+                "H_DIV_RP:\n" LOAD_AR
+                "H_DIV_AP:\n" LOAD_BP("zb") "bra.uni DIVBODY;\n"
+                "H_DIV_PR:\n" LOAD_AP "bra.uni H_DIV_AR;\n"
+                "H_DIV_RR:\n" LOAD_AR
+                "H_DIV_AR:\n" LOAD_BR("zb") "bra.uni DIVBODY;\n"
+                "H_DIV_RA:\n" MOV_B_A LOAD_AR "bra.uni DIVBODY;\n"
+                "H_DIV_PA:\n" MOV_B_A LOAD_AP "bra.uni DIVBODY;\n"
+                "H_DIV_AA:\n" MOV_B_A
+                "DIVBODY:\n"
+                "setp.eq.u32 pall, 0, 0;\n"
+                DIV1(A0, B0, "qr0") DIV1(A1, B1, "qr1") DIV1(A2, B2, "qr2") DIV1(A3, B3, "qr3")
+                "vote.sync.all.pred p1, pall, 0xffffffff;\n"
+                "@!p1 bra.uni X_SLOW_DIV;\n"
+                "mov.f64 " A0 ", qr0;\n mov.f64 " A1 ", qr1;\n mov.f64 " A2 ", qr2;\n mov.f64 " A3 ", qr3;\n"
+                NEXT_LINE
+                "H_EXP_R:\n" LOAD_AR
+                "H_EXP_A:\n"
+                "setp.ne.u32 prare, 0, 0;\n"
+                EXP_RARE(A0, "0") EXP_RARE(A1, "1") EXP_RARE(A2, "2") EXP_RARE(A3, "3")
+                "vote.sync.any.pred p1, prare, 0xffffffff;\n"
+                "@p1 bra.uni X_SLOW_EXP;\n"
+                EXP_MAIN(A0, "0") EXP_MAIN(A1, "1") EXP_MAIN(A2, "2") EXP_MAIN(A3, "3")
+                NEXT_LINE
+                "H_LN_R:\n" LOAD_AR
+                "H_LN_A:\n"
+                "setp.ne.u32 prare, 0, 0;\n"
+                LN_RARE(A0, "0") LN_RARE(A1, "1") LN_RARE(A2, "2") LN_RARE(A3, "3")
+                "vote.sync.any.pred p1, prare, 0xffffffff;\n"
+                "@p1 bra.uni X_SLOW_LN;\n"
+                LN_MAIN(A0, "0") LN_MAIN(A1, "1") LN_MAIN(A2, "2") LN_MAIN(A3, "3")
+                NEXT_LINE
+                /* multByConst: a * c / 10 ([REF] mnist/src/main.cpp:54) */
+                "H_MULC_P:\n" LOAD_AP "bra.uni H_MULC_A;\n"
+                "H_MULC_R:\n" LOAD_AR
+                "H_MULC_A:\n"
+                "add.u32 ra, zb, " CBASE ";\n ld.shared.f64 cst, [ra];\n"
+                "mul.rn.f64 " A0 ", " A0 ", cst;\n mul.rn.f64 " A1 ", " A1 ", cst;\n mul.rn.f64 " A2 ", " A2 ", cst;\n mul.rn.f64 " A3 ", " A3 ", cst;\n"
+                "setp.eq.u32 pall, 0, 0;\n"
+                DIV10_1(A0, "qr0") DIV10_1(A1, "qr1") DIV10_1(A2, "qr2") DIV10_1(A3, "qr3")
+                "vote.sync.all.pred p1, pall, 0xffffffff;\n"
+                "@!p1 bra.uni X_SLOW_MULC;\n"
+                "mov.f64 " A0 ", qr0;\n mov.f64 " A1 ", qr1;\n mov.f64 " A2 ", qr2;\n mov.f64 " A3 ", qr3;\n"
+                NEXT_LINE
+                "X_SLOW_DIV:\n mov.u32 " CODE ", 1000;\n bra.uni XEND;\n"
+                "X_SLOW_EXP:\n mov.u32 " CODE ", 1001;\n bra.uni XEND;\n"
+                "X_SLOW_LN:\n mov.u32 " CODE ", 1002;\n bra.uni XEND;\n"
+                "X_SLOW_MULC:\n mov.u32 " CODE ", 1003;\n bra.uni XEND;\n"
+                "H_NEXT:\n"
+                "H_END:\n"
+                "mov.u32 " CODE ", hx;\n"
+                "XEND:\n"
+                "}\n"
+                : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(b0), "+d"(b1), "+d"(b2), "+d"(b3), "+r"(lp), "=r"(xc)
+                : "r"(regs_lane), "r"(lane), "l"(gtile), "l"(sobel_tile), "l"(p.pixel_lut), "r"(code), "r"(tabs.exp_addr), "r"(tabs.log_addr)
+                : "memory");
+            if (xc == K2H_END) break;
+            if (xc == K2H_NEXT) { /* programs longer than one block: stage the next K1V2_CAP entries synchronously */
+                __syncwarp();
+                const int m = min(d0.y - staged, K1V2_CAP);
+                for (int i = lane; i < m; i += 32) {
+                    const uint4 q = __ldg(stream + d0.x + K1V2_CQ + staged + i);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(code + (K1V2_CQ + i) * 16), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+                }
+                __syncwarp();
+                staged += m;
+                lp = code + K1V2_CQ * 16;
+                continue;
+            }
+            /* rare operands of a heavy operation (a subnormal somewhere, the slivers next to exp's overflow / underflow
+               thresholds): the generic routines, sample by sample */
+            double a[4] = {a0, a1, a2, a3}, r[4];
+            if (xc == K2X_SLOW_DIV) {
+                const double b[4] = {b0, b1, b2, b3};
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv(a[k], b[k]);
+            } else if (xc == K2X_SLOW_EXP) {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) r[k] = tpgx_math::exp(a[k]);
+            } else if (xc == K2X_SLOW_LN) {
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) r[k] = tpgx_math::log(a[k]);
+            } else { /* K2X_SLOW_MULC: the products are in the accumulator */
+#pragma unroll 1
+                for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv10(a[k]);
+            }
+            a0 = r[0]; a1 = r[1]; a2 = r[2]; a3 = r[3];
+        }
+        /* the last effective line of a program writes register 0: the bid is the accumulator.
+           [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
+        double res[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
+        if (!TEAM) {
+            double* out = p.bid + (size_t)c.row * p.row_stride + (size_t)c.tile * K2_TS + lane * 4;
+            *reinterpret_cast<double2*>(out) = make_double2(res[0], res[1]);
+            *reinterpret_cast<double2*>(out + 2) = make_double2(res[2], res[3]);
+        } else {
+            /* [UP] evaluateTeam: the first edge is the initial best; a later edge replaces it if
+               bid >= best (last-max) / bid > best (first-max) */
+            const int dst = __ldg(p.row_dst + c.row);
+            const bool first = c.row == c.first;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool take = first | (p.tie_break == TPGX_TIE_LAST_MAX ? (res[k] >= best[k]) : (res[k] > best[k]));
+                best[k] = take ? res[k] : best[k];
+                best_dst[k] = take ? dst : best_dst[k];
+            }
+            if (c.row + 1 == c.row_end) {
+                int* out = p.decision + (size_t)c.unit * p.row_stride + (size_t)c.tile * K2_TS + lane * 4;
+                *reinterpret_cast<int4*>(out) = make_int4(best_dst[0], best_dst[1], best_dst[2], best_dst[3]);
+            }
+        }
+        c = nx; d0 = d1; cur ^= 1;
+    }
+    k2_cp_async_wait_all();
+}
+
+size_t tpgx_bid2_smem_bytes() {
+    return (size_t)K2_NW * K1V2_SLOTS * K2_TS * 8 + (size_t)K2_NW * 2 * K2_BUF * 16 + K2_TAB_BYTES;
+}
+
+cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team, int nb_ctas, cudaStream_t st) {
+    const size_t smem = tpgx_bid2_smem_bytes();
+    cudaError_t e = cudaMemsetAsync(p.work_counter, 0, 4, st);
+    if (e != cudaSuccess) return e;
+    if (team) {
+        e = cudaFuncSetAttribute(tpgx_bid2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tpgx_bid2_kernel<true><<<nb_ctas, K2_NW * 32, smem, st>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(tpgx_bid2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        tpgx_bid2_kernel<false><<<nb_ctas, K2_NW * 32, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+/* the stream of K1 v2, written on the device from the generic code: one thread per row */
+__global__ void tpgx_k1v2_encode_kernel(const uint32_t* __restrict__ code, const int32_t* __restrict__ prog_offset,
+                                        const double* __restrict__ constants, int nb_constants, const int32_t* __restrict__ active_prog,
+                                        const int2* __restrict__ desc, int nb_rows, int width, int hw, int nwin, uint4* __restrict__ stream,
+                                        int* __restrict__ flags) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nb_rows) return;
+    const int pidx = active_prog[row];
+    const int2 d = desc[row];
+    double* cq = reinterpret_cast<double*>(stream + d.x);
+    for (int k = 0; k < 2 * K1V2_CQ; k++) cq[k] = k < nb_constants ? constants[(size_t)pidx * nb_constants + k] : 0.0;
+    const tpgx_k1v2_info info = tpgx_k1v2_encode(code + prog_offset[pidx], prog_offset[pidx + 1] - prog_offset[pidx], K2_TS, (uint32_t)width,
+                                                 (uint32_t)hw, (uint32_t)nwin, reinterpret_cast<tpgx_k1_quad*>(stream + d.x + K1V2_CQ));
+    if (!info.ok || info.entries != d.y || info.slots > K1V2_SLOTS) atomicOr(flags, 4);
+}
+cudaError_t tpgx_launch_k1v2_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
+                                    const int32_t* active_prog, const int2* desc, int nb_rows, int width, int hw, int nwin, uint4* stream,
+                                    int* flags, cudaStream_t st) {
+    if (nb_rows <= 0) return cudaSuccess;
+    tpgx_k1v2_encode_kernel<<<(nb_rows + 127) / 128, 128, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, nb_rows, width, hw,
+                                                                  nwin, stream, flags);
+    return cudaGetLastError();
+}

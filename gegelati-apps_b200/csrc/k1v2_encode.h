@@ -1,0 +1,184 @@
+/*
+ * k1v2_encode.h — program encoder of the threaded bid interpreter (csrc/k1_bid2.cu).
+ *
+ * Input: the generic 32-bit line words of ONE program (tpgx_internal.h: introns removed, locations reduced,
+ * never-written registers marked).  Output: the program's entry stream for K1 v2, 16 bytes per entry
+ * {x = handler id, y = operand A, z = operand B, w = destination slot}, ready to be dispatched by ONE
+ * indirect branch per entry.  What the encoder decides, statically and per program:
+ *
+ *   accumulator forwarding  the result of a line stays in the interpreter's machine registers ("the
+ *       accumulator", kind A).  A later operand that names the PREVIOUS line's destination reads the
+ *       accumulator: no shared-memory load.  A result only the next line reads is never stored.
+ *   slot allocation         a result that a line after the next one still reads gets a slot of the warp's
+ *       shared-memory register file by live range (lowest free slot; freed at its last use), written by an
+ *       explicit ST entry.  [UP] ProgramExecutionEngine's 8 TPG registers thus become at most
+ *       `slots needed` <= 8 physical slots; programs that fit K1V2_SLOTS run on K1 v2, the others on K1 v1.
+ *   handler specialisation  one handler per (operation, kind of A, kind of B), kinds being accumulator /
+ *       slot / pixel; commutative operations are canonicalised (the accumulator or the slot first).
+ *   blocks                  K1 v2 stages K1V2_CAP entries at a time in shared memory; longer programs are
+ *       chained with NEXT entries, every program ends with END.
+ *
+ * The function compiles for the host (slot / entry counts during planning, unit tests) and for the device
+ * (the stream itself is written by tpgx_k1v2_encode_kernel from the generic code already in HBM).
+ */
+#ifndef TPGX_K1V2_ENCODE_H
+#define TPGX_K1V2_ENCODE_H
+
+#include "tpgx_internal.h"
+
+#define K1V2_SLOTS 5      /* shared-memory register slots per warp */
+#define K1V2_CQ 4         /* constant quads at the head of a program's stream (8 doubles) */
+#define K1V2_CAP 36       /* entries staged at a time */
+#define K1V2_MAX_LINES 256 /* longer programs run on K1 v1 */
+
+/* handler ids, in the order of the interpreter's branch-target table.  Binary operations: <op>_<A><B> with
+ * A = accumulator, R = slot, P = pixel; the operand that is not the accumulator travels in y (operand A) or z
+ * (operand B) as the byte offset of its slot, or as the index of lane 0's packed pixel word in the tile. */
+#define K1V2_HANDLERS(X)                                                                                   \
+    X(END) X(NEXT) X(ST)                                                                                   \
+    X(ADD_AA) X(ADD_AR) X(ADD_RR) X(ADD_AP) X(ADD_RP) X(ADD_PP)                                            \
+    X(MUL_AA) X(MUL_AR) X(MUL_RR) X(MUL_AP) X(MUL_RP) X(MUL_PP)                                            \
+    X(SUB_AA) X(SUB_AR) X(SUB_RR) X(SUB_PR) X(SUB_AP) X(SUB_RP) X(SUB_PP) X(SUB_RA) X(SUB_PA)              \
+    X(MAX_AA) X(MAX_AR) X(MAX_RR) X(MAX_PR) X(MAX_AP) X(MAX_RP) X(MAX_PP) X(MAX_RA) X(MAX_PA)              \
+    X(DIV_AA) X(DIV_AR) X(DIV_RR) X(DIV_PR) X(DIV_AP) X(DIV_RP) X(DIV_PP) X(DIV_RA) X(DIV_PA)              \
+    X(EXP_A) X(EXP_R) X(LN_A) X(LN_R) X(LUTE) X(LUTL)                                                      \
+    X(MULC_A) X(MULC_R) X(MULC_P)                                                                          \
+    X(SOBM) X(SOBD)
+enum {
+#define K1V2_ENUM(n) K2H_##n,
+    K1V2_HANDLERS(K1V2_ENUM)
+#undef K1V2_ENUM
+    K2H_COUNT
+};
+
+struct tpgx_k1v2_info {
+    int entries;  /* stream entries incl. ST, NEXT and END (the stream is K1V2_CQ + entries quads) */
+    int slots;    /* shared-memory slots the program needs */
+    int ok;       /* 0: not encodable for K1 v2 (instruction outside the MNIST set, too long) */
+};
+
+/* kinds of an operand after forwarding */
+#define K2K_A 0u
+#define K2K_R 1u
+#define K2K_P 2u
+
+/* handler of a binary operation given the operand kinds; *swap = 1 when y / z must be exchanged (commutative
+ * canonicalisation) */
+TPGX_HOSTDEV static inline int tpgx_k1v2_binary(int op, uint32_t ka, uint32_t kb, int* swap) {
+    *swap = 0;
+    if (op == TPGX_OP_ADD || op == TPGX_OP_MUL) {
+        const int base = op == TPGX_OP_ADD ? K2H_ADD_AA : K2H_MUL_AA;
+        /* order: A before R before P */
+        if (ka > kb) { const uint32_t t = ka; ka = kb; kb = t; *swap = 1; }
+        if (ka == K2K_A) return base + (kb == K2K_A ? 0 : kb == K2K_R ? 1 : 3);             /* AA AR AP */
+        if (ka == K2K_R) return base + (kb == K2K_R ? 2 : 4);                                  /* RR RP */
+        return base + 5;                                                                       /* PP */
+    }
+    const int base = op == TPGX_OP_SUB ? K2H_SUB_AA : op == TPGX_OP_MAX ? K2H_MAX_AA : K2H_DIV_AA;
+    /* AA AR RR PR AP RP PP RA PA */
+    if (kb == K2K_A) return base + (ka == K2K_A ? 0 : ka == K2K_R ? 7 : 8);
+    if (kb == K2K_R) return base + (ka == K2K_A ? 1 : ka == K2K_R ? 2 : 3);
+    return base + (ka == K2K_A ? 4 : ka == K2K_R ? 5 : 6);
+}
+
+/* Encodes one program.  words[n]: generic line words; ts: samples per tile (128); width, hw: row length and
+ * element count of the 2-D source; nwin: window positions per observation.  out == nullptr: count only. */
+TPGX_HOSTDEV static inline tpgx_k1v2_info tpgx_k1v2_encode(const uint32_t* words, int n, uint32_t ts, uint32_t width, uint32_t hw,
+                                                          uint32_t nwin, tpgx_k1_quad* out) {
+    tpgx_k1v2_info info = {0, 0, 1};
+    if (n > K1V2_MAX_LINES) { info.ok = 0; return info; }
+    int pos = 0; /* entry position within the staged block */
+    auto emit = [&](uint32_t h, uint32_t y, uint32_t z, uint32_t w) {
+        if (pos == K1V2_CAP - 1 && h != K2H_END) { /* the block's last entry chains to the next block */
+            if (out) { out[info.entries].x = K2H_NEXT; out[info.entries].y = out[info.entries].z = out[info.entries].w = 0; }
+            info.entries++;
+            pos = 0;
+        }
+        if (out) { out[info.entries].x = h; out[info.entries].y = y; out[info.entries].z = z; out[info.entries].w = w; }
+        info.entries++;
+        pos++;
+    };
+    int slot_of[TPGX_MAX_REGS];   /* slot holding the current value of each TPG register, -1: none */
+    int def_of[TPGX_MAX_REGS];    /* line that wrote it */
+    int last_use_of[TPGX_MAX_REGS]; /* last line reading the current value */
+    for (int r = 0; r < TPGX_MAX_REGS; r++) { slot_of[r] = -1; def_of[r] = -2; last_use_of[r] = -1; }
+    uint32_t free_mask = 0xffu;
+    const uint32_t zero_word = hw * (ts / 4u); /* index of lane 0's packed word of the all-zero pixel row */
+    if (n == 0) emit(K2H_ADD_PP, zero_word, zero_word, 0); /* [UP] executeProgram: register 0 is still 0.0 */
+    for (int i = 0; i < n; i++) {
+        const uint32_t word = words[i];
+        const int op = (int)(word & 31u);
+        const uint32_t dst = (word >> 5) & 7u;
+        const uint32_t f[2] = {(word >> 8) & 0xfffu, word >> 20};
+        const tpgx_op_info oi = tpgx_get_op_info(op);
+        /* operands after forwarding */
+        uint32_t kind[2] = {K2K_P, K2K_P}, val[2] = {zero_word, zero_word};
+        int reg[2] = {-1, -1};
+        for (int k = 0; k < 2; k++) {
+            if (k >= oi.nb_operands) continue;
+            const uint32_t kd = f[k] >> 10, loc = f[k] & 1023u;
+            if (oi.type[k] == TPGX_T_C) { val[k] = loc * 8u; continue; }
+            if (oi.type[k] == TPGX_T_W) { /* window: index of lane 0's 32-byte group in the tile's Sobel planes */
+                val[k] = ((loc / width) * (width - 2u) + loc % width) * (ts / 4u);
+                continue;
+            }
+            if (oi.type[k] != TPGX_T_D) { info.ok = 0; continue; }
+            if (kd == TPGX_KIND_REG && loc < TPGX_LOC_ZERO) {
+                reg[k] = (int)loc;
+                if (def_of[loc] == i - 1) kind[k] = K2K_A;
+                else { kind[k] = K2K_R; val[k] = (uint32_t)slot_of[loc] * ts * 8u; if (slot_of[loc] < 0) info.ok = 0; }
+            } else if (kd == TPGX_KIND_REG) { kind[k] = K2K_P; val[k] = zero_word; }
+            else if (kd == TPGX_KIND_SRC0) { kind[k] = K2K_P; val[k] = loc * (ts / 4u); }
+            else info.ok = 0;
+        }
+        /* slots whose value dies here are free for this line's own result */
+        for (int k = 0; k < 2; k++) {
+            const int r = reg[k];
+            if (r >= 0 && last_use_of[r] == i && slot_of[r] >= 0) { free_mask |= 1u << slot_of[r]; slot_of[r] = -1; }
+        }
+        switch (op) {
+        case TPGX_OP_ADD: case TPGX_OP_MUL: case TPGX_OP_SUB: case TPGX_OP_MAX: case TPGX_OP_DIV: {
+            int swap;
+            const int h = tpgx_k1v2_binary(op, kind[0], kind[1], &swap);
+            emit((uint32_t)h, swap ? val[1] : val[0], swap ? val[0] : val[1], 0);
+            break;
+        }
+        case TPGX_OP_EXP: case TPGX_OP_LOG:
+            if (kind[0] == K2K_P) emit(op == TPGX_OP_EXP ? K2H_LUTE : K2H_LUTL, val[0], 0, 0);
+            else emit((op == TPGX_OP_EXP ? K2H_EXP_A : K2H_LN_A) + (kind[0] == K2K_R ? 1 : 0), val[0], 0, 0);
+            break;
+        case TPGX_OP_MULC:
+            emit(K2H_MULC_A + kind[0], val[0], val[1], 0);
+            break;
+        case TPGX_OP_SOBEL_MAGN: emit(K2H_SOBM, val[0], 0, 0); break;
+        case TPGX_OP_SOBEL_DIR: emit(K2H_SOBD, val[0] + nwin * (ts / 4u), 0, 0); break;
+        default: info.ok = 0; break;
+        }
+        /* the new value of dst: who reads it, and until when */
+        int last = -1;
+        for (int j = i + 1; j < n; j++) {
+            const uint32_t wj = words[j];
+            const tpgx_op_info oj = tpgx_get_op_info((int)(wj & 31u));
+            const uint32_t fj[2] = {(wj >> 8) & 0xfffu, wj >> 20};
+            for (int k = 0; k < oj.nb_operands && k < 2; k++)
+                if (oj.type[k] == TPGX_T_D && (fj[k] >> 10) == TPGX_KIND_REG && (fj[k] & 1023u) == dst) last = j;
+            if (((wj >> 5) & 7u) == dst) break; /* overwritten */
+        }
+        if (slot_of[dst] >= 0) { free_mask |= 1u << slot_of[dst]; slot_of[dst] = -1; } /* stale value overwritten (cannot be live) */
+        def_of[dst] = i;
+        last_use_of[dst] = last;
+        if (last > i + 1) { /* read by a line after the next one: needs a slot */
+            int s = 0;
+            while (s < 8 && !((free_mask >> s) & 1u)) s++;
+            if (s >= 8) { info.ok = 0; s = 0; }
+            free_mask &= ~(1u << s);
+            slot_of[dst] = s;
+            if (s + 1 > info.slots) info.slots = s + 1;
+            emit(K2H_ST, 0, 0, (uint32_t)s * ts * 8u);
+        }
+    }
+    emit(K2H_END, 0, 0, 0);
+    return info;
+}
+
+#endif

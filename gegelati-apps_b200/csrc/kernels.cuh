@@ -30,6 +30,30 @@ struct tpgx_bid_params {
     int tie_break;
 };
 
+/* K1 v2 (k1_bid2.cu): threaded interpreter, persistent grid; stream / desc in the v2 encoding (k1v2_encode.h). */
+struct tpgx_bid2_params {
+    const uint8_t* tiles;        /* [tiles][hw + 1][128] pixel-major sample tiles (first tile of the pass) */
+    int hw;
+    const uint4* stream;         /* per row: K1V2_CQ constant quads, then its entries                     */
+    const int2* desc;            /* [rows] {first quad of the row in stream, number of entries}            */
+    const double* pixel_lut;
+    const double* sobel;
+    int nwin;
+    int nb_units, units_per_item, items_per_tile, nb_items;
+    unsigned int* work_counter;  /* next unclaimed item (zeroed by the launcher)                           */
+    double* bid;
+    long long row_stride;
+    const int2* team;
+    const int32_t* row_dst;
+    int32_t* decision;
+    int tie_break;
+};
+size_t tpgx_bid2_smem_bytes();
+cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team_mode, int nb_ctas, cudaStream_t st);
+cudaError_t tpgx_launch_k1v2_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
+                                    const int32_t* active_prog, const int2* desc, int nb_rows, int width, int hw, int nwin, uint4* stream,
+                                    int* flags, cudaStream_t st);
+
 /* K2: graph traversal per (root, sample) on the bid matrix. */
 struct tpgx_trav_params {
     const double* bid;

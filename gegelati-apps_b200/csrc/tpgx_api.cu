@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "episodes.cuh"
+#include "k1v2_encode.h"
 #include "kernels.cuh"
 #include "tpgx_internal.h"
 
@@ -53,6 +54,7 @@ struct ShardPlan { /* programs reachable from a root range, cached between evalu
     bool k1_ext = false;  /* the shard uses instructions outside the MNIST set */
     bool team_mode = false; /* [UP] evaluateTeam fused into K1 (acyclic shard, no bid output, little program sharing) */
     bool want_bid = false;
+    bool k1_v2 = false;   /* the threaded interpreter (k1_bid2.cu) runs this shard */
     int nb_units = 0;     /* teams in team mode, programs otherwise */
     int64_t active_lines = 0, active_flops = 0;
 };
@@ -70,12 +72,15 @@ struct tpgx_ctx {
     cudaStream_t stream = nullptr;
     std::vector<cudaEvent_t> events;
     int variant = 0;
+    int sm_count = 148;
     size_t bid_budget = (size_t)16 << 30;
+    std::vector<int32_t> v2_entries;  /* per program: entries of its K1 v2 stream, -1 = not encodable for v2 */
+    std::vector<uint8_t> v2_slots;    /* per program: shared-memory slots it needs there */
 
     DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
-    DevBuf d_scratch[16];
+    DevBuf d_scratch[16], d_work;
     /* tpgx_set_observations_pinned enqueues its copy / re-tiling / Sobel-plane work on a stream of its own, so that
        the graph uploads that follow on the main stream are not queued behind 47 MB of observations; consumers of the
        tiles wait for obs_ready */
@@ -213,27 +218,45 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
     if ((st = upload(ctx, ctx->d_edge_row, ctx->h_edge_row.data(), ctx->h_edge_row.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_roots, f.root_team.data() + rb, (size_t)(re - rb) * 4)) != TPGX_OK) return st;
     tr.lap("reachability + uploads");
-    /* K1 stream: per row its constants (TPGX_K1_CQ quads) followed by its pre-decoded wide lines.  The host
-       ships only the row descriptors; the quads are expanded on the device from the generic code. */
+    /* K1 stream: per row its constants followed by its pre-decoded lines.  The host ships only the row
+       descriptors; the quads are expanded on the device from the generic code.  K1 v2 (threaded interpreter,
+       k1_bid2.cu) takes the shard when every program of it is in the MNIST instruction set and fits its slots;
+       otherwise K1 v1 (k1_bid.cu). */
     {
         const int nrows = (int)ctx->h_active.size();
+        const char* v2env = getenv("TPGX_K1_V2");
+        bool v2 = !(v2env && v2env[0] == '0') && !ctx->uses_ext && !ctx->uses_int && ts == 128 && ctx->variant == 0 &&
+                  ctx->v2_entries.size() == (size_t)f.nb_programs;
+        for (int row = 0; v2 && row < nrows; row++) {
+            const int p = ctx->h_active[row];
+            if (ctx->v2_entries[p] < 0 || ctx->v2_slots[p] > K1V2_SLOTS) v2 = false;
+        }
+        pl.k1_v2 = v2;
         std::vector<int32_t> desc(2 * (size_t)nrows);
         int64_t nq = 0;
         for (int row = 0; row < nrows; row++) {
             const int p = ctx->h_active[row];
             desc[2 * row] = (int32_t)nq;
-            desc[2 * row + 1] = f.prog_offset[p + 1] - f.prog_offset[p];
-            nq += TPGX_K1_CQ + desc[2 * row + 1];
+            desc[2 * row + 1] = v2 ? ctx->v2_entries[p] : f.prog_offset[p + 1] - f.prog_offset[p];
+            nq += (v2 ? K1V2_CQ : TPGX_K1_CQ) + desc[2 * row + 1];
         }
         if ((st = upload(ctx, ctx->d_k1_desc, desc.data(), desc.size() * 4)) != TPGX_OK) return st;
         CU(ctx->d_k1_stream.ensure(((size_t)nq + 64) * sizeof(tpgx_k1_quad))); /* slack: a lane may address up to 32 quads past a row's start */
         CU(ctx->d_status.ensure(16));
         int* d_flags = ctx->d_status.as<int>() + 2;
         CU(cudaMemsetAsync(d_flags, 0, 4, ctx->stream));
-        CU(tpgx_launch_k1_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
-                                 ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->obs_hw, ctx->d_k1_stream.as<uint4>(),
-                                 d_flags, ctx->stream));
+        if (v2)
+            CU(tpgx_launch_k1v2_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
+                                       ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ctx->obs_width, ctx->obs_hw,
+                                       std::max(0, (ctx->src[0].height - 2) * (ctx->src[0].width - 2)), ctx->d_k1_stream.as<uint4>(), d_flags, ctx->stream));
+        else
+            CU(tpgx_launch_k1_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
+                                     ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->obs_hw, ctx->d_k1_stream.as<uint4>(),
+                                     d_flags, ctx->stream));
+        int flags = 0;
+        CU(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream)); /* desc is a local */
+        if (flags & 4) return fail(ctx, TPGX_ERR_CUDA, "K1 v2 encoder: device stream disagrees with the host's entry / slot counts");
         /* which build of K1 (MNIST set only / extended) is known on the host from the opcode table */
         if (ctx->uses_int) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
         pl.k1_ext = ctx->uses_ext;
@@ -332,7 +355,37 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
         const int64_t s0 = t0 * ts;
         const int ns = (int)std::min<int64_t>((int64_t)nt * ts, nS - s0);
         if (timing) CU(cudaEventRecord(ctx->event(ev++), ctx->stream));
-        if (nA > 0) {
+        if (nA > 0 && ctx->plan.k1_v2) {
+            tpgx_bid2_params bp{};
+            bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * (hw + 1) * ts;
+            bp.hw = hw;
+            bp.stream = ctx->d_k1_stream.as<uint4>();
+            bp.desc = ctx->d_k1_desc.as<int2>();
+            bp.pixel_lut = ctx->d_pixel_lut.as<double>();
+            bp.sobel = ctx->nwin ? ctx->d_sobel.as<double>() + (size_t)t0 * 2 * ctx->nwin * ts : nullptr;
+            bp.nwin = ctx->nwin;
+            bp.nb_units = nU;
+            /* work items = (tile, group of units), claimed warp by warp: ~20 items per resident warp when there is that
+               much work (dynamic balance to the last item), at most 8 teams / 32 programs per item */
+            const int64_t warps = (int64_t)ctx->sm_count * 32;
+            int g = (int)std::min<int64_t>(team_mode ? 8 : 32, std::max<int64_t>(1, (int64_t)nt * nU / (20 * warps)));
+            if (const char* v = getenv("TPGX_K1_GROUP")) g = std::max(1, atoi(v)); /* experiments */
+            bp.units_per_item = g;
+            bp.items_per_tile = (nU + g - 1) / g;
+            bp.nb_items = bp.items_per_tile * nt;
+            CU(ctx->d_work.ensure(16));
+            bp.work_counter = ctx->d_work.as<unsigned int>();
+            bp.bid = ctx->d_bid.as<double>();
+            bp.row_stride = (long long)nt * ts;
+            bp.team = ctx->d_tm_team.as<int2>();
+            bp.row_dst = ctx->d_tm_dst.as<int32_t>();
+            bp.decision = ctx->d_decision.as<int32_t>();
+            bp.tie_break = ctx->cfg.tie_break;
+            int ctas = (int)std::min<int64_t>(ctx->sm_count, ((int64_t)bp.nb_items + 31) / 32);
+            if (const char* v = getenv("TPGX_K1_CTAS")) ctas = std::max(1, atoi(v));
+            CU(tpgx_launch_bid2(bp, team_mode, ctas, ctx->stream));
+            etr.lap(team_mode ? "K1 v2 launch (team mode)" : "K1 v2 launch (bid mode)");
+        } else if (nA > 0) {
             tpgx_bid_params bp{};
             bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * (hw + 1) * ts;
             bp.hw = hw; bp.width = ctx->obs_width;
@@ -452,6 +505,7 @@ tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out) {
     if (prop.major < 10) return fail(nullptr, TPGX_ERR_UNSUPPORTED, "libtpgx is built for sm_100a (Blackwell) only");
     ctx = new tpgx_ctx();
     ctx->cfg = *cfg;
+    ctx->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->obs_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->obs_ready, cudaEventDisableTiming);
@@ -476,7 +530,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_tm_team, &ctx->d_tm_dst, &ctx->d_tm_stat, &ctx->d_tm_roots, &ctx->d_decision, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
-                     &ctx->d_counters, &ctx->d_status};
+                     &ctx->d_counters, &ctx->d_status, &ctx->d_work};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : ctx->d_scratch) b.release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
@@ -535,6 +589,17 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
         ctx->uses_int = present[TPGX_OP_SUB_II] || present[TPGX_OP_CAST_I];
         ctx->uses_ext = ctx->uses_trig || present[TPGX_OP_FMODG] || present[TPGX_OP_COND] || present[TPGX_OP_EQ0] || present[TPGX_OP_EQM1] ||
                         present[TPGX_OP_EQ1] || present[TPGX_OP_GE15] || present[TPGX_OP_PI];
+    }
+    { /* K1 v2: entries and shared-memory slots of every program (count pass of the encoder; the stream itself is written on the device) */
+        ctx->v2_entries.assign((size_t)F.nb_programs, -1);
+        ctx->v2_slots.assign((size_t)F.nb_programs, 0);
+        if (!ctx->uses_ext && !ctx->uses_int)
+            tpgx_parallel_blocks(F.nb_programs, 256, [&](int b, int e, int) {
+                for (int p = b; p < e; p++) {
+                    const tpgx_k1v2_info info = tpgx_k1v2_encode(F.code.data() + F.prog_offset[p], F.prog_offset[p + 1] - F.prog_offset[p], 128u, 28u, 784u, 676u, nullptr);
+                    if (info.ok) { ctx->v2_entries[p] = info.entries; ctx->v2_slots[p] = (uint8_t)info.slots; }
+                }
+            });
     }
     std::vector<int32_t> edge_lines(F.nb_edges);
     for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }

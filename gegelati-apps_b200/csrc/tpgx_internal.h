@@ -135,7 +135,7 @@ struct tpgx_op_info {
 };
 
 /* Operand signature per device opcode (= LambdaInstruction<...> template arguments of the apps). */
-static inline tpgx_op_info tpgx_get_op_info(int op) {
+TPGX_HOSTDEV static inline tpgx_op_info tpgx_get_op_info(int op) {
     switch (op) {
     case TPGX_OP_SUB: case TPGX_OP_ADD: case TPGX_OP_MUL: case TPGX_OP_DIV: case TPGX_OP_MAX:
         return {2, {TPGX_T_D, TPGX_T_D}, 1};

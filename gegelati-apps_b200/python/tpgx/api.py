@@ -12,7 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..", "..", "lib", "libtpgx.so"))
 
 EXPORTS = [
-    "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table",
+    "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table", "tpgx_k1v2_encode_program", "tpgx_k1v2_handler_name",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
@@ -83,6 +83,39 @@ def flatten_programs(opcodes, sources, graph, nb_registers=8, nb_constants=0):
     if st != A.OK:
         raise TpgxError(st, err.value.decode())
     return dict(intron=intron, effective_lines=eff, code=code[:n.value])
+
+
+def k1v2_handler_names():
+    """Handler names of the K1 v2 interpreter, indexed by handler id."""
+    lib = load_library()
+    lib.tpgx_k1v2_handler_name.restype = C.c_char_p
+    lib.tpgx_k1v2_handler_name.argtypes = [C.c_int32]
+    names = []
+    while True:
+        n = lib.tpgx_k1v2_handler_name(len(names))
+        if n is None:
+            return names
+        names.append(n.decode())
+
+
+def k1v2_encode_program(words, width=28, hw=784, nwin=676):
+    """K1 v2 entry stream of one program (host only): dict(quads uint32[entries][4], slots) or None when the program is
+    not encodable for K1 v2."""
+    lib = load_library()
+    lib.tpgx_k1v2_encode_program.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    w = np.ascontiguousarray(words, dtype=np.uint32)
+    ne, ns = C.c_int32(0), C.c_int32(0)
+    st = lib.tpgx_k1v2_encode_program(w.ctypes.data, len(w), width, hw, nwin, None, 0, C.byref(ne), C.byref(ns))
+    if st == A.ERR_UNSUPPORTED:
+        return None
+    if st != A.OK:
+        raise TpgxError(st, "tpgx_k1v2_encode_program")
+    q = np.zeros((ne.value, 4), dtype=np.uint32)
+    st = lib.tpgx_k1v2_encode_program(w.ctypes.data, len(w), width, hw, nwin, q.ctypes.data, len(q), C.byref(ne), C.byref(ns))
+    if st != A.OK:
+        raise TpgxError(st, "tpgx_k1v2_encode_program")
+    return dict(quads=q, slots=ns.value)
 
 
 def mnist_episode_indices(seed, mode, dataset_size, nb_actions):

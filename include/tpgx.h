@@ -398,6 +398,17 @@ tpgx_status tpgx_flatten_programs(const tpgx_config* cfg, int32_t nb_instruction
                                   const tpgx_source_desc* sources, const tpgx_graph* g, uint8_t* intron, int32_t* effective_lines,
                                   uint32_t* code, int64_t code_capacity, int64_t* nb_code_words, char* err, size_t err_len);
 
+/* K1 v2 stream encoder on its own (host only; csrc/k1v2_encode.h — the device runs the same function when a graph is
+ * planned): the entry stream of ONE program given its packed generic words (tpgx_flatten_programs' `code`), for a
+ * 2-D uint8 source of `hw` elements in rows of `width` with `nwin` 3x3 window positions, 128 samples per tile.
+ * quads: optional [quad_capacity][4] uint32 {handler, operand A, operand B, destination slot}; *nb_entries and
+ * *nb_slots receive the entry count (incl. ST / NEXT / END entries) and the shared-memory slots the program needs.
+ * TPGX_ERR_UNSUPPORTED: instruction outside the MNIST set or program too long for K1 v2 (K1 v1 runs it).
+ * tpgx_k1v2_handler_name: name of handler id h ("ADD_AR", ...), NULL past the table.                         */
+tpgx_status tpgx_k1v2_encode_program(const uint32_t* words, int32_t nb_words, int32_t width, int32_t hw, int32_t nwin,
+                                     uint32_t* quads, int32_t quad_capacity, int32_t* nb_entries, int32_t* nb_slots);
+const char* tpgx_k1v2_handler_name(int32_t h);
+
 /* The image indices one MNIST evaluation classifies, restating [REF] mnist/src/mnist.cpp:58-69 (reset:
  * rng.setSeed(seed) with the RAW seed, currentIndex = -1, changeCurrentImage) and :8-34 / :50-56 (every
  * doAction classifies the current image, then draws the next): in TRAINING (0) and VALIDATION (1) mode
