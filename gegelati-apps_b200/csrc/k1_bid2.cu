@@ -72,6 +72,7 @@ struct k2_tab_shared {
 #define CBASE "%15"
 #define EXPT "%16"
 #define LOGT "%17"
+#define NEVER "%18"
 
 
 /* IEEE-754 double constants of tpgx_math.h, as PTX literals */
@@ -109,25 +110,28 @@ struct k2_tab_shared {
 #define K2X_SLOW_LN 1002
 #define K2X_SLOW_MULC 1003
 
-/* tpgx_math::xdiv_k, one sample: quotient of a / b into q; pall &= (special | fast path accepted) */
-#define DIV1(a, b, q)                                                                            \
-    "rcp.approx.ftz.f64 sd, " b ";\n"                                                            \
+/* tpgx_math::xdiv_k, one sample k.  DIV_CLASS: reciprocal seed sd<k>, special-operand predicate psp<k>, pany |= !special.
+   DIV_SEQ: quotient of a / b into qr<k> (a * seed when special); pall &= (special | fast path accepted). */
+#define DIV_CLASS(a, b, k)                                                                       \
+    "rcp.approx.ftz.f64 sd" k ", " b ";\n"                                                       \
     "mov.b64 {alo, ahi}, " a ";\n mov.b64 {blo, bhi}, " b ";\n"                                  \
     "and.b32 ha, ahi, 0x7fffffff;\n and.b32 hb, bhi, 0x7fffffff;\n"                              \
     "or.b32 t0, ha, alo;\n setp.eq.u32 p1, t0, 0;\n setp.ge.u32 p2, ha, 0x7ff00000;\n or.pred pas, p1, p2;\n" \
     "or.b32 t0, hb, blo;\n setp.eq.u32 p1, t0, 0;\n setp.ge.u32 p2, hb, 0x7ff00000;\n or.pred pbs, p1, p2;\n" \
-    "sub.u32 t0, hb, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fb00000;\n and.pred pas, pas, p1;\n or.pred psp, pbs, pas;\n" \
-    "mov.b64 {slo, shi}, sd;\n mov.b32 slo, 1;\n mov.b64 rr, {slo, shi};\n"                      \
+    "sub.u32 t0, hb, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fb00000;\n and.pred pas, pas, p1;\n or.pred psp" k ", pbs, pas;\n" \
+    "not.pred p1, psp" k ";\n or.pred pany, pany, p1;\n"
+#define DIV_SEQ(a, b, k)                                                                         \
+    "mov.b64 {slo, shi}, sd" k ";\n mov.b32 slo, 1;\n mov.b64 rr, {slo, shi};\n"                 \
     "neg.f64 nb, " b ";\n"                                                                       \
     "fma.rn.f64 t1, nb, rr, " KD_ONE ";\n fma.rn.f64 t1, t1, t1, t1;\n fma.rn.f64 r1, rr, t1, rr;\n" \
     "fma.rn.f64 t2, nb, r1, " KD_ONE ";\n fma.rn.f64 r2, r1, t2, r1;\n"                           \
-    "mul.rn.f64 q0, " a ", r2;\n fma.rn.f64 rem, nb, q0, " a ";\n fma.rn.f64 " q ", r2, rem, q0;\n" \
-    "mov.b64 {qlo, qhi}, " q ";\n"                                                               \
+    "mul.rn.f64 q0, " a ", r2;\n fma.rn.f64 rem, nb, q0, " a ";\n fma.rn.f64 qr" k ", r2, rem, q0;\n" \
+    "mov.b64 {qlo, qhi}, qr" k ";\n mov.b64 {alo, ahi}, " a ";\n mov.b64 {blo, bhi}, " b ";\n"   \
     "mov.b32 fq, qhi;\n mov.b32 fb, bhi;\n mov.b32 fa, ahi;\n"                                   \
     "fma.rn.f32 ft, 0f00000000, fb, fq;\n abs.f32 ft, ft;\n setp.gt.f32 p1, ft, 0f00100000;\n"   \
     "abs.f32 fa, fa;\n setp.ge.f32 p2, fa, 0f03600000;\n and.pred p1, p1, p2;\n"                 \
-    "or.pred p1, p1, psp;\n and.pred pall, pall, p1;\n"                                          \
-    "mul.rn.f64 sp, " a ", sd;\n selp.f64 " q ", sp, " q ", psp;\n"
+    "or.pred p1, p1, psp" k ";\n and.pred pall, pall, p1;\n"                                     \
+    "mul.rn.f64 sp, " a ", sd" k ";\n selp.f64 qr" k ", sp, qr" k ", psp" k ";\n"
 
 /* tpgx_math::exp_k, one sample (x in place).  EXP_RARE accumulates the sliver test, EXP_MAIN computes. */
 #define EXP_RARE(x, k)                                                                            \
@@ -146,10 +150,16 @@ struct k2_tab_shared {
     "mov.b64 {ylo, yhi}, y;\n shl.b32 ee, ee, 20;\n add.u32 yhi, yhi, ee;\n mov.b64 y, {ylo, yhi};\n" \
     "add.rn.f64 ev, " x ", " KD_INF ";\n selp.f64 ev, " KD_ZERO ", ev, pt" k ";\n selp.f64 " x ", y, ev, pm" k ";\n"
 
-/* tpgx_math::log_k, one sample (x in place) */
+/* tpgx_math::log_k, one sample k (x in place).  LN_RARE: zero predicate pz<k>, main-range predicate pm<k> (positive, normal,
+   finite), prare |= positive subnormal, pany |= main.  LN_MAIN: the table-driven path + edge selects.  LN_EDGE: the edge
+   answers alone (no sample of the warp is in the main range). */
 #define LN_RARE(x, k)                                                                             \
     "mov.b64 {xlo, xhi}, " x ";\n setp.eq.f64 pz" k ", " x ", " KD_ZERO ";\n setp.lt.u32 p1, xhi, 0x00100000;\n" \
-    "not.pred p2, pz" k ";\n and.pred p1, p1, p2;\n or.pred prare, prare, p1;\n"
+    "not.pred p2, pz" k ";\n and.pred p1, p1, p2;\n or.pred prare, prare, p1;\n"                    \
+    "sub.u32 t0, xhi, 0x00100000;\n setp.lt.u32 pm" k ", t0, 0x7fe00000;\n or.pred pany, pany, pm" k ";\n"
+#define LN_EDGE(x, k)                                                                             \
+    "add.rn.f64 ev, " x ", " x ";\n setp.lt.f64 p2, " x ", " KD_ZERO ";\n selp.f64 ev, " KD_NAN ", ev, p2;\n" \
+    "selp.f64 " x ", " KD_NINF ", ev, pz" k ";\n"
 #define LN_MAIN(x, k)                                                                             \
     "mov.b64 {xlo, xhi}, " x ";\n"                                                               \
     "sub.u32 t0, xhi, 0x3FE6B000;\n shr.u32 ii, t0, 13;\n and.b32 ii, ii, 127;\n shr.s32 kk, t0, 20;\n" \
@@ -160,9 +170,8 @@ struct k2_tab_shared {
     "mul.rn.f64 r2, r, r;\n fma.rn.f64 pa, r, " KD_C1_7 ", " KD_CM1_6 ";\n fma.rn.f64 pa, r, pa, " KD_C0_2 ";\n" \
     "fma.rn.f64 pa, r, pa, " KD_CM0_25 ";\n fma.rn.f64 pa, r, pa, " KD_C1_3 ";\n fma.rn.f64 pa, r, pa, " KD_CM0_5 ";\n" \
     "fma.rn.f64 tmp, r2, pa, lo;\n add.rn.f64 y, hi, tmp;\n"                                     \
-    "sub.u32 t0, xhi, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fe00000;\n"                           \
     "add.rn.f64 ev, " x ", " x ";\n setp.lt.f64 p2, " x ", " KD_ZERO ";\n selp.f64 ev, " KD_NAN ", ev, p2;\n" \
-    "selp.f64 ev, " KD_NINF ", ev, pz" k ";\n selp.f64 " x ", y, ev, p1;\n"
+    "selp.f64 ev, " KD_NINF ", ev, pz" k ";\n selp.f64 " x ", y, ev, pm" k ";\n"
 
 /* tpgx_math::xdiv10_k, one sample: x / 10 into q; pall &= accepted */
 #define DIV10_1(x, q)                                                                             \
@@ -174,15 +183,38 @@ struct k2_tab_shared {
     "and.pred p1, p1, p2;\n or.pred p1, p1, psp;\n and.pred pall, pall, p1;\n"                   \
     "selp.f64 " q ", q0, " q ", psp;\n"
 
-/* 4 doubles of the lane from a shared-memory slot (byte offset in `f`) */
-#define LOAD_R(d0, d1, d2, d3, f)                          \
-    "add.u32 ra, " f ", " REGS ";\n"                       \
+/* Dispatch.  Default (K2_PIPELINED 0): one fetch + indirect branch, every handler ends with a branch back to it.
+ * K2_PIPELINED 1 / 2 are the measured alternatives (profiles/r2_k1v2_experiments.md): every handler fetches the NEXT entry
+ * into the same registers once its own operand fields are addresses (PF) and ends with its own indirect branch (GO) —
+ * 4 % fewer instructions but 21 % SLOWER on C2: ptxas sinks the fetch back next to the branch, and 28 BRX sites plus
+ * 3.5 KB more code drop the instruction-cache hit rate from 99.3 % to 93 % (no_instruction stalls x4, short scoreboard x3). */
+#ifndef K2_PIPELINED
+#define K2_PIPELINED 0
+#endif
+#if K2_PIPELINED == 2
+/* the fetch is fenced by a never-taken branch so that ptxas cannot sink the LDS below the handler's body */
+#define PF "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n add.u32 " LP ", " LP ", 16;\n @pnever bra.uni XEND;\n"
+#define GO "brx.idx.uni hx, tlist;\n"
+#define UNFETCH "sub.u32 " LP ", " LP ", 16;\n"
+#elif K2_PIPELINED
+#define PF "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n add.u32 " LP ", " LP ", 16;\n"
+#define GO "brx.idx.uni hx, tlist;\n"
+#define UNFETCH "sub.u32 " LP ", " LP ", 16;\n" /* a handler that leaves the block after PF hands the next entry back */
+#else
+#define PF ""
+#define GO "bra.uni FETCH;\n"
+#define UNFETCH ""
+#endif
+
+/* address of a shared-memory slot operand (byte offset in field f) / of the lane's packed pixel word (word index in f) */
+#define ADDR_R(f) "add.u32 ra, " f ", " REGS ";\n"
+#define ADDR_P(f) "add.u32 pw, " f ", " LANE ";\n mad.wide.u32 ga, pw, 4, " GTILE ";\n"
+/* 4 doubles of the lane from the slot at ra */
+#define LD_R(d0, d1, d2, d3)                               \
     "ld.shared.v2.f64 {" d0 ", " d1 "}, [ra];\n"           \
     "ld.shared.v2.f64 {" d2 ", " d3 "}, [ra+512];\n"
-/* 4 pixels of the lane (word index of lane 0 in `f`), uint8 -> double (exact) */
-#define LOAD_P(d0, d1, d2, d3, f)                          \
-    "add.u32 pw, " f ", " LANE ";\n"                       \
-    "mad.wide.u32 ga, pw, 4, " GTILE ";\n"                 \
+/* 4 pixels of the lane from ga, uint8 -> double (exact) */
+#define LD_P(d0, d1, d2, d3)                               \
     "ld.global.nc.u32 pw, [ga];\n"                         \
     "cvt.rn.f64.u8 " d0 ", pw;\n"                          \
     "shr.u32 t0, pw, 8;\n"                                 \
@@ -191,12 +223,15 @@ struct k2_tab_shared {
     "cvt.rn.f64.u8 " d2 ", t0;\n"                          \
     "shr.u32 t0, pw, 24;\n"                                \
     "cvt.rn.f64.u8 " d3 ", t0;\n"
-#define LOAD_AR LOAD_R(A0, A1, A2, A3, "ya")
-#define LOAD_AP LOAD_P(A0, A1, A2, A3, "ya")
-#define LOAD_BR(f) LOAD_R(B0, B1, B2, B3, f)
-#define LOAD_BP(f) LOAD_P(B0, B1, B2, B3, f)
+/* operand A of the entry into the accumulator (not the last use of the entry's fields: no PF) */
+#define LOAD_AR ADDR_R("ya") LD_R(A0, A1, A2, A3)
+#define LOAD_AP ADDR_P("ya") LD_P(A0, A1, A2, A3)
+/* last operand of the entry into b: address, then the next entry's fetch, then the load */
+#define LAST_BR(f) ADDR_R(f) PF LD_R(B0, B1, B2, B3)
+#define LAST_BP(f) ADDR_P(f) PF LD_P(B0, B1, B2, B3)
+#define LAST_AR ADDR_R("ya") PF LD_R(A0, A1, A2, A3)
+#define LAST_AP ADDR_P("ya") PF LD_P(A0, A1, A2, A3)
 #define MOV_B_A "mov.f64 " B0 ", " A0 ";\n mov.f64 " B1 ", " A1 ";\n mov.f64 " B2 ", " A2 ";\n mov.f64 " B3 ", " A3 ";\n"
-#define NEXT_LINE "bra.uni FETCH;\n"
 /* acc = acc op b / acc = b op acc / acc = acc op acc */
 #define OP_AB(op) op " " A0 ", " A0 ", " B0 ";\n" op " " A1 ", " A1 ", " B1 ";\n" op " " A2 ", " A2 ", " B2 ";\n" op " " A3 ", " A3 ", " B3 ";\n"
 #define OP_BA(op) op " " A0 ", " B0 ", " A0 ";\n" op " " A1 ", " B1 ", " A1 ";\n" op " " A2 ", " B2 ", " A2 ";\n" op " " A3 ", " B3 ", " A3 ";\n"
@@ -211,21 +246,21 @@ struct k2_tab_shared {
 #define BIN_COMM(N, op)                                                   \
     "H_" N "_PP:\n" LOAD_AP "bra.uni H_" N "_AP;\n"                       \
     "H_" N "_RP:\n" LOAD_AR                                               \
-    "H_" N "_AP:\n" LOAD_BP("zb") OP_AB(op) NEXT_LINE                     \
+    "H_" N "_AP:\n" LAST_BP("zb") OP_AB(op) GO                            \
     "H_" N "_RR:\n" LOAD_AR                                               \
-    "H_" N "_AR:\n" LOAD_BR("zb") OP_AB(op) NEXT_LINE                     \
-    "H_" N "_AA:\n" OP_AA(op) NEXT_LINE
+    "H_" N "_AR:\n" LAST_BR("zb") OP_AB(op) GO                            \
+    "H_" N "_AA:\n" PF OP_AA(op) GO
 /* ordered binary operation: AA AR RR PR AP RP PP RA PA, with the given bodies */
 #define BIN_ORD(N, body_ab, body_ba, body_aa)                             \
     "H_" N "_PP:\n" LOAD_AP "bra.uni H_" N "_AP;\n"                       \
     "H_" N "_RP:\n" LOAD_AR                                               \
-    "H_" N "_AP:\n" LOAD_BP("zb") body_ab NEXT_LINE                       \
+    "H_" N "_AP:\n" LAST_BP("zb") body_ab GO                              \
     "H_" N "_PR:\n" LOAD_AP "bra.uni H_" N "_AR;\n"                       \
     "H_" N "_RR:\n" LOAD_AR                                               \
-    "H_" N "_AR:\n" LOAD_BR("zb") body_ab NEXT_LINE                       \
-    "H_" N "_RA:\n" LOAD_BR("ya") body_ba NEXT_LINE                       \
-    "H_" N "_PA:\n" LOAD_BP("ya") body_ba NEXT_LINE                       \
-    "H_" N "_AA:\n" body_aa NEXT_LINE
+    "H_" N "_AR:\n" LAST_BR("zb") body_ab GO                              \
+    "H_" N "_RA:\n" LAST_BR("ya") body_ba GO                              \
+    "H_" N "_PA:\n" LAST_BP("ya") body_ba GO                              \
+    "H_" N "_AA:\n" PF body_aa GO
 
 #define K2_TARGET(n) "H_" #n ", "
 
@@ -246,85 +281,88 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
     const uint4* __restrict__ stream = p.stream;
     const int tile_bytes = (p.hw + 1) * K2_TS;
     const long long plane_stride = (long long)p.nwin * K2_TS; /* doubles per plane of a tile */
+    const uint32_t never = p.nb_items < 0 ? 1u : 0u; /* always 0; only the compiler does not know */
 
-    /* cursor over the rows (programs) this warp runs: item = (tile, group of units); unit = team or program */
-    struct Cur { int tile, unit, unit_end, row, row_end, first; };
+    /* cursor over the rows (programs) this warp runs.  item = (tile, group of consecutive units); the rows of consecutive
+       units are consecutive in the stream, and every row's header quad names the edge's destination, the entry count of
+       the row after it and whether it opens / closes its unit — so a warp reads global metadata once per ITEM
+       (unit_first) and nothing per row. */
+    struct Cur { int tile, unit, unit_end, q, n; }; /* q: first quad of the row in the stream, n: its entries */
     auto claim = [&]() {
         unsigned int i = 0;
         if (lane == 0) i = atomicAdd(p.work_counter, 1u);
         return (int)__shfl_sync(0xffffffffu, i, 0);
     };
-    auto open_unit = [&](Cur& c) {
-        const int2 t = TEAM ? __ldg(p.team + c.unit) : make_int2(c.unit, 1);
-        c.row = t.x; c.row_end = t.x + t.y; c.first = t.x;
-    };
     auto open_item = [&](Cur& c) {
         const int item = claim();
-        if (item >= p.nb_items) { c.tile = -1; return; }
+        if (item >= p.nb_items) { c.tile = -1; c.q = 0; c.n = 0; return; }
         c.tile = item / p.items_per_tile;
         const int g = item - c.tile * p.items_per_tile;
         c.unit = g * p.units_per_item;
         c.unit_end = min(c.unit + p.units_per_item, p.nb_units);
-        open_unit(c);
+        const int2 f = __ldg(p.unit_first + c.unit);
+        c.q = f.x; c.n = f.y;
     };
-    auto advance = [&](Cur& c) {
-        if (++c.row < c.row_end) return;
-        if (++c.unit < c.unit_end) { open_unit(c); return; }
-        open_item(c);
-    };
-    auto load_desc = [&](const Cur& c) { return c.tile >= 0 ? __ldg(p.desc + c.row) : make_int2(0, 0); };
-    /* asynchronous copy of a program's constants + first block of entries into a code buffer */
-    auto stage = [&](uint32_t buf, const int2 d) {
-        const int nq = K1V2_CQ + min(d.y, K1V2_CAP);
-        for (int i = lane; i < nq; i += 32) k2_cp_async16(buf + i * 16, stream + d.x + i);
+    /* asynchronous copy of a row's head (constants + header) and first block of entries into a code buffer */
+    auto stage = [&](uint32_t buf, const Cur& c) {
+        const int nq = c.tile >= 0 ? K1V2_CQ + min(c.n, K1V2_CAP) : 0;
+        for (int i = lane; i < nq; i += 32) k2_cp_async16(buf + i * 16, stream + c.q + i);
         k2_cp_async_commit();
     };
 
     Cur c;
     open_item(c);
-    int2 d0 = load_desc(c);
     int cur = 0;
-    stage(mycode, d0);
+    stage(mycode, c);
     double best[4];
     int best_dst[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { best[k] = 0.0; best_dst[k] = 0; }
 
     while (c.tile >= 0) {
-        Cur nx = c;
-        advance(nx);
-        const int2 d1 = load_desc(nx);
         k2_cp_async_wait_all();
         __syncwarp();
         const uint32_t code = mycode + cur * (K2_BUF * 16);
-        stage(mycode + (cur ^ 1) * (K2_BUF * 16), d1); /* next program's code: in flight while this one runs */
+        uint32_t h_dst, h_next, h_flags, h_pad;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_pad) : "r"(code + K1V2_HDR * 16));
+        /* the row after this one */
+        Cur nx = c;
+        nx.q = c.q + K1V2_CQ + c.n;
+        nx.n = (int)h_next;
+        if (h_flags & K1V2_ROW_LAST) {
+            if (++nx.unit >= c.unit_end) open_item(nx);
+        }
+        stage(mycode + (cur ^ 1) * (K2_BUF * 16), nx); /* next row's code: in flight while this one runs */
 
         const uint8_t* __restrict__ const gtile = p.tiles + (size_t)c.tile * tile_bytes;
         const double* __restrict__ const sobel_tile = p.sobel + (size_t)c.tile * 2 * plane_stride;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         uint32_t lp = code + K1V2_CQ * 16;
-        int staged = min(d0.y, K1V2_CAP); /* entries of the program staged so far */
+        int staged = min(c.n, K1V2_CAP); /* entries of the program staged so far */
         for (;;) {
             uint32_t xc;
+            double b0, b1, b2, b3; /* second operand of the heavy handlers; meaningful after a slow-path exit only */
             asm volatile(
                 "{\n"
                 ".reg .b32 hx, ya, zb, wd, ra, pw, t0;\n"
                 ".reg .b64 ga;\n"
-                ".reg .pred pq, p1, p2, pas, pbs, psp, pall, prare, pm0, pm1, pm2, pm3, pt0, pt1, pt2, pt3, pz0, pz1, pz2, pz3;\n"
+                ".reg .pred pnever, pq, p1, p2, pas, pbs, psp, psp0, psp1, psp2, psp3, pall, pany, prare, pslow, pm0, pm1, pm2, pm3, pt0, pt1, pt2, pt3, pz0, pz1, pz2, pz3;\n"
                 ".reg .b32 alo, ahi, blo, bhi, ha, hb, slo, shi, qlo, qhi, xlo, xhi, ax, ki, ii, ee, kk, ylo, yhi;\n"
                 ".reg .f32 fq, fb, fa, ft;\n"
-                ".reg .f64 sd, rr, nb, t1, t2, r1, r2, q0, rem, sp, qr0, qr1, qr2, qr3, cst;\n"
+                ".reg .f64 sd0, sd1, sd2, sd3, rr, nb, t1, t2, r1, r2, q0, rem, sp, qr0, qr1, qr2, qr3, cst;\n"
                 ".reg .f64 z, tm, kd, r, tail, TT, pa, pb, tmp, r4, y, ev, invc, lchi, lclo, w, hi, lo;\n"
                 "tlist: .branchtargets " K1V2_HANDLERS(K2_TARGET) "H_END;\n"
+                "setp.ne.u32 pnever, " NEVER ", 0;\n"
                 "FETCH:\n"
                 "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n"
                 "add.u32 " LP ", " LP ", 16;\n"
                 "brx.idx.uni hx, tlist;\n"
                 "H_ST:\n"
                 "add.u32 ra, wd, " REGS ";\n"
+                PF
                 "st.shared.v2.f64 [ra], {" A0 ", " A1 "};\n"
                 "st.shared.v2.f64 [ra+512], {" A2 ", " A3 "};\n"
-                NEXT_LINE
+                GO
                 BIN_COMM("ADD", "add.rn.f64")
                 BIN_COMM("MUL", "mul.rn.f64")
                 BIN_ORD("SUB", OP_AB("sub.rn.f64"), OP_BA("sub.rn.f64"), OP_AA("sub.rn.f64"))
@@ -334,91 +372,122 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 "H_SOBD:\n"
                 "add.u32 pw, ya, " LANE ";\n"
                 "mad.wide.u32 ga, pw, 32, " SOBEL ";\n"
+                PF
                 "ld.global.nc.v2.f64 {" A0 ", " A1 "}, [ga];\n"
                 "ld.global.nc.v2.f64 {" A2 ", " A3 "}, [ga+16];\n"
-                NEXT_LINE
+                GO
                 /* exp / ln of a pixel: 256-entry tables */
                 "H_LUTL:\n"
-                "add.u32 pw, ya, " LANE ";\n"
-                "mad.wide.u32 ga, pw, 4, " GTILE ";\n"
+                ADDR_P("ya") PF
                 "ld.global.nc.u32 pw, [ga];\n"
                 "and.b32 t0, pw, 255;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A0 ", [ga+2048];\n"
                 "bfe.u32 t0, pw, 8, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A1 ", [ga+2048];\n"
                 "bfe.u32 t0, pw, 16, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A2 ", [ga+2048];\n"
                 "shr.u32 t0, pw, 24;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A3 ", [ga+2048];\n"
-                NEXT_LINE
+                GO
                 "H_LUTE:\n"
-                "add.u32 pw, ya, " LANE ";\n"
-                "mad.wide.u32 ga, pw, 4, " GTILE ";\n"
+                ADDR_P("ya") PF
                 "ld.global.nc.u32 pw, [ga];\n"
                 "and.b32 t0, pw, 255;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A0 ", [ga];\n"
                 "bfe.u32 t0, pw, 8, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A1 ", [ga];\n"
                 "bfe.u32 t0, pw, 16, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A2 ", [ga];\n"
                 "shr.u32 t0, pw, 24;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A3 ", [ga];\n"
-                NEXT_LINE
+                GO
                 /* division: operands into (acc, b) in order, then the body */
                 "H_DIV_PP:\n" LOAD_AP "bra.uni H_DIV_AP;\n"
                 "H_DIV_RP:\n" LOAD_AR
-                "H_DIV_AP:\n" LOAD_BP("zb") "bra.uni DIVBODY;\n"
+                "H_DIV_AP:\n" LAST_BP("zb") "bra.uni DIVBODY;\n"
                 "H_DIV_PR:\n" LOAD_AP "bra.uni H_DIV_AR;\n"
                 "H_DIV_RR:\n" LOAD_AR
-                "H_DIV_AR:\n" LOAD_BR("zb") "bra.uni DIVBODY;\n"
-                "H_DIV_RA:\n" MOV_B_A LOAD_AR "bra.uni DIVBODY;\n"
-                "H_DIV_PA:\n" MOV_B_A LOAD_AP "bra.uni DIVBODY;\n"
-                "H_DIV_AA:\n" MOV_B_A
+                "H_DIV_AR:\n" LAST_BR("zb") "bra.uni DIVBODY;\n"
+                "H_DIV_RA:\n" MOV_B_A LAST_AR "bra.uni DIVBODY;\n"
+                "H_DIV_PA:\n" MOV_B_A LAST_AP "bra.uni DIVBODY;\n"
+                "H_DIV_AA:\n" MOV_B_A PF
                 "DIVBODY:\n"
+                /* classes first: when every sample of the warp has a zero / infinite / NaN operand (a fifth of the
+                   divisions of evolved programs) the quotients are a * seed and the Newton sequence is skipped */
+                "setp.ne.u32 pany, 0, 0;\n"
+                DIV_CLASS(A0, B0, "0") DIV_CLASS(A1, B1, "1") DIV_CLASS(A2, B2, "2") DIV_CLASS(A3, B3, "3")
+                "vote.sync.any.pred p1, pany, 0xffffffff;\n"
+                "@!p1 bra.uni DIV_ALLSP;\n"
                 "setp.eq.u32 pall, 0, 0;\n"
-                DIV1(A0, B0, "qr0") DIV1(A1, B1, "qr1") DIV1(A2, B2, "qr2") DIV1(A3, B3, "qr3")
+                DIV_SEQ(A0, B0, "0") DIV_SEQ(A1, B1, "1") DIV_SEQ(A2, B2, "2") DIV_SEQ(A3, B3, "3")
                 "vote.sync.all.pred p1, pall, 0xffffffff;\n"
                 "@!p1 bra.uni X_SLOW_DIV;\n"
                 "mov.f64 " A0 ", qr0;\n mov.f64 " A1 ", qr1;\n mov.f64 " A2 ", qr2;\n mov.f64 " A3 ", qr3;\n"
-                NEXT_LINE
+                GO
+                "DIV_ALLSP:\n"
+                "mul.rn.f64 " A0 ", " A0 ", sd0;\n mul.rn.f64 " A1 ", " A1 ", sd1;\n mul.rn.f64 " A2 ", " A2 ", sd2;\n mul.rn.f64 " A3 ", " A3 ", sd3;\n"
+                GO
+                /* exp / ln: the rare operands (the slivers next to exp's thresholds, positive subnormals for ln) are known
+                   from the inputs; when a lane has one, the inputs are kept in b, the fast path runs for everybody and
+                   the block is left afterwards so that the C++ side patches just those samples */
                 "H_EXP_R:\n" LOAD_AR
                 "H_EXP_A:\n"
+                PF
                 "setp.ne.u32 prare, 0, 0;\n"
                 EXP_RARE(A0, "0") EXP_RARE(A1, "1") EXP_RARE(A2, "2") EXP_RARE(A3, "3")
-                "vote.sync.any.pred p1, prare, 0xffffffff;\n"
-                "@p1 bra.uni X_SLOW_EXP;\n"
+                "vote.sync.any.pred pslow, prare, 0xffffffff;\n"
+                "@pslow bra.uni EXP_KEEP;\n"
+                "EXP_GO:\n"
                 EXP_MAIN(A0, "0") EXP_MAIN(A1, "1") EXP_MAIN(A2, "2") EXP_MAIN(A3, "3")
-                NEXT_LINE
+                "@pslow bra.uni X_SLOW_EXP;\n"
+                GO
+                "EXP_KEEP:\n" MOV_B_A "bra.uni EXP_GO;\n"
                 "H_LN_R:\n" LOAD_AR
                 "H_LN_A:\n"
-                "setp.ne.u32 prare, 0, 0;\n"
+                PF
+                "setp.ne.u32 prare, 0, 0;\n setp.ne.u32 pany, 0, 0;\n"
                 LN_RARE(A0, "0") LN_RARE(A1, "1") LN_RARE(A2, "2") LN_RARE(A3, "3")
-                "vote.sync.any.pred p1, prare, 0xffffffff;\n"
-                "@p1 bra.uni X_SLOW_LN;\n"
+                "vote.sync.any.pred pslow, prare, 0xffffffff;\n"
+                "@pslow bra.uni LN_KEEP;\n"
+                "LN_GO:\n"
+                /* no sample of the warp is positive, normal and finite (a fifth of the ln lines): edge answers only */
+                "vote.sync.any.pred p1, pany, 0xffffffff;\n"
+                "@!p1 bra.uni LN_EDGES;\n"
                 LN_MAIN(A0, "0") LN_MAIN(A1, "1") LN_MAIN(A2, "2") LN_MAIN(A3, "3")
-                NEXT_LINE
+                "@pslow bra.uni X_SLOW_LN;\n"
+                GO
+                "LN_EDGES:\n"
+                LN_EDGE(A0, "0") LN_EDGE(A1, "1") LN_EDGE(A2, "2") LN_EDGE(A3, "3")
+                "@pslow bra.uni X_SLOW_LN;\n"
+                GO
+                "LN_KEEP:\n" MOV_B_A "bra.uni LN_GO;\n"
                 /* multByConst: a * c / 10 ([REF] mnist/src/main.cpp:54) */
                 "H_MULC_P:\n" LOAD_AP "bra.uni H_MULC_A;\n"
                 "H_MULC_R:\n" LOAD_AR
                 "H_MULC_A:\n"
-                "add.u32 ra, zb, " CBASE ";\n ld.shared.f64 cst, [ra];\n"
+                "add.u32 ra, zb, " CBASE ";\n"
+                PF
+                "ld.shared.f64 cst, [ra];\n"
                 "mul.rn.f64 " A0 ", " A0 ", cst;\n mul.rn.f64 " A1 ", " A1 ", cst;\n mul.rn.f64 " A2 ", " A2 ", cst;\n mul.rn.f64 " A3 ", " A3 ", cst;\n"
                 "setp.eq.u32 pall, 0, 0;\n"
                 DIV10_1(A0, "qr0") DIV10_1(A1, "qr1") DIV10_1(A2, "qr2") DIV10_1(A3, "qr3")
-                "vote.sync.all.pred p1, pall, 0xffffffff;\n"
-                "@!p1 bra.uni X_SLOW_MULC;\n"
+                "vote.sync.all.pred pslow, pall, 0xffffffff;\n"
+                "@!pslow bra.uni MULC_KEEP;\n"
+                "MULC_FIN:\n"
                 "mov.f64 " A0 ", qr0;\n mov.f64 " A1 ", qr1;\n mov.f64 " A2 ", qr2;\n mov.f64 " A3 ", qr3;\n"
-                NEXT_LINE
-                "X_SLOW_DIV:\n mov.u32 " CODE ", 1000;\n bra.uni XEND;\n"
-                "X_SLOW_EXP:\n mov.u32 " CODE ", 1001;\n bra.uni XEND;\n"
-                "X_SLOW_LN:\n mov.u32 " CODE ", 1002;\n bra.uni XEND;\n"
-                "X_SLOW_MULC:\n mov.u32 " CODE ", 1003;\n bra.uni XEND;\n"
+                "@!pslow bra.uni X_SLOW_MULC;\n"
+                GO
+                "MULC_KEEP:\n" MOV_B_A "bra.uni MULC_FIN;\n"
+                "X_SLOW_DIV:\n" UNFETCH "mov.u32 " CODE ", 1000;\n bra.uni XEND;\n"
+                "X_SLOW_EXP:\n" UNFETCH "mov.u32 " CODE ", 1001;\n bra.uni XEND;\n"
+                "X_SLOW_LN:\n" UNFETCH "mov.u32 " CODE ", 1002;\n bra.uni XEND;\n"
+                "X_SLOW_MULC:\n" UNFETCH "mov.u32 " CODE ", 1003;\n bra.uni XEND;\n"
                 "H_NEXT:\n"
                 "H_END:\n"
                 "mov.u32 " CODE ", hx;\n"
                 "XEND:\n"
                 "}\n"
-                : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "+d"(b0), "+d"(b1), "+d"(b2), "+d"(b3), "+r"(lp), "=r"(xc)
-                : "r"(regs_lane), "r"(lane), "l"(gtile), "l"(sobel_tile), "l"(p.pixel_lut), "r"(code), "r"(tabs.exp_addr), "r"(tabs.log_addr)
+                : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "=&d"(b0), "=&d"(b1), "=&d"(b2), "=&d"(b3), "+r"(lp), "=&r"(xc)
+                : "r"(regs_lane), "r"(lane), "l"(gtile), "l"(sobel_tile), "l"(p.pixel_lut), "r"(code), "r"(tabs.exp_addr), "r"(tabs.log_addr), "r"(never)
                 : "memory");
             if (xc == K2H_END) break;
             if (xc == K2H_NEXT) { /* programs longer than one block: stage the next K1V2_CAP entries synchronously */
                 __syncwarp();
-                const int m = min(d0.y - staged, K1V2_CAP);
+                const int m = min(c.n - staged, K1V2_CAP);
                 for (int i = lane; i < m; i += 32) {
-                    const uint4 q = __ldg(stream + d0.x + K1V2_CQ + staged + i);
+                    const uint4 q = __ldg(stream + c.q + K1V2_CQ + staged + i);
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(code + (K1V2_CQ + i) * 16), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
                 }
                 __syncwarp();
@@ -427,23 +496,25 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 continue;
             }
             /* rare operands of a heavy operation (a subnormal somewhere, the slivers next to exp's overflow / underflow
-               thresholds): the generic routines, sample by sample */
-            double a[4] = {a0, a1, a2, a3}, r[4];
-            if (xc == K2X_SLOW_DIV) {
-                const double b[4] = {b0, b1, b2, b3};
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv(a[k], b[k]);
-            } else if (xc == K2X_SLOW_EXP) {
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) r[k] = tpgx_math::exp(a[k]);
+               thresholds, |a * c| outside 2^+-1000): the fast path has answered every other sample; patch these */
+            if (xc == K2X_SLOW_DIV) { /* operands intact in (a, b) */
+                a0 = tpgx_math::xdiv(a0, b0); a1 = tpgx_math::xdiv(a1, b1); a2 = tpgx_math::xdiv(a2, b2); a3 = tpgx_math::xdiv(a3, b3);
+            } else if (xc == K2X_SLOW_EXP) { /* inputs in b, fast results in a */
+                if (tpgx_math::exp_is_rare(b0)) a0 = tpgx_math::exp_slow(b0);
+                if (tpgx_math::exp_is_rare(b1)) a1 = tpgx_math::exp_slow(b1);
+                if (tpgx_math::exp_is_rare(b2)) a2 = tpgx_math::exp_slow(b2);
+                if (tpgx_math::exp_is_rare(b3)) a3 = tpgx_math::exp_slow(b3);
             } else if (xc == K2X_SLOW_LN) {
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) r[k] = tpgx_math::log(a[k]);
-            } else { /* K2X_SLOW_MULC: the products are in the accumulator */
-#pragma unroll 1
-                for (int k = 0; k < 4; k++) r[k] = tpgx_math::xdiv10(a[k]);
+                if (tpgx_math::log_is_rare(b0)) a0 = tpgx_math::log_slow(b0);
+                if (tpgx_math::log_is_rare(b1)) a1 = tpgx_math::log_slow(b1);
+                if (tpgx_math::log_is_rare(b2)) a2 = tpgx_math::log_slow(b2);
+                if (tpgx_math::log_is_rare(b3)) a3 = tpgx_math::log_slow(b3);
+            } else { /* K2X_SLOW_MULC: the products a * c in b, fast quotients in a */
+                if (!tpgx_math::div10_fast_ok(b0)) a0 = tpgx_math::xdiv(b0, 10.0);
+                if (!tpgx_math::div10_fast_ok(b1)) a1 = tpgx_math::xdiv(b1, 10.0);
+                if (!tpgx_math::div10_fast_ok(b2)) a2 = tpgx_math::xdiv(b2, 10.0);
+                if (!tpgx_math::div10_fast_ok(b3)) a3 = tpgx_math::xdiv(b3, 10.0);
             }
-            a0 = r[0]; a1 = r[1]; a2 = r[2]; a3 = r[3];
         }
         /* the last effective line of a program writes register 0: the bid is the accumulator.
            [UP] TPGExecutionEngine::evaluateEdge: NaN bid -> -inf */
@@ -452,26 +523,26 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
         for (int k = 0; k < 4; k++)
             if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
         if (!TEAM) {
-            double* out = p.bid + (size_t)c.row * p.row_stride + (size_t)c.tile * K2_TS + lane * 4;
+            double* out = p.bid + (size_t)c.unit * p.row_stride + (size_t)c.tile * K2_TS + lane * 4; /* bid mode: unit = row */
             *reinterpret_cast<double2*>(out) = make_double2(res[0], res[1]);
             *reinterpret_cast<double2*>(out + 2) = make_double2(res[2], res[3]);
         } else {
             /* [UP] evaluateTeam: the first edge is the initial best; a later edge replaces it if
                bid >= best (last-max) / bid > best (first-max) */
-            const int dst = __ldg(p.row_dst + c.row);
-            const bool first = c.row == c.first;
+            const int dst = (int)h_dst;
+            const bool first = (h_flags & K1V2_ROW_FIRST) != 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const bool take = first | (p.tie_break == TPGX_TIE_LAST_MAX ? (res[k] >= best[k]) : (res[k] > best[k]));
                 best[k] = take ? res[k] : best[k];
                 best_dst[k] = take ? dst : best_dst[k];
             }
-            if (c.row + 1 == c.row_end) {
+            if (h_flags & K1V2_ROW_LAST) {
                 int* out = p.decision + (size_t)c.unit * p.row_stride + (size_t)c.tile * K2_TS + lane * 4;
                 *reinterpret_cast<int4*>(out) = make_int4(best_dst[0], best_dst[1], best_dst[2], best_dst[3]);
             }
         }
-        c = nx; d0 = d1; cur ^= 1;
+        c = nx; cur ^= 1;
     }
     k2_cp_async_wait_all();
 }
@@ -499,23 +570,25 @@ cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team, int nb_ctas, 
 /* the stream of K1 v2, written on the device from the generic code: one thread per row */
 __global__ void tpgx_k1v2_encode_kernel(const uint32_t* __restrict__ code, const int32_t* __restrict__ prog_offset,
                                         const double* __restrict__ constants, int nb_constants, const int32_t* __restrict__ active_prog,
-                                        const int2* __restrict__ desc, int nb_rows, int width, int hw, int nwin, uint4* __restrict__ stream,
-                                        int* __restrict__ flags) {
+                                        const int2* __restrict__ desc, const int32_t* __restrict__ row_dst, const uint8_t* __restrict__ row_flags,
+                                        int nb_rows, int width, int hw, int nwin, uint4* __restrict__ stream, int* __restrict__ flags) {
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nb_rows) return;
     const int pidx = active_prog[row];
     const int2 d = desc[row];
     double* cq = reinterpret_cast<double*>(stream + d.x);
-    for (int k = 0; k < 2 * K1V2_CQ; k++) cq[k] = k < nb_constants ? constants[(size_t)pidx * nb_constants + k] : 0.0;
+    for (int k = 0; k < 2 * K1V2_HDR; k++) cq[k] = k < nb_constants ? constants[(size_t)pidx * nb_constants + k] : 0.0;
+    stream[d.x + K1V2_HDR] = make_uint4(row_dst ? (uint32_t)row_dst[row] : 0u, row + 1 < nb_rows ? (uint32_t)desc[row + 1].y : 0u,
+                                        row_flags ? (uint32_t)row_flags[row] : (K1V2_ROW_FIRST | K1V2_ROW_LAST), 0u);
     const tpgx_k1v2_info info = tpgx_k1v2_encode(code + prog_offset[pidx], prog_offset[pidx + 1] - prog_offset[pidx], K2_TS, (uint32_t)width,
                                                  (uint32_t)hw, (uint32_t)nwin, reinterpret_cast<tpgx_k1_quad*>(stream + d.x + K1V2_CQ));
     if (!info.ok || info.entries != d.y || info.slots > K1V2_SLOTS) atomicOr(flags, 4);
 }
 cudaError_t tpgx_launch_k1v2_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
-                                    const int32_t* active_prog, const int2* desc, int nb_rows, int width, int hw, int nwin, uint4* stream,
-                                    int* flags, cudaStream_t st) {
+                                    const int32_t* active_prog, const int2* desc, const int32_t* row_dst, const uint8_t* row_flags, int nb_rows,
+                                    int width, int hw, int nwin, uint4* stream, int* flags, cudaStream_t st) {
     if (nb_rows <= 0) return cudaSuccess;
-    tpgx_k1v2_encode_kernel<<<(nb_rows + 127) / 128, 128, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, nb_rows, width, hw,
-                                                                  nwin, stream, flags);
+    tpgx_k1v2_encode_kernel<<<(nb_rows + 127) / 128, 128, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, row_dst, row_flags,
+                                                                  nb_rows, width, hw, nwin, stream, flags);
     return cudaGetLastError();
 }

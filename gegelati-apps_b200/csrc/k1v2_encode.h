@@ -27,7 +27,10 @@
 #include "tpgx_internal.h"
 
 #define K1V2_SLOTS 5      /* shared-memory register slots per warp */
-#define K1V2_CQ 4         /* constant quads at the head of a program's stream (8 doubles) */
+#define K1V2_CQ 5         /* quads at the head of a row's stream: 4 of program constants (8 doubles), then the row header */
+#define K1V2_HDR 4        /* header quad {x = destination of the edge, y = entries of the NEXT row of the stream, z = flags} */
+#define K1V2_ROW_LAST 1u  /* flags: last row (edge) of its unit (team) */
+#define K1V2_ROW_FIRST 2u /* first row of its unit */
 #define K1V2_CAP 36       /* entries staged at a time */
 #define K1V2_MAX_LINES 256 /* longer programs run on K1 v1 */
 

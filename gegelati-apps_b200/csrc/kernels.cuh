@@ -34,8 +34,8 @@ struct tpgx_bid_params {
 struct tpgx_bid2_params {
     const uint8_t* tiles;        /* [tiles][hw + 1][128] pixel-major sample tiles (first tile of the pass) */
     int hw;
-    const uint4* stream;         /* per row: K1V2_CQ constant quads, then its entries                     */
-    const int2* desc;            /* [rows] {first quad of the row in stream, number of entries}            */
+    const uint4* stream;         /* per row: K1V2_CQ head quads (constants, row header), then its entries   */
+    const int2* unit_first;      /* [units] {first quad, number of entries} of the unit's first row         */
     const double* pixel_lut;
     const double* sobel;
     int nwin;
@@ -43,16 +43,14 @@ struct tpgx_bid2_params {
     unsigned int* work_counter;  /* next unclaimed item (zeroed by the launcher)                           */
     double* bid;
     long long row_stride;
-    const int2* team;
-    const int32_t* row_dst;
     int32_t* decision;
     int tie_break;
 };
 size_t tpgx_bid2_smem_bytes();
 cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team_mode, int nb_ctas, cudaStream_t st);
 cudaError_t tpgx_launch_k1v2_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
-                                    const int32_t* active_prog, const int2* desc, int nb_rows, int width, int hw, int nwin, uint4* stream,
-                                    int* flags, cudaStream_t st);
+                                    const int32_t* active_prog, const int2* desc, const int32_t* row_dst, const uint8_t* row_flags, int nb_rows,
+                                    int width, int hw, int nwin, uint4* stream, int* flags, cudaStream_t st);
 
 /* K2: graph traversal per (root, sample) on the bid matrix. */
 struct tpgx_trav_params {

@@ -80,7 +80,7 @@ struct tpgx_ctx {
     DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
-    DevBuf d_scratch[16], d_work;
+    DevBuf d_scratch[16], d_work, d_k2_rflags, d_k2_ufirst;
     /* tpgx_set_observations_pinned enqueues its copy / re-tiling / Sobel-plane work on a stream of its own, so that
        the graph uploads that follow on the main stream are not queued behind 47 MB of observations; consumers of the
        tiles wait for obs_ready */
@@ -183,6 +183,7 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
     pl.team_mode = !want_bid && acyclic && edge_lines_total * 4 <= uniq_lines * 5 && !(force && force[0] == '0');
     pl.want_bid = want_bid;
     tpgx_status st;
+    std::vector<int32_t> team_rows; /* team mode: {first row, number of rows} per unit */
     if (pl.team_mode) {
         std::vector<int32_t> team(2 * queue.size()), stat(2 * queue.size()), rows, dsts, roots(re - rb);
         for (size_t u = 0; u < queue.size(); u++) {
@@ -200,6 +201,7 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         }
         for (int r = rb; r < re; r++) roots[r - rb] = unit_of[f.root_team[r]];
         ctx->h_active = rows;
+        team_rows = team;
         pl.nb_units = (int)queue.size();
         if ((st = upload(ctx, ctx->d_tm_team, team.data(), team.size() * 4)) != TPGX_OK) return st;
         if ((st = upload(ctx, ctx->d_tm_stat, stat.data(), stat.size() * 4)) != TPGX_OK) return st;
@@ -245,10 +247,29 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         CU(ctx->d_status.ensure(16));
         int* d_flags = ctx->d_status.as<int>() + 2;
         CU(cudaMemsetAsync(d_flags, 0, 4, ctx->stream));
-        if (v2)
+        if (v2) {
+            /* row headers: edge destination (team mode: already on the device), entries of the next row, first / last row of
+               its unit; and per unit where its first row starts */
+            const uint8_t* d_row_flags = nullptr;
+            if (pl.team_mode) {
+                std::vector<uint8_t> rflags((size_t)nrows, 0);
+                std::vector<int32_t> ufirst(2 * (size_t)pl.nb_units);
+                for (int u = 0; u < pl.nb_units; u++) {
+                    const int r0 = team_rows[2 * u], nr = team_rows[2 * u + 1];
+                    rflags[r0] |= K1V2_ROW_FIRST;
+                    rflags[r0 + nr - 1] |= K1V2_ROW_LAST;
+                    ufirst[2 * u] = desc[2 * r0]; ufirst[2 * u + 1] = desc[2 * r0 + 1];
+                }
+                if ((st = upload(ctx, ctx->d_k2_rflags, rflags.data(), rflags.size())) != TPGX_OK) return st;
+                if ((st = upload(ctx, ctx->d_k2_ufirst, ufirst.data(), ufirst.size() * 4)) != TPGX_OK) return st;
+                CU(cudaStreamSynchronize(ctx->stream)); /* locals */
+                d_row_flags = ctx->d_k2_rflags.as<uint8_t>();
+            }
             CU(tpgx_launch_k1v2_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
-                                       ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ctx->obs_width, ctx->obs_hw,
+                                       ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), pl.team_mode ? ctx->d_tm_dst.as<int32_t>() : nullptr,
+                                       d_row_flags, nrows, ctx->obs_width, ctx->obs_hw,
                                        std::max(0, (ctx->src[0].height - 2) * (ctx->src[0].width - 2)), ctx->d_k1_stream.as<uint4>(), d_flags, ctx->stream));
+        }
         else
             CU(tpgx_launch_k1_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
                                      ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->obs_hw, ctx->d_k1_stream.as<uint4>(),
@@ -360,7 +381,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.tiles = ctx->d_tiles.as<uint8_t>() + (size_t)t0 * (hw + 1) * ts;
             bp.hw = hw;
             bp.stream = ctx->d_k1_stream.as<uint4>();
-            bp.desc = ctx->d_k1_desc.as<int2>();
+            bp.unit_first = team_mode ? ctx->d_k2_ufirst.as<int2>() : ctx->d_k1_desc.as<int2>();
             bp.pixel_lut = ctx->d_pixel_lut.as<double>();
             bp.sobel = ctx->nwin ? ctx->d_sobel.as<double>() + (size_t)t0 * 2 * ctx->nwin * ts : nullptr;
             bp.nwin = ctx->nwin;
@@ -377,8 +398,6 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.work_counter = ctx->d_work.as<unsigned int>();
             bp.bid = ctx->d_bid.as<double>();
             bp.row_stride = (long long)nt * ts;
-            bp.team = ctx->d_tm_team.as<int2>();
-            bp.row_dst = ctx->d_tm_dst.as<int32_t>();
             bp.decision = ctx->d_decision.as<int32_t>();
             bp.tie_break = ctx->cfg.tie_break;
             int ctas = (int)std::min<int64_t>(ctx->sm_count, ((int64_t)bp.nb_items + 31) / 32);
@@ -530,7 +549,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_tm_team, &ctx->d_tm_dst, &ctx->d_tm_stat, &ctx->d_tm_roots, &ctx->d_decision, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
-                     &ctx->d_counters, &ctx->d_status, &ctx->d_work};
+                     &ctx->d_counters, &ctx->d_status, &ctx->d_work, &ctx->d_k2_rflags, &ctx->d_k2_ufirst};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : ctx->d_scratch) b.release();
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
