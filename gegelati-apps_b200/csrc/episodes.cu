@@ -185,6 +185,7 @@ struct StickGame {
         }
     }
     __device__ bool do_action(const tpgx_episode_params&, int a, tpgx_rng_cursor& rng) {
+        if (a < 0 || a >= 3) return false; /* [REF] stickGameAdversarial.cpp:61: LearningEnvironment::doAction throws past nbActions = 3 */
         if (!is_terminal()) {
             const bool first = turn % 2 == 0;
             int s = sticks[0];
@@ -240,6 +241,7 @@ struct TicTacToe {
         if (turn > 8) { null_game = 1; end = 1; }
     }
     __device__ bool do_action(const tpgx_episode_params&, int a, tpgx_rng_cursor& rng) {
+        if (a < 0 || a >= 9) return false; /* [REF] TicTacToe.cpp:41,46: board.getDataAt / setDataAt(actionID) throw outside the 9 cells */
         const bool even = turn % 2 == 0;
         if (!is_terminal()) {
             const double cell = board[a];

@@ -12,6 +12,8 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include <cub/device/device_scan.cuh>
 
 #include "dev_ops.cuh"
@@ -98,8 +100,12 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_traverse_kernel(const tpgx_
         if (action >= 0) {
             if (p.action) p.action[(size_t)r * p.action_stride + s] = (uint8_t)action;
             if (p.labels) {
-                if (action < C) atomicAdd(&s_table[(int)__ldg(p.labels + s) * C + action], 1u);
-                else err |= TPGX_DEV_BAD_ACTION;
+                /* [UP] ClassificationLearningEnvironment::doAction: classificationTable.at(currentClass).at(actionID) throws
+                   outside the table; here both are reported */
+                const int lab = (int)__ldg(p.labels + s);
+                if (action >= C) err |= TPGX_DEV_BAD_ACTION;
+                else if (lab >= C) err |= TPGX_DEV_BAD_LABEL;
+                else atomicAdd(&s_table[lab * C + action], 1u);
             }
         }
     }
@@ -124,10 +130,21 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_traverse_kernel(const tpgx_
     if (threadIdx.x < 4 && p.counters) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
-cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p, cudaStream_t st) {
-    dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
-    tpgx_traverse_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
-    return cudaGetLastError();
+/* roots ride on grid.y (<= 65 535): larger shards are launched in slices of the root range */
+#define TPGX_MAX_GRID_Y 65535
+cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p0, cudaStream_t st) {
+    for (int r0 = 0; r0 < p0.nb_roots; r0 += TPGX_MAX_GRID_Y) {
+        tpgx_trav_params p = p0;
+        p.nb_roots = std::min(TPGX_MAX_GRID_Y, p0.nb_roots - r0);
+        p.roots = p0.roots + r0;
+        if (p.action) p.action = p0.action + (size_t)r0 * p0.action_stride;
+        if (p.confusion) p.confusion = p0.confusion + (size_t)r0 * p0.nb_classes * p0.nb_classes;
+        dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
+        tpgx_traverse_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 /* ================================================================================================
@@ -178,8 +195,9 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk
         if (action >= 0) {
             if (p.action) p.action[(size_t)r * p.action_stride + s] = (uint8_t)action;
             if (p.labels) {
-                if (action < C) atomicAdd(&s_table[lab[it] * C + action], 1u);
-                else err |= TPGX_DEV_BAD_ACTION;
+                if (action >= C) err |= TPGX_DEV_BAD_ACTION;
+                else if (lab[it] >= C) err |= TPGX_DEV_BAD_LABEL;
+                else atomicAdd(&s_table[lab[it] * C + action], 1u);
             }
         }
     }
@@ -203,10 +221,19 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk
     if (threadIdx.x < 4 && p.counters) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
-cudaError_t tpgx_launch_walk(const tpgx_walk_params& p, cudaStream_t st) {
-    dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
-    tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
-    return cudaGetLastError();
+cudaError_t tpgx_launch_walk(const tpgx_walk_params& p0, cudaStream_t st) {
+    for (int r0 = 0; r0 < p0.nb_roots; r0 += TPGX_MAX_GRID_Y) {
+        tpgx_walk_params p = p0;
+        p.nb_roots = std::min(TPGX_MAX_GRID_Y, p0.nb_roots - r0);
+        p.root_unit = p0.root_unit + r0;
+        if (p.action) p.action = p0.action + (size_t)r0 * p0.action_stride;
+        if (p.confusion) p.confusion = p0.confusion + (size_t)r0 * p0.nb_classes * p0.nb_classes;
+        dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
+        tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 /* ================================================================================================
@@ -252,10 +279,18 @@ __global__ void tpgx_arch_count_kernel(const tpgx_arch_params p) {
     if (err) atomicOr(p.status, err);
     p.counts[(size_t)r * p.nb_samples + s] = n;
 }
-cudaError_t tpgx_launch_arch_count(const tpgx_arch_params& p, cudaStream_t st) {
-    dim3 grid((p.nb_samples + 127) / 128, p.nb_roots);
-    tpgx_arch_count_kernel<<<grid, 128, 0, st>>>(p);
-    return cudaGetLastError();
+cudaError_t tpgx_launch_arch_count(const tpgx_arch_params& p0, cudaStream_t st) {
+    for (int r0 = 0; r0 < p0.nb_roots; r0 += TPGX_MAX_GRID_Y) {
+        tpgx_arch_params p = p0;
+        p.nb_roots = std::min(TPGX_MAX_GRID_Y, p0.nb_roots - r0);
+        p.roots = p0.roots + r0;
+        p.counts = p0.counts + (size_t)r0 * p0.nb_samples;
+        dim3 grid((p.nb_samples + 127) / 128, p.nb_roots);
+        tpgx_arch_count_kernel<<<grid, 128, 0, st>>>(p);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 /* inclusive prefix of every root's row, in place (temp == NULL: size query) */
 cudaError_t tpgx_arch_scan(const tpgx_arch_params& p, void* temp, size_t* temp_bytes, cudaStream_t st) {

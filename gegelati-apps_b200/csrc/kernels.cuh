@@ -124,6 +124,7 @@ cudaError_t tpgx_launch_arch_resolve(const tpgx_arch_params& p, cudaStream_t st)
 #define TPGX_DEV_PATH_TOO_LONG 2
 #define TPGX_DEV_BAD_ACTION 4
 #define TPGX_DEV_RNG_EXHAUSTED 8
+#define TPGX_DEV_BAD_LABEL 16
 
 /* Launchers (defined in kernels.cu). variant: 0 = default tile shape. Returns cudaError_t. */
 int tpgx_bid_tile_samples(int variant);

@@ -492,7 +492,8 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
 tpgx_status check_device_status(tpgx_ctx* ctx, int status) {
     if (status & TPGX_DEV_NO_EDGE) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "a team had no admissible outgoing edge (the reference throws \"No outgoing edge to evaluate\")");
     if (status & TPGX_DEV_PATH_TOO_LONG) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "root->action path longer than TPGX_MAX_PATH teams");
-    if (status & TPGX_DEV_BAD_ACTION) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "action id outside [0, nb_classes)");
+    if (status & TPGX_DEV_BAD_ACTION) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "action id outside the environment's action range (the reference throws in doAction)");
+    if (status & TPGX_DEV_BAD_LABEL) return fail(ctx, TPGX_ERR_BAD_ARG, "observation label outside [0, nb_classes) (the reference's classificationTable.at() throws)");
     if (status & TPGX_DEV_RNG_EXHAUSTED) return fail(ctx, TPGX_ERR_STATE, "episode consumed more RNG draws than the table holds");
     return TPGX_OK;
 }
@@ -580,6 +581,13 @@ tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_de
     }
     ctx->src.assign(src, src + n);
     ctx->has_graph = false;
+    /* everything derived from the previous source shape goes: uploaded observations, their tiles and Sobel planes, the plan */
+    ctx->obs_dev = nullptr;
+    ctx->labels_dev = nullptr;
+    ctx->nb_obs = 0;
+    ctx->obs_hw = ctx->obs_width = ctx->nwin = 0;
+    ctx->tiles_identity_valid = false;
+    ctx->plan = ShardPlan();
     return TPGX_OK;
 }
 
@@ -901,7 +909,8 @@ static tpgx_status episodes_impl(tpgx_ctx* ctx, const tpgx_episode_request* req,
     /* RNG streams: every root sees the same seed per iteration ([UP] evaluateJob), so the raw
        mt19937_64 outputs are generated once per iteration on the host and shared by all jobs */
     std::vector<uint64_t> raw((size_t)NI * TPGX_RNG_TABLE);
-    for (int it = 0; it < NI; it++) tpgx_rng_fill_raw(tpgx_env_seed(req->seeds[it], req->mode), TPGX_RNG_TABLE, raw.data() + (size_t)it * TPGX_RNG_TABLE);
+    for (int it = 0; it < NI; it++)
+        tpgx_rng_fill_raw(req->rng_seeds ? req->rng_seeds[it] : tpgx_env_seed(req->seeds[it], req->mode), TPGX_RNG_TABLE, raw.data() + (size_t)it * TPGX_RNG_TABLE);
     std::vector<int32_t> job_teams((size_t)J * K);
     for (int i = 0; i < J * K; i++) job_teams[i] = ctx->flat.root_team[req->job_roots[i]];
     tpgx_status st;

@@ -73,8 +73,10 @@ TPGX_RNG_HD double tpgx_rng_f64(tpgx_rng_cursor& c, double lo, double hi) {
     return canon * (hi - lo) + lo;
 }
 
-/* [UP] Data::Hash<T> = std::hash<T> (identity on libstdc++): the environments seed their RNG with
- * Hash(seed) ^ Hash(mode) ([REF] pendulum/src/Learn/pendulum.cpp:45). */
+/* The environments seed their RNG with Data::Hash(seed) ^ Data::Hash(mode) ([REF] pendulum/src/Learn/pendulum.cpp:45).
+ * A caller that links GEGELATI passes that value itself (tpgx_episode_request.rng_seeds: the C++ adapter does); this is
+ * the default for callers that do not, assuming [UP] Data::Hash<T> = std::hash<T>, the identity on libstdc++ — an
+ * assumption about upstream, "parity unpinned". */
 TPGX_RNG_HD uint64_t tpgx_env_seed(uint64_t seed, int mode) { return seed ^ (uint64_t)mode; }
 
 #endif

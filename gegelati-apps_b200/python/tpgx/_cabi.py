@@ -85,7 +85,7 @@ class EpisodeRequest(C.Structure):
     _fields_ = [("env", C.c_int32), ("mode", C.c_int32), ("nb_iterations", C.c_int32), ("max_actions", C.c_int32),
                 ("seeds", C.c_void_p), ("nb_jobs", C.c_int32), ("roots_per_job", C.c_int32), ("job_roots", C.c_void_p),
                 ("second_player_random", C.c_int32), ("nb_pendulum_actions", C.c_int32), ("pendulum_actions", C.c_void_p),
-                ("trace_steps", C.c_int32), ("reserved", C.c_int32)]
+                ("trace_steps", C.c_int32), ("reserved", C.c_int32), ("rng_seeds", C.c_void_p)]
 
 
 class EpisodeResult(C.Structure):

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TPGX_ABI_VERSION 1
+#define TPGX_ABI_VERSION 2
 
 typedef int32_t tpgx_status;
 enum {
@@ -258,6 +258,10 @@ typedef struct {
     const double* pendulum_actions; /* [nb_pendulum_actions] ([REF] pendulum/src/Learn/main.cpp:33)  */
     int32_t trace_steps;         /* >0: record the first trace_steps actions of every episode        */
     int32_t reserved;
+    const uint64_t* rng_seeds;   /* optional [nb_iterations]: the value the environment's reset() hands to rng.setSeed(),
+                                    i.e. Data::Hash<size_t>()(seed) ^ Data::Hash<LearningMode>()(mode) computed by the CALLER
+                                    with the GEGELATI it links ([REF] pendulum/src/Learn/pendulum.cpp:45-48) — keeps the library
+                                    independent of Data::Hash.  NULL: seeds[it] ^ mode (std::hash on libstdc++ is the identity) */
 } tpgx_episode_request;
 
 typedef struct {                 /* every pointer optional                                            */

@@ -146,14 +146,16 @@ class Oracle:
         return dict(program=prog[:n.value], sample=samp[:n.value], bid=bid[:n.value])
 
     def evaluate_episodes(self, env, seeds, job_roots, max_actions, mode=A.MODE_TRAINING, roots_per_job=1,
-                          second_player_random=0, pendulum_actions=None, trace_steps=0, nb_threads=1):
+                          second_player_random=0, pendulum_actions=None, trace_steps=0, nb_threads=1, rng_seeds=None):
         seeds = np.ascontiguousarray(seeds, dtype=np.uint64)
+        rs = np.ascontiguousarray(rng_seeds, dtype=np.uint64) if rng_seeds is not None else None
         jr = np.ascontiguousarray(job_roots, dtype=np.int32).reshape(-1, roots_per_job)
         J, NI = jr.shape[0], len(seeds)
         pa = np.ascontiguousarray(pendulum_actions, dtype=np.float64) if pendulum_actions is not None else None
         req = A.EpisodeRequest(env=env, mode=mode, nb_iterations=NI, max_actions=max_actions, seeds=seeds.ctypes.data, nb_jobs=J,
                                roots_per_job=roots_per_job, job_roots=jr.ctypes.data, second_player_random=second_player_random,
-                               nb_pendulum_actions=0 if pa is None else len(pa), pendulum_actions=_ptr(pa), trace_steps=trace_steps)
+                               nb_pendulum_actions=0 if pa is None else len(pa), pendulum_actions=_ptr(pa), trace_steps=trace_steps,
+                               rng_seeds=_ptr(rs))
         out = dict(score=np.zeros((J, roots_per_job)), episode_score=np.zeros((J, NI, roots_per_job)),
                    episode_actions=np.zeros((J, NI), dtype=np.int32), final_state=np.zeros((J, NI, 4)))
         cnt = A.Counters()

@@ -318,7 +318,7 @@ inline uint64_t data_hash(uint64_t v) { return v; }
 /* ================================================================== environments (Appendix B) */
 struct Env {
     virtual ~Env() {}
-    virtual void reset(uint64_t seed, int mode) = 0;
+    virtual void reset(uint64_t seed, int mode, bool raw = false) = 0; /* raw: `seed` is the value handed to rng.setSeed() as is */
     virtual bool do_action(double a) = 0; /* false = the reference would throw */
     virtual bool is_terminal() const = 0;
     virtual double score(int player) const = 0;
@@ -340,7 +340,7 @@ struct GridWorldEnv : Env {
         static const int grid[3][4] = {{0, 0, 0, 2}, {0, 0, 3, 3}, {0, 0, 0, 1}}; /* gridworld.h:18-20 */
         return grid[yy][xx];
     }
-    void reset(uint64_t, int) override { x = 0; y = 0; terminated = false; total = 0.0; st[0] = 0; st[1] = 0; } /* gridworld.cpp:3-15 */
+    void reset(uint64_t, int, bool = false) override { x = 0; y = 0; terminated = false; total = 0.0; st[0] = 0; st[1] = 0; } /* gridworld.cpp:3-15 */
     static bool available(int px, int py) { /* gridworld.cpp:17-37 */
         if (px == 4 || px == -1) return false;
         if (py == 3 || py == -1) return false;
@@ -382,8 +382,8 @@ struct StickGameEnv : Env {
     bool second_random;
     Rng rng;
     explicit StickGameEnv(bool sr) : second_random(sr) { reset(0, 0); }
-    void reset(uint64_t seed, int mode) override { /* .cpp:105-116 */
-        rng.set_seed(data_hash(seed) ^ data_hash((uint64_t)mode));
+    void reset(uint64_t seed, int mode, bool raw = false) override { /* .cpp:105-116 */
+        rng.set_seed(raw ? seed : (data_hash(seed) ^ data_hash((uint64_t)mode)));
         sticks[0] = 21; first_won = false; forb1 = false; forb2 = false; turn = 0;
     }
     void random_play() { /* .cpp:38-57 */
@@ -397,6 +397,7 @@ struct StickGameEnv : Env {
         }
     }
     bool do_action(double a) override { /* .cpp:59-103 */
+        if (a < 0 || a >= 3.0) return false; /* :61 LearningEnvironment::doAction(actionID) throws past nbActions */
         if (!is_terminal()) {
             bool first = turn % 2 == 0;
             bool& forbidden = first ? forb1 : forb2;
@@ -435,8 +436,8 @@ struct TicTacToeEnv : Env {
     bool second_random;
     Rng rng;
     explicit TicTacToeEnv(bool sr) : second_random(sr) { reset(0, 0); }
-    void reset(uint64_t seed, int mode) override { /* TicTacToe.cpp:101-116 */
-        rng.set_seed(data_hash(seed) ^ data_hash((uint64_t)mode));
+    void reset(uint64_t seed, int mode, bool raw = false) override { /* TicTacToe.cpp:101-116 */
+        rng.set_seed(raw ? seed : (data_hash(seed) ^ data_hash((uint64_t)mode)));
         for (int i = 0; i < 9; i++) board[i] = -1.0;
         turn = 0; win1 = win2 = forb1 = forb2 = null_game = end = false;
     }
@@ -461,6 +462,7 @@ struct TicTacToeEnv : Env {
         if (turn > 8) { null_game = true; end = true; }
     }
     bool do_action(double a) override { /* :33-74 */
+        if (a < 0 || a >= 9.0) return false; /* :41,46 the board handler's getDataAt / setDataAt throw outside its 9 cells */
         bool& forbidden = (turn % 2 == 0 ? forb1 : forb2);
         if (!is_terminal()) {
             double cell = board[(int)a];
@@ -513,8 +515,8 @@ struct PendulumEnv : Env {
     double st[2] = {0, 0};
     Math m;
     PendulumEnv(const double* a, int n, Math mm) : avail(a, a + n), m(mm) { for (auto& h : hist) h = 0.0; }
-    void reset(uint64_t seed, int mode) override { /* pendulum.cpp:42-55 */
-        rng.set_seed(data_hash(seed) ^ data_hash((uint64_t)mode));
+    void reset(uint64_t seed, int mode, bool raw = false) override { /* pendulum.cpp:42-55 */
+        rng.set_seed(raw ? seed : (data_hash(seed) ^ data_hash((uint64_t)mode)));
         st[0] = rng.f64(-M_PI, M_PI);
         st[1] = rng.f64(-1.0, 1.0);
         n_act = 0; total = 0.0;
@@ -776,7 +778,7 @@ int32_t orc_evaluate_episodes(const orc_engine* e, const tpgx_episode_request* r
         std::vector<int> visited;
         std::vector<double> result(K, 0.0);
         for (int it = 0; it < NI; it++) {
-            env->reset(req->seeds[it], req->mode);
+            if (req->rng_seeds) env->reset(req->rng_seeds[it], req->mode, true); else env->reset(req->seeds[it], req->mode);
             int n = 0, turn = 0;
             while (!env->is_terminal() && n < req->max_actions) {
                 for (int s = 0; s < env->nb_sources(); s++) v[s] = env->view(s);
@@ -826,7 +828,7 @@ int32_t orc_archive_episodes(const orc_engine* e, const tpgx_episode_request* re
         if (!env || env->nb_sources() != (int)e->src.size()) return TPGX_ERR_BAD_ARG;
         std::vector<SourceView> v(env->nb_sources());
         for (int it = 0; it < NI; it++) {
-            env->reset(req->seeds[it], req->mode);
+            if (req->rng_seeds) env->reset(req->rng_seeds[it], req->mode, true); else env->reset(req->seeds[it], req->mode);
             int n = 0, turn = 0;
             while (!env->is_terminal() && n < req->max_actions) {
                 int q = 0;

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     lib = tpgx.load_library()
     for name in declared_functions():
         assert hasattr(lib, name), name
-    assert lib.tpgx_abi_version() == 1
+    assert lib.tpgx_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -55,7 +55,7 @@ def test_ragged_and_empty_programs(oracle_mod):
     """Programs of different lengths, including empty ones (bid 0.0, Appendix F U5), and a sample count that is
     not a multiple of the tile."""
     g, ev = make(roots=16, edges=4, lines=6, depth=2, seed=3, line_jitter=6, intron_lines=2)
-    assert (np.diff(g.program_line_offset) == 2).any() or True
+    assert (np.diff(g.program_line_offset) == 0).any(), "the generator must have produced at least one empty program"
     img, lab = tpgx.synthetic_images(77, seed=9)
     ev.set_observations(img, lab)
     want = ("score", "confusion", "action", "bid", "counters")
@@ -205,7 +205,10 @@ def test_full_size_properties():
     assert conf.shape == (R, 10, 10) and (conf.sum(axis=(1, 2)) == S).all()
     assert (conf.sum(axis=2) == np.bincount(lab, minlength=10)[None, :]).all()
     assert ((out["score"] >= 0) & (out["score"] <= 1)).all() and np.isfinite(out["class_f1"]).all()
-    assert np.array_equal(bits(out["score"]), bits(out["class_f1"].sum(axis=1) / 10.0)) or np.allclose(out["score"], out["class_f1"].mean(axis=1), rtol=0, atol=1e-15)
+    seq = np.zeros(R)                                   # [UP] ClassificationLearningAgent: sequential sum over the classes, then / nbClasses
+    for c_ in range(10):
+        seq = seq + out["class_f1"][:, c_]
+    assert np.array_equal(bits(out["score"]), bits(seq / 10.0))
     c = out["counters"]
     assert (c["evaluations"], c["team_visits"], c["program_executions"], c["lines_executed"]) == (R * S, R * S, R * E * S, R * E * L * S)
     again = ev.evaluate_classification(want=("score", "confusion"))
@@ -325,3 +328,136 @@ def test_pinned_uploads_interleave_with_graph_uploads_and_other_observations(ora
     ref = oracle_for(oracle_mod, g1).archive_classification(sets[1][0], seeds, 0.05, 64)
     assert np.array_equal(dev["program"], ref["program"]) and np.array_equal(dev["sample"], ref["sample"])
     assert np.array_equal(dev["bid"].view(np.uint64), ref["bid"].view(np.uint64))
+
+
+# ---- oracle-checked slices of the benchmarked configurations (BASELINE C2: 2000 roots, C4: 8192 roots, 60 000 samples) ----
+import os
+
+_THREADS = max(1, os.cpu_count() or 1)
+
+
+def _headline(roots):
+    g, ev = make(roots=roots, edges=5, lines=20, depth=1, seed=42)
+    img, lab = tpgx.synthetic_images(60000)
+    ev.set_observations(img, lab)
+    return g, ev, img, lab
+
+
+def test_c2_root_slice_all_samples_vs_oracle(oracle_mod):
+    """C2 as bench.py runs it (G(2000, 5, 20, 1, uniform, 42), 60 000 samples): 64 roots of the shard through
+    root_begin / root_end on ALL samples — actions, confusion tables, score bits and counters against the oracle."""
+    g, ev, img, lab = _headline(2000)
+    want = ("score", "class_f1", "confusion", "action", "counters")
+    for rb in (0, 1936):
+        dev = ev.evaluate_classification(root_begin=rb, root_end=rb + 64, want=want)
+        ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, root_begin=rb, root_end=rb + 64, want=want, nb_threads=_THREADS)
+        compare(dev, ref)
+
+
+@pytest.mark.parametrize("roots", [2000, 8192])
+def test_headline_all_roots_sample_slice_vs_oracle(oracle_mod, roots):
+    """C2 / C4: ALL roots of the graph on 2048 of the 60 000 samples (an index list spread over the whole set)."""
+    g, ev, img, lab = _headline(roots)
+    idx = (np.arange(2048, dtype=np.int64) * 29 + 7).astype(np.int32) % 60000
+    want = ("score", "class_f1", "confusion", "action", "counters")
+    dev = ev.evaluate_classification(sample_index=idx, want=want)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, sample_index=idx, want=want, nb_threads=_THREADS)
+    compare(dev, ref)
+    # and the full evaluation that follows (what bench.py times) is consistent with it on those samples' share:
+    full = ev.evaluate_classification(want=("score", "confusion"))
+    assert (full["confusion"].sum(axis=(1, 2)) == 60000).all()
+
+
+def test_k1_v2_equals_k1_v1_and_oracle(oracle_mod, monkeypatch):
+    """The threaded interpreter (K1 v2, the default for MNIST-set shards) and K1 v1 give the same bids, in bid and in team
+    mode, on programs with introns, shared programs, ragged lengths and several sample tiles."""
+    g = tpgx.synthetic_graph("mnist", roots=80, edges=5, lines=20, depth=2, share_prob=0.1, seed=7, intron_lines=4, line_jitter=6)
+    img, lab = tpgx.synthetic_images(700, seed=7)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=("score", "confusion", "action", "bid", "counters"))
+    for v2 in ("1", "0"):
+        monkeypatch.setenv("TPGX_K1_V2", v2)
+        ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+        ev.set_graph(g)
+        ev.set_observations(img, lab)
+        compare(ev.evaluate_classification(want=("score", "confusion", "action", "bid", "counters")), ref)
+        compare(ev.evaluate_classification(want=("score", "confusion", "action", "counters")), ref)
+
+
+def _wide_program(nb_live):
+    """r1..r<nb_live> each hold a pixel sum that stays live until a final chain of additions into r0."""
+    ln = np.zeros(2 * nb_live, dtype=tpgx.LINE_DTYPE)
+    ADD, IMG = 1, 2          # mnist set index of add; source 2 = the image (0 registers, 1 constants)
+    for k in range(nb_live):
+        ln[k] = (ADD, (k + 1) % 8, (IMG, IMG), (10 * k + 3, 10 * k + 40))
+    ln[nb_live] = (ADD, 0, (0, 0), (1 % 8, 2 % 8))
+    for k in range(2, nb_live):
+        ln[nb_live + k - 1] = (ADD, 0, (0, 0), (0, (k + 1) % 8))
+    return ln[:2 * nb_live - 1]
+
+
+@pytest.mark.parametrize("nb_live", [3, 5, 6, 7])
+def test_programs_needing_more_slots_than_k1_v2_has_run_on_v1(oracle_mod, nb_live):
+    """K1 v2 keeps at most 5 values of a program in shared memory besides the accumulator; a program that holds more run
+    on K1 v1 — same bits either way."""
+    ln = _wide_program(nb_live)
+    enc = tpgx.k1v2_encode_program(tpgx.flatten_programs(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], tpgx.TPGraph(
+        lines=ln, program_line_offset=np.array([0, len(ln)], dtype=np.int64), constants=np.zeros((1, 5)), team_edge_offset=np.array([0, 1], dtype=np.int32),
+        edge_program=np.zeros(1, dtype=np.int32), edge_destination=np.full(1, -1, dtype=np.int32), root_team=np.zeros(1, dtype=np.int32)), nb_constants=5)["code"])
+    assert enc["slots"] == nb_live
+    base = tpgx.synthetic_graph("mnist", roots=6, edges=3, lines=8, depth=1, seed=3)
+    lines = np.concatenate([base.lines, ln])
+    plo = np.concatenate([base.program_line_offset, [len(lines)]]).astype(np.int64)
+    consts = np.concatenate([base.constants, np.zeros((1, 5))])
+    ep = base.edge_program.copy()
+    ep[4] = base.nb_programs                     # one edge of root 1 runs the wide program
+    g = tpgx.TPGraph(lines=lines, program_line_offset=plo, constants=consts, team_edge_offset=base.team_edge_offset, edge_program=ep,
+                     edge_destination=base.edge_destination, root_team=base.root_team)
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+    ev.set_graph(g)
+    img, lab = tpgx.synthetic_images(300, seed=5)
+    ev.set_observations(img, lab)
+    for want in (("score", "confusion", "action", "bid", "counters"), ("score", "confusion", "action", "counters")):
+        compare(ev.evaluate_classification(want=want), oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want))
+
+
+def test_mnist_app_shape_against_the_glibc_flavour_oracle(oracle_mod, capsys):
+    """The mnist app's evaluation shape ([REF] mnist/params.json: 500 roots, 500 images drawn per generation, [REF]
+    mnist/src/mnist.cpp:16-19) against the oracle computing exp / ln / atan with GLIBC (what the real app's CPU agent runs):
+    the single-source libm of the GPU differs from glibc in the last ulps of some bids, so bids are compared as a histogram of
+    ulp distances, while the chosen actions, confusion tables and root scores — everything selection depends on — must be
+    EQUAL.  (Against the `shared` flavour every bid is bit-exact: the tests above.)"""
+    g, ev = make(roots=500, edges=5, lines=20, depth=3, share_prob=0.1, seed=2024)
+    img, lab = tpgx.synthetic_images(10000, seed=77)
+    ev.set_observations(img, lab)
+    idx = tpgx.mnist_episode_indices(seed=5 ^ 0, mode=A.MODE_TRAINING, dataset_size=10000, nb_actions=500)
+    want = ("score", "class_f1", "confusion", "action", "bid", "counters")
+    dev = ev.evaluate_classification(sample_index=idx, want=want)
+    std = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], g, nb_constants=5,
+                            math=oracle_mod.MATH_STD).evaluate_classification(img, lab, sample_index=idx, want=want, nb_threads=_THREADS)
+    assert np.array_equal(dev["action"], std["action"])
+    assert np.array_equal(dev["confusion"], std["confusion"])
+    assert np.array_equal(bits(dev["score"]), bits(std["score"])) and np.array_equal(bits(dev["class_f1"]), bits(std["class_f1"]))
+    a, b = dev["bid"], std["bid"]
+    done = ~np.isnan(a)                                       # rows of programs no root reaches stay NaN on the device
+    assert np.array_equal(np.isinf(a[done]), np.isinf(b[done])) and not np.isnan(b[done]).any()
+    fin = done & np.isfinite(a) & np.isfinite(b)
+    ulp = np.abs(a.view(np.int64)[fin] - b.view(np.int64)[fin])
+    hist = np.bincount(np.minimum(ulp, 5).astype(np.int64), minlength=6)
+    with capsys.disabled():
+        print("\n[glibc-flavour parity] finite bids %d: ulp distance 0/1/2/3/4/>=5 = %s (%.2f %% differ); actions, confusion, scores equal"
+              % (fin.sum(), hist.tolist(), 100.0 * (ulp > 0).mean()))
+    assert (ulp > 0).mean() < 0.05
+
+
+def test_labels_outside_the_class_range_are_reported():
+    """[UP] ClassificationLearningEnvironment::doAction indexes classificationTable.at(currentClass): a label past nbClasses
+    throws in the reference; here it is BAD_ARG, not a silent write past the shared confusion table."""
+    g, ev = make(roots=4, edges=3, lines=6, depth=1, seed=1)
+    img, lab = tpgx.synthetic_images(64, seed=1)
+    lab = lab.copy()
+    lab[17] = 200
+    ev.set_observations(img, lab)
+    for want in (("score",), ("score", "bid")):
+        with pytest.raises(tpgx.TpgxError) as e:
+            ev.evaluate_classification(want=want)
+        assert e.value.status == A.ERR_BAD_ARG and "label" in str(e.value)

@@ -138,3 +138,36 @@ def test_wide_teams_take_several_rounds(oracle_mod):
     jobs = np.random.default_rng(3).integers(0, 12, (20, 2))
     kw = dict(seeds=np.arange(4, dtype=np.uint64) + 11, job_roots=jobs, roots_per_job=2, max_actions=9, second_player_random=0, trace_steps=9)
     check(ev.evaluate_episodes(A.ENV_TICTACTOE, **kw), o.evaluate_episodes(A.ENV_TICTACTOE, **kw))
+
+
+def test_caller_supplied_rng_seeds_keep_the_library_independent_of_data_hash(oracle_mod):
+    """tpgx_episode_request.rng_seeds: the value the environment's reset() hands to rng.setSeed(), computed by the caller
+    with the Data::Hash of the GEGELATI it links.  With the identity hash (libstdc++) it must reproduce the default path;
+    with any other value the draws follow that value, on the device and in the oracle alike."""
+    g = tpgx.synthetic_graph("pendulum", roots=12, edges=4, lines=10, depth=2, seed=8)
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["pendulum"], tpgx.APP_SOURCES["pendulum"], nb_constants=5)
+    ev.set_graph(g)
+    o = oracle_mod.Oracle(tpgx.INSTRUCTION_SETS["pendulum"], tpgx.APP_SOURCES["pendulum"], g, nb_constants=5)
+    pa = [0.05, 0.1, 0.2, 0.4, 0.6, 0.8, 1.0]
+    kw = dict(seeds=[11, 12, 13], job_roots=np.arange(12), max_actions=120, pendulum_actions=pa, mode=A.MODE_VALIDATION)
+    base = ev.evaluate_episodes(A.ENV_PENDULUM, **kw)
+    same = ev.evaluate_episodes(A.ENV_PENDULUM, rng_seeds=[11 ^ 1, 12 ^ 1, 13 ^ 1], **kw)
+    assert np.array_equal(base["score"].view(np.uint64), same["score"].view(np.uint64))
+    other = ev.evaluate_episodes(A.ENV_PENDULUM, rng_seeds=[0x9E3779B97F4A7C15, 5, 77], **kw)
+    ref = o.evaluate_episodes(A.ENV_PENDULUM, rng_seeds=[0x9E3779B97F4A7C15, 5, 77], **kw)
+    assert not np.array_equal(other["score"], base["score"])
+    assert np.array_equal(other["score"].view(np.uint64), ref["score"].view(np.uint64))
+    assert np.array_equal(other["episode_actions"], ref["episode_actions"])
+
+
+def test_action_ids_outside_the_environment_are_reported(oracle_mod):
+    """[REF] TicTacToe.cpp:41,46 (board handler access) and stickGameAdversarial.cpp:61 (LearningEnvironment::doAction) throw
+    for an action id past the environment's actions; the device reports GRAPH_INVALID instead of touching memory."""
+    for app, env in (("tictactoe", A.ENV_TICTACTOE), ("stickgame", A.ENV_STICKGAME)):
+        g = tpgx.synthetic_graph(app, roots=4, edges=3, lines=6, depth=1, seed=2)
+        g.edge_destination[:] = -1 - 20          # every edge leads to action 20
+        ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], nb_constants=0)
+        ev.set_graph(g)
+        with pytest.raises(tpgx.TpgxError) as e:
+            ev.evaluate_episodes(env, seeds=[1], job_roots=np.arange(4), max_actions=5, second_player_random=1)
+        assert e.value.status == A.ERR_GRAPH_INVALID
