@@ -1094,9 +1094,9 @@ struct EpBackend {
     tpgx_ctx* ctx;
     tpgx_episode_request req;
 };
-tpgx_status epbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, const uint64_t* archive_seed, double probability,
-                          int32_t archive_size, double* scores, int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len,
-                          int32_t* nb_records) {
+tpgx_status epbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, int32_t mode, const uint64_t* archive_seed, double probability,
+                          int32_t archive_size, double* scores, int32_t /*nb_classes*/, double* /*class_scores*/, uint64_t* /*class_counts*/,
+                          int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len, int32_t* nb_records) {
     EpBackend* b = static_cast<EpBackend*>(user);
     tpgx_status st = tpgx_set_graph(b->ctx, g);
     if (st != TPGX_OK) return st;
@@ -1106,12 +1106,16 @@ tpgx_status epbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, 
     std::vector<uint64_t> seeds((size_t)NI);
     for (int it = 0; it < NI; it++) seeds[it] = 1000ull * generation + (uint64_t)it; /* stands for Hash(gen) ^ Hash(it) */
     tpgx_episode_request req = b->req;
+    req.mode = mode;
     req.nb_jobs = R; req.roots_per_job = 1; req.job_roots = job_roots.data(); req.seeds = seeds.data(); req.trace_steps = 0;
+    tpgx_episode_result ev{};
+    ev.score = scores;
+    *nb_records = 0;
+    if (archive_size <= 0 || probability == 0.0 || mode != 0 /* [UP] only a TRAINING evaluation archives */)
+        return tpgx_evaluate_episodes(b->ctx, &req, &ev);
     const size_t cap = (size_t)std::max(1, archive_size);
     std::vector<int32_t> job(cap), iteration(cap), step(cap);
     tpgx_archive_request ar{archive_seed, probability, archive_size, 0};
-    tpgx_episode_result ev{};
-    ev.score = scores;
     tpgx_episode_archive_result out{rec_program, job.data(), iteration.data(), step.data(), rec_bid, rec_obs, obs_len, 0};
     st = tpgx_archive_episodes(b->ctx, &req, &ar, &ev, &out);
     *nb_records = out.nb_records;
@@ -1154,22 +1158,35 @@ struct ClBackend {
     int32_t nb_classes;
     int64_t actions;
 };
-tpgx_status clbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, const uint64_t* archive_seed, double probability,
-                          int32_t archive_size, double* scores, int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len,
-                          int32_t* nb_records) {
+tpgx_status clbe_evaluate(void* user, const tpgx_graph* g, uint64_t generation, int32_t mode, const uint64_t* archive_seed, double probability,
+                          int32_t archive_size, double* scores, int32_t nb_classes, double* class_scores, uint64_t* class_counts,
+                          int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len, int32_t* nb_records) {
     ClBackend* b = static_cast<ClBackend*>(user);
     tpgx_status st = tpgx_set_graph(b->ctx, g);
     if (st != TPGX_OK) return st;
-    /* [REF] mnist/src/mnist.cpp:58-69 + :8-34: the evaluation classifies the images drawn from the episode seed */
+    if (nb_classes != 0 && nb_classes != b->nb_classes) return fail(b->ctx, TPGX_ERR_BAD_ARG, "trainer and backend disagree on the number of classes");
+    /* [REF] mnist/src/mnist.cpp:58-69 + :8-34: the evaluation classifies the images drawn from the episode seed; TRAINING and
+       VALIDATION both draw from the training set, the mode does not enter the draw (rng.setSeed(seed): mnist.cpp:64) */
     std::vector<int32_t> idx((size_t)b->actions);
-    if ((st = tpgx_mnist_episode_indices(1000ull * generation, 0 /* TRAINING */, b->nb_images, b->actions, idx.data())) != TPGX_OK) return st;
+    if ((st = tpgx_mnist_episode_indices(1000ull * generation, mode, b->nb_images, b->actions, idx.data())) != TPGX_OK) return st;
+    const int R = g->nb_roots, C = b->nb_classes;
     tpgx_classif_request req{};
-    req.nb_samples = b->actions; req.sample_index = idx.data(); req.nb_classes = b->nb_classes; req.root_begin = 0; req.root_end = g->nb_roots;
+    req.nb_samples = b->actions; req.sample_index = idx.data(); req.nb_classes = C; req.root_begin = 0; req.root_end = R;
     tpgx_classif_result ev{};
     ev.score = scores;
+    std::vector<uint64_t> conf;
+    if (class_scores) ev.class_f1 = class_scores;
+    if (class_counts) { conf.resize((size_t)R * C * C); ev.confusion = conf.data(); }
     if ((st = tpgx_evaluate_classification(b->ctx, &req, &ev)) != TPGX_OK) return st;
+    if (class_counts) /* [UP] nbEvaluationPerClass: the samples of each class the root has classified */
+        for (int r = 0; r < R; r++)
+            for (int c = 0; c < C; c++) {
+                uint64_t n = 0;
+                for (int a = 0; a < C; a++) n += conf[((size_t)r * C + c) * C + a];
+                class_counts[(size_t)r * C + c] = n;
+            }
     *nb_records = 0;
-    if (archive_size <= 0 || probability == 0.0) return TPGX_OK;
+    if (archive_size <= 0 || probability == 0.0 || mode != 0) return TPGX_OK;
     const int px = b->ctx->obs_hw;
     if (obs_len < px) return fail(b->ctx, TPGX_ERR_BAD_ARG, "observation rows shorter than an image");
     std::vector<int64_t> sample((size_t)archive_size);

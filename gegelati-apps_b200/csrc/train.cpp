@@ -33,6 +33,36 @@ struct TTeam {
     bool alive = false;
 };
 struct ARec { int prog; double bid; std::vector<double> obs; };
+/* [UP] Learn::EvaluationResult / ClassificationEvaluationResult of one root, as LearningAgent::resultsPerRoot keeps it */
+struct REval {
+    double score = 0.0;
+    uint64_t n = 0;                      /* nbEvaluation */
+    std::vector<double> class_score;     /* classification: score per class */
+    std::vector<uint64_t> class_n;       /* classification: nbEvaluationPerClass */
+    /* [UP] EvaluationResult::operator+= — `*this` is the NEW evaluation, `o` the stored one: evaluation-count-weighted mean,
+       in upstream's operation order.  Classification: per class, then the general score is the mean over the classes and
+       nbEvaluation the sum (unverifiable upstream detail; the oracle-side test util restates the
+       same function, so GPU-vs-oracle evolution parity does not depend on it). */
+    void combine(const REval& o) {
+        if (!class_score.empty() && class_score.size() == o.class_score.size()) {
+            double sum = 0.0;
+            uint64_t total = 0;
+            for (size_t c = 0; c < class_score.size(); c++) {
+                class_score[c] = class_score[c] * (double)class_n[c] + o.class_score[c] * (double)o.class_n[c];
+                class_n[c] += o.class_n[c];
+                if (class_n[c] != 0) class_score[c] /= (double)class_n[c];
+                sum += class_score[c];
+                total += class_n[c];
+            }
+            score = sum / (double)class_score.size();
+            n = total;
+            return;
+        }
+        score = score * (double)n + o.score * (double)o.n;
+        score /= (double)n + (double)o.n;
+        n += o.n;
+    }
+};
 /* a program created by this populate: still to be mutated / behaviour-checked against its origin */
 struct NewProg {
     int id;
@@ -55,6 +85,9 @@ struct tpgx_trainer {
     std::vector<int> free_teams;
     std::vector<int> order;          /* alive teams in creation order: the graph's vertex / root iteration order */
     std::deque<ARec> archive;
+    std::map<int, REval> results_per_root; /* [UP] LearningAgent::resultsPerRoot, keyed by team id */
+    int best_team = -1;                    /* [UP] bestRoot */
+    double best_team_score = 0.0;
     int obs_len = 0;
     uint32_t max_loc = 1;
     int nb_src_total = 0;
@@ -137,6 +170,7 @@ struct tpgx_trainer {
     void remove_team(int team) {
         while (!teams[team].edges.empty()) remove_edge(team, teams[team].edges.size() - 1);
         teams[team].alive = false;
+        results_per_root.erase(team); /* [UP] decimateWorstRoots: keep only results of non-decimated roots */
         order.erase(std::find(order.begin(), order.end(), team));
         free_teams.push_back(team);
     }
@@ -303,7 +337,8 @@ struct tpgx_trainer {
     }
 
     /* ---- view in the C ABI's layout ---- */
-    void build_view(tpgx_graph* g) {
+    /* skip (optional, by team id): root teams left out of the view's root list — the jobs [UP] evaluateJob would skip */
+    void build_view(tpgx_graph* g, const std::vector<char>* skip = nullptr) {
         std::vector<int> pidx(progs.size(), -1);
         v_prog_id.clear();
         for (size_t p = 0; p < progs.size(); p++)
@@ -325,7 +360,7 @@ struct tpgx_trainer {
         for (int t : order) {
             for (const TEdge& e : teams[t].edges) { v_ep.push_back(pidx[e.prog]); v_ed.push_back(e.dest >= 0 ? tidx[e.dest] : e.dest); }
             v_teo.push_back((int32_t)v_ep.size());
-            if (teams[t].incoming == 0) { v_roots.push_back(tidx[t]); v_root_team.push_back(t); }
+            if (teams[t].incoming == 0 && !(skip && (*skip)[(size_t)t])) { v_roots.push_back(tidx[t]); v_root_team.push_back(t); }
         }
         g->nb_programs = nP;
         g->program_line_offset = v_off.data();
@@ -581,16 +616,35 @@ tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_back
     tpgx_status st = tpgx_trainer_populate(t, be, &s);
     if (st != TPGX_OK) return st;
     const auto t1 = now();
+    /* [UP] evaluateAllRoots(generation, TRAINING): makeJobs draws one archive seed per root, in root order; evaluateJob then
+       returns the stored result of a root that already has maxNbEvaluationPerPolicy evaluations without running it */
+    const std::vector<int> all_roots = t->roots();
+    const int R = (int)all_roots.size(), cap = t->P.archive_size, C = std::max(0, t->P.nb_classes);
+    std::vector<uint64_t> aseed_all((size_t)R);
+    for (int j = 0; j < R; j++) aseed_all[j] = t->u64(0, UINT64_MAX); /* [UP] Job::archiveSeed drawn from the agent's RNG */
+    std::vector<char> skip(t->teams.size(), 0);
+    std::vector<uint64_t> aseed;
+    std::vector<int> job_root; /* index in all_roots of every job */
+    for (int j = 0; j < R; j++) {
+        const auto it = t->results_per_root.find(all_roots[j]);
+        const bool skipped = it != t->results_per_root.end() && t->P.max_nb_evaluation_per_policy > 0 &&
+                             it->second.n >= (uint64_t)t->P.max_nb_evaluation_per_policy;
+        if (skipped) skip[(size_t)all_roots[j]] = 1;
+        else { aseed.push_back(aseed_all[j]); job_root.push_back(j); }
+    }
+    const int J = (int)job_root.size();
     tpgx_graph g{};
-    t->build_view(&g);
-    const int R = g.nb_roots, cap = t->P.archive_size;
-    std::vector<uint64_t> aseed((size_t)R);
-    for (int j = 0; j < R; j++) aseed[j] = t->u64(0, UINT64_MAX); /* [UP] Job::archiveSeed drawn from the agent's RNG */
-    std::vector<double> scores((size_t)R, 0.0), rbid((size_t)std::max(1, cap)), robs((size_t)std::max(1, cap) * (size_t)std::max(1, t->obs_len));
+    t->build_view(&g, &skip);
+    std::vector<double> scores((size_t)std::max(1, J), 0.0), rbid((size_t)std::max(1, cap)), robs((size_t)std::max(1, cap) * (size_t)std::max(1, t->obs_len));
+    std::vector<double> cscore((size_t)std::max(1, J * C));
+    std::vector<uint64_t> ccount((size_t)std::max(1, J * C));
     std::vector<int32_t> rprog((size_t)std::max(1, cap));
     int32_t nrec = 0;
-    st = be->evaluate(be->user, &g, generation, aseed.data(), t->P.archiving_probability, cap, scores.data(), rprog.data(), rbid.data(), robs.data(), t->obs_len, &nrec);
-    if (st != TPGX_OK) { t->err = "backend evaluate failed"; return st; }
+    if (J > 0) {
+        st = be->evaluate(be->user, &g, generation, 0 /* TRAINING */, aseed.data(), t->P.archiving_probability, cap, scores.data(), C,
+                          C ? cscore.data() : nullptr, C ? ccount.data() : nullptr, rprog.data(), rbid.data(), robs.data(), t->obs_len, &nrec);
+        if (st != TPGX_OK) { t->err = "backend evaluate failed"; return st; }
+    }
     const auto t2 = now();
     if (nrec < 0 || nrec > std::max(0, cap)) { t->err = "backend returned more archive records than archive_size"; return TPGX_ERR_STATE; }
     for (int i = 0; i < nrec; i++) {
@@ -602,17 +656,103 @@ tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_back
         t->archive.push_back(std::move(r));
     }
     while ((int)t->archive.size() > cap) t->archive.pop_front();
+    /* [UP] evaluateJob: the new result, combined with the stored one if any; [UP] updateEvaluationRecords stores it */
+    for (int k = 0; k < J; k++) {
+        const int team = all_roots[job_root[k]];
+        REval e;
+        e.score = scores[k];
+        e.n = (uint64_t)std::max(1, t->P.nb_iterations_per_policy_evaluation);
+        if (C) {
+            e.class_score.assign(cscore.begin() + (long)k * C, cscore.begin() + (long)(k + 1) * C);
+            e.class_n.assign(ccount.begin() + (long)k * C, ccount.begin() + (long)(k + 1) * C);
+            e.n = 0;
+            for (uint64_t v : e.class_n) e.n += v;
+        }
+        const auto it = t->results_per_root.find(team);
+        if (it != t->results_per_root.end()) e.combine(it->second);
+        t->results_per_root[team] = std::move(e);
+    }
+    std::vector<double> all_scores((size_t)R);
+    for (int j = 0; j < R; j++) all_scores[j] = t->results_per_root[all_roots[j]].score;
+    /* [UP] updateEvaluationRecords / bestRoot: the best result of this generation (the last of equal scores in the
+       reference's multimap order, i.e. the latest root) replaces the stored best when it is at least as good or the stored
+       best has left the graph */
+    {
+        int bj = 0;
+        for (int j = 1; j < R; j++) if (all_scores[j] >= all_scores[bj]) bj = j;
+        const bool have = t->best_team >= 0 && t->best_team < (int)t->teams.size() && t->teams[(size_t)t->best_team].alive;
+        if (!have || all_scores[bj] >= t->best_team_score) { t->best_team = all_roots[bj]; t->best_team_score = all_scores[bj]; }
+    }
     tpgx_train_stats d{};
-    st = tpgx_trainer_decimate(t, scores.data(), &d);
+    st = tpgx_trainer_decimate(t, all_scores.data(), &d);
     if (st != TPGX_OK) return st;
-    if (trace) fprintf(stderr, "[tpgx] generation %llu: populate %.3f ms (%d new programs, %d behaviour retries), evaluate + archive %.3f ms, archive merge + decimate %.3f ms\n",
-                       (unsigned long long)generation, ms(t0, t1), s.nb_new_programs, s.behaviour_retries, ms(t1, t2), ms(t2, now()));
+    const auto t3 = now();
+    /* [UP] trainOneGeneration: if (params.doValidation) evaluateAllRoots(generation, VALIDATION) on what is left; the results
+       go to the loggers, they are neither stored nor combined (previousEval is only looked up in TRAINING mode) */
+    double vbest = NAN, vmean = NAN;
+    if (t->P.do_validation) {
+        tpgx_graph gv{};
+        t->build_view(&gv);
+        const int RV = gv.nb_roots;
+        std::vector<double> vs((size_t)std::max(1, RV)), vcs((size_t)std::max(1, RV * C));
+        std::vector<uint64_t> vcc((size_t)std::max(1, RV * C));
+        int32_t vrec = 0;
+        st = be->evaluate(be->user, &gv, generation, 1 /* VALIDATION */, nullptr, 0.0, 0, vs.data(), C, C ? vcs.data() : nullptr, C ? vcc.data() : nullptr,
+                          rprog.data(), rbid.data(), robs.data(), t->obs_len, &vrec);
+        if (st != TPGX_OK) { t->err = "backend evaluate (validation) failed"; return st; }
+        vbest = -INFINITY; vmean = 0.0;
+        for (int j = 0; j < RV; j++) { vbest = std::max(vbest, vs[j]); vmean += vs[j]; }
+        vmean /= (double)std::max(1, RV);
+    }
+    if (trace) fprintf(stderr, "[tpgx] generation %llu: populate %.3f ms (%d new programs, %d behaviour retries), evaluate + archive %.3f ms (%d jobs, %d skipped), "
+                       "archive merge + decimate %.3f ms, validation %.3f ms\n",
+                       (unsigned long long)generation, ms(t0, t1), s.nb_new_programs, s.behaviour_retries, ms(t1, t2), J, R - J, ms(t2, t3), ms(t3, now()));
     if (stats) {
         *stats = d;
         stats->nb_new_programs = s.nb_new_programs;
         stats->behaviour_retries = s.behaviour_retries;
         stats->nb_roots = R; stats->nb_teams = s.nb_teams; stats->nb_programs = s.nb_programs; /* sizes as evaluated */
+        stats->nb_evaluated_roots = J; stats->nb_skipped_roots = R - J;
+        stats->best_validation_score = vbest; stats->mean_validation_score = vmean;
     }
+    return TPGX_OK;
+}
+
+int32_t tpgx_trainer_root_results(tpgx_trainer* t, double* score, uint64_t* nb_evaluation, int32_t capacity) {
+    if (!t) return 0;
+    const std::vector<int> roots = t->roots();
+    for (int j = 0; j < (int)roots.size() && j < capacity; j++) {
+        const auto it = t->results_per_root.find(roots[j]);
+        if (score) score[j] = it == t->results_per_root.end() ? NAN : it->second.score;
+        if (nb_evaluation) nb_evaluation[j] = it == t->results_per_root.end() ? 0 : it->second.n;
+    }
+    return (int32_t)roots.size();
+}
+
+tpgx_status tpgx_trainer_best_root(tpgx_trainer* t, int32_t* root_index, double* score) {
+    if (!t) return TPGX_ERR_BAD_ARG;
+    if (t->best_team < 0 || t->best_team >= (int)t->teams.size() || !t->teams[(size_t)t->best_team].alive) { t->err = "no best root recorded"; return TPGX_ERR_STATE; }
+    const std::vector<int> roots = t->roots();
+    const auto it = std::find(roots.begin(), roots.end(), t->best_team);
+    if (it == roots.end()) { t->err = "the best root is no longer a root"; return TPGX_ERR_STATE; }
+    if (root_index) *root_index = (int32_t)(it - roots.begin());
+    if (score) *score = t->best_team_score;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_trainer_keep_best_policy(tpgx_trainer* t) {
+    if (!t) return TPGX_ERR_BAD_ARG;
+    if (t->best_team < 0 || t->best_team >= (int)t->teams.size() || !t->teams[(size_t)t->best_team].alive) { t->err = "no best root recorded"; return TPGX_ERR_STATE; }
+    /* [UP] keepBestPolicy: remove every root that is not the best one, again and again (removals uncover new roots) */
+    t->defer_archive = true;
+    for (;;) {
+        const std::vector<int> roots = t->roots();
+        bool removed = false;
+        for (int r : roots)
+            if (r != t->best_team) { t->remove_team(r); removed = true; }
+        if (!removed) break;
+    }
+    t->purge_archive();
     return TPGX_OK;
 }
 

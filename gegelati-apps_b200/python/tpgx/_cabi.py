@@ -101,12 +101,14 @@ class TrainParams(C.Structure):
                 ("force_program_behavior_change", C.c_int32), ("max_program_size", C.c_int32),
                 ("p_delete", C.c_double), ("p_add", C.c_double), ("p_mutate", C.c_double), ("p_swap", C.c_double), ("p_constant_mutation", C.c_double),
                 ("min_const_value", C.c_int32), ("max_const_value", C.c_int32), ("ratio_deleted_roots", C.c_double),
-                ("archive_size", C.c_int32), ("reserved", C.c_int32), ("archiving_probability", C.c_double)]
+                ("archive_size", C.c_int32), ("reserved", C.c_int32), ("archiving_probability", C.c_double),
+                ("max_nb_evaluation_per_policy", C.c_int32), ("do_validation", C.c_int32), ("nb_iterations_per_policy_evaluation", C.c_int32),
+                ("nb_classes", C.c_int32)]
 
 
-EVALUATE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Graph), C.c_uint64, C.POINTER(C.c_uint64), C.c_double, C.c_int32,
-                          C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32,
-                          C.POINTER(C.c_int32))
+EVALUATE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Graph), C.c_uint64, C.c_int32, C.POINTER(C.c_uint64), C.c_double, C.c_int32,
+                          C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_uint64),
+                          C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_int32))
 EXECUTE_FN = C.CFUNCTYPE(C.c_int32, C.c_void_p, C.POINTER(Graph), C.c_int64, C.POINTER(C.c_double), C.c_int32, C.POINTER(C.c_double))
 
 
@@ -117,7 +119,9 @@ class TrainBackend(C.Structure):
 class TrainStats(C.Structure):
     _fields_ = [("nb_teams", C.c_int32), ("nb_programs", C.c_int32), ("nb_roots", C.c_int32), ("nb_new_programs", C.c_int32),
                 ("nb_removed_roots", C.c_int32), ("archive_records", C.c_int32), ("behaviour_retries", C.c_int32), ("reserved", C.c_int32),
-                ("best_score", C.c_double), ("mean_score", C.c_double), ("worst_score", C.c_double)]
+                ("best_score", C.c_double), ("mean_score", C.c_double), ("worst_score", C.c_double),
+                ("nb_evaluated_roots", C.c_int32), ("nb_skipped_roots", C.c_int32),
+                ("best_validation_score", C.c_double), ("mean_validation_score", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}

@@ -17,7 +17,7 @@ EXPORTS = [
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
     "tpgx_trainer_create", "tpgx_trainer_destroy", "tpgx_trainer_last_error", "tpgx_trainer_graph", "tpgx_trainer_train_generation",
-    "tpgx_trainer_populate", "tpgx_trainer_decimate", "tpgx_trainer_fingerprint", "tpgx_train_backend_episodes", "tpgx_train_backend_classification", "tpgx_train_backend_release",
+    "tpgx_trainer_populate", "tpgx_trainer_decimate", "tpgx_trainer_fingerprint", "tpgx_trainer_root_results", "tpgx_trainer_best_root", "tpgx_trainer_keep_best_policy", "tpgx_train_backend_episodes", "tpgx_train_backend_classification", "tpgx_train_backend_release",
 ]
 
 _lib = None

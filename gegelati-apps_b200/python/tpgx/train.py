@@ -30,7 +30,10 @@ def load_params_json(path, nb_actions):
         ratio_deleted_roots=j["ratioDeletedRoots"], archive_size=j["archiveSize"], archiving_probability=j["archivingProbability"],
         # not trainer fields, but what the evaluation request needs
         nb_iterations=j.get("nbIterationsPerPolicyEvaluation", 1), max_actions=j["maxNbActionsPerEval"], nb_generations=j["nbGenerations"],
-        nb_registers=j.get("nbRegisters", 8), nb_constants=j.get("nbProgramConstant", 0))
+        nb_registers=j.get("nbRegisters", 8), nb_constants=j.get("nbProgramConstant", 0),
+        # [UP] evaluateJob's skip-and-merge of previous results and the validation pass of trainOneGeneration
+        max_nb_evaluation_per_policy=j.get("maxNbEvaluationPerPolicy", 0), do_validation=int(bool(j.get("doValidation", False))),
+        nb_iterations_per_policy_evaluation=j.get("nbIterationsPerPolicyEvaluation", 1), nb_classes=0)
 
 
 _TRAINER_FIELDS = [k for k, _ in A.TrainParams._fields_ if k != "reserved"]
@@ -38,17 +41,23 @@ _TRAINER_FIELDS = [k for k, _ in A.TrainParams._fields_ if k != "reserved"]
 
 def python_backend(evaluate, execute=None, nb_constants=0):
     """Backend from Python callables (tests plug the CPU oracle in here; the product backend is Evaluator-based, see
-    episodes_backend).  evaluate(graph, generation, archive_seeds, probability, archive_size, obs_len) ->
-    (scores[R], rec_program, rec_bid, rec_obs[n, obs_len]);  execute(graph, obs[count, obs_len]) -> bid[P, count]."""
+    episodes_backend).  evaluate(graph, generation, mode, archive_seeds, probability, archive_size, obs_len) ->
+    (scores[R], rec_program, rec_bid, rec_obs[n, obs_len]) or, for a classification agent, the same tuple followed by
+    (class_scores[R, C], class_counts[R, C]); the graph's root list holds exactly the jobs.
+    execute(graph, obs[count, obs_len]) -> bid[P, count]."""
     def graph_of(gp):
         return view_to_graph(gp.contents, nb_constants)
 
-    def ev(_user, gp, generation, aseed, prob, cap, scores, rprog, rbid, robs, obs_len, nrec):
+    def ev(_user, gp, generation, mode, aseed, prob, cap, scores, nb_classes, cscores, ccounts, rprog, rbid, robs, obs_len, nrec):
         try:
             g = graph_of(gp)
-            seeds = np.ctypeslib.as_array(aseed, shape=(g.nb_roots,)).copy()
-            sc, p, b, o = evaluate(g, int(generation), seeds, float(prob), int(cap), int(obs_len))
+            seeds = np.ctypeslib.as_array(aseed, shape=(g.nb_roots,)).copy() if aseed else np.zeros(g.nb_roots, dtype=np.uint64)
+            res = evaluate(g, int(generation), int(mode), seeds, float(prob), int(cap), int(obs_len))
+            sc, p, b, o = res[:4]
             np.ctypeslib.as_array(scores, shape=(g.nb_roots,))[:] = sc
+            if nb_classes > 0:
+                np.ctypeslib.as_array(cscores, shape=(g.nb_roots * nb_classes,))[:] = np.asarray(res[4], dtype=np.float64).reshape(-1)
+                np.ctypeslib.as_array(ccounts, shape=(g.nb_roots * nb_classes,))[:] = np.asarray(res[5], dtype=np.uint64).reshape(-1)
             n = len(p)
             if n:
                 np.ctypeslib.as_array(rprog, shape=(n,))[:] = p
@@ -116,7 +125,9 @@ class Trainer:
         cfg = A.Config(device=0, nb_registers=nb_registers, nb_constants=nb_constants, tie_break=A.TIE_LAST_MAX)
         ops = np.ascontiguousarray(opcodes, dtype=np.int32)
         sd = (A.SourceDesc * len(sources))(*[A.SourceDesc(*s) for s in sources])
-        tp = A.TrainParams(**{k: params[k] for k in _TRAINER_FIELDS})
+        defaults = dict(max_nb_evaluation_per_policy=0, do_validation=0, nb_classes=0,
+                        nb_iterations_per_policy_evaluation=params.get("nb_iterations", 1))
+        tp = A.TrainParams(**{k: params[k] if k in params else defaults[k] for k in _TRAINER_FIELDS})
         h = C.c_void_p()
         st = L.tpgx_trainer_create(C.byref(cfg), len(ops), ops.ctypes.data, len(sources), C.cast(sd, C.c_void_p), C.byref(tp), int(seed), C.byref(h))
         if st != A.OK:
@@ -161,6 +172,27 @@ class Trainer:
 
     def fingerprint(self):
         return int(self.lib.tpgx_trainer_fingerprint(self.h))
+
+    def root_results(self):
+        """[UP] resultsPerRoot of the current roots: (score[R] — NaN where not evaluated yet —, nb_evaluation[R])."""
+        L = self.lib
+        L.tpgx_trainer_root_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
+        n = L.tpgx_trainer_root_results(self.h, None, None, 0)
+        sc, ne = np.zeros(n), np.zeros(n, dtype=np.uint64)
+        L.tpgx_trainer_root_results(self.h, sc.ctypes.data, ne.ctypes.data, n)
+        return sc, ne
+
+    def best_root(self):
+        """(index in the current root list, stored score) of [UP] getBestRoot()."""
+        L = self.lib
+        L.tpgx_trainer_best_root.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+        i, sc = C.c_int32(-1), C.c_double(0.0)
+        self._check(L.tpgx_trainer_best_root(self.h, C.byref(i), C.byref(sc)))
+        return i.value, sc.value
+
+    def keep_best_policy(self):
+        self.lib.tpgx_trainer_keep_best_policy.argtypes = [C.c_void_p]
+        self._check(self.lib.tpgx_trainer_keep_best_policy(self.h))
 
 
 def episodes_backend(evaluator, env, nb_iterations, max_actions, mode=A.MODE_TRAINING, second_player_random=0, pendulum_actions=None):

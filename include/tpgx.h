@@ -326,16 +326,27 @@ typedef struct {
     int32_t archive_size;              /* archiveSize                                                               */
     int32_t reserved;
     double archiving_probability;      /* archivingProbability                                                      */
+    int32_t max_nb_evaluation_per_policy;      /* maxNbEvaluationPerPolicy ([REF] gridworld/params.json:20): a root whose stored
+                                                  result already counts that many evaluations is not evaluated again in
+                                                  TRAINING mode ([UP] LearningAgent::isRootEvalSkipped); <= 0: never skipped  */
+    int32_t do_validation;                     /* doValidation ([REF] mnist/params.json:11): evaluateAllRoots(VALIDATION) on the
+                                                  surviving roots after the decimation                                       */
+    int32_t nb_iterations_per_policy_evaluation; /* nbIterationsPerPolicyEvaluation: evaluations one plain job adds to a root     */
+    int32_t nb_classes;                        /* > 0: Learn::ClassificationLearningAgent (results combine per class)        */
 } tpgx_train_params;
 
 typedef struct {
     void* user;
-    /* evaluateAllRoots(generation, TRAINING) of graph g, job j = root j: scores[nb_roots]; archive side effect with one
-       Archive per job seeded archive_seed[j]: <= archive_size records (program id in g, bid, observation row of obs_len
-       doubles) in archive order.  Returns a tpgx_status.                                                            */
-    tpgx_status (*evaluate)(void* user, const tpgx_graph* g, uint64_t generation, const uint64_t* archive_seed, double probability,
-                            int32_t archive_size, double* scores, int32_t* rec_program, double* rec_bid, double* rec_obs,
-                            int32_t obs_len, int32_t* nb_records);
+    /* evaluateAllRoots(generation, mode) of graph g, whose root list holds exactly the roots to evaluate (the trainer leaves
+       out the roots [UP] evaluateJob skips), job j = root j: scores[nb_roots]; for a classification agent (nb_classes > 0)
+       also class_scores[nb_roots][nb_classes] (per-class F1) and class_counts[nb_roots][nb_classes] (samples of each class
+       seen).  Archive side effect when archive_size > 0 and probability > 0 (TRAINING only): one Archive per job seeded
+       archive_seed[j], <= archive_size records (program id in g, bid, observation row of obs_len doubles) in archive order.
+       Returns a tpgx_status.                                                                                        */
+    tpgx_status (*evaluate)(void* user, const tpgx_graph* g, uint64_t generation, int32_t mode, const uint64_t* archive_seed,
+                            double probability, int32_t archive_size, double* scores, int32_t nb_classes, double* class_scores,
+                            uint64_t* class_counts, int32_t* rec_program, double* rec_bid, double* rec_obs, int32_t obs_len,
+                            int32_t* nb_records);
     /* bid[nb_programs][count] of every program of g on `count` observation rows (obs_len doubles each)             */
     tpgx_status (*execute)(void* user, const tpgx_graph* g, int64_t count, const double* obs, int32_t obs_len, double* bid);
 } tpgx_train_backend;
@@ -343,7 +354,9 @@ typedef struct {
 typedef struct {
     int32_t nb_teams, nb_programs, nb_roots, nb_new_programs; /* after populate                                      */
     int32_t nb_removed_roots, archive_records, behaviour_retries, reserved;
-    double best_score, mean_score, worst_score;              /* over the evaluated roots                             */
+    double best_score, mean_score, worst_score;              /* over all roots: stored results of the skipped ones included */
+    int32_t nb_evaluated_roots, nb_skipped_roots;            /* TRAINING pass: jobs run / roots at maxNbEvaluationPerPolicy  */
+    double best_validation_score, mean_validation_score;     /* doValidation: over the surviving roots, else NaN            */
 } tpgx_train_stats;
 
 typedef struct tpgx_trainer tpgx_trainer;
@@ -366,8 +379,16 @@ tpgx_status tpgx_trainer_populate(tpgx_trainer* t, const tpgx_train_backend* bac
 tpgx_status tpgx_trainer_decimate(tpgx_trainer* t, const double* root_scores, tpgx_train_stats* stats);
 /* 64-bit fingerprint of the graph (teams, edges, programs, constants): equal fingerprints <=> same evolution so far */
 uint64_t tpgx_trainer_fingerprint(const tpgx_trainer* t);
+/* [UP] resultsPerRoot: the stored result of every current root, in root order (tpgx_trainer_graph's root list):
+ * score[r] (NaN when the root has not been evaluated yet) and nb_evaluation[r].  Returns the number of roots.          */
+int32_t tpgx_trainer_root_results(tpgx_trainer* t, double* score, uint64_t* nb_evaluation, int32_t capacity);
+/* [UP] LearningAgent::getBestRoot() / Selector::getBestRoot(): index in the current root list of the best root seen by
+ * the last updateEvaluationRecords and its stored score; TPGX_ERR_STATE before the first generation or when that root
+ * has left the graph.  [UP] keepBestPolicy(): every other root team is removed until the best root is the only root.  */
+tpgx_status tpgx_trainer_best_root(tpgx_trainer* t, int32_t* root_index, double* score);
+tpgx_status tpgx_trainer_keep_best_policy(tpgx_trainer* t);
 /* GPU backend for the sequential environments: evaluate = tpgx_set_graph + tpgx_archive_episodes with the request
- * template `req` (nb_jobs / job_roots / seeds are filled per generation: job j = root j, iteration seeds
+ * template `req` (nb_jobs / job_roots / seeds / mode are filled per call: job j = root j, iteration seeds
  * 1000 * generation + it — SURVEY.md §8d, the real Data::Hash is upstream), execute = tpgx_set_graph +
  * tpgx_execute_programs.  The backend borrows ctx and req (and req->pendulum_actions); free with
  * tpgx_train_backend_release.                                                                                       */

@@ -109,7 +109,7 @@ def test_gridworld_training_learns_with_the_oracle_backend(oracle_mod):
     stats = [tr.train_generation(be, gen) for gen in range(10)]
     best = [s["best_score"] for s in stats]
     assert best[0] <= best[-1] and max(best) > 0.0, best
-    assert all(np.array_equal(np.sort(sc)[::-1][0], s["best_score"]) for sc, s in zip(log, stats))
+    assert all(np.array_equal(np.sort(sc)[::-1][0], s["best_score"]) for (_, _, sc), s in zip(log, stats))
     assert stats[-1]["archive_records"] > 0 and sum(s["behaviour_retries"] for s in stats) >= 0
     assert all(s["nb_roots"] == 60 and s["nb_removed_roots"] == 30 for s in stats)
 
@@ -129,3 +129,90 @@ def test_batched_behaviour_test_equals_one_mutant_per_call(oracle_mod, monkeypat
         prints.append((tr.fingerprint(), [s["behaviour_retries"] for s in stats], [s["best_score"] for s in stats]))
     assert sum(prints[0][1]) > 0, "the behaviour test never had to retry: the case does not exercise it"
     assert prints[0] == prints[1] == prints[2]
+
+
+def test_evaluate_job_skips_roots_at_the_evaluation_cap_and_merges_previous_results(oracle_mod):
+    """[UP] LearningAgent::evaluateJob ([REF] */params.json maxNbEvaluationPerPolicy: gridworld / pendulum 10, mnist 2000):
+    a root whose stored result counts maxNbEvaluationPerPolicy evaluations is NOT run again in TRAINING mode, any other
+    root's new result is combined with its stored one (evaluation-count-weighted mean, upstream's operation order).  With
+    ratioDeletedRoots = 0 the roots never change, so the stored results can be recomputed from the backend's log."""
+    tr, p = make("stickgame", seed=4, nb_roots=24, archive_size=0, ratio_deleted_roots=0.0, force_program_behavior_change=0,
+                 max_nb_evaluation_per_policy=6, nb_iterations_per_policy_evaluation=2)
+    log = []
+    be = oracle_backend(oracle_mod, "stickgame", nb_iterations=2, max_actions=11, second_player_random=1, log=log)
+    want, n = None, 0
+    for gen in range(5):
+        before = len(log)
+        st = tr.train_generation(be, gen)
+        score, nb = tr.root_results()
+        if gen < 3:                                     # 2 evaluations per generation: the cap of 6 is reached after three
+            assert st["nb_evaluated_roots"] == 24 and st["nb_skipped_roots"] == 0 and len(log) == before + 1
+            mode, jobs, new = log[-1]
+            assert mode == A.MODE_TRAINING and jobs == 24
+            if want is None:
+                want, n = new.copy(), 2
+            else:                                       # EvaluationResult::operator+=, `new` on the left
+                want = (new * 2.0 + want * float(n)) / (2.0 + float(n))
+                n += 2
+        else:                                           # every root is at the cap: nothing is launched, results stand
+            assert st["nb_evaluated_roots"] == 0 and st["nb_skipped_roots"] == 24 and len(log) == before
+        assert np.array_equal(score.view(np.uint64), want.view(np.uint64)) and (nb == n).all()
+        assert st["best_score"] == want.max()
+    assert len({tuple(s) for (_, _, s) in log}) > 1, "the generations' raw scores must differ for the merge to be visible"
+
+
+def test_new_roots_are_evaluated_while_capped_ones_are_skipped(oracle_mod):
+    """With decimation on, the surviving roots keep their evaluation count and the fresh ones start at zero: the backend
+    sees a root list holding only the roots below the cap."""
+    tr, p = make(seed=5, max_nb_evaluation_per_policy=2, nb_iterations_per_policy_evaluation=1, **SMALL)
+    log = []
+    be = oracle_backend(oracle_mod, "gridworld", nb_iterations=1, max_actions=100, log=log)
+    stats = [tr.train_generation(be, gen) for gen in range(12)]
+    assert stats[0]["nb_skipped_roots"] == 0 and stats[1]["nb_skipped_roots"] == 0
+    # a survivor stays a root only until a new team points at it, so few roots ever reach the cap in a small population
+    assert sum(s["nb_skipped_roots"] for s in stats[2:]) > 0, [s["nb_skipped_roots"] for s in stats]
+    for s, (mode, jobs, sc) in zip(stats, log):
+        assert mode == A.MODE_TRAINING and jobs == s["nb_evaluated_roots"] == 60 - s["nb_skipped_roots"] and len(sc) == jobs
+    score, nb = tr.root_results()
+    assert nb.max() <= 2 and nb.min() >= 1 and not np.isnan(score).any()
+
+
+def test_validation_pass_runs_after_the_decimation_on_the_survivors(oracle_mod):
+    """[UP] trainOneGeneration with doValidation ([REF] mnist/params.json:11, pendulum/params.json:14): a second
+    evaluateAllRoots in VALIDATION mode on the roots left by the decimation; its results are reported, not stored."""
+    tr, p = make("pendulum", seed=6, do_validation=1, nb_iterations_per_policy_evaluation=1, **SMALL)
+    log = []
+    pa = [0.05, 0.1, 0.2, 0.4, 0.6, 0.8, 1.0]
+    be = oracle_backend(oracle_mod, "pendulum", nb_iterations=1, max_actions=60, pendulum_actions=pa, log=log)
+    for gen in range(3):
+        st = tr.train_generation(be, gen)
+        (m0, j0, s0), (m1, j1, s1) = log[-2:]
+        # removing 30 roots can uncover teams only they pointed at: the survivors are the graph's roots after the decimation
+        assert (m0, j0) == (A.MODE_TRAINING, 60) and m1 == A.MODE_VALIDATION and j1 == tr.graph().nb_roots >= 30
+        seq = 0.0
+        for v in s1:
+            seq += v                                          # the trainer sums sequentially (numpy's mean sums pairwise)
+        assert st["best_validation_score"] == s1.max() and st["mean_validation_score"] == seq / len(s1)
+        assert not np.array_equal(np.sort(s1)[-20:], np.sort(s0)[-20:]), "validation draws its own initial states (mode enters the seed)"
+    off, p2 = make("pendulum", seed=6, do_validation=0, nb_iterations_per_policy_evaluation=1, **SMALL)
+    be2 = oracle_backend(oracle_mod, "pendulum", nb_iterations=1, max_actions=60, pendulum_actions=pa)
+    for gen in range(3):
+        st2 = off.train_generation(be2, gen)
+    assert np.isnan(st2["best_validation_score"]) and off.fingerprint() == tr.fingerprint(), "validation must not change the evolution"
+
+
+def test_best_root_and_keep_best_policy(oracle_mod):
+    """[UP] getBestRoot / keepBestPolicy as the apps call them after training ([REF] gridworld/src/main.cpp:68,79)."""
+    tr, p = make(seed=5, **SMALL)
+    be = oracle_backend(oracle_mod, "gridworld", nb_iterations=1, max_actions=100)
+    for gen in range(6):
+        st = tr.train_generation(be, gen)
+    idx, sc = tr.best_root()
+    score, _ = tr.root_results()
+    assert sc == score[idx] == np.nanmax(score)
+    before = tr.graph()
+    tr.keep_best_policy()
+    after = tr.graph()
+    assert after.nb_roots == 1 and after.nb_teams <= before.nb_teams
+    check_invariants(after, p, "gridworld")
+    assert tr.best_root()[0] == 0

@@ -21,14 +21,14 @@ def split_obs(sources, obs):
 def oracle_backend(oracle_mod, app, nb_iterations, max_actions, second_player_random=0, pendulum_actions=None, log=None):
     ops, src, nc, env = tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], tpgx.APP_CONSTANTS[app], tpgx.APP_ENV[app]
 
-    def evaluate(g, generation, aseeds, prob, cap, obs_len):
+    def evaluate(g, generation, mode, aseeds, prob, cap, obs_len):
         o = oracle_mod.Oracle(ops, src, g, nb_constants=nc)
         kw = dict(seeds=np.arange(nb_iterations, dtype=np.uint64) + np.uint64(1000 * generation), job_roots=np.arange(g.nb_roots),
-                  max_actions=max_actions, second_player_random=second_player_random, pendulum_actions=pendulum_actions)
+                  max_actions=max_actions, second_player_random=second_player_random, pendulum_actions=pendulum_actions, mode=mode)
         score = o.evaluate_episodes(env, **kw)["score"][:, 0]
         if log is not None:
-            log.append(score.copy())
-        if cap == 0 or prob == 0.0:
+            log.append((mode, g.nb_roots, score.copy()))
+        if cap == 0 or prob == 0.0 or mode != A.MODE_TRAINING:
             return score, [], [], np.zeros((0, obs_len))
         ar = o.archive_episodes(env, archive_seeds=aseeds, probability=prob, archive_size=cap, obs_len=obs_len, **kw)
         return score, ar["program"], ar["bid"], ar["observation"]
@@ -40,19 +40,22 @@ def oracle_backend(oracle_mod, app, nb_iterations, max_actions, second_player_ra
     return tpgx.python_backend(evaluate, execute, nb_constants=nc)
 
 
-def oracle_classification_backend(oracle_mod, images, labels, actions):
+def oracle_classification_backend(oracle_mod, images, labels, actions, log=None):
     """Same conventions as tpgx_train_backend_classification: the images of generation `gen` are those
     tpgx_mnist_episode_indices draws from seed 1000 * gen in TRAINING mode; the archived observation is the image."""
     ops, src, nc = tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], tpgx.APP_CONSTANTS["mnist"]
 
-    def evaluate(g, generation, aseeds, prob, cap, obs_len):
+    def evaluate(g, generation, mode, aseeds, prob, cap, obs_len):
         o = oracle_mod.Oracle(ops, src, g, nb_constants=nc)
-        idx = tpgx.mnist_episode_indices(seed=1000 * generation, mode=A.MODE_TRAINING, dataset_size=len(images), nb_actions=actions)
-        score = o.evaluate_classification(images, labels, sample_index=idx, want=("score",))["score"]
-        if cap == 0 or prob == 0.0:
-            return score, [], [], np.zeros((0, obs_len))
+        idx = tpgx.mnist_episode_indices(seed=1000 * generation, mode=mode, dataset_size=len(images), nb_actions=actions)
+        out = o.evaluate_classification(images, labels, sample_index=idx, want=("score", "class_f1", "confusion"))
+        score, cls = out["score"], (out["class_f1"], out["confusion"].sum(axis=2))
+        if log is not None:
+            log.append((mode, g.nb_roots, score.copy()))
+        if cap == 0 or prob == 0.0 or mode != A.MODE_TRAINING:
+            return (score, [], [], np.zeros((0, obs_len))) + cls
         ar = o.archive_classification(images, aseeds, prob, cap, sample_index=idx)
-        return score, ar["program"], ar["bid"], images[ar["sample"]].astype(np.float64)
+        return (score, ar["program"], ar["bid"], images[ar["sample"]].astype(np.float64)) + cls
 
     def execute(g, obs):
         return oracle_mod.Oracle(ops, src, g, nb_constants=nc).execute_programs(len(obs), [obs])
