@@ -565,7 +565,7 @@ static cudaError_t launch_cta(const tpgx_episode_params& p, size_t smem, cudaStr
     }
     dim3 grid(p.nb_jobs, (p.nb_iterations + 31) / 32);
     if (grid.y > 65535u) return cudaErrorInvalidConfiguration;
-    tpgx_episode_cta_kernel<Env><<<grid, p.cta_warps * 32, smem, st>>>(p);
+    tpgx_episode_cta_kernel<Env><<<grid, p.cta_warps * 32, smem, st>>>(p); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -602,20 +602,20 @@ cudaError_t tpgx_launch_episodes(const tpgx_episode_params& p, cudaStream_t st) 
         if (e != cudaSuccess) return e;
         if (p.hit_offset) return cudaSuccess; /* archive pass: scores were produced by the counting pass */
         const int n = p.nb_jobs * p.roots_per_job;
-        tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+        tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p); TPGX_COUNT_LAUNCH();
         return cudaGetLastError();
     }
     switch (p.env) {
-    case TPGX_ENV_GRIDWORLD: tpgx_episode_kernel<GridWorld><<<blocks, threads, 0, st>>>(p); break;
-    case TPGX_ENV_STICKGAME: tpgx_episode_kernel<StickGame><<<blocks, threads, 0, st>>>(p); break;
-    case TPGX_ENV_TICTACTOE: tpgx_episode_kernel<TicTacToe><<<blocks, threads, 0, st>>>(p); break;
-    case TPGX_ENV_PENDULUM: tpgx_episode_kernel<Pendulum><<<blocks, threads, 0, st>>>(p); break;
+    case TPGX_ENV_GRIDWORLD: tpgx_episode_kernel<GridWorld><<<blocks, threads, 0, st>>>(p); TPGX_COUNT_LAUNCH(); break;
+    case TPGX_ENV_STICKGAME: tpgx_episode_kernel<StickGame><<<blocks, threads, 0, st>>>(p); TPGX_COUNT_LAUNCH(); break;
+    case TPGX_ENV_TICTACTOE: tpgx_episode_kernel<TicTacToe><<<blocks, threads, 0, st>>>(p); TPGX_COUNT_LAUNCH(); break;
+    case TPGX_ENV_PENDULUM: tpgx_episode_kernel<Pendulum><<<blocks, threads, 0, st>>>(p); TPGX_COUNT_LAUNCH(); break;
     default: return cudaErrorInvalidValue;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     if (p.hit_offset) return cudaSuccess; /* archive pass: scores were produced by the counting pass */
     const int n = p.nb_jobs * p.roots_per_job;
-    tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p);
+    tpgx_job_score_kernel<<<(n + 127) / 128, 128, 0, st>>>(p); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -416,7 +416,7 @@ template <int K, int NW, bool EXT, bool TEAM, bool TS_>
 static cudaError_t launch_bid_k(const tpgx_bid_params& p, dim3 grid, size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(tpgx_bid_kernel<K, NW, EXT, TEAM, TS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tpgx_bid_kernel<K, NW, EXT, TEAM, TS_><<<grid, NW * 32, smem, st>>>(p);
+    tpgx_bid_kernel<K, NW, EXT, TEAM, TS_><<<grid, NW * 32, smem, st>>>(p); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 template <int K, int NW, bool TS_>

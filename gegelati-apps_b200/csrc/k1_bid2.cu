@@ -558,11 +558,11 @@ cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team, int nb_ctas, 
     if (team) {
         e = cudaFuncSetAttribute(tpgx_bid2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tpgx_bid2_kernel<true><<<nb_ctas, K2_NW * 32, smem, st>>>(p);
+        tpgx_bid2_kernel<true><<<nb_ctas, K2_NW * 32, smem, st>>>(p); TPGX_COUNT_LAUNCH();
     } else {
         e = cudaFuncSetAttribute(tpgx_bid2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        tpgx_bid2_kernel<false><<<nb_ctas, K2_NW * 32, smem, st>>>(p);
+        tpgx_bid2_kernel<false><<<nb_ctas, K2_NW * 32, smem, st>>>(p); TPGX_COUNT_LAUNCH();
     }
     return cudaGetLastError();
 }
@@ -589,6 +589,6 @@ cudaError_t tpgx_launch_k1v2_encode(const uint32_t* code, const int32_t* prog_of
                                     int width, int hw, int nwin, uint4* stream, int* flags, cudaStream_t st) {
     if (nb_rows <= 0) return cudaSuccess;
     tpgx_k1v2_encode_kernel<<<(nb_rows + 127) / 128, 128, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, row_dst, row_flags,
-                                                                  nb_rows, width, hw, nwin, stream, flags);
+                                                                  nb_rows, width, hw, nwin, stream, flags); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }

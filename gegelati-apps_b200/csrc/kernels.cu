@@ -19,6 +19,11 @@
 #include "dev_ops.cuh"
 #include "kernels.cuh"
 
+std::atomic<unsigned long long>& tpgx_launch_counter() {
+    static std::atomic<unsigned long long> n{0};
+    return n;
+}
+
 /* ================================================================================================
  * K2 — traversal.  block = (span of samples, one root); thread = one (root, sample) walk.
  * [UP] executeFromRoot: from the root team follow the best admissible edge until an action;
@@ -140,7 +145,7 @@ cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p0, cudaStream_t st) {
         if (p.action) p.action = p0.action + (size_t)r0 * p0.action_stride;
         if (p.confusion) p.confusion = p0.confusion + (size_t)r0 * p0.nb_classes * p0.nb_classes;
         dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
-        tpgx_traverse_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
+        tpgx_traverse_kernel<<<grid, TRAV_THREADS, 0, st>>>(p); TPGX_COUNT_LAUNCH();
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -229,7 +234,7 @@ cudaError_t tpgx_launch_walk(const tpgx_walk_params& p0, cudaStream_t st) {
         if (p.action) p.action = p0.action + (size_t)r0 * p0.action_stride;
         if (p.confusion) p.confusion = p0.confusion + (size_t)r0 * p0.nb_classes * p0.nb_classes;
         dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
-        tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p);
+        tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p); TPGX_COUNT_LAUNCH();
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -286,7 +291,7 @@ cudaError_t tpgx_launch_arch_count(const tpgx_arch_params& p0, cudaStream_t st) 
         p.roots = p0.roots + r0;
         p.counts = p0.counts + (size_t)r0 * p0.nb_samples;
         dim3 grid((p.nb_samples + 127) / 128, p.nb_roots);
-        tpgx_arch_count_kernel<<<grid, 128, 0, st>>>(p);
+        tpgx_arch_count_kernel<<<grid, 128, 0, st>>>(p); TPGX_COUNT_LAUNCH();
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
@@ -325,7 +330,7 @@ __global__ void tpgx_arch_resolve_kernel(const tpgx_arch_params p) {
 }
 cudaError_t tpgx_launch_arch_resolve(const tpgx_arch_params& p, cudaStream_t st) {
     if (p.nb_hits <= 0) return cudaSuccess;
-    tpgx_arch_resolve_kernel<<<(p.nb_hits + 127) / 128, 128, 0, st>>>(p);
+    tpgx_arch_resolve_kernel<<<(p.nb_hits + 127) / 128, 128, 0, st>>>(p); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -354,7 +359,7 @@ __global__ void tpgx_score_kernel(const unsigned long long* __restrict__ confusi
 }
 
 cudaError_t tpgx_launch_score(const unsigned long long* confusion, int nb_roots, int nb_classes, double* records, cudaStream_t st) {
-    tpgx_score_kernel<<<(nb_roots + 127) / 128, 128, 0, st>>>(confusion, nb_roots, nb_classes, records);
+    tpgx_score_kernel<<<(nb_roots + 127) / 128, 128, 0, st>>>(confusion, nb_roots, nb_classes, records); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -392,7 +397,7 @@ cudaError_t tpgx_launch_pack(const uint8_t* obs, const int32_t* sample_index, lo
                              int ts, uint8_t* tiles, const uint8_t* labels_in, uint8_t* labels_out, cudaStream_t st) {
     const long long nb_tiles = (nb_samples + ts - 1) / ts;
     dim3 grid((unsigned)nb_tiles, (hw + 1 + 31) / 32);
-    tpgx_pack_kernel<<<grid, 256, 0, st>>>(obs, sample_index, nb_samples, nb_obs, hw, ts, tiles, labels_in, labels_out);
+    tpgx_pack_kernel<<<grid, 256, 0, st>>>(obs, sample_index, nb_samples, nb_obs, hw, ts, tiles, labels_in, labels_out); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -426,7 +431,7 @@ cudaError_t tpgx_launch_sobel_planes(const uint8_t* tiles, long long nb_tiles, i
                                      double* planes, cudaStream_t st) {
     const int nwin_w = width - 2, nwin = (height - 2) * nwin_w;
     dim3 grid((nwin * ts + 255) / 256, (unsigned)nb_tiles);
-    tpgx_sobel_planes_kernel<<<grid, 256, 0, st>>>(tiles, hw, width, nwin_w, nwin, ts, lut, planes);
+    tpgx_sobel_planes_kernel<<<grid, 256, 0, st>>>(tiles, hw, width, nwin_w, nwin, ts, lut, planes); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -461,7 +466,7 @@ cudaError_t tpgx_launch_k1_encode(const uint32_t* code, const int32_t* prog_offs
                                   const int32_t* active_prog, const int2* desc, int nb_rows, int ts, int width, int hw, uint4* stream,
                                   int* flags, cudaStream_t st) {
     if (nb_rows <= 0) return cudaSuccess;
-    tpgx_k1_encode_kernel<<<nb_rows, 32, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, ts, width, hw, stream, flags);
+    tpgx_k1_encode_kernel<<<nb_rows, 32, 0, st>>>(code, prog_offset, constants, nb_constants, active_prog, desc, ts, width, hw, stream, flags); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -497,7 +502,7 @@ cudaError_t tpgx_launch_exec_generic(const uint32_t* code, const int32_t* prog_o
                                      cudaStream_t st) {
     dim3 grid(nb_programs, (unsigned)std::min<long long>((count + 127) / 128, 65535));
     tpgx_exec_generic_kernel<<<grid, 128, 0, st>>>(code, prog_offset, constants, nb_constants, nb_programs, count, f0, f1, i0,
-                                                   i1, space0, space1, width0, width1, bid);
+                                                   i1, space0, space1, width0, width1, bid); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -518,11 +523,11 @@ __global__ void tpgx_sobel_lut_kernel(double2* __restrict__ magn_dir) {
                                                         tpgx_math::atan(tpgx_math::xdiv_small_int(ay, ax)));
 }
 cudaError_t tpgx_launch_pixel_lut(double* lut, cudaStream_t st) {
-    tpgx_pixel_lut_kernel<<<1, 256, 0, st>>>(lut);
+    tpgx_pixel_lut_kernel<<<1, 256, 0, st>>>(lut); TPGX_COUNT_LAUNCH();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dim3 grid((TPGX_SOBEL_LUT_N + 127) / 128, TPGX_SOBEL_LUT_N);
-    tpgx_sobel_lut_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<double2*>(lut + 512));
+    tpgx_sobel_lut_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<double2*>(lut + 512)); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -564,7 +569,7 @@ __global__ void tpgx_math_probe_kernel(int fn, long long n, const double* __rest
 
 cudaError_t tpgx_launch_math_probe(int fn, long long n, const double* a, const double* b, double* out, cudaStream_t st) {
     const long long threads = (n + 3) / 4;
-    tpgx_math_probe_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(fn, n, a, b, out);
+    tpgx_math_probe_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(fn, n, a, b, out); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -593,6 +598,6 @@ __global__ void __launch_bounds__(256) tpgx_fp64_peak_kernel(int mode, int iters
 }
 
 cudaError_t tpgx_launch_fp64_peak(int mode, int blocks, int iters, double* sink, cudaStream_t st) {
-    tpgx_fp64_peak_kernel<<<blocks, 256, 0, st>>>(mode, iters, sink);
+    tpgx_fp64_peak_kernel<<<blocks, 256, 0, st>>>(mode, iters, sink); TPGX_COUNT_LAUNCH();
     return cudaGetLastError();
 }

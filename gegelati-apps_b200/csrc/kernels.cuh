@@ -7,7 +7,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "tpgx_internal.h"
+
+/* kernels launched by this library in this process (tpgx_kernel_launches) */
+std::atomic<unsigned long long>& tpgx_launch_counter();
+#define TPGX_COUNT_LAUNCH() ((void)tpgx_launch_counter().fetch_add(1ull, std::memory_order_relaxed))
 
 /* K1: bid interpreter over a 2-D uint8 observation source (MNIST shape). */
 struct tpgx_bid_params {

@@ -4,6 +4,8 @@
  * There is no CPU fallback: every evaluation entry point launches CUDA kernels or fails.
  */
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -80,7 +82,9 @@ struct tpgx_ctx {
     DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
-    DevBuf d_scratch[16], d_work, d_k2_rflags, d_k2_ufirst;
+    DevBuf d_scratch[16], d_work, d_k2_rflags, d_k2_ufirst, d_gather;
+    ncclComm_t comm = nullptr;           /* owned; NCCL communicator of this context's rank */
+    int comm_rank = 0, comm_world = 1;
     /* tpgx_set_observations_pinned enqueues its copy / re-tiling / Sobel-plane work on a stream of its own, so that
        the graph uploads that follow on the main stream are not queued behind 47 MB of observations; consumers of the
        tiles wait for obs_ready */
@@ -498,11 +502,200 @@ tpgx_status check_device_status(tpgx_ctx* ctx, int status) {
     return TPGX_OK;
 }
 
+/* ---- NCCL, bound at run time: a Python process that imported torch already has libnccl.so.2 mapped (the loader hands
+   that one back), a C++ host gets the system's; libtpgx.so itself carries no NCCL dependency */
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string err;
+    bool load() {
+        if (h) return true;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { h = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+        if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+#define TPGX_NCCL_SYM(field, sym) field = reinterpret_cast<decltype(field)>(dlsym(h, sym)); if (!field) { err = "libnccl lacks " sym; h = nullptr; return false; }
+        TPGX_NCCL_SYM(GetUniqueId, "ncclGetUniqueId") TPGX_NCCL_SYM(CommInitRank, "ncclCommInitRank") TPGX_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+        TPGX_NCCL_SYM(CommDestroy, "ncclCommDestroy") TPGX_NCCL_SYM(AllGather, "ncclAllGather") TPGX_NCCL_SYM(GroupStart, "ncclGroupStart")
+        TPGX_NCCL_SYM(GroupEnd, "ncclGroupEnd") TPGX_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef TPGX_NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+#define NC(call)                                                                                                      \
+    do {                                                                                                              \
+        ncclResult_t r__ = (call);                                                                                    \
+        if (r__ != ncclSuccess) return fail(ctx, TPGX_ERR_NCCL, std::string(#call) + ": " + g_nccl.GetErrorString(r__)); \
+    } while (0)
+
+void tpgx_comm_release(tpgx_ctx* ctx) {
+    if (ctx->comm && g_nccl.h) g_nccl.CommDestroy(ctx->comm);
+    ctx->comm = nullptr; ctx->comm_rank = 0; ctx->comm_world = 1;
+}
+
+void shard_of(const tpgx_ctx* ctx, int total, int* slot, int* rb, int* re) {
+    const int s = (total + ctx->comm_world - 1) / ctx->comm_world;
+    *slot = s;
+    *rb = std::min(total, ctx->comm_rank * s);
+    *re = std::min(total, (ctx->comm_rank + 1) * s);
+}
+
+/* K1 -> K2 -> K3 of this rank's shard with K3 writing into the rank's slot of the gather buffer; returns the buffer */
+tpgx_status enqueue_shard_for_gather(tpgx_ctx* ctx, const tpgx_classif_request* req, int total, double** gather, size_t* count) {
+    if (!req) return fail(ctx, TPGX_ERR_BAD_ARG, "null request");
+    if (total < 1 || total > ctx->flat.nb_roots) return fail(ctx, TPGX_ERR_BAD_ARG, "total_roots exceeds the roots of the graph");
+    int slot, rb, re;
+    shard_of(ctx, total, &slot, &rb, &re);
+    const int C = req->nb_classes;
+    if (C < 1 || C > 16) return fail(ctx, TPGX_ERR_UNSUPPORTED, "nb_classes must be in [1,16]");
+    *count = (size_t)slot * (C + 1);
+    CU(ctx->d_gather.ensure(*count * ctx->comm_world * 8));
+    double* mine = ctx->d_gather.as<double>() + (size_t)ctx->comm_rank * *count;
+    CU(cudaMemsetAsync(mine, 0, *count * 8, ctx->stream)); /* the padding of an uneven last shard */
+    if (re > rb) {
+        tpgx_classif_request r = *req;
+        r.root_begin = rb; r.root_end = re;
+        const tpgx_status st = enqueue_classification(ctx, &r, mine, false, false, nullptr, false);
+        if (st != TPGX_OK) return st;
+    }
+    *gather = ctx->d_gather.as<double>();
+    return TPGX_OK;
+}
+
 } // namespace
 
 extern "C" {
 
 int32_t tpgx_abi_version(void) { return TPGX_ABI_VERSION; }
+uint64_t tpgx_kernel_launches(void) { return tpgx_launch_counter().load(); }
+
+tpgx_status tpgx_comm_unique_id(uint8_t* id) {
+    tpgx_ctx* ctx = nullptr;
+    if (!id) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_comm_unique_id: null id");
+    static_assert(sizeof(ncclUniqueId) <= TPGX_COMM_ID_BYTES, "NCCL unique id does not fit");
+    if (!g_nccl.load()) return fail(ctx, TPGX_ERR_NCCL, g_nccl.err);
+    ncclUniqueId u;
+    NC(g_nccl.GetUniqueId(&u));
+    memset(id, 0, TPGX_COMM_ID_BYTES);
+    memcpy(id, &u, sizeof u);
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_comm_init(tpgx_ctx* ctx, const uint8_t* id, int32_t rank, int32_t world) {
+    if (!ctx || !id || world < 1 || rank < 0 || rank >= world) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_comm_init: bad argument");
+    if (!g_nccl.load()) return fail(ctx, TPGX_ERR_NCCL, g_nccl.err);
+    cudaSetDevice(ctx->cfg.device);
+    tpgx_comm_release(ctx);
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NC(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
+    ctx->comm_rank = rank; ctx->comm_world = world;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_comm_init_all(tpgx_ctx* const* ctxs, int32_t n) {
+    tpgx_ctx* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+    if (!ctx) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_comm_init_all: bad argument");
+    if (!g_nccl.load()) return fail(ctx, TPGX_ERR_NCCL, g_nccl.err);
+    std::vector<int> devs((size_t)n);
+    std::vector<ncclComm_t> comms((size_t)n);
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i]) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_comm_init_all: null context");
+        for (int j = 0; j < i; j++) if (ctxs[j]->cfg.device == ctxs[i]->cfg.device) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_comm_init_all: two contexts on one device");
+        devs[i] = ctxs[i]->cfg.device;
+        tpgx_comm_release(ctxs[i]);
+    }
+    NC(g_nccl.CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->comm_rank = i; ctxs[i]->comm_world = n; }
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_comm_shard(const tpgx_ctx* ctx, int32_t total_roots, int32_t* rank, int32_t* world, int32_t* root_begin, int32_t* root_end) {
+    if (!ctx || total_roots < 0) return TPGX_ERR_BAD_ARG;
+    int slot, rb, re;
+    shard_of(ctx, total_roots, &slot, &rb, &re);
+    if (rank) *rank = ctx->comm_rank;
+    if (world) *world = ctx->comm_world;
+    if (root_begin) *root_begin = rb;
+    if (root_end) *root_end = re;
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_evaluate_classification_allgather_device(tpgx_ctx* ctx, const tpgx_classif_request* req, int32_t total_roots,
+                                                          double* d_records_all, void* stream) {
+    if (!ctx || !req || !d_records_all) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_classification_allgather_device: null argument");
+    if (ctx->comm_world > 1 && !ctx->comm) return fail(ctx, TPGX_ERR_STATE, "no communicator: call tpgx_comm_init first");
+    cudaSetDevice(ctx->cfg.device);
+    cudaStream_t user = static_cast<cudaStream_t>(stream);
+    cudaEvent_t ev_in = ctx->event(62), ev_out = ctx->event(63);
+    CU(cudaEventRecord(ev_in, user));
+    CU(cudaStreamWaitEvent(ctx->stream, ev_in, 0));
+    double* gather = nullptr;
+    size_t count = 0;
+    tpgx_status st = enqueue_shard_for_gather(ctx, req, total_roots, &gather, &count);
+    if (st != TPGX_OK) return st;
+    if (ctx->comm_world > 1) NC(g_nccl.AllGather(gather + (size_t)ctx->comm_rank * count, gather, count, ncclDouble, ctx->comm, ctx->stream));
+    /* slots are per rank; with slot * world >= total the first total_roots records are the roots in order */
+    CU(cudaMemcpyAsync(d_records_all, gather, (size_t)total_roots * (req->nb_classes + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaEventRecord(ev_out, ctx->stream));
+    CU(cudaStreamWaitEvent(user, ev_out, 0));
+    return TPGX_OK;
+}
+
+tpgx_status tpgx_evaluate_classification_allgather(tpgx_ctx* ctx, const tpgx_classif_request* req, int32_t total_roots, double* records_all) {
+    if (!ctx || !req) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_classification_allgather: null argument");
+    if (ctx->comm_world > 1 && !ctx->comm) return fail(ctx, TPGX_ERR_STATE, "no communicator: call tpgx_comm_init first");
+    cudaSetDevice(ctx->cfg.device);
+    double* gather = nullptr;
+    size_t count = 0;
+    tpgx_status st = enqueue_shard_for_gather(ctx, req, total_roots, &gather, &count);
+    if (st != TPGX_OK) return st;
+    if (ctx->comm_world > 1) NC(g_nccl.AllGather(gather + (size_t)ctx->comm_rank * count, gather, count, ncclDouble, ctx->comm, ctx->stream));
+    if (records_all) CU(cudaMemcpyAsync(records_all, gather, (size_t)total_roots * (req->nb_classes + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    int status = 0;
+    CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
+    return check_device_status(ctx, status);
+}
+
+tpgx_status tpgx_evaluate_classification_allgather_all(tpgx_ctx* const* ctxs, int32_t n, const tpgx_classif_request* req, int32_t total_roots,
+                                                       double* records_all) {
+    tpgx_ctx* ctx = (ctxs && n > 0) ? ctxs[0] : nullptr;
+    if (!ctx || !req) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_classification_allgather_all: bad argument");
+    std::vector<double*> gather((size_t)n, nullptr);
+    size_t count = 0;
+    for (int i = 0; i < n; i++) { /* every device works on its shard at the same time */
+        tpgx_ctx* c = ctxs[i];
+        if (!c || c->comm_world != n || c->comm_rank != i || (n > 1 && !c->comm)) return fail(ctx, TPGX_ERR_STATE, "contexts are not the ranks of one tpgx_comm_init_all");
+        cudaSetDevice(c->cfg.device);
+        const tpgx_status st = enqueue_shard_for_gather(c, req, total_roots, &gather[i], &count);
+        if (st != TPGX_OK) { if (c != ctx) ctx->err = c->err; return st; }
+    }
+    if (n > 1) {
+        NC(g_nccl.GroupStart());
+        for (int i = 0; i < n; i++)
+            NC(g_nccl.AllGather(gather[i] + (size_t)i * count, gather[i], count, ncclDouble, ctxs[i]->comm, ctxs[i]->stream));
+        NC(g_nccl.GroupEnd());
+    }
+    for (int i = 0; i < n; i++) {
+        tpgx_ctx* c = ctxs[i];
+        cudaSetDevice(c->cfg.device);
+        if (i == 0 && records_all) CU(cudaMemcpyAsync(records_all, gather[0], (size_t)total_roots * (req->nb_classes + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        int status = 0;
+        CU(cudaMemcpy(&status, c->d_status.p, 4, cudaMemcpyDeviceToHost));
+        const tpgx_status st = check_device_status(c, status);
+        if (st != TPGX_OK) { if (c != ctx) ctx->err = c->err; return st; }
+    }
+    return TPGX_OK;
+}
+
 
 const char* tpgx_last_error(const tpgx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
@@ -550,9 +743,10 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_tm_team, &ctx->d_tm_dst, &ctx->d_tm_stat, &ctx->d_tm_roots, &ctx->d_decision, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
-                     &ctx->d_counters, &ctx->d_status, &ctx->d_work, &ctx->d_k2_rflags, &ctx->d_k2_ufirst};
+                     &ctx->d_counters, &ctx->d_status, &ctx->d_work, &ctx->d_k2_rflags, &ctx->d_k2_ufirst, &ctx->d_gather};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : ctx->d_scratch) b.release();
+    tpgx_comm_release(ctx);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->obs_stream) { cudaStreamSynchronize(ctx->obs_stream); cudaStreamDestroy(ctx->obs_stream); }
     if (ctx->obs_ready) cudaEventDestroy(ctx->obs_ready);

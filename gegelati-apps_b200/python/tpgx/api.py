@@ -12,7 +12,8 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..", "..", "lib", "libtpgx.so"))
 
 EXPORTS = [
-    "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table", "tpgx_k1v2_encode_program", "tpgx_k1v2_handler_name",
+    "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table", "tpgx_k1v2_encode_program", "tpgx_k1v2_handler_name", "tpgx_comm_unique_id", "tpgx_comm_init", "tpgx_comm_init_all", "tpgx_comm_shard",
+    "tpgx_evaluate_classification_allgather", "tpgx_evaluate_classification_allgather_device", "tpgx_evaluate_classification_allgather_all", "tpgx_kernel_launches",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
@@ -116,6 +117,36 @@ def k1v2_encode_program(words, width=28, hw=784, nwin=676):
     if st != A.OK:
         raise TpgxError(st, "tpgx_k1v2_encode_program")
     return dict(quads=q, slots=ns.value)
+
+
+def kernel_launches():
+    """Kernels launched by libtpgx in this process so far."""
+    lib = load_library()
+    lib.tpgx_kernel_launches.restype = C.c_uint64
+    return int(lib.tpgx_kernel_launches())
+
+
+def comm_init_all(evaluators):
+    """Single-process multi-GPU: one NCCL communicator over the evaluators' contexts (one per device)."""
+    lib = load_library()
+    arr = (C.c_void_p * len(evaluators))(*[e.h for e in evaluators])
+    lib.tpgx_comm_init_all.argtypes = [C.c_void_p, C.c_int32]
+    st = lib.tpgx_comm_init_all(C.cast(arr, C.c_void_p), len(evaluators))
+    if st != A.OK:
+        raise TpgxError(st, (lib.tpgx_last_error(evaluators[0].h) or b"").decode())
+
+
+def evaluate_classification_allgather_all(evaluators, total_roots, nb_samples, nb_classes=10):
+    """The single-process collective over all contexts; returns dict(score, class_f1) of all roots."""
+    lib = load_library()
+    arr = (C.c_void_p * len(evaluators))(*[e.h for e in evaluators])
+    req = A.ClassifRequest(nb_samples=int(nb_samples), sample_index=None, nb_classes=nb_classes, root_begin=0, root_end=0)
+    rec = np.zeros((int(total_roots), nb_classes + 1))
+    lib.tpgx_evaluate_classification_allgather_all.argtypes = [C.c_void_p, C.c_int32, C.POINTER(A.ClassifRequest), C.c_int32, C.c_void_p]
+    st = lib.tpgx_evaluate_classification_allgather_all(C.cast(arr, C.c_void_p), len(evaluators), C.byref(req), int(total_roots), rec.ctypes.data)
+    if st != A.OK:
+        raise TpgxError(st, (lib.tpgx_last_error(evaluators[0].h) or b"").decode())
+    return dict(score=rec[:, 0].copy(), class_f1=rec[:, 1:].copy())
 
 
 def mnist_episode_indices(seed, mode, dataset_size, nb_actions):
@@ -230,6 +261,46 @@ class Evaluator:
         root_end = self.graph.nb_roots if root_end is None else root_end
         req = A.ClassifRequest(nb_samples=int(nb_samples), sample_index=None, nb_classes=nb_classes, root_begin=root_begin, root_end=root_end)
         self._check(self.lib.tpgx_evaluate_classification_device(self.h, C.byref(req), records_ptr, stream_ptr))
+
+    # ---- multi-GPU: the library's own NCCL communicator (include/tpgx.h, "multi-GPU") ----
+    @staticmethod
+    def comm_unique_id():
+        """128-byte NCCL unique id (rank 0 creates it, the caller hands it to every rank)."""
+        lib = load_library()
+        lib.tpgx_comm_unique_id.argtypes = [C.c_void_p]
+        buf = np.zeros(128, dtype=np.uint8)
+        st = lib.tpgx_comm_unique_id(buf.ctypes.data)
+        if st != A.OK:
+            raise TpgxError(st, (lib.tpgx_last_error(None) or b"").decode())
+        return buf
+
+    def comm_init(self, unique_id, rank, world):
+        self.lib.tpgx_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        self._check(self.lib.tpgx_comm_init(self.h, uid.ctypes.data, int(rank), int(world)))
+
+    def comm_shard(self, total_roots):
+        """(rank, world, root_begin, root_end) of this context for a graph of total_roots roots."""
+        self.lib.tpgx_comm_shard.argtypes = [C.c_void_p, C.c_int32] + [C.POINTER(C.c_int32)] * 4
+        v = [C.c_int32(0) for _ in range(4)]
+        self._check(self.lib.tpgx_comm_shard(self.h, int(total_roots), *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    def evaluate_classification_allgather(self, total_roots, nb_samples=None, sample_index=None, nb_classes=10):
+        """Collective: this rank's shard evaluated, all ranks' records gathered by the library's NCCL all-gather.
+        Returns dict(score [total_roots], class_f1 [total_roots, C])."""
+        idx = np.ascontiguousarray(sample_index, dtype=np.int32) if sample_index is not None else None
+        nS = int(nb_samples if nb_samples is not None else (len(idx) if idx is not None else self.nb_obs))
+        req = A.ClassifRequest(nb_samples=nS, sample_index=_ptr(idx), nb_classes=nb_classes, root_begin=0, root_end=0)
+        rec = np.zeros((int(total_roots), nb_classes + 1))
+        self.lib.tpgx_evaluate_classification_allgather.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.c_int32, C.c_void_p]
+        self._check(self.lib.tpgx_evaluate_classification_allgather(self.h, C.byref(req), int(total_roots), rec.ctypes.data))
+        return dict(score=rec[:, 0].copy(), class_f1=rec[:, 1:].copy())
+
+    def evaluate_classification_allgather_device(self, records_all_ptr, stream_ptr, total_roots, nb_samples, nb_classes=10):
+        req = A.ClassifRequest(nb_samples=int(nb_samples), sample_index=None, nb_classes=nb_classes, root_begin=0, root_end=0)
+        self.lib.tpgx_evaluate_classification_allgather_device.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.c_int32, C.c_void_p, C.c_void_p]
+        self._check(self.lib.tpgx_evaluate_classification_allgather_device(self.h, C.byref(req), int(total_roots), int(records_all_ptr), stream_ptr))
 
     def archive_classification(self, archive_seeds, probability, archive_size, nb_samples=None, sample_index=None, root_begin=0, root_end=None):
         """Archive left by a TRAINING evaluateAllRoots ([UP] Archive::addRecording): dict(program, sample, bid) in archive order."""

@@ -18,9 +18,13 @@ COMMON = dict(nb_roots=roots, p_edge_deletion=0.7, p_edge_addition=0.7, p_progra
               p_edge_destination_is_action=0.5, force_program_behavior_change=1, max_program_size=20, p_delete=0.5, p_add=0.5, p_mutate=1.0,
               p_swap=1.0, p_constant_mutation=0.5, min_const_value=-10, max_const_value=10, ratio_deleted_roots=0.5, archiving_probability=0.01)
 if app == "gridworld":
-    P = dict(COMMON, nb_actions=4, max_init_outgoing_edges=4, max_outgoing_edges=10, archive_size=2000)
+    # [REF] gridworld/params.json:11,20,97: no validation, maxNbEvaluationPerPolicy 10, 1 iteration per evaluation
+    P = dict(COMMON, nb_actions=4, max_init_outgoing_edges=4, max_outgoing_edges=10, archive_size=2000, do_validation=0,
+             max_nb_evaluation_per_policy=10, nb_iterations_per_policy_evaluation=1)
 else:
-    P = dict(COMMON, nb_actions=10, max_init_outgoing_edges=3, max_outgoing_edges=5, archive_size=500)
+    # [REF] mnist/params.json:11,20: validation on, maxNbEvaluationPerPolicy 2000 (= 4 evaluations of 500 images), per-class results
+    P = dict(COMMON, nb_actions=10, max_init_outgoing_edges=3, max_outgoing_edges=5, archive_size=500, do_validation=1,
+             max_nb_evaluation_per_policy=2000, nb_iterations_per_policy_evaluation=1, nb_classes=10)
 tr = tpgx.Trainer(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], P, nb_constants=5, seed=0)
 ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS[app], tpgx.APP_SOURCES[app], nb_constants=5)
 if app == "gridworld":
@@ -34,7 +38,8 @@ t0 = time.perf_counter()
 for gen in range(1, gens + 1):
     s = tr.train_generation(be, gen)
     if gen % max(1, gens // 10) == 0:
-        print("gen %4d  best %8.4f  mean %9.4f  teams %4d  programs %5d  archive %4d  retries %5d" %
-              (gen, s["best_score"], s["mean_score"], s["nb_teams"], s["nb_programs"], s["archive_records"], s["behaviour_retries"]))
+        print("gen %4d  best %8.4f  mean %9.4f  validation best %8.4f  teams %4d  programs %5d  archive %4d  retries %5d  jobs %3d  skipped %3d" %
+              (gen, s["best_score"], s["mean_score"], s["best_validation_score"], s["nb_teams"], s["nb_programs"], s["archive_records"],
+               s["behaviour_retries"], s["nb_evaluated_roots"], s["nb_skipped_roots"]))
 dt = time.perf_counter() - t0
 print("%s: %d generations in %.2f s = %.1f generations/s (%d roots, fingerprint %016x)" % (app, gens, dt, gens / dt, roots, tr.fingerprint()))

@@ -175,6 +175,22 @@ tpgx_status tpgx_set_observations_pinned(tpgx_ctx* ctx, int32_t source, int32_t 
 tpgx_status tpgx_set_observations_device(tpgx_ctx* ctx, int32_t source, int32_t store,
                                          const void* d_data, const uint8_t* d_labels, int64_t count);
 
+/* ---- multi-GPU: roots shard across the GPUs of one box, per-root score records are combined with ONE
+ * NCCL all-gather that the library enqueues on the evaluation stream (K3 writes the records straight into the collective's
+ * buffer; no host synchronisation between the kernels and the collective).  The library owns the communicator.
+ * Two ways to set it up, as NCCL itself offers:
+ *   - one process per GPU: rank 0 calls tpgx_comm_unique_id, the caller distributes the TPGX_COMM_ID_BYTES by any means
+ *     (MPI, a file, torch.distributed's store), every rank calls tpgx_comm_init on its context;
+ *   - one process, N contexts on N devices (the reference's single-process model): tpgx_comm_init_all.
+ * Sharding convention: with slot = ceil(total_roots / world), rank r evaluates roots [r * slot, min((r + 1) * slot, total)).
+ * NCCL (libnccl.so.2) is loaded at the first of these calls; TPGX_ERR_NCCL when it is missing or reports an error.   */
+#define TPGX_COMM_ID_BYTES 128
+tpgx_status tpgx_comm_unique_id(uint8_t* id);
+tpgx_status tpgx_comm_init(tpgx_ctx* ctx, const uint8_t* id, int32_t rank, int32_t world);
+tpgx_status tpgx_comm_init_all(tpgx_ctx* const* ctxs, int32_t n);
+/* this context's rank / world size (0 / 1 without a communicator) and its root shard of `total_roots`             */
+tpgx_status tpgx_comm_shard(const tpgx_ctx* ctx, int32_t total_roots, int32_t* rank, int32_t* world, int32_t* root_begin, int32_t* root_end);
+
 /* Classification evaluation request: one generation of evaluateAllRoots for a
  * ClassificationLearningEnvironment ([UP] ClassificationLearningAgent::evaluateJob; [REF]
  * mnist/src/mnist.cpp:50-69).  Every root in [root_begin, root_end) classifies the same sample
@@ -401,6 +417,19 @@ tpgx_status tpgx_train_backend_episodes(tpgx_ctx* ctx, const tpgx_episode_reques
 tpgx_status tpgx_train_backend_classification(tpgx_ctx* ctx, const uint8_t* images, int64_t nb_images, int32_t nb_classes,
                                               int64_t actions_per_evaluation, tpgx_train_backend* out);
 void tpgx_train_backend_release(tpgx_train_backend* backend);
+
+/* evaluateAllRoots over all GPUs: this context evaluates its shard of the `total_roots` roots of the graph it was given
+ * (req->root_begin / root_end are ignored: the shard is tpgx_comm_shard's) and the records of ALL roots come back, in root
+ * order, [total_roots][1 + nb_classes] = {mean F1, F1 per class}: records_all (host, may be NULL) after a synchronisation,
+ * or — _device — d_records_all left on the device, ordered on `stream` like tpgx_evaluate_classification_device.
+ * Every rank must make the call (it is a collective).  _all: the single-process form, one request per context.       */
+tpgx_status tpgx_evaluate_classification_allgather(tpgx_ctx* ctx, const tpgx_classif_request* req, int32_t total_roots, double* records_all);
+tpgx_status tpgx_evaluate_classification_allgather_device(tpgx_ctx* ctx, const tpgx_classif_request* req, int32_t total_roots,
+                                                          double* d_records_all, void* stream);
+tpgx_status tpgx_evaluate_classification_allgather_all(tpgx_ctx* const* ctxs, int32_t n, const tpgx_classif_request* req, int32_t total_roots,
+                                                       double* records_all);
+/* number of kernels this library has launched in the calling process so far (bench.py's gpu_launches)               */
+uint64_t tpgx_kernel_launches(void);
 
 /* Direct access to single engine steps (used by parity tests; replaces
  * [UP] ProgramExecutionEngine::executeProgram on an explicit observation batch):
