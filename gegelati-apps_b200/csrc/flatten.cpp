@@ -94,7 +94,7 @@ void tpgx_pool_run(int nt, void (*fn)(int, void*), void* arg) {
 
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
                                const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
-                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out) {
+                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out, const std::vector<uint8_t>* prog_mask) {
     auto fail = [&](tpgx_status st, const std::string& m) { if (err) *err = m; return st; };
     if (!g || !g->program_line_offset || !g->team_edge_offset || !g->edge_program || !g->edge_destination || !g->root_team)
         return fail(TPGX_ERR_BAD_ARG, "tpgx_set_graph: null array in graph");
@@ -137,6 +137,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
         Err& er = errs[w];
         auto bad = [&](tpgx_status st, const std::string& m) { if (er.st == TPGX_OK) { er.st = st; er.msg = m; } };
         for (int p = pb; p < pe && er.st == TPGX_OK; p++) {
+            if (prog_mask && !(*prog_mask)[(size_t)p]) continue; /* not reachable from this context's shard: left empty, never run */
             const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
             const tpgx_line* L = g->lines + b;
             uint8_t* kp = keep.data() + b;
@@ -170,7 +171,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                 live = (live & ~(k1 << l.destination)) | (reads & (0u - k1));
             }
             n_eff[p] = cnt;
-            if (g->intron && er.st == TPGX_OK) {
+            if (g->intron && er.st == TPGX_OK && !prog_mask) {
                 for (int i = 0; i < n; i++)
                     if ((g->intron[b + i] != 0) == (kp[i] != 0)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i)); break; }
             }

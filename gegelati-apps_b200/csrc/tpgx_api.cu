@@ -85,6 +85,7 @@ struct tpgx_ctx {
     DevBuf d_scratch[16], d_work, d_k2_rflags, d_k2_ufirst, d_gather;
     ncclComm_t comm = nullptr;           /* owned; NCCL communicator of this context's rank */
     int comm_rank = 0, comm_world = 1;
+    int flat_root_begin = 0, flat_root_end = -1; /* tpgx_set_graph_sharded: the only roots this context may evaluate (end < 0: all) */
     /* tpgx_set_observations_pinned enqueues its copy / re-tiling / Sobel-plane work on a stream of its own, so that
        the graph uploads that follow on the main stream are not queued behind 47 MB of observations; consumers of the
        tiles wait for obs_ready */
@@ -319,6 +320,8 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     if (req->nb_classes < 1 || req->nb_classes > 16) return fail(ctx, TPGX_ERR_UNSUPPORTED, "nb_classes must be in [1,16]");
     if (req->root_begin < 0 || req->root_end > ctx->flat.nb_roots || req->root_begin >= req->root_end)
         return fail(ctx, TPGX_ERR_BAD_ARG, "root range out of bounds");
+    if (ctx->flat_root_end >= 0 && (req->root_begin < ctx->flat_root_begin || req->root_end > ctx->flat_root_end))
+        return fail(ctx, TPGX_ERR_STATE, "the graph was set with tpgx_set_graph_sharded: only this context's root shard can be evaluated");
     if (!req->sample_index && req->nb_samples > ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples exceeds uploaded observations");
     if (!ctx->labels_dev) return fail(ctx, TPGX_ERR_STATE, "classification needs labels");
     Trace etr("enqueue_classification");
@@ -785,7 +788,11 @@ tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_de
     return TPGX_OK;
 }
 
-tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
+static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only);
+tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, false); }
+tpgx_status tpgx_set_graph_sharded(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, true); }
+
+static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only) {
     if (!ctx) return TPGX_ERR_BAD_ARG;
     if (ctx->opcode.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: instruction table not set");
     if (ctx->src.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: data sources not set");
@@ -793,7 +800,38 @@ tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) {
     std::string msg;
     tpgx_flat_graph f;
     Trace tr("set_graph");
-    tpgx_status st = tpgx_flatten_graph(ctx->cfg, ctx->opcode, ctx->src, g, &f, &msg);
+    /* sharded: only the programs this context's root shard can reach are flattened and encoded (a rank of N pays 1/N of the
+       host work); the rest of the graph stays empty and evaluating a root outside the shard is refused */
+    std::vector<uint8_t> mask;
+    ctx->flat_root_begin = 0; ctx->flat_root_end = -1;
+    if (shard_only && ctx->comm_world > 1 && g && g->nb_roots > 0 && g->nb_teams > 0 && g->nb_programs > 0 && g->team_edge_offset && g->edge_program &&
+        g->edge_destination && g->root_team) {
+        int slot, rb, re;
+        shard_of(ctx, g->nb_roots, &slot, &rb, &re);
+        mask.assign((size_t)g->nb_programs, 0);
+        std::vector<uint8_t> seen((size_t)g->nb_teams, 0);
+        std::vector<int32_t> queue;
+        bool ok = true;
+        for (int r = rb; r < re && ok; r++) {
+            const int t = g->root_team[r];
+            if (t < 0 || t >= g->nb_teams) { ok = false; break; }
+            if (!seen[(size_t)t]) { seen[(size_t)t] = 1; queue.push_back(t); }
+        }
+        for (size_t q = 0; q < queue.size() && ok; q++) {
+            const int t = queue[q];
+            const int eb = g->team_edge_offset[t], ee = g->team_edge_offset[t + 1];
+            if (eb < 0 || ee < eb) { ok = false; break; }
+            for (int e = eb; e < ee; e++) {
+                const int p = g->edge_program[e], d = g->edge_destination[e];
+                if (p < 0 || p >= g->nb_programs || d >= g->nb_teams) { ok = false; break; }
+                mask[(size_t)p] = 1;
+                if (d >= 0 && !seen[(size_t)d]) { seen[(size_t)d] = 1; queue.push_back(d); }
+            }
+        }
+        if (ok) { ctx->flat_root_begin = rb; ctx->flat_root_end = re; }
+        else mask.clear(); /* malformed graph: the full flattener reports it */
+    }
+    tpgx_status st = tpgx_flatten_graph(ctx->cfg, ctx->opcode, ctx->src, g, &f, &msg, nullptr, mask.empty() ? nullptr : &mask);
     if (st != TPGX_OK) return fail(ctx, st, msg);
     tr.lap("flatten");
     ctx->flat = std::move(f);

@@ -218,6 +218,7 @@ static inline int tpgx_parallel_workers() { return 16; }
 /* Validates and flattens; returns TPGX_OK or an error code with a message in err. */
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
                                const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
-                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out = nullptr);
+                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out = nullptr,
+                               const std::vector<uint8_t>* prog_mask = nullptr);
 
 #endif

@@ -4,4 +4,4 @@ from .api import Evaluator, TpgxError, load_library, LIB_PATH, EXPORTS, mnist_ep
 from .graph import (TPGraph, INSTRUCTION_SETS, APP_SOURCES, APP_CONSTANTS, APP_ACTIONS, APP_ENV, import_dot, export_dot,
                     synthetic_graph, synthetic_images, random_programs, address_space, LINE_DTYPE)
 from .train import Trainer, load_params_json, python_backend, episodes_backend, classification_backend
-from .sharding import shard_range, gather_records, records_from
+from .sharding import shard_range, slot_shard, gather_records, records_from

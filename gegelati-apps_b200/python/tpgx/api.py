@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..
 EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table", "tpgx_k1v2_encode_program", "tpgx_k1v2_handler_name", "tpgx_comm_unique_id", "tpgx_comm_init", "tpgx_comm_init_all", "tpgx_comm_shard",
     "tpgx_evaluate_classification_allgather", "tpgx_evaluate_classification_allgather_device", "tpgx_evaluate_classification_allgather_all", "tpgx_kernel_launches",
-    "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
+    "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_graph_sharded", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
     "tpgx_trainer_create", "tpgx_trainer_destroy", "tpgx_trainer_last_error", "tpgx_trainer_graph", "tpgx_trainer_train_generation",
@@ -215,6 +215,13 @@ class Evaluator:
     def set_graph(self, g: TPGraph):
         cs, keep = g.c_struct()
         self._check(self.lib.tpgx_set_graph(self.h, C.byref(cs)))
+        self.graph = g
+
+    def set_graph_sharded(self, g: TPGraph):
+        """tpgx_set_graph_sharded: only what this rank's root shard reaches is flattened and uploaded."""
+        self.lib.tpgx_set_graph_sharded.argtypes = [C.c_void_p, C.POINTER(A.Graph)]
+        cs, self._graph_keep = g.c_struct()
+        self._check(self.lib.tpgx_set_graph_sharded(self.h, C.byref(cs)))
         self.graph = g
 
     def set_observations(self, images_u8, labels=None):

@@ -16,6 +16,15 @@ def shard_range(rank, world, nb_roots):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def slot_shard(rank, world, nb_roots):
+    """The library's own convention (tpgx_comm_shard): slot = ceil(nb_roots / world) roots per rank, rank r evaluates
+    [r * slot, min((r + 1) * slot, nb_roots)) — the gathered buffer is then indexed by the global root number directly."""
+    if not (0 <= rank < world) or nb_roots < 0:
+        raise ValueError("bad shard request")
+    slot = -(-nb_roots // world)
+    return min(nb_roots, rank * slot), min(nb_roots, (rank + 1) * slot)
+
+
 def gather_records(local_records, world, nb_roots, dist=None):
     """All-gathers [n_local, 1 + C] float64 records into [nb_roots, 1 + C] in job-index order.
     Works on torch tensors of any device (NCCL for CUDA tensors, gloo for CPU tensors)."""

@@ -159,6 +159,11 @@ tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_de
  * as seen by [UP] TPGExecutionEngine / ProgramExecutionEngine.  Flattens programs (introns
  * stripped, locations reduced) to packed device bytecode and uploads it with the CSR graph.        */
 tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g);
+/* Same for a context that is one rank of a communicator (tpgx_comm_init*): every rank is handed the WHOLE graph, as every
+ * rank of a replicated host loop has it, but flattens, encodes and uploads only the programs its own root shard
+ * (tpgx_comm_shard of g->nb_roots) can reach — 1/N of the host work per rank.  Evaluating a root outside the shard is then
+ * TPGX_ERR_STATE.  Without a communicator it is tpgx_set_graph.                                                   */
+tpgx_status tpgx_set_graph_sharded(tpgx_ctx* ctx, const tpgx_graph* g);
 
 /* Replaces: the static dataset of [REF] mnist/src/mnist.cpp:6 / the Array2DWrapper pointer swap
  * of MNIST::changeCurrentImage (:8-34).  `data` is sample-major [count][height*width] of `store`

@@ -229,13 +229,18 @@ class LearningAgent {
         const tpgx_graph g = f.view();
         check(ctx, tpgx_set_graph(ctx, &g), "tpgx_set_graph");
         const int NI = (int)params.nbIterationsPerPolicyEvaluation, R = (int)f.roots.size();
-        std::vector<uint64_t> seeds(NI);
-        for (int it = 0; it < NI; it++) seeds[it] = Data::Hash<uint64_t>()(generationNumber) ^ Data::Hash<uint64_t>()((uint64_t)it);
+        std::vector<uint64_t> seeds(NI), rngSeeds(NI);
+        for (int it = 0; it < NI; it++) {
+            seeds[it] = Data::Hash<uint64_t>()(generationNumber) ^ Data::Hash<uint64_t>()((uint64_t)it);
+            /* what the environment's reset() hands to rng.setSeed() ([REF] pendulum/src/Learn/pendulum.cpp:45-48), computed here with the
+               linked library's Data::Hash so that libtpgx does not have to know it */
+            rngSeeds[it] = (uint64_t)(Data::Hash<size_t>()((size_t)seeds[it]) ^ Data::Hash<Learn::LearningMode>()(mode));
+        }
         std::vector<int32_t> jobRoots(R);
         for (int r = 0; r < R; r++) jobRoots[r] = r;
         tpgx_episode_request rq{};
         rq.env = kind; rq.mode = (int32_t)mode; rq.nb_iterations = NI; rq.max_actions = (int32_t)params.maxNbActionsPerEval;
-        rq.seeds = seeds.data(); rq.nb_jobs = R; rq.roots_per_job = 1; rq.job_roots = jobRoots.data();
+        rq.seeds = seeds.data(); rq.rng_seeds = rngSeeds.data(); rq.nb_jobs = R; rq.roots_per_job = 1; rq.job_roots = jobRoots.data();
         rq.second_player_random = secondPlayerRandom;
         rq.nb_pendulum_actions = (int32_t)pendulumActions.size(); rq.pendulum_actions = pendulumActions.data();
         std::vector<double> score(R);
@@ -326,6 +331,200 @@ class ClassificationAgent {
         }
         return results;
     }
+};
+
+/* ---- the training surface the apps call ------------------------------------------------------------
+ * [REF] gridworld/src/main.cpp:34-36,63,68,79 / pendulum/src/Learn/main.cpp:38-39,83,88,96 (v2 spelling) and
+ * stickgame/src/Learn/main.cpp:70,81 (old spelling): init(), trainOneGeneration(i), getTPGGraph(),
+ * getSelector()->{getBestRoot, keepBestPolicy}, getBestRoot(), keepBestPolicy().  The generation loop itself is
+ * libtpgx's host trainer (tpgx_trainer_*: populate / evaluate / archive / skip-and-merge / decimate / validation) with
+ * every evaluation on the GPU; this class owns the trainer, feeds it the GPU backend and keeps the GEGELATI-side
+ * TPG::TPGGraph object (the one exporters and loggers hold a reference to) in step with it.                         */
+inline tpgx_env_kind envKindOf(const Learn::LearningEnvironment& le) {
+    const std::string n = typeid(le).name(); /* the mangled name holds the class name */
+    if (n.find("GridWorld") != std::string::npos) return TPGX_ENV_GRIDWORLD;
+    if (n.find("Pendulum") != std::string::npos) return TPGX_ENV_PENDULUM;
+    if (n.find("StickGame") != std::string::npos) return TPGX_ENV_STICKGAME;
+    if (n.find("TicTacToe") != std::string::npos) return TPGX_ENV_TICTACTOE;
+    throw std::runtime_error("tpgx: no device restatement of LearningEnvironment " + n + " (no CPU fallback)");
+}
+
+class TrainingAgent : public LearningAgent {
+    tpgx_trainer* trainer = nullptr;
+    tpgx_train_backend backend{};
+    std::vector<tpgx_source_desc> sources;
+    std::vector<int32_t> opcodes;
+    int obsLen = 0;
+    std::ostream* log = nullptr;
+    tpgx_train_stats last{};
+    std::vector<const TPG::TPGVertex*> rootVertex; /* GEGELATI-side vertex of every current root, in root order */
+
+    /* backend callbacks: evaluateAllRoots(generation, mode) on the GPU with upstream's seed derivation */
+    static tpgx_status evaluateCb(void* user, const tpgx_graph* g, uint64_t generation, int32_t mode, const uint64_t* archiveSeed, double probability,
+                                  int32_t archiveSize, double* scores, int32_t, double*, uint64_t*, int32_t* recProgram, double* recBid, double* recObs,
+                                  int32_t obsLen_, int32_t* nbRecords) {
+        TrainingAgent* a = static_cast<TrainingAgent*>(user);
+        tpgx_status st = tpgx_set_graph(a->ctx, g);
+        if (st != TPGX_OK) return st;
+        const int R = g->nb_roots, NI = (int)a->params.nbIterationsPerPolicyEvaluation;
+        std::vector<int32_t> jobRoots((size_t)R);
+        for (int j = 0; j < R; j++) jobRoots[j] = j;
+        std::vector<uint64_t> seeds((size_t)NI), rngSeeds((size_t)NI);
+        for (int it = 0; it < NI; it++) {
+            seeds[it] = Data::Hash<uint64_t>()(generation) ^ Data::Hash<uint64_t>()((uint64_t)it);
+            rngSeeds[it] = (uint64_t)(Data::Hash<size_t>()((size_t)seeds[it]) ^ Data::Hash<Learn::LearningMode>()((Learn::LearningMode)mode));
+        }
+        tpgx_episode_request rq{};
+        rq.env = a->kind; rq.mode = mode; rq.nb_iterations = NI; rq.max_actions = (int32_t)a->params.maxNbActionsPerEval;
+        rq.seeds = seeds.data(); rq.rng_seeds = rngSeeds.data(); rq.nb_jobs = R; rq.roots_per_job = 1; rq.job_roots = jobRoots.data();
+        rq.second_player_random = a->secondPlayerRandom;
+        rq.nb_pendulum_actions = (int32_t)a->pendulumActions.size(); rq.pendulum_actions = a->pendulumActions.data();
+        tpgx_episode_result ev{};
+        ev.score = scores;
+        *nbRecords = 0;
+        if (archiveSize <= 0 || probability == 0.0 || mode != 0) return tpgx_evaluate_episodes(a->ctx, &rq, &ev);
+        const size_t cap = (size_t)archiveSize;
+        std::vector<int32_t> job(cap), iteration(cap), step(cap);
+        tpgx_archive_request ar{archiveSeed, probability, archiveSize, 0};
+        tpgx_episode_archive_result out{recProgram, job.data(), iteration.data(), step.data(), recBid, recObs, obsLen_, 0};
+        st = tpgx_archive_episodes(a->ctx, &rq, &ar, &ev, &out);
+        *nbRecords = out.nb_records;
+        return st;
+    }
+    static tpgx_status executeCb(void* user, const tpgx_graph* g, int64_t count, const double* obs, int32_t obsLen_, double* bid) {
+        TrainingAgent* a = static_cast<TrainingAgent*>(user);
+        tpgx_status st = tpgx_set_graph(a->ctx, g);
+        if (st != TPGX_OK) return st;
+        std::vector<std::vector<double>> f(a->sources.size());
+        std::vector<std::vector<int32_t>> iv(a->sources.size());
+        const double* pf[2] = {nullptr, nullptr};
+        const int32_t* pi[2] = {nullptr, nullptr};
+        int col = 0;
+        for (size_t k = 0; k < a->sources.size(); k++) { /* archived observation rows -> one array per data source */
+            const int sp = a->sources[k].height * a->sources[k].width;
+            if (a->sources[k].elem == TPGX_ELEM_F64) {
+                f[k].resize((size_t)count * sp);
+                for (int64_t i = 0; i < count; i++) for (int q = 0; q < sp; q++) f[k][(size_t)i * sp + q] = obs[(size_t)i * obsLen_ + col + q];
+                pf[k] = f[k].data();
+            } else {
+                iv[k].resize((size_t)count * sp);
+                for (int64_t i = 0; i < count; i++) for (int q = 0; q < sp; q++) iv[k][(size_t)i * sp + q] = (int32_t)obs[(size_t)i * obsLen_ + col + q];
+                pi[k] = iv[k].data();
+            }
+            col += sp;
+        }
+        return tpgx_execute_programs(a->ctx, count, pf, pi, bid);
+    }
+    void checkTrainer(tpgx_status st, const char* where) const {
+        if (st != TPGX_OK) throw std::runtime_error(std::string(where) + ": " + (trainer ? tpgx_trainer_last_error(trainer) : "no trainer") + " / " + tpgx_last_error(ctx));
+    }
+    /* the trainer's graph -> the GEGELATI-side graph object, rebuilt in place (vertices in creation order: teams, then actions) */
+    void syncGraph() {
+        tpgx_graph v{};
+        checkTrainer(tpgx_trainer_graph(trainer, &v), "tpgx_trainer_graph");
+        tpg->clear();
+        std::vector<TPG::TPGTeam*> team((size_t)v.nb_teams);
+        for (int t = 0; t < v.nb_teams; t++) team[t] = &tpg->addNewTeam();
+        std::map<int, const TPG::TPGAction*> action;
+        std::vector<std::shared_ptr<Program::Program>> prog((size_t)v.nb_programs);
+        const size_t nc = env.getNbConstant();
+        for (int p = 0; p < v.nb_programs; p++) {
+            prog[p] = std::make_shared<Program::Program>(env);
+            for (int64_t l = v.program_line_offset[p]; l < v.program_line_offset[p + 1]; l++) {
+                Program::Line& L = prog[p]->addNewLine();
+                L.setInstructionIndex(v.lines[l].instruction);
+                L.setDestinationIndex(v.lines[l].destination);
+                L.setOperand(0, v.lines[l].src[0], v.lines[l].loc[0]);
+                L.setOperand(1, v.lines[l].src[1], v.lines[l].loc[1]);
+            }
+            for (size_t c = 0; c < nc; c++) prog[p]->setConstantAt(c, v.constants[(size_t)p * nc + c]);
+        }
+        for (int t = 0; t < v.nb_teams; t++)
+            for (int e = v.team_edge_offset[t]; e < v.team_edge_offset[t + 1]; e++) {
+                const int d = v.edge_destination[e];
+                const TPG::TPGVertex* dst;
+                if (d >= 0) dst = team[d];
+                else {
+                    auto it = action.find(-1 - d);
+                    if (it == action.end()) it = action.emplace(-1 - d, &tpg->addNewAction((uint64_t)(-1 - d))).first;
+                    dst = it->second;
+                }
+                tpg->addNewEdge(*team[t], *dst, prog[v.edge_program[e]]);
+            }
+        rootVertex.clear();
+        for (int r = 0; r < v.nb_roots; r++) rootVertex.push_back(team[v.root_team[r]]);
+        tpg->setRootVertices(rootVertex);
+    }
+
+  public:
+    TrainingAgent(Learn::LearningEnvironment& le, const Instructions::Set& set, const Learn::LearningParameters& p, int tieBreak = TPGX_TIE_LAST_MAX)
+        : LearningAgent(le, set, p, envKindOf(le), tieBreak) {
+        opcodes = fingerprint(set);
+        for (const Data::DataHandler& dh : le.getDataSources()) {
+            const size_t nd = dh.getAddressSpace(typeid(double)), ni = dh.getAddressSpace(typeid(int));
+            sources.push_back(tpgx_source_desc{nd ? TPGX_ELEM_F64 : TPGX_ELEM_I32, 1, (int32_t)(nd ? nd : ni), 0});
+            obsLen += (int)(nd ? nd : ni);
+        }
+        backend.user = this; backend.evaluate = &TrainingAgent::evaluateCb; backend.execute = &TrainingAgent::executeCb;
+    }
+    ~TrainingAgent() { if (trainer) tpgx_trainer_destroy(trainer); }
+
+    /* [UP] LearningAgent::init(seed): RNG seeded, initRandomTPG */
+    void init(uint64_t seed = 0) {
+        if (trainer) { tpgx_trainer_destroy(trainer); trainer = nullptr; }
+        tpgx_config cfg{};
+        cfg.device = 0; cfg.nb_registers = (int32_t)params.nbRegisters; cfg.nb_constants = (int32_t)params.nbProgramConstant; cfg.tie_break = TPGX_TIE_LAST_MAX;
+        const auto& mt = params.mutation.tpg;
+        const auto& mp = params.mutation.prog;
+        tpgx_train_params tp{};
+        tp.nb_actions = (int32_t)learningEnvironment.getNbActions(); tp.nb_roots = (int32_t)mt.nbRoots;
+        tp.max_init_outgoing_edges = (int32_t)mt.maxInitOutgoingEdges; tp.max_outgoing_edges = (int32_t)mt.maxOutgoingEdges;
+        tp.p_edge_deletion = mt.pEdgeDeletion; tp.p_edge_addition = mt.pEdgeAddition; tp.p_program_mutation = mt.pProgramMutation;
+        tp.p_edge_destination_change = mt.pEdgeDestinationChange; tp.p_edge_destination_is_action = mt.pEdgeDestinationIsAction;
+        tp.force_program_behavior_change = mt.forceProgramBehaviorChangeOnMutation ? 1 : 0;
+        tp.max_program_size = (int32_t)mp.maxProgramSize; tp.p_delete = mp.pDelete; tp.p_add = mp.pAdd; tp.p_mutate = mp.pMutate; tp.p_swap = mp.pSwap;
+        tp.p_constant_mutation = mp.pConstantMutation; tp.min_const_value = (int32_t)mp.minConstValue; tp.max_const_value = (int32_t)mp.maxConstValue;
+        tp.ratio_deleted_roots = params.ratioDeletedRoots; tp.archive_size = (int32_t)params.archiveSize; tp.archiving_probability = params.archivingProbability;
+        tp.max_nb_evaluation_per_policy = (int32_t)params.maxNbEvaluationPerPolicy; tp.do_validation = params.doValidation ? 1 : 0;
+        tp.nb_iterations_per_policy_evaluation = (int32_t)params.nbIterationsPerPolicyEvaluation; tp.nb_classes = 0;
+        checkTrainer(tpgx_trainer_create(&cfg, (int32_t)opcodes.size(), opcodes.data(), (int32_t)sources.size(), sources.data(), &tp, seed, &trainer), "tpgx_trainer_create");
+        syncGraph();
+    }
+    /* [UP] LearningAgent::trainOneGeneration */
+    void trainOneGeneration(uint64_t generationNumber) {
+        if (!trainer) throw std::runtime_error("tpgx::TrainingAgent::trainOneGeneration: init() has not been called");
+        checkTrainer(tpgx_trainer_train_generation(trainer, &backend, generationNumber, &last), "tpgx_trainer_train_generation");
+        syncGraph();
+        if (log) {
+            char buf[256];
+            snprintf(buf, sizeof buf, "%6llu %6d %8d %12.4f %12.4f %12.4f %6d %6d %016llx\n", (unsigned long long)generationNumber, last.nb_teams, last.nb_programs,
+                     last.worst_score, last.mean_score, last.best_score, last.nb_evaluated_roots, last.nb_skipped_roots, (unsigned long long)tpgx_trainer_fingerprint(trainer));
+            *log << buf << std::flush;
+        }
+    }
+    const tpgx_train_stats& getLastStats() const { return last; }
+    uint64_t fingerprintOfGraph() const { return trainer ? tpgx_trainer_fingerprint(trainer) : 0; }
+    void logTo(std::ostream* os) {
+        log = os;
+        if (log) *log << "   Gen  Teams Programs          Min          Avg          Max   Jobs Skipped      Fingerprint\n";
+    }
+    /* [UP] getBestRoot(): (vertex, its stored result) */
+    std::pair<const TPG::TPGVertex*, std::shared_ptr<Learn::EvaluationResult>> getBestRoot() const {
+        int32_t idx = -1;
+        double score = 0.0;
+        if (!trainer || tpgx_trainer_best_root(trainer, &idx, &score) != TPGX_OK || idx < 0 || idx >= (int32_t)rootVertex.size()) return {nullptr, nullptr};
+        std::vector<double> sc(rootVertex.size());
+        std::vector<uint64_t> ne(rootVertex.size());
+        tpgx_trainer_root_results(trainer, sc.data(), ne.data(), (int32_t)sc.size());
+        return {rootVertex[(size_t)idx], std::make_shared<Learn::EvaluationResult>(score, (size_t)ne[(size_t)idx])};
+    }
+    /* [UP] keepBestPolicy() */
+    void keepBestPolicy() {
+        checkTrainer(tpgx_trainer_keep_best_policy(trainer), "tpgx_trainer_keep_best_policy");
+        syncGraph();
+    }
+    /* v2 spelling: la.getSelector()->getBestRoot() / keepBestPolicy() */
+    TrainingAgent* getSelector() { return this; }
 };
 
 } // namespace tpgx

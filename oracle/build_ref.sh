@@ -67,5 +67,16 @@ if [ -f "$LIBDIR/libtpgx.so" ]; then
       -L"$LIBDIR" -ltpgx -Wl,-rpath,'$ORIGIN/../../gegelati-apps_b200/lib'
   echo "built $OUT/adapter_driver"
 fi
+# The gridworld app's own main.cpp, UNMODIFIED ([REF] gridworld/src/main.cpp), against the shim + the C++ adapter: its
+# Learn::ParallelLearningAgent is the GPU-backed agent (init / trainOneGeneration / getSelector()->keepBestPolicy / getBestRoot).
+# ROOT_DIR "." : the test runs it in a scratch directory next to a copy of the app's params.json (kept under _ref/).
+if [ -f "$LIBDIR/libtpgx.so" ]; then
+  mkdir -p "$OUT/gridworld_app"
+  cp "$REF/gridworld/params.json" "$OUT/gridworld_app/params.json"
+  "$CXX" $FLAGS -I"$HERE/../include" -DTPGX_SHIM_WITH_AGENT -DNO_CONSOLE_CONTROL -DROOT_DIR='"."' \
+      "$REF/gridworld/src/main.cpp" "$REF/gridworld/src/gridworld.cpp" "$REF/gridworld/src/instructions.cpp" -o "$OUT/gridworld_main" \
+      -L"$LIBDIR" -ltpgx -Wl,-rpath,'$ORIGIN/../../gegelati-apps_b200/lib'
+  echo "built $OUT/gridworld_main"
+fi
 rm -f "$OUT"/*.o
 echo "built $OUT/libtpgref.so"

@@ -301,6 +301,7 @@ class TPGGraph {
     void setRootVertices(const std::vector<const TPGVertex*>& r) { roots = r; }
     const std::vector<const TPGVertex*>& getRootVertices() const { return roots; }
     void clearProgramIntrons() {}
+    void clear() { roots.clear(); edges.clear(); vertices.clear(); } /* [UP] TPGGraph::clear() */
 };
 } // namespace TPG
 class Archive;
@@ -466,10 +467,24 @@ class ClassificationEvaluationResult : public EvaluationResult {
     const std::vector<size_t>& getNbEvaluationPerClass() const { return nbEvaluationPerClass; }
 };
 
-struct LearningParameters {   /* the fields evaluation reads (the apps' params.json files) */
-    size_t nbRegisters = 8, nbProgramConstant = 0;
-    uint64_t maxNbActionsPerEval = 1000, nbIterationsPerPolicyEvaluation = 5, nbIterationsPerJob = 1;
+struct TPGParameters {   /* [UP] Mutator::TPGParameters, the keys of "mutation": {"tpg": {...}} */
+    size_t nbRoots = 100, maxInitOutgoingEdges = 3, maxOutgoingEdges = 5;
+    double pEdgeDeletion = 0.7, pEdgeAddition = 0.7, pProgramMutation = 0.2, pEdgeDestinationChange = 0.1, pEdgeDestinationIsAction = 0.5;
+    bool forceProgramBehaviorChangeOnMutation = false;
+};
+struct ProgramParameters {   /* [UP] Mutator::ProgramParameters, "mutation": {"prog": {...}} */
+    size_t maxProgramSize = 96;
+    double pDelete = 0.5, pAdd = 0.5, pMutate = 1.0, pSwap = 1.0, pConstantMutation = 0.5;
+    int32_t minConstValue = -100, maxConstValue = 100;
+};
+struct MutationParameters { TPGParameters tpg; ProgramParameters prog; };
+struct LearningParameters {   /* the fields the apps' params.json files set */
+    MutationParameters mutation;
+    size_t nbRegisters = 8, nbProgramConstant = 0, archiveSize = 50;
+    double archivingProbability = 0.05, ratioDeletedRoots = 0.5;
+    uint64_t maxNbActionsPerEval = 1000, nbIterationsPerPolicyEvaluation = 5, nbIterationsPerJob = 1, maxNbEvaluationPerPolicy = 1000;
     uint64_t nbGenerations = 1, nbThreads = 1;
+    bool doValidation = false;
 };
 
 class AdversarialEvaluationResult : public EvaluationResult {
@@ -488,5 +503,96 @@ class AdversarialLearningEnvironment : public LearningEnvironment {
 };
 
 } // namespace Learn
+
+/* ---- scaffolding for compiling an app's main.cpp UNMODIFIED ([REF] gridworld/src/main.cpp): parameter file reader, graph
+ * exporter, loggers and policy statistics are upstream subsystems that are out of scope; what follows is the
+ * least that lets the unmodified main() compile and run, with Learn::ParallelLearningAgent standing for the GPU-backed agent
+ * of include/tpgx_gegelati.hpp (in a real GEGELATI build the maintainer subclasses / patches ParallelLearningAgent instead:
+ * INTEGRATION.md).  Enabled by -DTPGX_SHIM_WITH_AGENT. */
+#ifdef TPGX_SHIM_WITH_AGENT
+#include "tpgx_gegelati.hpp"
+namespace Learn {
+using LearningAgent = tpgx::TrainingAgent;
+using ParallelLearningAgent = tpgx::TrainingAgent;
+} // namespace Learn
+namespace File {
+class ParametersParser {
+    static std::string strip(const std::string& in) { /* the apps' params.json files carry C and C++ comments */
+        std::string out;
+        for (size_t i = 0; i < in.size();) {
+            if (in.compare(i, 2, "/*") == 0) { const size_t e = in.find("*/", i + 2); i = e == std::string::npos ? in.size() : e + 2; }
+            else if (in.compare(i, 2, "//") == 0) { const size_t e = in.find('\n', i); i = e == std::string::npos ? in.size() : e; }
+            else out += in[i++];
+        }
+        return out;
+    }
+    static bool find(const std::string& txt, const std::string& key, std::string* val) {
+        const size_t k = txt.find("\"" + key + "\"");
+        if (k == std::string::npos) return false;
+        size_t c = txt.find(':', k);
+        if (c == std::string::npos) return false;
+        c++;
+        while (c < txt.size() && isspace((unsigned char)txt[c])) c++;
+        size_t e = c;
+        while (e < txt.size() && txt[e] != ',' && txt[e] != '}' && txt[e] != '\n') e++;
+        *val = txt.substr(c, e - c);
+        return true;
+    }
+    template <class T> static void num(const std::string& txt, const char* key, T& field) {
+        std::string v;
+        if (!find(txt, key, &v)) return;
+        if (v.find("true") != std::string::npos) field = (T)1;
+        else if (v.find("false") != std::string::npos) field = (T)0;
+        else field = (T)std::stod(v);
+    }
+  public:
+    static void loadParametersFromJson(const char* path, Learn::LearningParameters& p) {
+        std::ifstream f(path);
+        if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+        std::stringstream ss;
+        ss << f.rdbuf();
+        const std::string t = strip(ss.str());
+        num(t, "archiveSize", p.archiveSize); num(t, "archivingProbability", p.archivingProbability); num(t, "doValidation", p.doValidation);
+        num(t, "maxNbActionsPerEval", p.maxNbActionsPerEval); num(t, "maxNbEvaluationPerPolicy", p.maxNbEvaluationPerPolicy);
+        num(t, "nbGenerations", p.nbGenerations); num(t, "nbIterationsPerPolicyEvaluation", p.nbIterationsPerPolicyEvaluation);
+        num(t, "nbIterationsPerJob", p.nbIterationsPerJob); num(t, "nbProgramConstant", p.nbProgramConstant); num(t, "nbRegisters", p.nbRegisters);
+        num(t, "nbThreads", p.nbThreads); num(t, "ratioDeletedRoots", p.ratioDeletedRoots);
+        auto& g = p.mutation.tpg;
+        num(t, "nbRoots", g.nbRoots); num(t, "maxInitOutgoingEdges", g.maxInitOutgoingEdges); num(t, "maxOutgoingEdges", g.maxOutgoingEdges);
+        num(t, "pEdgeDeletion", g.pEdgeDeletion); num(t, "pEdgeAddition", g.pEdgeAddition); num(t, "pProgramMutation", g.pProgramMutation);
+        num(t, "pEdgeDestinationChange", g.pEdgeDestinationChange); num(t, "pEdgeDestinationIsAction", g.pEdgeDestinationIsAction);
+        num(t, "forceProgramBehaviorChangeOnMutation", g.forceProgramBehaviorChangeOnMutation);
+        auto& m = p.mutation.prog;
+        num(t, "maxProgramSize", m.maxProgramSize); num(t, "pDelete", m.pDelete); num(t, "pAdd", m.pAdd); num(t, "pMutate", m.pMutate); num(t, "pSwap", m.pSwap);
+        num(t, "pConstantMutation", m.pConstantMutation); num(t, "minConstValue", m.minConstValue); num(t, "maxConstValue", m.maxConstValue);
+    }
+    static void writeParametersToJson(const char*, const Learn::LearningParameters&) {}
+};
+class TPGGraphDotExporter { /* writes vertex / edge counts only: the product's exporter is python/tpgx/graph.py export_dot */
+    std::string path;
+    const TPG::TPGGraph& graph;
+  public:
+    TPGGraphDotExporter(const char* p, const TPG::TPGGraph& g) : path(p), graph(g) {}
+    void setNewFilePath(const char* p) { path = p; }
+    void print() {
+        std::ofstream f(path);
+        f << "// stand-in exporter: " << graph.getVertices().size() << " vertices, " << graph.getRootVertices().size() << " roots\n";
+    }
+};
+} // namespace File
+namespace Log {
+class LABasicLogger { public: explicit LABasicLogger(Learn::LearningAgent& la, std::ostream& os = std::cout) { la.logTo(&os); } };
+class LAPolicyStatsLogger { public: LAPolicyStatsLogger(Learn::LearningAgent&, std::ostream&) {} };
+} // namespace Log
+namespace TPG {
+class PolicyStats {
+    const TPGVertex* root = nullptr;
+  public:
+    void setEnvironment(const Environment&) {}
+    void analyzePolicy(const TPGVertex* r) { root = r; }
+    friend std::ostream& operator<<(std::ostream& os, const PolicyStats& ps) { return os << "policy root " << (ps.root ? "set" : "missing") << "\n"; }
+};
+} // namespace TPG
+#endif
 
 #endif

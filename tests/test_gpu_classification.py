@@ -54,8 +54,20 @@ def test_bids_actions_scores_bit_exact(oracle_mod, mix, depth, tie):
 def test_ragged_and_empty_programs(oracle_mod):
     """Programs of different lengths, including empty ones (bid 0.0, Appendix F U5), and a sample count that is
     not a multiple of the tile."""
-    g, ev = make(roots=16, edges=4, lines=6, depth=2, seed=3, line_jitter=6, intron_lines=2)
-    assert (np.diff(g.program_line_offset) == 0).any(), "the generator must have produced at least one empty program"
+    g, _ = make(roots=16, edges=4, lines=6, depth=2, seed=3, line_jitter=6, intron_lines=2)
+    # programs 0 and 5 lose all their lines, program 9 keeps only introns (a line writing a register nobody reads)
+    off = g.program_line_offset
+    keep = np.ones(len(g.lines), dtype=bool)
+    for p_ in (0, 5):
+        keep[off[p_]:off[p_ + 1]] = False
+    keep[off[9] + 1:off[10]] = False
+    g.lines["destination"][off[9]] = 3
+    counts = np.add.reduceat(keep.astype(np.int64), off[:-1])
+    g = tpgx.TPGraph(lines=g.lines[keep], program_line_offset=np.concatenate([[0], np.cumsum(counts)]).astype(np.int64), constants=g.constants,
+                     team_edge_offset=g.team_edge_offset, edge_program=g.edge_program, edge_destination=g.edge_destination, root_team=g.root_team)
+    assert (np.diff(g.program_line_offset) == 0).sum() == 2
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+    ev.set_graph(g)
     img, lab = tpgx.synthetic_images(77, seed=9)
     ev.set_observations(img, lab)
     want = ("score", "confusion", "action", "bid", "counters")

@@ -80,3 +80,32 @@ def test_mnist_reference_environment_and_main_set_drive_the_gpu_classifier(oracl
         img, lab, sample_index=idx.astype(np.int32), want=("score", "class_f1"))
     assert np.array_equal(f1.view(np.uint64), ref["class_f1"].view(np.uint64))
     assert np.allclose(score, ref["score"], rtol=0, atol=1e-15)   # the result object averages the 10 F1 values itself
+
+
+GRID_MAIN = os.path.join(ROOT, "oracle", "_ref", "gridworld_main")
+GRID_PARAMS = os.path.join(ROOT, "oracle", "_ref", "gridworld_app", "params.json")
+
+
+@pytest.mark.skipif(not (os.path.exists(GRID_MAIN) and os.path.exists(GRID_PARAMS)), reason="oracle/_ref/gridworld_main not built (needs /root/reference at build time)")
+def test_the_gridworld_apps_own_main_runs_unmodified_on_the_gpu_agent(tmp_path):
+    """[REF] gridworld/src/main.cpp compiled UNMODIFIED (oracle/build_ref.sh) with Learn::ParallelLearningAgent standing for
+    tpgx::TrainingAgent: la.init(), params.nbGenerations x la.trainOneGeneration(i), la.getSelector()->keepBestPolicy(),
+    getBestRoot() — its params.json as is (500 roots, archive 2000 @ 0.01, maxNbEvaluationPerPolicy 10, 10 generations).
+    The logger's per-generation lines (statistics + graph fingerprint) must equal the Python-driven trainer's."""
+    import shutil
+    shutil.copy(GRID_PARAMS, tmp_path / "params.json")
+    out = subprocess.run([GRID_MAIN], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    rows = [ln.split() for ln in out.stdout.splitlines() if ln.strip() and ln.split()[0].isdigit()]
+    p = tpgx.load_params_json(str(tmp_path / "params.json"), nb_actions=4)
+    assert len(rows) == p["nb_generations"] == 10
+    tr = tpgx.Trainer(tpgx.INSTRUCTION_SETS["gridworld"], tpgx.APP_SOURCES["gridworld"], p, nb_registers=p["nb_registers"], nb_constants=p["nb_constants"], seed=0)
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["gridworld"], tpgx.APP_SOURCES["gridworld"], nb_registers=p["nb_registers"], nb_constants=p["nb_constants"])
+    be = tpgx.episodes_backend(ev, A.ENV_GRIDWORLD, nb_iterations=p["nb_iterations"], max_actions=p["max_actions"])
+    for gen, row in enumerate(rows):
+        st = tr.train_generation(be, gen)
+        assert int(row[0]) == gen and int(row[1]) == st["nb_teams"] and int(row[2]) == st["nb_programs"]
+        assert float(row[5]) == pytest.approx(st["best_score"], abs=1e-3) and int(row[6]) == st["nb_evaluated_roots"] and int(row[7]) == st["nb_skipped_roots"]
+        assert int(row[8], 16) == tr.fingerprint(), gen
+    # keepBestPolicy + exports ran: the app's output files exist
+    assert (tmp_path / "out_best.dot").exists() and (tmp_path / "out_best_stats.md").read_text().startswith("policy root set")

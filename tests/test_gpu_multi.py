@@ -56,3 +56,28 @@ def test_allgather_without_a_communicator_is_the_single_gpu_evaluation():
     assert ev.comm_shard(20) == (0, 1, 0, 20)
     assert np.array_equal(a["score"].view(np.uint64), b["score"].view(np.uint64)) and np.array_equal(a["class_f1"], b["class_f1"])
     assert tpgx.kernel_launches() > 0
+
+
+def test_sharded_set_graph_flattens_only_the_shard_and_refuses_other_roots():
+    n = device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    roots = 64
+    g = tpgx.synthetic_graph("mnist", roots=roots, edges=5, lines=20, depth=2, share_prob=0.1, seed=21)
+    img, lab = tpgx.synthetic_images(700, seed=4)
+    single = evaluator(g, img, lab, 0).evaluate_classification(want=("score", "class_f1"))
+    evs = [evaluator(g, img, lab, d) for d in range(2)]
+    tpgx.comm_init_all(evs)
+    for e in evs:
+        e.set_graph_sharded(g)
+    out = tpgx.evaluate_classification_allgather_all(evs, roots, len(img))
+    assert np.array_equal(out["score"].view(np.uint64), single["score"].view(np.uint64))
+    assert np.array_equal(out["class_f1"].view(np.uint64), single["class_f1"].view(np.uint64))
+    _, _, rb, re = evs[1].comm_shard(roots)
+    own = evs[1].evaluate_classification(root_begin=rb, root_end=re, want=("score",))["score"]
+    assert np.array_equal(own.view(np.uint64), single["score"][rb:re].view(np.uint64))
+    with pytest.raises(tpgx.TpgxError) as err:
+        evs[1].evaluate_classification(root_begin=0, root_end=4, want=("score",))
+    assert err.value.status == tpgx.abi.ERR_STATE
+    evs[1].set_graph(g)                                  # the plain call lifts the restriction
+    assert np.array_equal(evs[1].evaluate_classification(root_begin=0, root_end=4, want=("score",))["score"], single["score"][:4])

@@ -23,6 +23,17 @@ def test_shard_ranges_partition_the_roots():
         tpgx.shard_range(2, 2, 10)
 
 
+def test_slot_shards_of_the_library_partition_the_roots_and_index_the_gather_buffer():
+    """tpgx_comm_shard's convention (restated in tpgx.slot_shard): equal slots, so that rank r's records sit at their global
+    root numbers in the all-gathered buffer; trailing ranks may be short or empty."""
+    for n in (1, 7, 8, 13, 2000, 8192):
+        for world in (1, 2, 3, 8):
+            r = [tpgx.slot_shard(k, world, n) for k in range(world)]
+            slot = -(-n // world)
+            assert r[0][0] == 0 and r[-1][1] == n and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            assert all(b == min(n, k * slot) and e - b <= slot for k, (b, e) in enumerate(r))
+
+
 def _worker(rank, world, port, nb_roots, out_dir):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gegelati-apps_b200", "python"))
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
