@@ -80,7 +80,7 @@ struct tpgx_ctx {
     std::vector<uint8_t> v2_slots;    /* per program: shared-memory slots it needs there */
 
     DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
-    DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active;
+    DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active, d_edge_prog;
     DevBuf d_obs_raw, d_labels_raw, d_tiles, d_labels, d_index, d_bid, d_conf, d_records, d_action, d_counters, d_status;
     DevBuf d_scratch[16], d_work, d_k2_rflags, d_k2_ufirst, d_gather;
     ncclComm_t comm = nullptr;           /* owned; NCCL communicator of this context's rank */
@@ -100,6 +100,7 @@ struct tpgx_ctx {
     int tiles_ts = 0;
     ShardPlan plan;
     std::vector<int32_t> h_edge_row, h_active;
+    std::vector<uint8_t> h_stage_in, h_stage_out; /* episode calls: one transfer each way */
 
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); }
@@ -746,7 +747,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     DevBuf* all[] = {&ctx->d_pixel_lut, &ctx->d_sobel, &ctx->d_tm_team, &ctx->d_tm_dst, &ctx->d_tm_stat, &ctx->d_tm_roots, &ctx->d_decision, &ctx->d_code, &ctx->d_k1_stream, &ctx->d_k1_desc, &ctx->d_prog_off, &ctx->d_consts, &ctx->d_team_off, &ctx->d_edge_dst, &ctx->d_edge_row,
                      &ctx->d_edge_lines, &ctx->d_roots, &ctx->d_active, &ctx->d_obs_raw, &ctx->d_labels_raw, &ctx->d_tiles,
                      &ctx->d_labels, &ctx->d_index, &ctx->d_bid, &ctx->d_conf, &ctx->d_records, &ctx->d_action,
-                     &ctx->d_counters, &ctx->d_status, &ctx->d_work, &ctx->d_k2_rflags, &ctx->d_k2_ufirst, &ctx->d_gather};
+                     &ctx->d_counters, &ctx->d_status, &ctx->d_work, &ctx->d_k2_rflags, &ctx->d_k2_ufirst, &ctx->d_gather, &ctx->d_edge_prog};
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : ctx->d_scratch) b.release();
     tpgx_comm_release(ctx);
@@ -868,6 +869,7 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
     if ((st = upload(ctx, ctx->d_team_off, F.team_edge_offset.data(), F.team_edge_offset.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_dst, F.edge_destination.data(), F.edge_destination.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_lines, edge_lines.data(), edge_lines.size() * 4)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_edge_prog, F.edge_program.data(), F.edge_program.size() * 4)) != TPGX_OK) return st;
     CU(cudaStreamSynchronize(ctx->stream));
     tr.lap("uploads");
     ctx->graph_version++;
@@ -1143,90 +1145,99 @@ static tpgx_status episodes_impl(tpgx_ctx* ctx, const tpgx_episode_request* req,
     std::vector<uint64_t> raw((size_t)NI * TPGX_RNG_TABLE);
     for (int it = 0; it < NI; it++)
         tpgx_rng_fill_raw(req->rng_seeds ? req->rng_seeds[it] : tpgx_env_seed(req->seeds[it], req->mode), TPGX_RNG_TABLE, raw.data() + (size_t)it * TPGX_RNG_TABLE);
-    std::vector<int32_t> job_teams((size_t)J * K);
-    for (int i = 0; i < J * K; i++) job_teams[i] = ctx->flat.root_team[req->job_roots[i]];
     tpgx_status st;
     DevBuf* sc = ctx->d_scratch;
     const size_t nE = (size_t)J * NI;
-    if ((st = upload(ctx, sc[0], raw.data(), raw.size() * 8)) != TPGX_OK) return st;
-    if ((st = upload(ctx, sc[1], job_teams.data(), job_teams.size() * 4)) != TPGX_OK) return st;
-    if ((st = upload(ctx, sc[7], ctx->flat.edge_program.data(), ctx->flat.edge_program.size() * 4)) != TPGX_OK) return st;
-    CU(sc[2].ensure(nE * K * 8));                  /* episode scores */
-    CU(sc[3].ensure(nE * 4));                      /* episode action counts */
-    CU(sc[4].ensure(nE * 4 * 8));                  /* final state */
-    CU(sc[5].ensure(std::max<size_t>(16, nE * (size_t)ep.trace_steps)));
-    CU(sc[6].ensure((size_t)J * K * 8));           /* job scores */
-    CU(ctx->d_counters.ensure(64));
-    CU(ctx->d_status.ensure(16));
-    CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
-    ep.rng_raw = sc[0].as<uint64_t>();
-    ep.job_teams = sc[1].as<int32_t>();
+    /* ONE host -> device transfer for the per-call inputs and ONE device -> host transfer for everything the call returns
+       (a generation of the training loop makes two of these calls; a dozen small synchronous copies each used to cost more
+       than the kernels): both sides are laid out as blocks of 8-byte-aligned sections */
+    struct Section { size_t off = 0, bytes = 0; };
+    auto carve = [](size_t& total, size_t bytes) { Section s; s.off = total; s.bytes = bytes; total += (bytes + 15) & ~(size_t)15; return s; };
+    size_t in_total = 0;
+    const Section i_raw = carve(in_total, raw.size() * 8), i_teams = carve(in_total, (size_t)J * K * 4);
+    Section i_hoff, i_hexec, i_hslot;
+    if (hp) { i_hoff = carve(in_total, hp->hit_offset.size() * 4); i_hexec = carve(in_total, std::max<size_t>(1, hp->hit_exec.size()) * 4); i_hslot = carve(in_total, std::max<size_t>(1, hp->hit_slot.size()) * 4); }
+    std::vector<uint8_t>& hin = ctx->h_stage_in;
+    hin.resize(in_total);
+    memcpy(hin.data() + i_raw.off, raw.data(), i_raw.bytes);
+    int32_t* job_teams = reinterpret_cast<int32_t*>(hin.data() + i_teams.off);
+    for (int i = 0; i < J * K; i++) job_teams[i] = ctx->flat.root_team[req->job_roots[i]];
+    if (hp) {
+        memcpy(hin.data() + i_hoff.off, hp->hit_offset.data(), hp->hit_offset.size() * 4);
+        memcpy(hin.data() + i_hexec.off, hp->hit_exec.data(), hp->hit_exec.size() * 4);
+        memcpy(hin.data() + i_hslot.off, hp->hit_slot.data(), hp->hit_slot.size() * 4);
+    }
+    if ((st = upload(ctx, sc[0], hin.data(), in_total)) != TPGX_OK) return st;
+    const size_t nr = hp ? (size_t)std::max(1, hp->nb_records) : 0;
+    size_t out_total = 0;
+    const Section o_status = carve(out_total, 16), o_counters = carve(out_total, 64), o_job = carve(out_total, (size_t)J * K * 8),
+                  o_escore = carve(out_total, nE * K * 8), o_final = carve(out_total, nE * 4 * 8), o_actions = carve(out_total, nE * 4),
+                  o_progs = carve(out_total, progs_out ? nE * 4 : 0), o_trace = carve(out_total, nE * (size_t)ep.trace_steps),
+                  o_rbid = carve(out_total, nr * 8), o_robs = carve(out_total, hp ? nr * (size_t)std::max(1, hp->obs_len) * 8 : 0),
+                  o_rprog = carve(out_total, nr * 4), o_rstep = carve(out_total, nr * 4);
+    CU(sc[2].ensure(out_total));
+    uint8_t* dout = sc[2].as<uint8_t>();
+    const uint8_t* din = sc[0].as<uint8_t>();
+    CU(cudaMemsetAsync(dout, 0, o_job.off, ctx->stream)); /* status + counters */
+    ep.rng_raw = reinterpret_cast<const uint64_t*>(din + i_raw.off);
+    ep.job_teams = reinterpret_cast<const int32_t*>(din + i_teams.off);
     ep.code = ctx->d_code.as<uint32_t>();
     ep.prog_offset = ctx->d_prog_off.as<int32_t>();
     ep.constants = ctx->d_consts.as<double>();
     ep.team_edge_offset = ctx->d_team_off.as<int32_t>();
-    ep.edge_program = sc[7].as<int32_t>();
+    ep.edge_program = ctx->d_edge_prog.as<int32_t>();
     ep.edge_destination = ctx->d_edge_dst.as<int32_t>();
-    ep.episode_score = sc[2].as<double>();
-    ep.episode_actions = sc[3].as<int32_t>();
-    ep.final_state = sc[4].as<double>();
-    ep.trace = sc[5].as<int8_t>();
-    ep.job_score = sc[6].as<double>();
-    ep.counters = ctx->d_counters.as<unsigned long long>();
-    ep.status = ctx->d_status.as<int>();
-    if (progs_out) {
-        CU(sc[8].ensure(nE * 4));
-        ep.episode_progs = sc[8].as<int32_t>();
-    }
+    ep.episode_score = reinterpret_cast<double*>(dout + o_escore.off);
+    ep.episode_actions = reinterpret_cast<int32_t*>(dout + o_actions.off);
+    ep.final_state = reinterpret_cast<double*>(dout + o_final.off);
+    ep.trace = reinterpret_cast<int8_t*>(dout + o_trace.off);
+    ep.job_score = reinterpret_cast<double*>(dout + o_job.off);
+    ep.counters = reinterpret_cast<unsigned long long*>(dout + o_counters.off);
+    ep.status = reinterpret_cast<int*>(dout + o_status.off);
+    if (progs_out) ep.episode_progs = reinterpret_cast<int32_t*>(dout + o_progs.off);
     if (hp) {
-        if ((st = upload(ctx, sc[9], hp->hit_offset.data(), hp->hit_offset.size() * 4)) != TPGX_OK) return st;
-        if ((st = upload(ctx, sc[10], hp->hit_exec.data(), std::max<size_t>(1, hp->hit_exec.size()) * 4)) != TPGX_OK) return st;
-        if ((st = upload(ctx, sc[11], hp->hit_slot.data(), std::max<size_t>(1, hp->hit_slot.size()) * 4)) != TPGX_OK) return st;
-        const size_t nr = (size_t)std::max(1, hp->nb_records);
-        CU(sc[12].ensure(nr * 4));
-        CU(sc[13].ensure(nr * 4));
-        CU(sc[14].ensure(nr * 8));
-        CU(sc[15].ensure(nr * (size_t)std::max(1, hp->obs_len) * 8));
-        ep.hit_offset = sc[9].as<int32_t>();
-        ep.hit_exec = sc[10].as<int32_t>();
-        ep.hit_slot = sc[11].as<int32_t>();
-        ep.rec_program = sc[12].as<int32_t>();
-        ep.rec_step = sc[13].as<int32_t>();
-        ep.rec_bid = sc[14].as<double>();
-        ep.rec_obs = hp->obs_len > 0 ? sc[15].as<double>() : nullptr;
+        ep.hit_offset = reinterpret_cast<const int32_t*>(din + i_hoff.off);
+        ep.hit_exec = reinterpret_cast<const int32_t*>(din + i_hexec.off);
+        ep.hit_slot = reinterpret_cast<const int32_t*>(din + i_hslot.off);
+        ep.rec_program = reinterpret_cast<int32_t*>(dout + o_rprog.off);
+        ep.rec_step = reinterpret_cast<int32_t*>(dout + o_rstep.off);
+        ep.rec_bid = reinterpret_cast<double*>(dout + o_rbid.off);
+        ep.rec_obs = hp->obs_len > 0 ? reinterpret_cast<double*>(dout + o_robs.off) : nullptr;
         ep.obs_len = hp->obs_len;
     }
     CU(cudaEventRecord(ctx->event(0), ctx->stream));
     CU(tpgx_launch_episodes(ep, ctx->stream));
     CU(cudaEventRecord(ctx->event(1), ctx->stream));
+    std::vector<uint8_t>& hout = ctx->h_stage_out;
+    hout.resize(out_total);
+    CU(cudaMemcpyAsync(hout.data(), dout, out_total, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     int status = 0;
-    CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
+    memcpy(&status, hout.data() + o_status.off, 4);
     if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
     if (progs_out) {
         progs_out->resize(nE);
-        CU(cudaMemcpy(progs_out->data(), sc[8].p, nE * 4, cudaMemcpyDeviceToHost));
+        memcpy(progs_out->data(), hout.data() + o_progs.off, nE * 4);
     }
     if (hp) {
-        const size_t nr = (size_t)hp->nb_records;
-        hp->rec_program.resize(nr); hp->rec_step.resize(nr); hp->rec_bid.resize(nr); hp->rec_obs.resize(nr * (size_t)hp->obs_len);
-        if (nr) {
-            CU(cudaMemcpy(hp->rec_program.data(), sc[12].p, nr * 4, cudaMemcpyDeviceToHost));
-            CU(cudaMemcpy(hp->rec_step.data(), sc[13].p, nr * 4, cudaMemcpyDeviceToHost));
-            CU(cudaMemcpy(hp->rec_bid.data(), sc[14].p, nr * 8, cudaMemcpyDeviceToHost));
-            if (hp->obs_len > 0) CU(cudaMemcpy(hp->rec_obs.data(), sc[15].p, nr * (size_t)hp->obs_len * 8, cudaMemcpyDeviceToHost));
+        const size_t n = (size_t)hp->nb_records;
+        hp->rec_program.resize(n); hp->rec_step.resize(n); hp->rec_bid.resize(n); hp->rec_obs.resize(n * (size_t)hp->obs_len);
+        if (n) {
+            memcpy(hp->rec_program.data(), hout.data() + o_rprog.off, n * 4);
+            memcpy(hp->rec_step.data(), hout.data() + o_rstep.off, n * 4);
+            memcpy(hp->rec_bid.data(), hout.data() + o_rbid.off, n * 8);
+            if (hp->obs_len > 0) memcpy(hp->rec_obs.data(), hout.data() + o_robs.off, n * (size_t)hp->obs_len * 8);
         }
         return TPGX_OK; /* the archive pass writes records only */
     }
-    if (out->score) CU(cudaMemcpy(out->score, sc[6].p, (size_t)J * K * 8, cudaMemcpyDeviceToHost));
-    if (out->episode_score) CU(cudaMemcpy(out->episode_score, sc[2].p, nE * K * 8, cudaMemcpyDeviceToHost));
-    if (out->episode_actions) CU(cudaMemcpy(out->episode_actions, sc[3].p, nE * 4, cudaMemcpyDeviceToHost));
-    if (out->final_state) CU(cudaMemcpy(out->final_state, sc[4].p, nE * 4 * 8, cudaMemcpyDeviceToHost));
-    if (out->trace && ep.trace_steps > 0) CU(cudaMemcpy(out->trace, sc[5].p, nE * (size_t)ep.trace_steps, cudaMemcpyDeviceToHost));
+    if (out->score) memcpy(out->score, hout.data() + o_job.off, (size_t)J * K * 8);
+    if (out->episode_score) memcpy(out->episode_score, hout.data() + o_escore.off, nE * K * 8);
+    if (out->episode_actions) memcpy(out->episode_actions, hout.data() + o_actions.off, nE * 4);
+    if (out->final_state) memcpy(out->final_state, hout.data() + o_final.off, nE * 4 * 8);
+    if (out->trace && ep.trace_steps > 0) memcpy(out->trace, hout.data() + o_trace.off, nE * (size_t)ep.trace_steps);
     if (out->counters) {
         unsigned long long c[4];
-        CU(cudaMemcpy(c, ctx->d_counters.p, 32, cudaMemcpyDeviceToHost));
+        memcpy(c, hout.data() + o_counters.off, 32);
         memset(out->counters, 0, sizeof(*out->counters));
         out->counters->evaluations = c[0]; out->counters->team_visits = c[1];
         out->counters->program_executions = c[2]; out->counters->lines_executed = c[3];

@@ -35,11 +35,19 @@ else:
     be = tpgx.classification_backend(ev, img, nb_classes=10, actions_per_evaluation=500)
 tr.train_generation(be, 0)  # warm-up (context buffers, first-launch costs)
 t0 = time.perf_counter()
+per_gen = []
 for gen in range(1, gens + 1):
+    g0 = time.perf_counter()
     s = tr.train_generation(be, gen)
+    per_gen.append(time.perf_counter() - g0)
     if gen % max(1, gens // 10) == 0:
         print("gen %4d  best %8.4f  mean %9.4f  validation best %8.4f  teams %4d  programs %5d  archive %4d  retries %5d  jobs %3d  skipped %3d" %
               (gen, s["best_score"], s["mean_score"], s["best_validation_score"], s["nb_teams"], s["nb_programs"], s["archive_records"],
                s["behaviour_retries"], s["nb_evaluated_roots"], s["nb_skipped_roots"]))
 dt = time.perf_counter() - t0
 print("%s: %d generations in %.2f s = %.1f generations/s (%d roots, fingerprint %016x)" % (app, gens, dt, gens / dt, roots, tr.fingerprint()))
+import numpy as np  # noqa: E402
+pg = np.array(per_gen) * 1e3
+worst = int(pg.argmax())
+print("per generation: median %.2f ms, p99 %.2f ms, slowest %.2f ms at generation %d; without the slowest: %.1f generations/s; CUDA_MODULE_LOADING=%s"
+      % (np.median(pg), np.percentile(pg, 99), pg[worst], worst + 1, (gens - 1) / ((pg.sum() - pg[worst]) * 1e-3), os.environ.get("CUDA_MODULE_LOADING", "(default: LAZY)")))
