@@ -101,6 +101,9 @@ struct tpgx_ctx {
     ShardPlan plan;
     std::vector<int32_t> h_edge_row, h_active;
     std::vector<uint8_t> h_stage_in, h_stage_out; /* episode calls: one transfer each way */
+    void* pin_ring = nullptr;            /* page-locked staging ring of upload() */
+    size_t pin_used = 0;
+    bool pin_failed = false;
 
     cudaEvent_t event(size_t i) {
         while (events.size() <= i) { cudaEvent_t e; cudaEventCreate(&e); events.push_back(e); }
@@ -129,9 +132,28 @@ static cudaError_t wait_for_observations(tpgx_ctx* ctx) {
     return cudaStreamWaitEvent(ctx->stream, ctx->obs_ready, 0);
 }
 
-tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes) {
+/* Small host -> device copies (graph arrays, plans, per-call inputs: a dozen per generation) go through a page-locked ring:
+   a copy from pageable memory is staged by the driver and blocks the host, one from page-locked memory is only enqueued.
+   The ring wraps after a stream synchronisation, so a slot is never reused while a copy may still read it. */
+tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes, bool through_ring = true) {
     CU(b.ensure(bytes ? bytes : 16));
-    if (bytes) CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (!bytes) return TPGX_OK;
+    const size_t ring = (size_t)48 << 20, limit = (size_t)8 << 20;
+    if (through_ring && bytes <= limit) {
+        if (!ctx->pin_ring && !ctx->pin_failed) {
+            if (cudaHostAlloc(&ctx->pin_ring, ring, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); ctx->pin_ring = nullptr; ctx->pin_failed = true; }
+        }
+        if (ctx->pin_ring) {
+            const size_t need = (bytes + 255) & ~(size_t)255;
+            if (ctx->pin_used + need > ring) { CU(cudaStreamSynchronize(ctx->stream)); ctx->pin_used = 0; }
+            void* slot = static_cast<uint8_t*>(ctx->pin_ring) + ctx->pin_used;
+            ctx->pin_used += need;
+            memcpy(slot, src, bytes);
+            CU(cudaMemcpyAsync(b.p, slot, bytes, cudaMemcpyHostToDevice, ctx->stream));
+            return TPGX_OK;
+        }
+    }
+    CU(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return TPGX_OK;
 }
 
@@ -596,6 +618,7 @@ tpgx_status tpgx_comm_init(tpgx_ctx* ctx, const uint8_t* id, int32_t rank, int32
     if (!g_nccl.load()) return fail(ctx, TPGX_ERR_NCCL, g_nccl.err);
     cudaSetDevice(ctx->cfg.device);
     tpgx_comm_release(ctx);
+    if (ctx->pin_ring) cudaFreeHost(ctx->pin_ring);
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
     NC(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
@@ -925,11 +948,11 @@ static tpgx_status set_observations_host(tpgx_ctx* ctx, int32_t source, int32_t 
         CU(cudaStreamWaitEvent(ctx->obs_stream, ctx->event(60), 0));
         ctx->stream = ctx->obs_stream;
     }
-    if ((st = upload(ctx, ctx->d_obs_raw, data, (size_t)count * ctx->obs_hw)) != TPGX_OK) return st;
+    if ((st = upload(ctx, ctx->d_obs_raw, data, (size_t)count * ctx->obs_hw, false)) != TPGX_OK) return st;
     ctx->obs_dev = ctx->d_obs_raw.as<uint8_t>();
     ctx->labels_dev = nullptr;
     if (labels) {
-        if ((st = upload(ctx, ctx->d_labels_raw, labels, (size_t)count)) != TPGX_OK) return st;
+        if ((st = upload(ctx, ctx->d_labels_raw, labels, (size_t)count, false)) != TPGX_OK) return st;
         ctx->labels_dev = ctx->d_labels_raw.as<uint8_t>();
     }
     /* the caller may free its buffers on return: wait for the host -> device copies only; the re-tiling and

@@ -473,3 +473,20 @@ def test_labels_outside_the_class_range_are_reported():
         with pytest.raises(tpgx.TpgxError) as e:
             ev.evaluate_classification(want=want)
         assert e.value.status == A.ERR_BAD_ARG and "label" in str(e.value)
+
+
+@pytest.mark.parametrize("ctas,group", [("1", "1"), ("3", "5"), ("148", "2"), ("37", "64")])
+def test_k1_v2_work_distribution_does_not_change_results(oracle_mod, monkeypatch, ctas, group):
+    """K1 v2's warps pull (tile, unit group) items from one global counter, stage code through per-warp cp.async double
+    buffers and share nothing else: any grid size / item size must give the oracle's bits, run after run (compute-sanitizer
+    is not available on this pool — profiles/r2_sanitizer.md — so this and the encoder's bound checks stand in for it)."""
+    monkeypatch.setenv("TPGX_K1_CTAS", ctas)
+    monkeypatch.setenv("TPGX_K1_GROUP", group)
+    g, ev = make(roots=70, edges=5, lines=20, depth=3, share_prob=0.1, seed=61, intron_lines=3, line_jitter=8)
+    img, lab = tpgx.synthetic_images(1100, seed=6)          # 9 tiles, the last one ragged
+    ev.set_observations(img, lab)
+    want_b, want_t = ("score", "confusion", "action", "bid", "counters"), ("score", "confusion", "action", "counters")
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want_b)
+    for _ in range(3):
+        compare(ev.evaluate_classification(want=want_b), ref)
+        compare(ev.evaluate_classification(want=want_t), ref)

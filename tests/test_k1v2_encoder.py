@@ -100,7 +100,7 @@ def run_v2(quads, slots, consts, px, magn, dirn, names):
                 return px[v // TS4]
 
             if name in ("SOBM", "SOBD"):
-                assert y % TS4 == 0
+                assert y % TS4 == 0 and y // TS4 < 2 * NWIN and (y // TS4 >= NWIN) == (name == "SOBD"), "window outside the tile's two Sobel planes"
                 acc = planes[y // TS4]
                 continue
             if name in ("LUTE", "LUTL"):
@@ -112,7 +112,7 @@ def run_v2(quads, slots, consts, px, magn, dirn, names):
                 acc = (f_exp if op == "EXP" else f_ln)(np.float64(get[kinds[0]](y)))
                 continue
             if op == "MULC":
-                assert z % 8 == 0
+                assert z % 8 == 0 and z // 8 < 8, "constant outside the 8 doubles at the head of the code buffer"
                 acc = np.float64(get[kinds[0]](y)) * consts[z // 8] / 10.0
                 continue
             a, b = np.float64(get[kinds[0]](y)), np.float64(get[kinds[1]](z))
