@@ -490,3 +490,56 @@ def test_k1_v2_work_distribution_does_not_change_results(oracle_mod, monkeypatch
     for _ in range(3):
         compare(ev.evaluate_classification(want=want_b), ref)
         compare(ev.evaluate_classification(want=want_t), ref)
+
+
+def test_k1_v2_heavy_handlers_on_wide_operand_ranges(oracle_mod):
+    """The division, exp, ln and a*c/10 sequences of K1 v2 are hand-written PTX; programs whose constants span the whole
+    double range (2^-1074 .. 2^1023, both signs, zeros, infinities, NaN) push subnormal operands and results, overflow, the
+    slivers next to exp's thresholds and every special-operand class through them — including the exits to the generic
+    routines — and every bid must carry the oracle's bits.  Shapes: r = (px*c0/10) / (px*c1/10), exp / ln of px*c/10,
+    chains of a*c/10, and the reversed-operand forms."""
+    rng = np.random.default_rng(2025)
+    P = 1500
+    MULC, DIV, EXP, LN, SUB, ADD, MUL, MAX = 7, 3, 5, 6, 0, 1, 2, 4     # indices in the mnist instruction set
+    REG, CST, IMG = 0, 1, 2
+    lines, off, consts = [], [0], np.zeros((P, 5))
+    for p in range(P):
+        e = rng.uniform(-1074, 1023, 5)
+        c = np.ldexp(rng.uniform(1.0, 2.0, 5), e.astype(int)) * rng.choice([-1.0, 1.0], 5)
+        special = rng.random(5) < 0.08
+        c[special] = rng.choice([0.0, -0.0, np.inf, -np.inf, np.nan, 5e-324, -5e-324, 2.2250738585072014e-308, 1.7976931348623157e308, 10.0, 700.5, -745.2, 709.9], special.sum())
+        if p % 3 == 0:   # exp's thresholds, in reach of px * c / 10 with px in 1 .. 255
+            c[0] = rng.choice([-1.0, 1.0]) * rng.uniform(27.0, 7500.0)
+        consts[p] = c
+        px = lambda: int(rng.integers(0, 784))
+        shape = p % 6
+        prog = [(MULC, 1, (IMG, CST), (px(), 0)), (MULC, 2, (IMG, CST), (px(), 1))]
+        if shape == 0: prog += [(DIV, 0, (REG, REG), (1, 2))]                                              # DIV_RA / DIV_RR forms
+        elif shape == 1: prog += [(DIV, 3, (REG, IMG), (2, px())), (DIV, 0, (IMG, REG), (px(), 3))]        # DIV_AP, DIV_PA
+        elif shape == 2: prog += [(EXP, 3, (REG, REG), (1, 0)), (LN, 4, (REG, REG), (2, 0)), (SUB, 0, (REG, REG), (3, 4))]
+        elif shape == 3: prog += [(LN, 3, (REG, REG), (2, 0)), (EXP, 0, (REG, REG), (3, 0))]               # exp(ln(x)): accumulator forms
+        elif shape == 4: prog += [(MULC, 3, (REG, CST), (2, 2)), (MULC, 3, (REG, CST), (3, 3)), (DIV, 0, (REG, REG), (3, 1))]
+        else: prog += [(MUL, 3, (REG, REG), (1, 2)), (MAX, 4, (REG, REG), (3, 1)), (DIV, 5, (REG, REG), (4, 4)), (ADD, 0, (REG, REG), (5, 2))]
+        lines += prog
+        off.append(len(lines))
+    ln = np.zeros(len(lines), dtype=tpgx.LINE_DTYPE)
+    for i, (ins, dst, src, loc) in enumerate(lines):
+        ln[i] = (ins, dst, src, loc)
+    R, E = P // 5, 5
+    g = tpgx.TPGraph(lines=ln, program_line_offset=np.array(off, dtype=np.int64), constants=consts, team_edge_offset=(np.arange(R + 1) * E).astype(np.int32),
+                     edge_program=np.arange(P, dtype=np.int32), edge_destination=(-1 - rng.integers(0, 10, P)).astype(np.int32),
+                     root_team=np.arange(R, dtype=np.int32))
+    img = rng.integers(0, 256, (256, 784)).astype(np.uint8)
+    img[:, ::7] = rng.choice([0, 1, 2, 10, 100, 255], (256, 112)).astype(np.uint8)
+    img[:32] = 0
+    lab = (np.arange(256) % 10).astype(np.uint8)
+    ev = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5)
+    ev.set_graph(g)
+    ev.set_observations(img, lab)
+    want = ("score", "confusion", "action", "bid", "counters")
+    dev = ev.evaluate_classification(want=want)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, want=want)
+    b = ref["bid"]
+    assert np.isinf(b).any() and (np.abs(b[np.isfinite(b)]) < 2.3e-308).any() and (np.abs(b[np.isfinite(b)]) > 1e300).any(), "the case must reach subnormal and huge bids"
+    compare(dev, ref)
+    compare(ev.evaluate_classification(want=("score", "confusion", "action", "counters")), ref)      # team mode
