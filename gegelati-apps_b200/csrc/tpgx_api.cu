@@ -618,7 +618,6 @@ tpgx_status tpgx_comm_init(tpgx_ctx* ctx, const uint8_t* id, int32_t rank, int32
     if (!g_nccl.load()) return fail(ctx, TPGX_ERR_NCCL, g_nccl.err);
     cudaSetDevice(ctx->cfg.device);
     tpgx_comm_release(ctx);
-    if (ctx->pin_ring) cudaFreeHost(ctx->pin_ring);
     ncclUniqueId u;
     memcpy(&u, id, sizeof u);
     NC(g_nccl.CommInitRank(&ctx->comm, world, u, rank));
@@ -774,6 +773,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     for (DevBuf* b : all) b->release();
     for (DevBuf& b : ctx->d_scratch) b.release();
     tpgx_comm_release(ctx);
+    if (ctx->pin_ring) cudaFreeHost(ctx->pin_ring);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->obs_stream) { cudaStreamSynchronize(ctx->obs_stream); cudaStreamDestroy(ctx->obs_stream); }
     if (ctx->obs_ready) cudaEventDestroy(ctx->obs_ready);
