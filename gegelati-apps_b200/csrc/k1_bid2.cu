@@ -32,7 +32,11 @@
 #define K2_NW 32
 #define K2_TS 128
 #define K2_BUF (K1V2_CQ + K1V2_CAP) /* quads per code buffer */
-#define K2_TAB_BYTES (256 * 8 + 512 * 8)
+#define K2_TAB_BYTES (256 * 8 + 512 * 8 + 512 * 8) /* exp table, ln table, exp / ln of the 256 pixel values */
+#define K2_HEAD_BYTES (K2_TAB_BYTES + 16)        /* ... and the stream's address */
+#define K2_WST_BYTES 64 /* per-warp row cursor record */
+#define K2_WARP_FIXED (K2_WST_BYTES + 2 * K2_BUF * 16)
+static_assert(K1V2_CQ == 5 && K1V2_HDR == 4 && K1V2_CAP == 36 && K2_TAB_BYTES == 10240, "the NEXT handler of the interpreter block spells these out");
 
 __device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void k2_cp_async16(uint32_t dst, const void* src) {
@@ -40,17 +44,6 @@ __device__ __forceinline__ void k2_cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void k2_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-struct k2_tab_shared {
-    uint32_t exp_addr, log_addr;
-    __device__ __forceinline__ void exp_entry(int i, double& tail, double& T) const {
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(tail), "=d"(T) : "r"(exp_addr + (uint32_t)i * 16u));
-    }
-    __device__ __forceinline__ void log_entry(int i, double& invc, double& logc_hi, double& logc_lo) const {
-        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(invc), "=d"(logc_hi) : "r"(log_addr + (uint32_t)i * 32u));
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(logc_lo) : "r"(log_addr + (uint32_t)i * 32u + 16u));
-    }
-};
 
 /* ---- the interpreter block --------------------------------------------------------------------------------
  * operands of the asm statement */
@@ -65,14 +58,10 @@ struct k2_tab_shared {
 #define LP "%8"
 #define CODE "%9"
 #define REGS "%10"
-#define LANE "%11"
-#define GTILE "%12"
-#define SOBEL "%13"
-#define LUT "%14"
-#define CBASE "%15"
-#define EXPT "%16"
-#define LOGT "%17"
-#define NEVER "%18"
+#define GTILE "%11" /* the lane's 4 samples in pixel row 0 of the tile */
+#define SOBEL "%12" /* the lane's 4 samples at window 0 of the tile's first plane */
+#define CBASE "%13"
+#define TAB "%14" /* exp table; +2048 ln table; +6144 exp / ln of the 256 pixel values */
 
 
 /* IEEE-754 double constants of tpgx_math.h, as PTX literals */
@@ -113,7 +102,6 @@ struct k2_tab_shared {
 /* tpgx_math::xdiv_k, one sample k.  DIV_CLASS: reciprocal seed sd<k>, special-operand predicate psp<k>, pany |= !special.
    DIV_SEQ: quotient of a / b into qr<k> (a * seed when special); pall &= (special | fast path accepted). */
 #define DIV_CLASS(a, b, k)                                                                       \
-    "rcp.approx.ftz.f64 sd" k ", " b ";\n"                                                       \
     "mov.b64 {alo, ahi}, " a ";\n mov.b64 {blo, bhi}, " b ";\n"                                  \
     "and.b32 ha, ahi, 0x7fffffff;\n and.b32 hb, bhi, 0x7fffffff;\n"                              \
     "or.b32 t0, ha, alo;\n setp.eq.u32 p1, t0, 0;\n setp.ge.u32 p2, ha, 0x7ff00000;\n or.pred pas, p1, p2;\n" \
@@ -121,7 +109,8 @@ struct k2_tab_shared {
     "sub.u32 t0, hb, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fb00000;\n and.pred pas, pas, p1;\n or.pred psp" k ", pbs, pas;\n" \
     "not.pred p1, psp" k ";\n or.pred pany, pany, p1;\n"
 #define DIV_SEQ(a, b, k)                                                                         \
-    "mov.b64 {slo, shi}, sd" k ";\n mov.b32 slo, 1;\n mov.b64 rr, {slo, shi};\n"                 \
+    "rcp.approx.ftz.f64 sd, " b ";\n"                                                            \
+    "mov.b64 {slo, shi}, sd;\n mov.b32 slo, 1;\n mov.b64 rr, {slo, shi};\n"                      \
     "neg.f64 nb, " b ";\n"                                                                       \
     "fma.rn.f64 t1, nb, rr, " KD_ONE ";\n fma.rn.f64 t1, t1, t1, t1;\n fma.rn.f64 r1, rr, t1, rr;\n" \
     "fma.rn.f64 t2, nb, r1, " KD_ONE ";\n fma.rn.f64 r2, r1, t2, r1;\n"                           \
@@ -131,7 +120,9 @@ struct k2_tab_shared {
     "fma.rn.f32 ft, 0f00000000, fb, fq;\n abs.f32 ft, ft;\n setp.gt.f32 p1, ft, 0f00100000;\n"   \
     "abs.f32 fa, fa;\n setp.ge.f32 p2, fa, 0f03600000;\n and.pred p1, p1, p2;\n"                 \
     "or.pred p1, p1, psp" k ";\n and.pred pall, pall, p1;\n"                                     \
-    "mul.rn.f64 sp, " a ", sd" k ";\n selp.f64 qr" k ", sp, qr" k ", psp" k ";\n"
+    "mul.rn.f64 sp, " a ", sd;\n selp.f64 qr" k ", sp, qr" k ", psp" k ";\n"
+/* every sample of the warp has a special operand: the quotient is a * seed */
+#define DIV_SP(a, b) "rcp.approx.ftz.f64 sd, " b ";\n mul.rn.f64 " a ", " a ", sd;\n"
 
 /* tpgx_math::exp_k, one sample (x in place).  EXP_RARE accumulates the sliver test, EXP_MAIN computes. */
 #define EXP_RARE(x, k)                                                                            \
@@ -142,7 +133,7 @@ struct k2_tab_shared {
     "mul.rn.f64 z, " x ", " KD_INV_LN2N ";\n add.rn.f64 tm, z, " KD_MAGIC ";\n sub.rn.f64 kd, tm, " KD_MAGIC ";\n" \
     "mov.b64 {ki, t0}, tm;\n"                                                                    \
     "fma.rn.f64 r, kd, " KD_NEG_LN2N_HI ", " x ";\n fma.rn.f64 r, kd, " KD_NEG_LN2N_LO ", r;\n"   \
-    "and.b32 ii, ki, 127;\n shr.s32 ee, ki, 7;\n shl.b32 ii, ii, 4;\n add.u32 ii, ii, " EXPT ";\n" \
+    "and.b32 ii, ki, 127;\n shr.s32 ee, ki, 7;\n shl.b32 ii, ii, 4;\n add.u32 ii, ii, " TAB ";\n" \
     "ld.shared.v2.f64 {tail, TT}, [ii];\n"                                                       \
     "mul.rn.f64 r2, r, r;\n fma.rn.f64 pa, r, " KD_C1_6 ", " KD_HALF ";\n fma.rn.f64 pb, r, " KD_C1_120 ", " KD_C1_24 ";\n" \
     "add.rn.f64 tmp, tail, r;\n fma.rn.f64 tmp, r2, pa, tmp;\n mul.rn.f64 r4, r2, r2;\n fma.rn.f64 tmp, r4, pb, tmp;\n" \
@@ -164,7 +155,7 @@ struct k2_tab_shared {
     "mov.b64 {xlo, xhi}, " x ";\n"                                                               \
     "sub.u32 t0, xhi, 0x3FE6B000;\n shr.u32 ii, t0, 13;\n and.b32 ii, ii, 127;\n shr.s32 kk, t0, 20;\n" \
     "and.b32 t0, t0, 0xfff00000;\n sub.u32 t0, xhi, t0;\n mov.b64 z, {xlo, t0};\n"               \
-    "shl.b32 ii, ii, 5;\n add.u32 ii, ii, " LOGT ";\n ld.shared.v2.f64 {invc, lchi}, [ii];\n ld.shared.f64 lclo, [ii+16];\n" \
+    "shl.b32 ii, ii, 5;\n add.u32 ii, ii, " TAB ";\n ld.shared.v2.f64 {invc, lchi}, [ii+2048];\n ld.shared.f64 lclo, [ii+2064];\n" \
     "fma.rn.f64 r, z, invc, " KD_MONE ";\n cvt.rn.f64.s32 kd, kk;\n fma.rn.f64 w, kd, " KD_LN2_HI ", lchi;\n add.rn.f64 hi, w, r;\n" \
     "sub.rn.f64 lo, w, hi;\n add.rn.f64 lo, lo, r;\n fma.rn.f64 tmp, kd, " KD_LN2_LO ", lclo;\n add.rn.f64 lo, lo, tmp;\n" \
     "mul.rn.f64 r2, r, r;\n fma.rn.f64 pa, r, " KD_C1_7 ", " KD_CM1_6 ";\n fma.rn.f64 pa, r, pa, " KD_C0_2 ";\n" \
@@ -183,32 +174,19 @@ struct k2_tab_shared {
     "and.pred p1, p1, p2;\n or.pred p1, p1, psp;\n and.pred pall, pall, p1;\n"                   \
     "selp.f64 " q ", q0, " q ", psp;\n"
 
-/* Dispatch.  Default (K2_PIPELINED 0): one fetch + indirect branch, every handler ends with a branch back to it.
- * K2_PIPELINED 1 / 2 are the measured alternatives (profiles/r2_k1v2_experiments.md): every handler fetches the NEXT entry
- * into the same registers once its own operand fields are addresses (PF) and ends with its own indirect branch (GO) —
- * 4 % fewer instructions but 21 % SLOWER on C2: ptxas sinks the fetch back next to the branch, and 28 BRX sites plus
- * 3.5 KB more code drop the instruction-cache hit rate from 99.3 % to 93 % (no_instruction stalls x4, short scoreboard x3). */
-#ifndef K2_PIPELINED
-#define K2_PIPELINED 0
-#endif
-#if K2_PIPELINED == 2
-/* the fetch is fenced by a never-taken branch so that ptxas cannot sink the LDS below the handler's body */
-#define PF "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n add.u32 " LP ", " LP ", 16;\n @pnever bra.uni XEND;\n"
-#define GO "brx.idx.uni hx, tlist;\n"
-#define UNFETCH "sub.u32 " LP ", " LP ", 16;\n"
-#elif K2_PIPELINED
-#define PF "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n add.u32 " LP ", " LP ", 16;\n"
-#define GO "brx.idx.uni hx, tlist;\n"
-#define UNFETCH "sub.u32 " LP ", " LP ", 16;\n" /* a handler that leaves the block after PF hands the next entry back */
-#else
+/* Dispatch: one fetch + indirect branch, every handler ends with a branch back to it.  The measured alternative (every
+ * handler fetches the NEXT entry and ends with its own indirect branch) executes 4 % fewer instructions and is 21 % SLOWER on
+ * C2: 28 BRX sites plus 3.5 KB more code drop the instruction-cache hit rate from 99.3 % to 93 % (profiles/r2_k1v2_experiments.md). */
 #define PF ""
+/* Sobel planes: two 16-byte loads per lane of one 32-byte sector.  L1::no_allocate was measured 4.6 % slower (the second load
+   misses the sector the first one brought in) */
+#define LDSOB "ld.global.nc.v2.f64"
 #define GO "bra.uni FETCH;\n"
 #define UNFETCH ""
-#endif
 
 /* address of a shared-memory slot operand (byte offset in field f) / of the lane's packed pixel word (word index in f) */
 #define ADDR_R(f) "add.u32 ra, " f ", " REGS ";\n"
-#define ADDR_P(f) "add.u32 pw, " f ", " LANE ";\n mad.wide.u32 ga, pw, 4, " GTILE ";\n"
+#define ADDR_P(f) "mad.wide.u32 ga, " f ", 4, " GTILE ";\n"
 /* 4 doubles of the lane from the slot at ra */
 #define LD_R(d0, d1, d2, d3)                               \
     "ld.shared.v2.f64 {" d0 ", " d1 "}, [ra];\n"           \
@@ -266,27 +244,29 @@ struct k2_tab_shared {
 
 template <bool TEAM>
 __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid2_params p) {
+    /* shared memory: [exp, ln, pixel exp / ln tables] then per warp [row cursor record | 2 code buffers | p.slots register slots] */
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* regs = smem;
-    uint4* codeb = reinterpret_cast<uint4*>(regs + K2_NW * K1V2_SLOTS * K2_TS * 8);
-    double* s_tab = reinterpret_cast<double*>(codeb + K2_NW * 2 * K2_BUF);
+    double* s_tab = reinterpret_cast<double*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 256 + 512; i += K2_NW * 32)
-        s_tab[i] = i < 256 ? tpgx_math::tpgx_exp_tab_dev[i] : tpgx_math::tpgx_log_tab_dev[i - 256];
-    const k2_tab_shared tabs = {k2_smem_u32(s_tab), k2_smem_u32(s_tab + 256)};
+    for (int i = threadIdx.x; i < 256 + 512 + 512; i += K2_NW * 32)
+        s_tab[i] = i < 256 ? tpgx_math::tpgx_exp_tab_dev[i] : i < 768 ? tpgx_math::tpgx_log_tab_dev[i - 256] : __ldg(p.pixel_lut + (i - 768));
+    if (threadIdx.x == 0) *reinterpret_cast<const uint4**>(smem + K2_TAB_BYTES) = p.stream;
+    const uint32_t tab = k2_smem_u32(s_tab);
     __syncthreads();
     /* from here on every warp is on its own */
-    const uint32_t regs_lane = k2_smem_u32(regs) + warp * (K1V2_SLOTS * K2_TS * 8) + lane * 16;
-    const uint32_t mycode = k2_smem_u32(codeb + warp * (2 * K2_BUF));
+    const uint32_t wst = tab + K2_HEAD_BYTES + warp * (K2_WARP_FIXED + p.slots * (K2_TS * 8));
+    const uint32_t mycode = wst + K2_WST_BYTES;
+    const uint32_t regs_lane = wst + K2_WARP_FIXED + lane * 16;
     const uint4* __restrict__ stream = p.stream;
     const int tile_bytes = (p.hw + 1) * K2_TS;
     const long long plane_stride = (long long)p.nwin * K2_TS; /* doubles per plane of a tile */
-    const uint32_t never = p.nb_items < 0 ? 1u : 0u; /* always 0; only the compiler does not know */
 
     /* cursor over the rows (programs) this warp runs.  item = (tile, group of consecutive units); the rows of consecutive
        units are consecutive in the stream, and every row's header quad names the edge's destination, the entry count of
        the row after it and whether it opens / closes its unit — so a warp reads global metadata once per ITEM
-       (unit_first) and nothing per row. */
+       (unit_first) and nothing per row.  The cursor is warp-uniform and needed only between two rows: it lives in a
+       64-byte per-warp record in shared memory, not in registers across the interpreter block (whose heavy handlers
+       need them: the register file is 64 x 1024 threads). */
     struct Cur { int tile, unit, unit_end, q, n; }; /* q: first quad of the row in the stream, n: its entries */
     auto claim = [&]() {
         unsigned int i = 0;
@@ -295,7 +275,7 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
     };
     auto open_item = [&](Cur& c) {
         const int item = claim();
-        if (item >= p.nb_items) { c.tile = -1; c.q = 0; c.n = 0; return; }
+        if (item >= p.nb_items) { c.tile = -1; c.unit = 0; c.unit_end = 0; c.q = 0; c.n = 0; return; }
         c.tile = item / p.items_per_tile;
         const int g = item - c.tile * p.items_per_tile;
         c.unit = g * p.units_per_item;
@@ -309,36 +289,53 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
         for (int i = lane; i < nq; i += 32) k2_cp_async16(buf + i * 16, stream + c.q + i);
         k2_cp_async_commit();
     };
+    /* the record: [0..4] the row to run next, [8..9] {tile, unit} of the row being run.  Every lane
+       writes the same words and reads them back itself: no synchronisation needed */
+    auto put_next = [&](const Cur& c) {
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n st.shared.u32 [%0+16], %5;" ::"r"(wst), "r"(c.tile), "r"(c.unit), "r"(c.unit_end), "r"(c.q), "r"(c.n) : "memory");
+    };
+    auto get_next = [&](Cur& c) {
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n ld.shared.u32 %4, [%5+16];" : "=r"(c.tile), "=r"(c.unit), "=r"(c.unit_end), "=r"(c.q), "=r"(c.n) : "r"(wst) : "memory");
+    };
 
-    Cur c;
-    open_item(c);
-    int cur = 0;
-    stage(mycode, c);
+    {
+        Cur c0;
+        open_item(c0);
+        stage(mycode, c0);
+        put_next(c0);
+    }
+    uint32_t code = mycode;
     double best[4];
     int best_dst[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) { best[k] = 0.0; best_dst[k] = 0; }
 
-    while (c.tile >= 0) {
-        k2_cp_async_wait_all();
-        __syncwarp();
-        const uint32_t code = mycode + cur * (K2_BUF * 16);
-        uint32_t h_dst, h_next, h_flags, h_pad;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_pad) : "r"(code + K1V2_HDR * 16));
-        /* the row after this one */
-        Cur nx = c;
-        nx.q = c.q + K1V2_CQ + c.n;
-        nx.n = (int)h_next;
-        if (h_flags & K1V2_ROW_LAST) {
-            if (++nx.unit >= c.unit_end) open_item(nx);
+    for (;;) {
+        const uint8_t* __restrict__ gtile;
+        const double* __restrict__ sobel_tile;
+        {
+            Cur c;
+            get_next(c);
+            if (c.tile < 0) break;
+            k2_cp_async_wait_all();
+            __syncwarp();
+            uint32_t h_dst, h_next, h_flags, h_pad;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_pad) : "r"(code + K1V2_HDR * 16));
+            /* the row after this one */
+            Cur nx = c;
+            nx.q = c.q + K1V2_CQ + c.n;
+            nx.n = (int)h_next;
+            if (h_flags & K1V2_ROW_LAST) {
+                if (++nx.unit >= c.unit_end) open_item(nx);
+            }
+            stage(2 * mycode + K2_BUF * 16 - code, nx); /* next row's code: in flight while this one runs */
+            put_next(nx);
+            asm volatile("st.shared.v2.u32 [%0+32], {%1, %2};" ::"r"(wst), "r"(c.tile), "r"(c.unit) : "memory");
+            gtile = p.tiles + (size_t)c.tile * tile_bytes + lane * 4;
+            sobel_tile = p.sobel + (size_t)c.tile * 2 * plane_stride + lane * 4;
         }
-        stage(mycode + (cur ^ 1) * (K2_BUF * 16), nx); /* next row's code: in flight while this one runs */
-
-        const uint8_t* __restrict__ const gtile = p.tiles + (size_t)c.tile * tile_bytes;
-        const double* __restrict__ const sobel_tile = p.sobel + (size_t)c.tile * 2 * plane_stride;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         uint32_t lp = code + K1V2_CQ * 16;
-        int staged = min(c.n, K1V2_CAP); /* entries of the program staged so far */
         for (;;) {
             uint32_t xc;
             double b0, b1, b2, b3; /* second operand of the heavy handlers; meaningful after a slow-path exit only */
@@ -346,13 +343,12 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 "{\n"
                 ".reg .b32 hx, ya, zb, wd, ra, pw, t0;\n"
                 ".reg .b64 ga;\n"
-                ".reg .pred pnever, pq, p1, p2, pas, pbs, psp, psp0, psp1, psp2, psp3, pall, pany, prare, pslow, pm0, pm1, pm2, pm3, pt0, pt1, pt2, pt3, pz0, pz1, pz2, pz3;\n"
+                ".reg .pred pq, p1, p2, pas, pbs, psp, psp0, psp1, psp2, psp3, pall, pany, prare, pslow, pm0, pm1, pm2, pm3, pt0, pt1, pt2, pt3, pz0, pz1, pz2, pz3;\n"
                 ".reg .b32 alo, ahi, blo, bhi, ha, hb, slo, shi, qlo, qhi, xlo, xhi, ax, ki, ii, ee, kk, ylo, yhi;\n"
                 ".reg .f32 fq, fb, fa, ft;\n"
-                ".reg .f64 sd0, sd1, sd2, sd3, rr, nb, t1, t2, r1, r2, q0, rem, sp, qr0, qr1, qr2, qr3, cst;\n"
+                ".reg .f64 sd, rr, nb, t1, t2, r1, r2, q0, rem, sp, qr0, qr1, qr2, qr3, cst;\n"
                 ".reg .f64 z, tm, kd, r, tail, TT, pa, pb, tmp, r4, y, ev, invc, lchi, lclo, w, hi, lo;\n"
                 "tlist: .branchtargets " K1V2_HANDLERS(K2_TARGET) "H_END;\n"
-                "setp.ne.u32 pnever, " NEVER ", 0;\n"
                 "FETCH:\n"
                 "ld.shared.v4.u32 {hx, ya, zb, wd}, [" LP "];\n"
                 "add.u32 " LP ", " LP ", 16;\n"
@@ -370,28 +366,27 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 /* Sobel planes: one 32-byte group per lane */
                 "H_SOBM:\n"
                 "H_SOBD:\n"
-                "add.u32 pw, ya, " LANE ";\n"
-                "mad.wide.u32 ga, pw, 32, " SOBEL ";\n"
+                "mad.wide.u32 ga, ya, 32, " SOBEL ";\n"
                 PF
-                "ld.global.nc.v2.f64 {" A0 ", " A1 "}, [ga];\n"
-                "ld.global.nc.v2.f64 {" A2 ", " A3 "}, [ga+16];\n"
+                LDSOB " {" A0 ", " A1 "}, [ga];\n"
+                LDSOB " {" A2 ", " A3 "}, [ga+16];\n"
                 GO
                 /* exp / ln of a pixel: 256-entry tables */
                 "H_LUTL:\n"
                 ADDR_P("ya") PF
                 "ld.global.nc.u32 pw, [ga];\n"
-                "and.b32 t0, pw, 255;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A0 ", [ga+2048];\n"
-                "bfe.u32 t0, pw, 8, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A1 ", [ga+2048];\n"
-                "bfe.u32 t0, pw, 16, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A2 ", [ga+2048];\n"
-                "shr.u32 t0, pw, 24;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A3 ", [ga+2048];\n"
+                "and.b32 t0, pw, 255;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A0 ", [t0+8192];\n"
+                "bfe.u32 t0, pw, 8, 8;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A1 ", [t0+8192];\n"
+                "bfe.u32 t0, pw, 16, 8;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A2 ", [t0+8192];\n"
+                "shr.u32 t0, pw, 24;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A3 ", [t0+8192];\n"
                 GO
                 "H_LUTE:\n"
                 ADDR_P("ya") PF
                 "ld.global.nc.u32 pw, [ga];\n"
-                "and.b32 t0, pw, 255;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A0 ", [ga];\n"
-                "bfe.u32 t0, pw, 8, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A1 ", [ga];\n"
-                "bfe.u32 t0, pw, 16, 8;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A2 ", [ga];\n"
-                "shr.u32 t0, pw, 24;\n mad.wide.u32 ga, t0, 8, " LUT ";\n ld.global.nc.f64 " A3 ", [ga];\n"
+                "and.b32 t0, pw, 255;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A0 ", [t0+6144];\n"
+                "bfe.u32 t0, pw, 8, 8;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A1 ", [t0+6144];\n"
+                "bfe.u32 t0, pw, 16, 8;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A2 ", [t0+6144];\n"
+                "shr.u32 t0, pw, 24;\n mad.lo.u32 t0, t0, 8, " TAB ";\n ld.shared.f64 " A3 ", [t0+6144];\n"
                 GO
                 /* division: operands into (acc, b) in order, then the body */
                 "H_DIV_PP:\n" LOAD_AP "bra.uni H_DIV_AP;\n"
@@ -417,7 +412,7 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 "mov.f64 " A0 ", qr0;\n mov.f64 " A1 ", qr1;\n mov.f64 " A2 ", qr2;\n mov.f64 " A3 ", qr3;\n"
                 GO
                 "DIV_ALLSP:\n"
-                "mul.rn.f64 " A0 ", " A0 ", sd0;\n mul.rn.f64 " A1 ", " A1 ", sd1;\n mul.rn.f64 " A2 ", " A2 ", sd2;\n mul.rn.f64 " A3 ", " A3 ", sd3;\n"
+                DIV_SP(A0, B0) DIV_SP(A1, B1) DIV_SP(A2, B2) DIV_SP(A3, B3)
                 GO
                 /* exp / ln: the rare operands (the slivers next to exp's thresholds, positive subnormals for ln) are known
                    from the inputs; when a lane has one, the inputs are kept in b, the fast path runs for everybody and
@@ -474,27 +469,37 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 "X_SLOW_EXP:\n" UNFETCH "mov.u32 " CODE ", 1001;\n bra.uni XEND;\n"
                 "X_SLOW_LN:\n" UNFETCH "mov.u32 " CODE ", 1002;\n bra.uni XEND;\n"
                 "X_SLOW_MULC:\n" UNFETCH "mov.u32 " CODE ", 1003;\n bra.uni XEND;\n"
+                /* programs longer than one block: the NEXT entry names the row-relative index of the next block's first
+                   entry (y); the row header's w is the row's first entry in the stream.  K1V2_CAP quads are copied (past the
+                   row's end that is the next row / the stream's slack: never dispatched) */
                 "H_NEXT:\n"
+                "vote.sync.all.pred p1, p1, 0xffffffff;\n" /* every lane has fetched the NEXT entry before the buffer is overwritten.  (vote, not
+                                                               bar.warp.sync: a warp barrier inside the loop makes ptxas wrap every
+                                                               dispatch in a BSSY / BSYNC pair — +3 instructions per entry; the warp never
+                                                               diverges in this block and its shared-memory accesses execute in order) */
+                "ld.shared.u32 t0, [" CBASE "+76];\n"     /* header quad (K1V2_HDR * 16), word 3 */
+                "add.u32 ya, ya, t0;\n"
+                "mov.u32 t0, %%laneid;\n"
+                "add.u32 ya, ya, t0;\n"
+                "ld.shared.u64 ga, [" TAB "+10240];\n"    /* K2_TAB_BYTES: the stream's address */
+                "mad.wide.u32 ga, ya, 16, ga;\n"
+                "shl.b32 t0, t0, 4;\n add.u32 ra, t0, " CBASE ";\n"
+                "ld.global.nc.v4.u32 {hx, ya, zb, wd}, [ga];\n"
+                "st.shared.v4.u32 [ra+80], {hx, ya, zb, wd};\n"   /* K1V2_CQ * 16 */
+                "setp.lt.u32 p1, t0, 64;\n"                       /* (K1V2_CAP - 32) lanes copy the tail */
+                "@p1 ld.global.nc.v4.u32 {hx, ya, zb, wd}, [ga+512];\n"
+                "@p1 st.shared.v4.u32 [ra+592], {hx, ya, zb, wd};\n"
+                "vote.sync.all.pred p1, p1, 0xffffffff;\n"
+                "add.u32 " LP ", " CBASE ", 80;\n"
+                "bra.uni FETCH;\n"
                 "H_END:\n"
                 "mov.u32 " CODE ", hx;\n"
                 "XEND:\n"
                 "}\n"
                 : "+d"(a0), "+d"(a1), "+d"(a2), "+d"(a3), "=&d"(b0), "=&d"(b1), "=&d"(b2), "=&d"(b3), "+r"(lp), "=&r"(xc)
-                : "r"(regs_lane), "r"(lane), "l"(gtile), "l"(sobel_tile), "l"(p.pixel_lut), "r"(code), "r"(tabs.exp_addr), "r"(tabs.log_addr), "r"(never)
+                : "r"(regs_lane), "l"(gtile), "l"(sobel_tile), "r"(code), "r"(tab)
                 : "memory");
             if (xc == K2H_END) break;
-            if (xc == K2H_NEXT) { /* programs longer than one block: stage the next K1V2_CAP entries synchronously */
-                __syncwarp();
-                const int m = min(c.n - staged, K1V2_CAP);
-                for (int i = lane; i < m; i += 32) {
-                    const uint4 q = __ldg(stream + c.q + K1V2_CQ + staged + i);
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(code + (K1V2_CQ + i) * 16), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
-                }
-                __syncwarp();
-                staged += m;
-                lp = code + K1V2_CQ * 16;
-                continue;
-            }
             /* rare operands of a heavy operation (a subnormal somewhere, the slivers next to exp's overflow / underflow
                thresholds, |a * c| outside 2^+-1000): the fast path has answered every other sample; patch these */
             if (xc == K2X_SLOW_DIV) { /* operands intact in (a, b) */
@@ -522,8 +527,12 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
+        uint32_t h_dst, h_next, h_flags, h_pad;
+        int c_tile, c_unit;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_pad) : "r"(code + K1V2_HDR * 16) : "memory");
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+32];" : "=r"(c_tile), "=r"(c_unit) : "r"(wst) : "memory");
         if (!TEAM) {
-            double* out = p.bid + (size_t)c.unit * p.row_stride + (size_t)c.tile * K2_TS + lane * 4; /* bid mode: unit = row */
+            double* out = p.bid + (size_t)c_unit * p.row_stride + (size_t)c_tile * K2_TS + lane * 4; /* bid mode: unit = row */
             *reinterpret_cast<double2*>(out) = make_double2(res[0], res[1]);
             *reinterpret_cast<double2*>(out + 2) = make_double2(res[2], res[3]);
         } else {
@@ -538,21 +547,20 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 best_dst[k] = take ? dst : best_dst[k];
             }
             if (h_flags & K1V2_ROW_LAST) {
-                int* out = p.decision + (size_t)c.unit * p.row_stride + (size_t)c.tile * K2_TS + lane * 4;
+                int* out = p.decision + (size_t)c_unit * p.row_stride + (size_t)c_tile * K2_TS + lane * 4;
                 *reinterpret_cast<int4*>(out) = make_int4(best_dst[0], best_dst[1], best_dst[2], best_dst[3]);
             }
         }
-        c = nx; cur ^= 1;
+        code = 2 * mycode + K2_BUF * 16 - code; /* the other buffer */
     }
     k2_cp_async_wait_all();
 }
 
-size_t tpgx_bid2_smem_bytes() {
-    return (size_t)K2_NW * K1V2_SLOTS * K2_TS * 8 + (size_t)K2_NW * 2 * K2_BUF * 16 + K2_TAB_BYTES;
-}
+size_t tpgx_bid2_smem_bytes(int slots) { return (size_t)K2_HEAD_BYTES + (size_t)K2_NW * (K2_WARP_FIXED + (size_t)slots * K2_TS * 8); }
 
 cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team, int nb_ctas, cudaStream_t st) {
-    const size_t smem = tpgx_bid2_smem_bytes();
+    if (p.slots < 1 || p.slots > K1V2_SLOTS) return cudaErrorInvalidValue;
+    const size_t smem = tpgx_bid2_smem_bytes(p.slots);
     cudaError_t e = cudaMemsetAsync(p.work_counter, 0, 4, st);
     if (e != cudaSuccess) return e;
     if (team) {
@@ -579,7 +587,7 @@ __global__ void tpgx_k1v2_encode_kernel(const uint32_t* __restrict__ code, const
     double* cq = reinterpret_cast<double*>(stream + d.x);
     for (int k = 0; k < 2 * K1V2_HDR; k++) cq[k] = k < nb_constants ? constants[(size_t)pidx * nb_constants + k] : 0.0;
     stream[d.x + K1V2_HDR] = make_uint4(row_dst ? (uint32_t)row_dst[row] : 0u, row + 1 < nb_rows ? (uint32_t)desc[row + 1].y : 0u,
-                                        row_flags ? (uint32_t)row_flags[row] : (K1V2_ROW_FIRST | K1V2_ROW_LAST), 0u);
+                                        row_flags ? (uint32_t)row_flags[row] : (K1V2_ROW_FIRST | K1V2_ROW_LAST), (uint32_t)(d.x + K1V2_CQ));
     const tpgx_k1v2_info info = tpgx_k1v2_encode(code + prog_offset[pidx], prog_offset[pidx + 1] - prog_offset[pidx], K2_TS, (uint32_t)width,
                                                  (uint32_t)hw, (uint32_t)nwin, reinterpret_cast<tpgx_k1_quad*>(stream + d.x + K1V2_CQ));
     if (!info.ok || info.entries != d.y || info.slots > K1V2_SLOTS) atomicOr(flags, 4);

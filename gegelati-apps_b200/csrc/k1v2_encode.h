@@ -16,7 +16,7 @@
  *   handler specialisation  one handler per (operation, kind of A, kind of B), kinds being accumulator /
  *       slot / pixel; commutative operations are canonicalised (the accumulator or the slot first).
  *   blocks                  K1 v2 stages K1V2_CAP entries at a time in shared memory; longer programs are
- *       chained with NEXT entries, every program ends with END.
+ *       chained with NEXT entries (y = row-relative index of the next block's first entry), every program ends with END.
  *
  * The function compiles for the host (slot / entry counts during planning, unit tests) and for the device
  * (the stream itself is written by tpgx_k1v2_encode_kernel from the generic code already in HBM).
@@ -28,7 +28,7 @@
 
 #define K1V2_SLOTS 5      /* shared-memory register slots per warp */
 #define K1V2_CQ 5         /* quads at the head of a row's stream: 4 of program constants (8 doubles), then the row header */
-#define K1V2_HDR 4        /* header quad {x = destination of the edge, y = entries of the NEXT row of the stream, z = flags} */
+#define K1V2_HDR 4        /* header quad {x = destination of the edge, y = entries of the NEXT row of the stream, z = flags, w = the row's first entry in the stream} */
 #define K1V2_ROW_LAST 1u  /* flags: last row (edge) of its unit (team) */
 #define K1V2_ROW_FIRST 2u /* first row of its unit */
 #define K1V2_CAP 36       /* entries staged at a time */
@@ -93,7 +93,7 @@ TPGX_HOSTDEV static inline tpgx_k1v2_info tpgx_k1v2_encode(const uint32_t* words
     int pos = 0; /* entry position within the staged block */
     auto emit = [&](uint32_t h, uint32_t y, uint32_t z, uint32_t w) {
         if (pos == K1V2_CAP - 1 && h != K2H_END) { /* the block's last entry chains to the next block */
-            if (out) { out[info.entries].x = K2H_NEXT; out[info.entries].y = out[info.entries].z = out[info.entries].w = 0; }
+            if (out) { out[info.entries].x = K2H_NEXT; out[info.entries].y = (uint32_t)info.entries + 1u; out[info.entries].z = out[info.entries].w = 0; }
             info.entries++;
             pos = 0;
         }

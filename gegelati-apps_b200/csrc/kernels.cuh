@@ -45,6 +45,7 @@ struct tpgx_bid2_params {
     const double* pixel_lut;
     const double* sobel;
     int nwin;
+    int slots;                   /* shared-memory register slots per warp: the largest need of the shard's programs (<= K1V2_SLOTS) */
     int nb_units, units_per_item, items_per_tile, nb_items;
     unsigned int* work_counter;  /* next unclaimed item (zeroed by the launcher)                           */
     double* bid;
@@ -52,7 +53,7 @@ struct tpgx_bid2_params {
     int32_t* decision;
     int tie_break;
 };
-size_t tpgx_bid2_smem_bytes();
+size_t tpgx_bid2_smem_bytes(int slots);
 cudaError_t tpgx_launch_bid2(const tpgx_bid2_params& p, bool team_mode, int nb_ctas, cudaStream_t st);
 cudaError_t tpgx_launch_k1v2_encode(const uint32_t* code, const int32_t* prog_offset, const double* constants, int nb_constants,
                                     const int32_t* active_prog, const int2* desc, const int32_t* row_dst, const uint8_t* row_flags, int nb_rows,

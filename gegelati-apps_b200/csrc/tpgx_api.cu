@@ -57,6 +57,7 @@ struct ShardPlan { /* programs reachable from a root range, cached between evalu
     bool team_mode = false; /* [UP] evaluateTeam fused into K1 (acyclic shard, no bid output, little program sharing) */
     bool want_bid = false;
     bool k1_v2 = false;   /* the threaded interpreter (k1_bid2.cu) runs this shard */
+    int k1_slots = 1;     /* ... with this many shared-memory register slots per warp (the largest need of its programs) */
     int nb_units = 0;     /* teams in team mode, programs otherwise */
     int64_t active_lines = 0, active_flops = 0;
 };
@@ -257,11 +258,14 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         const char* v2env = getenv("TPGX_K1_V2");
         bool v2 = !(v2env && v2env[0] == '0') && !ctx->uses_ext && !ctx->uses_int && ts == 128 && ctx->variant == 0 &&
                   ctx->v2_entries.size() == (size_t)f.nb_programs;
+        int slots = 1;
         for (int row = 0; v2 && row < nrows; row++) {
             const int p = ctx->h_active[row];
             if (ctx->v2_entries[p] < 0 || ctx->v2_slots[p] > K1V2_SLOTS) v2 = false;
+            else slots = std::max(slots, (int)ctx->v2_slots[p]);
         }
         pl.k1_v2 = v2;
+        pl.k1_slots = slots;
         std::vector<int32_t> desc(2 * (size_t)nrows);
         int64_t nq = 0;
         for (int row = 0; row < nrows; row++) {
@@ -416,6 +420,8 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.sobel = ctx->nwin ? ctx->d_sobel.as<double>() + (size_t)t0 * 2 * ctx->nwin * ts : nullptr;
             bp.nwin = ctx->nwin;
             bp.nb_units = nU;
+            bp.slots = ctx->plan.k1_slots;
+            if (const char* v = getenv("TPGX_K1_SLOTS")) bp.slots = std::min(K1V2_SLOTS, std::max(bp.slots, atoi(v))); /* experiments: more than needed */
             /* work items = (tile, group of units), claimed warp by warp: ~20 items per resident warp when there is that
                much work (dynamic balance to the last item), at most 8 teams / 32 programs per item */
             const int64_t warps = (int64_t)ctx->sm_count * 32;

@@ -84,6 +84,7 @@ def run_v2(quads, slots, consts, px, magn, dirn, names):
                 return acc, nb_st
             if name == "NEXT":
                 assert i % CAP == CAP - 1, "NEXT must be the last entry of a staged block"
+                assert y == i + 1, "NEXT names the row-relative index of the next block's first entry"
                 continue
             if name == "ST":
                 assert w % 1024 == 0 and w // 1024 < slots
