@@ -178,9 +178,10 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
  * handler fetches the NEXT entry and ends with its own indirect branch) executes 4 % fewer instructions and is 21 % SLOWER on
  * C2: 28 BRX sites plus 3.5 KB more code drop the instruction-cache hit rate from 99.3 % to 93 % (profiles/r2_k1v2_experiments.md). */
 #define PF ""
-/* Sobel planes: two 16-byte loads per lane of one 32-byte sector.  L1::no_allocate was measured 4.6 % slower (the second load
-   misses the sector the first one brought in) */
-#define LDSOB "ld.global.nc.v2.f64"
+/* Sobel planes: the lane's 4 samples are one 32-byte sector, read once per (program, tile) by one 256-bit load that does
+   not displace anything in what is left of L1 (8.22 -> 8.15 ms on C2).  As two 16-byte loads, L1::no_allocate was 4.6 %
+   SLOWER: the second load missed the sector the first one had brought in. */
+#define LDSOB "ld.global.nc.L1::no_allocate.v4.f64"
 #define GO "bra.uni FETCH;\n"
 #define UNFETCH ""
 
@@ -368,8 +369,7 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
                 "H_SOBD:\n"
                 "mad.wide.u32 ga, ya, 32, " SOBEL ";\n"
                 PF
-                LDSOB " {" A0 ", " A1 "}, [ga];\n"
-                LDSOB " {" A2 ", " A3 "}, [ga+16];\n"
+                LDSOB " {" A0 ", " A1 ", " A2 ", " A3 "}, [ga];\n"
                 GO
                 /* exp / ln of a pixel: 256-entry tables */
                 "H_LUTL:\n"
