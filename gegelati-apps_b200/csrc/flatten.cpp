@@ -8,6 +8,7 @@
  *   - static reduction of every location,
  *   - "never written => 0.0" register reads marked so the device needs no register clear.
  */
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -103,6 +104,14 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     if (src.size() > 2) return fail(TPGX_ERR_UNSUPPORTED, "device bytecode addresses at most 2 data sources");
     SourceMap sm{cfg, src};
     const int R = cfg.nb_registers;
+    const bool trace = getenv("TPGX_TRACE_FLATTEN") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace) return;
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[tpgx] flatten: %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
 
     tpgx_flat_graph& f = *out;
     f = tpgx_flat_graph();
@@ -130,14 +139,37 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     }
     const int nsrc = sm.total();
     std::vector<uint32_t> space_tab((size_t)nsrc * 8, 0u);
+    std::vector<uint64_t> space_inv((size_t)nsrc * 8, 0u); /* loc % space without a division: a mod d = ((M * a mod 2^64) * d) >> 64, M = ceil(2^64 / d) */
     for (int sidx = 0; sidx < nsrc; sidx++)
-        for (int t = 0; t <= TPGX_T_W; t++) space_tab[(size_t)sidx * 8 + t] = sm.space(sidx, t);
+        for (int t = 0; t <= TPGX_T_W; t++) {
+            const uint32_t sp = sm.space(sidx, t);
+            space_tab[(size_t)sidx * 8 + t] = sp;
+            space_inv[(size_t)sidx * 8 + t] = sp ? UINT64_C(0xFFFFFFFFFFFFFFFF) / sp + 1 : 0;
+        }
+    auto reduce = [](uint32_t a, uint32_t sp, uint64_t inv) -> uint32_t {
+        return a < sp ? a : (uint32_t)(((unsigned __int128)(inv * a) * sp) >> 64);
+    };
+    /* [UP] Array2DWrapper window address -> top-left element, per environment source (addresses are below TPGX_MAX_LOC) */
+    std::vector<uint16_t> win_tab(src.size() * (size_t)TPGX_MAX_LOC, 0);
+    for (size_t ks = 0; ks < src.size(); ks++) {
+        const uint32_t ww = src[ks].width > 2 ? (uint32_t)src[ks].width - 2u : 1u;
+        for (uint32_t a = 0; a < TPGX_MAX_LOC; a++) win_tab[ks * TPGX_MAX_LOC + a] = (uint16_t)std::min<uint32_t>(65535u, (a / ww) * (uint32_t)src[ks].width + (a % ww));
+    }
     const uint32_t nI = (uint32_t)opcode.size();
-    tpgx_parallel_blocks(P, 256, [&](int pb, int pe, int w) {
+    /* the programs to flatten: all, or the ones reachable from this context's root shard (the others stay empty and are never
+       run).  The host threads split THIS list, so a shard of 1/N of the graph takes 1/N of the time on every thread */
+    std::vector<int32_t> sel;
+    if (prog_mask) {
+        sel.reserve((size_t)P);
+        for (int p = 0; p < P; p++) if ((*prog_mask)[(size_t)p]) sel.push_back(p);
+    }
+    const int nsel = prog_mask ? (int)sel.size() : P;
+    lap("setup");
+    tpgx_parallel_blocks(nsel, 128, [&](int pb, int pe, int w) {
         Err& er = errs[w];
         auto bad = [&](tpgx_status st, const std::string& m) { if (er.st == TPGX_OK) { er.st = st; er.msg = m; } };
-        for (int p = pb; p < pe && er.st == TPGX_OK; p++) {
-            if (prog_mask && !(*prog_mask)[(size_t)p]) continue; /* not reachable from this context's shard: left empty, never run */
+        for (int q = pb; q < pe && er.st == TPGX_OK; q++) {
+            const int p = prog_mask ? sel[(size_t)q] : q;
             const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
             const tpgx_line* L = g->lines + b;
             uint8_t* kp = keep.data() + b;
@@ -162,7 +194,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                         ok = false;
                         break;
                     }
-                    if (sidx == 0) reads |= 1u << (l.loc[k] < sp ? l.loc[k] : l.loc[k] % sp);
+                    if (sidx == 0) reads |= 1u << reduce(l.loc[k], sp, space_inv[(size_t)sidx * 8 + o.type[k]]);
                 }
                 if (!ok) break;
                 const uint32_t k1 = (live >> l.destination) & 1u;
@@ -177,6 +209,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
             }
         }
     });
+    lap("pass 1 (introns)");
     for (const Err& er : errs) if (er.st != TPGX_OK) return fail(er.st, er.msg);
     if (keep_out) *keep_out = keep;
     f.prog_offset.assign((size_t)P + 1, 0);
@@ -185,10 +218,17 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     f.total_lines = f.prog_offset[P];
     f.total_introns = total_in - f.total_lines;
 
-    /* pass 2 (parallel): encode the effective lines */
-    tpgx_parallel_blocks(P, 256, [&](int pb, int pe, int w) {
+    lap("offsets");
+    /* pass 2 (parallel): encode the effective lines; while a program's words are hot, the count pass of the K1 v2 stream
+       encoder (entries, slots) and the opcodes present */
+    f.v2_entries.assign((size_t)P, -1);
+    f.v2_slots.assign((size_t)P, 0);
+    std::vector<uint32_t> op_seen(tpgx_parallel_workers(), 0u);
+    tpgx_parallel_blocks(nsel, 128, [&](int pb, int pe, int w) {
         Err& er = errs[w];
-        for (int p = pb; p < pe && er.st == TPGX_OK; p++) {
+        uint32_t seen = 0;
+        for (int q = pb; q < pe && er.st == TPGX_OK; q++) {
+            const int p = prog_mask ? sel[(size_t)q] : q;
             const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
             const tpgx_line* L = g->lines + b;
             const int n = (int)(e - b);
@@ -203,16 +243,13 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                 for (int k = 0; k < o.nb; k++) {
                     const int s = (int)l.src[k];
                     const uint32_t sp = space_tab[(size_t)s * 8 + o.type[k]];
-                    uint32_t a = l.loc[k] < sp ? l.loc[k] : l.loc[k] % sp;
+                    uint32_t a = reduce(l.loc[k], sp, space_inv[(size_t)s * 8 + o.type[k]]);
                     if (s == 0) { kind[k] = TPGX_KIND_REG; loc[k] = ((written >> a) & 1u) ? a : TPGX_LOC_ZERO; }
                     else if (cfg.nb_constants > 0 && s == 1) { kind[k] = TPGX_KIND_CONST; loc[k] = a; }
                     else {
                         const int ks = s - sm.first_env();
                         kind[k] = ks == 0 ? TPGX_KIND_SRC0 : TPGX_KIND_SRC1;
-                        if (o.type[k] == TPGX_T_W) { /* [UP] Array2DWrapper window address -> top-left element */
-                            const uint32_t ww = (uint32_t)src[ks].width - 2u;
-                            a = (a / ww) * (uint32_t)src[ks].width + (a % ww);
-                        }
+                        if (o.type[k] == TPGX_T_W) a = a < TPGX_MAX_LOC ? win_tab[(size_t)ks * TPGX_MAX_LOC + a] : TPGX_MAX_LOC;
                         if (a >= TPGX_MAX_LOC) {
                             if (er.st == TPGX_OK) { er.st = TPGX_ERR_UNSUPPORTED; er.msg = fmt("program %ld line %ld: location %ld exceeds the 10-bit device field", p, i, a); }
                             a = 0;
@@ -223,10 +260,16 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                 *out_code++ = tpgx_pack_line((uint32_t)o.op, l.destination, kind[0], loc[0], kind[1], loc[1]);
                 written |= 1u << l.destination;
                 flops += o.flops;
+                seen |= 1u << (o.op & 31);
             }
             f.prog_flops[p] = flops;
+            const tpgx_k1v2_info info = tpgx_k1v2_encode(f.code.data() + f.prog_offset[p], f.prog_offset[p + 1] - f.prog_offset[p], 128u, 28u, 784u, 676u, nullptr);
+            if (info.ok) { f.v2_entries[p] = info.entries; f.v2_slots[p] = (uint8_t)info.slots; }
         }
+        op_seen[w] |= seen;
     });
+    for (uint32_t m : op_seen) f.op_mask |= m;
+    lap("pass 2 (encode + K1 v2 counts)");
     for (const Err& er : errs) if (er.st != TPGX_OK) return fail(er.st, er.msg);
 
     f.nb_teams = g->nb_teams;
@@ -247,6 +290,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     f.nb_roots = g->nb_roots;
     f.root_team.assign(g->root_team, g->root_team + g->nb_roots);
     for (int r : f.root_team) if (r < 0 || r >= g->nb_teams) return fail(TPGX_ERR_BAD_ARG, "root team out of range");
+    lap("graph arrays");
     return TPGX_OK;
 }
 

@@ -101,6 +101,23 @@ TPGX_HOSTDEV static inline tpgx_k1v2_info tpgx_k1v2_encode(const uint32_t* words
         info.entries++;
         pos++;
     };
+    /* last_read[i]: the last line reading the value line i defines (-1: none), in one forward pass: a line's register
+       operands name the lines that defined them */
+    int16_t last_read[K1V2_MAX_LINES];
+    {
+        int def_line[TPGX_MAX_REGS];
+        for (int r = 0; r < TPGX_MAX_REGS; r++) def_line[r] = -1;
+        for (int i = 0; i < n; i++) {
+            const uint32_t w = words[i];
+            const tpgx_op_info oi = tpgx_get_op_info((int)(w & 31u));
+            const uint32_t f[2] = {(w >> 8) & 0xfffu, w >> 20};
+            for (int k = 0; k < oi.nb_operands && k < 2; k++)
+                if (oi.type[k] == TPGX_T_D && (f[k] >> 10) == TPGX_KIND_REG && (f[k] & 1023u) < TPGX_MAX_REGS && def_line[f[k] & 1023u] >= 0)
+                    last_read[def_line[f[k] & 1023u]] = (int16_t)i;
+            last_read[i] = -1;
+            def_line[(w >> 5) & 7u] = i;
+        }
+    }
     int slot_of[TPGX_MAX_REGS];   /* slot holding the current value of each TPG register, -1: none */
     int def_of[TPGX_MAX_REGS];    /* line that wrote it */
     int last_use_of[TPGX_MAX_REGS]; /* last line reading the current value */
@@ -157,16 +174,8 @@ TPGX_HOSTDEV static inline tpgx_k1v2_info tpgx_k1v2_encode(const uint32_t* words
         case TPGX_OP_SOBEL_DIR: emit(K2H_SOBD, val[0] + nwin * (ts / 4u), 0, 0); break;
         default: info.ok = 0; break;
         }
-        /* the new value of dst: who reads it, and until when */
-        int last = -1;
-        for (int j = i + 1; j < n; j++) {
-            const uint32_t wj = words[j];
-            const tpgx_op_info oj = tpgx_get_op_info((int)(wj & 31u));
-            const uint32_t fj[2] = {(wj >> 8) & 0xfffu, wj >> 20};
-            for (int k = 0; k < oj.nb_operands && k < 2; k++)
-                if (oj.type[k] == TPGX_T_D && (fj[k] >> 10) == TPGX_KIND_REG && (fj[k] & 1023u) == dst) last = j;
-            if (((wj >> 5) & 7u) == dst) break; /* overwritten */
-        }
+        /* the new value of dst: the last line that reads it before it is overwritten */
+        const int last = last_read[i];
         if (slot_of[dst] >= 0) { free_mask |= 1u << slot_of[dst]; slot_of[dst] = -1; } /* stale value overwritten (cannot be live) */
         def_of[dst] = i;
         last_use_of[dst] = last;

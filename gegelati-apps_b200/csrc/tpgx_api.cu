@@ -33,9 +33,12 @@ struct Trace {
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    bool borrowed = false; /* p belongs to another context's buffer (pipeline lanes share the observation tiles) */
+    void alias(const DevBuf& o) { release(); p = o.p; cap = o.cap; borrowed = o.p != nullptr; }
     cudaError_t ensure(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p && !borrowed) cudaFree(p);
+        borrowed = false;
         p = nullptr;
         cap = 0;
         size_t want = bytes + bytes / 8 + 256;
@@ -44,7 +47,7 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want;
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -77,8 +80,6 @@ struct tpgx_ctx {
     int variant = 0;
     int sm_count = 148;
     size_t bid_budget = (size_t)16 << 30;
-    std::vector<int32_t> v2_entries;  /* per program: entries of its K1 v2 stream, -1 = not encodable for v2 */
-    std::vector<uint8_t> v2_slots;    /* per program: shared-memory slots it needs there */
 
     DevBuf d_pixel_lut, d_sobel, d_tm_team, d_tm_dst, d_tm_stat, d_tm_roots, d_decision;
     DevBuf d_code, d_k1_stream, d_k1_desc, d_prog_off, d_consts, d_team_off, d_edge_dst, d_edge_row, d_edge_lines, d_roots, d_active, d_edge_prog;
@@ -102,7 +103,10 @@ struct tpgx_ctx {
     ShardPlan plan;
     std::vector<int32_t> h_edge_row, h_active;
     std::vector<uint8_t> h_stage_in, h_stage_out; /* episode calls: one transfer each way */
+    std::vector<tpgx_ctx*> lanes;        /* tpgx_evaluate_graph_classification_allgather: contexts of the pipeline's slices (owned) */
+    bool tiles_shared = false;           /* a lane: d_tiles / d_labels / d_sobel are the parent's, prepared for the request */
     void* pin_ring = nullptr;            /* page-locked staging ring of upload() */
+    int* h_status = nullptr;             /* page-locked copy of d_status ({device status, -, K1 encoder flags, -}) */
     size_t pin_used = 0;
     bool pin_failed = false;
 
@@ -135,7 +139,9 @@ static cudaError_t wait_for_observations(tpgx_ctx* ctx) {
 
 /* Small host -> device copies (graph arrays, plans, per-call inputs: a dozen per generation) go through a page-locked ring:
    a copy from pageable memory is staged by the driver and blocks the host, one from page-locked memory is only enqueued.
-   The ring wraps after a stream synchronisation, so a slot is never reused while a copy may still read it. */
+   The ring wraps after a stream synchronisation, so a slot is never reused while a copy may still read it.
+   Contract: the source is consumed when upload() returns (copied into the ring, or staged by the driver when it is
+   pageable memory going the direct way), so callers may pass locals and need no synchronisation of their own. */
 tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes, bool through_ring = true) {
     CU(b.ensure(bytes ? bytes : 16));
     if (!bytes) return TPGX_OK;
@@ -236,7 +242,6 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         if ((st = upload(ctx, ctx->d_tm_stat, stat.data(), stat.size() * 4)) != TPGX_OK) return st;
         if ((st = upload(ctx, ctx->d_tm_dst, dsts.data(), dsts.size() * 4)) != TPGX_OK) return st;
         if ((st = upload(ctx, ctx->d_tm_roots, roots.data(), roots.size() * 4)) != TPGX_OK) return st;
-        CU(cudaStreamSynchronize(ctx->stream)); /* locals */
     } else {
         ctx->h_active = uniq;
         pl.nb_units = (int)uniq.size();
@@ -257,12 +262,12 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         const int nrows = (int)ctx->h_active.size();
         const char* v2env = getenv("TPGX_K1_V2");
         bool v2 = !(v2env && v2env[0] == '0') && !ctx->uses_ext && !ctx->uses_int && ts == 128 && ctx->variant == 0 &&
-                  ctx->v2_entries.size() == (size_t)f.nb_programs;
+                  f.v2_entries.size() == (size_t)f.nb_programs;
         int slots = 1;
         for (int row = 0; v2 && row < nrows; row++) {
             const int p = ctx->h_active[row];
-            if (ctx->v2_entries[p] < 0 || ctx->v2_slots[p] > K1V2_SLOTS) v2 = false;
-            else slots = std::max(slots, (int)ctx->v2_slots[p]);
+            if (f.v2_entries[p] < 0 || f.v2_slots[p] > K1V2_SLOTS) v2 = false;
+            else slots = std::max(slots, (int)f.v2_slots[p]);
         }
         pl.k1_v2 = v2;
         pl.k1_slots = slots;
@@ -271,7 +276,7 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
         for (int row = 0; row < nrows; row++) {
             const int p = ctx->h_active[row];
             desc[2 * row] = (int32_t)nq;
-            desc[2 * row + 1] = v2 ? ctx->v2_entries[p] : f.prog_offset[p + 1] - f.prog_offset[p];
+            desc[2 * row + 1] = v2 ? f.v2_entries[p] : f.prog_offset[p + 1] - f.prog_offset[p];
             nq += (v2 ? K1V2_CQ : TPGX_K1_CQ) + desc[2 * row + 1];
         }
         if ((st = upload(ctx, ctx->d_k1_desc, desc.data(), desc.size() * 4)) != TPGX_OK) return st;
@@ -294,7 +299,6 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
                 }
                 if ((st = upload(ctx, ctx->d_k2_rflags, rflags.data(), rflags.size())) != TPGX_OK) return st;
                 if ((st = upload(ctx, ctx->d_k2_ufirst, ufirst.data(), ufirst.size() * 4)) != TPGX_OK) return st;
-                CU(cudaStreamSynchronize(ctx->stream)); /* locals */
                 d_row_flags = ctx->d_k2_rflags.as<uint8_t>();
             }
             CU(tpgx_launch_k1v2_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
@@ -306,10 +310,8 @@ tpgx_status make_plan(tpgx_ctx* ctx, int rb, int re, int ts, bool want_bid) {
             CU(tpgx_launch_k1_encode(ctx->d_code.as<uint32_t>(), ctx->d_prog_off.as<int32_t>(), ctx->d_consts.as<double>(), ctx->cfg.nb_constants,
                                      ctx->d_active.as<int32_t>(), ctx->d_k1_desc.as<int2>(), nrows, ts, ctx->obs_width, ctx->obs_hw, ctx->d_k1_stream.as<uint4>(),
                                      d_flags, ctx->stream));
-        int flags = 0;
-        CU(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream)); /* desc is a local */
-        if (flags & 4) return fail(ctx, TPGX_ERR_CUDA, "K1 v2 encoder: device stream disagrees with the host's entry / slot counts");
+        /* the encoder's verdict (flag 4: its entry / slot counts disagree with the host's) is read back with the device status
+           at the end of the evaluation: no synchronisation here */
         /* which build of K1 (MNIST set only / extended) is known on the host from the opcode table */
         if (ctx->uses_int) return fail(ctx, TPGX_ERR_UNSUPPORTED, "int-typed instruction in a program evaluated on a uint8 image source");
         pl.k1_ext = ctx->uses_ext;
@@ -328,6 +330,35 @@ tpgx_status sobel_planes(tpgx_ctx* ctx, int64_t nTiles, int ts) {
     CU(ctx->d_sobel.ensure((size_t)nTiles * 2 * ctx->nwin * ts * 8));
     CU(tpgx_launch_sobel_planes(ctx->d_tiles.as<uint8_t>(), nTiles, ctx->obs_hw, d.height, d.width, ts, ctx->d_pixel_lut.as<double>(),
                                 ctx->d_sobel.as<double>(), ctx->stream));
+    return TPGX_OK;
+}
+
+/* Observation tiles of a request: the identity packing made at upload time, or a re-tiling of the indexed samples (and their
+   Sobel planes).  A pipeline lane uses its parent's, prepared once for the request. */
+tpgx_status sobel_planes(tpgx_ctx* ctx, int64_t nTiles, int ts);
+tpgx_status prepare_tiles(tpgx_ctx* ctx, const tpgx_classif_request* req, int ts) {
+    const int64_t nS = req->nb_samples;
+    const int64_t nTiles = (nS + ts - 1) / ts;
+    const int hw = ctx->obs_hw;
+    tpgx_status st;
+    const bool identity = (req->sample_index == nullptr) && nS == ctx->nb_obs;
+    if (!ctx->tiles_shared && !(identity && ctx->tiles_identity_valid && ctx->tiles_ts == ts)) {
+        const int32_t* d_index = nullptr;
+        if (req->sample_index) {
+            for (int64_t i = 0; i < nS; i++)
+                if (req->sample_index[i] < 0 || req->sample_index[i] >= ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "sample_index out of range");
+            if ((st = upload(ctx, ctx->d_index, req->sample_index, (size_t)nS * 4)) != TPGX_OK) return st;
+            d_index = ctx->d_index.as<int32_t>();
+        }
+        CU(ctx->d_tiles.ensure((size_t)nTiles * (hw + 1) * ts));
+        CU(ctx->d_labels.ensure((size_t)nTiles * ts));
+        CU(tpgx_launch_pack(ctx->obs_dev, d_index, nS, ctx->nb_obs, hw, ts, ctx->d_tiles.as<uint8_t>(), ctx->labels_dev,
+                            ctx->d_labels.as<uint8_t>(), ctx->stream));
+        if ((st = sobel_planes(ctx, nTiles, ts)) != TPGX_OK) return st;
+        ctx->tiles_identity_valid = identity;
+        ctx->tiles_ts = ts;
+    }
+
     return TPGX_OK;
 }
 
@@ -364,24 +395,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     etr.lap("plan");
     const int nA = ctx->plan.nb_active;
 
-    /* observation tiles */
-    const bool identity = (req->sample_index == nullptr) && nS == ctx->nb_obs;
-    if (!(identity && ctx->tiles_identity_valid && ctx->tiles_ts == ts)) {
-        const int32_t* d_index = nullptr;
-        if (req->sample_index) {
-            for (int64_t i = 0; i < nS; i++)
-                if (req->sample_index[i] < 0 || req->sample_index[i] >= ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "sample_index out of range");
-            if ((st = upload(ctx, ctx->d_index, req->sample_index, (size_t)nS * 4)) != TPGX_OK) return st;
-            d_index = ctx->d_index.as<int32_t>();
-        }
-        CU(ctx->d_tiles.ensure((size_t)nTiles * (hw + 1) * ts));
-        CU(ctx->d_labels.ensure((size_t)nTiles * ts));
-        CU(tpgx_launch_pack(ctx->obs_dev, d_index, nS, ctx->nb_obs, hw, ts, ctx->d_tiles.as<uint8_t>(), ctx->labels_dev,
-                            ctx->d_labels.as<uint8_t>(), ctx->stream));
-        if ((st = sobel_planes(ctx, nTiles, ts)) != TPGX_OK) return st;
-        ctx->tiles_identity_valid = identity;
-        ctx->tiles_ts = ts;
-    }
+    if ((st = prepare_tiles(ctx, req, ts)) != TPGX_OK) return st;
 
     etr.lap("tiles + Sobel planes");
     /* pass planning: keep the bid matrix (or, in team mode, the decision matrix) of one pass within the budget */
@@ -399,7 +413,7 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     CU(ctx->d_status.ensure(16));
     CU(cudaMemsetAsync(ctx->d_conf.p, 0, (size_t)nR * C * C * 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_counters.p, 0, 64, ctx->stream));
-    CU(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, 8, ctx->stream)); /* words 2.. are the K1 encoder's flags, set when the plan was made */
     if (want_action) CU(ctx->d_action.ensure((size_t)nR * nS));
     etr.lap("buffers");
 
@@ -525,13 +539,22 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
     return TPGX_OK;
 }
 
-tpgx_status check_device_status(tpgx_ctx* ctx, int status) {
+tpgx_status check_device_status(tpgx_ctx* ctx, int status, int encoder_flags = 0) {
+    if (encoder_flags & 4) return fail(ctx, TPGX_ERR_CUDA, "K1 v2 encoder: device stream disagrees with the host's entry / slot counts");
     if (status & TPGX_DEV_NO_EDGE) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "a team had no admissible outgoing edge (the reference throws \"No outgoing edge to evaluate\")");
     if (status & TPGX_DEV_PATH_TOO_LONG) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "root->action path longer than TPGX_MAX_PATH teams");
     if (status & TPGX_DEV_BAD_ACTION) return fail(ctx, TPGX_ERR_GRAPH_INVALID, "action id outside the environment's action range (the reference throws in doAction)");
     if (status & TPGX_DEV_BAD_LABEL) return fail(ctx, TPGX_ERR_BAD_ARG, "observation label outside [0, nb_classes) (the reference's classificationTable.at() throws)");
     if (status & TPGX_DEV_RNG_EXHAUSTED) return fail(ctx, TPGX_ERR_STATE, "episode consumed more RNG draws than the table holds");
     return TPGX_OK;
+}
+
+/* End of an evaluation: device status and encoder flags come back with the stream's last copy (one synchronisation) */
+static tpgx_status finish_stream(tpgx_ctx* ctx) {
+    if (!ctx->h_status) CU(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_status), 64, cudaHostAllocDefault));
+    CU(cudaMemcpyAsync(ctx->h_status, ctx->d_status.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return check_device_status(ctx, ctx->h_status[0], ctx->h_status[2]);
 }
 
 /* ---- NCCL, bound at run time: a Python process that imported torch already has libnccl.so.2 mapped (the loader hands
@@ -690,10 +713,7 @@ tpgx_status tpgx_evaluate_classification_allgather(tpgx_ctx* ctx, const tpgx_cla
     if (st != TPGX_OK) return st;
     if (ctx->comm_world > 1) NC(g_nccl.AllGather(gather + (size_t)ctx->comm_rank * count, gather, count, ncclDouble, ctx->comm, ctx->stream));
     if (records_all) CU(cudaMemcpyAsync(records_all, gather, (size_t)total_roots * (req->nb_classes + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    int status = 0;
-    CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
-    return check_device_status(ctx, status);
+    return finish_stream(ctx);
 }
 
 tpgx_status tpgx_evaluate_classification_allgather_all(tpgx_ctx* const* ctxs, int32_t n, const tpgx_classif_request* req, int32_t total_roots,
@@ -719,10 +739,7 @@ tpgx_status tpgx_evaluate_classification_allgather_all(tpgx_ctx* const* ctxs, in
         tpgx_ctx* c = ctxs[i];
         cudaSetDevice(c->cfg.device);
         if (i == 0 && records_all) CU(cudaMemcpyAsync(records_all, gather[0], (size_t)total_roots * (req->nb_classes + 1) * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        int status = 0;
-        CU(cudaMemcpy(&status, c->d_status.p, 4, cudaMemcpyDeviceToHost));
-        const tpgx_status st = check_device_status(c, status);
+        const tpgx_status st = finish_stream(c);
         if (st != TPGX_OK) { if (c != ctx) ctx->err = c->err; return st; }
     }
     return TPGX_OK;
@@ -769,6 +786,8 @@ tpgx_status tpgx_create(const tpgx_config* cfg, tpgx_ctx** out) {
 
 tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     if (!ctx) return TPGX_OK;
+    for (tpgx_ctx* lane : ctx->lanes) tpgx_destroy(lane);
+    ctx->lanes.clear();
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->obs_stream) cudaStreamSynchronize(ctx->obs_stream);
@@ -780,6 +799,7 @@ tpgx_status tpgx_destroy(tpgx_ctx* ctx) {
     for (DevBuf& b : ctx->d_scratch) b.release();
     tpgx_comm_release(ctx);
     if (ctx->pin_ring) cudaFreeHost(ctx->pin_ring);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
     for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
     if (ctx->obs_stream) { cudaStreamSynchronize(ctx->obs_stream); cudaStreamDestroy(ctx->obs_stream); }
     if (ctx->obs_ready) cudaEventDestroy(ctx->obs_ready);
@@ -818,11 +838,12 @@ tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_de
     return TPGX_OK;
 }
 
-static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only);
-tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, false); }
-tpgx_status tpgx_set_graph_sharded(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, true); }
+static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only, int range_begin, int range_end);
+tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, false, -1, -1); }
+tpgx_status tpgx_set_graph_sharded(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, true, -1, -1); }
 
-static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only) {
+/* range_begin >= 0: only the programs reachable from roots [range_begin, range_end) (a pipeline slice) */
+static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only, int range_begin, int range_end) {
     if (!ctx) return TPGX_ERR_BAD_ARG;
     if (ctx->opcode.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: instruction table not set");
     if (ctx->src.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: data sources not set");
@@ -834,10 +855,12 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
        host work); the rest of the graph stays empty and evaluating a root outside the shard is refused */
     std::vector<uint8_t> mask;
     ctx->flat_root_begin = 0; ctx->flat_root_end = -1;
-    if (shard_only && ctx->comm_world > 1 && g && g->nb_roots > 0 && g->nb_teams > 0 && g->nb_programs > 0 && g->team_edge_offset && g->edge_program &&
+    if (range_begin >= 0) shard_only = true;
+    if (shard_only && (ctx->comm_world > 1 || range_begin >= 0) && g && g->nb_roots > 0 && g->nb_teams > 0 && g->nb_programs > 0 && g->team_edge_offset && g->edge_program &&
         g->edge_destination && g->root_team) {
         int slot, rb, re;
         shard_of(ctx, g->nb_roots, &slot, &rb, &re);
+        if (range_begin >= 0) { rb = std::min(range_begin, g->nb_roots); re = std::min(std::max(range_end, rb), g->nb_roots); }
         mask.assign((size_t)g->nb_programs, 0);
         std::vector<uint8_t> seen((size_t)g->nb_teams, 0);
         std::vector<int32_t> queue;
@@ -867,28 +890,14 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
     ctx->flat = std::move(f);
     const tpgx_flat_graph& F = ctx->flat;
     ctx->uses_trig = ctx->uses_ext = ctx->uses_int = false;
-    { /* instruction classes present among the effective lines (selects the K1 build, rejects int ops on image sources) */
-        bool present[32] = {false};
-        std::vector<uint32_t> seen(tpgx_parallel_workers(), 0u);
-        tpgx_parallel_blocks((int)F.code.size(), 1 << 15, [&](int b, int e, int w) { uint32_t m = 0; for (int i = b; i < e; i++) m |= 1u << (F.code[i] & 31u); seen[w] |= m; });
-        uint32_t mask = 0;
-        for (uint32_t m : seen) mask |= m;
-        for (int op = 0; op < 32; op++) present[op] = (mask >> op) & 1u;
-        ctx->uses_trig = present[TPGX_OP_SIN] || present[TPGX_OP_COS] || present[TPGX_OP_TAN];
-        ctx->uses_int = present[TPGX_OP_SUB_II] || present[TPGX_OP_CAST_I];
-        ctx->uses_ext = ctx->uses_trig || present[TPGX_OP_FMODG] || present[TPGX_OP_COND] || present[TPGX_OP_EQ0] || present[TPGX_OP_EQM1] ||
-                        present[TPGX_OP_EQ1] || present[TPGX_OP_GE15] || present[TPGX_OP_PI];
-    }
-    { /* K1 v2: entries and shared-memory slots of every program (count pass of the encoder; the stream itself is written on the device) */
-        ctx->v2_entries.assign((size_t)F.nb_programs, -1);
-        ctx->v2_slots.assign((size_t)F.nb_programs, 0);
-        if (!ctx->uses_ext && !ctx->uses_int)
-            tpgx_parallel_blocks(F.nb_programs, 256, [&](int b, int e, int) {
-                for (int p = b; p < e; p++) {
-                    const tpgx_k1v2_info info = tpgx_k1v2_encode(F.code.data() + F.prog_offset[p], F.prog_offset[p + 1] - F.prog_offset[p], 128u, 28u, 784u, 676u, nullptr);
-                    if (info.ok) { ctx->v2_entries[p] = info.entries; ctx->v2_slots[p] = (uint8_t)info.slots; }
-                }
-            });
+    { /* instruction classes present among the effective lines (selects the K1 build, rejects int ops on image sources); the
+         flattener also ran the count pass of the K1 v2 encoder (entries and shared-memory slots per program; the stream
+         itself is written on the device) */
+        auto present = [&](int op) { return ((F.op_mask >> op) & 1u) != 0; };
+        ctx->uses_trig = present(TPGX_OP_SIN) || present(TPGX_OP_COS) || present(TPGX_OP_TAN);
+        ctx->uses_int = present(TPGX_OP_SUB_II) || present(TPGX_OP_CAST_I);
+        ctx->uses_ext = ctx->uses_trig || present(TPGX_OP_FMODG) || present(TPGX_OP_COND) || present(TPGX_OP_EQ0) || present(TPGX_OP_EQM1) ||
+                        present(TPGX_OP_EQ1) || present(TPGX_OP_GE15) || present(TPGX_OP_PI);
     }
     std::vector<int32_t> edge_lines(F.nb_edges);
     for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }
@@ -899,11 +908,96 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
     if ((st = upload(ctx, ctx->d_edge_dst, F.edge_destination.data(), F.edge_destination.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_lines, edge_lines.data(), edge_lines.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_prog, F.edge_program.data(), F.edge_program.size() * 4)) != TPGX_OK) return st;
-    CU(cudaStreamSynchronize(ctx->stream));
-    tr.lap("uploads");
+    tr.lap("uploads enqueued"); /* no synchronisation: upload() has consumed its sources */
     ctx->graph_version++;
     ctx->has_graph = true;
     return TPGX_OK;
+}
+
+/* One generation in one call: tpgx_set_graph_sharded + tpgx_evaluate_classification_allgather, with the host side of the
+   graph (flatten, stream encoding counts, plan, uploads: ~0.1 us per line) pipelined behind the device work.  The rank's
+   root shard is cut into slices; slice k is flattened and planned on the host while the kernels of slice k - 1 run.  Every
+   slice has a context of its own ("lane": stream, graph buffers, plan) that shares the parent's observation tiles and
+   writes its records straight into the parent's gather buffer; the collective and the read-back stay on the parent. */
+tpgx_status tpgx_evaluate_graph_classification_allgather(tpgx_ctx* ctx, const tpgx_graph* g, const tpgx_classif_request* req, int32_t total_roots,
+                                                         double* records_all) {
+    if (!ctx || !g || !req) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_evaluate_graph_classification_allgather: null argument");
+    if (ctx->comm_world > 1 && !ctx->comm) return fail(ctx, TPGX_ERR_STATE, "no communicator: call tpgx_comm_init first");
+    if (total_roots < 1 || total_roots > g->nb_roots) return fail(ctx, TPGX_ERR_BAD_ARG, "total_roots exceeds the roots of the graph");
+    if (!ctx->obs_dev) return fail(ctx, TPGX_ERR_STATE, "tpgx_evaluate_graph_classification_allgather: no observations set");
+    const int C = req->nb_classes;
+    if (C < 1 || C > 16) return fail(ctx, TPGX_ERR_UNSUPPORTED, "nb_classes must be in [1,16]");
+    cudaSetDevice(ctx->cfg.device);
+    int slot, rb, re;
+    shard_of(ctx, total_roots, &slot, &rb, &re);
+    int want = 4;
+    if (const char* v = getenv("TPGX_PIPELINE")) want = std::max(1, std::min(8, atoi(v)));
+    const int K = std::max(1, std::min(want, (re - rb) / 256)); /* slices of at least 256 roots */
+    ctx->has_graph = false; /* the parent keeps no graph after this call */
+    if (K <= 1) {
+        tpgx_status st = set_graph_impl(ctx, g, true, rb, std::max(re, rb));
+        if (st != TPGX_OK) return st;
+        return tpgx_evaluate_classification_allgather(ctx, req, total_roots, records_all);
+    }
+    Trace tr("evaluate_graph");
+    /* lanes: created once, configured like the parent */
+    while ((int)ctx->lanes.size() < K) {
+        tpgx_ctx* lane = nullptr;
+        const tpgx_status st = tpgx_create(&ctx->cfg, &lane);
+        if (st != TPGX_OK) return fail(ctx, st, std::string("pipeline lane: ") + tpgx_last_error(nullptr));
+        ctx->lanes.push_back(lane);
+    }
+    const size_t count = (size_t)slot * (C + 1);
+    CU(ctx->d_gather.ensure(count * ctx->comm_world * 8));
+    double* mine = ctx->d_gather.as<double>() + (size_t)ctx->comm_rank * count;
+    CU(cudaMemsetAsync(mine, 0, count * 8, ctx->stream)); /* the padding of an uneven last shard */
+    CU(wait_for_observations(ctx));
+    /* the request's sample tiles (a sample_index re-tiles) are prepared once, on the parent */
+    const int ts = tpgx_bid_tile_samples(ctx->variant);
+    {
+        const int64_t nS = req->nb_samples;
+        if (nS <= 0) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples must be positive");
+        if (!req->sample_index && nS > ctx->nb_obs) return fail(ctx, TPGX_ERR_BAD_ARG, "nb_samples exceeds uploaded observations");
+        if (!ctx->labels_dev) return fail(ctx, TPGX_ERR_STATE, "classification needs labels");
+        tpgx_status st = prepare_tiles(ctx, req, ts);
+        if (st != TPGX_OK) return st;
+    }
+    cudaEvent_t start = ctx->event(58);
+    CU(cudaEventRecord(start, ctx->stream));
+    tr.lap("lanes + tiles");
+    for (int k = 0; k < K; k++) {
+        tpgx_ctx* lane = ctx->lanes[k];
+        /* the first slice is half as long as the others: the device starts after 1 / (2K - 1) of the host work */
+        auto cut = [&](int i) { return i <= 0 ? rb : i >= K ? re : rb + (int)((int64_t)(re - rb) * (2 * i - 1) / (2 * K - 1)); };
+        const int b = cut(k), e = cut(k + 1);
+        lane->opcode = ctx->opcode; lane->src = ctx->src; lane->variant = ctx->variant; lane->bid_budget = ctx->bid_budget;
+        lane->d_tiles.alias(ctx->d_tiles); lane->d_labels.alias(ctx->d_labels); lane->d_sobel.alias(ctx->d_sobel);
+        lane->obs_dev = ctx->obs_dev; lane->labels_dev = ctx->labels_dev; lane->nb_obs = ctx->nb_obs; lane->obs_hw = ctx->obs_hw;
+        lane->obs_width = ctx->obs_width; lane->nwin = ctx->nwin; lane->tiles_ts = ts; lane->tiles_shared = true; lane->obs_pending = false;
+        if (cudaStreamWaitEvent(lane->stream, start, 0) != cudaSuccess) return fail(ctx, TPGX_ERR_CUDA, "cudaStreamWaitEvent (lane)");
+        tpgx_status st = set_graph_impl(lane, g, true, b, e);
+        if (st == TPGX_OK) {
+            tpgx_classif_request r = *req;
+            r.root_begin = b; r.root_end = e;
+            st = enqueue_classification(lane, &r, mine + (size_t)(b - rb) * (C + 1), false, false, nullptr, false);
+        }
+        if (st != TPGX_OK) { ctx->err = lane->err; return st; }
+        cudaEvent_t done = lane->event(61);
+        if (cudaEventRecord(done, lane->stream) != cudaSuccess || cudaStreamWaitEvent(ctx->stream, done, 0) != cudaSuccess)
+            return fail(ctx, TPGX_ERR_CUDA, "cudaEventRecord (lane)");
+        tr.lap("slice enqueued");
+    }
+    if (ctx->comm_world > 1) NC(g_nccl.AllGather(mine, ctx->d_gather.as<double>(), count, ncclDouble, ctx->comm, ctx->stream));
+    if (records_all) CU(cudaMemcpyAsync(records_all, ctx->d_gather.p, (size_t)total_roots * (C + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(ctx->d_status.ensure(16));
+    CU(cudaMemsetAsync(ctx->d_status.p, 0, 16, ctx->stream));
+    tpgx_status st = finish_stream(ctx);
+    for (int k = 0; k < K && st == TPGX_OK; k++) {
+        st = finish_stream(ctx->lanes[k]);
+        if (st != TPGX_OK) ctx->err = ctx->lanes[k]->err;
+    }
+    tr.lap("device + read-back");
+    return st;
 }
 
 static tpgx_status set_obs_common(tpgx_ctx* ctx, int32_t source, int32_t store, int64_t count) {
@@ -1012,11 +1106,8 @@ tpgx_status tpgx_evaluate_classification(tpgx_ctx* ctx, const tpgx_classif_reque
     tpgx_status st = enqueue_classification(ctx, req, ctx->d_records.as<double>(), out->action != nullptr, out->bid != nullptr, &run, true);
     if (st != TPGX_OK) return st;
     tr.lap("enqueue (plan + launches)");
-    CU(cudaStreamSynchronize(ctx->stream));
+    if ((st = finish_stream(ctx)) != TPGX_OK) return st;
     tr.lap("device");
-    int status = 0;
-    CU(cudaMemcpy(&status, ctx->d_status.p, 4, cudaMemcpyDeviceToHost));
-    if ((st = check_device_status(ctx, status)) != TPGX_OK) return st;
     const int nR = run.nR, C = run.C;
     if (out->score || out->class_f1) {
         std::vector<double> rec((size_t)nR * (C + 1));

@@ -186,6 +186,9 @@ struct tpgx_flat_graph {
     std::vector<double> constants;      /* [P][nb_constants]                                    */
     std::vector<int32_t> team_edge_offset, edge_program, edge_destination, root_team;
     int64_t total_lines = 0, total_introns = 0;
+    uint32_t op_mask = 0;               /* bit o set: device opcode o occurs among the effective lines */
+    std::vector<int32_t> v2_entries;    /* [P] entries of the program's K1 v2 stream (k1v2_encode.h), -1: not encodable for v2 */
+    std::vector<uint8_t> v2_slots;      /* [P] shared-memory slots it needs there                */
 };
 
 /* Persistent host worker pool (flatten.cpp): run(nt, fn) calls fn(t) for t in [0, nt), t = 0 on the caller, the rest on

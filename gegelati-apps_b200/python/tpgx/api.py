@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get("TPGX_LIB") or os.path.normpath(os.path.join(_PKG, "..
 
 EXPORTS = [
     "tpgx_create", "tpgx_destroy", "tpgx_last_error", "tpgx_abi_version", "tpgx_set_instruction_table", "tpgx_k1v2_encode_program", "tpgx_k1v2_handler_name", "tpgx_comm_unique_id", "tpgx_comm_init", "tpgx_comm_init_all", "tpgx_comm_shard",
-    "tpgx_evaluate_classification_allgather", "tpgx_evaluate_classification_allgather_device", "tpgx_evaluate_classification_allgather_all", "tpgx_kernel_launches",
+    "tpgx_evaluate_classification_allgather", "tpgx_evaluate_graph_classification_allgather", "tpgx_evaluate_classification_allgather_device", "tpgx_evaluate_classification_allgather_all", "tpgx_kernel_launches",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_graph_sharded", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
     "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
@@ -302,6 +302,21 @@ class Evaluator:
         rec = np.zeros((int(total_roots), nb_classes + 1))
         self.lib.tpgx_evaluate_classification_allgather.argtypes = [C.c_void_p, C.POINTER(A.ClassifRequest), C.c_int32, C.c_void_p]
         self._check(self.lib.tpgx_evaluate_classification_allgather(self.h, C.byref(req), int(total_roots), rec.ctypes.data))
+        return dict(score=rec[:, 0].copy(), class_f1=rec[:, 1:].copy())
+
+    def evaluate_graph_allgather(self, graph, total_roots=None, nb_samples=None, sample_index=None, nb_classes=10):
+        """One generation in one call (tpgx_evaluate_graph_classification_allgather): the graph from host memory, this rank's
+        shard evaluated with the host side pipelined behind the device work, all ranks' records gathered.
+        Returns dict(score [total_roots], class_f1 [total_roots, C])."""
+        total_roots = graph.nb_roots if total_roots is None else int(total_roots)
+        idx = np.ascontiguousarray(sample_index, dtype=np.int32) if sample_index is not None else None
+        nS = int(nb_samples if nb_samples is not None else (len(idx) if idx is not None else self.nb_obs))
+        req = A.ClassifRequest(nb_samples=nS, sample_index=_ptr(idx), nb_classes=nb_classes, root_begin=0, root_end=0)
+        rec = np.zeros((total_roots, nb_classes + 1))
+        gs, keep = graph.c_struct()
+        self.lib.tpgx_evaluate_graph_classification_allgather.argtypes = [C.c_void_p, C.POINTER(A.Graph), C.POINTER(A.ClassifRequest), C.c_int32, C.c_void_p]
+        self._check(self.lib.tpgx_evaluate_graph_classification_allgather(self.h, C.byref(gs), C.byref(req), total_roots, rec.ctypes.data))
+        del keep
         return dict(score=rec[:, 0].copy(), class_f1=rec[:, 1:].copy())
 
     def evaluate_classification_allgather_device(self, records_all_ptr, stream_ptr, total_roots, nb_samples, nb_classes=10):

@@ -543,3 +543,28 @@ def test_k1_v2_heavy_handlers_on_wide_operand_ranges(oracle_mod):
     assert np.isinf(b).any() and (np.abs(b[np.isfinite(b)]) < 2.3e-308).any() and (np.abs(b[np.isfinite(b)]) > 1e300).any(), "the case must reach subnormal and huge bids"
     compare(dev, ref)
     compare(ev.evaluate_classification(want=("score", "confusion", "action", "counters")), ref)      # team mode
+
+
+@pytest.mark.parametrize("slices", ["1", "2", "3", "4"])
+def test_pipelined_generation_call_equals_the_two_call_form(oracle_mod, monkeypatch, slices):
+    """tpgx_evaluate_graph_classification_allgather (graph + evaluation in one call, host work of slice k behind the kernels
+    of slice k - 1, one context per slice sharing the observation tiles) gives the records of tpgx_set_graph +
+    tpgx_evaluate_classification bit for bit — full sample set and an app-style index draw — and the oracle's on a slice."""
+    monkeypatch.setenv("TPGX_PIPELINE", slices)
+    g, ev = make(roots=1100, edges=4, lines=12, depth=2, share_prob=0.1, seed=31, intron_lines=3)
+    img, lab = tpgx.synthetic_images(700, seed=9)
+    ev.set_observations(img, lab)
+    two = ev.evaluate_classification(want=("score", "class_f1"))
+    one = ev.evaluate_graph_allgather(g)
+    assert np.array_equal(bits(one["score"]), bits(two["score"])) and np.array_equal(bits(one["class_f1"]), bits(two["class_f1"]))
+    idx = tpgx.mnist_episode_indices(3000, A.MODE_TRAINING, len(img), 300)
+    ev.set_graph(g)
+    two = ev.evaluate_classification(sample_index=idx, want=("score", "class_f1"))
+    one = ev.evaluate_graph_allgather(g, sample_index=idx)
+    assert np.array_equal(bits(one["score"]), bits(two["score"])) and np.array_equal(bits(one["class_f1"]), bits(two["class_f1"]))
+    # the identity tiles are back for the next full-set call, and the context still works after the pipelined calls
+    again = ev.evaluate_graph_allgather(g)
+    ev.set_graph(g)
+    ref = oracle_for(oracle_mod, g).evaluate_classification(img, lab, root_begin=500, root_end=540, want=("score",))
+    assert np.array_equal(bits(again["score"][500:540]), bits(ref["score"]))
+    assert np.array_equal(bits(ev.evaluate_classification(want=("score",))["score"]), bits(again["score"]))
