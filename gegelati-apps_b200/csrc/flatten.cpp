@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <mutex>
 
 #include "k1v2_encode.h"
@@ -117,19 +118,18 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     f = tpgx_flat_graph();
     f.nb_programs = g->nb_programs;
     f.prog_flops.resize(g->nb_programs);
-    if (cfg.nb_constants > 0) f.constants.assign(g->constants, g->constants + (size_t)g->nb_programs * cfg.nb_constants);
+    /* constants are uploaded straight from the caller's array (tpgx_api.cu): no host copy */
 
     /* pass 1 (parallel over programs): validate, mark introns by backward liveness, count effective lines */
     const int P = g->nb_programs;
     const int64_t total_in = P > 0 ? g->program_line_offset[P] : 0;
     if (total_in < 0) return fail(TPGX_ERR_BAD_ARG, "negative line count");
-    std::vector<uint8_t> keep((size_t)total_in, 0);
+    /* 1 = effective; written for the programs that are flattened, never read for the others */
+    std::unique_ptr<uint8_t[]> keep_buf(new uint8_t[(size_t)std::max<int64_t>(total_in, 1)]);
+    uint8_t* const keep = keep_buf.get();
     std::vector<int32_t> n_eff((size_t)P, 0);
     struct Err { tpgx_status st = TPGX_OK; std::string msg; };
     std::vector<Err> errs(tpgx_parallel_workers());
-    for (int p = 0; p < P; p++)
-        if (g->program_line_offset[p + 1] < g->program_line_offset[p] || g->program_line_offset[p] < 0)
-            return fail(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p));
     /* per-instruction operand signature and per-(source, type) address space, looked up per line below */
     struct OpRow { int32_t op, nb, type[2], flops; };
     std::vector<OpRow> optab(opcode.size());
@@ -171,8 +171,9 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
         for (int q = pb; q < pe && er.st == TPGX_OK; q++) {
             const int p = prog_mask ? sel[(size_t)q] : q;
             const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
+            if (e < b || b < 0 || e > total_in) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p)); break; }
             const tpgx_line* L = g->lines + b;
-            uint8_t* kp = keep.data() + b;
+            uint8_t* kp = keep + b;
             const int n = (int)(e - b);
             /* [UP] Program::identifyIntrons: backward liveness from register 0, as a bit mask and without
                data-dependent branches (whether a line is an intron is unpredictable) */
@@ -211,7 +212,9 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
     });
     lap("pass 1 (introns)");
     for (const Err& er : errs) if (er.st != TPGX_OK) return fail(er.st, er.msg);
-    if (keep_out) *keep_out = keep;
+    if (keep_out) { /* host-only entry point (no mask): every program was marked */
+        keep_out->assign(keep, keep + total_in);
+    }
     f.prog_offset.assign((size_t)P + 1, 0);
     for (int p = 0; p < P; p++) f.prog_offset[p + 1] = f.prog_offset[p] + n_eff[p];
     f.code.assign((size_t)f.prog_offset[P], 0u);
@@ -263,7 +266,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                 seen |= 1u << (o.op & 31);
             }
             f.prog_flops[p] = flops;
-            const tpgx_k1v2_info info = tpgx_k1v2_encode(f.code.data() + f.prog_offset[p], f.prog_offset[p + 1] - f.prog_offset[p], 128u, 28u, 784u, 676u, nullptr);
+            const tpgx_k1v2_info info = tpgx_k1v2_count(f.code.data() + f.prog_offset[p], f.prog_offset[p + 1] - f.prog_offset[p]);
             if (info.ok) { f.v2_entries[p] = info.entries; f.v2_slots[p] = (uint8_t)info.slots; }
         }
         op_seen[w] |= seen;
@@ -328,6 +331,8 @@ extern "C" tpgx_status tpgx_k1v2_encode_program(const uint32_t* words, int32_t n
                                                 uint32_t* quads, int32_t quad_capacity, int32_t* nb_entries, int32_t* nb_slots) {
     if ((!words && nb_words > 0) || nb_words < 0 || width < 1 || hw < 1) return TPGX_ERR_BAD_ARG;
     const tpgx_k1v2_info count = tpgx_k1v2_encode(words, nb_words, 128u, (uint32_t)width, (uint32_t)hw, (uint32_t)nwin, nullptr);
+    const tpgx_k1v2_info lean = tpgx_k1v2_count(words, nb_words); /* the planner's count pass must agree with the encoder */
+    if (lean.ok != count.ok || (count.ok && (lean.entries != count.entries || lean.slots != count.slots))) return TPGX_ERR_STATE;
     if (nb_entries) *nb_entries = count.entries;
     if (nb_slots) *nb_slots = count.slots;
     if (!count.ok) return TPGX_ERR_UNSUPPORTED;

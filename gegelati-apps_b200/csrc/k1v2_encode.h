@@ -193,4 +193,83 @@ TPGX_HOSTDEV static inline tpgx_k1v2_info tpgx_k1v2_encode(const uint32_t* words
     return info;
 }
 
+/* Count pass on its own, for the host planner: entries and slots of tpgx_k1v2_encode(words, n, ..., nullptr) without the
+ * operand / handler work (the stream itself is written by the device, which reports any disagreement with these counts).
+ * Same liveness and slot rules, statement for statement. */
+static inline tpgx_k1v2_info tpgx_k1v2_count(const uint32_t* words, int n) {
+    tpgx_k1v2_info info = {0, 0, 1};
+    if (n > K1V2_MAX_LINES) { info.ok = 0; return info; }
+    /* per opcode: bit 0-1 number of operands, bit 2 / 3 operand 0 / 1 is a register-file (double) operand, bit 7 in the MNIST set */
+    static const uint8_t sig[32] = {
+#define K1V2_SIG(op) ((op) == TPGX_OP_ADD || (op) == TPGX_OP_MUL || (op) == TPGX_OP_SUB || (op) == TPGX_OP_MAX || (op) == TPGX_OP_DIV ? (2 | 4 | 8 | 128) \
+                      : (op) == TPGX_OP_EXP || (op) == TPGX_OP_LOG ? (1 | 4 | 128) : (op) == TPGX_OP_MULC ? (2 | 4 | 128)                                    \
+                      : (op) == TPGX_OP_SOBEL_MAGN || (op) == TPGX_OP_SOBEL_DIR ? (1 | 128) : 0)
+        K1V2_SIG(0), K1V2_SIG(1), K1V2_SIG(2), K1V2_SIG(3), K1V2_SIG(4), K1V2_SIG(5), K1V2_SIG(6), K1V2_SIG(7), K1V2_SIG(8), K1V2_SIG(9), K1V2_SIG(10),
+        K1V2_SIG(11), K1V2_SIG(12), K1V2_SIG(13), K1V2_SIG(14), K1V2_SIG(15), K1V2_SIG(16), K1V2_SIG(17), K1V2_SIG(18), K1V2_SIG(19), K1V2_SIG(20),
+        K1V2_SIG(21), K1V2_SIG(22), K1V2_SIG(23), K1V2_SIG(24), K1V2_SIG(25), K1V2_SIG(26), K1V2_SIG(27), K1V2_SIG(28), K1V2_SIG(29), K1V2_SIG(30), K1V2_SIG(31)
+#undef K1V2_SIG
+    };
+    int16_t last_read[K1V2_MAX_LINES];
+    int8_t rd[K1V2_MAX_LINES][2]; /* register read by operand k of line i, -1: none */
+    {
+        int def_line[TPGX_MAX_REGS];
+        for (int r = 0; r < TPGX_MAX_REGS; r++) def_line[r] = -1;
+        for (int i = 0; i < n; i++) {
+            const uint32_t w = words[i];
+            const uint8_t sg = sig[w & 31u];
+            if (!(sg & 128)) info.ok = 0;
+            const uint32_t f[2] = {(w >> 8) & 0xfffu, w >> 20};
+            for (int k = 0; k < 2; k++) {
+                int r = -1;
+                if (k < (sg & 3) && (sg & (4 << k))) {
+                    const uint32_t kd = f[k] >> 10, loc = f[k] & 1023u;
+                    if (kd == TPGX_KIND_REG) { if (loc < TPGX_LOC_ZERO) r = (int)loc; }
+                    else if (kd != TPGX_KIND_SRC0) info.ok = 0; /* the generic encoder: an operand kind K1 v2 has no handler for */
+                }
+                rd[i][k] = (int8_t)r;
+                if (r >= 0 && def_line[r] >= 0) last_read[def_line[r]] = (int16_t)i;
+            }
+            last_read[i] = -1;
+            def_line[(w >> 5) & 7u] = i;
+        }
+    }
+    int pos = 0;
+    auto emit = [&](bool end) {
+        if (pos == K1V2_CAP - 1 && !end) { info.entries++; pos = 0; }
+        info.entries++;
+        pos++;
+    };
+    int slot_of[TPGX_MAX_REGS], def_of[TPGX_MAX_REGS], last_use_of[TPGX_MAX_REGS];
+    for (int r = 0; r < TPGX_MAX_REGS; r++) { slot_of[r] = -1; def_of[r] = -2; last_use_of[r] = -1; }
+    uint32_t free_mask = 0xffu;
+    if (n == 0) emit(false);
+    for (int i = 0; i < n; i++) {
+        const uint32_t dst = (words[i] >> 5) & 7u;
+        for (int k = 0; k < 2; k++) {
+            const int r = rd[i][k];
+            if (r >= 0 && def_of[r] != i - 1 && slot_of[r] < 0) info.ok = 0;
+        }
+        for (int k = 0; k < 2; k++) {
+            const int r = rd[i][k];
+            if (r >= 0 && last_use_of[r] == i && slot_of[r] >= 0) { free_mask |= 1u << slot_of[r]; slot_of[r] = -1; }
+        }
+        emit(false);
+        const int last = last_read[i];
+        if (slot_of[dst] >= 0) { free_mask |= 1u << slot_of[dst]; slot_of[dst] = -1; }
+        def_of[dst] = i;
+        last_use_of[dst] = last;
+        if (last > i + 1) {
+            int s = 0;
+            while (s < 8 && !((free_mask >> s) & 1u)) s++;
+            if (s >= 8) { info.ok = 0; s = 0; }
+            free_mask &= ~(1u << s);
+            slot_of[dst] = s;
+            if (s + 1 > info.slots) info.slots = s + 1;
+            emit(false);
+        }
+    }
+    emit(true);
+    return info;
+}
+
 #endif

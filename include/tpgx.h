@@ -436,8 +436,8 @@ tpgx_status tpgx_evaluate_classification_allgather_all(tpgx_ctx* const* ctxs, in
 /* One generation in one call = tpgx_set_graph_sharded(ctx, g) + tpgx_evaluate_classification_allgather(ctx, req, ...),
  * i.e. [UP] LearningAgent::evaluateAllRoots on the graph the host has just mutated ([REF] mnist/src/main.cpp:145), with the host
  * side of the graph (introns, flattening, stream planning, uploads) pipelined behind the device: the rank's root shard is
- * cut into TPGX_PIPELINE slices (environment, default 4, of 256 roots or more on average, the first one half as long as the
- * others) and slice k is prepared while the kernels of slice k - 1 run.  Results are identical to the two-call form.  `g` is only read during the call; ctx holds no graph
+ * cut into up to 3 slices of 512 roots or more on average (TPGX_PIPELINE in the environment overrides the count), the first one
+ * half as long as the others, and slice k is prepared while the kernels of slice k - 1 run.  Results are identical to the two-call form.  `g` is only read during the call; ctx holds no graph
  * afterwards when more than one slice ran (call tpgx_set_graph before using the other entry points).  Collective.        */
 tpgx_status tpgx_evaluate_graph_classification_allgather(tpgx_ctx* ctx, const tpgx_graph* g, const tpgx_classif_request* req,
                                                          int32_t total_roots, double* records_all);
