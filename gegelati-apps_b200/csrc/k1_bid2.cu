@@ -259,16 +259,16 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
     const uint32_t mycode = wst + K2_WST_BYTES;
     const uint32_t regs_lane = wst + K2_WARP_FIXED + lane * 16;
     const uint4* __restrict__ stream = p.stream;
-    const int tile_bytes = (p.hw + 1) * K2_TS;
-    const long long plane_stride = (long long)p.nwin * K2_TS; /* doubles per plane of a tile */
+    const unsigned int tile_bytes = (unsigned int)(p.hw + 1) * K2_TS;
+    const unsigned int tile_doubles = 2u * (unsigned int)p.nwin * K2_TS; /* Sobel planes of a tile */
 
     /* cursor over the rows (programs) this warp runs.  item = (tile, group of consecutive units); the rows of consecutive
-       units are consecutive in the stream, and every row's header quad names the edge's destination, the entry count of
-       the row after it and whether it opens / closes its unit — so a warp reads global metadata once per ITEM
-       (unit_first) and nothing per row.  The cursor is warp-uniform and needed only between two rows: it lives in a
-       64-byte per-warp record in shared memory, not in registers across the interpreter block (whose heavy handlers
-       need them: the register file is 64 x 1024 threads). */
-    struct Cur { int tile, unit, unit_end, q, n; }; /* q: first quad of the row in the stream, n: its entries */
+       units are consecutive in the stream, and every row's header quad names the edge's destination, where the row after
+       it starts and whether it opens / closes its unit — so a warp reads global metadata once per ITEM (unit_first) and
+       nothing per row.  The cursor is warp-uniform and needed only between two rows: it lives in a 64-byte per-warp
+       record in shared memory, not in registers across the interpreter block (whose heavy handlers need them: the
+       register file is 64 x 1024 threads). */
+    struct Cur { int tile, unit, unit_end, q; }; /* q: first quad of the row in the stream */
     auto claim = [&]() {
         unsigned int i = 0;
         if (lane == 0) i = atomicAdd(p.work_counter, 1u);
@@ -276,27 +276,30 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
     };
     auto open_item = [&](Cur& c) {
         const int item = claim();
-        if (item >= p.nb_items) { c.tile = -1; c.unit = 0; c.unit_end = 0; c.q = 0; c.n = 0; return; }
+        if (item >= p.nb_items) { c.tile = -1; c.unit = 0; c.unit_end = 0; c.q = 0; return; }
         c.tile = item / p.items_per_tile;
         const int g = item - c.tile * p.items_per_tile;
         c.unit = g * p.units_per_item;
         c.unit_end = min(c.unit + p.units_per_item, p.nb_units);
-        const int2 f = __ldg(p.unit_first + c.unit);
-        c.q = f.x; c.n = f.y;
+        c.q = __ldg(&p.unit_first[c.unit].x);
     };
-    /* asynchronous copy of a row's head (constants + header) and first block of entries into a code buffer */
+    /* asynchronous copy of a row's head (constants + header) and first block of entries into a code buffer: always the
+       K2_BUF quads of a full buffer (past a short row that is the next row, past the last row the stream's slack) */
     auto stage = [&](uint32_t buf, const Cur& c) {
-        const int nq = c.tile >= 0 ? K1V2_CQ + min(c.n, K1V2_CAP) : 0;
-        for (int i = lane; i < nq; i += 32) k2_cp_async16(buf + i * 16, stream + c.q + i);
+        if (c.tile >= 0) {
+            const uint4* src = stream + (unsigned int)c.q + lane;
+            k2_cp_async16(buf + lane * 16, src);
+            if (lane < K2_BUF - 32) k2_cp_async16(buf + (32 + lane) * 16, src + 32);
+        }
         k2_cp_async_commit();
     };
-    /* the record: [0..4] the row to run next, [8..9] {tile, unit} of the row being run.  Every lane
+    /* the record: [0..3] the row to run next, [8..9] {tile, unit} of the row being run.  Every lane
        writes the same words and reads them back itself: no synchronisation needed */
     auto put_next = [&](const Cur& c) {
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n st.shared.u32 [%0+16], %5;" ::"r"(wst), "r"(c.tile), "r"(c.unit), "r"(c.unit_end), "r"(c.q), "r"(c.n) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(wst), "r"(c.tile), "r"(c.unit), "r"(c.unit_end), "r"(c.q) : "memory");
     };
     auto get_next = [&](Cur& c) {
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%5];\n ld.shared.u32 %4, [%5+16];" : "=r"(c.tile), "=r"(c.unit), "=r"(c.unit_end), "=r"(c.q), "=r"(c.n) : "r"(wst) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.tile), "=r"(c.unit), "=r"(c.unit_end), "=r"(c.q) : "r"(wst) : "memory");
     };
 
     {
@@ -320,20 +323,19 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
             if (c.tile < 0) break;
             k2_cp_async_wait_all();
             __syncwarp();
-            uint32_t h_dst, h_next, h_flags, h_pad;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_pad) : "r"(code + K1V2_HDR * 16));
+            uint32_t h_dst, h_next, h_flags, h_first;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_first) : "r"(code + K1V2_HDR * 16));
             /* the row after this one */
             Cur nx = c;
-            nx.q = c.q + K1V2_CQ + c.n;
-            nx.n = (int)h_next;
+            nx.q = (int)h_next;
             if (h_flags & K1V2_ROW_LAST) {
                 if (++nx.unit >= c.unit_end) open_item(nx);
             }
             stage(2 * mycode + K2_BUF * 16 - code, nx); /* next row's code: in flight while this one runs */
             put_next(nx);
             asm volatile("st.shared.v2.u32 [%0+32], {%1, %2};" ::"r"(wst), "r"(c.tile), "r"(c.unit) : "memory");
-            gtile = p.tiles + (size_t)c.tile * tile_bytes + lane * 4;
-            sobel_tile = p.sobel + (size_t)c.tile * 2 * plane_stride + lane * 4;
+            gtile = p.tiles + (size_t)((unsigned long long)(unsigned int)c.tile * tile_bytes) + lane * 4;
+            sobel_tile = p.sobel + (size_t)((unsigned long long)(unsigned int)c.tile * tile_doubles) + lane * 4;
         }
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         uint32_t lp = code + K1V2_CQ * 16;
@@ -527,9 +529,9 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
 #pragma unroll
         for (int k = 0; k < 4; k++)
             if (res[k] != res[k]) res[k] = __longlong_as_double(0xfff0000000000000LL);
-        uint32_t h_dst, h_next, h_flags, h_pad;
+        uint32_t h_dst, h_next, h_flags, h_first;
         int c_tile, c_unit;
-        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_pad) : "r"(code + K1V2_HDR * 16) : "memory");
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(h_dst), "=r"(h_next), "=r"(h_flags), "=r"(h_first) : "r"(code + K1V2_HDR * 16) : "memory");
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+32];" : "=r"(c_tile), "=r"(c_unit) : "r"(wst) : "memory");
         if (!TEAM) {
             double* out = p.bid + (size_t)c_unit * p.row_stride + (size_t)c_tile * K2_TS + lane * 4; /* bid mode: unit = row */
@@ -539,12 +541,17 @@ __global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid
             /* [UP] evaluateTeam: the first edge is the initial best; a later edge replaces it if
                bid >= best (last-max) / bid > best (first-max) */
             const int dst = (int)h_dst;
-            const bool first = (h_flags & K1V2_ROW_FIRST) != 0;
+            const unsigned int first = h_flags & K1V2_ROW_FIRST;
+            if (p.tie_break == TPGX_TIE_LAST_MAX) {
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const bool take = first | (p.tie_break == TPGX_TIE_LAST_MAX ? (res[k] >= best[k]) : (res[k] > best[k]));
-                best[k] = take ? res[k] : best[k];
-                best_dst[k] = take ? dst : best_dst[k];
+                for (int k = 0; k < 4; k++)
+                    asm("{\n .reg .pred pf, pt;\n setp.ne.u32 pf, %3, 0;\n setp.ge.or.f64 pt, %2, %0, pf;\n selp.f64 %0, %2, %0, pt;\n selp.b32 %1, %4, %1, pt;\n}"
+                        : "+d"(best[k]), "+r"(best_dst[k]) : "d"(res[k]), "r"(first), "r"(dst));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    asm("{\n .reg .pred pf, pt;\n setp.ne.u32 pf, %3, 0;\n setp.gt.or.f64 pt, %2, %0, pf;\n selp.f64 %0, %2, %0, pt;\n selp.b32 %1, %4, %1, pt;\n}"
+                        : "+d"(best[k]), "+r"(best_dst[k]) : "d"(res[k]), "r"(first), "r"(dst));
             }
             if (h_flags & K1V2_ROW_LAST) {
                 int* out = p.decision + (size_t)c_unit * p.row_stride + (size_t)c_tile * K2_TS + lane * 4;
@@ -586,7 +593,7 @@ __global__ void tpgx_k1v2_encode_kernel(const uint32_t* __restrict__ code, const
     const int2 d = desc[row];
     double* cq = reinterpret_cast<double*>(stream + d.x);
     for (int k = 0; k < 2 * K1V2_HDR; k++) cq[k] = k < nb_constants ? constants[(size_t)pidx * nb_constants + k] : 0.0;
-    stream[d.x + K1V2_HDR] = make_uint4(row_dst ? (uint32_t)row_dst[row] : 0u, row + 1 < nb_rows ? (uint32_t)desc[row + 1].y : 0u,
+    stream[d.x + K1V2_HDR] = make_uint4(row_dst ? (uint32_t)row_dst[row] : 0u, (uint32_t)(d.x + K1V2_CQ + d.y),
                                         row_flags ? (uint32_t)row_flags[row] : (K1V2_ROW_FIRST | K1V2_ROW_LAST), (uint32_t)(d.x + K1V2_CQ));
     const tpgx_k1v2_info info = tpgx_k1v2_encode(code + prog_offset[pidx], prog_offset[pidx + 1] - prog_offset[pidx], K2_TS, (uint32_t)width,
                                                  (uint32_t)hw, (uint32_t)nwin, reinterpret_cast<tpgx_k1_quad*>(stream + d.x + K1V2_CQ));

@@ -28,7 +28,7 @@
 
 #define K1V2_SLOTS 5      /* shared-memory register slots per warp */
 #define K1V2_CQ 5         /* quads at the head of a row's stream: 4 of program constants (8 doubles), then the row header */
-#define K1V2_HDR 4        /* header quad {x = destination of the edge, y = entries of the NEXT row of the stream, z = flags, w = the row's first entry in the stream} */
+#define K1V2_HDR 4        /* header quad {x = destination of the edge, y = first quad of the NEXT row of the stream, z = flags, w = the row's first entry in the stream} */
 #define K1V2_ROW_LAST 1u  /* flags: last row (edge) of its unit (team) */
 #define K1V2_ROW_FIRST 2u /* first row of its unit */
 #define K1V2_CAP 36       /* entries staged at a time */
