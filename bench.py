@@ -388,6 +388,8 @@ def main():
     pin_img = torch.from_numpy(img).pin_memory()
     pin_lab = torch.from_numpy(lab).pin_memory()
     pin_img_np, pin_lab_np = pin_img.numpy(), pin_lab.numpy()
+    pin_rec = torch.zeros(RT, C + 1, dtype=torch.float64).pin_memory()
+    pin_rec_np = pin_rec.numpy()
     ev2 = tpgx.Evaluator(tpgx.INSTRUCTION_SETS["mnist"], tpgx.APP_SOURCES["mnist"], nb_constants=5, device=local)
     if world > 1:
         uid = torch.from_numpy(tpgx.Evaluator.comm_unique_id() if rank == 0 else np.zeros(128, dtype=np.uint8)).to(dev)
@@ -402,8 +404,9 @@ def main():
         if two_calls:
             ev2.set_graph_sharded(g)   # every rank holds the whole graph; it flattens / uploads what its root shard reaches
             return ev2.evaluate_classification_allgather(RT, S, nb_classes=C)
-        # one call per generation: the host side of the graph is pipelined behind the kernels, slice by slice
-        return ev2.evaluate_graph_allgather(g, RT, S, nb_classes=C)
+        # one call per generation: the host side of the graph is pipelined behind the kernels, slice by slice; the records of
+        # all roots land in a page-locked host buffer
+        return ev2.evaluate_graph_allgather(g, RT, S, nb_classes=C, records_out=pin_rec_np)
 
     def time_e2e(upload_observations, two_calls=False):
         n = max(2, min(a.steps, 5))

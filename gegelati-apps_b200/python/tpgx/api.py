@@ -304,19 +304,26 @@ class Evaluator:
         self._check(self.lib.tpgx_evaluate_classification_allgather(self.h, C.byref(req), int(total_roots), rec.ctypes.data))
         return dict(score=rec[:, 0].copy(), class_f1=rec[:, 1:].copy())
 
-    def evaluate_graph_allgather(self, graph, total_roots=None, nb_samples=None, sample_index=None, nb_classes=10):
+    def evaluate_graph_allgather(self, graph, total_roots=None, nb_samples=None, sample_index=None, nb_classes=10, records_out=None):
         """One generation in one call (tpgx_evaluate_graph_classification_allgather): the graph from host memory, this rank's
         shard evaluated with the host side pipelined behind the device work, all ranks' records gathered.
-        Returns dict(score [total_roots], class_f1 [total_roots, C])."""
+        Returns dict(score [total_roots], class_f1 [total_roots, C]); with records_out (a C-contiguous float64 array
+        [total_roots, 1 + C], e.g. page-locked) the records land there and the result holds views of it."""
         total_roots = graph.nb_roots if total_roots is None else int(total_roots)
         idx = np.ascontiguousarray(sample_index, dtype=np.int32) if sample_index is not None else None
         nS = int(nb_samples if nb_samples is not None else (len(idx) if idx is not None else self.nb_obs))
         req = A.ClassifRequest(nb_samples=nS, sample_index=_ptr(idx), nb_classes=nb_classes, root_begin=0, root_end=0)
-        rec = np.zeros((total_roots, nb_classes + 1))
+        if records_out is None:
+            rec = np.zeros((total_roots, nb_classes + 1))
+        else:
+            rec = records_out
+            assert rec.dtype == np.float64 and rec.shape == (total_roots, nb_classes + 1) and rec.flags["C_CONTIGUOUS"]
         gs, keep = graph.c_struct()
         self.lib.tpgx_evaluate_graph_classification_allgather.argtypes = [C.c_void_p, C.POINTER(A.Graph), C.POINTER(A.ClassifRequest), C.c_int32, C.c_void_p]
         self._check(self.lib.tpgx_evaluate_graph_classification_allgather(self.h, C.byref(gs), C.byref(req), total_roots, rec.ctypes.data))
         del keep
+        if records_out is not None:
+            return dict(score=rec[:, 0], class_f1=rec[:, 1:])
         return dict(score=rec[:, 0].copy(), class_f1=rec[:, 1:].copy())
 
     def evaluate_classification_allgather_device(self, records_all_ptr, stream_ptr, total_roots, nb_samples, nb_classes=10):
