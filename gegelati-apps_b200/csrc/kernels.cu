@@ -157,52 +157,66 @@ cudaError_t tpgx_launch_traverse(const tpgx_trav_params& p0, cudaStream_t st) {
  * the destination of the winning edge.  [UP] executeFromRoot is then a pointer chase from the root's unit
  * until an action; the reference-equivalent work counters come from per-team constants (in team mode the
  * reachable graph is acyclic, so every edge of a visited team is admissible).                       */
-__global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk_params p) {
-    __shared__ unsigned int s_table[256];
+#define WALK_THREADS 256
+#define WALK_VEC 4 /* 16-byte decision vectors (4 samples) a thread has in flight */
+__global__ void __launch_bounds__(WALK_THREADS) tpgx_walk_kernel(const tpgx_walk_params p, int samples_per_cta) {
+    /* one confusion table per warp (32 lanes land on <= C*C counters: a table per CTA serialised them 8 ways) */
+    __shared__ unsigned int s_table[WALK_THREADS / 32][256];
     __shared__ unsigned long long s_cnt[4];
     const int C = p.nb_classes;
-    for (int i = threadIdx.x; i < C * C; i += TRAV_THREADS) s_table[i] = 0;
+    unsigned int* const my_table = s_table[threadIdx.x >> 5];
+    for (int i = threadIdx.x; i < (WALK_THREADS / 32) * 256; i += WALK_THREADS) (&s_table[0][0])[i] = 0;
     if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
     __syncthreads();
     const int r = blockIdx.y;
     const int root = __ldg(p.root_unit + r);
     unsigned int c_eval = 0, c_team = 0, c_prog = 0, c_line = 0;
     int err = 0;
-    const int s_begin = blockIdx.x * (TRAV_THREADS * TRAV_SPT);
-    /* the first decision (the root's) and the label of all of the thread's samples are requested up front: the walk is
-       a chain of dependent L2 round trips per sample, so the samples' chains have to overlap */
-    int first[TRAV_SPT];
-    int lab[TRAV_SPT];
+    const int s0 = blockIdx.x * samples_per_cta, s1 = min(s0 + samples_per_cta, p.nb_samples);
     const int2 root_stat = __ldg(p.team_stat + root);
+    const int32_t* const row = p.decision + (size_t)root * p.row_stride;
+    /* the root's decisions stream in as 16-byte vectors (rows are padded to whole tiles, so a vector that starts below the
+       sample count is in bounds), WALK_VEC of them per thread requested before any is used: the walk below is a chain of
+       dependent L2 round trips per sample only where a decision names another team */
+    for (int base = s0; base < s1; base += WALK_THREADS * 4 * WALK_VEC) {
+        int4 first[WALK_VEC];
+        uchar4 lab[WALK_VEC];
 #pragma unroll
-    for (int it = 0; it < TRAV_SPT; it++) {
-        const int s = s_begin + it * TRAV_THREADS + threadIdx.x;
-        const bool in = s < p.nb_samples;
-        first[it] = in ? __ldg(p.decision + (size_t)root * p.row_stride + s) : 0;
-        lab[it] = (in && p.labels) ? (int)__ldg(p.labels + s) : 0;
-    }
-#pragma unroll
-    for (int it = 0; it < TRAV_SPT; it++) {
-        const int s = s_begin + it * TRAV_THREADS + threadIdx.x;
-        if (s >= p.nb_samples) break;
-        int cur = root, action = -1;
-        for (int depth = 0;; depth++) {
-            if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; break; }
-            const int2 st = depth == 0 ? root_stat : __ldg(p.team_stat + cur);
-            c_team++;
-            c_prog += (unsigned int)st.x;
-            c_line += (unsigned int)st.y;
-            const int d = depth == 0 ? first[it] : __ldg(p.decision + (size_t)cur * p.row_stride + s);
-            if (d < 0) { action = -1 - d; break; }
-            cur = d;
+        for (int k = 0; k < WALK_VEC; k++) {
+            const int s = base + (k * WALK_THREADS + threadIdx.x) * 4;
+            const bool in = s < s1;
+            first[k] = in ? __ldg(reinterpret_cast<const int4*>(row + s)) : make_int4(0, 0, 0, 0);
+            lab[k] = (in && p.labels) ? __ldg(reinterpret_cast<const uchar4*>(p.labels + s)) : make_uchar4(0, 0, 0, 0);
         }
-        c_eval++;
-        if (action >= 0) {
-            if (p.action) p.action[(size_t)r * p.action_stride + s] = (uint8_t)action;
-            if (p.labels) {
-                if (action >= C) err |= TPGX_DEV_BAD_ACTION;
-                else if (lab[it] >= C) err |= TPGX_DEV_BAD_LABEL;
-                else atomicAdd(&s_table[lab[it] * C + action], 1u);
+#pragma unroll
+        for (int k = 0; k < WALK_VEC; k++) {
+            const int sv = base + (k * WALK_THREADS + threadIdx.x) * 4;
+            const int fd[4] = {first[k].x, first[k].y, first[k].z, first[k].w};
+            const int fl[4] = {lab[k].x, lab[k].y, lab[k].z, lab[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int s = sv + j;
+                if (s >= s1) break;
+                int cur = root, action = -1;
+                for (int depth = 0;; depth++) {
+                    if (depth >= TPGX_MAX_PATH) { err |= TPGX_DEV_PATH_TOO_LONG; break; }
+                    const int2 st = depth == 0 ? root_stat : __ldg(p.team_stat + cur);
+                    c_team++;
+                    c_prog += (unsigned int)st.x;
+                    c_line += (unsigned int)st.y;
+                    const int d = depth == 0 ? fd[j] : __ldg(p.decision + (size_t)cur * p.row_stride + s);
+                    if (d < 0) { action = -1 - d; break; }
+                    cur = d;
+                }
+                c_eval++;
+                if (action >= 0) {
+                    if (p.action) p.action[(size_t)r * p.action_stride + s] = (uint8_t)action;
+                    if (p.labels) {
+                        if (action >= C) err |= TPGX_DEV_BAD_ACTION;
+                        else if (fl[j] >= C) err |= TPGX_DEV_BAD_LABEL;
+                        else atomicAdd(&my_table[fl[j] * C + action], 1u);
+                    }
+                }
             }
         }
     }
@@ -221,20 +235,28 @@ __global__ void __launch_bounds__(TRAV_THREADS) tpgx_walk_kernel(const tpgx_walk
     if (err) atomicOr(p.status, err);
     __syncthreads();
     if (p.labels)
-        for (int i = threadIdx.x; i < C * C; i += TRAV_THREADS)
-            if (s_table[i]) atomicAdd(p.confusion + (size_t)r * C * C + i, (unsigned long long)s_table[i]);
+        for (int i = threadIdx.x; i < C * C; i += WALK_THREADS) {
+            unsigned int n = 0;
+#pragma unroll
+            for (int w = 0; w < WALK_THREADS / 32; w++) n += s_table[w][i];
+            if (n) atomicAdd(p.confusion + (size_t)r * C * C + i, (unsigned long long)n);
+        }
     if (threadIdx.x < 4 && p.counters) atomicAdd(p.counters + threadIdx.x, s_cnt[threadIdx.x]);
 }
 
 cudaError_t tpgx_launch_walk(const tpgx_walk_params& p0, cudaStream_t st) {
+    /* samples per CTA: whole kilo-samples, enough CTAs for ~4 waves of 8 per SM when the problem has them, at most 16 Ki */
+    const long long work = (long long)p0.nb_samples * std::max(1, p0.nb_roots);
+    long long spc = (work / (148LL * 8 * 4) + 1023) / 1024 * 1024;
+    spc = std::max<long long>(1024, std::min<long long>(16384, spc));
     for (int r0 = 0; r0 < p0.nb_roots; r0 += TPGX_MAX_GRID_Y) {
         tpgx_walk_params p = p0;
         p.nb_roots = std::min(TPGX_MAX_GRID_Y, p0.nb_roots - r0);
         p.root_unit = p0.root_unit + r0;
         if (p.action) p.action = p0.action + (size_t)r0 * p0.action_stride;
         if (p.confusion) p.confusion = p0.confusion + (size_t)r0 * p0.nb_classes * p0.nb_classes;
-        dim3 grid((p.nb_samples + TRAV_THREADS * TRAV_SPT - 1) / (TRAV_THREADS * TRAV_SPT), p.nb_roots);
-        tpgx_walk_kernel<<<grid, TRAV_THREADS, 0, st>>>(p); TPGX_COUNT_LAUNCH();
+        dim3 grid((unsigned)((p.nb_samples + spc - 1) / spc), p.nb_roots);
+        tpgx_walk_kernel<<<grid, WALK_THREADS, 0, st>>>(p, (int)spc); TPGX_COUNT_LAUNCH();
         const cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
