@@ -29,7 +29,12 @@
 #include "k1v2_encode.h"
 #include "kernels.cuh"
 
+#ifndef K2_MINB
+#define K2_MINB 1 /* CTAs per SM */
+#endif
+#ifndef K2_NW
 #define K2_NW 32
+#endif
 #define K2_TS 128
 #define K2_BUF (K1V2_CQ + K1V2_CAP) /* quads per code buffer */
 #define K2_TAB_BYTES (256 * 8 + 512 * 8 + 512 * 8) /* exp table, ln table, exp / ln of the 256 pixel values */
@@ -244,7 +249,7 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
 #define K2_TARGET(n) "H_" #n ", "
 
 template <bool TEAM>
-__global__ void __launch_bounds__(K2_NW * 32, 1) tpgx_bid2_kernel(const tpgx_bid2_params p) {
+__global__ void __launch_bounds__(K2_NW * 32, K2_MINB) tpgx_bid2_kernel(const tpgx_bid2_params p) {
     /* shared memory: [exp, ln, pixel exp / ln tables] then per warp [row cursor record | 2 code buffers | p.slots register slots] */
     extern __shared__ __align__(128) uint8_t smem[];
     double* s_tab = reinterpret_cast<double*>(smem);

@@ -150,6 +150,7 @@ tpgx_status upload(tpgx_ctx* ctx, DevBuf& b, const void* src, size_t bytes, bool
 /* ... into a buffer that is already large enough, at a byte offset */
 tpgx_status upload_at(tpgx_ctx* ctx, DevBuf& b, size_t offset, const void* src, size_t bytes, bool through_ring) {
     if (!bytes) return TPGX_OK;
+    if (!b.p || offset + bytes > b.cap) return fail(ctx, TPGX_ERR_STATE, "upload_at: destination buffer too small");
     uint8_t* const dst = static_cast<uint8_t*>(b.p) + offset;
     const size_t ring = (size_t)48 << 20, limit = (size_t)8 << 20;
     if (through_ring && bytes <= limit) {
