@@ -129,12 +129,14 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
 /* every sample of the warp has a special operand: the quotient is a * seed */
 #define DIV_SP(a, b) "rcp.approx.ftz.f64 sd, " b ";\n mul.rn.f64 " a ", " a ", sd;\n"
 
-/* tpgx_math::exp_k, one sample (x in place).  EXP_RARE accumulates the sliver test, EXP_MAIN computes. */
-#define EXP_RARE(x, k)                                                                            \
-    "mov.b64 {xlo, xhi}, " x ";\n and.b32 ax, xhi, 0x7fffffff;\n setp.lt.u32 pm" k ", ax, 0x4085e000;\n" \
-    "setp.lt.f64 p1, " x ", " KD_X710 ";\n setp.le.f64 pt" k ", " x ", " KD_XM746 ";\n"            \
-    "not.pred p2, pm" k ";\n and.pred p1, p1, p2;\n not.pred p2, pt" k ";\n and.pred p1, p1, p2;\n or.pred prare, prare, p1;\n"
-#define EXP_MAIN(x, k)                                                                            \
+/* tpgx_math::exp_k, one sample (x in place).  EXP_RARE accumulates the sliver test (prare |= exp_is_rare(x), on the high word:
+   |x| in [700, 710) for x > 0, [700, 746) for x < 0), EXP_MAIN computes.  The range predicates of a sample are made where they
+   are used, after its polynomial: 8 predicates kept across the four samples' arithmetic do not fit the 7 predicate registers and
+   ptxas spilled them into a GPR bit field (~20 extra instructions per line). */
+#define EXP_RARE(x)                                                                               \
+    "mov.b64 {xlo, xhi}, " x ";\n and.b32 ax, xhi, 0x7fffffff;\n sub.u32 t0, ax, 0x4085e000;\n"    \
+    "shr.u32 ee, xhi, 31;\n mad.lo.u32 ee, ee, 0x12000, 0x5000;\n setp.lt.or.u32 prare, t0, ee, prare;\n"
+#define EXP_MAIN(x)                                                                               \
     "mul.rn.f64 z, " x ", " KD_INV_LN2N ";\n add.rn.f64 tm, z, " KD_MAGIC ";\n sub.rn.f64 kd, tm, " KD_MAGIC ";\n" \
     "mov.b64 {ki, t0}, tm;\n"                                                                    \
     "fma.rn.f64 r, kd, " KD_NEG_LN2N_HI ", " x ";\n fma.rn.f64 r, kd, " KD_NEG_LN2N_LO ", r;\n"   \
@@ -144,19 +146,20 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
     "add.rn.f64 tmp, tail, r;\n fma.rn.f64 tmp, r2, pa, tmp;\n mul.rn.f64 r4, r2, r2;\n fma.rn.f64 tmp, r4, pb, tmp;\n" \
     "fma.rn.f64 y, TT, tmp, TT;\n"                                                               \
     "mov.b64 {ylo, yhi}, y;\n shl.b32 ee, ee, 20;\n add.u32 yhi, yhi, ee;\n mov.b64 y, {ylo, yhi};\n" \
-    "add.rn.f64 ev, " x ", " KD_INF ";\n selp.f64 ev, " KD_ZERO ", ev, pt" k ";\n selp.f64 " x ", y, ev, pm" k ";\n"
+    "mov.b64 {xlo, xhi}, " x ";\n and.b32 ax, xhi, 0x7fffffff;\n setp.lt.u32 p1, ax, 0x4085e000;\n setp.le.f64 p2, " x ", " KD_XM746 ";\n" \
+    "add.rn.f64 ev, " x ", " KD_INF ";\n selp.f64 ev, " KD_ZERO ", ev, p2;\n selp.f64 " x ", y, ev, p1;\n"
 
-/* tpgx_math::log_k, one sample k (x in place).  LN_RARE: zero predicate pz<k>, main-range predicate pm<k> (positive, normal,
-   finite), prare |= positive subnormal, pany |= main.  LN_MAIN: the table-driven path + edge selects.  LN_EDGE: the edge
-   answers alone (no sample of the warp is in the main range). */
-#define LN_RARE(x, k)                                                                             \
-    "mov.b64 {xlo, xhi}, " x ";\n setp.eq.f64 pz" k ", " x ", " KD_ZERO ";\n setp.lt.u32 p1, xhi, 0x00100000;\n" \
-    "not.pred p2, pz" k ";\n and.pred p1, p1, p2;\n or.pred prare, prare, p1;\n"                    \
-    "sub.u32 t0, xhi, 0x00100000;\n setp.lt.u32 pm" k ", t0, 0x7fe00000;\n or.pred pany, pany, pm" k ";\n"
-#define LN_EDGE(x, k)                                                                             \
+/* tpgx_math::log_k, one sample (x in place).  LN_RARE: prare |= positive subnormal, pany |= main range (positive, normal,
+   finite).  LN_MAIN: the table-driven path + edge selects (zero, negative, NaN / inf), their predicates made at the end.
+   LN_EDGE: the edge answers alone (no sample of the warp is in the main range). */
+#define LN_RARE(x)                                                                                \
+    "mov.b64 {xlo, xhi}, " x ";\n or.b32 t0, xhi, xlo;\n setp.ne.u32 p1, t0, 0;\n setp.lt.and.u32 p1, xhi, 0x00100000, p1;\n" \
+    "or.pred prare, prare, p1;\n"                                                                \
+    "sub.u32 t0, xhi, 0x00100000;\n setp.lt.or.u32 pany, t0, 0x7fe00000, pany;\n"
+#define LN_EDGE(x)                                                                                \
     "add.rn.f64 ev, " x ", " x ";\n setp.lt.f64 p2, " x ", " KD_ZERO ";\n selp.f64 ev, " KD_NAN ", ev, p2;\n" \
-    "selp.f64 " x ", " KD_NINF ", ev, pz" k ";\n"
-#define LN_MAIN(x, k)                                                                             \
+    "setp.eq.f64 p1, " x ", " KD_ZERO ";\n selp.f64 " x ", " KD_NINF ", ev, p1;\n"
+#define LN_MAIN(x)                                                                                \
     "mov.b64 {xlo, xhi}, " x ";\n"                                                               \
     "sub.u32 t0, xhi, 0x3FE6B000;\n shr.u32 ii, t0, 13;\n and.b32 ii, ii, 127;\n shr.s32 kk, t0, 20;\n" \
     "and.b32 t0, t0, 0xfff00000;\n sub.u32 t0, xhi, t0;\n mov.b64 z, {xlo, t0};\n"               \
@@ -167,7 +170,8 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
     "fma.rn.f64 pa, r, pa, " KD_CM0_25 ";\n fma.rn.f64 pa, r, pa, " KD_C1_3 ";\n fma.rn.f64 pa, r, pa, " KD_CM0_5 ";\n" \
     "fma.rn.f64 tmp, r2, pa, lo;\n add.rn.f64 y, hi, tmp;\n"                                     \
     "add.rn.f64 ev, " x ", " x ";\n setp.lt.f64 p2, " x ", " KD_ZERO ";\n selp.f64 ev, " KD_NAN ", ev, p2;\n" \
-    "selp.f64 ev, " KD_NINF ", ev, pz" k ";\n selp.f64 " x ", y, ev, pm" k ";\n"
+    "setp.eq.f64 p1, " x ", " KD_ZERO ";\n selp.f64 ev, " KD_NINF ", ev, p1;\n"                  \
+    "sub.u32 t0, xhi, 0x00100000;\n setp.lt.u32 p1, t0, 0x7fe00000;\n selp.f64 " x ", y, ev, p1;\n"
 
 /* tpgx_math::xdiv10_k, one sample: x / 10 into q; pall &= accepted */
 #define DIV10_1(x, q)                                                                             \
@@ -351,7 +355,7 @@ __global__ void __launch_bounds__(K2_NW * 32, K2_MINB) tpgx_bid2_kernel(const tp
                 "{\n"
                 ".reg .b32 hx, ya, zb, wd, ra, pw, t0;\n"
                 ".reg .b64 ga;\n"
-                ".reg .pred pq, p1, p2, pas, pbs, psp, psp0, psp1, psp2, psp3, pall, pany, prare, pslow, pm0, pm1, pm2, pm3, pt0, pt1, pt2, pt3, pz0, pz1, pz2, pz3;\n"
+                ".reg .pred pq, p1, p2, pas, pbs, psp, psp0, psp1, psp2, psp3, pall, pany, prare, pslow;\n"
                 ".reg .b32 alo, ahi, blo, bhi, ha, hb, slo, shi, qlo, qhi, xlo, xhi, ax, ki, ii, ee, kk, ylo, yhi;\n"
                 ".reg .f32 fq, fb, fa, ft;\n"
                 ".reg .f64 sd, rr, nb, t1, t2, r1, r2, q0, rem, sp, qr0, qr1, qr2, qr3, cst;\n"
@@ -428,11 +432,11 @@ __global__ void __launch_bounds__(K2_NW * 32, K2_MINB) tpgx_bid2_kernel(const tp
                 "H_EXP_A:\n"
                 PF
                 "setp.ne.u32 prare, 0, 0;\n"
-                EXP_RARE(A0, "0") EXP_RARE(A1, "1") EXP_RARE(A2, "2") EXP_RARE(A3, "3")
+                EXP_RARE(A0) EXP_RARE(A1) EXP_RARE(A2) EXP_RARE(A3)
                 "vote.sync.any.pred pslow, prare, 0xffffffff;\n"
                 "@pslow bra.uni EXP_KEEP;\n"
                 "EXP_GO:\n"
-                EXP_MAIN(A0, "0") EXP_MAIN(A1, "1") EXP_MAIN(A2, "2") EXP_MAIN(A3, "3")
+                EXP_MAIN(A0) EXP_MAIN(A1) EXP_MAIN(A2) EXP_MAIN(A3)
                 "@pslow bra.uni X_SLOW_EXP;\n"
                 GO
                 "EXP_KEEP:\n" MOV_B_A "bra.uni EXP_GO;\n"
@@ -440,18 +444,18 @@ __global__ void __launch_bounds__(K2_NW * 32, K2_MINB) tpgx_bid2_kernel(const tp
                 "H_LN_A:\n"
                 PF
                 "setp.ne.u32 prare, 0, 0;\n setp.ne.u32 pany, 0, 0;\n"
-                LN_RARE(A0, "0") LN_RARE(A1, "1") LN_RARE(A2, "2") LN_RARE(A3, "3")
+                LN_RARE(A0) LN_RARE(A1) LN_RARE(A2) LN_RARE(A3)
                 "vote.sync.any.pred pslow, prare, 0xffffffff;\n"
                 "@pslow bra.uni LN_KEEP;\n"
                 "LN_GO:\n"
                 /* no sample of the warp is positive, normal and finite (a fifth of the ln lines): edge answers only */
                 "vote.sync.any.pred p1, pany, 0xffffffff;\n"
                 "@!p1 bra.uni LN_EDGES;\n"
-                LN_MAIN(A0, "0") LN_MAIN(A1, "1") LN_MAIN(A2, "2") LN_MAIN(A3, "3")
+                LN_MAIN(A0) LN_MAIN(A1) LN_MAIN(A2) LN_MAIN(A3)
                 "@pslow bra.uni X_SLOW_LN;\n"
                 GO
                 "LN_EDGES:\n"
-                LN_EDGE(A0, "0") LN_EDGE(A1, "1") LN_EDGE(A2, "2") LN_EDGE(A3, "3")
+                LN_EDGE(A0) LN_EDGE(A1) LN_EDGE(A2) LN_EDGE(A3)
                 "@pslow bra.uni X_SLOW_LN;\n"
                 GO
                 "LN_KEEP:\n" MOV_B_A "bra.uni LN_GO;\n"
