@@ -209,66 +209,57 @@ static inline tpgx_k1v2_info tpgx_k1v2_count(const uint32_t* words, int n) {
         K1V2_SIG(21), K1V2_SIG(22), K1V2_SIG(23), K1V2_SIG(24), K1V2_SIG(25), K1V2_SIG(26), K1V2_SIG(27), K1V2_SIG(28), K1V2_SIG(29), K1V2_SIG(30), K1V2_SIG(31)
 #undef K1V2_SIG
     };
-    int16_t last_read[K1V2_MAX_LINES];
-    int8_t rd[K1V2_MAX_LINES][2]; /* register read by operand k of line i, -1: none */
+    /* What the encoder's slot allocator and entry emitter amount to, without replaying them (the replay is a chain of dependent
+       loads and stores through the per-register tables, 30 ns per line: it was 60 % of the host time of a generation's flatten):
+         - the value line i defines needs a slot and an ST entry iff its last reader is a line after the next one;
+         - such a value holds its slot from line i's allocation until line `last` frees it BEFORE allocating its own, i.e. over
+           the allocation steps [i, last); lowest-free-slot allocation in order of definition is greedy colouring of an interval
+           graph by left end point, which uses exactly as many slots as the largest number of values live at once;
+         - a NEXT entry precedes every (K1V2_CAP - 1)-th entry that is not the first; END closes the row.
+       The encoder's own consistency checks (a register operand is the accumulator or holds a slot) cannot fail on flattener
+       output and stay with the encoder, which runs on the device and reports any disagreement with these counts (flag 4).
+       Index TPGX_MAX_REGS of def_line and index -1 of last_read are dummies that absorb "not a register operand". */
+    int16_t last_read_store[K1V2_MAX_LINES + 1];
+    int16_t* const last_read = last_read_store + 1;
+    uint32_t ok = 1u;
     {
-        int def_line[TPGX_MAX_REGS];
-        for (int r = 0; r < TPGX_MAX_REGS; r++) def_line[r] = -1;
+        int def_line[TPGX_MAX_REGS + 1];
+        for (int r = 0; r <= TPGX_MAX_REGS; r++) def_line[r] = -1;
         for (int i = 0; i < n; i++) {
             const uint32_t w = words[i];
-            const uint8_t sg = sig[w & 31u];
-            if (!(sg & 128)) info.ok = 0;
+            const uint32_t sg = sig[w & 31u];
+            ok &= sg >> 7;
             const uint32_t f[2] = {(w >> 8) & 0xfffu, w >> 20};
-            for (int k = 0; k < 2; k++) {
-                int r = -1;
-                if (k < (sg & 3) && (sg & (4 << k))) {
-                    const uint32_t kd = f[k] >> 10, loc = f[k] & 1023u;
-                    if (kd == TPGX_KIND_REG) { if (loc < TPGX_LOC_ZERO) r = (int)loc; }
-                    else if (kd != TPGX_KIND_SRC0) info.ok = 0; /* the generic encoder: an operand kind K1 v2 has no handler for */
-                }
-                rd[i][k] = (int8_t)r;
-                if (r >= 0 && def_line[r] >= 0) last_read[def_line[r]] = (int16_t)i;
+            for (uint32_t k = 0; k < 2; k++) {
+                const uint32_t kd = f[k] >> 10, loc = f[k] & 1023u;
+                const uint32_t active = (uint32_t)(k < (sg & 3u)) & ((sg >> (2u + k)) & 1u);
+                const uint32_t isreg = active & (uint32_t)(kd == TPGX_KIND_REG) & (uint32_t)(loc < TPGX_LOC_ZERO);
+                ok &= 1u ^ (active & (uint32_t)(kd != TPGX_KIND_REG) & (uint32_t)(kd != TPGX_KIND_SRC0)); /* an operand kind K1 v2 has no handler for */
+                last_read[def_line[TPGX_MAX_REGS ^ ((TPGX_MAX_REGS ^ loc) & (0u - isreg))]] = (int16_t)i; /* isreg ? loc : the dummy, without a branch */
             }
             last_read[i] = -1;
             def_line[(w >> 5) & 7u] = i;
         }
     }
-    int pos = 0;
-    auto emit = [&](bool end) {
-        if (pos == K1V2_CAP - 1 && !end) { info.entries++; pos = 0; }
-        info.entries++;
-        pos++;
-    };
-    int slot_of[TPGX_MAX_REGS], def_of[TPGX_MAX_REGS], last_use_of[TPGX_MAX_REGS];
-    for (int r = 0; r < TPGX_MAX_REGS; r++) { slot_of[r] = -1; def_of[r] = -2; last_use_of[r] = -1; }
-    uint32_t free_mask = 0xffu;
-    if (n == 0) emit(false);
+    int8_t delta[K1V2_MAX_LINES + 1]; /* slots taken (+1 at the defining line) and given back (-1 at the last reader) */
+    for (int i = 0; i <= n; i++) delta[i] = 0;
+    int stores = 0;
     for (int i = 0; i < n; i++) {
-        const uint32_t dst = (words[i] >> 5) & 7u;
-        for (int k = 0; k < 2; k++) {
-            const int r = rd[i][k];
-            if (r >= 0 && def_of[r] != i - 1 && slot_of[r] < 0) info.ok = 0;
-        }
-        for (int k = 0; k < 2; k++) {
-            const int r = rd[i][k];
-            if (r >= 0 && last_use_of[r] == i && slot_of[r] >= 0) { free_mask |= 1u << slot_of[r]; slot_of[r] = -1; }
-        }
-        emit(false);
         const int last = last_read[i];
-        if (slot_of[dst] >= 0) { free_mask |= 1u << slot_of[dst]; slot_of[dst] = -1; }
-        def_of[dst] = i;
-        last_use_of[dst] = last;
-        if (last > i + 1) {
-            int s = 0;
-            while (s < 8 && !((free_mask >> s) & 1u)) s++;
-            if (s >= 8) { info.ok = 0; s = 0; }
-            free_mask &= ~(1u << s);
-            slot_of[dst] = s;
-            if (s + 1 > info.slots) info.slots = s + 1;
-            emit(false);
-        }
+        const int need = last > i + 1;
+        stores += need;
+        delta[i] += (int8_t)need;
+        delta[n ^ ((n ^ last) & -need)] -= (int8_t)need; /* need ? last : n */
     }
-    emit(true);
+    int live = 0, slots = 0;
+    for (int i = 0; i < n; i++) {
+        live += delta[i];
+        slots = std::max(slots, live);
+    }
+    const int real = n == 0 ? 1 : n + stores; /* an empty program is one ADD of two zero rows */
+    info.entries = real + (real - 1) / (K1V2_CAP - 1) + 1;
+    info.slots = slots;
+    info.ok = (int)(ok & (uint32_t)(slots <= 8));
     return info;
 }
 
