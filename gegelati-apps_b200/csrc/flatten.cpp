@@ -96,7 +96,8 @@ void tpgx_pool_run(int nt, void (*fn)(int, void*), void* arg) {
 
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
                                const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
-                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out, const std::vector<uint8_t>* prog_mask) {
+                               tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out, const std::vector<uint8_t>* prog_mask,
+                               const int32_t* prog_ids) {
     auto fail = [&](tpgx_status st, const std::string& m) { if (err) *err = m; return st; };
     if (!g || !g->program_line_offset || !g->team_edge_offset || !g->edge_program || !g->edge_destination || !g->root_team)
         return fail(TPGX_ERR_BAD_ARG, "tpgx_set_graph: null array in graph");
@@ -122,7 +123,20 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
 
     /* pass 1 (parallel over programs): validate, mark introns by backward liveness, count effective lines */
     const int P = g->nb_programs;
-    const int64_t total_in = P > 0 ? g->program_line_offset[P] : 0;
+    /* prog_ids (a slice of a larger graph): program p of g has its lines and constants at program prog_ids[p] of the caller's
+       arrays; the intron marks then live at offsets of their own (line_base), and nothing below is sized by the caller's graph */
+    if (prog_ids && (keep_out || prog_mask)) return fail(TPGX_ERR_BAD_ARG, "tpgx_flatten_graph: prog_ids excludes keep_out / prog_mask");
+    std::vector<int64_t> line_base;
+    if (prog_ids) {
+        line_base.resize((size_t)P + 1);
+        line_base[0] = 0;
+        for (int p = 0; p < P; p++) {
+            const int64_t n = g->program_line_offset[prog_ids[p] + 1] - g->program_line_offset[prog_ids[p]];
+            if (n < 0) return fail(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", prog_ids[p]));
+            line_base[(size_t)p + 1] = line_base[(size_t)p] + n;
+        }
+    }
+    const int64_t total_in = prog_ids ? line_base[(size_t)P] : P > 0 ? g->program_line_offset[P] : 0;
     if (total_in < 0) return fail(TPGX_ERR_BAD_ARG, "negative line count");
     /* 1 = effective; written for the programs that are flattened, never read for the others */
     std::unique_ptr<uint8_t[]> keep_buf(new uint8_t[(size_t)std::max<int64_t>(total_in, 1)]);
@@ -170,10 +184,11 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
         auto bad = [&](tpgx_status st, const std::string& m) { if (er.st == TPGX_OK) { er.st = st; er.msg = m; } };
         for (int q = pb; q < pe && er.st == TPGX_OK; q++) {
             const int p = prog_mask ? sel[(size_t)q] : q;
-            const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
-            if (e < b || b < 0 || e > total_in) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", p)); break; }
+            const int gp = prog_ids ? prog_ids[p] : p; /* the caller's program id: addresses its arrays, named in messages */
+            const int64_t b = g->program_line_offset[gp], e = g->program_line_offset[gp + 1];
+            if (e < b || b < 0 || (!prog_ids && e > total_in)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld: negative length", gp)); break; }
             const tpgx_line* L = g->lines + b;
-            uint8_t* kp = keep + b;
+            uint8_t* kp = keep + (prog_ids ? line_base[(size_t)p] : b);
             const int n = (int)(e - b);
             /* [UP] Program::identifyIntrons: backward liveness from register 0, as a bit mask and without
                data-dependent branches (whether a line is an intron is unpredictable) */
@@ -181,17 +196,17 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
             int cnt = 0;
             for (int i = n - 1; i >= 0; i--) {
                 const tpgx_line& l = L[i];
-                if (l.instruction >= nI) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", p, i, l.instruction)); break; }
-                if (l.destination >= (uint32_t)R) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: destination register out of range", p, i)); break; }
+                if (l.instruction >= nI) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: instruction index %ld out of range", gp, i, l.instruction)); break; }
+                if (l.destination >= (uint32_t)R) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: destination register out of range", gp, i)); break; }
                 const OpRow& o = optab[l.instruction];
                 uint32_t reads = 0;
                 bool ok = true;
                 for (int k = 0; k < o.nb; k++) {
                     const uint32_t sidx = l.src[k];
-                    if (sidx >= (uint32_t)nsrc) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", p, i, sidx)); ok = false; break; }
+                    if (sidx >= (uint32_t)nsrc) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: operand source %ld out of range", gp, i, sidx)); ok = false; break; }
                     const uint32_t sp = space_tab[(size_t)sidx * 8 + o.type[k]];
                     if (sp == 0) {
-                        bad(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", p, i, sidx));
+                        bad(TPGX_ERR_GRAPH_INVALID, fmt("program %ld line %ld: source %ld cannot provide the operand type (the reference engine throws here)", gp, i, sidx));
                         ok = false;
                         break;
                     }
@@ -206,7 +221,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
             n_eff[p] = cnt;
             if (g->intron && er.st == TPGX_OK && !prog_mask) {
                 for (int i = 0; i < n; i++)
-                    if ((g->intron[b + i] != 0) == (kp[i] != 0)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", p, i)); break; }
+                    if ((g->intron[b + i] != 0) == (kp[i] != 0)) { bad(TPGX_ERR_BAD_ARG, fmt("program %ld line %ld: caller's intron flag disagrees with identifyIntrons", gp, i)); break; }
             }
         }
     });
@@ -232,14 +247,16 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
         uint32_t seen = 0;
         for (int q = pb; q < pe && er.st == TPGX_OK; q++) {
             const int p = prog_mask ? sel[(size_t)q] : q;
-            const int64_t b = g->program_line_offset[p], e = g->program_line_offset[p + 1];
+            const int gp = prog_ids ? prog_ids[p] : p;
+            const int64_t b = g->program_line_offset[gp], e = g->program_line_offset[gp + 1];
             const tpgx_line* L = g->lines + b;
+            const uint8_t* const kp = keep + (prog_ids ? line_base[(size_t)p] : b);
             const int n = (int)(e - b);
             uint32_t written = 0;
             int flops = 0;
             uint32_t* out_code = f.code.data() + f.prog_offset[p];
             for (int i = 0; i < n; i++) {
-                if (!keep[b + i]) continue;
+                if (!kp[i]) continue;
                 const tpgx_line& l = L[i];
                 const OpRow& o = optab[l.instruction];
                 uint32_t kind[2] = {TPGX_KIND_REG, TPGX_KIND_REG}, loc[2] = {TPGX_LOC_ZERO, TPGX_LOC_ZERO};
@@ -254,7 +271,7 @@ tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t
                         kind[k] = ks == 0 ? TPGX_KIND_SRC0 : TPGX_KIND_SRC1;
                         if (o.type[k] == TPGX_T_W) a = a < TPGX_MAX_LOC ? win_tab[(size_t)ks * TPGX_MAX_LOC + a] : TPGX_MAX_LOC;
                         if (a >= TPGX_MAX_LOC) {
-                            if (er.st == TPGX_OK) { er.st = TPGX_ERR_UNSUPPORTED; er.msg = fmt("program %ld line %ld: location %ld exceeds the 10-bit device field", p, i, a); }
+                            if (er.st == TPGX_OK) { er.st = TPGX_ERR_UNSUPPORTED; er.msg = fmt("program %ld line %ld: location %ld exceeds the 10-bit device field", gp, i, a); }
                             a = 0;
                         }
                         loc[k] = a;

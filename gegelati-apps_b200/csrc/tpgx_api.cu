@@ -67,6 +67,15 @@ struct ShardPlan { /* programs reachable from a root range, cached between evalu
 
 } // namespace
 
+/* set_graph_slice: stamped renumbering tables (a table entry is valid when its stamp is the current one: no clearing
+   between slices) and the slice's sub-graph arrays, reused from call to call */
+struct SliceMaps {
+    uint32_t stamp = 0;
+    std::vector<uint32_t> team_stamp, prog_stamp;
+    std::vector<int32_t> team_id, prog_id, teams, progs, team_off, edge_prog, edge_dst, roots;
+    std::vector<double> consts;
+};
+
 struct tpgx_ctx {
     tpgx_config cfg{};
     std::string err;
@@ -104,6 +113,7 @@ struct tpgx_ctx {
     std::vector<int32_t> h_edge_row, h_active;
     std::vector<uint8_t> h_stage_in, h_stage_out; /* episode calls: one transfer each way */
     std::vector<tpgx_ctx*> lanes;        /* tpgx_evaluate_graph_classification_allgather: contexts of the pipeline's slices (owned) */
+    SliceMaps slice_maps;                /* ... and the renumbering tables of set_graph_slice */
     bool tiles_shared = false;           /* a lane: d_tiles / d_labels / d_sobel are the parent's, prepared for the request */
     void* pin_ring = nullptr;            /* page-locked staging ring of upload() */
     int* h_status = nullptr;             /* page-locked copy of d_status ({device status, -, K1 encoder flags, -}) */
@@ -846,6 +856,7 @@ tpgx_status tpgx_set_data_sources(tpgx_ctx* ctx, int32_t n, const tpgx_source_de
 }
 
 static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard_only, int range_begin, int range_end);
+static tpgx_status upload_flat_graph(tpgx_ctx* ctx, const double* constants, const std::vector<uint8_t>& mask);
 tpgx_status tpgx_set_graph(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, false, -1, -1); }
 tpgx_status tpgx_set_graph_sharded(tpgx_ctx* ctx, const tpgx_graph* g) { return set_graph_impl(ctx, g, true, -1, -1); }
 
@@ -895,6 +906,15 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
     if (st != TPGX_OK) return fail(ctx, st, msg);
     tr.lap("flatten");
     ctx->flat = std::move(f);
+    st = upload_flat_graph(ctx, g->constants, mask);
+    tr.lap("uploads enqueued"); /* no synchronisation: upload() has consumed its sources */
+    return st;
+}
+
+/* The flattened graph (ctx->flat) to the device.  constants: [nb_programs][nb_constants] in the numbering of ctx->flat; mask (may be
+   empty): the programs that were flattened — only their constants travel. */
+static tpgx_status upload_flat_graph(tpgx_ctx* ctx, const double* constants, const std::vector<uint8_t>& mask) {
+    tpgx_status st;
     const tpgx_flat_graph& F = ctx->flat;
     ctx->uses_trig = ctx->uses_ext = ctx->uses_int = false;
     { /* instruction classes present among the effective lines (selects the K1 build, rejects int ops on image sources); the
@@ -910,18 +930,18 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
     for (int e = 0; e < F.nb_edges; e++) { int p = F.edge_program[e]; edge_lines[e] = F.prog_offset[p + 1] - F.prog_offset[p]; }
     if ((st = upload(ctx, ctx->d_code, F.code.data(), F.code.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_prog_off, F.prog_offset.data(), F.prog_offset.size() * 4)) != TPGX_OK) return st;
-    /* program constants straight from the caller's array; a shard / slice sends the runs of programs it reaches only */
+    /* program constants straight from the caller's array; a shard sends the runs of programs it reaches only */
     if (ctx->cfg.nb_constants > 0 && F.nb_programs > 0) {
         const size_t row = (size_t)ctx->cfg.nb_constants * 8;
         CU(ctx->d_consts.ensure((size_t)F.nb_programs * row));
         if (mask.empty()) {
-            if ((st = upload_at(ctx, ctx->d_consts, 0, g->constants, (size_t)F.nb_programs * row)) != TPGX_OK) return st;
+            if ((st = upload_at(ctx, ctx->d_consts, 0, constants, (size_t)F.nb_programs * row)) != TPGX_OK) return st;
         } else {
             for (int p = 0; p < F.nb_programs;) {
                 if (!mask[(size_t)p]) { p++; continue; }
                 int q = p;
                 while (q < F.nb_programs && mask[(size_t)q]) q++;
-                if ((st = upload_at(ctx, ctx->d_consts, (size_t)p * row, g->constants + (size_t)p * ctx->cfg.nb_constants, (size_t)(q - p) * row)) != TPGX_OK) return st;
+                if ((st = upload_at(ctx, ctx->d_consts, (size_t)p * row, constants + (size_t)p * ctx->cfg.nb_constants, (size_t)(q - p) * row)) != TPGX_OK) return st;
                 p = q;
             }
         }
@@ -930,10 +950,85 @@ static tpgx_status set_graph_impl(tpgx_ctx* ctx, const tpgx_graph* g, bool shard
     if ((st = upload(ctx, ctx->d_edge_dst, F.edge_destination.data(), F.edge_destination.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_lines, edge_lines.data(), edge_lines.size() * 4)) != TPGX_OK) return st;
     if ((st = upload(ctx, ctx->d_edge_prog, F.edge_program.data(), F.edge_program.size() * 4)) != TPGX_OK) return st;
-    tr.lap("uploads enqueued"); /* no synchronisation: upload() has consumed its sources */
     ctx->graph_version++;
     ctx->has_graph = true;
     return TPGX_OK;
+}
+
+/* A slice of the caller's graph — roots [rb, re) and what they reach — as a graph of its own on `ctx`: teams, edges and
+   programs renumbered in breadth-first order (edge order within a team kept: it decides ties), roots 0 .. re - rb - 1.  The
+   lines stay where they are (the flattener follows prog_ids); the constants are gathered.  Every cost — flatten, plan,
+   uploads — scales with the slice, none with the graph: a 1 / 16 slice of an 8192-root graph paid 0.5 ms of fixed
+   full-graph work (array copies, zero fills, 0.7 MB of uploads) per call before.  `owner` keeps the renumbering tables
+   (stamped, never cleared). */
+static tpgx_status set_graph_slice(tpgx_ctx* ctx, tpgx_ctx* owner, const tpgx_graph* g, int rb, int re) {
+    if (ctx->opcode.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: instruction table not set");
+    if (ctx->src.empty()) return fail(ctx, TPGX_ERR_STATE, "tpgx_set_graph: data sources not set");
+    if (!g || !g->program_line_offset || !g->lines || !g->team_edge_offset || !g->edge_program || !g->edge_destination || !g->root_team)
+        return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_graph: null array in graph");
+    if (g->nb_programs < 1 || g->nb_teams < 1 || rb < 0 || re > g->nb_roots || rb >= re) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_graph: empty graph slice");
+    if (ctx->cfg.nb_constants > 0 && !g->constants) return fail(ctx, TPGX_ERR_BAD_ARG, "tpgx_set_graph: constants missing");
+    cudaSetDevice(ctx->cfg.device);
+    Trace tr("set_graph (slice)");
+    SliceMaps& M = owner->slice_maps;
+    if ((int)M.team_stamp.size() < g->nb_teams) { M.team_stamp.assign((size_t)g->nb_teams, 0u); M.team_id.resize((size_t)g->nb_teams); }
+    if ((int)M.prog_stamp.size() < g->nb_programs) { M.prog_stamp.assign((size_t)g->nb_programs, 0u); M.prog_id.resize((size_t)g->nb_programs); }
+    if (++M.stamp == 0) { std::fill(M.team_stamp.begin(), M.team_stamp.end(), 0u); std::fill(M.prog_stamp.begin(), M.prog_stamp.end(), 0u); M.stamp = 1; }
+    const uint32_t stamp = M.stamp;
+    std::vector<int32_t>& teams = M.teams; /* new id -> the caller's team */
+    std::vector<int32_t>& progs = M.progs; /* new id -> the caller's program */
+    std::vector<int32_t>&team_off = M.team_off, &edge_prog = M.edge_prog, &edge_dst = M.edge_dst, &roots = M.roots;
+    teams.clear(); progs.clear(); team_off.clear(); edge_prog.clear(); edge_dst.clear(); roots.clear();
+    auto team_of = [&](int t) {
+        if (M.team_stamp[(size_t)t] != stamp) { M.team_stamp[(size_t)t] = stamp; M.team_id[(size_t)t] = (int32_t)teams.size(); teams.push_back(t); }
+        return M.team_id[(size_t)t];
+    };
+    for (int r = rb; r < re; r++) {
+        const int t = g->root_team[r];
+        if (t < 0 || t >= g->nb_teams) return fail(ctx, TPGX_ERR_BAD_ARG, "root team out of range");
+        roots.push_back(team_of(t));
+    }
+    team_off.push_back(0);
+    for (size_t q = 0; q < teams.size(); q++) {
+        const int t = teams[q];
+        const int eb = g->team_edge_offset[t], ee = g->team_edge_offset[t + 1];
+        if (eb < 0 || ee < eb) return fail(ctx, TPGX_ERR_BAD_ARG, "team_edge_offset not monotone");
+        for (int e = eb; e < ee; e++) {
+            const int p = g->edge_program[e], d = g->edge_destination[e];
+            if (p < 0 || p >= g->nb_programs) return fail(ctx, TPGX_ERR_BAD_ARG, "edge " + std::to_string(e) + ": program out of range");
+            if (d >= g->nb_teams) return fail(ctx, TPGX_ERR_BAD_ARG, "edge " + std::to_string(e) + ": destination team out of range");
+            if (M.prog_stamp[(size_t)p] != stamp) { M.prog_stamp[(size_t)p] = stamp; M.prog_id[(size_t)p] = (int32_t)progs.size(); progs.push_back(p); }
+            edge_prog.push_back(M.prog_id[(size_t)p]);
+            edge_dst.push_back(d >= 0 ? team_of(d) : d);
+        }
+        team_off.push_back((int32_t)edge_prog.size());
+    }
+    const int nc = ctx->cfg.nb_constants;
+    std::vector<double>& consts = M.consts;
+    consts.resize((size_t)progs.size() * (size_t)std::max(nc, 0));
+    if (nc > 0)
+        for (size_t p = 0; p < progs.size(); p++) memcpy(consts.data() + p * nc, g->constants + (size_t)progs[p] * nc, (size_t)nc * 8);
+    tpgx_graph cg = *g;
+    cg.nb_programs = (int32_t)progs.size();
+    cg.intron = nullptr;
+    cg.constants = nc > 0 ? consts.data() : nullptr;
+    cg.nb_teams = (int32_t)teams.size();
+    cg.team_edge_offset = team_off.data();
+    cg.edge_program = edge_prog.data();
+    cg.edge_destination = edge_dst.data();
+    cg.nb_roots = re - rb;
+    cg.root_team = roots.data();
+    tr.lap("sub-graph");
+    std::string msg;
+    tpgx_flat_graph f;
+    tpgx_status st = tpgx_flatten_graph(ctx->cfg, ctx->opcode, ctx->src, &cg, &f, &msg, nullptr, nullptr, progs.data());
+    if (st != TPGX_OK) return fail(ctx, st, msg);
+    tr.lap("flatten");
+    ctx->flat = std::move(f);
+    ctx->flat_root_begin = 0; ctx->flat_root_end = -1;
+    st = upload_flat_graph(ctx, cg.constants, std::vector<uint8_t>());
+    tr.lap("uploads enqueued");
+    return st;
 }
 
 /* One generation in one call: tpgx_set_graph_sharded + tpgx_evaluate_classification_allgather, with the host side of the
@@ -958,6 +1053,8 @@ tpgx_status tpgx_evaluate_graph_classification_allgather(tpgx_ctx* ctx, const tp
     int want = 3, min_roots = 512;
     if (const char* v = getenv("TPGX_PIPELINE")) { want = std::max(1, std::min(8, atoi(v))); min_roots = 128; }
     const int K = std::max(1, std::min(want, (re - rb) / min_roots));
+    int first_pm = 0;
+    if (const char* v = getenv("TPGX_PIPELINE_FIRST")) first_pm = std::max(0, std::min(900, atoi(v)));
     ctx->has_graph = false; /* the parent keeps no graph after this call */
     if (K <= 1) {
         tpgx_status st = set_graph_impl(ctx, g, true, rb, std::max(re, rb));
@@ -993,17 +1090,25 @@ tpgx_status tpgx_evaluate_graph_classification_allgather(tpgx_ctx* ctx, const tp
     for (int k = 0; k < K; k++) {
         tpgx_ctx* lane = ctx->lanes[k];
         /* the first slice is half as long as the others: the device starts after 1 / (2K - 1) of the host work */
-        auto cut = [&](int i) { return i <= 0 ? rb : i >= K ? re : rb + (int)((int64_t)(re - rb) * (2 * i - 1) / (2 * K - 1)); };
+        auto cut = [&](int i) {
+            if (i <= 0) return rb;
+            if (i >= K) return re;
+            if (first_pm > 0) { /* experiments: the first slice takes first_pm / 1000 of the shard, the others share the rest */
+                const int first = std::max(1, (int)((int64_t)(re - rb) * first_pm / 1000));
+                return rb + first + (int)((int64_t)(re - rb - first) * (i - 1) / (K - 1));
+            }
+            return rb + (int)((int64_t)(re - rb) * (2 * i - 1) / (2 * K - 1));
+        };
         const int b = cut(k), e = cut(k + 1);
         lane->opcode = ctx->opcode; lane->src = ctx->src; lane->variant = ctx->variant; lane->bid_budget = ctx->bid_budget;
         lane->d_tiles.alias(ctx->d_tiles); lane->d_labels.alias(ctx->d_labels); lane->d_sobel.alias(ctx->d_sobel);
         lane->obs_dev = ctx->obs_dev; lane->labels_dev = ctx->labels_dev; lane->nb_obs = ctx->nb_obs; lane->obs_hw = ctx->obs_hw;
         lane->obs_width = ctx->obs_width; lane->nwin = ctx->nwin; lane->tiles_ts = ts; lane->tiles_shared = true; lane->obs_pending = false;
         if (cudaStreamWaitEvent(lane->stream, start, 0) != cudaSuccess) return fail(ctx, TPGX_ERR_CUDA, "cudaStreamWaitEvent (lane)");
-        tpgx_status st = set_graph_impl(lane, g, true, b, e);
+        tpgx_status st = set_graph_slice(lane, ctx, g, b, e); /* roots b .. e - 1 are roots 0 .. e - b - 1 of the lane's graph */
         if (st == TPGX_OK) {
             tpgx_classif_request r = *req;
-            r.root_begin = b; r.root_end = e;
+            r.root_begin = 0; r.root_end = e - b;
             st = enqueue_classification(lane, &r, mine + (size_t)(b - rb) * (C + 1), false, false, nullptr, false);
         }
         if (st != TPGX_OK) { ctx->err = lane->err; return st; }

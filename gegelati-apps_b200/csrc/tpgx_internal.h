@@ -222,6 +222,6 @@ static inline int tpgx_parallel_workers() { return 16; }
 tpgx_status tpgx_flatten_graph(const tpgx_config& cfg, const std::vector<int32_t>& opcode,
                                const std::vector<tpgx_source_desc>& src, const tpgx_graph* g,
                                tpgx_flat_graph* out, std::string* err, std::vector<uint8_t>* keep_out = nullptr,
-                               const std::vector<uint8_t>* prog_mask = nullptr);
+                               const std::vector<uint8_t>* prog_mask = nullptr, const int32_t* prog_ids = nullptr);
 
 #endif
