@@ -163,7 +163,7 @@ __device__ __forceinline__ void k2_cp_async_wait_all() { asm volatile("cp.async.
     "mov.b64 {xlo, xhi}, " x ";\n"                                                               \
     "sub.u32 t0, xhi, 0x3FE6B000;\n shr.u32 ii, t0, 13;\n and.b32 ii, ii, 127;\n shr.s32 kk, t0, 20;\n" \
     "and.b32 t0, t0, 0xfff00000;\n sub.u32 t0, xhi, t0;\n mov.b64 z, {xlo, t0};\n"               \
-    "shl.b32 ii, ii, 5;\n add.u32 ii, ii, " TAB ";\n ld.shared.v2.f64 {invc, lchi}, [ii+2048];\n ld.shared.f64 lclo, [ii+2064];\n" \
+    "mad.lo.u32 t0, ii, 8, " TAB ";\n mad.lo.u32 ii, ii, 16, " TAB ";\n ld.shared.v2.f64 {invc, lchi}, [ii+2048];\n ld.shared.f64 lclo, [t0+4096];\n" \
     "fma.rn.f64 r, z, invc, " KD_MONE ";\n cvt.rn.f64.s32 kd, kk;\n fma.rn.f64 w, kd, " KD_LN2_HI ", lchi;\n add.rn.f64 hi, w, r;\n" \
     "sub.rn.f64 lo, w, hi;\n add.rn.f64 lo, lo, r;\n fma.rn.f64 tmp, kd, " KD_LN2_LO ", lclo;\n add.rn.f64 lo, lo, tmp;\n" \
     "mul.rn.f64 r2, r, r;\n fma.rn.f64 pa, r, " KD_C1_7 ", " KD_CM1_6 ";\n fma.rn.f64 pa, r, pa, " KD_C0_2 ";\n" \
@@ -258,8 +258,16 @@ __global__ void __launch_bounds__(K2_NW * 32, K2_MINB) tpgx_bid2_kernel(const tp
     extern __shared__ __align__(128) uint8_t smem[];
     double* s_tab = reinterpret_cast<double*>(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < 256 + 512 + 512; i += K2_NW * 32)
-        s_tab[i] = i < 256 ? tpgx_math::tpgx_exp_tab_dev[i] : i < 768 ? tpgx_math::tpgx_log_tab_dev[i - 256] : __ldg(p.pixel_lut + (i - 768));
+    /* the ln table {1/c, ln c high, ln c low, -} is split into 16-byte pairs {1/c, ln c high} and a plane of ln c low: 32-byte entries
+       put the 32 lanes' lookups on 4 groups of 8 banks (~11 wavefronts per load), 16-byte entries on 8 groups and the 8-byte plane on 16 */
+    for (int i = threadIdx.x; i < 256 + 512 + 512; i += K2_NW * 32) {
+        if (i < 256) s_tab[i] = tpgx_math::tpgx_exp_tab_dev[i];
+        else if (i < 768) {
+            const int e = (i - 256) >> 2, c = (i - 256) & 3;
+            if (c < 2) s_tab[256 + 2 * e + c] = tpgx_math::tpgx_log_tab_dev[i - 256];
+            else if (c == 2) s_tab[512 + e] = tpgx_math::tpgx_log_tab_dev[i - 256];
+        } else s_tab[i] = __ldg(p.pixel_lut + (i - 768));
+    }
     if (threadIdx.x == 0) *reinterpret_cast<const uint4**>(smem + K2_TAB_BYTES) = p.stream;
     const uint32_t tab = k2_smem_u32(s_tab);
     __syncthreads();

@@ -1052,11 +1052,11 @@ tpgx_status tpgx_evaluate_graph_classification_allgather(tpgx_ctx* ctx, const tp
        fixed part of the host work again) */
     int want = 3, min_roots = 512;
     if (const char* v = getenv("TPGX_PIPELINE")) { want = std::max(1, std::min(8, atoi(v))); min_roots = 128; }
-    const int K = std::max(1, std::min(want, (re - rb) / min_roots));
+    const int K = std::max(1, std::min(want, (re - rb) / min_roots)); /* one slice: no pipelining, but still the slice's own sub-graph */
     int first_pm = 0;
     if (const char* v = getenv("TPGX_PIPELINE_FIRST")) first_pm = std::max(0, std::min(900, atoi(v)));
     ctx->has_graph = false; /* the parent keeps no graph after this call */
-    if (K <= 1) {
+    if (re <= rb) { /* an empty shard (more ranks than roots): nothing of the graph to set, the collective still runs */
         tpgx_status st = set_graph_impl(ctx, g, true, rb, std::max(re, rb));
         if (st != TPGX_OK) return st;
         return tpgx_evaluate_classification_allgather(ctx, req, total_roots, records_all);
