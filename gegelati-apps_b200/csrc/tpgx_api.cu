@@ -1047,10 +1047,10 @@ tpgx_status tpgx_evaluate_graph_classification_allgather(tpgx_ctx* ctx, const tp
     cudaSetDevice(ctx->cfg.device);
     int slot, rb, re;
     shard_of(ctx, total_roots, &slot, &rb, &re);
-    /* slices of 512 roots or more, at most 3 (measured: 2000 roots on one GPU 9.42 / 9.51 / 9.58 ms with 3 / 4 / 5 slices against
-       10.1 ms in two calls; 1024 roots per GPU on 8 GPUs 6.08 / 6.25 / 6.35 ms with 2 / 3 / 4 against 7.24 ms: every slice pays the
-       fixed part of the host work again) */
-    int want = 3, min_roots = 512;
+    /* slices of 256 roots or more, at most 4.  Measured with every slice flattened as a sub-graph of its own (no cost of a slice
+       scales with the whole graph any more): 1024 roots per GPU on 8 GPUs 6.26 / 5.55 / 5.52 / 5.43 / 5.60 ms with 1 / 2 / 3 / 4 / 6
+       slices against 6.93 ms in two calls; 2000 roots on one GPU 9.06 / 9.06 ms with 3 / 4 */
+    int want = 4, min_roots = 256;
     if (const char* v = getenv("TPGX_PIPELINE")) { want = std::max(1, std::min(8, atoi(v))); min_roots = 128; }
     const int K = std::max(1, std::min(want, (re - rb) / min_roots)); /* one slice: no pipelining, but still the slice's own sub-graph */
     int first_pm = 0;
