@@ -454,9 +454,11 @@ tpgx_status enqueue_classification(tpgx_ctx* ctx, const tpgx_classif_request* re
             bp.slots = ctx->plan.k1_slots;
             if (const char* v = getenv("TPGX_K1_SLOTS")) bp.slots = std::min(K1V2_SLOTS, std::max(bp.slots, atoi(v))); /* experiments: more than needed */
             /* work items = (tile, group of units), claimed warp by warp: ~20 items per resident warp when there is that
-               much work (dynamic balance to the last item), at most 8 teams / 32 programs per item */
+               much work (dynamic balance to the last item), at most 2 teams / 8 programs per item — an item of 8 teams is 40 rows,
+               0.33 ms of a warp's time, and the last ones leave warps idle (C2 K1 7.97 -> 7.90 ms, a 1024-root shard 4.13 -> 4.08 with
+               2; the claim itself — one atomic and one descriptor load per item — does not show: 1 team per item measures the same) */
             const int64_t warps = (int64_t)ctx->sm_count * 32;
-            int g = (int)std::min<int64_t>(team_mode ? 8 : 32, std::max<int64_t>(1, (int64_t)nt * nU / (20 * warps)));
+            int g = (int)std::min<int64_t>(team_mode ? 2 : 8, std::max<int64_t>(1, (int64_t)nt * nU / (20 * warps)));
             if (const char* v = getenv("TPGX_K1_GROUP")) g = std::max(1, atoi(v)); /* experiments */
             bp.units_per_item = g;
             bp.items_per_tile = (nU + g - 1) / g;
