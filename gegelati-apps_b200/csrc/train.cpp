@@ -14,6 +14,8 @@
 #include <cstring>
 #include <deque>
 #include <map>
+#include <unordered_map>
+#include <memory>
 #include <random>
 
 #include "tpgx_internal.h"
@@ -68,7 +70,10 @@ struct NewProg {
     int id;
     std::vector<tpgx_line> parent_lines;
     double parent_consts[TPGX_MAX_CONSTS];
-    std::mt19937_64 rng; /* [UP] mutateNewProgramBehaviors gives every new program its own RNG, seeded from the agent's */
+    /* [UP] mutateNewProgramBehaviors gives every new program its own RNG, seeded from the agent's.  The 2.5 KB engine is made
+       when the program is known to survive the populate (settle_new_programs), not copied around with the record */
+    std::unique_ptr<std::mt19937_64> rng_store;
+    std::mt19937_64& rng_ref() { return *rng_store; }
 };
 
 } // namespace
@@ -123,9 +128,11 @@ struct tpgx_trainer {
     std::vector<uint32_t> prog_mark; /* mutate_team: programs already on the team carry the current stamp */
     uint32_t stamp = 0;
     std::vector<size_t> cand_scratch;
-    std::mt19937_64* cur = nullptr; /* the engine u64() / dbl() draw from: the agent's, or a new program's own while it is being mutated */
-    uint64_t u64(uint64_t lo, uint64_t hi) { return std::uniform_int_distribution<uint64_t>(lo, hi)(cur ? *cur : rng); } /* [UP] RNG::getUnsignedInt64 */
-    double dbl() { return std::uniform_real_distribution<double>(0.0, 1.0)(cur ? *cur : rng); }                          /* [UP] RNG::getDouble(0, 1) */
+    /* the engine u64() / dbl() draw from: the agent's, or a new program's own while it is being mutated — per host thread, so that
+       the new programs of a generation (an engine each) mutate in parallel on the pool */
+    static std::mt19937_64*& cur() { static thread_local std::mt19937_64* e = nullptr; return e; }
+    uint64_t u64(uint64_t lo, uint64_t hi) { return std::uniform_int_distribution<uint64_t>(lo, hi)(cur() ? *cur() : rng); } /* [UP] RNG::getUnsignedInt64 */
+    double dbl() { return std::uniform_real_distribution<double>(0.0, 1.0)(cur() ? *cur() : rng); }                          /* [UP] RNG::getDouble(0, 1) */
 
     /* ---- bookkeeping ---- */
     int new_prog() {
@@ -177,6 +184,11 @@ struct tpgx_trainer {
     int nb_action_edges(int team) const {
         int n = 0;
         for (const TEdge& e : teams[team].edges) n += e.dest < 0;
+        return n;
+    }
+    int count_roots() const {
+        int n = 0;
+        for (int t : order) n += teams[t].incoming == 0;
         return n;
     }
     std::vector<int> roots() const {
@@ -320,7 +332,7 @@ struct tpgx_trainer {
                 rec.id = np;
                 rec.parent_lines = progs[old].lines;
                 std::memcpy(rec.parent_consts, progs[old].consts, sizeof rec.parent_consts);
-                fresh.push_back(rec);
+                fresh.push_back(std::move(rec));
                 T.edges[i].prog = np;
                 unref_prog(old);
                 if (dbl() < P.p_edge_destination_change) {
@@ -389,15 +401,38 @@ struct tpgx_trainer {
             fprintf(stderr, "[tpgx] settle: %s %.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tick).count());
             tick = t;
         };
-        for (NewProg& n : fresh) n.rng.seed(u64(0, UINT64_MAX));
-        struct Scope { tpgx_trainer* t; Scope(tpgx_trainer* t_, std::mt19937_64* e) : t(t_) { t->cur = e; } ~Scope() { t->cur = nullptr; } };
-        for (NewProg& n : fresh) { Scope sc(this, &n.rng); mutate_program(progs[n.id]); }
+        std::vector<uint64_t> seeds(fresh.size()); /* drawn in order from the agent's engine; the engines are made in parallel below */
+        for (uint64_t& sd : seeds) sd = u64(0, UINT64_MAX);
+        struct Scope { Scope(tpgx_trainer*, std::mt19937_64* e) { cur() = e; } ~Scope() { cur() = nullptr; } };
+        /* every program draws from its own engine and touches its own entry of progs: independent of the others, of their order
+           and of the number of threads */
+        tpgx_parallel_blocks((int)fresh.size(), 16, [&](int b, int e, int) {
+            for (int i = b; i < e; i++) {
+                NewProg& n = fresh[(size_t)i];
+                n.rng_store.reset(new std::mt19937_64(seeds[(size_t)i]));
+                Scope sc(this, &n.rng_ref());
+                mutate_program(progs[n.id]);
+            }
+        });
         lap("seed + first mutation");
         if (!P.force_program_behavior_change || archive.empty() || fresh.empty()) return TPGX_OK;
         if (!be || !be->execute) { err = "forceProgramBehaviorChangeOnMutation needs a backend to run the new programs on the archive"; return TPGX_ERR_BAD_ARG; }
         /* the distinct archived observations ([UP] the archive keys its data-handler copies by hash) and, per archived
            program, its recorded bid on each of them */
-        std::map<std::vector<double>, int> obs_index;
+        struct ObsHash { /* keyed by the bytes of the doubles, as [UP] the archive hashes its data-handler copies (+0.0 and -0.0 are two observations) */
+            size_t operator()(const std::vector<double>& v) const {
+                uint64_t h = 1469598103934665603ull;
+                for (double d : v) { uint64_t b; std::memcpy(&b, &d, 8); h = (h ^ b) * 1099511628211ull; h ^= h >> 29; }
+                return (size_t)h;
+            }
+        };
+        struct ObsEq {
+            bool operator()(const std::vector<double>& a, const std::vector<double>& b) const {
+                return a.size() == b.size() && (a.empty() || std::memcmp(a.data(), b.data(), a.size() * 8) == 0);
+            }
+        };
+        std::unordered_map<std::vector<double>, int, ObsHash, ObsEq> obs_index;
+        obs_index.reserve(archive.size() * 2);
         std::vector<double> obs;
         std::map<int, std::map<int, double>> by_prog;
         for (const ARec& r : archive) {
@@ -429,12 +464,14 @@ struct tpgx_trainer {
             const int M = (int)pending.size();
             /* candidates of pending program i: c[0] = its current mutant, c[k] = one more mutation of c[k-1] */
             std::vector<TProg> cand((size_t)M * S);
-            for (int i = 0; i < M; i++) {
-                NewProg& n = fresh[pending[i]];
-                Scope sc(this, &n.rng);
-                cand[(size_t)i * S] = progs[n.id];
-                for (int k = 1; k < S; k++) { cand[(size_t)i * S + k] = cand[(size_t)i * S + k - 1]; mutate_program(cand[(size_t)i * S + k]); }
-            }
+            tpgx_parallel_blocks(M, 16, [&](int b, int e, int) {
+                for (int i = b; i < e; i++) {
+                    NewProg& n = fresh[pending[(size_t)i]];
+                    Scope sc(this, &n.rng_ref());
+                    cand[(size_t)i * S] = progs[n.id];
+                    for (int k = 1; k < S; k++) { cand[(size_t)i * S + k] = cand[(size_t)i * S + k - 1]; mutate_program(cand[(size_t)i * S + k]); }
+                }
+            });
             lap("candidates");
             /* a scratch graph: per pending program its S candidates then its origin, one team pointing at all of them */
             const int per = S + 1, NP = M * per;
@@ -483,7 +520,7 @@ struct tpgx_trainer {
                 if (pick >= 0) progs[n.id] = cand[(size_t)i * S + pick];
                 else { /* all S failed: one more mutation of the last one opens the next call (a retry like the others) */
                     progs[n.id] = cand[(size_t)i * S + S - 1];
-                    Scope sc(this, &n.rng);
+                    Scope sc(this, &n.rng_ref());
                     mutate_program(progs[n.id]);
                     again.push_back(pending[i]);
                 }
@@ -563,14 +600,18 @@ tpgx_status tpgx_trainer_populate(tpgx_trainer* t, const tpgx_train_backend* bac
     const std::vector<int> pre_teams = t->order;
     t->pre_built = nullptr;
     std::vector<NewProg> fresh;
+    fresh.reserve(1024);
     int nb_roots = (int)parents.size();
+    static const bool trace = getenv("TPGX_TRACE") != nullptr;
+    const auto c0 = std::chrono::steady_clock::now();
     while (nb_roots < t->P.nb_roots) {
         const int parent = parents[t->u64(0, parents.size() - 1)];
         const int child = t->new_team();
         for (const TEdge e : std::vector<TEdge>(t->teams[parent].edges)) t->add_edge(child, e.prog, e.dest);
         t->mutate_team(child, pre_edges, pre_teams, fresh);
-        nb_roots = (int)t->roots().size(); /* a destination change may have turned a parent into an inner team */
+        nb_roots = t->count_roots(); /* a destination change may have turned a parent into an inner team */
     }
+    if (trace) fprintf(stderr, "[tpgx] populate: clone + mutate teams %.3f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - c0).count());
     /* programs created and dropped again within this populate are gone already */
     std::vector<NewProg> live;
     for (NewProg& n : fresh) if (t->progs[n.id].alive && t->progs[n.id].refs > 0) live.push_back(std::move(n));
