@@ -41,7 +41,9 @@ struct DevBuf {
         borrowed = false;
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        /* head room: small buffers (graph arrays, scratch of a generation loop: they grow a little every generation while the graph
+           does) double, so that a loop stops allocating after a few generations; large ones (matrices, planes) take an eighth */
+        size_t want = bytes < ((size_t)64 << 20) ? 2 * bytes + 256 : bytes + bytes / 8 + 256;
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
         if (e == cudaSuccess) cap = want;

@@ -113,6 +113,9 @@ struct tpgx_trainer {
     std::map<int, std::vector<int>> pre_by_prog;
     bool defer_archive = false;      /* set while no program id can be reused (decimation): unref_prog only notes the deleted programs */
     std::vector<int> dead_progs;
+    std::vector<int64_t> s_off;        /* settle_new_programs' scratch graph and bids, kept between generations */
+    std::vector<tpgx_line> s_lines;
+    std::vector<double> s_consts, s_bid, s_obs;
     void purge_archive() {
         if (!dead_progs.empty()) {
             std::vector<char> dead(progs.size(), 0);
@@ -433,7 +436,8 @@ struct tpgx_trainer {
         };
         std::unordered_map<std::vector<double>, int, ObsHash, ObsEq> obs_index;
         obs_index.reserve(archive.size() * 2);
-        std::vector<double> obs;
+        std::vector<double>& obs = s_obs;
+        obs.clear();
         std::map<int, std::map<int, double>> by_prog;
         for (const ARec& r : archive) {
             auto it = obs_index.find(r.obs);
@@ -475,9 +479,14 @@ struct tpgx_trainer {
             lap("candidates");
             /* a scratch graph: per pending program its S candidates then its origin, one team pointing at all of them */
             const int per = S + 1, NP = M * per;
-            std::vector<int64_t> off(1, 0);
-            std::vector<tpgx_line> lines;
-            std::vector<double> consts((size_t)NP * (size_t)std::max(1, nC), 0.0);
+            /* the big scratch arrays (lines, bids: tens of MB) live in the trainer and keep their capacity: fresh pages every call cost
+               page faults, and on the virtualised GPU boxes a burst of first-touch faults now and then stalls for 0.5 - 0.8 s */
+            std::vector<int64_t>& off = s_off;
+            std::vector<tpgx_line>& lines = s_lines;
+            std::vector<double>& consts = s_consts;
+            off.assign(1, 0);
+            lines.clear();
+            consts.assign((size_t)NP * (size_t)std::max(1, nC), 0.0);
             std::vector<int32_t> teo = {0, NP}, ep((size_t)NP), ed((size_t)NP, -1), root = {0};
             for (int i = 0; i < M; i++) {
                 const NewProg& n = fresh[pending[i]];
@@ -493,7 +502,8 @@ struct tpgx_trainer {
             }
             for (int q = 0; q < NP; q++) ep[q] = q;
             tpgx_graph g{NP, off.data(), lines.data(), nullptr, nC > 0 ? consts.data() : nullptr, 1, teo.data(), ep.data(), ed.data(), 1, root.data()};
-            std::vector<double> bid((size_t)NP * (size_t)count);
+            std::vector<double>& bid = s_bid;
+            bid.resize((size_t)NP * (size_t)count);
             lap("scratch graph");
             const tpgx_status st = be->execute(be->user, &g, count, obs.data(), obs_len, bid.data());
             if (st != TPGX_OK) { err = "backend execute failed"; return st; }
