@@ -178,3 +178,44 @@ def test_empty_program_and_unsupported_sets():
     # an instruction outside the MNIST set (cos) is left to K1 v1
     word = A.OP_COS | (0 << 5) | ((2 << 10 | 5) << 8)
     assert tpgx.k1v2_encode_program(np.array([word], dtype=np.uint32)) is None
+
+
+@pytest.mark.parametrize("lines", [1, 5, 20, 34, 35, 36, 70, 71, 141, 256])
+def test_count_pass_equals_the_encoder_on_dense_random_words(lines):
+    """The planner's count pass is closed-form (stores = values read later than the next line, slots = the largest number of
+    them live at once, NEXT entries from the entry count); tpgx_k1v2_encode_program returns TPGX_ERR_STATE when it disagrees
+    with the encoder's own replay of the slot allocator.  Random line words straight in the device format: every register
+    written before it is read, registers reused heavily (long live ranges, up to 8 values in slots), lengths around the
+    block capacity and up to the 256-line limit."""
+    rng = np.random.default_rng(1000 + lines)
+    ops = [A.OP_SUB, A.OP_ADD, A.OP_MUL, A.OP_DIV, A.OP_MAX, A.OP_EXP, A.OP_LOG, A.OP_MULC, A.OP_SOBEL_MAGN, A.OP_SOBEL_DIR]
+    seen_slots, seen_next = 0, False
+    for _ in range(60):
+        written, words = 0, []
+        for i in range(lines):
+            op = int(rng.choice(ops))
+            dst = 0 if i == lines - 1 else int(rng.integers(0, 8))
+            f = []
+            for k in range(2):
+                if rng.random() < 0.7:
+                    r = int(rng.integers(0, 8))
+                    f.append((0 << 10) | (r if (written >> r) & 1 else 8))     # register, or "never written" (reads 0.0)
+                else:
+                    f.append((2 << 10) | int(rng.integers(0, 784)))            # pixel
+            if op == A.OP_MULC:
+                f[1] = (1 << 10) | int(rng.integers(0, 5))                      # program constant
+            if op in (A.OP_SOBEL_MAGN, A.OP_SOBEL_DIR):
+                f[0] = (2 << 10) | (int(rng.integers(0, 26)) * 28 + int(rng.integers(0, 26)))
+            words.append(op | (dst << 5) | (f[0] << 8) | (f[1] << 20))
+            written |= 1 << dst
+        enc = tpgx.k1v2_encode_program(np.array(words, dtype=np.uint32))        # raises on TPGX_ERR_STATE
+        assert enc is not None
+        names = [tpgx.k1v2_handler_names()[h] for h in enc["quads"][:, 0]]
+        assert names[-1] == "END" and names.count("END") == 1
+        seen_slots = max(seen_slots, enc["slots"])
+        seen_next |= "NEXT" in names
+        assert names.count("NEXT") == (len(names) - names.count("NEXT") - 2) // (CAP - 1)
+    if lines >= 20:
+        assert seen_slots >= 4, seen_slots
+    assert seen_next or lines < CAP, "a program of a block's length or more chains blocks"
+    assert not (seen_next and lines <= 5)

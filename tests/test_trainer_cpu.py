@@ -131,6 +131,21 @@ def test_batched_behaviour_test_equals_one_mutant_per_call(oracle_mod, monkeypat
     assert prints[0] == prints[1] == prints[2]
 
 
+def test_evolution_does_not_depend_on_the_host_thread_count(oracle_mod, monkeypatch):
+    """The new programs of a generation mutate in parallel on the host pool, each with an engine of its own seeded in order
+    from the agent's: the evolution (graph fingerprint, retries, scores) must be the same with 1, 3 and 8 host threads.
+    120 roots so that a generation has more new programs than one pool block (16)."""
+    prints = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("TPGX_HOST_THREADS", threads)
+        tr, _ = make(seed=3, nb_roots=120, archive_size=400, archiving_probability=0.05)
+        be = oracle_backend(oracle_mod, "gridworld", nb_iterations=1, max_actions=100)
+        stats = [tr.train_generation(be, gen) for gen in range(5)]
+        assert max(s["nb_new_programs"] for s in stats) > 32
+        prints.append((tr.fingerprint(), [s["behaviour_retries"] for s in stats], [s["best_score"] for s in stats]))
+    assert prints[0] == prints[1] == prints[2]
+
+
 def test_evaluate_job_skips_roots_at_the_evaluation_cap_and_merges_previous_results(oracle_mod):
     """[UP] LearningAgent::evaluateJob ([REF] */params.json maxNbEvaluationPerPolicy: gridworld / pendulum 10, mnist 2000):
     a root whose stored result counts maxNbEvaluationPerPolicy evaluations is NOT run again in TRAINING mode, any other
