@@ -959,6 +959,44 @@ static tpgx_status upload_flat_graph(tpgx_ctx* ctx, const double* constants, con
     return TPGX_OK;
 }
 
+/* The sub-graph roots [rb, re) of g reach, renumbered: teams breadth-first from the roots in root order (M.teams: new id ->
+   the caller's team), programs in order of first appearance (M.progs), every team's edges in the caller's order (it decides
+   ties).  Stamped tables: nothing is cleared between calls. */
+static tpgx_status build_slice(SliceMaps& M, const tpgx_graph* g, int rb, int re, std::string* why) {
+    auto bad = [&](const std::string& m) { if (why) *why = m; return TPGX_ERR_BAD_ARG; };
+    if ((int)M.team_stamp.size() < g->nb_teams) { M.team_stamp.assign((size_t)g->nb_teams, 0u); M.team_id.resize((size_t)g->nb_teams); }
+    if ((int)M.prog_stamp.size() < g->nb_programs) { M.prog_stamp.assign((size_t)g->nb_programs, 0u); M.prog_id.resize((size_t)g->nb_programs); }
+    if (++M.stamp == 0) { std::fill(M.team_stamp.begin(), M.team_stamp.end(), 0u); std::fill(M.prog_stamp.begin(), M.prog_stamp.end(), 0u); M.stamp = 1; }
+    const uint32_t stamp = M.stamp;
+    std::vector<int32_t>&teams = M.teams, &progs = M.progs, &team_off = M.team_off, &edge_prog = M.edge_prog, &edge_dst = M.edge_dst, &roots = M.roots;
+    teams.clear(); progs.clear(); team_off.clear(); edge_prog.clear(); edge_dst.clear(); roots.clear();
+    auto team_of = [&](int t) {
+        if (M.team_stamp[(size_t)t] != stamp) { M.team_stamp[(size_t)t] = stamp; M.team_id[(size_t)t] = (int32_t)teams.size(); teams.push_back(t); }
+        return M.team_id[(size_t)t];
+    };
+    for (int r = rb; r < re; r++) {
+        const int t = g->root_team[r];
+        if (t < 0 || t >= g->nb_teams) return bad("root team out of range");
+        roots.push_back(team_of(t));
+    }
+    team_off.push_back(0);
+    for (size_t q = 0; q < teams.size(); q++) {
+        const int t = teams[q];
+        const int eb = g->team_edge_offset[t], ee = g->team_edge_offset[t + 1];
+        if (eb < 0 || ee < eb) return bad("team_edge_offset not monotone");
+        for (int e = eb; e < ee; e++) {
+            const int p = g->edge_program[e], d = g->edge_destination[e];
+            if (p < 0 || p >= g->nb_programs) return bad("edge " + std::to_string(e) + ": program out of range");
+            if (d >= g->nb_teams) return bad("edge " + std::to_string(e) + ": destination team out of range");
+            if (M.prog_stamp[(size_t)p] != stamp) { M.prog_stamp[(size_t)p] = stamp; M.prog_id[(size_t)p] = (int32_t)progs.size(); progs.push_back(p); }
+            edge_prog.push_back(M.prog_id[(size_t)p]);
+            edge_dst.push_back(d >= 0 ? team_of(d) : d);
+        }
+        team_off.push_back((int32_t)edge_prog.size());
+    }
+    return TPGX_OK;
+}
+
 /* A slice of the caller's graph — roots [rb, re) and what they reach — as a graph of its own on `ctx`: teams, edges and
    programs renumbered in breadth-first order (edge order within a team kept: it decides ties), roots 0 .. re - rb - 1.  The
    lines stay where they are (the flattener follows prog_ids); the constants are gathered.  Every cost — flatten, plan,
@@ -975,38 +1013,12 @@ static tpgx_status set_graph_slice(tpgx_ctx* ctx, tpgx_ctx* owner, const tpgx_gr
     cudaSetDevice(ctx->cfg.device);
     Trace tr("set_graph (slice)");
     SliceMaps& M = owner->slice_maps;
-    if ((int)M.team_stamp.size() < g->nb_teams) { M.team_stamp.assign((size_t)g->nb_teams, 0u); M.team_id.resize((size_t)g->nb_teams); }
-    if ((int)M.prog_stamp.size() < g->nb_programs) { M.prog_stamp.assign((size_t)g->nb_programs, 0u); M.prog_id.resize((size_t)g->nb_programs); }
-    if (++M.stamp == 0) { std::fill(M.team_stamp.begin(), M.team_stamp.end(), 0u); std::fill(M.prog_stamp.begin(), M.prog_stamp.end(), 0u); M.stamp = 1; }
-    const uint32_t stamp = M.stamp;
-    std::vector<int32_t>& teams = M.teams; /* new id -> the caller's team */
-    std::vector<int32_t>& progs = M.progs; /* new id -> the caller's program */
-    std::vector<int32_t>&team_off = M.team_off, &edge_prog = M.edge_prog, &edge_dst = M.edge_dst, &roots = M.roots;
-    teams.clear(); progs.clear(); team_off.clear(); edge_prog.clear(); edge_dst.clear(); roots.clear();
-    auto team_of = [&](int t) {
-        if (M.team_stamp[(size_t)t] != stamp) { M.team_stamp[(size_t)t] = stamp; M.team_id[(size_t)t] = (int32_t)teams.size(); teams.push_back(t); }
-        return M.team_id[(size_t)t];
-    };
-    for (int r = rb; r < re; r++) {
-        const int t = g->root_team[r];
-        if (t < 0 || t >= g->nb_teams) return fail(ctx, TPGX_ERR_BAD_ARG, "root team out of range");
-        roots.push_back(team_of(t));
+    {
+        std::string why;
+        const tpgx_status bst = build_slice(M, g, rb, re, &why);
+        if (bst != TPGX_OK) return fail(ctx, bst, why);
     }
-    team_off.push_back(0);
-    for (size_t q = 0; q < teams.size(); q++) {
-        const int t = teams[q];
-        const int eb = g->team_edge_offset[t], ee = g->team_edge_offset[t + 1];
-        if (eb < 0 || ee < eb) return fail(ctx, TPGX_ERR_BAD_ARG, "team_edge_offset not monotone");
-        for (int e = eb; e < ee; e++) {
-            const int p = g->edge_program[e], d = g->edge_destination[e];
-            if (p < 0 || p >= g->nb_programs) return fail(ctx, TPGX_ERR_BAD_ARG, "edge " + std::to_string(e) + ": program out of range");
-            if (d >= g->nb_teams) return fail(ctx, TPGX_ERR_BAD_ARG, "edge " + std::to_string(e) + ": destination team out of range");
-            if (M.prog_stamp[(size_t)p] != stamp) { M.prog_stamp[(size_t)p] = stamp; M.prog_id[(size_t)p] = (int32_t)progs.size(); progs.push_back(p); }
-            edge_prog.push_back(M.prog_id[(size_t)p]);
-            edge_dst.push_back(d >= 0 ? team_of(d) : d);
-        }
-        team_off.push_back((int32_t)edge_prog.size());
-    }
+    std::vector<int32_t>&progs = M.progs, &teams = M.teams, &team_off = M.team_off, &edge_prog = M.edge_prog, &edge_dst = M.edge_dst, &roots = M.roots;
     const int nc = ctx->cfg.nb_constants;
     std::vector<double>& consts = M.consts;
     consts.resize((size_t)progs.size() * (size_t)std::max(nc, 0));
@@ -1033,6 +1045,28 @@ static tpgx_status set_graph_slice(tpgx_ctx* ctx, tpgx_ctx* owner, const tpgx_gr
     st = upload_flat_graph(ctx, cg.constants, std::vector<uint8_t>());
     tr.lap("uploads enqueued");
     return st;
+}
+
+/* Host only (include/tpgx.h): the renumbered sub-graph of set_graph_slice on its own. */
+tpgx_status tpgx_slice_graph(const tpgx_graph* g, int32_t root_begin, int32_t root_end, int32_t* nb_teams, int32_t* nb_edges, int32_t* nb_programs,
+                             int32_t* team_ids, int32_t* team_edge_offset, int32_t* edge_program, int32_t* edge_destination, int32_t* program_ids,
+                             int32_t* root_team) {
+    if (!g || !g->team_edge_offset || !g->edge_program || !g->edge_destination || !g->root_team || !nb_teams || !nb_edges || !nb_programs) return TPGX_ERR_BAD_ARG;
+    if (g->nb_programs < 1 || g->nb_teams < 1 || root_begin < 0 || root_end > g->nb_roots || root_begin >= root_end) return TPGX_ERR_BAD_ARG;
+    SliceMaps M;
+    const tpgx_status st = build_slice(M, g, root_begin, root_end, nullptr);
+    if (st != TPGX_OK) return st;
+    /* sizes first; the arrays are filled when the caller's counts (from a first call) say they are large enough */
+    const bool fits = *nb_teams >= (int32_t)M.teams.size() && *nb_edges >= (int32_t)M.edge_prog.size() && *nb_programs >= (int32_t)M.progs.size();
+    *nb_teams = (int32_t)M.teams.size(); *nb_edges = (int32_t)M.edge_prog.size(); *nb_programs = (int32_t)M.progs.size();
+    if (!fits || !team_ids || !team_edge_offset || !edge_program || !edge_destination || !program_ids || !root_team) return TPGX_OK;
+    std::copy(M.teams.begin(), M.teams.end(), team_ids);
+    std::copy(M.team_off.begin(), M.team_off.end(), team_edge_offset);
+    std::copy(M.edge_prog.begin(), M.edge_prog.end(), edge_program);
+    std::copy(M.edge_dst.begin(), M.edge_dst.end(), edge_destination);
+    std::copy(M.progs.begin(), M.progs.end(), program_ids);
+    std::copy(M.roots.begin(), M.roots.end(), root_team);
+    return TPGX_OK;
 }
 
 /* One generation in one call: tpgx_set_graph_sharded + tpgx_evaluate_classification_allgather, with the host side of the

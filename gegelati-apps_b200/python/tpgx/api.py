@@ -16,7 +16,7 @@ EXPORTS = [
     "tpgx_evaluate_classification_allgather", "tpgx_evaluate_graph_classification_allgather", "tpgx_evaluate_classification_allgather_device", "tpgx_evaluate_classification_allgather_all", "tpgx_kernel_launches",
     "tpgx_set_data_sources", "tpgx_set_graph", "tpgx_set_graph_sharded", "tpgx_set_observations", "tpgx_set_observations_pinned", "tpgx_set_observations_device",
     "tpgx_evaluate_classification", "tpgx_evaluate_classification_device", "tpgx_archive_classification", "tpgx_evaluate_episodes", "tpgx_archive_episodes",
-    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs",
+    "tpgx_execute_programs", "tpgx_measure_fp64_peak", "tpgx_math_probe", "tpgx_mnist_episode_indices", "tpgx_flatten_programs", "tpgx_slice_graph",
     "tpgx_trainer_create", "tpgx_trainer_destroy", "tpgx_trainer_last_error", "tpgx_trainer_graph", "tpgx_trainer_train_generation",
     "tpgx_trainer_populate", "tpgx_trainer_decimate", "tpgx_trainer_fingerprint", "tpgx_trainer_root_results", "tpgx_trainer_best_root", "tpgx_trainer_keep_best_policy", "tpgx_train_backend_episodes", "tpgx_train_backend_classification", "tpgx_train_backend_release",
 ]
@@ -84,6 +84,30 @@ def flatten_programs(opcodes, sources, graph, nb_registers=8, nb_constants=0):
     if st != A.OK:
         raise TpgxError(st, err.value.decode())
     return dict(intron=intron, effective_lines=eff, code=code[:n.value])
+
+
+def slice_graph(graph, root_begin, root_end):
+    """tpgx_slice_graph (host only): the renumbered sub-graph roots [root_begin, root_end) reach, as the library sets up each
+    pipeline slice of evaluate_graph_allgather.  Returns dict(team_ids, program_ids, team_edge_offset, edge_program,
+    edge_destination, root_team); raises TpgxError on a malformed graph."""
+    lib = load_library()
+    I32 = C.POINTER(C.c_int32)
+    lib.tpgx_slice_graph.argtypes = [C.POINTER(A.Graph), C.c_int32, C.c_int32, I32, I32, I32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p]
+    gs, keep = graph.c_struct()
+    nt, ne, npg = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+    st = lib.tpgx_slice_graph(C.byref(gs), root_begin, root_end, C.byref(nt), C.byref(ne), C.byref(npg), None, None, None, None, None, None)
+    if st != A.OK:
+        raise TpgxError(st, "tpgx_slice_graph")
+    out = dict(team_ids=np.zeros(nt.value, dtype=np.int32), team_edge_offset=np.zeros(nt.value + 1, dtype=np.int32),
+               edge_program=np.zeros(ne.value, dtype=np.int32), edge_destination=np.zeros(ne.value, dtype=np.int32),
+               program_ids=np.zeros(npg.value, dtype=np.int32), root_team=np.zeros(root_end - root_begin, dtype=np.int32))
+    st = lib.tpgx_slice_graph(C.byref(gs), root_begin, root_end, C.byref(nt), C.byref(ne), C.byref(npg), out["team_ids"].ctypes.data,
+                              out["team_edge_offset"].ctypes.data, out["edge_program"].ctypes.data, out["edge_destination"].ctypes.data,
+                              out["program_ids"].ctypes.data, out["root_team"].ctypes.data)
+    if st != A.OK:
+        raise TpgxError(st, "tpgx_slice_graph")
+    return out
 
 
 def k1v2_handler_names():

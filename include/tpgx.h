@@ -465,6 +465,19 @@ tpgx_status tpgx_flatten_programs(const tpgx_config* cfg, int32_t nb_instruction
                                   const tpgx_source_desc* sources, const tpgx_graph* g, uint8_t* intron, int32_t* effective_lines,
                                   uint32_t* code, int64_t code_capacity, int64_t* nb_code_words, char* err, size_t err_len);
 
+/* Host only, no GPU needed: the sub-graph that roots [root_begin, root_end) of g reach, renumbered the way
+ * tpgx_evaluate_graph_classification_allgather sets up each pipeline slice — teams breadth-first from the roots in root order,
+ * programs in order of first appearance, every team's edges in the caller's order (the order decides ties in
+ * [UP] TPGExecutionEngine::evaluateTeam), roots 0 .. root_end - root_begin - 1.  Evaluating root i of the sub-graph is
+ * evaluating root root_begin + i of g.
+ * Call once with the arrays NULL: *nb_teams / *nb_edges / *nb_programs receive the sizes.  Call again with the counts set to
+ * the capacities: team_ids[nb_teams] and program_ids[nb_programs] map new ids to g's, team_edge_offset[nb_teams + 1],
+ * edge_program[nb_edges] (new program ids), edge_destination[nb_edges] (new team ids, or the action code unchanged),
+ * root_team[root_end - root_begin] (new team ids).                                                                     */
+tpgx_status tpgx_slice_graph(const tpgx_graph* g, int32_t root_begin, int32_t root_end, int32_t* nb_teams, int32_t* nb_edges, int32_t* nb_programs,
+                             int32_t* team_ids, int32_t* team_edge_offset, int32_t* edge_program, int32_t* edge_destination, int32_t* program_ids,
+                             int32_t* root_team);
+
 /* K1 v2 stream encoder on its own (host only; csrc/k1v2_encode.h — the device runs the same function when a graph is
  * planned): the entry stream of ONE program given its packed generic words (tpgx_flatten_programs' `code`), for a
  * 2-D uint8 source of `hw` elements in rows of `width` with `nwin` 3x3 window positions, 128 samples per tile.

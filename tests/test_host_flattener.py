@@ -71,3 +71,41 @@ def test_validation_errors_mirror_the_reference():
     with pytest.raises(tpgx.TpgxError) as e:
         tpgx.flatten_programs(ops, src, empty_team)
     assert e.value.status == A.ERR_GRAPH_INVALID and "no outgoing edge" in str(e.value)
+
+
+@pytest.mark.parametrize("seed,rb,re", [(3, 0, 17), (4, 40, 41), (5, 13, 60), (6, 0, 60)])
+def test_slice_graph_is_the_renumbered_reachable_subgraph(seed, rb, re):
+    """tpgx_slice_graph — what every pipeline slice of tpgx_evaluate_graph_classification_allgather is flattened, planned and
+    uploaded as — against the Python restatement TPGraph.subgraph: teams breadth-first from the roots in root order, programs
+    in order of first appearance, edge order within a team kept, shared programs and shared teams appear once."""
+    g = tpgx.synthetic_graph("mnist", roots=60, edges=4, lines=8, depth=3, share_prob=0.3, seed=seed, intron_lines=2)
+    s = tpgx.slice_graph(g, rb, re)
+    ref = g.subgraph(rb, re)
+    assert np.array_equal(s["team_edge_offset"], ref.team_edge_offset)
+    assert np.array_equal(s["edge_program"], ref.edge_program)
+    assert np.array_equal(s["edge_destination"], ref.edge_destination)
+    assert np.array_equal(s["root_team"], ref.root_team)
+    # the id maps: new -> old, injective; every edge of every kept team maps back to the caller's edge, in order
+    assert len(set(s["team_ids"].tolist())) == len(s["team_ids"]) and len(set(s["program_ids"].tolist())) == len(s["program_ids"])
+    assert np.array_equal(s["team_ids"][s["root_team"]], np.asarray(g.root_team[rb:re]))
+    for new_t, old_t in enumerate(s["team_ids"]):
+        old = slice(g.team_edge_offset[old_t], g.team_edge_offset[old_t + 1])
+        new = slice(s["team_edge_offset"][new_t], s["team_edge_offset"][new_t + 1])
+        assert np.array_equal(s["program_ids"][s["edge_program"][new]], g.edge_program[old])
+        d_old, d_new = g.edge_destination[old], s["edge_destination"][new]
+        assert np.array_equal(np.where(d_new >= 0, s["team_ids"][np.maximum(d_new, 0)], d_new), d_old)
+    # the programs' lines are the caller's (the library reads them in place through program_ids)
+    assert np.array_equal(ref.program_line_offset[1:] - ref.program_line_offset[:-1],
+                          (g.program_line_offset[1:] - g.program_line_offset[:-1])[s["program_ids"]])
+
+
+def test_slice_graph_rejects_bad_ranges_and_indices():
+    g = tpgx.synthetic_graph("mnist", roots=10, edges=3, lines=4, depth=2, seed=1)
+    for rb, re in [(-1, 3), (3, 3), (5, 11)]:
+        with pytest.raises(tpgx.TpgxError):
+            tpgx.slice_graph(g, rb, re)
+    bad = tpgx.TPGraph(lines=g.lines, program_line_offset=g.program_line_offset, constants=g.constants, team_edge_offset=g.team_edge_offset,
+                       edge_program=np.where(np.arange(g.nb_edges) == 0, g.nb_programs, g.edge_program).astype(np.int32),
+                       edge_destination=g.edge_destination, root_team=g.root_team)
+    with pytest.raises(tpgx.TpgxError):
+        tpgx.slice_graph(bad, 0, 10)
