@@ -110,7 +110,7 @@ struct tpgx_trainer {
     uint64_t deaths = 0, pre_deaths = 0;
     std::vector<size_t> pre_valid;
     std::vector<int> pre_pos;
-    std::map<int, std::vector<int>> pre_by_prog;
+    std::vector<int> pre_bp_off, pre_bp_pos, pre_bp_fill; /* valid pre-existing edges by program: CSR over program ids -> positions in pre_valid */
     bool defer_archive = false;      /* set while no program id can be reused (decimation): unref_prog only notes the deleted programs */
     std::vector<int> dead_progs;
     std::vector<int64_t> s_off;        /* settle_new_programs' scratch graph and bids, kept between generations */
@@ -294,15 +294,22 @@ struct tpgx_trainer {
                — scanning all pre-existing edges here used to be the bulk of a generation's host time. */
             if (pre_built != &pre_edges || pre_deaths != deaths) {
                 pre_built = &pre_edges; pre_deaths = deaths;
-                pre_valid.clear(); pre_pos.assign(pre_edges.size(), -1); pre_by_prog.clear();
+                /* ... and grouped by program as a CSR index (offsets per program id, positions in pre_valid): an ordered map of
+                   vectors here was 0.3 ms of a 1.2 ms populate */
+                pre_valid.clear(); pre_pos.assign(pre_edges.size(), -1);
+                pre_bp_off.assign(progs.size() + 1, 0);
                 for (size_t i = 0; i < pre_edges.size(); i++) {
                     const TEdge& pe = pre_edges[i];
                     if (progs[pe.prog].alive && (pe.dest < 0 || teams[pe.dest].alive)) {
                         pre_pos[i] = (int)pre_valid.size();
                         pre_valid.push_back(i);
-                        pre_by_prog[pe.prog].push_back((int)i);
+                        pre_bp_off[(size_t)pe.prog + 1]++;
                     }
                 }
+                for (size_t p = 0; p < progs.size(); p++) pre_bp_off[p + 1] += pre_bp_off[p];
+                pre_bp_pos.resize(pre_valid.size());
+                pre_bp_fill.assign(pre_bp_off.begin(), pre_bp_off.end() - 1);
+                for (size_t v = 0; v < pre_valid.size(); v++) pre_bp_pos[(size_t)pre_bp_fill[(size_t)pre_edges[pre_valid[v]].prog]++] = (int)v;
             }
             if (prog_mark.size() < progs.size()) prog_mark.resize(progs.size() * 2, 0u);
             stamp++;
@@ -311,8 +318,8 @@ struct tpgx_trainer {
             for (const TEdge& e : T.edges) {
                 if (prog_mark[(size_t)e.prog] == stamp) continue;
                 prog_mark[(size_t)e.prog] = stamp;
-                const auto it = pre_by_prog.find(e.prog);
-                if (it != pre_by_prog.end()) for (int i : it->second) out.push_back((size_t)pre_pos[(size_t)i]);
+                if ((size_t)e.prog + 1 < pre_bp_off.size()) /* a program made after the index has no pre-existing edge */
+                    for (int k = pre_bp_off[(size_t)e.prog]; k < pre_bp_off[(size_t)e.prog + 1]; k++) out.push_back((size_t)pre_bp_pos[(size_t)k]);
             }
             if (pre_valid.size() == out.size()) break;
             size_t r = u64(0, pre_valid.size() - out.size() - 1); /* r-th candidate = r-th valid position not taken out */
