@@ -115,7 +115,8 @@ struct tpgx_trainer {
     std::vector<int> dead_progs;
     std::vector<int64_t> s_off;        /* settle_new_programs' scratch graph and bids, kept between generations */
     std::vector<tpgx_line> s_lines;
-    std::vector<double> s_consts, s_bid, s_obs;
+    std::vector<double> s_consts, s_bid, s_obs, s_rbid, s_robs;
+    std::vector<int32_t> s_rprog;
     void purge_archive() {
         if (!dead_progs.empty()) {
             std::vector<char> dead(progs.size(), 0);
@@ -693,10 +694,15 @@ tpgx_status tpgx_trainer_train_generation(tpgx_trainer* t, const tpgx_train_back
     const int J = (int)job_root.size();
     tpgx_graph g{};
     t->build_view(&g, &skip);
-    std::vector<double> scores((size_t)std::max(1, J), 0.0), rbid((size_t)std::max(1, cap)), robs((size_t)std::max(1, cap) * (size_t)std::max(1, t->obs_len));
+    /* the archive buffers (archive_size x observation length doubles: 3 MB for the mnist app) are the trainer's and keep their pages */
+    std::vector<double> scores((size_t)std::max(1, J), 0.0);
+    std::vector<double>&rbid = t->s_rbid, &robs = t->s_robs;
+    std::vector<int32_t>& rprog = t->s_rprog;
+    rbid.resize((size_t)std::max(1, cap));
+    robs.resize((size_t)std::max(1, cap) * (size_t)std::max(1, t->obs_len));
+    rprog.resize((size_t)std::max(1, cap));
     std::vector<double> cscore((size_t)std::max(1, J * C));
     std::vector<uint64_t> ccount((size_t)std::max(1, J * C));
-    std::vector<int32_t> rprog((size_t)std::max(1, cap));
     int32_t nrec = 0;
     if (J > 0) {
         st = be->evaluate(be->user, &g, generation, 0 /* TRAINING */, aseed.data(), t->P.archiving_probability, cap, scores.data(), C,
